@@ -1,0 +1,188 @@
+/*
+ * pm.h -- C ABI of libpm: B200 (sm_100a) descriptor matching + epipolar geometry.
+ *
+ * Drop-in boundary for the hot path of /root/reference/Points Matching/main.cpp.
+ * The reference has no plugin/FFI layer: the boundary is the OpenCV C++ API subset
+ * that main.cpp calls (and that "x64/Debug/Points Matching.exe" imports).  Each entry
+ * point cites the call it replaces.  Plain C: no exceptions or STL cross the
+ * boundary, outputs are caller-owned buffers sized by the caller, every function
+ * returns a pm_status.  One pm_ctx per host thread (it owns the device, a stream,
+ * a workspace arena and the TMA descriptors); a ctx is not thread-safe.
+ *
+ * There is NO CPU fallback: without a CUDA device pm_create fails with
+ * PM_NO_DEVICE and nothing else can be called.
+ *
+ * Two families:
+ *   host-buffer calls   (pm_knn2_*, pm_match_*, pm_find_fundamental ...):
+ *       synchronous, take HOST pointers, copy in/out -- what main.cpp would call.
+ *   device-resident calls (pm_*_dev): take DEVICE pointers, enqueue on the ctx
+ *       stream and return without synchronising -- for pipelines that keep data
+ *       in HBM (bench `value`, batched config 5, multi-GPU shards).
+ */
+#ifndef PM_H
+#define PM_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM_VERSION 100
+
+typedef struct pm_ctx pm_ctx;
+
+/* Layout-identical to cv::DMatch (main.cpp:45 vector<DMatch>; fields used at
+ * main.cpp:54,65,76-78,110-113).  16 bytes.  distance is L2 (not squared) for
+ * float descriptors and an integer-valued float for Hamming; imgIdx is 0.
+ * An absent neighbour (k > number of train rows) has trainIdx = -1, distance = FLT_MAX. */
+typedef struct pm_dmatch {
+    int32_t queryIdx;
+    int32_t trainIdx;
+    int32_t imgIdx;
+    float   distance;
+} pm_dmatch;
+
+typedef enum pm_status {
+    PM_OK        = 0,
+    PM_EMPTY     = 1,   /* OpenCV returns an empty Mat (e.g. N < 7): outputs untouched */
+    PM_BAD_ARG   = -1,  /* OpenCV would raise cv::Exception -215 (type/dim mismatch)   */
+    PM_CUDA_ERR  = -2,
+    PM_NCCL_ERR  = -3,
+    PM_NO_DEVICE = -4
+} pm_status;
+
+/* ---- context ---------------------------------------------------------------- */
+int  pm_version(void);
+int  pm_create(pm_ctx **ctx, int device);
+int  pm_destroy(pm_ctx *ctx);
+/* Run on an existing cudaStream_t (e.g. torch's current stream); NULL = ctx-owned stream. */
+int  pm_set_stream(pm_ctx *ctx, void *cuda_stream);
+int  pm_sync(pm_ctx *ctx);
+const char *pm_last_error(pm_ctx *ctx);
+/* Number of libpm kernels launched by this ctx since creation (bench "gpu_launches"). */
+uint64_t pm_launch_count(pm_ctx *ctx);
+/* Counters of the last L2 call: [0] exact-integer mode (1/0), [1] rows sent to the
+ * exact fallback, [2] MMA k-blocks per tile, [3] segments per row tile. */
+int  pm_l2_stats(pm_ctx *ctx, int32_t out[4]);
+
+/* ---- descriptor matching ----------------------------------------------------
+ * Replaces BruteForceMatcher<L2<float>> matcher; matcher.match(d1, d2, matches)
+ * (main.cpp:43-46; 4.x spelling BFMatcher(NORM_L2).knnMatch(q, t, k=2)).
+ * out is [nq][2], sorted ascending per row, ties -> lowest trainIdx; out[i][0] is
+ * exactly what match() (k=1) returns.  q_index_base is added to queryIdx (row shards). */
+int pm_knn2_l2_f32(pm_ctx *ctx, const float *q, int nq, const float *t, int nt, int dim,
+                   pm_dmatch *out);
+/* SIFT stored as bytes (0..255): same result as the f32 call on the widened data. */
+int pm_knn2_l2_u8(pm_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt, int dim,
+                  pm_dmatch *out);
+/* BFMatcher(NORM_HAMMING).knnMatch(q, t, k=2) for `bytes`-wide binary rows (ORB: 32). */
+int pm_knn2_hamming(pm_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt, int bytes,
+                    pm_dmatch *out);
+
+int pm_knn2_l2_f32_dev(pm_ctx *ctx, const float *dq, int nq, const float *dt, int nt, int dim,
+                       int q_index_base, pm_dmatch *dout);
+int pm_knn2_l2_u8_dev(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, int dim,
+                      int q_index_base, pm_dmatch *dout);
+int pm_knn2_hamming_dev(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt,
+                        int bytes, int q_index_base, pm_dmatch *dout);
+
+/* ---- good-match filters (main.cpp:49-69) -------------------------------------
+ * Lowe ratio test over a [nq][2] kNN result: keep knn[i][0] iff both neighbours
+ * exist and d0 < ratio*d1.  Output is compacted in queryIdx order. */
+int pm_ratio_filter(pm_ctx *ctx, const pm_dmatch *knn, int nq, float ratio,
+                    pm_dmatch *out, int *n_out);
+int pm_ratio_filter_dev(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio,
+                        pm_dmatch *dout, int32_t *dn_out);
+/* The reference's literal rule (main.cpp:49-69): min starts at 1, max at 0, keep
+ * distance < min + (max-min)/2.  m is a k=1 match list (stride_elems 1) or the
+ * first column of a kNN-2 result (stride_elems 2). */
+int pm_minmax_filter(pm_ctx *ctx, const pm_dmatch *m, int n, int stride_elems,
+                     pm_dmatch *out, int *n_out, double *min_out, double *max_out);
+int pm_minmax_filter_dev(pm_ctx *ctx, const pm_dmatch *dm, int n, int stride_elems,
+                         pm_dmatch *dout, int32_t *dn_out, double *dminmax /* [2] */);
+/* BFMatcher(norm, crossCheck=true).match(q, t): (i, j) survives iff j is i's nearest
+ * train row and i is j's nearest query row, both with lowest-index ties. */
+int pm_match_cross_l2_f32(pm_ctx *ctx, const float *q, int nq, const float *t, int nt, int dim,
+                          pm_dmatch *out, int *n_out);
+int pm_match_cross_hamming(pm_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt,
+                           int bytes, pm_dmatch *out, int *n_out);
+/* Building blocks of the sharded cross-check: column minima over a query
+ * shard as packed u64 (float_bits(dist) << 32 | queryIdx) -- all-reduce(min) them
+ * across ranks -- then the local filter bwd[fwd[i]] == i. */
+int pm_col_best_hamming_dev(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt,
+                            int bytes, int q_index_base, uint64_t *dcol_best /* [nt] */);
+int pm_col_best_l2_f32_dev(pm_ctx *ctx, const float *dq, int nq, const float *dt, int nt, int dim,
+                           int q_index_base, uint64_t *dcol_best /* [nt] */);
+int pm_cross_check_dev(pm_ctx *ctx, const pm_dmatch *dknn, int nq, int knn_stride_elems,
+                       const uint64_t *dcol_best, int nt, pm_dmatch *dout, int32_t *dn_out);
+
+/* ---- KeyPoint::convert(keypoints, points, indices) (main.cpp:89-91) ---------- */
+int pm_gather_points(pm_ctx *ctx, const float *kp_xy /* [nkp][2] */, int nkp,
+                     const int32_t *idx, int n, float *out /* [n][2] */);
+/* Device hand-off: matches -> the two correspondence lists, no host trip. */
+int pm_gather_matches_dev(pm_ctx *ctx, const pm_dmatch *dmatches, const int32_t *dn_matches,
+                          int max_matches, const float *dkp1, int nkp1, const float *dkp2, int nkp2,
+                          float *dp1, float *dp2);
+
+/* ---- cv::findFundamentalMat (main.cpp:95-98) --------------------------------- */
+enum { PM_METRIC_SAMPSON = 0,      /* r^2 / (a^2+b^2+a'^2+b'^2)      (north_star)          */
+       PM_METRIC_SYMEPI  = 1 };    /* max(d(x2,Fx1)^2, d(x1,F^Tx2)^2) (OpenCV computeError) */
+
+typedef struct pm_ransac_params {
+    int32_t sample_size;   /* 8: normalised 8-point; 7: 7-point (up to 3 models per sample) */
+    int32_t metric;        /* PM_METRIC_*                                                     */
+    float   threshold;     /* pixels; inlier <=> err <= threshold^2                           */
+    int32_t n_hyp;         /* hypotheses (minimal samples) to evaluate                        */
+    int32_t refit;         /* !=0: N-point normalised 8-point on the winner's inliers         */
+    const int32_t *sample_idx; /* [n_hyp][sample_size] HOST (host call) / DEVICE (_dev call)  */
+                           /* index sets, distinct within a row; NULL: generated from `seed`  */
+    uint64_t seed;
+    int32_t hyp_id_base;   /* global id of this shard's hypothesis 0 (multi-GPU)              */
+    int32_t reserved;
+} pm_ransac_params;
+
+/* RANSAC over minimal samples.  Winner = max inlier count, ties -> lowest model id
+ * (id = hyp for 8-point, 3*hyp+k for 7-point).  F is row-major 3x3 f64 with F[8]=1;
+ * mask[n] in {0,1} is the winner's inlier set (before the refit); PM_EMPTY when n <
+ * sample_size or no hypothesis produced a model (F, mask untouched). */
+int pm_find_fundamental(pm_ctx *ctx, const float *p1 /* [n][2] */, const float *p2, int n,
+                        const pm_ransac_params *prm,
+                        double F[9], uint8_t *mask, int *n_inliers);
+
+/* Deterministic minimal-sample index sets ([n_hyp][m], distinct within a row); the
+ * same (n_points, n_hyp, m, seed) gives the same sets on every rank. */
+int pm_make_sample_sets(int n_points, int n_hyp, int m, uint64_t seed, int32_t *out);
+
+/* Staged device API (what pm_find_fundamental runs; exposed for shards and tests).
+ *  solve : dF32 [n_hyp][models][12] f32 (9 used; NaN = no model), models = 1 or 3
+ *  score : dcounts [n_hyp*models] inlier count per model, FP32 arithmetic as in DESIGN.md
+ *  best  : *dkey = max over models of (count << 32 | (0xFFFFFFFF - model_id)), 0 if none
+ *  finish: winner re-scored -> dmask, dn_inliers; optional refit -> dF (f64[9]) */
+int pm_ransac_solve_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n,
+                        const int32_t *dsample_idx, int n_hyp, int sample_size, float *dF32);
+int pm_ransac_score_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n,
+                        const float *dF32, int n_models, float threshold, int metric,
+                        int32_t *dcounts);
+int pm_ransac_best_dev(pm_ctx *ctx, const int32_t *dcounts, int n_models, int model_id_base,
+                       uint64_t *dkey);
+int pm_ransac_finish_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n,
+                         const float *dF32_winner /* [12] */, float threshold, int metric, int refit,
+                         double *dF /* [9] */, uint8_t *dmask, int32_t *dn_inliers);
+
+/* N-point normalised 8-point (findFundamentalMat(..., FM_8POINT)); mask all ones. */
+int pm_fundamental_8point(pm_ctx *ctx, const float *p1, const float *p2, int n, double F[9]);
+
+/* ---- diagnostics (main.cpp:103-123, 127-132) --------------------------------- */
+/* cv::computeCorrespondEpilines: l = F x (which_image 1) or F^T x (2), a^2+b^2 = 1. */
+int pm_epilines(pm_ctx *ctx, const float *pts, int n, int which_image, const double F[9],
+                float *lines /* [n][3] */);
+/* Per-correspondence residuals in the correct convention x2^T F x1 (main.cpp:110-117
+ * evaluates x1^T F x2): out[i] = Sampson or sym-epi distance (f32). */
+int pm_residuals(pm_ctx *ctx, const float *p1, const float *p2, int n, const double F[9],
+                 int metric, float *out, double *mean_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PM_H */

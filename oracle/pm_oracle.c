@@ -57,12 +57,21 @@ void orc_knn2_l2_f32(const float *q, int nq, const float *t, int nt, int dim,
 
 float orc_l2sq_f32_rerank(const float *a, const float *b, int dim)
 {
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k = 0; k < dim; ++k) {
-        float d = a[k] - b[k];
-        s[k & 3] = fmaf(d, d, s[k & 3]);
+    /* The product's "re-rank order" (DESIGN.md): 32 lanes, lane l owns k = 128c + 4l + e
+     * (c ascending, e = 0..3) as one fmaf chain, then an xor-butterfly sum 16,8,4,2,1. */
+    float p[32], q[32];
+    for (int l = 0; l < 32; ++l) p[l] = 0.f;
+    for (int c = 0; c < dim; c += 128)
+        for (int l = 0; l < 32; ++l)
+            for (int e = 0; e < 4; ++e) {
+                int k = c + 4 * l + e;
+                if (k < dim) { float d = a[k] - b[k]; p[l] = fmaf(d, d, p[l]); }
+            }
+    for (int off = 16; off > 0; off >>= 1) {
+        for (int l = 0; l < 32; ++l) q[l] = p[l] + p[l ^ off];
+        memcpy(p, q, sizeof(p));
     }
-    return (s[0] + s[1]) + (s[2] + s[3]);
+    return p[0];
 }
 
 static inline int popc8(const uint8_t *a, const uint8_t *b, int bytes)

@@ -44,7 +44,7 @@ enum { ORC_METRIC_SAMPSON = 0, ORC_METRIC_SYMEPI = 1 };
 void orc_knn2_l2_f32(const float *q, int nq, const float *t, int nt, int dim,
                      orc_dmatch *out /* [nq][2] */, int nthreads);
 /* Same arithmetic as the product's FP32 re-rank (fixed summation order, see
- * DESIGN.md "re-rank order"): 4 partial sums over k%4, combined (s0+s1)+(s2+s3). */
+ * DESIGN.md "re-rank order"): 32 lane-partials (fmaf chains) + xor-butterfly sum. */
 float orc_l2sq_f32_rerank(const float *a, const float *b, int dim);
 /* Hamming kNN-2 over `bytes`-wide rows; distance is an integer-valued float. */
 void orc_knn2_hamming(const uint8_t *q, int nq, const uint8_t *t, int nt, int bytes,

@@ -1,0 +1,67 @@
+"""ctypes loader for libpm.so (the C ABI of include/pm.h).
+
+There is no Python or CPU fallback: if the library is missing or no B200 is visible the
+import / context creation fails loudly.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libpm.so")
+
+PM_OK, PM_EMPTY, PM_BAD_ARG, PM_CUDA_ERR, PM_NCCL_ERR, PM_NO_DEVICE = 0, 1, -1, -2, -3, -4
+DMATCH = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+assert DMATCH.itemsize == 16
+
+
+class RansacParams(C.Structure):
+    _fields_ = [("sample_size", C.c_int32), ("metric", C.c_int32), ("threshold", C.c_float),
+                ("n_hyp", C.c_int32), ("refit", C.c_int32), ("sample_idx", C.c_void_p),
+                ("seed", C.c_uint64), ("hyp_id_base", C.c_int32), ("reserved", C.c_int32)]
+
+
+# every symbol include/pm.h declares (tests/test_abi.py checks the header against this list)
+EXPORTS = [
+    "pm_version", "pm_create", "pm_destroy", "pm_set_stream", "pm_sync", "pm_last_error",
+    "pm_launch_count", "pm_l2_stats",
+    "pm_knn2_l2_f32", "pm_knn2_l2_u8", "pm_knn2_hamming",
+    "pm_knn2_l2_f32_dev", "pm_knn2_l2_u8_dev", "pm_knn2_hamming_dev",
+    "pm_ratio_filter", "pm_ratio_filter_dev", "pm_minmax_filter", "pm_minmax_filter_dev",
+    "pm_match_cross_l2_f32", "pm_match_cross_hamming",
+    "pm_col_best_hamming_dev", "pm_col_best_l2_f32_dev", "pm_cross_check_dev",
+    "pm_gather_points", "pm_gather_matches_dev",
+    "pm_find_fundamental", "pm_make_sample_sets",
+    "pm_ransac_solve_dev", "pm_ransac_score_dev", "pm_ransac_best_dev", "pm_ransac_finish_dev",
+    "pm_fundamental_8point", "pm_epilines", "pm_residuals",
+]
+
+
+def build(force=False):
+    """Compile libpm.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    src_dir = os.path.join(_HERE, "csrc")
+    if force:
+        subprocess.check_call(["make", "-C", src_dir, "clean", "-s"])
+    subprocess.check_call(["make", "-C", src_dir, "-s", "-j8"])
+    return SO_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(
+                f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(points_matching_b200 has no CPU fallback)")
+        L = C.CDLL(SO_PATH)
+        L.pm_last_error.restype = C.c_char_p
+        L.pm_launch_count.restype = C.c_uint64
+        for name in EXPORTS:
+            getattr(L, name)
+        _lib = L
+    return _lib

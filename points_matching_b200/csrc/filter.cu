@@ -1,0 +1,231 @@
+// filter.cu -- K5: good-match filters with order-preserving stream compaction, and the
+// match -> correspondence gather.
+//
+// Replaces the host loops at /root/reference/Points Matching/main.cpp:49-69 (min/max
+// midpoint rule), the ratio test / cross-check the north_star names for the same step,
+// and main.cpp:71-79 + 89-91 (index lists + KeyPoint::convert).
+//
+// All of it is streaming, HBM-bound work over <= a few MB: one coalesced pass for the
+// predicate + block counts, one tiny scan, one scatter pass (output stays in queryIdx
+// order, exactly like the reference's push_back loop).
+#include "pm_internal.h"
+
+namespace {
+
+constexpr int FB = 1024;   // rows per compaction block
+
+struct RatioPred {
+    const pm_dmatch *knn; float ratio;
+    __device__ bool operator()(int i, pm_dmatch &m) const {
+        const pm_dmatch a = knn[(size_t)i * 2], b = knn[(size_t)i * 2 + 1];
+        m = a;
+        return a.trainIdx >= 0 && b.trainIdx >= 0 && a.distance < ratio * b.distance;
+    }
+};
+struct CrossPred {
+    const pm_dmatch *knn; int stride; const unsigned long long *col_best; int nt;
+    __device__ bool operator()(int i, pm_dmatch &m) const {
+        m = knn[(size_t)i * stride];
+        const int j = m.trainIdx;
+        if (j < 0 || j >= nt) return false;
+        return (unsigned)(col_best[j] & 0xFFFFFFFFull) == (unsigned)m.queryIdx;
+    }
+};
+struct MinMaxPred {
+    const pm_dmatch *m_in; int stride; const unsigned *mm_bits;
+    __device__ bool operator()(int i, pm_dmatch &m) const {
+        m = m_in[(size_t)i * stride];
+        const double mn = (double)__uint_as_float(mm_bits[0]), mx = (double)__uint_as_float(mm_bits[1]);
+        return (double)m.distance < mn + (mx - mn) / 2;      // main.cpp:65
+    }
+};
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total)
+{
+    __shared__ int warp_sums[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_sums[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+        warp_sums[lane] = s;
+    }
+    __syncthreads();
+    const int base = w > 0 ? warp_sums[w - 1] : 0;
+    *total = warp_sums[(blockDim.x >> 5) - 1];
+    __syncthreads();
+    return base + x - v;
+}
+
+template <class Pred>
+__global__ void __launch_bounds__(FB) compact_count_kernel(Pred pred, int n, int32_t *block_counts)
+{
+    const int i = blockIdx.x * FB + threadIdx.x;
+    pm_dmatch m;
+    const int f = i < n ? (int)pred(i, m) : 0;
+    const int c = __syncthreads_count(f);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+}
+
+// single block: exclusive scan of block counts in place, total -> *n_out
+__global__ void __launch_bounds__(FB) compact_scan_kernel(int32_t *block_counts, int nblocks, int32_t *n_out)
+{
+    int carry = 0;
+    for (int b0 = 0; b0 < nblocks; b0 += FB) {
+        const int i = b0 + threadIdx.x;
+        const int v = i < nblocks ? block_counts[i] : 0;
+        int total;
+        const int ex = block_exclusive_scan(v, &total);
+        if (i < nblocks) block_counts[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *n_out = carry;
+}
+
+template <class Pred>
+__global__ void __launch_bounds__(FB) compact_scatter_kernel(Pred pred, int n, const int32_t *block_offsets,
+                                                             pm_dmatch *out)
+{
+    const int i = blockIdx.x * FB + threadIdx.x;
+    pm_dmatch m;
+    const int f = i < n ? (int)pred(i, m) : 0;
+    int total;
+    const int ex = block_exclusive_scan(f, &total);
+    if (f) out[block_offsets[blockIdx.x] + ex] = m;
+}
+
+// small inputs: one CTA does predicate + scan + scatter in a single launch
+template <class Pred>
+__global__ void __launch_bounds__(FB) compact_single_kernel(Pred pred, int n, pm_dmatch *out, int32_t *n_out)
+{
+    int carry = 0;
+    for (int b0 = 0; b0 < n; b0 += FB) {
+        const int i = b0 + threadIdx.x;
+        pm_dmatch m;
+        const int f = i < n ? (int)pred(i, m) : 0;
+        int total;
+        const int ex = block_exclusive_scan(f, &total);
+        if (f) out[carry + ex] = m;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *n_out = carry;
+}
+
+template <class Pred>
+int run_compact(pm_ctx *ctx, Pred pred, int n, pm_dmatch *dout, int32_t *dn_out)
+{
+    if (n <= 0) {
+        PM_CUDA(ctx, cudaMemsetAsync(dn_out, 0, sizeof(int32_t), ctx->stream));
+        return PM_OK;
+    }
+    if (n <= 16 * FB) {
+        compact_single_kernel<<<1, FB, 0, ctx->stream>>>(pred, n, dout, dn_out);
+        PM_CHECK_LAUNCH(ctx);
+        return PM_OK;
+    }
+    const int nb = pm_cdiv(n, FB);
+    PM_WS(ctx, counts, int32_t *, WS_COUNT, (size_t)nb * sizeof(int32_t));
+    compact_count_kernel<<<nb, FB, 0, ctx->stream>>>(pred, n, counts);
+    PM_CHECK_LAUNCH(ctx);
+    compact_scan_kernel<<<1, FB, 0, ctx->stream>>>(counts, nb, dn_out);
+    PM_CHECK_LAUNCH(ctx);
+    compact_scatter_kernel<<<nb, FB, 0, ctx->stream>>>(pred, n, counts, dout);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}
+
+// main.cpp:49-56: minMatch = 1, maxMatch = 0, then a running min/max of `distance`.
+// Distances are non-negative floats, so their bit patterns order like unsigned ints.
+__global__ void minmax_init_kernel(unsigned *mm) { mm[0] = __float_as_uint(1.0f); mm[1] = __float_as_uint(0.0f); }
+__global__ void minmax_reduce_kernel(const pm_dmatch *m, int n, int stride, unsigned *mm)
+{
+    unsigned lo = __float_as_uint(1.0f), hi = 0u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned b = __float_as_uint(m[(size_t)i * stride].distance);
+        lo = min(lo, b); hi = max(hi, b);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&mm[0], lo); atomicMax(&mm[1], hi); }
+}
+__global__ void minmax_export_kernel(const unsigned *mm, double *out)
+{
+    out[0] = (double)__uint_as_float(mm[0]);
+    out[1] = (double)__uint_as_float(mm[1]);
+}
+
+__global__ void gather_points_kernel(const float2 *__restrict__ kp, int nkp, const int32_t *__restrict__ idx,
+                                     int n, float2 *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int k = idx[i];
+    out[i] = (k >= 0 && k < nkp) ? kp[k] : make_float2(0.f, 0.f);
+}
+
+__global__ void gather_matches_kernel(const pm_dmatch *__restrict__ m, const int32_t *__restrict__ n_ptr,
+                                      int max_matches, const float2 *__restrict__ kp1, int nkp1,
+                                      const float2 *__restrict__ kp2, int nkp2,
+                                      float2 *__restrict__ p1, float2 *__restrict__ p2)
+{
+    const int n = min(*n_ptr, max_matches);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const pm_dmatch d = m[i];
+    p1[i] = (d.queryIdx >= 0 && d.queryIdx < nkp1) ? kp1[d.queryIdx] : make_float2(0.f, 0.f);
+    p2[i] = (d.trainIdx >= 0 && d.trainIdx < nkp2) ? kp2[d.trainIdx] : make_float2(0.f, 0.f);
+}
+
+}  // namespace
+
+int pmk_ratio_filter(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout, int32_t *dn_out)
+{
+    return run_compact(ctx, RatioPred{dknn, ratio}, nq, dout, dn_out);
+}
+
+int pmk_cross_check(pm_ctx *ctx, const pm_dmatch *dknn, int nq, int stride, const uint64_t *dcol_best, int nt,
+                    pm_dmatch *dout, int32_t *dn_out)
+{
+    return run_compact(ctx, CrossPred{dknn, stride, (const unsigned long long *)dcol_best, nt}, nq, dout, dn_out);
+}
+
+int pmk_minmax_filter(pm_ctx *ctx, const pm_dmatch *dm, int n, int stride, pm_dmatch *dout, int32_t *dn_out,
+                      double *dminmax)
+{
+    PM_WS(ctx, mm, unsigned *, WS_MISC, 64);
+    minmax_init_kernel<<<1, 1, 0, ctx->stream>>>(mm);
+    PM_CHECK_LAUNCH(ctx);
+    if (n > 0) {
+        const int blocks = min(pm_cdiv(n, 256), 4 * ctx->num_sms);
+        minmax_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(dm, n, stride, mm);
+        PM_CHECK_LAUNCH(ctx);
+    }
+    if (dminmax) {
+        minmax_export_kernel<<<1, 1, 0, ctx->stream>>>(mm, dminmax);
+        PM_CHECK_LAUNCH(ctx);
+    }
+    return run_compact(ctx, MinMaxPred{dm, stride, mm}, n, dout, dn_out);
+}
+
+int pmk_gather_points(pm_ctx *ctx, const float *dkp, int nkp, const int32_t *didx, int n, float *dout)
+{
+    if (n <= 0) return PM_OK;
+    gather_points_kernel<<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>((const float2 *)dkp, nkp, didx, n, (float2 *)dout);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}
+
+int pmk_gather_matches(pm_ctx *ctx, const pm_dmatch *dm, const int32_t *dn, int max_matches, const float *dkp1,
+                       int nkp1, const float *dkp2, int nkp2, float *dp1, float *dp2)
+{
+    if (max_matches <= 0) return PM_OK;
+    gather_matches_kernel<<<pm_cdiv(max_matches, 256), 256, 0, ctx->stream>>>(
+        dm, dn, max_matches, (const float2 *)dkp1, nkp1, (const float2 *)dkp2, nkp2, (float2 *)dp1, (float2 *)dp2);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}

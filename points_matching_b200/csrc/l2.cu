@@ -1,0 +1,341 @@
+// l2.cu -- float L2 kNN-2: K1 (pack + squared-norm pre-pass), K3 (merge, FP32 re-rank,
+// certification), the exact FP32 kernel used for uncertified rows / wide descriptors,
+// and the orchestration around the tensor-core kernel K2 (l2_tc.cu).
+//
+// Replaces BruteForceMatcher<L2<float>>::match / knnMatch (k = 2), the matcher named at
+// /root/reference/Points Matching/main.cpp:43 and called at main.cpp:46; results follow
+// OpenCV's batchDistance semantics: distance = sqrt(sum (a-b)^2) in f32, rows sorted
+// ascending, ties -> lowest trainIdx.
+//
+// "re-rank order" (DESIGN.md): the FP32 squared distance is defined as
+//   lane l (0..31): p_l = fma-chain over k = 128c + 4l + e (c ascending, e = 0..3) of (a_k-b_k)^2
+//   then the xor-butterfly p += shfl_xor(p, 16|8|4|2|1)
+// which the oracle restates bit for bit (orc_l2sq_f32_rerank).
+#include <cuda_bf16.h>
+#include "pm_internal.h"
+#include "l2_common.h"
+
+namespace {
+
+constexpr float L2_EPS_REL = 6.2e-5f;   // bound on |approx - exact| / (||a|| ||b||max), split mode
+#define L2_INF __int_as_float(0x7f800000)
+
+__device__ __forceinline__ float warp_sum_butterfly(float p)
+{
+    p += __shfl_xor_sync(0xffffffffu, p, 16);
+    p += __shfl_xor_sync(0xffffffffu, p, 8);
+    p += __shfl_xor_sync(0xffffffffu, p, 4);
+    p += __shfl_xor_sync(0xffffffffu, p, 2);
+    p += __shfl_xor_sync(0xffffffffu, p, 1);
+    return p;
+}
+
+template <typename T> __device__ __forceinline__ float load_elem(const T *p, size_t i) { return (float)p[i]; }
+
+// ---------------------------------------------------------------------------------
+// K1: one warp per row.  Writes [hi|lo] bf16 (train rows pre-scaled by -2), ||row||^2,
+// the exact-integer flag, max train norm, and (query side) the +inf candidate init.
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+l2_pack_kernel(const T *__restrict__ src, int n, int dim, int n_pad, int is_train,
+               __nv_bfloat16 *__restrict__ pack, float *__restrict__ norm, L2Flags *flags,
+               L2Cand *__restrict__ part, int part_per_row)
+{
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_pad) return;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row < n) {
+        const T *p = src + (size_t)row * dim;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (4 * lane + e < dim) x[e] = load_elem(p, 4 * lane + e);
+    }
+    float s = 0.f;
+    bool integral = true;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        s = fmaf(x[e], x[e], s);
+        integral = integral && (x[e] == rintf(x[e])) && x[e] >= 0.f && x[e] <= 255.f;
+    }
+    s = warp_sum_butterfly(s);
+    const float scale = is_train ? -2.f : 1.f;
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float v = x[e] * scale;
+        hi[e] = __float2bfloat16_rn(v);
+        lo[e] = __float2bfloat16_rn(v - __bfloat162float(hi[e]));
+    }
+    __nv_bfloat16 *dst = pack + (size_t)row * L2_PACK_COLS;
+    *reinterpret_cast<uint2 *>(dst + 4 * lane) = *reinterpret_cast<uint2 *>(hi);
+    *reinterpret_cast<uint2 *>(dst + L2_KDIM + 4 * lane) = *reinterpret_cast<uint2 *>(lo);
+    if (lane == 0) norm[row] = row < n ? s : (is_train ? L2_INF : 0.f);
+    if (!__all_sync(0xffffffffu, integral) && lane == 0) flags->nonexact = 1;
+    if (is_train && row < n && lane == 0) atomicMax(&flags->max_tnorm_bits, __float_as_uint(s));
+    if (part)
+        for (int k = lane; k < part_per_row; k += 32) part[(size_t)row * part_per_row + k] = L2Cand{L2_INF, -1};
+}
+
+// order-preserving float -> uint map (handles negatives; t = ||b||^2 - 2ab can be < 0)
+__device__ __forceinline__ unsigned f2ord(float f)
+{
+    const unsigned b = __float_as_uint(f);
+    return b ^ ((unsigned)((int)b >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u)
+{
+    const unsigned b = (u & 0x80000000u) ? (u ^ 0x80000000u) : ~u;
+    return __uint_as_float(b);
+}
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long k)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long y = __shfl_xor_sync(0xffffffffu, k, o);
+        k = y < k ? y : k;
+    }
+    return k;
+}
+
+// exact FP32 squared distance between the query chunk held in registers (dim <= 128) and a train row
+__device__ __forceinline__ float warp_l2sq_regs(const float (&a)[4], const float *__restrict__ b, int dim, int lane)
+{
+    float p = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        if (4 * lane + e < dim) { const float d = a[e] - __ldg(b + 4 * lane + e); p = fmaf(d, d, p); }
+    return warp_sum_butterfly(p);
+}
+
+// ---------------------------------------------------------------------------------
+// K3: one warp per query row.  Merges the per-segment candidates, re-ranks in FP32
+// (split mode), certifies the top-2 or queues the row for the exact kernel.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__restrict__ qnorm,
+                 const float *__restrict__ q, const float *__restrict__ t, int nq, int dim,
+                 L2Flags *flags, int *__restrict__ flagged, int q_index_base, pm_dmatch *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= nq) return;
+    unsigned long long key = ~0ull;
+    if (lane < ncand) {
+        const L2Cand c = part[(size_t)i * ncand + lane];
+        if (c.idx >= 0) key = ((unsigned long long)f2ord(c.d) << 32) | (unsigned)c.idx;
+    }
+    unsigned long long k[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        k[r] = warp_min_u64(key);
+        if (key == k[r]) key = ~0ull;      // keys are unique (distinct train indices)
+    }
+    const float na = qnorm[i];
+    float d2[3]; int idx[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        idx[r] = k[r] == ~0ull ? -1 : (int)(k[r] & 0xFFFFFFFFu);
+        d2[r] = k[r] == ~0ull ? L2_INF : ord2f((unsigned)(k[r] >> 32)) + na;
+    }
+    const bool split = flags->nonexact != 0;
+    bool certified = true;
+    if (split) {
+        const float bound = d2[2];        // approx d^2 of the third candidate: every non-candidate is >= this
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (4 * lane + e < dim) a[e] = __ldg(q + (size_t)i * dim + 4 * lane + e);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            if (idx[r] >= 0) d2[r] = warp_l2sq_regs(a, t + (size_t)idx[r] * dim, dim, lane);
+        // sort the three by (exact d^2, index)
+#define L2_CSWAP(x, y)                                                                     \
+        if (d2[y] < d2[x] || (d2[y] == d2[x] && (unsigned)idx[y] < (unsigned)idx[x])) {    \
+            float td = d2[x]; d2[x] = d2[y]; d2[y] = td; int ti = idx[x]; idx[x] = idx[y]; idx[y] = ti; }
+        L2_CSWAP(0, 1) L2_CSWAP(1, 2) L2_CSWAP(0, 1)
+#undef L2_CSWAP
+        if (k[2] != ~0ull) {
+            const float eps = L2_EPS_REL * sqrtf(na * __uint_as_float(flags->max_tnorm_bits));
+            certified = d2[1] < bound - eps;
+        }
+    }
+    if (lane == 0) {
+        pm_dmatch r0, r1;
+        r0.queryIdx = r1.queryIdx = i + q_index_base;
+        r0.imgIdx = r1.imgIdx = 0;
+        r0.trainIdx = idx[0]; r0.distance = idx[0] < 0 ? 3.402823466e+38f : sqrtf(fmaxf(d2[0], 0.f));
+        r1.trainIdx = idx[1]; r1.distance = idx[1] < 0 ? 3.402823466e+38f : sqrtf(fmaxf(d2[1], 0.f));
+        out[(size_t)i * 2] = r0;
+        out[(size_t)i * 2 + 1] = r1;
+        if (!certified) flagged[atomicAdd(&flags->n_flagged, 1)] = i;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Exact FP32 kNN-2 for a list of rows (or all rows): one CTA per query row, warps
+// stride over the train rows, lexicographic (d^2, index) top-2.
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+l2_exact_kernel(const T *__restrict__ q, const T *__restrict__ t, int nq, int nt, int dim,
+                const int *__restrict__ row_list, const int *__restrict__ row_count,
+                int q_index_base, pm_dmatch *__restrict__ out)
+{
+    extern __shared__ float qs[];                 // [dim_pad] query row, then merge scratch
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int dim_pad = (dim + 127) / 128 * 128;
+    float *md = qs + dim_pad;                     // [nwarps][2]
+    int *mi = reinterpret_cast<int *>(md + 2 * nwarps);
+    const int nrows = row_list ? *row_count : nq;
+    for (int r = blockIdx.x; r < nrows; r += gridDim.x) {
+        const int i = row_list ? row_list[r] : r;
+        __syncthreads();
+        for (int k = threadIdx.x; k < dim_pad; k += blockDim.x) qs[k] = k < dim ? load_elem(q, (size_t)i * dim + k) : 0.f;
+        __syncthreads();
+        float b0 = L2_INF, b1 = L2_INF; int i0 = -1, i1 = -1;
+        for (int j = warp; j < nt; j += nwarps) {
+            const T *b = t + (size_t)j * dim;
+            float p = 0.f;
+            for (int c = 0; c < dim_pad; c += 128) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int kk = c + 4 * lane + e;
+                    if (kk < dim) { const float d = qs[kk] - load_elem(b, kk); p = fmaf(d, d, p); }
+                }
+            }
+            p = warp_sum_butterfly(p);
+            if (p < b0) { b1 = b0; i1 = i0; b0 = p; i0 = j; }      // j ascending within a warp
+            else if (p < b1) { b1 = p; i1 = j; }
+        }
+        if (lane == 0) { md[2 * warp] = b0; md[2 * warp + 1] = b1; mi[2 * warp] = i0; mi[2 * warp + 1] = i1; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float d0 = L2_INF, d1 = L2_INF; int j0 = -1, j1 = -1;
+            for (int w = 0; w < 2 * nwarps; ++w) {
+                const float d = md[w]; const int j = mi[w];
+                if (j < 0) continue;
+                if (d < d0 || (d == d0 && (unsigned)j < (unsigned)j0)) { d1 = d0; j1 = j0; d0 = d; j0 = j; }
+                else if (d < d1 || (d == d1 && (unsigned)j < (unsigned)j1)) { d1 = d; j1 = j; }
+            }
+            pm_dmatch r0, r1;
+            r0.queryIdx = r1.queryIdx = i + q_index_base;
+            r0.imgIdx = r1.imgIdx = 0;
+            r0.trainIdx = j0; r0.distance = j0 < 0 ? 3.402823466e+38f : sqrtf(d0);
+            r1.trainIdx = j1; r1.distance = j1 < 0 ? 3.402823466e+38f : sqrtf(d1);
+            out[(size_t)i * 2] = r0;
+            out[(size_t)i * 2 + 1] = r1;
+        }
+    }
+}
+
+__global__ void l2_knn_to_colbest_kernel(const pm_dmatch *__restrict__ knn, int n, int base,
+                                         unsigned long long *__restrict__ col)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const pm_dmatch m = knn[(size_t)j * 2];
+    col[j] = m.trainIdx < 0 ? ~0ull
+             : ((unsigned long long)__float_as_uint(m.distance) << 32) | (unsigned)(m.trainIdx + base);
+}
+
+template <typename T>
+int run_exact(pm_ctx *ctx, const T *dq, const T *dt, int nq, int nt, int dim, const int *rows, const int *count,
+              int base, pm_dmatch *dout)
+{
+    const int dim_pad = (dim + 127) / 128 * 128;
+    const size_t smem = (size_t)dim_pad * 4 + 8 * 4 * 4;
+    const int grid = min(nq, 8 * ctx->num_sms);
+    l2_exact_kernel<T><<<grid, 256, smem, ctx->stream>>>(dq, dt, nq, nt, dim, rows, count, base, dout);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}
+
+}  // namespace
+
+// Debug hook (tools/gpu_debug.py): dump of (||b||^2 - 2ab) from the tensor-core kernel.
+static float *g_l2_dump = nullptr;
+extern "C" void pm_debug_set_l2_dump(float *ddump) { g_l2_dump = ddump; }
+// Force the exact FP32 kernel for every row (parity cross-check of the two paths).
+static int g_l2_force_exact = 0;
+extern "C" void pm_debug_force_exact(int on) { g_l2_force_exact = on; }
+
+int pmk_l2_knn2(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
+                int q_index_base, pm_dmatch *dout)
+{
+    if (nq <= 0) return PM_OK;
+    const int mq_pad = pm_round_up(nq, 128), nt_pad = pm_round_up(nt > 0 ? nt : 1, 256);
+    const int MT = mq_pad / 128, NT = nt_pad / 256;
+    const int smax = l2_tc_smax(ctx, MT, NT);
+    const bool use_tc = dim <= L2_KDIM && nt > 0 && smax * 3 <= 32 && !g_l2_force_exact;
+    ctx->l2_stats[2] = 0; ctx->l2_stats[3] = 0;
+    if (!use_tc) {
+        if (is_u8) return run_exact(ctx, (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, nullptr, nullptr, q_index_base, dout);
+        return run_exact(ctx, (const float *)dq, (const float *)dt, nq, nt, dim, nullptr, nullptr, q_index_base, dout);
+    }
+    PM_WS(ctx, flags, L2Flags *, WS_L2_FLAGS, sizeof(L2Flags));
+    PM_WS(ctx, qpack, __nv_bfloat16 *, WS_Q_PACK, (size_t)mq_pad * L2_PACK_COLS * 2);
+    PM_WS(ctx, tpack, __nv_bfloat16 *, WS_T_PACK, (size_t)nt_pad * L2_PACK_COLS * 2);
+    PM_WS(ctx, qnorm, float *, WS_Q_NORM, (size_t)mq_pad * 4);
+    PM_WS(ctx, tnorm, float *, WS_T_NORM, (size_t)nt_pad * 4);
+    PM_WS(ctx, part, L2Cand *, WS_L2_PART, (size_t)mq_pad * smax * 3 * sizeof(L2Cand));
+    PM_WS(ctx, flagged, int *, WS_L2_FLAGGED, (size_t)nq * 4);
+    PM_CUDA(ctx, cudaMemsetAsync(flags, 0, sizeof(L2Flags), ctx->stream));
+    if (is_u8) {
+        l2_pack_kernel<uint8_t><<<pm_cdiv(nt_pad, 8), 256, 0, ctx->stream>>>((const uint8_t *)dt, nt, dim, nt_pad, 1, tpack, tnorm, flags, nullptr, 0);
+        PM_CHECK_LAUNCH(ctx);
+        l2_pack_kernel<uint8_t><<<pm_cdiv(mq_pad, 8), 256, 0, ctx->stream>>>((const uint8_t *)dq, nq, dim, mq_pad, 0, qpack, qnorm, flags, part, smax * 3);
+        PM_CHECK_LAUNCH(ctx);
+    } else {
+        l2_pack_kernel<float><<<pm_cdiv(nt_pad, 8), 256, 0, ctx->stream>>>((const float *)dt, nt, dim, nt_pad, 1, tpack, tnorm, flags, nullptr, 0);
+        PM_CHECK_LAUNCH(ctx);
+        l2_pack_kernel<float><<<pm_cdiv(mq_pad, 8), 256, 0, ctx->stream>>>((const float *)dq, nq, dim, mq_pad, 0, qpack, qnorm, flags, part, smax * 3);
+        PM_CHECK_LAUNCH(ctx);
+    }
+    int st = l2_tc_launch(ctx, qpack, mq_pad, tpack, nt_pad, tnorm, flags, part, smax, g_l2_dump);
+    if (st != PM_OK) return st;
+    l2_finish_kernel<<<pm_cdiv(nq, 8), 256, 0, ctx->stream>>>(part, smax * 3, qnorm, (const float *)dq, (const float *)dt, nq, dim,
+                                                               flags, flagged, q_index_base, dout);
+    PM_CHECK_LAUNCH(ctx);
+    if (!is_u8) {   // u8 input is always exact-integer mode: nothing can be flagged
+        int s2 = run_exact(ctx, (const float *)dq, (const float *)dt, nq, nt, dim, flagged, &flags->n_flagged, q_index_base, dout);
+        if (s2 != PM_OK) return s2;
+    }
+    ctx->l2_stats[3] = smax;
+    return PM_OK;
+}
+
+int pm_l2_stats(pm_ctx *ctx, int32_t out[4])
+{
+    if (!ctx) return PM_BAD_ARG;
+    L2Flags h = {};
+    if (ctx->slot_ptr[WS_L2_FLAGS]) {
+        PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        PM_CUDA(ctx, cudaMemcpy(&h, ctx->slot_ptr[WS_L2_FLAGS], sizeof(h), cudaMemcpyDeviceToHost));
+    }
+    out[0] = ctx->l2_stats[3] ? !h.nonexact : 0;
+    out[1] = h.n_flagged;
+    out[2] = ctx->l2_stats[3] ? (h.nonexact ? 6 : 2) : 0;
+    out[3] = ctx->l2_stats[3];
+    return PM_OK;
+}
+
+// Nearest query for every train row = kNN of the train set against the query shard.
+int pmk_l2_col_best(pm_ctx *ctx, const float *dq, int nq, const float *dt, int nt, int dim, int q_index_base,
+                    uint64_t *dcol_best)
+{
+    if (nt <= 0) return PM_OK;
+    PM_WS(ctx, knn, pm_dmatch *, WS_KNN2, (size_t)nt * 2 * sizeof(pm_dmatch));
+    if (nq <= 0) {
+        PM_CUDA(ctx, cudaMemsetAsync(dcol_best, 0xFF, (size_t)nt * 8, ctx->stream));
+        return PM_OK;
+    }
+    int st = pmk_l2_knn2(ctx, dt, nt, dq, nq, dim, 0, 0, knn);
+    if (st != PM_OK) return st;
+    // trainIdx here is a (local) query index: shift by the shard base
+    l2_knn_to_colbest_kernel<<<pm_cdiv(nt, 256), 256, 0, ctx->stream>>>(knn, nt, q_index_base,
+                                                                        (unsigned long long *)dcol_best);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}

@@ -1,0 +1,388 @@
+// l2_tc.cu -- K2: L2 distance GEMM on tcgen05 tensor cores with the top-3 selection fused
+// into the epilogue (the distance matrix never reaches HBM).  sm_100a only.
+//
+// Replaces the all-pairs distance + per-row k-smallest inside
+// BruteForceMatcher<L2<float>>::match / knnMatch, the matcher named at
+// /root/reference/Points Matching/main.cpp:43 (OpenCV batchDistance).
+//
+//   d^2(i,j) = ||a_i||^2 + ||b_j||^2 - 2 a_i.b_j
+// The -2 is folded into the packed train operand, ||a_i||^2 is row-constant and added
+// after selection, ||b_j||^2 is added in the epilogue.  Operands are bf16 "hi|lo" rows
+// written by K1 (l2.cu):
+//   exact-integer mode (SIFT, values 0..255): lo == 0, 2 k-blocks, the GEMM is exact
+//   split mode (general floats):  a.b ~ ah.bh + ah.bl + al.bh, 6 k-blocks
+//
+// Structure (one persistent CTA per SM, 384 threads):
+//   warp 0      TMA producer   : A row-tile resident (<= 4 x 16 KB), B k-blocks through a
+//                                4-stage 32 KB ring (cp.async.bulk.tensor, SWIZZLE_128B)
+//   warp 1      MMA issuer     : tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16,
+//                                accumulators double-buffered in TMEM (2 x 256 columns)
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue       : tcgen05.ld 32x32b.x32, + ||b||^2, per-thread running
+//                                (best, second, third) kept in registers across the sweep
+// Each CTA walks a contiguous range of the (row-tile, column-tile) space; per row tile it
+// writes one "segment" of candidates which K3 merges, re-ranks in FP32 and certifies.
+#include <cuda.h>
+#include "pm_internal.h"
+#include "l2_common.h"
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int A_BLK_BYTES = BM * BK * 2;     // 16 KB
+constexpr int B_BLK_BYTES = BN * BK * 2;     // 32 KB
+constexpr int NSTAGE = 4;
+constexpr int A_MAXBLK = 4;
+constexpr int TC_THREADS = 384;
+constexpr int EPI_WARP0 = 4;
+constexpr int SMEM_A = 0;
+constexpr int SMEM_B = A_MAXBLK * A_BLK_BYTES;                 // 65536
+constexpr int SMEM_BAR = SMEM_B + NSTAGE * B_BLK_BYTES;        // 196608
+constexpr int SMEM_SCRATCH = SMEM_BAR + 256;
+constexpr int SMEM_TOTAL = SMEM_SCRATCH + BM * 6 * 4 + 1024;   // + alignment slack
+
+// instruction descriptor: D=F32, A=B=BF16, K-major both, N=256, M=128
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// K-major, SWIZZLE_128B smem operand: 8-row atoms of 1024 B (SBO), LBO = 1 (16 B, unused
+// inside one 128 B swizzle span), descriptor version 1 (Blackwell), layout type 2.
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct Top3 {
+    float d1, d2, d3;
+    int i1, i2, i3;
+    __device__ __forceinline__ void reset()
+    {
+        d1 = d2 = d3 = __int_as_float(0x7f800000);
+        i1 = i2 = i3 = -1;
+    }
+    // strict <: columns arrive in ascending order, so the lowest index wins ties
+    __device__ __forceinline__ void insert(float t, int idx)
+    {
+        if (t < d3) {
+            if (t < d2) {
+                d3 = d2; i3 = i2;
+                if (t < d1) { d2 = d1; i2 = i1; d1 = t; i1 = idx; }
+                else { d2 = t; i2 = idx; }
+            } else { d3 = t; i3 = idx; }
+        }
+    }
+};
+
+struct TcParams {
+    const float *tnorm;          // [nt_pad] ||b||^2, +inf on pad rows
+    const L2Flags *flags;
+    L2Cand *part;                // [mq_pad][smax][3]
+    float *dump;                 // debug: [mq_pad][nt_pad] of (||b||^2 - 2ab), or null
+    int MT, NT, smax, nt_pad;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t, TcParams P)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t sA = sbase + SMEM_A, sB = sbase + SMEM_B, sBar = sbase + SMEM_BAR;
+    const uint32_t bar_full = sBar, bar_empty = sBar + 8 * NSTAGE;
+    const uint32_t bar_afull = sBar + 16 * NSTAGE, bar_aempty = bar_afull + 8;
+    const uint32_t bar_tfull = bar_aempty + 8, bar_tempty = bar_tfull + 16;
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(sgen + SMEM_BAR + 16 * NSTAGE + 48);
+    L2Cand *scratch = reinterpret_cast<L2Cand *>(sgen + SMEM_SCRATCH);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = P.flags->nonexact ? 6 : 2;
+    const int nablk = P.flags->nonexact ? 4 : 2;
+
+    const long long T = (long long)P.MT * P.NT;
+    const int G = gridDim.x;
+    const int t_begin = (int)((T * blockIdx.x) / G), t_end = (int)((T * (blockIdx.x + 1)) / G);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_q)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_t)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_afull, 1);
+        mbar_init(bar_aempty, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32((const void *)tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0, apar = 0; int cur_m = -1;
+            for (int tile = t_begin; tile < t_end; ++tile) {
+                const int m = tile / P.NT, n = tile % P.NT;
+                if (m != cur_m) {
+                    if (cur_m >= 0) { mbar_wait(bar_aempty, apar); apar ^= 1; }
+                    mbar_expect_tx(bar_afull, (uint32_t)(nablk * A_BLK_BYTES));
+                    for (int b = 0; b < nablk; ++b)
+                        tma_load_2d(sA + b * A_BLK_BYTES, &tmap_q, bar_afull, b * BK, m * BM);
+                    cur_m = m;
+                }
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    mbar_expect_tx(bar_full + 8 * stage, B_BLK_BYTES);
+                    // k-blocks: hi0 hi1 | lo0 lo1 | hi0 hi1   (packed row = [hi 0..127 | lo 128..255])
+                    const int kc = ((kb == 2 || kb == 3) ? 128 : 0) + (kb & 1) * BK;
+                    tma_load_2d(sB + stage * B_BLK_BYTES, &tmap_t, bar_full + 8 * stage, kc, n * BN);
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0, apar = 0, acc = 0, acc_phase = 0; int cur_m = -1;
+            for (int tile = t_begin; tile < t_end; ++tile) {
+                const int m = tile / P.NT;
+                if (m != cur_m) { mbar_wait(bar_afull, apar); apar ^= 1; cur_m = m; }
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    // A block: hi for kb 0..3 (x B hi, x B lo), lo for kb 4,5 (x B hi)
+                    const int ablk = kb < 4 ? (kb & 1) : 2 + (kb & 1);
+                    const uint64_t adesc = make_sdesc(sA + ablk * A_BLK_BYTES);
+                    const uint64_t bdesc = make_sdesc(sB + stage * B_BLK_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)   // +32 B per K=16 step inside the swizzle span
+                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (uint32_t)((kb | k) != 0));
+                    umma_commit(bar_empty + 8 * stage);
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(bar_tfull + 8 * acc);
+                if (tile + 1 < t_end && (tile + 1) / P.NT != m) umma_commit(bar_aempty);
+                acc ^= 1; if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===================== epilogue =====================
+        const int e = warp - EPI_WARP0;
+        const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+        const int half = e >> 2;               // which 128 of the tile's 256 columns
+        const int row = quarter * 32 + lane;   // row within the 128-row tile
+        uint32_t acc = 0, acc_phase = 0; int cur_m = -1;
+        Top3 best; best.reset();
+
+        auto flush = [&](int m) {
+            if (half == 1) {
+                scratch[row * 3 + 0] = L2Cand{best.d1, best.i1};
+                scratch[row * 3 + 1] = L2Cand{best.d2, best.i2};
+                scratch[row * 3 + 2] = L2Cand{best.d3, best.i3};
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (half == 0) {
+                // upper-half indices are all larger: strict < keeps the lower index on ties
+                for (int k = 0; k < 3; ++k) { const L2Cand c = scratch[row * 3 + k]; best.insert(c.d, c.idx); }
+                // segment slot = index of this CTA among the CTAs that touch row tile m
+                const long long first_tile = (long long)m * P.NT;
+                int c0 = (int)((first_tile * G) / T);
+                while ((T * (c0 + 1)) / G <= first_tile) ++c0;
+                while ((T * c0) / G > first_tile) --c0;
+                const int slot = (int)blockIdx.x - c0;
+                L2Cand *dst = P.part + ((size_t)(m * BM + row) * P.smax + slot) * 3;
+                dst[0] = L2Cand{best.d1, best.i1};
+                dst[1] = L2Cand{best.d2, best.i2};
+                dst[2] = L2Cand{best.d3, best.i3};
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            best.reset();
+        };
+
+        for (int tile = t_begin; tile < t_end; ++tile) {
+            const int m = tile / P.NT, n = tile % P.NT;
+            if (m != cur_m) { if (cur_m >= 0) flush(cur_m); cur_m = m; }
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            const int col0 = n * BN + half * 128;
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128;
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t r[32];
+                tmem_ld32(taddr0 + ch * 32, r);
+                float nb[32];
+                const float4 *np = reinterpret_cast<const float4 *>(P.tnorm + col0 + ch * 32);
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    const float4 x = __ldg(np + v);
+                    nb[4 * v] = x.x; nb[4 * v + 1] = x.y; nb[4 * v + 2] = x.z; nb[4 * v + 3] = x.w;
+                }
+                tmem_ld_wait();
+                if (P.dump) {
+                    float *drow = P.dump + (size_t)(m * BM + row) * P.nt_pad + col0 + ch * 32;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) drow[c] = __uint_as_float(r[c]) + nb[c];
+                }
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float t = __uint_as_float(r[c]) + nb[c];
+                    best.insert(t, col0 + ch * 32 + c);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+            acc ^= 1; if (acc == 0) acc_phase ^= 1;
+        }
+        if (cur_m >= 0) flush(cur_m);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tmap(pm_ctx *ctx, CUtensorMap *tm, const void *base, int rows_pad, int box_rows)
+{
+    if (!ctx->tmap_encode) {
+        cudaDriverEntryPointQueryResult qres;
+        void *fn = nullptr;
+        PM_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess)
+            return pm_fail(ctx, PM_CUDA_ERR, "cuTensorMapEncodeTiled entry point not found");
+        ctx->tmap_encode = fn;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)L2_PACK_COLS, (cuuint64_t)rows_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)L2_PACK_COLS * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ((tmap_encode_fn)ctx->tmap_encode)(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base),
+                                                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return pm_fail(ctx, PM_CUDA_ERR, "cuTensorMapEncodeTiled failed: %d", (int)r);
+    return PM_OK;
+}
+
+}  // namespace
+
+int l2_tc_grid(pm_ctx *ctx, int MT, int NT)
+{
+    long long T = (long long)MT * NT;
+    return (int)(T < ctx->num_sms ? T : ctx->num_sms);
+}
+
+// Max number of CTAs (segments) that can touch one row tile.
+int l2_tc_smax(pm_ctx *ctx, int MT, int NT)
+{
+    const long long T = (long long)MT * NT;
+    const int G = l2_tc_grid(ctx, MT, NT);
+    int smax = 1;
+    for (int m = 0; m < MT; ++m) {
+        const long long first = (long long)m * NT, last = first + NT - 1;
+        int c0 = (int)((first * G) / T);
+        while ((T * (c0 + 1)) / G <= first) ++c0;
+        while ((T * c0) / G > first) --c0;
+        int c1 = (int)((last * G) / T);
+        while ((T * (c1 + 1)) / G <= last) ++c1;
+        while ((T * c1) / G > last) --c1;
+        if (c1 - c0 + 1 > smax) smax = c1 - c0 + 1;
+    }
+    return smax;
+}
+
+int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, int nt_pad, const float *tnorm,
+                 const L2Flags *flags, L2Cand *part, int smax, float *dump)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        PM_CUDA(ctx, cudaFuncSetAttribute(l2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        attr_set = true;
+    }
+    CUtensorMap tq, tt;
+    int st;
+    if ((st = make_tmap(ctx, &tq, qpack, mq_pad, BM)) != PM_OK) return st;
+    if ((st = make_tmap(ctx, &tt, tpack, nt_pad, BN)) != PM_OK) return st;
+    TcParams P;
+    P.tnorm = tnorm; P.flags = flags; P.part = part; P.dump = dump;
+    P.MT = mq_pad / BM; P.NT = nt_pad / BN; P.smax = smax; P.nt_pad = nt_pad;
+    const int G = l2_tc_grid(ctx, P.MT, P.NT);
+    l2_tc_kernel<<<G, TC_THREADS, SMEM_TOTAL, ctx->stream>>>(tq, tt, P);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}

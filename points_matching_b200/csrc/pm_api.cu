@@ -1,0 +1,469 @@
+// pm_api.cu -- the C ABI of libpm (include/pm.h): context, workspace arena, and the
+// host-buffer entry points that stand in for the OpenCV calls of
+// /root/reference/Points Matching/main.cpp:43-46, 49-69, 89-91, 95-98, 103-132.
+// Every path runs CUDA kernels; there is no CPU fallback.
+#include <cstdarg>
+#include <cstdlib>
+#include <vector>
+#include "pm_internal.h"
+
+int pmk_ransac_pick(pm_ctx *ctx, const uint64_t *dkey, const float *dF32, int id_base, int n_models, float *dFw);
+
+int pm_fail(pm_ctx *ctx, int status, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return status;
+}
+
+void *pm_ws(pm_ctx *ctx, int slot, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    if (ctx->slot_bytes[slot] >= bytes) return ctx->slot_ptr[slot];
+    if (ctx->slot_ptr[slot]) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(ctx->slot_ptr[slot]);
+        ctx->slot_ptr[slot] = nullptr; ctx->slot_bytes[slot] = 0;
+    }
+    size_t cap = bytes + bytes / 4;            // growth slack
+    cap = (cap + 255) & ~(size_t)255;
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, cap);
+    if (e != cudaSuccess) {
+        pm_fail(ctx, PM_CUDA_ERR, "cudaMalloc(%zu) for workspace slot %d: %s", cap, slot, cudaGetErrorString(e));
+        return nullptr;
+    }
+    ctx->slot_ptr[slot] = p; ctx->slot_bytes[slot] = cap;
+    return p;
+}
+
+extern "C" {
+
+int pm_version(void) { return PM_VERSION; }
+
+int pm_create(pm_ctx **out, int device)
+{
+    if (!out) return PM_BAD_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return PM_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PM_NO_DEVICE;
+    if (prop.major != 10) return PM_NO_DEVICE;          // sm_100a kernels only
+    if (cudaSetDevice(device) != cudaSuccess) return PM_CUDA_ERR;
+    pm_ctx *ctx = new pm_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PM_CUDA_ERR; }
+    ctx->stream = ctx->own_stream;
+    if (cudaMallocHost((void **)&ctx->h_pinned, 4096) != cudaSuccess) { cudaStreamDestroy(ctx->own_stream); delete ctx; return PM_CUDA_ERR; }
+    *out = ctx;
+    return PM_OK;
+}
+
+int pm_destroy(pm_ctx *ctx)
+{
+    if (!ctx) return PM_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int s = 0; s < PM_NSLOTS; ++s) if (ctx->slot_ptr[s]) cudaFree(ctx->slot_ptr[s]);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return PM_OK;
+}
+
+int pm_set_stream(pm_ctx *ctx, void *s)
+{
+    if (!ctx) return PM_BAD_ARG;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return PM_OK;
+}
+
+int pm_sync(pm_ctx *ctx)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PM_OK;
+}
+
+const char *pm_last_error(pm_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+uint64_t pm_launch_count(pm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------
+// device-resident entry points
+// ---------------------------------------------------------------------------------
+#define PM_REQUIRE(ctx, cond, msg) do { if (!(cond)) return pm_fail(ctx, PM_BAD_ARG, "%s: %s", __func__, msg); } while (0)
+
+int pm_knn2_l2_f32_dev(pm_ctx *ctx, const float *dq, int nq, const float *dt, int nt, int dim, int base, pm_dmatch *dout)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && dim > 0, "negative size or dim <= 0");
+    PM_REQUIRE(ctx, nq == 0 || (dq && dout), "null pointer");
+    return pmk_l2_knn2(ctx, dq, nq, dt, nt, dim, 0, base, dout);
+}
+int pm_knn2_l2_u8_dev(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, int dim, int base, pm_dmatch *dout)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && dim > 0, "negative size or dim <= 0");
+    PM_REQUIRE(ctx, nq == 0 || (dq && dout), "null pointer");
+    return pmk_l2_knn2(ctx, dq, nq, dt, nt, dim, 1, base, dout);
+}
+int pm_knn2_hamming_dev(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, int bytes, int base, pm_dmatch *dout)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && bytes > 0, "negative size or bytes <= 0");
+    PM_REQUIRE(ctx, nq == 0 || (dq && dout), "null pointer");
+    return pmk_hamming_knn2(ctx, dq, nq, dt, nt, bytes, base, dout);
+}
+int pm_ratio_filter_dev(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout, int32_t *dn)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, nq >= 0 && dn, "bad argument");
+    return pmk_ratio_filter(ctx, dknn, nq, ratio, dout, dn);
+}
+int pm_minmax_filter_dev(pm_ctx *ctx, const pm_dmatch *dm, int n, int stride, pm_dmatch *dout, int32_t *dn, double *dminmax)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, n >= 0 && (stride == 1 || stride == 2) && dn, "bad argument");
+    return pmk_minmax_filter(ctx, dm, n, stride, dout, dn, dminmax);
+}
+int pm_col_best_hamming_dev(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, int bytes, int base, uint64_t *dcol)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && bytes > 0, "bad argument");
+    if (nq == 0 && nt > 0) { PM_CUDA(ctx, cudaMemsetAsync(dcol, 0xFF, (size_t)nt * 8, ctx->stream)); return PM_OK; }
+    return pmk_hamming_col_best(ctx, dq, nq, dt, nt, bytes, base, dcol);
+}
+int pm_col_best_l2_f32_dev(pm_ctx *ctx, const float *dq, int nq, const float *dt, int nt, int dim, int base, uint64_t *dcol)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && dim > 0, "bad argument");
+    return pmk_l2_col_best(ctx, dq, nq, dt, nt, dim, base, dcol);
+}
+int pm_cross_check_dev(pm_ctx *ctx, const pm_dmatch *dknn, int nq, int stride, const uint64_t *dcol, int nt, pm_dmatch *dout, int32_t *dn)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, nq >= 0 && (stride == 1 || stride == 2) && dn, "bad argument");
+    return pmk_cross_check(ctx, dknn, nq, stride, dcol, nt, dout, dn);
+}
+int pm_gather_matches_dev(pm_ctx *ctx, const pm_dmatch *dm, const int32_t *dn, int max_matches, const float *dkp1, int nkp1,
+                          const float *dkp2, int nkp2, float *dp1, float *dp2)
+{
+    if (!ctx) return PM_BAD_ARG;
+    return pmk_gather_matches(ctx, dm, dn, max_matches, dkp1, nkp1, dkp2, nkp2, dp1, dp2);
+}
+int pm_ransac_solve_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const int32_t *ds, int n_hyp, int m, float *dF32)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, (m == 7 || m == 8) && n >= m && n_hyp >= 0, "sample_size must be 7 or 8 and n >= sample_size");
+    return pmk_ransac_solve(ctx, dp1, dp2, n, ds, n_hyp, m, dF32);
+}
+int pm_ransac_score_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dF32, int n_models, float thr,
+                        int metric, int32_t *dcounts)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, n >= 0 && n_models >= 0 && (metric == PM_METRIC_SAMPSON || metric == PM_METRIC_SYMEPI), "bad argument");
+    return pmk_ransac_score(ctx, dp1, dp2, n, dF32, n_models, thr, metric, dcounts);
+}
+int pm_ransac_best_dev(pm_ctx *ctx, const int32_t *dcounts, int n_models, int id_base, uint64_t *dkey)
+{
+    if (!ctx) return PM_BAD_ARG;
+    return pmk_ransac_best(ctx, dcounts, n_models, id_base, dkey);
+}
+int pm_ransac_finish_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dFw, float thr, int metric,
+                         int refit, double *dF, uint8_t *dmask, int32_t *dn)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, n >= 0 && (metric == PM_METRIC_SAMPSON || metric == PM_METRIC_SYMEPI), "bad argument");
+    return pmk_ransac_finish(ctx, dp1, dp2, n, dFw, thr, metric, refit, dF, dmask, dn);
+}
+
+// ---------------------------------------------------------------------------------
+// host-buffer entry points (synchronous; H2D + kernels + D2H)
+// ---------------------------------------------------------------------------------
+#define H2D(ctx, dst, src, bytes) PM_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (ctx)->stream))
+#define D2H(ctx, dst, src, bytes) PM_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (ctx)->stream))
+
+static int knn2_host(pm_ctx *ctx, const void *q, int nq, const void *t, int nt, int width, size_t elem, int kind,
+                     pm_dmatch *out)
+{
+    // kind 0: l2 f32, 1: l2 u8, 2: hamming
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && width > 0, "negative size or zero width");
+    if (nq == 0) return PM_OK;                       // empty query -> empty result
+    PM_REQUIRE(ctx, q && out && (nt == 0 || t), "null pointer");
+    PM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t qb = (size_t)nq * width * elem, tb = (size_t)nt * width * elem;
+    PM_WS(ctx, dq, uint8_t *, WS_Q_RAW, qb);
+    PM_WS(ctx, dt, uint8_t *, WS_T_RAW, tb);
+    PM_WS(ctx, dout, pm_dmatch *, WS_OUT, (size_t)nq * 2 * sizeof(pm_dmatch));
+    H2D(ctx, dq, q, qb);
+    if (tb) H2D(ctx, dt, t, tb);
+    int st;
+    if (kind == 0) st = pmk_l2_knn2(ctx, dq, nq, dt, nt, width, 0, 0, dout);
+    else if (kind == 1) st = pmk_l2_knn2(ctx, dq, nq, dt, nt, width, 1, 0, dout);
+    else st = pmk_hamming_knn2(ctx, dq, nq, dt, nt, width, 0, dout);
+    if (st != PM_OK) return st;
+    D2H(ctx, out, dout, (size_t)nq * 2 * sizeof(pm_dmatch));
+    PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PM_OK;
+}
+
+int pm_knn2_l2_f32(pm_ctx *ctx, const float *q, int nq, const float *t, int nt, int dim, pm_dmatch *out)
+{ return knn2_host(ctx, q, nq, t, nt, dim, 4, 0, out); }
+int pm_knn2_l2_u8(pm_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt, int dim, pm_dmatch *out)
+{ return knn2_host(ctx, q, nq, t, nt, dim, 1, 1, out); }
+int pm_knn2_hamming(pm_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt, int bytes, pm_dmatch *out)
+{ return knn2_host(ctx, q, nq, t, nt, bytes, 1, 2, out); }
+
+static int read_count(pm_ctx *ctx, const int32_t *dn, int *n_out)
+{
+    D2H(ctx, ctx->h_pinned, dn, 4);
+    PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_out = ctx->h_pinned[0];
+    return PM_OK;
+}
+
+int pm_ratio_filter(pm_ctx *ctx, const pm_dmatch *knn, int nq, float ratio, pm_dmatch *out, int *n_out)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, nq >= 0 && n_out, "bad argument");
+    *n_out = 0;
+    if (nq == 0) return PM_OK;
+    PM_CUDA(ctx, cudaSetDevice(ctx->device));
+    PM_WS(ctx, dknn, pm_dmatch *, WS_KNN, (size_t)nq * 2 * sizeof(pm_dmatch));
+    PM_WS(ctx, dout, pm_dmatch *, WS_OUT2, (size_t)nq * sizeof(pm_dmatch));
+    PM_WS(ctx, dn, int32_t *, WS_KEY, 64);
+    H2D(ctx, dknn, knn, (size_t)nq * 2 * sizeof(pm_dmatch));
+    int st = pmk_ratio_filter(ctx, dknn, nq, ratio, dout, dn);
+    if (st != PM_OK) return st;
+    if ((st = read_count(ctx, dn, n_out)) != PM_OK) return st;
+    if (*n_out) { D2H(ctx, out, dout, (size_t)*n_out * sizeof(pm_dmatch)); PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); }
+    return PM_OK;
+}
+
+int pm_minmax_filter(pm_ctx *ctx, const pm_dmatch *m, int n, int stride, pm_dmatch *out, int *n_out, double *mn, double *mx)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, n >= 0 && (stride == 1 || stride == 2) && n_out, "bad argument");
+    *n_out = 0;
+    PM_CUDA(ctx, cudaSetDevice(ctx->device));
+    PM_WS(ctx, dm, pm_dmatch *, WS_KNN, (size_t)(n ? n : 1) * stride * sizeof(pm_dmatch));
+    PM_WS(ctx, dout, pm_dmatch *, WS_OUT2, (size_t)(n ? n : 1) * sizeof(pm_dmatch));
+    PM_WS(ctx, dn, int32_t *, WS_KEY, 64);
+    double *dmm = reinterpret_cast<double *>(dn + 4);
+    if (n) H2D(ctx, dm, m, (size_t)n * stride * sizeof(pm_dmatch));
+    int st = pmk_minmax_filter(ctx, dm, n, stride, dout, dn, dmm);
+    if (st != PM_OK) return st;
+    D2H(ctx, ctx->h_pinned, dn, 32);
+    PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_out = ctx->h_pinned[0];
+    const double *hmm = reinterpret_cast<const double *>(ctx->h_pinned + 4);
+    if (mn) *mn = hmm[0];
+    if (mx) *mx = hmm[1];
+    if (*n_out) { D2H(ctx, out, dout, (size_t)*n_out * sizeof(pm_dmatch)); PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); }
+    return PM_OK;
+}
+
+static int match_cross_host(pm_ctx *ctx, const void *q, int nq, const void *t, int nt, int width, size_t elem, int kind,
+                            pm_dmatch *out, int *n_out)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && width > 0 && n_out, "bad argument");
+    *n_out = 0;
+    if (nq == 0 || nt == 0) return PM_OK;
+    PM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t qb = (size_t)nq * width * elem, tb = (size_t)nt * width * elem;
+    PM_WS(ctx, dq, uint8_t *, WS_Q_RAW, qb);
+    PM_WS(ctx, dt, uint8_t *, WS_T_RAW, tb);
+    PM_WS(ctx, dknn, pm_dmatch *, WS_OUT, (size_t)nq * 2 * sizeof(pm_dmatch));
+    PM_WS(ctx, dout, pm_dmatch *, WS_OUT2, (size_t)nq * sizeof(pm_dmatch));
+    PM_WS(ctx, dcol, uint64_t *, WS_COLBEST, (size_t)nt * 8);
+    PM_WS(ctx, dn, int32_t *, WS_KEY, 64);
+    H2D(ctx, dq, q, qb);
+    H2D(ctx, dt, t, tb);
+    int st;
+    if (kind == 0) {
+        if ((st = pmk_l2_knn2(ctx, dq, nq, dt, nt, width, 0, 0, dknn)) != PM_OK) return st;
+        if ((st = pmk_l2_col_best(ctx, (const float *)dq, nq, (const float *)dt, nt, width, 0, dcol)) != PM_OK) return st;
+    } else {
+        if ((st = pmk_hamming_knn2(ctx, dq, nq, dt, nt, width, 0, dknn)) != PM_OK) return st;
+        if ((st = pmk_hamming_col_best(ctx, dq, nq, dt, nt, width, 0, dcol)) != PM_OK) return st;
+    }
+    if ((st = pmk_cross_check(ctx, dknn, nq, 2, dcol, nt, dout, dn)) != PM_OK) return st;
+    if ((st = read_count(ctx, dn, n_out)) != PM_OK) return st;
+    if (*n_out) { D2H(ctx, out, dout, (size_t)*n_out * sizeof(pm_dmatch)); PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); }
+    return PM_OK;
+}
+
+int pm_match_cross_l2_f32(pm_ctx *ctx, const float *q, int nq, const float *t, int nt, int dim, pm_dmatch *out, int *n_out)
+{ return match_cross_host(ctx, q, nq, t, nt, dim, 4, 0, out, n_out); }
+int pm_match_cross_hamming(pm_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt, int bytes, pm_dmatch *out, int *n_out)
+{ return match_cross_host(ctx, q, nq, t, nt, bytes, 1, 1, out, n_out); }
+
+int pm_gather_points(pm_ctx *ctx, const float *kp, int nkp, const int32_t *idx, int n, float *out)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, nkp >= 0 && n >= 0, "bad argument");
+    if (n == 0) return PM_OK;
+    PM_CUDA(ctx, cudaSetDevice(ctx->device));
+    PM_WS(ctx, dkp, float *, WS_KP, (size_t)(nkp ? nkp : 1) * 8);
+    PM_WS(ctx, didx, int32_t *, WS_IDX, (size_t)n * 4);
+    PM_WS(ctx, dout, float *, WS_P1, (size_t)n * 8);
+    if (nkp) H2D(ctx, dkp, kp, (size_t)nkp * 8);
+    H2D(ctx, didx, idx, (size_t)n * 4);
+    int st = pmk_gather_points(ctx, dkp, nkp, didx, n, dout);
+    if (st != PM_OK) return st;
+    D2H(ctx, out, dout, (size_t)n * 8);
+    PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PM_OK;
+}
+
+// splitmix64: deterministic, rank-invariant sample sets
+static inline uint64_t splitmix64(uint64_t &s)
+{
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+int pm_make_sample_sets(int n_points, int n_hyp, int m, uint64_t seed, int32_t *out)
+{
+    if (n_points < m || m <= 0 || m > 8 || n_hyp < 0 || !out) return PM_BAD_ARG;
+    for (int h = 0; h < n_hyp; ++h) {
+        uint64_t s = seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(h + 1));
+        int32_t *row = out + (size_t)h * m;
+        for (int i = 0; i < m; ++i) {
+            for (;;) {
+                const int32_t v = (int32_t)(splitmix64(s) % (uint64_t)n_points);
+                bool dup = false;
+                for (int k = 0; k < i; ++k) dup = dup || row[k] == v;
+                if (!dup) { row[i] = v; break; }
+            }
+        }
+    }
+    return PM_OK;
+}
+
+int pm_find_fundamental(pm_ctx *ctx, const float *p1, const float *p2, int n, const pm_ransac_params *prm,
+                        double F[9], uint8_t *mask, int *n_inliers)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, prm && p1 && p2 && F, "null pointer");
+    const int m = prm->sample_size;
+    PM_REQUIRE(ctx, m == 7 || m == 8, "sample_size must be 7 or 8");
+    PM_REQUIRE(ctx, prm->metric == PM_METRIC_SAMPSON || prm->metric == PM_METRIC_SYMEPI, "unknown metric");
+    PM_REQUIRE(ctx, prm->n_hyp >= 0 && n >= 0, "negative size");
+    if (n_inliers) *n_inliers = 0;
+    if (n < m || prm->n_hyp == 0) return PM_EMPTY;          // cv::findFundamentalMat: empty Mat
+    PM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int per = m == 8 ? 1 : 3, nh = prm->n_hyp;
+    PM_WS(ctx, dp1, float *, WS_P1, (size_t)n * 8);
+    PM_WS(ctx, dp2, float *, WS_P2, (size_t)n * 8);
+    PM_WS(ctx, ds, int32_t *, WS_SAMPLES, (size_t)nh * m * 4);
+    PM_WS(ctx, dF32, float *, WS_F32, ((size_t)nh * per + 1) * 12 * 4);
+    PM_WS(ctx, dcounts, int32_t *, WS_COUNTS, (size_t)nh * per * 4);
+    PM_WS(ctx, dkey, uint64_t *, WS_KEY, 64);
+    PM_WS(ctx, dmask, uint8_t *, WS_MASK, (size_t)n);
+    PM_WS(ctx, dFout, double *, WS_FOUT, 16 * 8);
+    float *dFw = dF32 + (size_t)nh * per * 12;
+    int32_t *dninl = reinterpret_cast<int32_t *>(dkey + 2);
+    H2D(ctx, dp1, p1, (size_t)n * 8);
+    H2D(ctx, dp2, p2, (size_t)n * 8);
+    std::vector<int32_t> gen;
+    const int32_t *hs = prm->sample_idx;
+    if (!hs) {
+        gen.resize((size_t)nh * m);
+        pm_make_sample_sets(n, nh, m, prm->seed, gen.data());
+        hs = gen.data();
+    }
+    H2D(ctx, ds, hs, (size_t)nh * m * 4);
+    if (!prm->sample_idx) PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // gen goes out of scope later; keep simple
+    int st;
+    if ((st = pmk_ransac_solve(ctx, dp1, dp2, n, ds, nh, m, dF32)) != PM_OK) return st;
+    if ((st = pmk_ransac_score(ctx, dp1, dp2, n, dF32, nh * per, prm->threshold, prm->metric, dcounts)) != PM_OK) return st;
+    if ((st = pmk_ransac_best(ctx, dcounts, nh * per, 0, dkey)) != PM_OK) return st;
+    if ((st = pmk_ransac_pick(ctx, dkey, dF32, 0, nh * per, dFw)) != PM_OK) return st;
+    if ((st = pmk_ransac_finish(ctx, dp1, dp2, n, dFw, prm->threshold, prm->metric, prm->refit, dFout, dmask, dninl)) != PM_OK) return st;
+    D2H(ctx, ctx->h_pinned, dkey, 32);
+    D2H(ctx, ctx->h_pinned + 16, dFout, 72);
+    PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint64_t key = *reinterpret_cast<const uint64_t *>(ctx->h_pinned);
+    if (key == 0) return PM_EMPTY;
+    memcpy(F, ctx->h_pinned + 16, 72);
+    if (n_inliers) *n_inliers = ctx->h_pinned[4];
+    if (mask) { D2H(ctx, mask, dmask, (size_t)n); PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); }
+    return PM_OK;
+}
+
+int pm_fundamental_8point(pm_ctx *ctx, const float *p1, const float *p2, int n, double F[9])
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, p1 && p2 && F && n >= 0, "bad argument");
+    if (n < 8) return PM_EMPTY;
+    PM_CUDA(ctx, cudaSetDevice(ctx->device));
+    PM_WS(ctx, dp1, float *, WS_P1, (size_t)n * 8);
+    PM_WS(ctx, dp2, float *, WS_P2, (size_t)n * 8);
+    PM_WS(ctx, dFout, double *, WS_FOUT, 16 * 8);
+    int32_t *dok = reinterpret_cast<int32_t *>(dFout + 12);
+    H2D(ctx, dp1, p1, (size_t)n * 8);
+    H2D(ctx, dp2, p2, (size_t)n * 8);
+    int st = pmk_fundamental_npoint(ctx, dp1, dp2, n, nullptr, dFout, dok);
+    if (st != PM_OK) return st;
+    D2H(ctx, ctx->h_pinned, dFout, 13 * 8);
+    PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_pinned[24] == 0) return PM_EMPTY;
+    memcpy(F, ctx->h_pinned, 72);
+    return PM_OK;
+}
+
+int pm_epilines(pm_ctx *ctx, const float *pts, int n, int which, const double F[9], float *lines)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, n >= 0 && (which == 1 || which == 2) && F, "bad argument");
+    if (n == 0) return PM_OK;
+    PM_CUDA(ctx, cudaSetDevice(ctx->device));
+    PM_WS(ctx, dp, float *, WS_P1, (size_t)n * 8);
+    PM_WS(ctx, dF, double *, WS_FOUT, 16 * 8);
+    PM_WS(ctx, dl, float *, WS_LINES, (size_t)n * 12);
+    H2D(ctx, dp, pts, (size_t)n * 8);
+    memcpy(ctx->h_pinned, F, 72);
+    H2D(ctx, dF, ctx->h_pinned, 72);
+    int st = pmk_epilines(ctx, dp, n, which, dF, dl);
+    if (st != PM_OK) return st;
+    D2H(ctx, lines, dl, (size_t)n * 12);
+    PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PM_OK;
+}
+
+int pm_residuals(pm_ctx *ctx, const float *p1, const float *p2, int n, const double F[9], int metric, float *out, double *mean_out)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, n >= 0 && F && (metric == PM_METRIC_SAMPSON || metric == PM_METRIC_SYMEPI), "bad argument");
+    if (mean_out) *mean_out = 0;
+    if (n == 0) return PM_OK;
+    PM_CUDA(ctx, cudaSetDevice(ctx->device));
+    PM_WS(ctx, dp1, float *, WS_P1, (size_t)n * 8);
+    PM_WS(ctx, dp2, float *, WS_P2, (size_t)n * 8);
+    PM_WS(ctx, dF, double *, WS_FOUT, 16 * 8);
+    PM_WS(ctx, dl, float *, WS_LINES, (size_t)n * 12);
+    H2D(ctx, dp1, p1, (size_t)n * 8);
+    H2D(ctx, dp2, p2, (size_t)n * 8);
+    memcpy(ctx->h_pinned, F, 72);
+    H2D(ctx, dF, ctx->h_pinned, 72);
+    int st = pmk_residuals(ctx, dp1, dp2, n, dF, metric, dl, dF + 10);
+    if (st != PM_OK) return st;
+    if (out) D2H(ctx, out, dl, (size_t)n * 4);
+    D2H(ctx, ctx->h_pinned + 32, dF + 10, 8);
+    PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (mean_out) *mean_out = *reinterpret_cast<const double *>(ctx->h_pinned + 32) / n;
+    return PM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+// pm_internal.h -- shared internals of libpm (context, workspace arena, launch helpers).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/pm.h"
+
+#define PM_NSLOTS 32
+
+// Workspace slots (one growable device buffer each).
+enum pm_slot {
+    WS_Q_RAW = 0, WS_T_RAW, WS_OUT, WS_OUT2, WS_COUNT,
+    WS_Q_PACK, WS_T_PACK, WS_Q_NORM, WS_T_NORM, WS_L2_PART, WS_L2_FLAGS, WS_L2_FLAGGED,
+    WS_HAM_Q, WS_HAM_T, WS_HAM_PART, WS_COLBEST,
+    WS_P1, WS_P2, WS_SAMPLES, WS_F32, WS_COUNTS, WS_KEY, WS_MASK, WS_FOUT, WS_REFIT, WS_MISC,
+    WS_KNN, WS_KNN2, WS_IDX, WS_KP, WS_LINES
+};
+
+struct pm_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    void *slot_ptr[PM_NSLOTS] = {};
+    size_t slot_bytes[PM_NSLOTS] = {};
+    uint64_t launches = 0;
+    std::string err;
+    int32_t l2_stats[4] = {0, 0, 0, 0};
+    void *tmap_encode = nullptr;   // cuTensorMapEncodeTiled entry point
+    int32_t *h_pinned = nullptr;   // 4 KB pinned scratch for small D2H reads
+};
+
+int pm_fail(pm_ctx *ctx, int status, const char *fmt, ...);
+void *pm_ws(pm_ctx *ctx, int slot, size_t bytes);   // nullptr on failure (ctx->err set)
+
+#define PM_CUDA(ctx, call)                                                              \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess)                                                         \
+            return pm_fail(ctx, PM_CUDA_ERR, "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+                           cudaGetErrorString(e__));                                    \
+    } while (0)
+
+#define PM_CHECK_LAUNCH(ctx)                                                            \
+    do {                                                                                \
+        (ctx)->launches++;                                                              \
+        cudaError_t e__ = cudaGetLastError();                                           \
+        if (e__ != cudaSuccess)                                                         \
+            return pm_fail(ctx, PM_CUDA_ERR, "%s:%d launch: %s", __FILE__, __LINE__,    \
+                           cudaGetErrorString(e__));                                    \
+    } while (0)
+
+#define PM_WS(ctx, var, type, slot, bytes)                                              \
+    type var = (type)pm_ws(ctx, slot, bytes);                                           \
+    if (!var) return PM_CUDA_ERR
+
+static inline int pm_cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int pm_round_up(int a, int b) { return pm_cdiv(a, b) * b; }
+
+// ---- kernels-by-file entry points (host launchers) --------------------------------
+// hamming.cu
+int pmk_hamming_knn2(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, int bytes,
+                     int q_index_base, pm_dmatch *dout);
+int pmk_hamming_col_best(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, int bytes,
+                         int q_index_base, uint64_t *dcol_best);
+// filter.cu
+int pmk_ratio_filter(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout,
+                     int32_t *dn_out);
+int pmk_cross_check(pm_ctx *ctx, const pm_dmatch *dknn, int nq, int stride, const uint64_t *dcol_best,
+                    int nt, pm_dmatch *dout, int32_t *dn_out);
+int pmk_minmax_filter(pm_ctx *ctx, const pm_dmatch *dm, int n, int stride, pm_dmatch *dout,
+                      int32_t *dn_out, double *dminmax);
+int pmk_gather_points(pm_ctx *ctx, const float *dkp, int nkp, const int32_t *didx, int n, float *dout);
+int pmk_gather_matches(pm_ctx *ctx, const pm_dmatch *dm, const int32_t *dn, int max_matches,
+                       const float *dkp1, int nkp1, const float *dkp2, int nkp2, float *dp1, float *dp2);
+// l2.cu / l2_tc.cu
+int pmk_l2_knn2(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
+                int q_index_base, pm_dmatch *dout);
+int pmk_l2_col_best(pm_ctx *ctx, const float *dq, int nq, const float *dt, int nt, int dim,
+                    int q_index_base, uint64_t *dcol_best);
+// ransac.cu
+int pmk_ransac_solve(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const int32_t *dsamples,
+                     int n_hyp, int m, float *dF32);
+int pmk_ransac_score(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dF32,
+                     int n_models, float thr, int metric, int32_t *dcounts);
+int pmk_ransac_best(pm_ctx *ctx, const int32_t *dcounts, int n_models, int id_base, uint64_t *dkey);
+int pmk_ransac_finish(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dFw,
+                      float thr, int metric, int refit, double *dF, uint8_t *dmask, int32_t *dn_inl);
+int pmk_fundamental_npoint(pm_ctx *ctx, const float *dp1, const float *dp2, int n,
+                           const uint8_t *dmask_or_null, double *dF, int32_t *dok);
+int pmk_epilines(pm_ctx *ctx, const float *dpts, int n, int which, const double *dF, float *dlines);
+int pmk_residuals(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const double *dF, int metric,
+                  float *dout, double *dsum);

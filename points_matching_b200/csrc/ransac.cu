@@ -1,0 +1,826 @@
+// ransac.cu -- K6/K7/K8: RANSAC fundamental-matrix estimation for sm_100a, plus the
+// epipolar diagnostics.
+//
+// Replaces cv::findFundamentalMat (/root/reference/Points Matching/main.cpp:95-98) --
+// CvFMEstimator run8Point / run7Point, computeReprojError + findInliers, model
+// selection -- cv::computeCorrespondEpilines (main.cpp:127-132) and the residual loop
+// at main.cpp:103-123 (in the correct convention x2^T F x1).
+//
+//   K6 solve : 8 lanes per hypothesis (4 hypotheses per warp).  Lane j holds the j-th
+//              sample's 9-vector; Householder QR of the 9x8 (9x7) matrix across lanes via
+//              width-8 shuffles; null vector(s) = Q e9 (Q e8, Q e9); rank-2 projection by
+//              a 3x3 one-sided Jacobi; all in registers, FP64 (the solve is <2% of the
+//              work, and FP64 keeps F within ~1e-12 of OpenCV's double-precision path).
+//   K7 score : all-pairs (model, point) -> FP32-issue bound, not HBM bound.  Each thread
+//              owns 4 models (36 coefficient registers), the CTA streams the packed
+//              correspondences through a double-buffered shared-memory tile and reads
+//              them with broadcast LDS.128; counts stay private -> no reduction in the
+//              hot loop.  Arithmetic is the fixed FP32 order of DESIGN.md "scoring op
+//              order" (explicit fmaf), bit-exact against the oracle.
+//   K8 finish: winner's mask + count, N-point normalised 8-point refit on the inliers
+//              (deterministic two-level FP64 reductions, 9x9 Jacobi on one warp).
+#include <cfloat>
+#include "pm_internal.h"
+
+namespace {
+
+// =====================================================================================
+// small FP64 helpers (register resident)
+// =====================================================================================
+__device__ __forceinline__ double grp_sum8(double v)
+{
+    v += __shfl_xor_sync(0xffffffffu, v, 4, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 2, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 1, 8);
+    return v;
+}
+
+// One-sided Jacobi on a 3x3 (columns rotated until orthogonal), then drop the column of
+// smallest norm: F <- rank-2 projection (OpenCV run8Point "make F0 singular").
+__device__ void rank2_project3(double (&F)[9])
+{
+    double A[9], V[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { A[i] = F[i]; V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        bool changed = false;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+            double a = 0, b = 0, g = 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { a += A[k * 3 + p] * A[k * 3 + p]; b += A[k * 3 + q] * A[k * 3 + q]; g += A[k * 3 + p] * A[k * 3 + q]; }
+            if (g == 0.0 || fabs(g) <= 1e-17 * sqrt(a * b)) continue;
+            changed = true;
+            const double zeta = (b - a) / (2 * g);
+            const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1 + zeta * zeta));
+            const double c = 1 / sqrt(1 + tt * tt), s = c * tt;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                double x = A[k * 3 + p], y = A[k * 3 + q];
+                A[k * 3 + p] = c * x - s * y; A[k * 3 + q] = s * x + c * y;
+                x = V[k * 3 + p]; y = V[k * 3 + q];
+                V[k * 3 + p] = c * x - s * y; V[k * 3 + q] = s * x + c * y;
+            }
+        }
+        if (!changed) break;
+    }
+    double nrm[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) nrm[j] = A[j] * A[j] + A[3 + j] * A[3 + j] + A[6 + j] * A[6 + j];
+    const int drop = (nrm[0] <= nrm[1] && nrm[0] <= nrm[2]) ? 0 : (nrm[1] <= nrm[2] ? 1 : 2);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double v = 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (k != drop) v += A[i * 3 + k] * V[j * 3 + k];
+            F[i * 3 + j] = v;
+        }
+}
+
+// cv::solveCubic restatement (c0 x^3 + c1 x^2 + c2 x + c3 = 0); returns the root count.
+__device__ int solve_cubic(const double (&c)[4], double (&r)[3])
+{
+    const double PI = 3.1415926535897932384626433832795;
+    double a0 = c[0], a1 = c[1], a2 = c[2], a3 = c[3];
+    double x0 = 0, x1 = 0, x2 = 0;
+    int n = 0;
+    if (a0 == 0) {
+        if (a1 == 0) {
+            if (a2 == 0) n = a3 == 0 ? -1 : 0;
+            else { x0 = -a3 / a2; n = 1; }
+        } else {
+            double d = a2 * a2 - 4 * a1 * a3;
+            if (d >= 0) {
+                d = sqrt(d);
+                const double q1 = (-a2 + d) * 0.5, q2 = (a2 + d) * -0.5;
+                if (fabs(q1) > fabs(q2)) { x0 = q1 / a1; x1 = a3 / q1; }
+                else { x0 = q2 / a1; x1 = a3 / q2; }
+                n = d > 0 ? 2 : 1;
+            }
+        }
+    } else {
+        a0 = 1. / a0; a1 *= a0; a2 *= a0; a3 *= a0;
+        const double Q = (a1 * a1 - 3 * a2) * (1. / 9);
+        const double R = (2 * a1 * a1 * a1 - 9 * a1 * a2 + 27 * a3) * (1. / 54);
+        const double Qcubed = Q * Q * Q;
+        double d = Qcubed - R * R;
+        if (d > 0) {
+            const double theta = acos(R / sqrt(Qcubed));
+            const double sqrtQ = sqrt(Q);
+            const double t0 = -2 * sqrtQ, t1 = theta * (1. / 3), t2 = a1 * (1. / 3);
+            x0 = t0 * cos(t1) - t2;
+            x1 = t0 * cos(t1 + (2. * PI / 3)) - t2;
+            x2 = t0 * cos(t1 + (4. * PI / 3)) - t2;
+            n = 3;
+        } else if (d == 0) {
+            if (R >= 0) { x0 = -2 * pow(R, 1. / 3) - a1 / 3; x1 = pow(R, 1. / 3) - a1 / 3; }
+            else { x0 = 2 * pow(-R, 1. / 3) - a1 / 3; x1 = -pow(-R, 1. / 3) - a1 / 3; }
+            x2 = 0;
+            n = x0 == x1 ? 1 : 2;
+            x1 = x0 == x1 ? 0 : x1;
+        } else {
+            d = sqrt(-d);
+            double e = pow(d + fabs(R), 1. / 3);
+            if (R > 0) e = -e;
+            x0 = (e + Q / e) - a1 * (1. / 3);
+            n = 1;
+        }
+    }
+    r[0] = x0; r[1] = x1; r[2] = x2;
+    return n;
+}
+
+__device__ __forceinline__ void store_model(float *dst, const double (&F)[9], bool valid)
+{
+#pragma unroll
+    for (int i = 0; i < 9; ++i) dst[i] = valid ? (float)F[i] : __int_as_float(0x7fc00000);
+    dst[9] = dst[10] = dst[11] = 0.f;
+}
+
+// =====================================================================================
+// K6: minimal solvers, 8 lanes per hypothesis
+// =====================================================================================
+template <int M>
+__global__ void __launch_bounds__(128)
+ransac_solve_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2, int n,
+                    const int32_t *__restrict__ samples, int n_hyp, float *__restrict__ Fout)
+{
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int h = gtid >> 3, sub = threadIdx.x & 7;
+    const bool live = h < n_hyp;
+    const bool has_pt = live && sub < M;
+    double x1 = 0, y1 = 0, x2 = 0, y2 = 0;
+    if (has_pt) {
+        int k = samples[(size_t)h * M + sub];
+        k = min(max(k, 0), n - 1);
+        const float2 a = p1[k], b = p2[k];
+        x1 = a.x; y1 = a.y; x2 = b.x; y2 = b.y;
+    }
+    bool valid = true;
+    double c1x = 0, c1y = 0, c2x = 0, c2y = 0, s1 = 1, s2 = 1;
+    if (M == 8) {
+        // Hartley normalisation: centroid to origin, mean distance sqrt(2)
+        c1x = grp_sum8(x1) * 0.125; c1y = grp_sum8(y1) * 0.125;
+        c2x = grp_sum8(x2) * 0.125; c2y = grp_sum8(y2) * 0.125;
+        double d1 = sqrt((x1 - c1x) * (x1 - c1x) + (y1 - c1y) * (y1 - c1y));
+        double d2 = sqrt((x2 - c2x) * (x2 - c2x) + (y2 - c2y) * (y2 - c2y));
+        d1 = grp_sum8(d1) * 0.125; d2 = grp_sum8(d2) * 0.125;
+        if (d1 < FLT_EPSILON || d2 < FLT_EPSILON) valid = false;
+        s1 = sqrt(2.) / d1; s2 = sqrt(2.) / d2;
+        x1 = (x1 - c1x) * s1; y1 = (y1 - c1y) * s1;
+        x2 = (x2 - c2x) * s2; y2 = (y2 - c2y) * s2;
+    }
+    // column `sub` of the 9 x M matrix = this sample's epipolar constraint row
+    double c[9] = {x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, 1.0};
+    if (sub >= M) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) c[i] = 0;
+    }
+    // Householder QR across lanes; lane k keeps its reflector w (entries k..8) and beta
+    double w[9], beta = 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) w[i] = 0;
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        double v[9];
+        double nrm2 = 0;
+#pragma unroll
+        for (int i = k; i < 9; ++i) nrm2 += c[i] * c[i];
+        const double alpha = c[k] >= 0 ? -sqrt(nrm2) : sqrt(nrm2);
+#pragma unroll
+        for (int i = k; i < 9; ++i) v[i] = c[i];
+        v[k] -= alpha;
+        double vtv = 0;
+#pragma unroll
+        for (int i = k; i < 9; ++i) vtv += v[i] * v[i];
+        double b = vtv > 0 ? 2.0 / vtv : 0.0;
+        // broadcast lane k's reflector to its group
+#pragma unroll
+        for (int i = k; i < 9; ++i) v[i] = __shfl_sync(0xffffffffu, v[i], k, 8);
+        b = __shfl_sync(0xffffffffu, b, k, 8);
+        if (sub == k) {
+#pragma unroll
+            for (int i = k; i < 9; ++i) w[i] = v[i];
+            beta = b;
+        }
+        double s = 0;
+#pragma unroll
+        for (int i = k; i < 9; ++i) s += v[i] * c[i];
+        s *= b;
+#pragma unroll
+        for (int i = k; i < 9; ++i) c[i] -= s * v[i];
+    }
+    // null-space basis: z = Q e_j = H_0 H_1 ... H_{M-1} e_j, j = 8 (and 7 for the 7-point)
+    double z[9], z2[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { z[i] = i == 8 ? 1.0 : 0.0; z2[i] = i == 7 ? 1.0 : 0.0; }
+#pragma unroll
+    for (int k = M - 1; k >= 0; --k) {
+        double v[9];
+#pragma unroll
+        for (int i = k; i < 9; ++i) v[i] = __shfl_sync(0xffffffffu, w[i], k, 8);
+        const double b = __shfl_sync(0xffffffffu, beta, k, 8);
+        double s = 0, t = 0;
+#pragma unroll
+        for (int i = k; i < 9; ++i) { s += v[i] * z[i]; t += v[i] * z2[i]; }
+        s *= b; t *= b;
+#pragma unroll
+        for (int i = k; i < 9; ++i) { z[i] -= s * v[i]; if (M == 7) z2[i] -= t * v[i]; }
+    }
+    if (!live || sub != 0) return;
+
+    if (M == 8) {
+        double F0[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) F0[i] = z[i];
+        rank2_project3(F0);
+        // F = T2^T F0 T1, T = [s 0 -s cx; 0 s -s cy; 0 0 1]
+        double Mx[9];
+        Mx[0] = s2 * F0[0]; Mx[1] = s2 * F0[1]; Mx[2] = s2 * F0[2];
+        Mx[3] = s2 * F0[3]; Mx[4] = s2 * F0[4]; Mx[5] = s2 * F0[5];
+        Mx[6] = -s2 * c2x * F0[0] - s2 * c2y * F0[3] + F0[6];
+        Mx[7] = -s2 * c2x * F0[1] - s2 * c2y * F0[4] + F0[7];
+        Mx[8] = -s2 * c2x * F0[2] - s2 * c2y * F0[5] + F0[8];
+        double F[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            F[i * 3 + 0] = Mx[i * 3 + 0] * s1;
+            F[i * 3 + 1] = Mx[i * 3 + 1] * s1;
+            F[i * 3 + 2] = -Mx[i * 3 + 0] * s1 * c1x - Mx[i * 3 + 1] * s1 * c1y + Mx[i * 3 + 2];
+        }
+        if (fabs(F[8]) > FLT_EPSILON) {
+            const double inv = 1.0 / F[8];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) F[i] *= inv;
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) valid = valid && isfinite(F[i]);
+        store_model(Fout + (size_t)h * 12, F, valid);
+    } else {
+        // 7-point: det(lambda*f1 + (1-lambda)*f2) = 0  (OpenCV run7Point)
+        double f1[9], f2[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { f1[i] = z2[i]; f2[i] = z[i]; f1[i] -= f2[i]; }
+        double cc[4], t0, t1, t2;
+        t0 = f2[4] * f2[8] - f2[5] * f2[7];
+        t1 = f2[3] * f2[8] - f2[5] * f2[6];
+        t2 = f2[3] * f2[7] - f2[4] * f2[6];
+        cc[3] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2;
+        cc[2] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2 -
+                f1[3] * (f2[1] * f2[8] - f2[2] * f2[7]) +
+                f1[4] * (f2[0] * f2[8] - f2[2] * f2[6]) -
+                f1[5] * (f2[0] * f2[7] - f2[1] * f2[6]) +
+                f1[6] * (f2[1] * f2[5] - f2[2] * f2[4]) -
+                f1[7] * (f2[0] * f2[5] - f2[2] * f2[3]) +
+                f1[8] * (f2[0] * f2[4] - f2[1] * f2[3]);
+        t0 = f1[4] * f1[8] - f1[5] * f1[7];
+        t1 = f1[3] * f1[8] - f1[5] * f1[6];
+        t2 = f1[3] * f1[7] - f1[4] * f1[6];
+        cc[1] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2 -
+                f2[3] * (f1[1] * f1[8] - f1[2] * f1[7]) +
+                f2[4] * (f1[0] * f1[8] - f1[2] * f1[6]) -
+                f2[5] * (f1[0] * f1[7] - f1[1] * f1[6]) +
+                f2[6] * (f1[1] * f1[5] - f1[2] * f1[4]) -
+                f2[7] * (f1[0] * f1[5] - f1[2] * f1[3]) +
+                f2[8] * (f1[0] * f1[4] - f1[1] * f1[3]);
+        cc[0] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2;
+        double r[3];
+        int nr = solve_cubic(cc, r);
+        if (nr < 1 || nr > 3) nr = 0;
+        for (int k = 0; k < 3; ++k) {
+            double F[9];
+            bool ok = k < nr;
+            if (ok) {
+                double lambda = r[k], mu = 1;
+                const double sc = f1[8] * r[k] + f2[8];
+                if (fabs(sc) > DBL_EPSILON) { mu = 1. / sc; lambda *= mu; F[8] = 1; }
+                else F[8] = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) F[i] = f1[i] * lambda + f2[i] * mu;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) ok = ok && isfinite(F[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) F[i] = 0;
+            }
+            store_model(Fout + ((size_t)h * 3 + k) * 12, F, ok);
+        }
+    }
+}
+
+// =====================================================================================
+// K7: scoring
+// =====================================================================================
+constexpr int SC_THREADS = 128;
+constexpr int SC_MPT = 4;          // models per thread
+constexpr int SC_TILE = 512;       // correspondences per shared-memory tile (8 KB)
+
+__global__ void pack_points_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2, int n,
+                                   float4 *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float2 a = p1[i], b = p2[i];
+    out[i] = make_float4(a.x, a.y, b.x, b.y);
+}
+
+// The FP32 inlier test, operation for operation (DESIGN.md "scoring op order").
+template <int METRIC>
+__device__ __forceinline__ bool is_inlier(const float (&F)[9], const float4 p, const float thr2)
+{
+    const float a = fmaf(F[0], p.x, fmaf(F[1], p.y, F[2]));
+    const float b = fmaf(F[3], p.x, fmaf(F[4], p.y, F[5]));
+    const float c = fmaf(F[6], p.x, fmaf(F[7], p.y, F[8]));
+    const float r = fmaf(p.z, a, fmaf(p.w, b, c));
+    const float at = fmaf(F[0], p.z, fmaf(F[3], p.w, F[6]));
+    const float bt = fmaf(F[1], p.z, fmaf(F[4], p.w, F[7]));
+    const float r2 = __fmul_rn(r, r);
+    if (METRIC == PM_METRIC_SAMPSON) {
+        const float den = fmaf(a, a, fmaf(b, b, fmaf(at, at, __fmul_rn(bt, bt))));
+        return r2 <= __fmul_rn(thr2, den);
+    } else {
+        const float n2 = fmaf(a, a, __fmul_rn(b, b));
+        const float n1 = fmaf(at, at, __fmul_rn(bt, bt));
+        return (r2 <= __fmul_rn(thr2, n2)) && (r2 <= __fmul_rn(thr2, n1));
+    }
+}
+
+__device__ __forceinline__ void sc_cp_async16(void *smem, const void *gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(SC_THREADS)
+ransac_score_kernel(const float4 *__restrict__ pts, int n, int chunk_pts, const float *__restrict__ Fm,
+                    int n_models, float thr2, int32_t *__restrict__ counts, int use_atomic)
+{
+    __shared__ __align__(16) float4 tile[2][SC_TILE];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * (SC_THREADS * SC_MPT);
+    float F[SC_MPT][9];
+#pragma unroll
+    for (int r = 0; r < SC_MPT; ++r) {
+        const int m = m0 + r * SC_THREADS + tid;
+        const float4 *src = reinterpret_cast<const float4 *>(Fm + (size_t)min(m, n_models - 1) * 12);
+        const float4 u = __ldg(src), v = __ldg(src + 1), w = __ldg(src + 2);
+        F[r][0] = u.x; F[r][1] = u.y; F[r][2] = u.z; F[r][3] = u.w;
+        F[r][4] = v.x; F[r][5] = v.y; F[r][6] = v.z; F[r][7] = v.w; F[r][8] = w.x;
+    }
+    int cnt[SC_MPT];
+#pragma unroll
+    for (int r = 0; r < SC_MPT; ++r) cnt[r] = 0;
+
+    const int p0 = blockIdx.y * chunk_pts, p1 = min(n, p0 + chunk_pts);
+    const int ntiles = (p1 - p0 + SC_TILE - 1) / SC_TILE;
+    auto load_tile = [&](int ti, int buf) {
+        const int b = p0 + ti * SC_TILE;
+        const int cntp = min(SC_TILE, p1 - b);
+        for (int v = tid; v < cntp; v += SC_THREADS) sc_cp_async16(&tile[buf][v], pts + b + v);
+        asm volatile("cp.async.commit_group;");
+    };
+    if (ntiles > 0) load_tile(0, 0);
+    for (int ti = 0; ti < ntiles; ++ti) {
+        const int buf = ti & 1;
+        if (ti + 1 < ntiles) { load_tile(ti + 1, buf ^ 1); asm volatile("cp.async.wait_group 1;"); }
+        else asm volatile("cp.async.wait_group 0;");
+        __syncthreads();
+        const int cntp = min(SC_TILE, p1 - (p0 + ti * SC_TILE));
+#pragma unroll 4
+        for (int j = 0; j < cntp; ++j) {
+            const float4 p = tile[buf][j];
+#pragma unroll
+            for (int r = 0; r < SC_MPT; ++r) cnt[r] += is_inlier<METRIC>(F[r], p, thr2) ? 1 : 0;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < SC_MPT; ++r) {
+        const int m = m0 + r * SC_THREADS + tid;
+        if (m < n_models) {
+            if (use_atomic) atomicAdd(&counts[m], cnt[r]);
+            else counts[m] = cnt[r];
+        }
+    }
+}
+
+// key = count << 32 | (0xFFFFFFFF - model_id): max key = max count, lowest id on ties
+__global__ void __launch_bounds__(256)
+ransac_best_kernel(const int32_t *__restrict__ counts, int n_models, int id_base, unsigned long long *key)
+{
+    unsigned long long best = 0;
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n_models; m += gridDim.x * blockDim.x) {
+        const int c = counts[m];
+        if (c > 0) {
+            const unsigned long long k = ((unsigned long long)(unsigned)c << 32) | (0xFFFFFFFFu - (unsigned)(id_base + m));
+            best = k > best ? k : best;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long y = __shfl_xor_sync(0xffffffffu, best, o);
+        best = y > best ? y : best;
+    }
+    if ((threadIdx.x & 31) == 0 && best) atomicMax(key, best);
+}
+
+__global__ void ransac_pick_kernel(const unsigned long long *key, const float *__restrict__ Fm, int id_base,
+                                   int n_models, float *Fw)
+{
+    const int i = threadIdx.x;
+    if (i >= 12) return;
+    const unsigned long long k = *key;
+    const long long m = (long long)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFu)) - id_base;
+    Fw[i] = (k != 0 && m >= 0 && m < n_models) ? Fm[(size_t)m * 12 + i] : __int_as_float(0x7fc00000);
+}
+
+// =====================================================================================
+// K8: mask + refit
+// =====================================================================================
+template <int METRIC>
+__global__ void __launch_bounds__(256)
+ransac_mask_kernel(const float4 *__restrict__ pts, int n, const float *__restrict__ Fw, float thr2,
+                   uint8_t *__restrict__ mask, int32_t *n_inl)
+{
+    float F[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) F[i] = Fw[i];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool in = false;
+    if (i < n) { in = is_inlier<METRIC>(F, pts[i], thr2); mask[i] = in ? 1 : 0; }
+    const int c = __syncthreads_count(in);
+    if (threadIdx.x == 0 && c) atomicAdd(n_inl, c);
+}
+
+constexpr int RF_BLOCKS = 64;      // fixed grid -> deterministic two-level reductions
+constexpr int RF_THREADS = 256;
+
+template <int NV>
+__device__ void block_reduce_store(double (&v)[NV], double *dst)
+{
+    __shared__ double sh[RF_THREADS / 32][NV];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) sh[w][k] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0;
+        for (int ww = 0; ww < RF_THREADS / 32; ++ww) s += sh[ww][threadIdx.x];
+        dst[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+// pass 1: sums of x1,y1,x2,y2 and the count over the selected points
+__global__ void __launch_bounds__(RF_THREADS)
+refit_sum_kernel(const float4 *__restrict__ pts, int n, const uint8_t *__restrict__ mask, double *partial)
+{
+    double v[5] = {0, 0, 0, 0, 0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (!mask || mask[i]) { const float4 p = pts[i]; v[0] += p.x; v[1] += p.y; v[2] += p.z; v[3] += p.w; v[4] += 1.0; }
+    block_reduce_store<5>(v, partial + blockIdx.x * 5);
+}
+// stats: [0..3] centroid, [4] count, [5] s1, [6] s2
+__global__ void refit_mean_kernel(const double *partial, double *stats)
+{
+    if (threadIdx.x != 0) return;
+    double s[5] = {0, 0, 0, 0, 0};
+    for (int b = 0; b < RF_BLOCKS; ++b)
+        for (int k = 0; k < 5; ++k) s[k] += partial[b * 5 + k];
+    const double inv = s[4] > 0 ? 1.0 / s[4] : 0.0;
+    for (int k = 0; k < 4; ++k) stats[k] = s[k] * inv;
+    stats[4] = s[4];
+}
+// pass 2: mean distances to the centroids
+__global__ void __launch_bounds__(RF_THREADS)
+refit_scale_kernel(const float4 *__restrict__ pts, int n, const uint8_t *__restrict__ mask,
+                   const double *__restrict__ stats, double *partial)
+{
+    const double c1x = stats[0], c1y = stats[1], c2x = stats[2], c2y = stats[3];
+    double v[2] = {0, 0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (!mask || mask[i]) {
+            const float4 p = pts[i];
+            v[0] += sqrt((p.x - c1x) * (p.x - c1x) + (p.y - c1y) * (p.y - c1y));
+            v[1] += sqrt((p.z - c2x) * (p.z - c2x) + (p.w - c2y) * (p.w - c2y));
+        }
+    block_reduce_store<2>(v, partial + blockIdx.x * 2);
+}
+__global__ void refit_scale_final_kernel(const double *partial, double *stats)
+{
+    if (threadIdx.x != 0) return;
+    double a = 0, b = 0;
+    for (int k = 0; k < RF_BLOCKS; ++k) { a += partial[k * 2]; b += partial[k * 2 + 1]; }
+    const double cnt = stats[4];
+    a = cnt > 0 ? a / cnt : 0; b = cnt > 0 ? b / cnt : 0;
+    stats[5] = a >= FLT_EPSILON ? sqrt(2.) / a : 0.0;
+    stats[6] = b >= FLT_EPSILON ? sqrt(2.) / b : 0.0;
+}
+// pass 3: upper triangle of the 9x9 normal matrix sum r r^T (45 entries)
+__global__ void __launch_bounds__(RF_THREADS)
+refit_ata_kernel(const float4 *__restrict__ pts, int n, const uint8_t *__restrict__ mask,
+                 const double *__restrict__ stats, double *partial)
+{
+    const double c1x = stats[0], c1y = stats[1], c2x = stats[2], c2y = stats[3], s1 = stats[5], s2 = stats[6];
+    double acc[45];
+#pragma unroll
+    for (int k = 0; k < 45; ++k) acc[k] = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (!mask || mask[i]) {
+            const float4 p = pts[i];
+            const double x1 = (p.x - c1x) * s1, y1 = (p.y - c1y) * s1, x2 = (p.z - c2x) * s2, y2 = (p.w - c2y) * s2;
+            const double r[9] = {x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, 1.0};
+            int k = 0;
+#pragma unroll
+            for (int a = 0; a < 9; ++a)
+#pragma unroll
+                for (int b = a; b < 9; ++b) acc[k++] += r[a] * r[b];
+        }
+    block_reduce_store<45>(acc, partial + blockIdx.x * 45);
+}
+
+// pass 4 (one warp): 9x9 cyclic Jacobi (lanes 0..8 each own index k of the rotation
+// updates), smallest eigenvector, rank-2 projection, de-normalisation.  Falls back to the
+// winning minimal model when there are < 8 points or the system is degenerate.
+__global__ void __launch_bounds__(32)
+refit_solve_kernel(const double *__restrict__ partial, const double *__restrict__ stats,
+                   const float *__restrict__ Ffallback, double *__restrict__ Fout, int32_t *ok_out)
+{
+    __shared__ double A[81], V[81];
+    const int lane = threadIdx.x;
+    for (int e = lane; e < 81; e += 32) { A[e] = 0; V[e] = (e % 10 == 0) ? 1.0 : 0.0; }
+    __syncwarp();
+    if (lane == 0) {
+        int k = 0;
+        for (int a = 0; a < 9; ++a)
+            for (int b = a; b < 9; ++b, ++k) {
+                double s = 0;
+                for (int blk = 0; blk < RF_BLOCKS; ++blk) s += partial[blk * 45 + k];
+                A[a * 9 + b] = s; A[b * 9 + a] = s;
+            }
+    }
+    __syncwarp();
+    const double cnt = stats[4], s1 = stats[5], s2 = stats[6];
+    bool ok = cnt >= 8 && s1 > 0 && s2 > 0;
+    for (int sweep = 0; sweep < 60 && ok; ++sweep) {
+        double off = 0, diag = 0;
+        for (int i = 0; i < 9; ++i) {
+            diag += A[i * 9 + i] * A[i * 9 + i];
+            for (int j = i + 1; j < 9; ++j) off += A[i * 9 + j] * A[i * 9 + j];
+        }
+        if (off <= 1e-34 * diag || off == 0) break;
+        for (int p = 0; p < 8; ++p)
+            for (int q = p + 1; q < 9; ++q) {
+                const double apq = A[p * 9 + q];
+                if (apq == 0) continue;                       // uniform across lanes
+                const double theta = (A[q * 9 + q] - A[p * 9 + p]) / (2 * apq);
+                const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
+                const double c = 1 / sqrt(tt * tt + 1), s = tt * c;
+                __syncwarp();
+                if (lane < 9) {
+                    const int k = lane;
+                    const double akp = A[k * 9 + p], akq = A[k * 9 + q];
+                    A[k * 9 + p] = c * akp - s * akq; A[k * 9 + q] = s * akp + c * akq;
+                }
+                __syncwarp();
+                if (lane < 9) {
+                    const int k = lane;
+                    const double apk = A[p * 9 + k], aqk = A[q * 9 + k];
+                    A[p * 9 + k] = c * apk - s * aqk; A[q * 9 + k] = s * apk + c * aqk;
+                    const double vpk = V[p * 9 + k], vqk = V[q * 9 + k];
+                    V[p * 9 + k] = c * vpk - s * vqk; V[q * 9 + k] = s * vpk + c * vqk;
+                }
+                __syncwarp();
+            }
+    }
+    if (lane != 0) return;
+    double F[9];
+    if (ok) {
+        int mn = 0, nsmall = 0;
+        for (int i = 0; i < 9; ++i) {
+            if (A[i * 9 + i] < A[mn * 9 + mn]) mn = i;
+            if (fabs(A[i * 9 + i]) < DBL_EPSILON) ++nsmall;
+        }
+        if (nsmall > 1) ok = false;        // rank < 8 (OpenCV: any of the 8 largest < DBL_EPSILON)
+        double F0[9];
+        for (int i = 0; i < 9; ++i) F0[i] = V[mn * 9 + i];
+        rank2_project3(F0);
+        const double c1x = stats[0], c1y = stats[1], c2x = stats[2], c2y = stats[3];
+        double Mx[9];
+        Mx[0] = s2 * F0[0]; Mx[1] = s2 * F0[1]; Mx[2] = s2 * F0[2];
+        Mx[3] = s2 * F0[3]; Mx[4] = s2 * F0[4]; Mx[5] = s2 * F0[5];
+        Mx[6] = -s2 * c2x * F0[0] - s2 * c2y * F0[3] + F0[6];
+        Mx[7] = -s2 * c2x * F0[1] - s2 * c2y * F0[4] + F0[7];
+        Mx[8] = -s2 * c2x * F0[2] - s2 * c2y * F0[5] + F0[8];
+        for (int i = 0; i < 3; ++i) {
+            F[i * 3 + 0] = Mx[i * 3 + 0] * s1;
+            F[i * 3 + 1] = Mx[i * 3 + 1] * s1;
+            F[i * 3 + 2] = -Mx[i * 3 + 0] * s1 * c1x - Mx[i * 3 + 1] * s1 * c1y + Mx[i * 3 + 2];
+        }
+        if (fabs(F[8]) > FLT_EPSILON) { const double inv = 1.0 / F[8]; for (int i = 0; i < 9; ++i) F[i] *= inv; }
+        for (int i = 0; i < 9; ++i) ok = ok && isfinite(F[i]);
+    }
+    if (!ok && Ffallback) for (int i = 0; i < 9; ++i) F[i] = (double)Ffallback[i];
+    if (ok || Ffallback) for (int i = 0; i < 9; ++i) Fout[i] = F[i];
+    if (ok_out) *ok_out = ok ? 1 : 0;
+}
+
+__global__ void copy_f32_to_f64_kernel(const float *src, double *dst, int n)
+{
+    if ((int)threadIdx.x < n) dst[threadIdx.x] = (double)src[threadIdx.x];
+}
+
+// =====================================================================================
+// diagnostics
+// =====================================================================================
+__global__ void epilines_kernel(const float2 *__restrict__ pts, int n, int which, const double *__restrict__ Fd,
+                                float *__restrict__ lines)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double f[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) f[r * 3 + c] = which == 2 ? Fd[c * 3 + r] : Fd[r * 3 + c];
+    const double x = pts[i].x, y = pts[i].y;
+    const double a = f[0] * x + f[1] * y + f[2], b = f[3] * x + f[4] * y + f[5], c = f[6] * x + f[7] * y + f[8];
+    double nu = a * a + b * b;
+    nu = nu ? 1. / sqrt(nu) : 1.;
+    lines[3 * i] = (float)(a * nu); lines[3 * i + 1] = (float)(b * nu); lines[3 * i + 2] = (float)(c * nu);
+}
+
+__global__ void __launch_bounds__(256)
+residuals_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2, int n, const double *__restrict__ F,
+                 int metric, float *__restrict__ out, double *sum)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0;
+    if (i < n) {
+        const double x1 = p1[i].x, y1 = p1[i].y, x2 = p2[i].x, y2 = p2[i].y;
+        const double a = F[0] * x1 + F[1] * y1 + F[2], b = F[3] * x1 + F[4] * y1 + F[5], c = F[6] * x1 + F[7] * y1 + F[8];
+        const double r = x2 * a + y2 * b + c;
+        const double at = F[0] * x2 + F[3] * y2 + F[6], bt = F[1] * x2 + F[4] * y2 + F[7];
+        if (metric == PM_METRIC_SAMPSON) e = r * r / (a * a + b * b + at * at + bt * bt);
+        else { const double e2 = r * r / (a * a + b * b), e1 = r * r / (at * at + bt * bt); e = e1 > e2 ? e1 : e2; }
+        out[i] = (float)e;
+    }
+    __shared__ double sh[8];
+    double x = e;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x == 0 && sum) {
+        double s = 0;
+        for (int w = 0; w < 8; ++w) s += sh[w];
+        atomicAdd(sum, s);
+    }
+}
+
+int get_pts4(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float4 **out)
+{
+    PM_WS(ctx, pts, float4 *, WS_MISC, (size_t)(n > 0 ? n : 1) * sizeof(float4));
+    if (n > 0) {
+        pack_points_kernel<<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, pts);
+        PM_CHECK_LAUNCH(ctx);
+    }
+    *out = pts;
+    return PM_OK;
+}
+
+int run_refit(pm_ctx *ctx, const float4 *pts, int n, const uint8_t *dmask, const float *dFfallback, double *dF,
+              int32_t *dok)
+{
+    PM_WS(ctx, ws, double *, WS_REFIT, (size_t)(RF_BLOCKS * 45 + 16) * sizeof(double));
+    double *stats = ws + RF_BLOCKS * 45;
+    refit_sum_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, ws);
+    PM_CHECK_LAUNCH(ctx);
+    refit_mean_kernel<<<1, 32, 0, ctx->stream>>>(ws, stats);
+    PM_CHECK_LAUNCH(ctx);
+    refit_scale_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, stats, ws);
+    PM_CHECK_LAUNCH(ctx);
+    refit_scale_final_kernel<<<1, 32, 0, ctx->stream>>>(ws, stats);
+    PM_CHECK_LAUNCH(ctx);
+    refit_ata_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, stats, ws);
+    PM_CHECK_LAUNCH(ctx);
+    refit_solve_kernel<<<1, 32, 0, ctx->stream>>>(ws, stats, dFfallback, dF, dok);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}
+
+}  // namespace
+
+int pmk_ransac_solve(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const int32_t *dsamples, int n_hyp,
+                     int m, float *dF32)
+{
+    if (n_hyp <= 0) return PM_OK;
+    const int blocks = pm_cdiv(n_hyp * 8, 128);
+    if (m == 8)
+        ransac_solve_kernel<8><<<blocks, 128, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dsamples, n_hyp, dF32);
+    else
+        ransac_solve_kernel<7><<<blocks, 128, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dsamples, n_hyp, dF32);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}
+
+int pmk_ransac_score(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dF32, int n_models,
+                     float thr, int metric, int32_t *dcounts)
+{
+    if (n_models <= 0) return PM_OK;
+    const float4 *pts;
+    int st = get_pts4(ctx, dp1, dp2, n, &pts);
+    if (st != PM_OK) return st;
+    const int mblocks = pm_cdiv(n_models, SC_THREADS * SC_MPT);
+    // split the correspondences across blockIdx.y only when the model blocks cannot fill the GPU
+    int chunks = 1;
+    if (mblocks < 2 * ctx->num_sms && n > 4 * SC_TILE)
+        chunks = min(pm_cdiv(2 * ctx->num_sms, mblocks), pm_cdiv(n, 4 * SC_TILE));
+    int chunk_pts = pm_round_up(pm_cdiv(n > 0 ? n : 1, chunks), SC_TILE);
+    chunks = pm_cdiv(n > 0 ? n : 1, chunk_pts);
+    const int use_atomic = chunks > 1;
+    if (use_atomic) PM_CUDA(ctx, cudaMemsetAsync(dcounts, 0, (size_t)n_models * 4, ctx->stream));
+    const float thr2 = thr * thr;
+    dim3 grid(mblocks, chunks);
+    if (metric == PM_METRIC_SAMPSON)
+        ransac_score_kernel<PM_METRIC_SAMPSON><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic);
+    else
+        ransac_score_kernel<PM_METRIC_SYMEPI><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}
+
+int pmk_ransac_best(pm_ctx *ctx, const int32_t *dcounts, int n_models, int id_base, uint64_t *dkey)
+{
+    PM_CUDA(ctx, cudaMemsetAsync(dkey, 0, 8, ctx->stream));
+    if (n_models <= 0) return PM_OK;
+    const int blocks = min(pm_cdiv(n_models, 256), 4 * ctx->num_sms);
+    ransac_best_kernel<<<blocks, 256, 0, ctx->stream>>>(dcounts, n_models, id_base, (unsigned long long *)dkey);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}
+
+int pmk_ransac_pick(pm_ctx *ctx, const uint64_t *dkey, const float *dF32, int id_base, int n_models, float *dFw)
+{
+    ransac_pick_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long *)dkey, dF32, id_base, n_models, dFw);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}
+
+int pmk_ransac_finish(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dFw, float thr, int metric,
+                      int refit, double *dF, uint8_t *dmask, int32_t *dn_inl)
+{
+    const float4 *pts;
+    int st = get_pts4(ctx, dp1, dp2, n, &pts);
+    if (st != PM_OK) return st;
+    PM_CUDA(ctx, cudaMemsetAsync(dn_inl, 0, 4, ctx->stream));
+    const float thr2 = thr * thr;
+    if (n > 0) {
+        if (metric == PM_METRIC_SAMPSON)
+            ransac_mask_kernel<PM_METRIC_SAMPSON><<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>(pts, n, dFw, thr2, dmask, dn_inl);
+        else
+            ransac_mask_kernel<PM_METRIC_SYMEPI><<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>(pts, n, dFw, thr2, dmask, dn_inl);
+        PM_CHECK_LAUNCH(ctx);
+    }
+    if (refit) return run_refit(ctx, pts, n, dmask, dFw, dF, nullptr);
+    copy_f32_to_f64_kernel<<<1, 32, 0, ctx->stream>>>(dFw, dF, 9);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}
+
+int pmk_fundamental_npoint(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const uint8_t *dmask, double *dF,
+                           int32_t *dok)
+{
+    const float4 *pts;
+    int st = get_pts4(ctx, dp1, dp2, n, &pts);
+    if (st != PM_OK) return st;
+    return run_refit(ctx, pts, n, dmask, nullptr, dF, dok);
+}
+
+int pmk_epilines(pm_ctx *ctx, const float *dpts, int n, int which, const double *dF, float *dlines)
+{
+    if (n <= 0) return PM_OK;
+    epilines_kernel<<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>((const float2 *)dpts, n, which, dF, dlines);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}
+
+int pmk_residuals(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const double *dF, int metric, float *dout,
+                  double *dsum)
+{
+    if (dsum) PM_CUDA(ctx, cudaMemsetAsync(dsum, 0, 8, ctx->stream));
+    if (n <= 0) return PM_OK;
+    residuals_kernel<<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dF, metric, dout, dsum);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}

@@ -1,0 +1,82 @@
+"""CPU-side checks of the C-ABI boundary: libpm.so builds, loads and exports every symbol
+include/pm.h declares; pm_dmatch is layout-identical to cv::DMatch; without a GPU the product
+fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    import points_matching_b200 as pm
+    pm.build()
+    from points_matching_b200 import _lib
+    return _lib.lib()
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "pm.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_header_symbol_is_exported(L):
+    from points_matching_b200 import _lib
+    syms = _header_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/pm.h but not exported by libpm.so"
+    assert sorted(_lib.EXPORTS) == syms
+
+
+def test_dmatch_layout_matches_cv_dmatch():
+    from points_matching_b200 import DMATCH
+    assert DMATCH.itemsize == 16
+    assert [DMATCH.fields[n][1] for n in ("queryIdx", "trainIdx", "imgIdx", "distance")] == [0, 4, 8, 12]
+
+
+def test_version_and_no_cpu_fallback(L):
+    import torch
+    assert L.pm_version() == 100
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the -m gpu tests")
+    h = C.c_void_p()
+    assert L.pm_create(C.byref(h), 0) == -4          # PM_NO_DEVICE
+    import points_matching_b200 as pm
+    with pytest.raises(pm.PMError):
+        pm.Context(0)
+    with pytest.raises(pm.PMError):
+        pm.BFMatcher(pm.NORM_L2).match(np.zeros((2, 128), np.float32), np.zeros((2, 128), np.float32))
+
+
+def test_sample_sets_host_generator(L):
+    from points_matching_b200.api import make_sample_sets
+    a = make_sample_sets(1000, 500, 8, seed=5)
+    b = make_sample_sets(1000, 500, 8, seed=5)
+    assert (a == b).all() and a.min() >= 0 and a.max() < 1000
+    s = np.sort(a, axis=1)
+    assert (s[:, 1:] != s[:, :-1]).all()             # distinct within a row
+    assert (make_sample_sets(1000, 500, 8, seed=6) != a).any()
+    c = make_sample_sets(8, 50, 8, seed=1)           # n == m: every row a permutation
+    assert (np.sort(c, axis=1) == np.arange(8)).all()
+    import points_matching_b200 as pm
+    with pytest.raises(pm.PMError):
+        make_sample_sets(5, 10, 8)
+
+
+def test_sass_is_blackwell_native():
+    """The L2 kernel must carry tcgen05 / TMA instructions (UTCHMMA, LDTM, UTMALDG)."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    from points_matching_b200 import SO_PATH
+    sass = subprocess.run(["cuobjdump", "-sass", SO_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "POPC"):
+        assert mnemonic in sass, mnemonic
+    assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", SO_PATH], capture_output=True, text=True).stdout

@@ -1,0 +1,379 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libpm.so), against the CPU
+oracle and the OpenCV golden vectors.  Bit-exact for Hamming / integer-valued L2 / index
+work / inlier counts on identical F; tolerances are written where floating point is compared.
+"""
+import numpy as np
+import pytest
+
+from points_matching_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import points_matching_b200 as pm
+    c = pm.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def pm():
+    import points_matching_b200 as pm
+    return pm
+
+
+def _same_knn(a, b, bit_exact_dist=True, rtol=0.0):
+    assert (a["queryIdx"] == b["queryIdx"]).all()
+    assert (a["trainIdx"] == b["trainIdx"]).all()
+    assert (a["imgIdx"] == 0).all()
+    if bit_exact_dist:
+        assert (a["distance"] == b["distance"]).all()
+    else:
+        assert np.allclose(a["distance"], b["distance"], rtol=rtol, atol=0)
+
+
+# --------------------------------------------------------------------------- Hamming
+@pytest.mark.parametrize("case", ["orb", "tie", "odd"])
+def test_hamming_golden(ctx, pm, golden, case):
+    g = golden["hamming"]
+    knn = ctx.knn2(g[case + "_q"], g[case + "_t"], pm.NORM_HAMMING)
+    assert (knn["trainIdx"] == g[case + "_idx"]).all()
+    assert (knn["distance"] == g[case + "_dist"]).all()
+
+
+@pytest.mark.parametrize("nq,nt,nbytes", [(3000, 5000, 32), (777, 1301, 32), (513, 129, 16), (400, 700, 64),
+                                          (300, 500, 8), (200, 300, 100), (1, 1, 32), (5, 2, 32)])
+def test_hamming_vs_oracle(ctx, pm, orc, nq, nt, nbytes):
+    q, t = synth.orb_pair(nq, nt, seed=100 + nq, nbytes=nbytes)
+    _same_knn(ctx.knn2(q, t, pm.NORM_HAMMING), orc.knn2_hamming(q, t))
+
+
+def test_hamming_edge_cases(ctx, pm, orc):
+    q, t = synth.orb_pair(10, 1, seed=1)
+    knn = ctx.knn2(q, t, pm.NORM_HAMMING)
+    assert (knn["trainIdx"][:, 0] == 0).all() and (knn["trainIdx"][:, 1] == -1).all()
+    assert ctx.knn2(q[:0], t, pm.NORM_HAMMING).shape == (0, 2)          # empty query -> empty result
+    knn = ctx.knn2(q, t[:0], pm.NORM_HAMMING)                           # empty train -> no neighbours
+    assert (knn["trainIdx"] == -1).all()
+    with pytest.raises(pm.PMError):
+        ctx.knn2(q.astype(np.float32), t, pm.NORM_HAMMING)              # type mismatch -> error
+    # all rows identical: every distance ties, indices must be 0 and 1
+    q = np.full((40, 32), 7, np.uint8); t = np.full((50, 32), 7, np.uint8)
+    knn = ctx.knn2(q, t, pm.NORM_HAMMING)
+    assert (knn["trainIdx"] == [0, 1]).all() and (knn["distance"] == 0).all()
+
+
+@pytest.mark.parametrize("case", ["orb", "tie"])
+def test_hamming_cross_check_golden(ctx, pm, golden, case):
+    g = golden["hamming"]
+    x = ctx.match_cross(g[case + "_q"], g[case + "_t"], pm.NORM_HAMMING)
+    assert (x["queryIdx"] == g[case + "_xq"]).all() and (x["trainIdx"] == g[case + "_xt"]).all()
+    assert (x["distance"] == g[case + "_xd"]).all()
+
+
+def test_hamming_cross_check_vs_oracle(ctx, pm, orc):
+    q, t = synth.orb_pair(2500, 3100, seed=7)
+    x = ctx.match_cross(q, t, pm.NORM_HAMMING)
+    ref = orc.cross_check(orc.knn2_hamming(q, t), orc.col_best_hamming(q, t))
+    assert len(x) == len(ref) and (x["queryIdx"] == ref["queryIdx"]).all() and (x["trainIdx"] == ref["trainIdx"]).all()
+
+
+def test_hamming_full_size_sampled(ctx, pm, orc):
+    """cfg3 per-GPU shard shape (12.5k x 100k): sampled rows against the oracle, plus
+    size-independent properties (sorted, planted neighbours found, idempotent)."""
+    q, t = synth.orb_pair(12500, 100000, seed=4321)
+    knn = ctx.knn2(q, t, pm.NORM_HAMMING)
+    rows = np.arange(0, 12500, 49)
+    ref = orc.knn2_hamming(q[rows], t)
+    assert (knn["trainIdx"][rows] == ref["trainIdx"]).all() and (knn["distance"][rows] == ref["distance"]).all()
+    assert (knn["distance"][:, 0] <= knn["distance"][:, 1]).all()
+    assert (knn["queryIdx"][:, 0] == np.arange(12500)).all()
+    again = ctx.knn2(q, t, pm.NORM_HAMMING)
+    assert (again == knn).all()
+
+
+# --------------------------------------------------------------------------- L2
+def test_l2_golden_sift(ctx, pm, golden):
+    g = golden["l2"]
+    q, t = g["sift_q"].astype(np.float32), g["sift_t"].astype(np.float32)
+    knn = ctx.knn2(q, t, pm.NORM_L2)
+    assert (knn["trainIdx"] == g["sift_idx"]).all()
+    assert (knn["distance"] == g["sift_dist"]).all()            # exact-integer mode: bit for bit vs OpenCV
+    assert ctx.l2_stats()["exact_mode"]
+    knn8 = ctx.knn2(g["sift_q"], g["sift_t"], pm.NORM_L2)       # u8 upload path
+    assert (knn8 == knn).all()
+    good = ctx.ratio_filter(knn, 0.75)
+    assert (good["queryIdx"] == g["ratio_q"]).all() and (good["trainIdx"] == g["ratio_t"]).all()
+    assert (good["distance"] == g["ratio_d"]).all()
+
+
+def test_l2_golden_surf(ctx, pm, golden):
+    g = golden["l2"]
+    knn = ctx.knn2(g["surf_q"], g["surf_t"], pm.NORM_L2)
+    assert (knn["trainIdx"] == g["surf_idx"]).all()                       # 100% index agreement
+    assert np.allclose(knn["distance"], g["surf_dist"], rtol=1e-5, atol=0)  # north_star: 1e-5 relative
+    assert not ctx.l2_stats()["exact_mode"]
+
+
+def test_l2_golden_ties_and_short(ctx, pm, golden):
+    g = golden["l2"]
+    knn = ctx.knn2(np.ones((5, 128), np.float32), np.ones((9, 128), np.float32), pm.NORM_L2)
+    assert (knn["trainIdx"] == g["eq_idx"]).all() and (knn["distance"] == g["eq_dist"]).all()
+    q, t = synth.sift_pair(4, 1, seed=13)
+    knn = ctx.knn2(q, t, pm.NORM_L2)
+    assert (knn["trainIdx"][:, 0] == 0).all() and (knn["trainIdx"][:, 1] == -1).all()
+    assert ctx.knn2(q[:0], t, pm.NORM_L2).shape == (0, 2)
+    assert (ctx.knn2(q, t[:0], pm.NORM_L2)["trainIdx"] == -1).all()
+    with pytest.raises(pm.PMError):
+        ctx.knn2(q, t.astype(np.uint8), pm.NORM_L2)
+
+
+def test_l2_image_pair_config1(ctx, pm, golden):
+    """Config 1 stand-in: real SIFT descriptors of img01/img02.JPG (fixture), OpenCV results."""
+    g = golden["image_pair"]
+    knn = ctx.knn2(g["desc1"], g["desc2"], pm.NORM_L2)
+    assert (knn["trainIdx"] == g["knn_idx"]).all() and (knn["distance"] == g["knn_dist"]).all()
+    good = ctx.ratio_filter(knn, 0.75)
+    assert (good["queryIdx"] == g["ratio_q"]).all() and (good["trainIdx"] == g["ratio_t"]).all()
+    lit, mn, mx = ctx.minmax_filter(knn)                        # the reference's literal rule, main.cpp:49-69
+    assert mn == g["lit_min"] and mx == g["lit_max"]
+    assert (lit["queryIdx"] == g["lit_q"]).all() and (lit["trainIdx"] == g["lit_t"]).all()
+    pts1 = ctx.gather_points(g["kp1"], good["queryIdx"])
+    assert (pts1 == g["kp1"][g["ratio_q"]]).all()
+
+
+@pytest.mark.parametrize("nq,nt", [(2000, 3000), (129, 257), (128, 256), (1000, 130), (3, 5000)])
+def test_l2_sift_vs_oracle(ctx, pm, orc, nq, nt):
+    q, t = synth.sift_pair(nq, nt, seed=nq + nt)
+    _same_knn(ctx.knn2(q, t, pm.NORM_L2), orc.knn2_l2(q, t))
+
+
+@pytest.mark.parametrize("nq,nt", [(2000, 3000), (300, 1000)])
+def test_l2_surf_vs_oracle(ctx, pm, orc, nq, nt):
+    q, t = synth.surf_pair(nq, nt, seed=nq)
+    _same_knn(ctx.knn2(q, t, pm.NORM_L2), orc.knn2_l2(q, t), bit_exact_dist=False, rtol=1e-5)
+
+
+@pytest.mark.parametrize("dim", [64, 100, 127, 130, 256])
+def test_l2_other_dims(ctx, pm, orc, dim):
+    rng = np.random.default_rng(dim)
+    q = rng.normal(0, 1, (300, dim)).astype(np.float32)
+    t = rng.normal(0, 1, (500, dim)).astype(np.float32)
+    _same_knn(ctx.knn2(q, t, pm.NORM_L2), orc.knn2_l2(q, t), bit_exact_dist=False, rtol=1e-5)
+
+
+def test_l2_rerank_distance_bits(ctx, pm, orc):
+    """The FP32 re-rank order is a defined arithmetic: d == sqrtf(orc_l2sq_f32_rerank)."""
+    q, t = synth.surf_pair(200, 400, seed=5)
+    knn = ctx.knn2(q, t, pm.NORM_L2)
+    for i in range(0, 200, 7):
+        for k in range(2):
+            j = knn["trainIdx"][i, k]
+            assert knn["distance"][i, k] == np.sqrt(np.float32(orc.l2sq_rerank(q[i], t[j])))
+
+
+def test_l2_full_size_cfg2(ctx, pm, orc):
+    """BASELINE cfg2 (10k x 10k x 128): sampled rows vs the oracle + properties."""
+    q, t = synth.sift_pair(10000, 10000, seed=1234)
+    knn = ctx.knn2(q, t, pm.NORM_L2)
+    st = ctx.l2_stats()
+    assert st["exact_mode"] and st["fallback_rows"] == 0
+    rows = np.arange(0, 10000, 23)
+    ref = orc.knn2_l2(q[rows], t)
+    assert (knn["trainIdx"][rows] == ref["trainIdx"]).all() and (knn["distance"][rows] == ref["distance"]).all()
+    assert (knn["distance"][:, 0] <= knn["distance"][:, 1]).all()
+    assert (ctx.knn2(q, t, pm.NORM_L2) == knn).all()                    # idempotent / deterministic
+    # planted neighbours pass the 0.75 ratio test for roughly half of the queries
+    assert 0.3 < len(ctx.ratio_filter(knn, 0.75)) / 10000 < 0.7
+    qs, ts = synth.surf_pair(10000, 10000, seed=77)
+    knn = ctx.knn2(qs, ts, pm.NORM_L2)
+    ref = orc.knn2_l2(qs[rows], ts)
+    assert (knn["trainIdx"][rows] == ref["trainIdx"]).all()
+    assert np.allclose(knn["distance"][rows], ref["distance"], rtol=1e-5, atol=0)
+
+
+def test_l2_cross_check(ctx, pm, orc):
+    q, t = synth.sift_pair(1500, 1700, seed=21)
+    x = ctx.match_cross(q, t, pm.NORM_L2)
+    fwd = orc.knn2_l2(q, t)
+    bwd = orc.knn2_l2(t, q)
+    keep = [i for i in range(1500) if bwd["trainIdx"][fwd["trainIdx"][i, 0], 0] == i]
+    assert (x["queryIdx"] == keep).all() and (x["trainIdx"] == fwd["trainIdx"][keep, 0]).all()
+
+
+# --------------------------------------------------------------------------- filters
+def test_filters_vs_oracle(ctx, pm, orc):
+    q, t = synth.sift_pair(40000, 300, seed=3)          # > 16384 rows: multi-block compaction path
+    knn = ctx.knn2(q, t, pm.NORM_L2)
+    ref = orc.knn2_l2(q, t)
+    assert (knn == ref.view(knn.dtype)).all()
+    for ratio in (0.6, 0.75, 0.9):
+        a, b = ctx.ratio_filter(knn, ratio), orc.ratio_filter(ref, ratio)
+        assert len(a) == len(b) and (a == b.view(a.dtype)).all()
+    a, mn, mx = ctx.minmax_filter(knn)
+    b, mn2, mx2 = orc.minmax_filter(np.ascontiguousarray(ref[:, 0]))
+    assert (mn, mx) == (mn2, mx2) and len(a) == len(b) and (a == b.view(a.dtype)).all()
+    # minMatch starts at 1 (main.cpp:49): distances all > 1 leave min == 1
+    assert mn == 1.0
+
+
+# --------------------------------------------------------------------------- RANSAC
+def _dev(ctx):
+    import torch
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    return torch
+
+
+def test_ransac_solve_vs_oracle_and_cv(ctx, pm, orc, golden):
+    torch = _dev(ctx)
+    g = golden["fundamental"]
+    p1, p2 = g["p1"], g["p2"]
+    d1, d2 = torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda()
+    for m, idx, Fg in ((8, g["idx8"], g["F8"]), (7, g["idx7"], g["F7"])):
+        per = 1 if m == 8 else 3
+        ds = torch.from_numpy(idx).cuda()
+        dF = torch.zeros((len(idx), per, 12), device="cuda", dtype=torch.float32)
+        ctx.ransac_solve_dev(d1.data_ptr(), d2.data_ptr(), len(p1), ds.data_ptr(), len(idx), m, dF.data_ptr())
+        torch.cuda.synchronize()
+        F = dF.cpu().numpy()[:, :, :9]
+        for h in range(len(idx)):
+            if m == 8:
+                # f32 storage of an f64 solve: 1e-6 relative to max|F| vs OpenCV's FM_8POINT
+                assert np.abs(F[h, 0].reshape(3, 3) - Fg[h]).max() / np.abs(Fg[h]).max() < 1e-6
+            else:
+                n = g["n7"][h]
+                got = [F[h, k].reshape(3, 3) for k in range(3) if np.isfinite(F[h, k]).all()]
+                assert len(got) == n
+                for a in Fg[h][:n]:
+                    assert min(np.abs(a - b).max() / np.abs(a).max() for b in got) < 1e-5
+    ctx.set_stream(0)
+
+
+def test_ransac_score_bit_exact(ctx, pm, orc):
+    """Inlier counts for identical F bits are bit-exact vs the oracle's FP32 restatement."""
+    torch = _dev(ctx)
+    p1, p2, gt = synth.correspondences(5000, seed=2)
+    idx = synth.sample_index_sets(5000, 700, 8, seed=3)
+    d1, d2 = torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda()
+    ds = torch.from_numpy(idx).cuda()
+    dF = torch.zeros((700, 12), device="cuda", dtype=torch.float32)
+    ctx.ransac_solve_dev(d1.data_ptr(), d2.data_ptr(), 5000, ds.data_ptr(), 700, 8, dF.data_ptr())
+    for metric in (pm.METRIC_SAMPSON, pm.METRIC_SYMEPI):
+        for thr in (0.5, 1.0, 3.0):
+            dc = torch.zeros(700, device="cuda", dtype=torch.int32)
+            ctx.ransac_score_dev(d1.data_ptr(), d2.data_ptr(), 5000, dF.data_ptr(), 700, thr, metric, dc.data_ptr())
+            torch.cuda.synchronize()
+            F = dF.cpu().numpy()[:, :9]
+            cnt = dc.cpu().numpy()
+            for h in range(0, 700, 9):
+                assert cnt[h] == orc.count_inliers_f32(F[h], p1, p2, thr, metric), (metric, thr, h)
+    ctx.set_stream(0)
+
+
+@pytest.mark.parametrize("m,metric,refit", [(8, 0, True), (8, 1, False), (7, 0, True), (7, 1, False)])
+def test_find_fundamental_vs_oracle(ctx, pm, orc, m, metric, refit):
+    p1, p2, gt = synth.correspondences(4000, seed=11)
+    idx = synth.sample_index_sets(4000, 3000, m, seed=12)
+    got = ctx.find_fundamental(p1, p2, sample_size=m, metric=metric, threshold=1.0, refit=refit, sample_idx=idx)
+    ref = orc.ransac_f(p1, p2, idx, metric, 1.0, refit=refit)
+    assert got is not None and ref is not None
+    F, mask, ninl = got
+    assert ninl == mask.sum()
+    # H4: GPU FP64 Householder solve vs the oracle's Jacobi solve agree to ~1e-12, so after the
+    # cast to f32 the winner and its inlier set agree up to points within ~1e-4 px of the threshold
+    assert abs(ninl - ref["n_inliers"]) <= 3
+    assert (mask != ref["mask"]).sum() <= 6
+    s_got = orc.sampson_f64(F, p1[gt], p2[gt]).mean()
+    s_ref = orc.sampson_f64(ref["F"], p1[gt], p2[gt]).mean()
+    assert s_got <= s_ref + 1e-3                                   # north_star: within 1e-3 mean Sampson error
+    assert abs(F[2, 2] - 1.0) < 1e-12
+    if refit:
+        assert np.abs(F - ref["F"]).max() / np.abs(ref["F"]).max() < 1e-4
+        assert abs(np.linalg.svd(F, compute_uv=False)[2]) < 1e-9  # rank 2
+
+
+def test_find_fundamental_edge_cases(ctx, pm):
+    p1, p2, _ = synth.correspondences(50, seed=1)
+    assert ctx.find_fundamental(p1[:6], p2[:6], n_hyp=16) is None               # N < sample size -> empty
+    with pytest.raises(pm.PMError):
+        ctx.find_fundamental(p1, p2, sample_size=5)
+    # degenerate: all points identical -> no model
+    z = np.ones((20, 2), np.float32)
+    assert ctx.find_fundamental(z, z, n_hyp=64) is None
+    # generated sample sets are deterministic
+    a = ctx.find_fundamental(p1, p2, n_hyp=512, seed=7)
+    b = ctx.find_fundamental(p1, p2, n_hyp=512, seed=7)
+    assert a is not None and (a[0] == b[0]).all() and (a[1] == b[1]).all()
+
+
+def test_fundamental_8point_npoint(ctx, pm, orc, golden):
+    g = golden["fundamental"]
+    gt = g["gt"]
+    F = ctx.fundamental_8point(g["p1"][gt], g["p2"][gt])
+    assert np.abs(F - g["F8_all"]).max() / np.abs(g["F8_all"]).max() < 1e-8       # vs cv2 FM_8POINT
+    assert ctx.fundamental_8point(g["p1"][:7], g["p2"][:7]) is None
+
+
+def test_ransac_full_size_sampled(ctx, pm, orc):
+    """cfg4 shape (100k correspondences, 50% outliers, thr 1 px) with 20k hypotheses:
+    sampled per-hypothesis counts bit-exact vs the oracle on the same F bits, and the
+    winner recovers the planted motion."""
+    torch = _dev(ctx)
+    n, nh = 100000, 20000
+    p1, p2, gt = synth.correspondences(n, seed=0)
+    idx = synth.sample_index_sets(n, nh, 8, seed=99)
+    d1, d2 = torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda()
+    ds = torch.from_numpy(idx).cuda()
+    dF = torch.zeros((nh, 12), device="cuda", dtype=torch.float32)
+    dc = torch.zeros(nh, device="cuda", dtype=torch.int32)
+    ctx.ransac_solve_dev(d1.data_ptr(), d2.data_ptr(), n, ds.data_ptr(), nh, 8, dF.data_ptr())
+    ctx.ransac_score_dev(d1.data_ptr(), d2.data_ptr(), n, dF.data_ptr(), nh, 1.0, pm.METRIC_SAMPSON, dc.data_ptr())
+    torch.cuda.synchronize()
+    F, cnt = dF.cpu().numpy()[:, :9], dc.cpu().numpy()
+    for h in list(range(0, nh, 997)) + [int(cnt.argmax())]:
+        assert cnt[h] == orc.count_inliers_f32(F[h], p1, p2, 1.0, pm.METRIC_SAMPSON)
+    ctx.set_stream(0)
+    got = ctx.find_fundamental(p1, p2, sample_size=8, threshold=1.0, refit=True, sample_idx=idx)
+    Fw, mask, ninl = got
+    assert ninl == cnt.max()
+    assert mask[gt].mean() > 0.8 and mask[~gt].mean() < 0.02
+    assert orc.sampson_f64(Fw, p1[gt][:5000], p2[gt][:5000]).mean() < 0.2
+
+
+# --------------------------------------------------------------------------- diagnostics + mirror API
+def test_epilines_and_residuals(ctx, pm, golden, orc):
+    g = golden["fundamental"]
+    F = g["ransac1_F"]
+    assert np.allclose(ctx.epilines(g["p1"], 1, F), g["lines1"], rtol=0, atol=1e-6)
+    assert np.allclose(ctx.epilines(g["p2"], 2, F), g["lines2"], rtol=0, atol=1e-6)
+    r, mean = ctx.residuals(g["p1"], g["p2"], F, pm.METRIC_SAMPSON)
+    assert np.allclose(r, g["sampson"], rtol=1e-5, atol=0) and abs(mean - g["sampson"].mean()) < 1e-6 * g["sampson"].mean() + 1e-9
+    r, _ = ctx.residuals(g["p1"], g["p2"], F, pm.METRIC_SYMEPI)
+    assert ((r <= np.float32(1.0)) == g["ransac1_mask"].astype(bool)).all()        # == cv2's RANSAC mask
+
+
+def test_opencv_lookalike_api(pm, golden):
+    g = golden["image_pair"]
+    d1, d2 = g["desc1"].astype(np.float32), g["desc2"].astype(np.float32)
+    matcher = pm.BFMatcher(pm.NORM_L2)
+    m = matcher.match(d1, d2)                                      # main.cpp:46
+    assert (m["trainIdx"] == g["knn_idx"][:, 0]).all()
+    rows = matcher.knnMatch(d1[:10], d2[:1], k=2)
+    assert all(len(r) == 1 for r in rows)                          # k > ntrain -> shorter rows
+    good = pm.ratio_test(matcher.knnMatchArray(d1, d2), 0.75)
+    pts1 = pm.keypoints_convert(g["kp1"], good["queryIdx"])        # main.cpp:90-91
+    pts2 = pm.keypoints_convert(g["kp2"], good["trainIdx"])
+    F, mask = pm.findFundamentalMat(pts1, pts2, pm.FM_RANSAC, 1.0, 0.99, maxIters=4096)
+    assert F is not None and F.shape == (3, 3) and mask.shape == (len(pts1),)
+    # quality at least OpenCV's on the same matches (OpenCV does not refit, D5)
+    inl = g["ransac_mask"].astype(bool)
+    from oracle import oracle as orc
+    assert orc.sampson_f64(F, pts1[inl], pts2[inl]).mean() <= orc.sampson_f64(g["ransac_F"], pts1[inl], pts2[inl]).mean() + 1e-3
+    assert mask.sum() >= 0.9 * inl.sum()
+    assert pm.findFundamentalMat(pts1[:6], pts2[:6])[0] is None    # N < 7 -> empty
+    lines = pm.computeCorrespondEpilines(pts1, 1, F)               # main.cpp:128-132
+    assert np.allclose(lines[:, 0] ** 2 + lines[:, 1] ** 2, 1.0, atol=1e-5)
+    with pytest.raises(pm.PMError):
+        pm.BFMatcher(pm.NORM_L2, crossCheck=True).knnMatch(d1, d2, k=2)
