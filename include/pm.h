@@ -65,6 +65,13 @@ uint64_t pm_launch_count(pm_ctx *ctx);
 /* Counters of the last L2 call: [0] exact-integer mode (1/0), [1] rows sent to the
  * exact fallback, [2] MMA k-blocks per tile, [3] segments per row tile. */
 int  pm_l2_stats(pm_ctx *ctx, int32_t out[4]);
+/* Device-side timing of the dominant kernels with CUDA events on the ctx stream (bench
+ * roofline): enable, run any number of calls, then read.  which: 0 = L2 tensor-core kernel
+ * (K2), 1 = Hamming kNN kernel (K4), 2 = RANSAC scoring kernel (K7).  pm_profile_read
+ * synchronises the stream, returns the summed milliseconds and the launch count since the
+ * last read, and resets them. */
+int  pm_profile_enable(pm_ctx *ctx, int on);
+int  pm_profile_read(pm_ctx *ctx, int which, double *total_ms, int *n_launches);
 
 /* ---- descriptor matching ----------------------------------------------------
  * Replaces BruteForceMatcher<L2<float>> matcher; matcher.match(d1, d2, matches)
@@ -79,6 +86,12 @@ int pm_knn2_l2_u8(pm_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int n
 /* BFMatcher(NORM_HAMMING).knnMatch(q, t, k=2) for `bytes`-wide binary rows (ORB: 32). */
 int pm_knn2_hamming(pm_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt, int bytes,
                     pm_dmatch *out);
+
+/* knnMatch(k=2) + Lowe ratio test in one call (the north_star flow for main.cpp:43-69):
+ * knn_out (optional, [nq][2]) and the compacted good matches come back together, so the
+ * kNN result never makes a host round trip between the two steps. */
+int pm_knn2_ratio_l2_f32(pm_ctx *ctx, const float *q, int nq, const float *t, int nt, int dim,
+                         float ratio, pm_dmatch *knn_out, pm_dmatch *good_out, int *n_good);
 
 int pm_knn2_l2_f32_dev(pm_ctx *ctx, const float *dq, int nq, const float *dt, int nt, int dim,
                        int q_index_base, pm_dmatch *dout);
@@ -169,6 +182,13 @@ int pm_ransac_best_dev(pm_ctx *ctx, const int32_t *dcounts, int n_models, int mo
 int pm_ransac_finish_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n,
                          const float *dF32_winner /* [12] */, float threshold, int metric, int refit,
                          double *dF /* [9] */, uint8_t *dmask, int32_t *dn_inliers);
+
+/* All four stages, device resident and asynchronous on the ctx stream (prm->sample_idx is a
+ * DEVICE pointer and must not be NULL).  dkey receives the winner key (0 = no model: dF,
+ * dmask are then undefined and *dn_inliers is 0). */
+int pm_find_fundamental_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n,
+                            const pm_ransac_params *prm, double *dF /* [9] */, uint8_t *dmask,
+                            int32_t *dn_inliers, uint64_t *dkey);
 
 /* N-point normalised 8-point (findFundamentalMat(..., FM_8POINT)); mask all ones. */
 int pm_fundamental_8point(pm_ctx *ctx, const float *p1, const float *p2, int n, double F[9]);

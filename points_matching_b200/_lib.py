@@ -26,14 +26,14 @@ class RansacParams(C.Structure):
 # every symbol include/pm.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
     "pm_version", "pm_create", "pm_destroy", "pm_set_stream", "pm_sync", "pm_last_error",
-    "pm_launch_count", "pm_l2_stats",
-    "pm_knn2_l2_f32", "pm_knn2_l2_u8", "pm_knn2_hamming",
+    "pm_launch_count", "pm_l2_stats", "pm_profile_enable", "pm_profile_read",
+    "pm_knn2_l2_f32", "pm_knn2_l2_u8", "pm_knn2_hamming", "pm_knn2_ratio_l2_f32",
     "pm_knn2_l2_f32_dev", "pm_knn2_l2_u8_dev", "pm_knn2_hamming_dev",
     "pm_ratio_filter", "pm_ratio_filter_dev", "pm_minmax_filter", "pm_minmax_filter_dev",
     "pm_match_cross_l2_f32", "pm_match_cross_hamming",
     "pm_col_best_hamming_dev", "pm_col_best_l2_f32_dev", "pm_cross_check_dev",
     "pm_gather_points", "pm_gather_matches_dev",
-    "pm_find_fundamental", "pm_make_sample_sets",
+    "pm_find_fundamental", "pm_find_fundamental_dev", "pm_make_sample_sets",
     "pm_ransac_solve_dev", "pm_ransac_score_dev", "pm_ransac_best_dev", "pm_ransac_finish_dev",
     "pm_fundamental_8point", "pm_epilines", "pm_residuals",
 ]

@@ -78,6 +78,48 @@ class Context:
         self._chk(self._L.pm_l2_stats(self._h, out))
         return dict(exact_mode=bool(out[0]), fallback_rows=out[1], k_blocks=out[2], segments=out[3])
 
+    def profile_enable(self, on=True):
+        self._chk(self._L.pm_profile_enable(self._h, int(bool(on))))
+
+    def profile_read(self, which):
+        """(total_ms, launches) of kernel class `which` (0 L2 tensor-core, 1 Hamming, 2 RANSAC scoring)."""
+        ms, n = C.c_double(0), C.c_int(0)
+        self._chk(self._L.pm_profile_read(self._h, which, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def knn2_ratio_l2_ptr(self, q_ptr, nq, t_ptr, nt, dim, ratio, knn_ptr, good_ptr):
+        """pm_knn2_ratio_l2_f32 on raw HOST pointers (pinned buffers in bench.py's e2e leg)."""
+        n = C.c_int(0)
+        self._chk(self._L.pm_knn2_ratio_l2_f32(self._h, C.c_void_p(q_ptr), nq, C.c_void_p(t_ptr), nt, dim,
+                                               C.c_float(ratio), C.c_void_p(knn_ptr), C.c_void_p(good_ptr),
+                                               C.byref(n)))
+        return n.value
+
+    def find_fundamental_ptr(self, p1_ptr, p2_ptr, n, sample_ptr, n_hyp, sample_size, metric, threshold, refit,
+                             F_ptr, mask_ptr):
+        """pm_find_fundamental on raw HOST pointers; returns n_inliers or None (PM_EMPTY)."""
+        prm = RansacParams()
+        prm.sample_size, prm.metric, prm.threshold = sample_size, metric, threshold
+        prm.n_hyp, prm.refit, prm.sample_idx = n_hyp, int(bool(refit)), sample_ptr
+        ninl = C.c_int(0)
+        st = self._chk(self._L.pm_find_fundamental(self._h, C.c_void_p(p1_ptr), C.c_void_p(p2_ptr), n, C.byref(prm),
+                                                   C.c_void_p(F_ptr), C.c_void_p(mask_ptr), C.byref(ninl)),
+                       allow_empty=True)
+        return None if st == PM_EMPTY else ninl.value
+
+    def knn2_ratio(self, query, train, ratio=0.75):
+        """(knn [nq,2], good [n]) == knnMatch(k=2) followed by the Lowe ratio test, one call."""
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        t = np.ascontiguousarray(train, dtype=np.float32)
+        nq, nt = q.shape[0], t.shape[0]
+        knn = np.zeros((nq, 2), dtype=DMATCH)
+        good = np.zeros(nq, dtype=DMATCH)
+        if nq == 0:
+            return knn, good
+        n = self.knn2_ratio_l2_ptr(q.ctypes.data, nq, t.ctypes.data, nt, q.shape[1], ratio, knn.ctypes.data,
+                                   good.ctypes.data)
+        return knn, good[:n]
+
     # ---- host-buffer calls ------------------------------------------------------------
     def knn2(self, query, train, norm=NORM_L2):
         """[nq, 2] DMATCH array == BFMatcher(norm).knnMatch(query, train, k=2)."""
@@ -243,6 +285,15 @@ class Context:
         self._chk(self._L.pm_gather_matches_dev(self._h, C.c_void_p(dm), C.c_void_p(dn), max_matches,
                                                 C.c_void_p(dkp1), nkp1, C.c_void_p(dkp2), nkp2,
                                                 C.c_void_p(dp1), C.c_void_p(dp2)))
+
+    def find_fundamental_dev(self, dp1, dp2, n, dsamples, n_hyp, sample_size, metric, threshold, refit,
+                             dF, dmask, dn_inl, dkey, hyp_id_base=0):
+        prm = RansacParams()
+        prm.sample_size, prm.metric, prm.threshold = sample_size, metric, threshold
+        prm.n_hyp, prm.refit, prm.sample_idx, prm.hyp_id_base = n_hyp, int(bool(refit)), dsamples, hyp_id_base
+        self._chk(self._L.pm_find_fundamental_dev(self._h, C.c_void_p(dp1), C.c_void_p(dp2), n, C.byref(prm),
+                                                  C.c_void_p(dF), C.c_void_p(dmask), C.c_void_p(dn_inl),
+                                                  C.c_void_p(dkey)))
 
     def ransac_solve_dev(self, dp1, dp2, n, dsamples, n_hyp, sample_size, dF32):
         self._chk(self._L.pm_ransac_solve_dev(self._h, C.c_void_p(dp1), C.c_void_p(dp2), n, C.c_void_p(dsamples),

@@ -237,10 +237,13 @@ int ham_run(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, i
 
     PM_WS(ctx, part, unsigned long long *, WS_HAM_PART, (size_t)chunks * nq * 2 * sizeof(unsigned long long));
     dim3 grid(qblocks, chunks);
+    {
+    pm_prof_scope prof(ctx, 1);
     if (W == 4)       ham_knn2_kernel<4><<<grid, HAM_THREADS, 0, ctx->stream>>>(pq, nq, pt, nt, chunk_rows, part);
     else if (W == 8)  ham_knn2_kernel<8><<<grid, HAM_THREADS, 0, ctx->stream>>>(pq, nq, pt, nt, chunk_rows, part);
     else if (W == 16) ham_knn2_kernel<16><<<grid, HAM_THREADS, 0, ctx->stream>>>(pq, nq, pt, nt, chunk_rows, part);
     else ham_knn2_generic_kernel<<<grid, 128, 0, ctx->stream>>>(pq, nq, pt, nt, W, chunk_rows, part);
+    }
     PM_CHECK_LAUNCH(ctx);
     ham_finalize_kernel<<<pm_cdiv(nq, 256), 256, 0, ctx->stream>>>(part, nq, chunks, q_index_base, mode,
                                                                   dout, (unsigned long long *)dcol);

@@ -121,16 +121,25 @@ l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__rest
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= nq) return;
-    unsigned long long key = ~0ull;
-    if (lane < ncand) {
-        const L2Cand c = part[(size_t)i * ncand + lane];
-        if (c.idx >= 0) key = ((unsigned long long)f2ord(c.d) << 32) | (unsigned)c.idx;
+    // lane-local sorted triple over this lane's strided share of the candidates, then three
+    // rounds of warp arg-min over the lane heads (keys are unique: distinct train indices)
+    unsigned long long h0 = ~0ull, h1 = ~0ull, h2 = ~0ull;
+    for (int c0 = lane; c0 < ncand; c0 += 32) {
+        const L2Cand c = part[(size_t)i * ncand + c0];
+        if (c.idx < 0) continue;
+        const unsigned long long key = ((unsigned long long)f2ord(c.d) << 32) | (unsigned)c.idx;
+        if (key < h2) {
+            if (key < h1) {
+                h2 = h1;
+                if (key < h0) { h1 = h0; h0 = key; } else h1 = key;
+            } else h2 = key;
+        }
     }
     unsigned long long k[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        k[r] = warp_min_u64(key);
-        if (key == k[r]) key = ~0ull;      // keys are unique (distinct train indices)
+        k[r] = warp_min_u64(h0);
+        if (h0 == k[r] && h0 != ~0ull) { h0 = h1; h1 = h2; h2 = ~0ull; }
     }
     const float na = qnorm[i];
     float d2[3]; int idx[3];
@@ -268,7 +277,7 @@ int pmk_l2_knn2(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int
     const int mq_pad = pm_round_up(nq, 128), nt_pad = pm_round_up(nt > 0 ? nt : 1, 256);
     const int MT = mq_pad / 128, NT = nt_pad / 256;
     const int smax = l2_tc_smax(ctx, MT, NT);
-    const bool use_tc = dim <= L2_KDIM && nt > 0 && smax * 3 <= 32 && !g_l2_force_exact;
+    const bool use_tc = dim <= L2_KDIM && nt > 0 && !g_l2_force_exact;
     ctx->l2_stats[2] = 0; ctx->l2_stats[3] = 0;
     if (!use_tc) {
         if (is_u8) return run_exact(ctx, (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, nullptr, nullptr, q_index_base, dout);

@@ -382,7 +382,10 @@ int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, 
     P.tnorm = tnorm; P.flags = flags; P.part = part; P.dump = dump;
     P.MT = mq_pad / BM; P.NT = nt_pad / BN; P.smax = smax; P.nt_pad = nt_pad;
     const int G = l2_tc_grid(ctx, P.MT, P.NT);
-    l2_tc_kernel<<<G, TC_THREADS, SMEM_TOTAL, ctx->stream>>>(tq, tt, P);
+    {
+        pm_prof_scope prof(ctx, 0);
+        l2_tc_kernel<<<G, TC_THREADS, SMEM_TOTAL, ctx->stream>>>(tq, tt, P);
+    }
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }

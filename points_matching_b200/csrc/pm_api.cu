@@ -71,6 +71,10 @@ int pm_destroy(pm_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int s = 0; s < PM_NSLOTS; ++s) if (ctx->slot_ptr[s]) cudaFree(ctx->slot_ptr[s]);
+    if (ctx->prof_alloc)
+        for (int w = 0; w < 3; ++w)
+            for (int i = 0; i < PM_PROF_RING; ++i)
+                for (int k = 0; k < 2; ++k) cudaEventDestroy(ctx->prof_ev[w][i][k]);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -88,6 +92,37 @@ int pm_sync(pm_ctx *ctx)
 {
     if (!ctx) return PM_BAD_ARG;
     PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PM_OK;
+}
+
+int pm_profile_enable(pm_ctx *ctx, int on)
+{
+    if (!ctx) return PM_BAD_ARG;
+    if (on && !ctx->prof_alloc) {
+        for (int w = 0; w < 3; ++w)
+            for (int i = 0; i < PM_PROF_RING; ++i)
+                for (int k = 0; k < 2; ++k) PM_CUDA(ctx, cudaEventCreate(&ctx->prof_ev[w][i][k]));
+        ctx->prof_alloc = true;
+    }
+    ctx->profile = on != 0;
+    for (int w = 0; w < 3; ++w) ctx->prof_n[w] = 0;
+    return PM_OK;
+}
+
+int pm_profile_read(pm_ctx *ctx, int which, double *total_ms, int *n_launches)
+{
+    if (!ctx || which < 0 || which > 2) return PM_BAD_ARG;
+    PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double tot = 0;
+    const int n = ctx->prof_n[which];
+    for (int i = 0; i < n; ++i) {
+        float ms = 0;
+        PM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->prof_ev[which][i][0], ctx->prof_ev[which][i][1]));
+        tot += ms;
+    }
+    ctx->prof_n[which] = 0;
+    if (total_ms) *total_ms = tot;
+    if (n_launches) *n_launches = n;
     return PM_OK;
 }
 
@@ -220,6 +255,34 @@ int pm_knn2_l2_u8(pm_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int n
 { return knn2_host(ctx, q, nq, t, nt, dim, 1, 1, out); }
 int pm_knn2_hamming(pm_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt, int bytes, pm_dmatch *out)
 { return knn2_host(ctx, q, nq, t, nt, bytes, 1, 2, out); }
+
+int pm_knn2_ratio_l2_f32(pm_ctx *ctx, const float *q, int nq, const float *t, int nt, int dim, float ratio,
+                         pm_dmatch *knn_out, pm_dmatch *good_out, int *n_good)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && dim > 0 && n_good, "bad argument");
+    *n_good = 0;
+    if (nq == 0) return PM_OK;
+    PM_REQUIRE(ctx, q && good_out && (nt == 0 || t), "null pointer");
+    PM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t qb = (size_t)nq * dim * 4, tb = (size_t)nt * dim * 4;
+    PM_WS(ctx, dq, float *, WS_Q_RAW, qb);
+    PM_WS(ctx, dt, float *, WS_T_RAW, tb);
+    PM_WS(ctx, dknn, pm_dmatch *, WS_OUT, (size_t)nq * 2 * sizeof(pm_dmatch));
+    PM_WS(ctx, dgood, pm_dmatch *, WS_OUT2, (size_t)nq * sizeof(pm_dmatch));
+    PM_WS(ctx, dn, int32_t *, WS_KEY, 64);
+    H2D(ctx, dq, q, qb);
+    if (tb) H2D(ctx, dt, t, tb);
+    int st;
+    if ((st = pmk_l2_knn2(ctx, dq, nq, dt, nt, dim, 0, 0, dknn)) != PM_OK) return st;
+    if ((st = pmk_ratio_filter(ctx, dknn, nq, ratio, dgood, dn)) != PM_OK) return st;
+    D2H(ctx, ctx->h_pinned, dn, 4);
+    if (knn_out) D2H(ctx, knn_out, dknn, (size_t)nq * 2 * sizeof(pm_dmatch));
+    PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_good = ctx->h_pinned[0];
+    if (*n_good) { D2H(ctx, good_out, dgood, (size_t)*n_good * sizeof(pm_dmatch)); PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); }
+    return PM_OK;
+}
 
 static int read_count(pm_ctx *ctx, const int32_t *dn, int *n_out)
 {
@@ -400,6 +463,27 @@ int pm_find_fundamental(pm_ctx *ctx, const float *p1, const float *p2, int n, co
     if (n_inliers) *n_inliers = ctx->h_pinned[4];
     if (mask) { D2H(ctx, mask, dmask, (size_t)n); PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); }
     return PM_OK;
+}
+
+int pm_find_fundamental_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const pm_ransac_params *prm,
+                            double *dF, uint8_t *dmask, int32_t *dn_inliers, uint64_t *dkey)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, prm && dp1 && dp2 && dF && dmask && dn_inliers && dkey && prm->sample_idx, "null pointer");
+    const int m = prm->sample_size;
+    PM_REQUIRE(ctx, m == 7 || m == 8, "sample_size must be 7 or 8");
+    PM_REQUIRE(ctx, prm->metric == PM_METRIC_SAMPSON || prm->metric == PM_METRIC_SYMEPI, "unknown metric");
+    PM_REQUIRE(ctx, prm->n_hyp > 0 && n >= m, "need n >= sample_size and n_hyp > 0");
+    const int per = m == 8 ? 1 : 3, nh = prm->n_hyp;
+    PM_WS(ctx, dF32, float *, WS_F32, ((size_t)nh * per + 1) * 12 * 4);
+    PM_WS(ctx, dcounts, int32_t *, WS_COUNTS, (size_t)nh * per * 4);
+    float *dFw = dF32 + (size_t)nh * per * 12;
+    int st;
+    if ((st = pmk_ransac_solve(ctx, dp1, dp2, n, prm->sample_idx, nh, m, dF32)) != PM_OK) return st;
+    if ((st = pmk_ransac_score(ctx, dp1, dp2, n, dF32, nh * per, prm->threshold, prm->metric, dcounts)) != PM_OK) return st;
+    if ((st = pmk_ransac_best(ctx, dcounts, nh * per, prm->hyp_id_base * per, dkey)) != PM_OK) return st;
+    if ((st = pmk_ransac_pick(ctx, dkey, dF32, prm->hyp_id_base * per, nh * per, dFw)) != PM_OK) return st;
+    return pmk_ransac_finish(ctx, dp1, dp2, n, dFw, prm->threshold, prm->metric, prm->refit, dF, dmask, dn_inliers);
 }
 
 int pm_fundamental_8point(pm_ctx *ctx, const float *p1, const float *p2, int n, double F[9])

@@ -9,6 +9,7 @@
 #include "../../include/pm.h"
 
 #define PM_NSLOTS 32
+#define PM_PROF_RING 4096
 
 // Workspace slots (one growable device buffer each).
 enum pm_slot {
@@ -31,6 +32,23 @@ struct pm_ctx {
     int32_t l2_stats[4] = {0, 0, 0, 0};
     void *tmap_encode = nullptr;   // cuTensorMapEncodeTiled entry point
     int32_t *h_pinned = nullptr;   // 4 KB pinned scratch for small D2H reads
+    // optional device-side kernel timing (pm_profile_*): ring of event pairs per kernel class
+    bool profile = false;
+    cudaEvent_t prof_ev[3][PM_PROF_RING][2] = {};
+    int prof_n[3] = {0, 0, 0};
+    bool prof_alloc = false;
+};
+
+// Brackets one launch with events when profiling is on (which: 0 K2, 1 K4, 2 K7).
+struct pm_prof_scope {
+    pm_ctx *c; int which; int slot;
+    pm_prof_scope(pm_ctx *ctx, int w) : c(ctx), which(w), slot(-1) {
+        if (c->profile && c->prof_n[w] < PM_PROF_RING) {
+            slot = c->prof_n[w]++;
+            cudaEventRecord(c->prof_ev[w][slot][0], c->stream);
+        }
+    }
+    ~pm_prof_scope() { if (slot >= 0) cudaEventRecord(c->prof_ev[which][slot][1], c->stream); }
 };
 
 int pm_fail(pm_ctx *ctx, int status, const char *fmt, ...);

@@ -752,10 +752,13 @@ int pmk_ransac_score(pm_ctx *ctx, const float *dp1, const float *dp2, int n, con
     if (use_atomic) PM_CUDA(ctx, cudaMemsetAsync(dcounts, 0, (size_t)n_models * 4, ctx->stream));
     const float thr2 = thr * thr;
     dim3 grid(mblocks, chunks);
-    if (metric == PM_METRIC_SAMPSON)
-        ransac_score_kernel<PM_METRIC_SAMPSON><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic);
-    else
-        ransac_score_kernel<PM_METRIC_SYMEPI><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic);
+    {
+        pm_prof_scope prof(ctx, 2);
+        if (metric == PM_METRIC_SAMPSON)
+            ransac_score_kernel<PM_METRIC_SAMPSON><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic);
+        else
+            ransac_score_kernel<PM_METRIC_SYMEPI><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic);
+    }
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }
