@@ -192,7 +192,12 @@ def run_ours(args):
     peaks = load_peaks()
 
     ctx = pm.Context(local)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream shared by torch and libpm: torch's legacy default stream has
+    # handle 0, which pm_set_stream reads as "use the ctx-owned stream", and torch events would
+    # then not see libpm's kernels
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
     def barrier():
@@ -302,6 +307,10 @@ def run_ours(args):
     if not args.no_ransac:
         secondary = bench_ransac(ctx, torch, dist, dev, world, rank, stream, barrier, peaks, args)
 
+    extra = None
+    if not args.no_hamming:
+        extra = {"hamming": bench_hamming(ctx, torch, dev, world, rank, stream, barrier, peaks)}
+
     clocks = sampler.stop() if sampler else None
 
     cpu_baseline = None
@@ -320,12 +329,57 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": config_dict(world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "secondary": secondary,
+            "cpu_baseline": cpu_baseline, "secondary": secondary, "extra": extra,
             "notes": {"good_matches_last_step": n_good_last, "clock_ramp_steps": ramp,
                       "dtype_detail": "bf16 operands (exact for 0..255 integers), fp32 accumulate in TMEM, "
                                       "fp32 norms / selection / output"}}
     print(json.dumps(line))
     return 0
+
+
+def bench_hamming(ctx, torch, dev, world, rank, stream, barrier, peaks):
+    """cfg3's per-GPU shard (12.5k of 100k ORB queries x 100k train rows, 256-bit): Hamming kNN-2 plus
+    the column minima and the cross-check filter (not a bench line of its own; reported for the roofline)."""
+    import points_matching_b200 as pm   # noqa: F401
+    from points_matching_b200 import synth
+    nq, nt = 12500, 100000
+    q, t = synth.orb_pair(nq, nt, seed=4321 + rank)
+    dq, dt_ = torch.from_numpy(q).to(dev), torch.from_numpy(t).to(dev)
+    knn = torch.zeros((nq, 2, 4), dtype=torch.int32, device=dev)
+    col = torch.zeros(nt, dtype=torch.int64, device=dev)
+    out = torch.zeros((nq, 4), dtype=torch.int32, device=dev)
+    cnt = torch.zeros(4, dtype=torch.int32, device=dev)
+
+    def step():
+        ctx.knn2_hamming_dev(dq.data_ptr(), nq, dt_.data_ptr(), nt, 32, knn.data_ptr(), rank * nq)
+        ctx.col_best_hamming_dev(dq.data_ptr(), nq, dt_.data_ptr(), nt, 32, col.data_ptr(), rank * nq)
+        ctx.cross_check_dev(knn.data_ptr(), nq, 2, col.data_ptr(), nt, out.data_ptr(), cnt.data_ptr())
+
+    for _ in range(2):
+        step()
+    barrier()
+    ctx.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 5
+    ev0.record(stream)
+    for _ in range(steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    k4_ms, k4_n = ctx.profile_read(1)
+    ctx.profile_enable(False)
+    ms = ev0.elapsed_time(ev1) / steps
+    pairs = float(nq) * nt
+    k4_avg = k4_ms / max(k4_n, 1)            # two K4 launches per step (forward kNN, column minima)
+    popc_peak = 148 * 16 * 1.965e9 / 8       # pairs/s: 8 POPC.32 per 256-bit pair, 16 POPC/clk/SM (nominal)
+    return {"workload": "cfg3 shard: ORB-like 256-bit, 12500 x 100000, kNN-2 + column minima + cross-check",
+            "ms_per_step": ms, "pairs_per_s_knn_kernel": pairs / (k4_avg * 1e-3) if k4_n else None,
+            "pairs_per_s_step": 2 * pairs / (ms * 1e-3), "kernel_ms": k4_avg, "mutual_matches": int(cnt[0].item()),
+            "roofline": {"bound": "popc_issue", "peak_pairs_per_s": popc_peak,
+                         "frac": (pairs / (k4_avg * 1e-3)) / popc_peak if k4_n else None,
+                         "peak_source": "nominal 148 SM x 16 POPC/clk x 1965 MHz / 8 POPC per pair",
+                         "hbm_equivalent": {"bytes_per_pair": 64, "achieved_gbs": pairs * 64 / (k4_avg * 1e-3) / 1e9 if k4_n else None,
+                                            "peak_gbs": peaks["hbm"]}}}
 
 
 def bench_ransac(ctx, torch, dist, dev, world, rank, stream, barrier, peaks, args):
@@ -427,6 +481,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-ransac", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-hamming", action="store_true")
     ap.add_argument("--ransac-steps", type=int, default=5)
     ap.add_argument("--no-ramp", action="store_true", help="skip the 1 s clock ramp (profiling runs under ncu)")
     args = ap.parse_args()

@@ -5,9 +5,9 @@
 // midpoint rule), the ratio test / cross-check the north_star names for the same step,
 // and main.cpp:71-79 + 89-91 (index lists + KeyPoint::convert).
 //
-// All of it is streaming, HBM-bound work over <= a few MB: one coalesced pass for the
-// predicate + block counts, one tiny scan, one scatter pass (output stays in queryIdx
-// order, exactly like the reference's push_back loop).
+// All of it is streaming, HBM-bound work over <= a few MB: ONE kernel does predicate, scan
+// (decoupled look-back across tiles) and scatter; output stays in queryIdx order, exactly
+// like the reference's push_back loop.
 #include "pm_internal.h"
 
 namespace {
@@ -62,58 +62,60 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *total)
     return base + x - v;
 }
 
-template <class Pred>
-__global__ void __launch_bounds__(FB) compact_count_kernel(Pred pred, int n, int32_t *block_counts)
+// Single-pass order-preserving compaction (decoupled look-back).  Tiles take tickets from an
+// atomic counter, so a tile only ever waits on tiles that have already started.  status[t] =
+// epoch << 34 | state << 32 | value with state 1 = tile aggregate, 2 = inclusive prefix; the
+// epoch (one per call) makes stale words from earlier calls invisible, so nothing is cleared
+// between calls.  counter[epoch & 1] hands out tickets; tile 0 zeroes the other counter for
+// the next call.
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
 {
-    const int i = blockIdx.x * FB + threadIdx.x;
-    pm_dmatch m;
-    const int f = i < n ? (int)pred(i, m) : 0;
-    const int c = __syncthreads_count(f);
-    if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
-
-// single block: exclusive scan of block counts in place, total -> *n_out
-__global__ void __launch_bounds__(FB) compact_scan_kernel(int32_t *block_counts, int nblocks, int32_t *n_out)
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v)
 {
-    int carry = 0;
-    for (int b0 = 0; b0 < nblocks; b0 += FB) {
-        const int i = b0 + threadIdx.x;
-        const int v = i < nblocks ? block_counts[i] : 0;
-        int total;
-        const int ex = block_exclusive_scan(v, &total);
-        if (i < nblocks) block_counts[i] = carry + ex;
-        carry += total;
-    }
-    if (threadIdx.x == 0) *n_out = carry;
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 template <class Pred>
-__global__ void __launch_bounds__(FB) compact_scatter_kernel(Pred pred, int n, const int32_t *block_offsets,
-                                                             pm_dmatch *out)
+__global__ void __launch_bounds__(FB) compact_lookback_kernel(Pred pred, int n, pm_dmatch *out, int32_t *n_out,
+                                                              unsigned long long *status, unsigned *counter,
+                                                              unsigned epoch)
 {
-    const int i = blockIdx.x * FB + threadIdx.x;
+    __shared__ int s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(&counter[epoch & 1u], 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    const int ntiles = (n + FB - 1) / FB;
+    const int i = tile * FB + threadIdx.x;
     pm_dmatch m;
     const int f = i < n ? (int)pred(i, m) : 0;
     int total;
     const int ex = block_exclusive_scan(f, &total);
-    if (f) out[block_offsets[blockIdx.x] + ex] = m;
-}
-
-// small inputs: one CTA does predicate + scan + scatter in a single launch
-template <class Pred>
-__global__ void __launch_bounds__(FB) compact_single_kernel(Pred pred, int n, pm_dmatch *out, int32_t *n_out)
-{
-    int carry = 0;
-    for (int b0 = 0; b0 < n; b0 += FB) {
-        const int i = b0 + threadIdx.x;
-        pm_dmatch m;
-        const int f = i < n ? (int)pred(i, m) : 0;
-        int total;
-        const int ex = block_exclusive_scan(f, &total);
-        if (f) out[carry + ex] = m;
-        carry += total;
+    if (threadIdx.x == 0) {
+        const unsigned long long tag = (unsigned long long)epoch << 34;
+        int prefix = 0;
+        if (tile == 0) {
+            counter[(epoch + 1u) & 1u] = 0u;
+            st_volatile_u64(&status[0], tag | (2ull << 32) | (unsigned)total);
+        } else {
+            st_volatile_u64(&status[tile], tag | (1ull << 32) | (unsigned)total);
+            for (int p = tile - 1; p >= 0;) {
+                const unsigned long long v = ld_volatile_u64(&status[p]);
+                if ((v >> 34) != (unsigned long long)epoch) continue;          // not published yet
+                prefix += (int)(unsigned)(v & 0xFFFFFFFFull);
+                if (((v >> 32) & 3ull) == 2ull) break;
+                --p;
+            }
+            st_volatile_u64(&status[tile], tag | (2ull << 32) | (unsigned)(prefix + total));
+        }
+        s_prefix = prefix;
+        if (tile == ntiles - 1) *n_out = prefix + total;
     }
-    if (threadIdx.x == 0) *n_out = carry;
+    __syncthreads();
+    if (f) out[s_prefix + ex] = m;
 }
 
 template <class Pred>
@@ -123,18 +125,22 @@ int run_compact(pm_ctx *ctx, Pred pred, int n, pm_dmatch *dout, int32_t *dn_out)
         PM_CUDA(ctx, cudaMemsetAsync(dn_out, 0, sizeof(int32_t), ctx->stream));
         return PM_OK;
     }
-    if (n <= 16 * FB) {
-        compact_single_kernel<<<1, FB, 0, ctx->stream>>>(pred, n, dout, dn_out);
-        PM_CHECK_LAUNCH(ctx);
-        return PM_OK;
-    }
     const int nb = pm_cdiv(n, FB);
-    PM_WS(ctx, counts, int32_t *, WS_COUNT, (size_t)nb * sizeof(int32_t));
-    compact_count_kernel<<<nb, FB, 0, ctx->stream>>>(pred, n, counts);
-    PM_CHECK_LAUNCH(ctx);
-    compact_scan_kernel<<<1, FB, 0, ctx->stream>>>(counts, nb, dn_out);
-    PM_CHECK_LAUNCH(ctx);
-    compact_scatter_kernel<<<nb, FB, 0, ctx->stream>>>(pred, n, counts, dout);
+    const size_t need = (size_t)(nb + 2) * 8;
+    const bool fresh = ctx->slot_bytes[WS_COUNT] < need;
+    PM_WS(ctx, st, unsigned long long *, WS_COUNT, need);
+    if (fresh) {        // newly (re)allocated: all epochs 0 / counters 0
+        PM_CUDA(ctx, cudaMemsetAsync(st, 0, ctx->slot_bytes[WS_COUNT], ctx->stream));
+        ctx->compact_epoch = 0;
+    }
+    const unsigned epoch = ++ctx->compact_epoch;
+    if (epoch >= (1u << 29)) {   // keep the 30-bit tag from wrapping into a stale match
+        PM_CUDA(ctx, cudaMemsetAsync(st, 0, ctx->slot_bytes[WS_COUNT], ctx->stream));
+        ctx->compact_epoch = 0;
+        return run_compact(ctx, pred, n, dout, dn_out);
+    }
+    unsigned *counter = reinterpret_cast<unsigned *>(st);          // st[0]: two ticket counters
+    compact_lookback_kernel<<<nb, FB, 0, ctx->stream>>>(pred, n, dout, dn_out, st + 1, counter, epoch);
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }

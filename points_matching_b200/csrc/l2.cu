@@ -33,25 +33,47 @@ __device__ __forceinline__ float warp_sum_butterfly(float p)
 template <typename T> __device__ __forceinline__ float load_elem(const T *p, size_t i) { return (float)p[i]; }
 
 // ---------------------------------------------------------------------------------
-// K1: one warp per row.  Writes [hi|lo] bf16 (train rows pre-scaled by -2), ||row||^2,
-// the exact-integer flag, max train norm, and (query side) the +inf candidate init.
+// K1: one warp per row, query and train rows in ONE launch (rows [0, mq_pad) are query
+// rows, the rest train rows).  Writes [hi|lo] bf16 (train rows pre-scaled by -2),
+// ||row||^2 (train pad rows: +inf), the integer-valued flag, the max norms, and (query
+// side) the +inf candidate init.  Pure streaming: 16 B loads, 8 B stores per lane.
 // ---------------------------------------------------------------------------------
+__device__ __forceinline__ void load_row4(const float *p, int lane, int dim, bool vec, float (&x)[4])
+{
+    if (vec) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(p) + lane);
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[e] = 4 * lane + e < dim ? __ldg(p + 4 * lane + e) : 0.f;
+    }
+}
+__device__ __forceinline__ void load_row4(const uint8_t *p, int lane, int dim, bool vec, float (&x)[4])
+{
+    if (vec) {
+        const uchar4 v = __ldg(reinterpret_cast<const uchar4 *>(p) + lane);
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[e] = 4 * lane + e < dim ? (float)__ldg(p + 4 * lane + e) : 0.f;
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
-l2_pack_kernel(const T *__restrict__ src, int n, int dim, int n_pad, int is_train,
-               __nv_bfloat16 *__restrict__ pack, float *__restrict__ norm, L2Flags *flags,
+l2_pack_kernel(const T *__restrict__ q, int nq, int mq_pad, const T *__restrict__ t, int nt, int nt_pad, int dim,
+               int vec, __nv_bfloat16 *__restrict__ qpack, __nv_bfloat16 *__restrict__ tpack,
+               float *__restrict__ qnorm, float *__restrict__ tnorm, L2Flags *flags,
                L2Cand *__restrict__ part, int part_per_row)
 {
     const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= n_pad) return;
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const bool is_train = row >= mq_pad;
+    if (is_train) row -= mq_pad;
+    const int n = is_train ? nt : nq;
+    if (row >= (is_train ? nt_pad : mq_pad)) return;
     float x[4] = {0.f, 0.f, 0.f, 0.f};
-    if (row < n) {
-        const T *p = src + (size_t)row * dim;
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (4 * lane + e < dim) x[e] = load_elem(p, 4 * lane + e);
-    }
+    if (row < n) load_row4((is_train ? t : q) + (size_t)row * dim, lane, dim, vec != 0, x);
     float s = 0.f;
     bool integral = true;
 #pragma unroll
@@ -68,13 +90,20 @@ l2_pack_kernel(const T *__restrict__ src, int n, int dim, int n_pad, int is_trai
         hi[e] = __float2bfloat16_rn(v);
         lo[e] = __float2bfloat16_rn(v - __bfloat162float(hi[e]));
     }
-    __nv_bfloat16 *dst = pack + (size_t)row * L2_PACK_COLS;
+    __nv_bfloat16 *dst = (is_train ? tpack : qpack) + (size_t)row * L2_PACK_COLS;
     *reinterpret_cast<uint2 *>(dst + 4 * lane) = *reinterpret_cast<uint2 *>(hi);
     *reinterpret_cast<uint2 *>(dst + L2_KDIM + 4 * lane) = *reinterpret_cast<uint2 *>(lo);
-    if (lane == 0) norm[row] = row < n ? s : (is_train ? L2_INF : 0.f);
+    if (lane == 0) {
+        if (is_train) {
+            tnorm[row] = row < n ? s : L2_INF;
+            if (row < n) atomicMax(&flags->max_tnorm_bits, __float_as_uint(s));
+        } else {
+            qnorm[row] = row < n ? s : 0.f;
+            if (row < n) atomicMax(&flags->max_qnorm_bits, __float_as_uint(s));
+        }
+    }
     if (!__all_sync(0xffffffffu, integral) && lane == 0) flags->nonexact = 1;
-    if (is_train && row < n && lane == 0) atomicMax(&flags->max_tnorm_bits, __float_as_uint(s));
-    if (part)
+    if (!is_train)
         for (int k = lane; k < part_per_row; k += 32) part[(size_t)row * part_per_row + k] = L2Cand{L2_INF, -1};
 }
 
@@ -115,18 +144,20 @@ __device__ __forceinline__ float warp_l2sq_regs(const float (&a)[4], const float
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__restrict__ qnorm,
-                 const float *__restrict__ q, const float *__restrict__ t, int nq, int dim,
-                 L2Flags *flags, int *__restrict__ flagged, int q_index_base, pm_dmatch *__restrict__ out)
+                 const float *__restrict__ q, const float *__restrict__ t, int nq, int nt, int dim,
+                 L2Flags *flags, L2Flags *flags_next, int *__restrict__ flagged, int q_index_base,
+                 pm_dmatch *__restrict__ out)
 {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *flags_next = L2Flags{0, 0u, 0u, 0};   // the next call's block
     if (i >= nq) return;
     // lane-local sorted triple over this lane's strided share of the candidates, then three
     // rounds of warp arg-min over the lane heads (keys are unique: distinct train indices)
     unsigned long long h0 = ~0ull, h1 = ~0ull, h2 = ~0ull;
     for (int c0 = lane; c0 < ncand; c0 += 32) {
         const L2Cand c = part[(size_t)i * ncand + c0];
-        if (c.idx < 0) continue;
+        if (c.idx < 0 || c.idx >= nt) continue;          // absent, or a pad column
         const unsigned long long key = ((unsigned long long)f2ord(c.d) << 32) | (unsigned)c.idx;
         if (key < h2) {
             if (key < h1) {
@@ -148,7 +179,7 @@ l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__rest
         idx[r] = k[r] == ~0ull ? -1 : (int)(k[r] & 0xFFFFFFFFu);
         d2[r] = k[r] == ~0ull ? L2_INF : ord2f((unsigned)(k[r] >> 32)) + na;
     }
-    const bool split = flags->nonexact != 0;
+    const bool split = !l2_exact_mode(*flags);
     bool certified = true;
     if (split) {
         const float bound = d2[2];        // approx d^2 of the third candidate: every non-candidate is >= this
@@ -255,7 +286,7 @@ int run_exact(pm_ctx *ctx, const T *dq, const T *dt, int nq, int nt, int dim, co
 {
     const int dim_pad = (dim + 127) / 128 * 128;
     const size_t smem = (size_t)dim_pad * 4 + 8 * 4 * 4;
-    const int grid = min(nq, 8 * ctx->num_sms);
+    const int grid = rows ? min(nq, ctx->num_sms) : min(nq, 8 * ctx->num_sms);
     l2_exact_kernel<T><<<grid, 256, smem, ctx->stream>>>(dq, dt, nq, nt, dim, rows, count, base, dout);
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
@@ -283,34 +314,38 @@ int pmk_l2_knn2(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int
         if (is_u8) return run_exact(ctx, (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, nullptr, nullptr, q_index_base, dout);
         return run_exact(ctx, (const float *)dq, (const float *)dt, nq, nt, dim, nullptr, nullptr, q_index_base, dout);
     }
-    PM_WS(ctx, flags, L2Flags *, WS_L2_FLAGS, sizeof(L2Flags));
+    const bool fresh_flags = ctx->slot_ptr[WS_L2_FLAGS] == nullptr;
+    PM_WS(ctx, flags2, L2Flags *, WS_L2_FLAGS, 2 * sizeof(L2Flags));
+    if (fresh_flags) { PM_CUDA(ctx, cudaMemsetAsync(flags2, 0, 2 * sizeof(L2Flags), ctx->stream)); ctx->l2_parity = 0; }
+    // two flag blocks: this call uses one, K3 zeroes the other for the next call (no memset)
+    L2Flags *flags = flags2 + ctx->l2_parity, *flags_next = flags2 + (ctx->l2_parity ^ 1);
     PM_WS(ctx, qpack, __nv_bfloat16 *, WS_Q_PACK, (size_t)mq_pad * L2_PACK_COLS * 2);
     PM_WS(ctx, tpack, __nv_bfloat16 *, WS_T_PACK, (size_t)nt_pad * L2_PACK_COLS * 2);
     PM_WS(ctx, qnorm, float *, WS_Q_NORM, (size_t)mq_pad * 4);
     PM_WS(ctx, tnorm, float *, WS_T_NORM, (size_t)nt_pad * 4);
     PM_WS(ctx, part, L2Cand *, WS_L2_PART, (size_t)mq_pad * smax * 3 * sizeof(L2Cand));
     PM_WS(ctx, flagged, int *, WS_L2_FLAGGED, (size_t)nq * 4);
-    PM_CUDA(ctx, cudaMemsetAsync(flags, 0, sizeof(L2Flags), ctx->stream));
+    const int pack_blocks = pm_cdiv(mq_pad + nt_pad, 8);
     if (is_u8) {
-        l2_pack_kernel<uint8_t><<<pm_cdiv(nt_pad, 8), 256, 0, ctx->stream>>>((const uint8_t *)dt, nt, dim, nt_pad, 1, tpack, tnorm, flags, nullptr, 0);
-        PM_CHECK_LAUNCH(ctx);
-        l2_pack_kernel<uint8_t><<<pm_cdiv(mq_pad, 8), 256, 0, ctx->stream>>>((const uint8_t *)dq, nq, dim, mq_pad, 0, qpack, qnorm, flags, part, smax * 3);
-        PM_CHECK_LAUNCH(ctx);
+        const int vec = dim == L2_KDIM && (((uintptr_t)dq | (uintptr_t)dt) & 3) == 0;
+        l2_pack_kernel<uint8_t><<<pack_blocks, 256, 0, ctx->stream>>>((const uint8_t *)dq, nq, mq_pad, (const uint8_t *)dt, nt, nt_pad, dim, vec,
+                                                                      qpack, tpack, qnorm, tnorm, flags, part, smax * 3);
     } else {
-        l2_pack_kernel<float><<<pm_cdiv(nt_pad, 8), 256, 0, ctx->stream>>>((const float *)dt, nt, dim, nt_pad, 1, tpack, tnorm, flags, nullptr, 0);
-        PM_CHECK_LAUNCH(ctx);
-        l2_pack_kernel<float><<<pm_cdiv(mq_pad, 8), 256, 0, ctx->stream>>>((const float *)dq, nq, dim, mq_pad, 0, qpack, qnorm, flags, part, smax * 3);
-        PM_CHECK_LAUNCH(ctx);
+        const int vec = dim == L2_KDIM && (((uintptr_t)dq | (uintptr_t)dt) & 15) == 0;
+        l2_pack_kernel<float><<<pack_blocks, 256, 0, ctx->stream>>>((const float *)dq, nq, mq_pad, (const float *)dt, nt, nt_pad, dim, vec,
+                                                                    qpack, tpack, qnorm, tnorm, flags, part, smax * 3);
     }
+    PM_CHECK_LAUNCH(ctx);
     int st = l2_tc_launch(ctx, qpack, mq_pad, tpack, nt_pad, tnorm, flags, part, smax, g_l2_dump);
     if (st != PM_OK) return st;
-    l2_finish_kernel<<<pm_cdiv(nq, 8), 256, 0, ctx->stream>>>(part, smax * 3, qnorm, (const float *)dq, (const float *)dt, nq, dim,
-                                                               flags, flagged, q_index_base, dout);
+    l2_finish_kernel<<<pm_cdiv(nq, 8), 256, 0, ctx->stream>>>(part, smax * 3, qnorm, (const float *)dq, (const float *)dt, nq, nt, dim,
+                                                               flags, flags_next, flagged, q_index_base, dout);
     PM_CHECK_LAUNCH(ctx);
-    if (!is_u8) {   // u8 input is always exact-integer mode: nothing can be flagged
+    if (!is_u8) {   // u8 input is always integer-valued: with SIFT-range norms nothing can be flagged
         int s2 = run_exact(ctx, (const float *)dq, (const float *)dt, nq, nt, dim, flagged, &flags->n_flagged, q_index_base, dout);
         if (s2 != PM_OK) return s2;
     }
+    ctx->l2_parity ^= 1;
     ctx->l2_stats[3] = smax;
     return PM_OK;
 }
@@ -319,13 +354,15 @@ int pm_l2_stats(pm_ctx *ctx, int32_t out[4])
 {
     if (!ctx) return PM_BAD_ARG;
     L2Flags h = {};
-    if (ctx->slot_ptr[WS_L2_FLAGS]) {
+    if (ctx->slot_ptr[WS_L2_FLAGS]) {     // the block the last call used (parity was flipped after it)
         PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        PM_CUDA(ctx, cudaMemcpy(&h, ctx->slot_ptr[WS_L2_FLAGS], sizeof(h), cudaMemcpyDeviceToHost));
+        PM_CUDA(ctx, cudaMemcpy(&h, (const L2Flags *)ctx->slot_ptr[WS_L2_FLAGS] + (ctx->l2_parity ^ 1), sizeof(h),
+                                cudaMemcpyDeviceToHost));
     }
-    out[0] = ctx->l2_stats[3] ? !h.nonexact : 0;
+    const bool exact = l2_exact_mode(h);
+    out[0] = ctx->l2_stats[3] ? exact : 0;
     out[1] = h.n_flagged;
-    out[2] = ctx->l2_stats[3] ? (h.nonexact ? 6 : 2) : 0;
+    out[2] = ctx->l2_stats[3] ? (exact ? 2 : 6) : 0;
     out[3] = ctx->l2_stats[3];
     return PM_OK;
 }

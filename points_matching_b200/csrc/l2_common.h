@@ -5,6 +5,11 @@
 // Packed operand row: [hi bf16 x128 | lo bf16 x128] = 512 B (K padded to 128).
 #define L2_PACK_COLS 256
 #define L2_KDIM 128
+// exact-integer mode: t + L2_EXACT_BIAS lies in [2^23, 2^24) -> unit spacing, so the low 24
+// bits of the float are (0x400000 + t) and order like the integers themselves
+#define L2_EXACT_BIAS 12582912.0f          /* 1.5 * 2^23 */
+#define L2_EXACT_PAD 16777215.0f           /* pad columns: largest value of that binade */
+#define L2_EXACT_NORM_LIMIT_BITS 0x4A800000u /* 2^22 as float bits: max ||.||^2 for exact mode */
 
 struct L2Cand {        // one candidate: approximate (||b||^2 - 2ab) and train index
     float d;
@@ -12,14 +17,28 @@ struct L2Cand {        // one candidate: approximate (||b||^2 - 2ab) and train i
 };
 
 struct L2Flags {
-    int nonexact;              // !=0: some value is not an integer in [0,255] -> split mode
+    int nonexact;              // !=0: some value is not an integer in [0,255]
     unsigned max_tnorm_bits;   // max ||b||^2 over real train rows (float bits)
+    unsigned max_qnorm_bits;   // max ||a||^2 over real query rows (float bits)
     int n_flagged;             // rows K3 could not certify -> exact fallback
-    int pad;
 };
+
+// exact-integer mode: integer-valued data and norms small enough for the biased key
+static __host__ __device__ __forceinline__ bool l2_exact_mode(const L2Flags &f)
+{
+    return !f.nonexact && f.max_tnorm_bits < L2_EXACT_NORM_LIMIT_BITS && f.max_qnorm_bits < L2_EXACT_NORM_LIMIT_BITS;
+}
+#ifdef __CUDACC__
+// split mode: shift added to every column norm so that (||b||^2 - 2ab + shift) > 0 and its
+// float bits order like unsigned integers
+static __device__ __forceinline__ float l2_split_shift(unsigned max_qnorm_bits)
+{
+    return __uint_as_float(max_qnorm_bits) * 1.001f + 1e-30f;
+}
+#endif
 
 struct pm_ctx;
 int l2_tc_grid(pm_ctx *ctx, int MT, int NT);
 int l2_tc_smax(pm_ctx *ctx, int MT, int NT);
-int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, int nt_pad, const float *tnorm,
-                 const L2Flags *flags, L2Cand *part, int smax, float *dump);
+int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, int nt_pad,
+                 const float *tnorm, const L2Flags *flags, L2Cand *part, int smax, float *dump);

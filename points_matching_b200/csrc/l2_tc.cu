@@ -1,4 +1,4 @@
-// l2_tc.cu -- K2: L2 distance GEMM on tcgen05 tensor cores with the top-3 selection fused
+// l2_tc.cu -- K2: L2 distance GEMM on tcgen05 tensor cores with the top-k selection fused
 // into the epilogue (the distance matrix never reaches HBM).  sm_100a only.
 //
 // Replaces the all-pairs distance + per-row k-smallest inside
@@ -12,14 +12,17 @@
 //   exact-integer mode (SIFT, values 0..255): lo == 0, 2 k-blocks, the GEMM is exact
 //   split mode (general floats):  a.b ~ ah.bh + ah.bl + al.bh, 6 k-blocks
 //
-// Structure (one persistent CTA per SM, 384 threads):
+// Structure (one persistent CTA per SM, 320 threads):
 //   warp 0      TMA producer   : A row-tile resident (<= 4 x 16 KB), B k-blocks through a
 //                                4-stage 32 KB ring (cp.async.bulk.tensor, SWIZZLE_128B)
 //   warp 1      MMA issuer     : tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16,
-//                                accumulators double-buffered in TMEM (2 x 256 columns)
-//   warp 2      TMEM allocator
-//   warps 4-11  epilogue       : tcgen05.ld 32x32b.x32, + ||b||^2, per-thread running
-//                                (best, second, third) kept in registers across the sweep
+//                                accumulators double-buffered in TMEM (2 x 256 columns);
+//                                also allocates / frees TMEM
+//   warps 2-9   epilogue       : tcgen05.ld 32x32b.x32, + ||b||^2, pack (value | column) into
+//                                one u32 key, branch-free min/max tournament (VIMNMX/VIMNMX3):
+//                                top-2 in exact mode, top-3 in split mode, kept in registers
+//                                across the whole sweep.  The ALU pipe is the binding
+//                                resource (2.5 / 5 min-max ops per element), not the MMA.
 // Each CTA walks a contiguous range of the (row-tile, column-tile) space; per row tile it
 // writes one "segment" of candidates which K3 merges, re-ranks in FP32 and certifies.
 #include <cuda.h>
@@ -33,13 +36,14 @@ constexpr int A_BLK_BYTES = BM * BK * 2;     // 16 KB
 constexpr int B_BLK_BYTES = BN * BK * 2;     // 32 KB
 constexpr int NSTAGE = 4;
 constexpr int A_MAXBLK = 4;
-constexpr int TC_THREADS = 384;
-constexpr int EPI_WARP0 = 4;
+constexpr int TC_THREADS = 320;     // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-9 epilogue
+constexpr int EPI_WARP0 = 2;
 constexpr int SMEM_A = 0;
 constexpr int SMEM_B = A_MAXBLK * A_BLK_BYTES;                 // 65536
 constexpr int SMEM_BAR = SMEM_B + NSTAGE * B_BLK_BYTES;        // 196608
 constexpr int SMEM_SCRATCH = SMEM_BAR + 256;
-constexpr int SMEM_TOTAL = SMEM_SCRATCH + BM * 6 * 4 + 1024;   // + alignment slack
+constexpr int SMEM_NORM = SMEM_SCRATCH + BM * 6 * 4;           // 2 x 256 column norms
+constexpr int SMEM_TOTAL = SMEM_NORM + 2 * BN * 4 + 1024;      // + alignment slack
 
 // instruction descriptor: D=F32, A=B=BF16, K-major both, N=256, M=128
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
@@ -111,29 +115,99 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-struct Top3 {
-    float d1, d2, d3;
-    int i1, i2, i3;
-    __device__ __forceinline__ void reset()
+// ---------------------------------------------------------------------------------------
+// epilogue: branch-free selection on packed keys.
+//   exact mode: acc + (||b||^2 + 1.5*2^23) is an integer-valued float in [2^23, 2^24), so
+//               bits * 256 + (c+1) = ((0x400000 + t) << 8) | (c+1) orders by (t, column).
+//   split mode: acc + (||b||^2 + shift) > 0, key = (bits & ~0xFF) | (c+1) (PRMT): the value is
+//               truncated by <= 2^-15 relative, which only lowers the certification bound.
+// The low byte (c+1 in 1..128, this thread's column within the tile) is non-zero for keys of
+// the current tile and zeroed on carried keys, so an equal distance from an earlier tile
+// always wins (lowest train index), and "which entries are new" needs no comparisons.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u32(a, b, c); }
+
+struct Sel2 {   // exact mode: running (best, second)
+    uint32_t m1, m2; int i1, i2;
+    __device__ __forceinline__ void reset() { m1 = m2 = 0xFFFFFFFFu; i1 = i2 = -1; }
+    // top-2 of 32 keys by a tournament (80 min/max ops), merged into the running pair
+    __device__ __forceinline__ void chunk(uint32_t (&k)[32])
     {
-        d1 = d2 = d3 = __int_as_float(0x7f800000);
-        i1 = i2 = i3 = -1;
+        uint32_t lo[16], hi[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { lo[i] = min(k[2 * i], k[2 * i + 1]); hi[i] = max(k[2 * i], k[2 * i + 1]); }
+#pragma unroll
+        for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+            for (int i = 0; i < w; ++i) {
+                const uint32_t L = min(lo[i], lo[i + w]);
+                const uint32_t S = umin3(max(lo[i], lo[i + w]), hi[i], hi[i + w]);
+                lo[i] = L; hi[i] = S;
+            }
+        m2 = umin3(m2, hi[0], max(m1, lo[0]));
+        m1 = min(m1, lo[0]);
     }
-    // strict <: columns arrive in ascending order, so the lowest index wins ties
+    // after a tile: resolve the indices of entries that came from it, zero their column byte
+    __device__ __forceinline__ void end_tile(int col0)
+    {
+        const uint32_t n1 = m1 & 0xFFu, n2 = m2 & 0xFFu;
+        const int g1 = col0 + (int)n1 - 1, g2 = col0 + (int)n2 - 1;
+        i2 = n2 ? g2 : (n1 ? i1 : i2);      // a carried second is the old best when a new best arrived
+        i1 = n1 ? g1 : i1;
+        m1 &= ~0xFFu; m2 &= ~0xFFu;
+    }
+    __device__ __forceinline__ float value(uint32_t m) const { return (float)((int)(m >> 8) - 0x400000); }
+};
+
+struct Sel3 {   // split mode: running (best, second, third)
+    uint32_t m1, m2, m3; int i1, i2, i3;
+    __device__ __forceinline__ void reset() { m1 = m2 = m3 = 0xFFFFFFFFu; i1 = i2 = i3 = -1; }
+    __device__ __forceinline__ void chunk(uint32_t (&k)[32])
+    {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {       // sorted pair (lo, hi) into the sorted triple: 8 ops / 2 elements
+            const uint32_t lo = min(k[2 * i], k[2 * i + 1]), hi = max(k[2 * i], k[2 * i + 1]);
+            const uint32_t c3 = umin3(max(m1, hi), max(m2, lo), m3);
+            const uint32_t c2 = umin3(hi, max(m1, lo), m2);
+            m1 = min(m1, lo); m2 = c2; m3 = c3;
+        }
+    }
+    __device__ __forceinline__ void end_tile(int col0)
+    {
+        const uint32_t n1 = m1 & 0xFFu, n2 = m2 & 0xFFu, n3 = m3 & 0xFFu;
+        const int g1 = col0 + (int)n1 - 1, g2 = col0 + (int)n2 - 1, g3 = col0 + (int)n3 - 1;
+        const int o1 = i1, o2 = i2, o3 = i3;
+        // carried entries keep their order: the p-th carried slot takes the p-th old index
+        const int c1 = n1 ? 0 : 1;                   // carried entries consumed before slot 2
+        const int c2 = c1 + (n2 ? 0 : 1);            // ... before slot 3
+        i1 = n1 ? g1 : o1;
+        i2 = n2 ? g2 : (c1 ? o2 : o1);
+        i3 = n3 ? g3 : (c2 == 0 ? o1 : (c2 == 1 ? o2 : o3));
+        m1 &= ~0xFFu; m2 &= ~0xFFu; m3 &= ~0xFFu;
+    }
+};
+
+// lexicographic (value, index) insert used when merging the two column halves at a flush
+struct Cand3 {
+    float d[3]; int i[3];
+    __device__ __forceinline__ void reset() { d[0] = d[1] = d[2] = __int_as_float(0x7f800000); i[0] = i[1] = i[2] = -1; }
+    __device__ __forceinline__ static bool less(float da, int ia, float db, int ib)
+    { return da < db || (da == db && (unsigned)ia < (unsigned)ib); }
     __device__ __forceinline__ void insert(float t, int idx)
     {
-        if (t < d3) {
-            if (t < d2) {
-                d3 = d2; i3 = i2;
-                if (t < d1) { d2 = d1; i2 = i1; d1 = t; i1 = idx; }
-                else { d2 = t; i2 = idx; }
-            } else { d3 = t; i3 = idx; }
+        if (idx < 0) return;
+        if (less(t, idx, d[2], i[2])) {
+            if (less(t, idx, d[1], i[1])) {
+                d[2] = d[1]; i[2] = i[1];
+                if (less(t, idx, d[0], i[0])) { d[1] = d[0]; i[1] = i[0]; d[0] = t; i[0] = idx; }
+                else { d[1] = t; i[1] = idx; }
+            } else { d[2] = t; i[2] = idx; }
         }
     }
 };
 
 struct TcParams {
-    const float *tnorm;          // [nt_pad] ||b||^2, +inf on pad rows
+    const float *tnorm;          // [nt_pad] ||b||^2 (pad columns: +inf)
     const L2Flags *flags;
     L2Cand *part;                // [mq_pad][smax][3]
     float *dump;                 // debug: [mq_pad][nt_pad] of (||b||^2 - 2ab), or null
@@ -154,8 +228,10 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     L2Cand *scratch = reinterpret_cast<L2Cand *>(sgen + SMEM_SCRATCH);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkb = P.flags->nonexact ? 6 : 2;
-    const int nablk = P.flags->nonexact ? 4 : 2;
+    const L2Flags fl = *P.flags;
+    const bool exact = l2_exact_mode(fl);
+    const int nkb = exact ? 2 : 6;
+    const int nablk = exact ? 2 : 4;
 
     const long long T = (long long)P.MT * P.NT;
     const int G = gridDim.x;
@@ -172,7 +248,8 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {
+    if (warp == 1) {
+        __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32((const void *)tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -239,19 +316,34 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         const int quarter = warp & 3;          // TMEM lane quarter this warp may access
         const int half = e >> 2;               // which 128 of the tile's 256 columns
         const int row = quarter * 32 + lane;   // row within the 128-row tile
+        const float shift = l2_split_shift(fl.max_qnorm_bits);
+        const float *tnorm = P.tnorm;
+        const float nb_off = exact ? L2_EXACT_BIAS : shift;     // folded into the staged column norms
+        float *snorm = reinterpret_cast<float *>(sgen + SMEM_NORM);     // [2][256] by accumulator parity
+        const int et = e * 32 + lane;                                   // 0..255: column this thread stages
         uint32_t acc = 0, acc_phase = 0; int cur_m = -1;
-        Top3 best; best.reset();
+        float nb_pref = t_begin < t_end ? __ldg(tnorm + (t_begin % P.NT) * BN + et) : 0.f;
+        Sel2 s2; s2.reset();
+        Sel3 s3; s3.reset();
 
         auto flush = [&](int m) {
+            Cand3 c; c.reset();
+            if (exact) {
+                if ((s2.m1 >> 8) != 0xFFFFFFu) c.insert(s2.value(s2.m1), s2.i1);
+                if ((s2.m2 >> 8) != 0xFFFFFFu) c.insert(s2.value(s2.m2), s2.i2);
+            } else {
+                if (s3.m1 != 0xFFFFFF00u) c.insert(__uint_as_float(s3.m1) - shift, s3.i1);
+                if (s3.m2 != 0xFFFFFF00u) c.insert(__uint_as_float(s3.m2) - shift, s3.i2);
+                if (s3.m3 != 0xFFFFFF00u) c.insert(__uint_as_float(s3.m3) - shift, s3.i3);
+            }
             if (half == 1) {
-                scratch[row * 3 + 0] = L2Cand{best.d1, best.i1};
-                scratch[row * 3 + 1] = L2Cand{best.d2, best.i2};
-                scratch[row * 3 + 2] = L2Cand{best.d3, best.i3};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) scratch[row * 3 + k] = L2Cand{c.d[k], c.i[k]};
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (half == 0) {
-                // upper-half indices are all larger: strict < keeps the lower index on ties
-                for (int k = 0; k < 3; ++k) { const L2Cand c = scratch[row * 3 + k]; best.insert(c.d, c.idx); }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { const L2Cand o = scratch[row * 3 + k]; c.insert(o.d, o.idx); }
                 // segment slot = index of this CTA among the CTAs that touch row tile m
                 const long long first_tile = (long long)m * P.NT;
                 int c0 = (int)((first_tile * G) / T);
@@ -259,12 +351,11 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                 while ((T * c0) / G > first_tile) --c0;
                 const int slot = (int)blockIdx.x - c0;
                 L2Cand *dst = P.part + ((size_t)(m * BM + row) * P.smax + slot) * 3;
-                dst[0] = L2Cand{best.d1, best.i1};
-                dst[1] = L2Cand{best.d2, best.i2};
-                dst[2] = L2Cand{best.d3, best.i3};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) dst[k] = L2Cand{c.d[k], c.i[k]};
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            best.reset();
+            s2.reset(); s3.reset();
         };
 
         for (int tile = t_begin; tile < t_end; ++tile) {
@@ -274,32 +365,54 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
             tc_fence_after();
             const int col0 = n * BN + half * 128;
             const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128;
-#pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t r[32];
-                tmem_ld32(taddr0 + ch * 32, r);
-                float nb[32];
-                const float4 *np = reinterpret_cast<const float4 *>(P.tnorm + col0 + ch * 32);
+            // stage this tile's 256 column norms in shared memory (prefetched one tile ahead),
+            // so the hot loop reads them with broadcast LDS.128 instead of waiting on L2
+            snorm[acc * BN + et] = (exact && nb_pref == __int_as_float(0x7f800000)) ? L2_EXACT_PAD : nb_pref + nb_off;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tile + 1 < t_end) nb_pref = __ldg(tnorm + ((tile + 1) % P.NT) * BN + et);
+            const float4 *np = reinterpret_cast<const float4 *>(snorm + acc * BN + half * 128);
+            uint32_t rb[2][32];
+            tmem_ld32(taddr0, rb[0]);
+            tmem_ld_wait();
 #pragma unroll
-                for (int v = 0; v < 8; ++v) {
-                    const float4 x = __ldg(np + v);
-                    nb[4 * v] = x.x; nb[4 * v + 1] = x.y; nb[4 * v + 2] = x.z; nb[4 * v + 3] = x.w;
-                }
-                tmem_ld_wait();
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t (&r)[32] = rb[ch & 1];
+                if (ch < 3) tmem_ld32(taddr0 + (ch + 1) * 32, rb[(ch + 1) & 1]);   // overlaps the math below
                 if (P.dump) {
                     float *drow = P.dump + (size_t)(m * BM + row) * P.nt_pad + col0 + ch * 32;
+                    const float off = exact ? L2_EXACT_BIAS : shift;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) drow[c] = __uint_as_float(r[c]) + nb[c];
+                    for (int c = 0; c < 32; ++c) drow[c] = __uint_as_float(r[c]) + snorm[acc * BN + half * 128 + ch * 32 + c] - off;
                 }
+                if (exact) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const float t = __uint_as_float(r[c]) + nb[c];
-                    best.insert(t, col0 + ch * 32 + c);
+                    for (int v = 0; v < 8; ++v) {
+                        const float4 x = np[ch * 8 + v];
+                        const int c = 4 * v;
+                        r[c] = __float_as_uint(__uint_as_float(r[c]) + x.x) * 256u + (uint32_t)(ch * 32 + c + 1);
+                        r[c + 1] = __float_as_uint(__uint_as_float(r[c + 1]) + x.y) * 256u + (uint32_t)(ch * 32 + c + 2);
+                        r[c + 2] = __float_as_uint(__uint_as_float(r[c + 2]) + x.z) * 256u + (uint32_t)(ch * 32 + c + 3);
+                        r[c + 3] = __float_as_uint(__uint_as_float(r[c + 3]) + x.w) * 256u + (uint32_t)(ch * 32 + c + 4);
+                    }
+                    s2.chunk(r);
+                } else {
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        const float4 x = np[ch * 8 + v];
+                        const int c = 4 * v;
+                        r[c] = __byte_perm(__float_as_uint(__uint_as_float(r[c]) + x.x), (uint32_t)(ch * 32 + c + 1), 0x3214);
+                        r[c + 1] = __byte_perm(__float_as_uint(__uint_as_float(r[c + 1]) + x.y), (uint32_t)(ch * 32 + c + 2), 0x3214);
+                        r[c + 2] = __byte_perm(__float_as_uint(__uint_as_float(r[c + 2]) + x.z), (uint32_t)(ch * 32 + c + 3), 0x3214);
+                        r[c + 3] = __byte_perm(__float_as_uint(__uint_as_float(r[c + 3]) + x.w), (uint32_t)(ch * 32 + c + 4), 0x3214);
+                    }
+                    s3.chunk(r);
                 }
+                if (ch < 3) tmem_ld_wait();
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+            if (exact) s2.end_tile(col0); else s3.end_tile(col0);
             acc ^= 1; if (acc == 0) acc_phase ^= 1;
         }
         if (cur_m >= 0) flush(cur_m);
@@ -307,7 +420,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -366,18 +479,25 @@ int l2_tc_smax(pm_ctx *ctx, int MT, int NT)
     return smax;
 }
 
-int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, int nt_pad, const float *tnorm,
-                 const L2Flags *flags, L2Cand *part, int smax, float *dump)
+int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, int nt_pad,
+                 const float *tnorm, const L2Flags *flags, L2Cand *part, int smax, float *dump)
 {
     static bool attr_set = false;
     if (!attr_set) {
         PM_CUDA(ctx, cudaFuncSetAttribute(l2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
         attr_set = true;
     }
-    CUtensorMap tq, tt;
-    int st;
-    if ((st = make_tmap(ctx, &tq, qpack, mq_pad, BM)) != PM_OK) return st;
-    if ((st = make_tmap(ctx, &tt, tpack, nt_pad, BN)) != PM_OK) return st;
+    static_assert(sizeof(CUtensorMap) == 128, "tmap_store size");
+    CUtensorMap *tmaps = reinterpret_cast<CUtensorMap *>(ctx->tmap_store);
+    const void *bases[2] = {qpack, tpack};
+    const int rows[2] = {mq_pad, nt_pad}, boxes[2] = {BM, BN};
+    for (int k = 0; k < 2; ++k)
+        if (ctx->tmap_base[k] != bases[k] || ctx->tmap_rows[k] != rows[k]) {   // re-encode only when the operand moved
+            int st = make_tmap(ctx, &tmaps[k], bases[k], rows[k], boxes[k]);
+            if (st != PM_OK) return st;
+            ctx->tmap_base[k] = bases[k]; ctx->tmap_rows[k] = rows[k];
+        }
+    const CUtensorMap &tq = tmaps[0], &tt = tmaps[1];
     TcParams P;
     P.tnorm = tnorm; P.flags = flags; P.part = part; P.dump = dump;
     P.MT = mq_pad / BM; P.NT = nt_pad / BN; P.smax = smax; P.nt_pad = nt_pad;

@@ -30,7 +30,13 @@ struct pm_ctx {
     uint64_t launches = 0;
     std::string err;
     int32_t l2_stats[4] = {0, 0, 0, 0};
+    unsigned compact_epoch = 0;    // filter.cu: tag of the current compaction call
+    int l2_parity = 0;             // l2.cu: which of the two L2Flags blocks this call uses
     void *tmap_encode = nullptr;   // cuTensorMapEncodeTiled entry point
+    // cached TMA descriptors (l2_tc.cu): [0] query operand, [1] train operand
+    alignas(64) unsigned char tmap_store[2][128] = {};
+    const void *tmap_base[2] = {nullptr, nullptr};
+    int tmap_rows[2] = {0, 0};
     int32_t *h_pinned = nullptr;   // 4 KB pinned scratch for small D2H reads
     // optional device-side kernel timing (pm_profile_*): ring of event pairs per kernel class
     bool profile = false;
