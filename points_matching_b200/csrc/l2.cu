@@ -129,22 +129,30 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long k)
 }
 
 // exact FP32 squared distance between the query chunk held in registers (dim <= 128) and a train row
-__device__ __forceinline__ float warp_l2sq_regs(const float (&a)[4], const float *__restrict__ b, int dim, int lane)
+template <typename T>
+__device__ __forceinline__ float warp_l2sq_regs(const float (&a)[4], const T *__restrict__ b, int dim, int lane)
 {
     float p = 0.f;
 #pragma unroll
     for (int e = 0; e < 4; ++e)
-        if (4 * lane + e < dim) { const float d = a[e] - __ldg(b + 4 * lane + e); p = fmaf(d, d, p); }
+        if (4 * lane + e < dim) { const float d = a[e] - load_elem(b, 4 * lane + e); p = fmaf(d, d, p); }
     return warp_sum_butterfly(p);
 }
 
 // ---------------------------------------------------------------------------------
-// K3: one warp per query row.  Merges the per-segment candidates, re-ranks in FP32
-// (split mode), certifies the top-2 or queues the row for the exact kernel.
+// K3: one warp per query row.  K2 hands over, per segment, the best adjacent-column
+// PAIR minima (value, index).  K3 merges them, re-computes the members of the winning
+// pairs in FP32 (the "re-rank"), and
+//   exact mode: the answer is exact -- the overall second best is either the second
+//               pair minimum or the partner (index ^ 1) of the best;
+//   split mode: both members of the three best pairs are re-ranked; every column outside
+//               them is >= the third pair minimum, which certifies the top-2 (else the
+//               row goes to the exact kernel).
 // ---------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(256)
 l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__restrict__ qnorm,
-                 const float *__restrict__ q, const float *__restrict__ t, int nq, int nt, int dim,
+                 const T *__restrict__ q, const T *__restrict__ t, int nq, int nt, int dim,
                  L2Flags *flags, L2Flags *flags_next, int *__restrict__ flagged, int q_index_base,
                  pm_dmatch *__restrict__ out)
 {
@@ -173,40 +181,51 @@ l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__rest
         if (h0 == k[r] && h0 != ~0ull) { h0 = h1; h1 = h2; h2 = ~0ull; }
     }
     const float na = qnorm[i];
-    float d2[3]; int idx[3];
+    const bool split = !l2_exact_mode(*flags);
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        if (4 * lane + e < dim) a[e] = load_elem(q, (size_t)i * dim + 4 * lane + e);
+
+    // candidate list: pair minima (and their partners), exact FP32 distances
+    float d2[6]; int idx[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { d2[r] = L2_INF; idx[r] = -1; }
+    const float bound = k[2] == ~0ull ? L2_INF : ord2f((unsigned)(k[2] >> 32)) + na;   // approx d^2 of the 3rd pair minimum
+    const int npairs = split ? 3 : 2;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        idx[r] = k[r] == ~0ull ? -1 : (int)(k[r] & 0xFFFFFFFFu);
-        d2[r] = k[r] == ~0ull ? L2_INF : ord2f((unsigned)(k[r] >> 32)) + na;
-    }
-    const bool split = !l2_exact_mode(*flags);
-    bool certified = true;
-    if (split) {
-        const float bound = d2[2];        // approx d^2 of the third candidate: every non-candidate is >= this
-        float a[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (4 * lane + e < dim) a[e] = __ldg(q + (size_t)i * dim + 4 * lane + e);
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-            if (idx[r] >= 0) d2[r] = warp_l2sq_regs(a, t + (size_t)idx[r] * dim, dim, lane);
-        // sort the three by (exact d^2, index)
-#define L2_CSWAP(x, y)                                                                     \
-        if (d2[y] < d2[x] || (d2[y] == d2[x] && (unsigned)idx[y] < (unsigned)idx[x])) {    \
-            float td = d2[x]; d2[x] = d2[y]; d2[y] = td; int ti = idx[x]; idx[x] = idx[y]; idx[y] = ti; }
-        L2_CSWAP(0, 1) L2_CSWAP(1, 2) L2_CSWAP(0, 1)
-#undef L2_CSWAP
-        if (k[2] != ~0ull) {
-            const float eps = L2_EPS_REL * sqrtf(na * __uint_as_float(flags->max_tnorm_bits));
-            certified = d2[1] < bound - eps;
+        if (r >= npairs || k[r] == ~0ull) continue;
+        const int j = (int)(k[r] & 0xFFFFFFFFu);
+        idx[2 * r] = j;
+        // exact mode: the GEMM value is already the exact integer; split mode: re-rank in FP32
+        d2[2 * r] = split ? warp_l2sq_regs(a, t + (size_t)j * dim, dim, lane) : ord2f((unsigned)(k[r] >> 32)) + na;
+        const int p = j ^ 1;                               // the other member of the column pair
+        if (p < nt && (split || r == 0)) {
+            idx[2 * r + 1] = p;
+            d2[2 * r + 1] = warp_l2sq_regs(a, t + (size_t)p * dim, dim, lane);
         }
+    }
+    // the two smallest by (d^2, index)
+    float b0 = L2_INF, b1 = L2_INF; int j0 = -1, j1 = -1;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        if (idx[r] < 0) continue;
+        const float d = d2[r]; const int j = idx[r];
+        if (d < b0 || (d == b0 && (unsigned)j < (unsigned)j0)) { b1 = b0; j1 = j0; b0 = d; j0 = j; }
+        else if (d < b1 || (d == b1 && (unsigned)j < (unsigned)j1)) { b1 = d; j1 = j; }
+    }
+    bool certified = true;
+    if (split && k[2] != ~0ull) {
+        const float eps = L2_EPS_REL * sqrtf(na * __uint_as_float(flags->max_tnorm_bits));
+        certified = b1 < bound - eps;
     }
     if (lane == 0) {
         pm_dmatch r0, r1;
         r0.queryIdx = r1.queryIdx = i + q_index_base;
         r0.imgIdx = r1.imgIdx = 0;
-        r0.trainIdx = idx[0]; r0.distance = idx[0] < 0 ? 3.402823466e+38f : sqrtf(fmaxf(d2[0], 0.f));
-        r1.trainIdx = idx[1]; r1.distance = idx[1] < 0 ? 3.402823466e+38f : sqrtf(fmaxf(d2[1], 0.f));
+        r0.trainIdx = j0; r0.distance = j0 < 0 ? 3.402823466e+38f : sqrtf(fmaxf(b0, 0.f));
+        r1.trainIdx = j1; r1.distance = j1 < 0 ? 3.402823466e+38f : sqrtf(fmaxf(b1, 0.f));
         out[(size_t)i * 2] = r0;
         out[(size_t)i * 2 + 1] = r1;
         if (!certified) flagged[atomicAdd(&flags->n_flagged, 1)] = i;
@@ -338,11 +357,16 @@ int pmk_l2_knn2(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int
     PM_CHECK_LAUNCH(ctx);
     int st = l2_tc_launch(ctx, qpack, mq_pad, tpack, nt_pad, tnorm, flags, part, smax, g_l2_dump);
     if (st != PM_OK) return st;
-    l2_finish_kernel<<<pm_cdiv(nq, 8), 256, 0, ctx->stream>>>(part, smax * 3, qnorm, (const float *)dq, (const float *)dt, nq, nt, dim,
-                                                               flags, flags_next, flagged, q_index_base, dout);
+    if (is_u8)
+        l2_finish_kernel<uint8_t><<<pm_cdiv(nq, 8), 256, 0, ctx->stream>>>(part, smax * 3, qnorm, (const uint8_t *)dq, (const uint8_t *)dt,
+                                                                            nq, nt, dim, flags, flags_next, flagged, q_index_base, dout);
+    else
+        l2_finish_kernel<float><<<pm_cdiv(nq, 8), 256, 0, ctx->stream>>>(part, smax * 3, qnorm, (const float *)dq, (const float *)dt,
+                                                                          nq, nt, dim, flags, flags_next, flagged, q_index_base, dout);
     PM_CHECK_LAUNCH(ctx);
-    if (!is_u8) {   // u8 input is always integer-valued: with SIFT-range norms nothing can be flagged
-        int s2 = run_exact(ctx, (const float *)dq, (const float *)dt, nq, nt, dim, flagged, &flags->n_flagged, q_index_base, dout);
+    {   // rows K3 could not certify (split mode only; the count lives on the device)
+        int s2 = is_u8 ? run_exact(ctx, (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, flagged, &flags->n_flagged, q_index_base, dout)
+                       : run_exact(ctx, (const float *)dq, (const float *)dt, nq, nt, dim, flagged, &flags->n_flagged, q_index_base, dout);
         if (s2 != PM_OK) return s2;
     }
     ctx->l2_parity ^= 1;

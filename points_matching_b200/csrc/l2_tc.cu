@@ -20,9 +20,10 @@
 //                                also allocates / frees TMEM
 //   warps 2-9   epilogue       : tcgen05.ld 32x32b.x32, + ||b||^2, pack (value | column) into
 //                                one u32 key, branch-free min/max tournament (VIMNMX/VIMNMX3):
-//                                top-2 in exact mode, top-3 in split mode, kept in registers
-//                                across the whole sweep.  The ALU pipe is the binding
-//                                resource (2.5 / 5 min-max ops per element), not the MMA.
+//                                over adjacent column PAIRS: top-2 pair minima in exact mode,
+//                                top-3 in split mode, kept in registers across the sweep (K3
+//                                re-checks the partners exactly).  1.75 / 2.5 ALU-pipe min-max
+//                                ops per element, so the ALU pipe no longer outweighs the MMA.
 // Each CTA walks a contiguous range of the (row-tile, column-tile) space; per row tile it
 // writes one "segment" of candidates which K3 merges, re-ranks in FP32 and certifies.
 #include <cuda.h>
@@ -130,14 +131,20 @@ __device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { 
 struct Sel2 {   // exact mode: running (best, second)
     uint32_t m1, m2; int i1, i2;
     __device__ __forceinline__ void reset() { m1 = m2 = 0xFFFFFFFFu; i1 = i2 = -1; }
-    // top-2 of 32 keys by a tournament (80 min/max ops), merged into the running pair
+    // The 32 keys are 16 adjacent (even, odd) column pairs.  Only the smaller key of each pair
+    // enters the top-2 tournament (56 min/max ops per 32 elements): the overall second best is
+    // either the second-smallest pair minimum or the partner (column ^ 1) of the best, and K3
+    // re-checks that single partner exactly.
     __device__ __forceinline__ void chunk(uint32_t (&k)[32])
     {
-        uint32_t lo[16], hi[16];
+        uint32_t lo[8], hi[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { lo[i] = min(k[2 * i], k[2 * i + 1]); hi[i] = max(k[2 * i], k[2 * i + 1]); }
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t p0 = min(k[4 * i], k[4 * i + 1]), p1 = min(k[4 * i + 2], k[4 * i + 3]);
+            lo[i] = min(p0, p1); hi[i] = max(p0, p1);
+        }
 #pragma unroll
-        for (int w = 8; w >= 1; w >>= 1)
+        for (int w = 4; w >= 1; w >>= 1)
 #pragma unroll
             for (int i = 0; i < w; ++i) {
                 const uint32_t L = min(lo[i], lo[i + w]);
@@ -162,11 +169,14 @@ struct Sel2 {   // exact mode: running (best, second)
 struct Sel3 {   // split mode: running (best, second, third)
     uint32_t m1, m2, m3; int i1, i2, i3;
     __device__ __forceinline__ void reset() { m1 = m2 = m3 = 0xFFFFFFFFu; i1 = i2 = i3 = -1; }
+    // as in Sel2 only the smaller key of each adjacent column pair competes; K3 re-ranks both
+    // members of the three winning pairs.  Two pair minima at a time go into the sorted triple.
     __device__ __forceinline__ void chunk(uint32_t (&k)[32])
     {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {       // sorted pair (lo, hi) into the sorted triple: 8 ops / 2 elements
-            const uint32_t lo = min(k[2 * i], k[2 * i + 1]), hi = max(k[2 * i], k[2 * i + 1]);
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t p0 = min(k[4 * i], k[4 * i + 1]), p1 = min(k[4 * i + 2], k[4 * i + 3]);
+            const uint32_t lo = min(p0, p1), hi = max(p0, p1);
             const uint32_t c3 = umin3(max(m1, hi), max(m2, lo), m3);
             const uint32_t c2 = umin3(hi, max(m1, lo), m2);
             m1 = min(m1, lo); m2 = c2; m3 = c3;
@@ -212,6 +222,7 @@ struct TcParams {
     L2Cand *part;                // [mq_pad][smax][3]
     float *dump;                 // debug: [mq_pad][nt_pad] of (||b||^2 - 2ab), or null
     int MT, NT, smax, nt_pad;
+    uint32_t mul256;             // == 256, passed at run time so the key pack stays an IMAD (FMA pipe), not an ALU LEA
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -320,6 +331,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         const float *tnorm = P.tnorm;
         const float nb_off = exact ? L2_EXACT_BIAS : shift;     // folded into the staged column norms
         float *snorm = reinterpret_cast<float *>(sgen + SMEM_NORM);     // [2][256] by accumulator parity
+        const uint32_t mul = P.mul256;
         const int et = e * 32 + lane;                                   // 0..255: column this thread stages
         uint32_t acc = 0, acc_phase = 0; int cur_m = -1;
         float nb_pref = t_begin < t_end ? __ldg(tnorm + (t_begin % P.NT) * BN + et) : 0.f;
@@ -389,10 +401,10 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                     for (int v = 0; v < 8; ++v) {
                         const float4 x = np[ch * 8 + v];
                         const int c = 4 * v;
-                        r[c] = __float_as_uint(__uint_as_float(r[c]) + x.x) * 256u + (uint32_t)(ch * 32 + c + 1);
-                        r[c + 1] = __float_as_uint(__uint_as_float(r[c + 1]) + x.y) * 256u + (uint32_t)(ch * 32 + c + 2);
-                        r[c + 2] = __float_as_uint(__uint_as_float(r[c + 2]) + x.z) * 256u + (uint32_t)(ch * 32 + c + 3);
-                        r[c + 3] = __float_as_uint(__uint_as_float(r[c + 3]) + x.w) * 256u + (uint32_t)(ch * 32 + c + 4);
+                        r[c] = __float_as_uint(__uint_as_float(r[c]) + x.x) * mul + (uint32_t)(ch * 32 + c + 1);
+                        r[c + 1] = __float_as_uint(__uint_as_float(r[c + 1]) + x.y) * mul + (uint32_t)(ch * 32 + c + 2);
+                        r[c + 2] = __float_as_uint(__uint_as_float(r[c + 2]) + x.z) * mul + (uint32_t)(ch * 32 + c + 3);
+                        r[c + 3] = __float_as_uint(__uint_as_float(r[c + 3]) + x.w) * mul + (uint32_t)(ch * 32 + c + 4);
                     }
                     s2.chunk(r);
                 } else {
@@ -500,7 +512,7 @@ int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, 
     const CUtensorMap &tq = tmaps[0], &tt = tmaps[1];
     TcParams P;
     P.tnorm = tnorm; P.flags = flags; P.part = part; P.dump = dump;
-    P.MT = mq_pad / BM; P.NT = nt_pad / BN; P.smax = smax; P.nt_pad = nt_pad;
+    P.MT = mq_pad / BM; P.NT = nt_pad / BN; P.smax = smax; P.nt_pad = nt_pad; P.mul256 = 256u;
     const int G = l2_tc_grid(ctx, P.MT, P.NT);
     {
         pm_prof_scope prof(ctx, 0);

@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Pretty-prints a bench.py JSON line and (optionally) an ncu launch-list CSV."""
+import collections
+import csv
+import json
+import sys
+
+
+def show_bench(path):
+    d = json.load(open(path))
+    print('value %.3e %s  ms_step %.4f  launches %d  n_gpus %d' % (d['value'], d['unit'], d['ms_per_step'], d['gpu_launches'], d['n_gpus']))
+    e = d['e2e']; print('e2e %.3e ms %.4f' % (e['value'], e['ms_per_step']))
+    r = d['roofline']; print('K2 ms %.4f achieved %.1f TF frac %.3f share %.2f exact=%s fb=%s' % (r['kernel_ms'], r['achieved'], r['frac'], r['kernel_share_of_step'], r['exact_integer_mode'], r['exact_fallback_rows']))
+    print('clocks', d['clocks'])
+    if d.get('cpu_baseline'):
+        print('cpu %.3e cores %d' % (d['cpu_baseline']['value'], d['cpu_baseline']['cores']))
+    s = d.get('secondary')
+    if s:
+        print('ransac %.3e hyp/s ms %.2f e2e %.3e k7_ms %.2f frac %.3f inl %s' % (s['value'], s['ms_per_step'], s['e2e']['value'], s['roofline']['kernel_ms'], s['roofline']['frac'], s['config']['winner_inliers']), s.get('cpu_baseline', {}).get('value'))
+    x = (d.get('extra') or {}).get('hamming')
+    if x:
+        print('hamming step ms %.3f kernel ms %.3f pairs/s(kernel) %.3e frac_popc %.3f mutual %d' % (x['ms_per_step'], x['kernel_ms'], x['pairs_per_s_knn_kernel'], x['roofline']['frac'], x['mutual_matches']))
+
+
+def show_launches(path):
+    rows = list(csv.reader(open(path)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
+    hdr, data = rows[hi], rows[hi + 1:]
+    kn, mv, mn = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Metric Name')
+    agg = collections.OrderedDict()
+    for r in data:
+        if len(r) <= mv or r[mn] != 'gpu__time_duration.sum':
+            continue
+        agg.setdefault(r[kn][:70], []).append(float(r[mv].replace(',', '')))
+    tot = sum(sum(v) / len(v) for v in agg.values())
+    for k, v in agg.items():
+        print(f"{k:70s} n={len(v):4d} avg_us={sum(v)/len(v)/1000:8.2f} share={sum(v)/len(v)/tot:5.2f}")
+    print('sum of avgs us %.2f' % (tot / 1000))
+
+
+if __name__ == '__main__':
+    for p in sys.argv[1:]:
+        (show_launches if p.endswith('.csv') else show_bench)(p)
