@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(FB) compact_lookback_kernel(Pred pred, int n, 
                                                               unsigned epoch)
 {
     __shared__ int s_tile, s_prefix;
+    pm_pdl_prologue();
     if (threadIdx.x == 0) s_tile = (int)atomicAdd(&counter[epoch & 1u], 1u);
     __syncthreads();
     const int tile = s_tile;
@@ -140,7 +141,8 @@ int run_compact(pm_ctx *ctx, Pred pred, int n, pm_dmatch *dout, int32_t *dn_out)
         return run_compact(ctx, pred, n, dout, dn_out);
     }
     unsigned *counter = reinterpret_cast<unsigned *>(st);          // st[0]: two ticket counters
-    compact_lookback_kernel<<<nb, FB, 0, ctx->stream>>>(pred, n, dout, dn_out, st + 1, counter, epoch);
+    PM_CUDA(ctx, pm_launch_pdl(compact_lookback_kernel<Pred>, dim3(nb), dim3(FB), 0, ctx->stream, pred, n, dout, dn_out, st + 1,
+                               counter, epoch));
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }

@@ -66,6 +66,7 @@ l2_pack_kernel(const T *__restrict__ q, int nq, int mq_pad, const T *__restrict_
                float *__restrict__ qnorm, float *__restrict__ tnorm, L2Flags *flags,
                L2Cand *__restrict__ part, int part_per_row)
 {
+    pm_pdl_prologue();
     const int lane = threadIdx.x & 31;
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const bool is_train = row >= mq_pad;
@@ -94,13 +95,10 @@ l2_pack_kernel(const T *__restrict__ q, int nq, int mq_pad, const T *__restrict_
     *reinterpret_cast<uint2 *>(dst + 4 * lane) = *reinterpret_cast<uint2 *>(hi);
     *reinterpret_cast<uint2 *>(dst + L2_KDIM + 4 * lane) = *reinterpret_cast<uint2 *>(lo);
     if (lane == 0) {
-        if (is_train) {
-            tnorm[row] = row < n ? s : L2_INF;
-            if (row < n) atomicMax(&flags->max_tnorm_bits, __float_as_uint(s));
-        } else {
-            qnorm[row] = row < n ? s : 0.f;
-            if (row < n) atomicMax(&flags->max_qnorm_bits, __float_as_uint(s));
-        }
+        (is_train ? tnorm : qnorm)[row] = row < n ? s : (is_train ? L2_INF : 0.f);
+        // same-address atomics serialise in L2: only rows that would raise the max issue one
+        unsigned *mx = is_train ? &flags->max_tnorm_bits : &flags->max_qnorm_bits;
+        if (row < n && __float_as_uint(s) > *reinterpret_cast<volatile unsigned *>(mx)) atomicMax(mx, __float_as_uint(s));
     }
     if (!__all_sync(0xffffffffu, integral) && lane == 0) flags->nonexact = 1;
     if (!is_train)
@@ -156,6 +154,7 @@ l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__rest
                  L2Flags *flags, L2Flags *flags_next, int *__restrict__ flagged, int q_index_base,
                  pm_dmatch *__restrict__ out)
 {
+    pm_pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x == 0) *flags_next = L2Flags{0, 0u, 0u, 0};   // the next call's block
@@ -243,6 +242,7 @@ l2_exact_kernel(const T *__restrict__ q, const T *__restrict__ t, int nq, int nt
                 int q_index_base, pm_dmatch *__restrict__ out)
 {
     extern __shared__ float qs[];                 // [dim_pad] query row, then merge scratch
+    pm_pdl_prologue();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int dim_pad = (dim + 127) / 128 * 128;
     float *md = qs + dim_pad;                     // [nwarps][2]
@@ -306,7 +306,8 @@ int run_exact(pm_ctx *ctx, const T *dq, const T *dt, int nq, int nt, int dim, co
     const int dim_pad = (dim + 127) / 128 * 128;
     const size_t smem = (size_t)dim_pad * 4 + 8 * 4 * 4;
     const int grid = rows ? min(nq, ctx->num_sms) : min(nq, 8 * ctx->num_sms);
-    l2_exact_kernel<T><<<grid, 256, smem, ctx->stream>>>(dq, dt, nq, nt, dim, rows, count, base, dout);
+    PM_CUDA(ctx, pm_launch_pdl(l2_exact_kernel<T>, dim3(grid), dim3(256), smem, ctx->stream, dq, dt, nq, nt, dim, rows, count,
+                               base, dout));
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }
@@ -347,22 +348,24 @@ int pmk_l2_knn2(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int
     const int pack_blocks = pm_cdiv(mq_pad + nt_pad, 8);
     if (is_u8) {
         const int vec = dim == L2_KDIM && (((uintptr_t)dq | (uintptr_t)dt) & 3) == 0;
-        l2_pack_kernel<uint8_t><<<pack_blocks, 256, 0, ctx->stream>>>((const uint8_t *)dq, nq, mq_pad, (const uint8_t *)dt, nt, nt_pad, dim, vec,
-                                                                      qpack, tpack, qnorm, tnorm, flags, part, smax * 3);
+        PM_CUDA(ctx, pm_launch_pdl(l2_pack_kernel<uint8_t>, dim3(pack_blocks), dim3(256), 0, ctx->stream, (const uint8_t *)dq, nq, mq_pad,
+                                   (const uint8_t *)dt, nt, nt_pad, dim, vec, qpack, tpack, qnorm, tnorm, flags, part, smax * 3));
     } else {
         const int vec = dim == L2_KDIM && (((uintptr_t)dq | (uintptr_t)dt) & 15) == 0;
-        l2_pack_kernel<float><<<pack_blocks, 256, 0, ctx->stream>>>((const float *)dq, nq, mq_pad, (const float *)dt, nt, nt_pad, dim, vec,
-                                                                    qpack, tpack, qnorm, tnorm, flags, part, smax * 3);
+        PM_CUDA(ctx, pm_launch_pdl(l2_pack_kernel<float>, dim3(pack_blocks), dim3(256), 0, ctx->stream, (const float *)dq, nq, mq_pad,
+                                   (const float *)dt, nt, nt_pad, dim, vec, qpack, tpack, qnorm, tnorm, flags, part, smax * 3));
     }
     PM_CHECK_LAUNCH(ctx);
     int st = l2_tc_launch(ctx, qpack, mq_pad, tpack, nt_pad, tnorm, flags, part, smax, g_l2_dump);
     if (st != PM_OK) return st;
     if (is_u8)
-        l2_finish_kernel<uint8_t><<<pm_cdiv(nq, 8), 256, 0, ctx->stream>>>(part, smax * 3, qnorm, (const uint8_t *)dq, (const uint8_t *)dt,
-                                                                            nq, nt, dim, flags, flags_next, flagged, q_index_base, dout);
+        PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<uint8_t>, dim3(pm_cdiv(nq, 8)), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,
+                                   (const float *)qnorm, (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, flags, flags_next, flagged,
+                                   q_index_base, dout));
     else
-        l2_finish_kernel<float><<<pm_cdiv(nq, 8), 256, 0, ctx->stream>>>(part, smax * 3, qnorm, (const float *)dq, (const float *)dt,
-                                                                          nq, nt, dim, flags, flags_next, flagged, q_index_base, dout);
+        PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<float>, dim3(pm_cdiv(nq, 8)), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,
+                                   (const float *)qnorm, (const float *)dq, (const float *)dt, nq, nt, dim, flags, flags_next, flagged,
+                                   q_index_base, dout));
     PM_CHECK_LAUNCH(ctx);
     {   // rows K3 could not certify (split mode only; the count lives on the device)
         int s2 = is_u8 ? run_exact(ctx, (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, flagged, &flags->n_flagged, q_index_base, dout)

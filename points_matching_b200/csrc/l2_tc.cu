@@ -12,18 +12,18 @@
 //   exact-integer mode (SIFT, values 0..255): lo == 0, 2 k-blocks, the GEMM is exact
 //   split mode (general floats):  a.b ~ ah.bh + ah.bl + al.bh, 6 k-blocks
 //
-// Structure (one persistent CTA per SM, 320 threads):
+// Structure (one persistent CTA per SM, 576 threads):
 //   warp 0      TMA producer   : A row-tile resident (<= 4 x 16 KB), B k-blocks through a
 //                                4-stage 32 KB ring (cp.async.bulk.tensor, SWIZZLE_128B)
 //   warp 1      MMA issuer     : tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16,
 //                                accumulators double-buffered in TMEM (2 x 256 columns);
 //                                also allocates / frees TMEM
-//   warps 2-9   epilogue       : tcgen05.ld 32x32b.x32, + ||b||^2, pack (value | column) into
-//                                one u32 key, branch-free min/max tournament (VIMNMX/VIMNMX3):
-//                                over adjacent column PAIRS: top-2 pair minima in exact mode,
-//                                top-3 in split mode, kept in registers across the sweep (K3
-//                                re-checks the partners exactly).  1.75 / 2.5 ALU-pipe min-max
-//                                ops per element, so the ALU pipe no longer outweighs the MMA.
+//   warps 2-17  epilogue       : 4 warps per scheduler, each owns 32 rows x 64 columns of a
+//                                tile: tcgen05.ld 32x32b.x32, + ||b||^2 (staged in smem),
+//                                pack (value | column) into one u32 key, branch-free min/max
+//                                tournament (VIMNMX/VIMNMX3) over adjacent column PAIRS: top-2
+//                                pair minima in exact mode, top-3 in split mode, kept in
+//                                registers across the sweep (K3 re-checks the partners exactly).
 // Each CTA walks a contiguous range of the (row-tile, column-tile) space; per row tile it
 // writes one "segment" of candidates which K3 merges, re-ranks in FP32 and certifies.
 #include <cuda.h>
@@ -37,13 +37,17 @@ constexpr int A_BLK_BYTES = BM * BK * 2;     // 16 KB
 constexpr int B_BLK_BYTES = BN * BK * 2;     // 32 KB
 constexpr int NSTAGE = 4;
 constexpr int A_MAXBLK = 4;
-constexpr int TC_THREADS = 320;     // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-9 epilogue
-constexpr int EPI_WARP0 = 2;
+constexpr int EPI_WARP0 = 2;        // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-17 epilogue
+constexpr int EPI_WARPS = 16;       // 4 per scheduler: enough TLP to keep the issue slots busy
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int TC_THREADS = (EPI_WARP0 + EPI_WARPS) * 32;   // 576
+constexpr int NSLICE = EPI_WARPS / 4;                      // column slices per tile
+constexpr int SLICE = BN / NSLICE;                         // 64 columns of each tile per warp
 constexpr int SMEM_A = 0;
 constexpr int SMEM_B = A_MAXBLK * A_BLK_BYTES;                 // 65536
 constexpr int SMEM_BAR = SMEM_B + NSTAGE * B_BLK_BYTES;        // 196608
-constexpr int SMEM_SCRATCH = SMEM_BAR + 256;
-constexpr int SMEM_NORM = SMEM_SCRATCH + BM * 6 * 4;           // 2 x 256 column norms
+constexpr int SMEM_SCRATCH = SMEM_BAR + 256;                   // (NSLICE-1) x 128 rows x 3 candidates
+constexpr int SMEM_NORM = SMEM_SCRATCH + (NSLICE - 1) * BM * 3 * 8;   // 2 x 256 staged column norms
 constexpr int SMEM_TOTAL = SMEM_NORM + 2 * BN * 4 + 1024;      // + alignment slack
 
 // instruction descriptor: D=F32, A=B=BF16, K-major both, N=256, M=128
@@ -122,20 +126,20 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //               bits * 256 + (c+1) = ((0x400000 + t) << 8) | (c+1) orders by (t, column).
 //   split mode: acc + (||b||^2 + shift) > 0, key = (bits & ~0xFF) | (c+1) (PRMT): the value is
 //               truncated by <= 2^-15 relative, which only lowers the certification bound.
-// The low byte (c+1 in 1..128, this thread's column within the tile) is non-zero for keys of
-// the current tile and zeroed on carried keys, so an equal distance from an earlier tile
-// always wins (lowest train index), and "which entries are new" needs no comparisons.
+// The low byte is the column within the warp's 64-column slice, plus one (1..64): non-zero
+// for keys of the current tile and zeroed on carried keys, so an equal distance from an
+// earlier tile always wins (lowest train index) and "which entries are new" needs no compare.
+// The 32 keys of a chunk are 16 adjacent (even, odd) column pairs; only the smaller key of a
+// pair competes: the overall runner-up is either another pair's minimum or the partner
+// (column ^ 1) of a winner, which K3 re-checks exactly.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u32(a, b, c); }
 
-struct Sel2 {   // exact mode: running (best, second)
+struct Sel2 {   // exact mode: running (best, second) pair minima
     uint32_t m1, m2; int i1, i2;
     __device__ __forceinline__ void reset() { m1 = m2 = 0xFFFFFFFFu; i1 = i2 = -1; }
-    // The 32 keys are 16 adjacent (even, odd) column pairs.  Only the smaller key of each pair
-    // enters the top-2 tournament (56 min/max ops per 32 elements): the overall second best is
-    // either the second-smallest pair minimum or the partner (column ^ 1) of the best, and K3
-    // re-checks that single partner exactly.
-    __device__ __forceinline__ void chunk(uint32_t (&k)[32])
+    // 56 min/max ops per 32 elements; chb = column base of the chunk inside the slice
+    __device__ __forceinline__ void chunk(uint32_t (&k)[32], uint32_t chb)
     {
         uint32_t lo[8], hi[8];
 #pragma unroll
@@ -151,8 +155,10 @@ struct Sel2 {   // exact mode: running (best, second)
                 const uint32_t S = umin3(max(lo[i], lo[i + w]), hi[i], hi[i + w]);
                 lo[i] = L; hi[i] = S;
             }
-        m2 = umin3(m2, hi[0], max(m1, lo[0]));
-        m1 = min(m1, lo[0]);
+        // keys carry the column within the chunk (1..32); make it the column within the slice
+        const uint32_t L = lo[0] + chb, S = hi[0] + chb;
+        m2 = umin3(m2, S, max(m1, L));
+        m1 = min(m1, L);
     }
     // after a tile: resolve the indices of entries that came from it, zero their column byte
     __device__ __forceinline__ void end_tile(int col0)
@@ -166,21 +172,26 @@ struct Sel2 {   // exact mode: running (best, second)
     __device__ __forceinline__ float value(uint32_t m) const { return (float)((int)(m >> 8) - 0x400000); }
 };
 
-struct Sel3 {   // split mode: running (best, second, third)
+struct Sel3 {   // split mode: running (best, second, third) pair minima
     uint32_t m1, m2, m3; int i1, i2, i3;
     __device__ __forceinline__ void reset() { m1 = m2 = m3 = 0xFFFFFFFFu; i1 = i2 = i3 = -1; }
-    // as in Sel2 only the smaller key of each adjacent column pair competes; K3 re-ranks both
-    // members of the three winning pairs.  Two pair minima at a time go into the sorted triple.
-    __device__ __forceinline__ void chunk(uint32_t (&k)[32])
+    __device__ __forceinline__ void chunk(uint32_t (&k)[32], uint32_t chb)
     {
+        uint32_t a1 = 0xFFFFFFFFu, a2 = 0xFFFFFFFFu, a3 = 0xFFFFFFFFu;     // chunk-local sorted triple
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 8; ++i) {       // two pair minima (sorted) at a time into the triple
             const uint32_t p0 = min(k[4 * i], k[4 * i + 1]), p1 = min(k[4 * i + 2], k[4 * i + 3]);
             const uint32_t lo = min(p0, p1), hi = max(p0, p1);
-            const uint32_t c3 = umin3(max(m1, hi), max(m2, lo), m3);
-            const uint32_t c2 = umin3(hi, max(m1, lo), m2);
-            m1 = min(m1, lo); m2 = c2; m3 = c3;
+            const uint32_t c3 = umin3(max(a1, hi), max(a2, lo), a3);
+            const uint32_t c2 = umin3(hi, max(a1, lo), a2);
+            a1 = min(a1, lo); a2 = c2; a3 = c3;
         }
+        a1 += chb; a2 += chb; a3 += chb;    // 16 distinct pair minima per chunk: all three are real
+        // merge two sorted triples
+        const uint32_t c1 = min(m1, a1);
+        const uint32_t c2 = umin3(a2, max(m1, a1), m2);
+        const uint32_t c3 = min(umin3(a3, max(m1, a2), max(m2, a1)), m3);
+        m1 = c1; m2 = c2; m3 = c3;
     }
     __device__ __forceinline__ void end_tile(int col0)
     {
@@ -197,7 +208,7 @@ struct Sel3 {   // split mode: running (best, second, third)
     }
 };
 
-// lexicographic (value, index) insert used when merging the two column halves at a flush
+// lexicographic (value, index) insert used when merging the column slices at a flush
 struct Cand3 {
     float d[3]; int i[3];
     __device__ __forceinline__ void reset() { d[0] = d[1] = d[2] = __int_as_float(0x7f800000); i[0] = i[1] = i[2] = -1; }
@@ -239,6 +250,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     L2Cand *scratch = reinterpret_cast<L2Cand *>(sgen + SMEM_SCRATCH);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pm_pdl_prologue();      // K1's outputs (flags, packed operands, norms) are complete past this point
     const L2Flags fl = *P.flags;
     const bool exact = l2_exact_mode(fl);
     const int nkb = exact ? 2 : 6;
@@ -252,14 +264,14 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_q)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_t)) : "memory");
     }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        mbar_init(bar_afull, 1);
-        mbar_init(bar_aempty, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+            mbar_init(bar_afull, 1);
+            mbar_init(bar_aempty, 1);
+            for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, EPI_WARPS); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32((const void *)tmem_slot)), "r"(512u) : "memory");
@@ -321,20 +333,19 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                 acc ^= 1; if (acc == 0) acc_phase ^= 1;
             }
         }
-    } else if (warp >= EPI_WARP0) {
+    } else {
         // ===================== epilogue =====================
         const int e = warp - EPI_WARP0;
         const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-        const int half = e >> 2;               // which 128 of the tile's 256 columns
+        const int slice = e >> 2;              // which 64 of the tile's 256 columns
         const int row = quarter * 32 + lane;   // row within the 128-row tile
         const float shift = l2_split_shift(fl.max_qnorm_bits);
-        const float *tnorm = P.tnorm;
-        const float nb_off = exact ? L2_EXACT_BIAS : shift;     // folded into the staged column norms
-        float *snorm = reinterpret_cast<float *>(sgen + SMEM_NORM);     // [2][256] by accumulator parity
+        const float nb_off = exact ? L2_EXACT_BIAS : shift;            // folded into the staged column norms
+        float *snorm = reinterpret_cast<float *>(sgen + SMEM_NORM);    // [2][256] by accumulator parity
         const uint32_t mul = P.mul256;
-        const int et = e * 32 + lane;                                   // 0..255: column this thread stages
+        const int et = e * 32 + lane;                                  // threads 0..255 stage one column norm each
         uint32_t acc = 0, acc_phase = 0; int cur_m = -1;
-        float nb_pref = t_begin < t_end ? __ldg(tnorm + (t_begin % P.NT) * BN + et) : 0.f;
+        float nb_pref = (et < BN && t_begin < t_end) ? __ldg(P.tnorm + (t_begin % P.NT) * BN + et) : 0.f;
         Sel2 s2; s2.reset();
         Sel3 s3; s3.reset();
 
@@ -344,18 +355,19 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                 if ((s2.m1 >> 8) != 0xFFFFFFu) c.insert(s2.value(s2.m1), s2.i1);
                 if ((s2.m2 >> 8) != 0xFFFFFFu) c.insert(s2.value(s2.m2), s2.i2);
             } else {
-                if (s3.m1 != 0xFFFFFF00u) c.insert(__uint_as_float(s3.m1) - shift, s3.i1);
-                if (s3.m2 != 0xFFFFFF00u) c.insert(__uint_as_float(s3.m2) - shift, s3.i2);
-                if (s3.m3 != 0xFFFFFF00u) c.insert(__uint_as_float(s3.m3) - shift, s3.i3);
+                if ((s3.m1 >> 8) != 0xFFFFFFu) c.insert(__uint_as_float(s3.m1) - shift, s3.i1);
+                if ((s3.m2 >> 8) != 0xFFFFFFu) c.insert(__uint_as_float(s3.m2) - shift, s3.i2);
+                if ((s3.m3 >> 8) != 0xFFFFFFu) c.insert(__uint_as_float(s3.m3) - shift, s3.i3);
             }
-            if (half == 1) {
+            if (slice > 0) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) scratch[row * 3 + k] = L2Cand{c.d[k], c.i[k]};
+                for (int k = 0; k < 3; ++k) scratch[((slice - 1) * BM + row) * 3 + k] = L2Cand{c.d[k], c.i[k]};
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (half == 0) {
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+            if (slice == 0) {
+                for (int sl = 0; sl < NSLICE - 1; ++sl)
 #pragma unroll
-                for (int k = 0; k < 3; ++k) { const L2Cand o = scratch[row * 3 + k]; c.insert(o.d, o.idx); }
+                    for (int k = 0; k < 3; ++k) { const L2Cand o = scratch[(sl * BM + row) * 3 + k]; c.insert(o.d, o.idx); }
                 // segment slot = index of this CTA among the CTAs that touch row tile m
                 const long long first_tile = (long long)m * P.NT;
                 int c0 = (int)((first_tile * G) / T);
@@ -366,60 +378,58 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
 #pragma unroll
                 for (int k = 0; k < 3; ++k) dst[k] = L2Cand{c.d[k], c.i[k]};
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             s2.reset(); s3.reset();
         };
 
         for (int tile = t_begin; tile < t_end; ++tile) {
             const int m = tile / P.NT, n = tile % P.NT;
             if (m != cur_m) { if (cur_m >= 0) flush(cur_m); cur_m = m; }
-            mbar_wait(bar_tfull + 8 * acc, acc_phase);
-            tc_fence_after();
-            const int col0 = n * BN + half * 128;
-            const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128;
             // stage this tile's 256 column norms in shared memory (prefetched one tile ahead),
             // so the hot loop reads them with broadcast LDS.128 instead of waiting on L2
-            snorm[acc * BN + et] = (exact && nb_pref == __int_as_float(0x7f800000)) ? L2_EXACT_PAD : nb_pref + nb_off;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (tile + 1 < t_end) nb_pref = __ldg(tnorm + ((tile + 1) % P.NT) * BN + et);
-            const float4 *np = reinterpret_cast<const float4 *>(snorm + acc * BN + half * 128);
-            uint32_t rb[2][32];
-            tmem_ld32(taddr0, rb[0]);
-            tmem_ld_wait();
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t (&r)[32] = rb[ch & 1];
-                if (ch < 3) tmem_ld32(taddr0 + (ch + 1) * 32, rb[(ch + 1) & 1]);   // overlaps the math below
+            if (et < BN)
+                snorm[acc * BN + et] = (exact && nb_pref == __int_as_float(0x7f800000)) ? L2_EXACT_PAD : nb_pref + nb_off;
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+            if (et < BN && tile + 1 < t_end) nb_pref = __ldg(P.tnorm + ((tile + 1) % P.NT) * BN + et);
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            const int col0 = n * BN + slice * SLICE;
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + slice * SLICE;
+            const float4 *np = reinterpret_cast<const float4 *>(snorm + acc * BN + slice * SLICE);
+#pragma unroll 1
+            for (int ch = 0; ch < SLICE / 32; ++ch) {
+                uint32_t r[32];
+                tmem_ld32(taddr0 + ch * 32, r);
+                tmem_ld_wait();
                 if (P.dump) {
                     float *drow = P.dump + (size_t)(m * BM + row) * P.nt_pad + col0 + ch * 32;
-                    const float off = exact ? L2_EXACT_BIAS : shift;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) drow[c] = __uint_as_float(r[c]) + snorm[acc * BN + half * 128 + ch * 32 + c] - off;
+                    for (int c = 0; c < 32; ++c)
+                        drow[c] = __uint_as_float(r[c]) + snorm[acc * BN + slice * SLICE + ch * 32 + c] - nb_off;
                 }
                 if (exact) {
 #pragma unroll
                     for (int v = 0; v < 8; ++v) {
                         const float4 x = np[ch * 8 + v];
                         const int c = 4 * v;
-                        r[c] = __float_as_uint(__uint_as_float(r[c]) + x.x) * mul + (uint32_t)(ch * 32 + c + 1);
-                        r[c + 1] = __float_as_uint(__uint_as_float(r[c + 1]) + x.y) * mul + (uint32_t)(ch * 32 + c + 2);
-                        r[c + 2] = __float_as_uint(__uint_as_float(r[c + 2]) + x.z) * mul + (uint32_t)(ch * 32 + c + 3);
-                        r[c + 3] = __float_as_uint(__uint_as_float(r[c + 3]) + x.w) * mul + (uint32_t)(ch * 32 + c + 4);
+                        r[c] = __float_as_uint(__uint_as_float(r[c]) + x.x) * mul + (uint32_t)(c + 1);
+                        r[c + 1] = __float_as_uint(__uint_as_float(r[c + 1]) + x.y) * mul + (uint32_t)(c + 2);
+                        r[c + 2] = __float_as_uint(__uint_as_float(r[c + 2]) + x.z) * mul + (uint32_t)(c + 3);
+                        r[c + 3] = __float_as_uint(__uint_as_float(r[c + 3]) + x.w) * mul + (uint32_t)(c + 4);
                     }
-                    s2.chunk(r);
+                    s2.chunk(r, (uint32_t)(ch * 32));
                 } else {
 #pragma unroll
                     for (int v = 0; v < 8; ++v) {
                         const float4 x = np[ch * 8 + v];
                         const int c = 4 * v;
-                        r[c] = __byte_perm(__float_as_uint(__uint_as_float(r[c]) + x.x), (uint32_t)(ch * 32 + c + 1), 0x3214);
-                        r[c + 1] = __byte_perm(__float_as_uint(__uint_as_float(r[c + 1]) + x.y), (uint32_t)(ch * 32 + c + 2), 0x3214);
-                        r[c + 2] = __byte_perm(__float_as_uint(__uint_as_float(r[c + 2]) + x.z), (uint32_t)(ch * 32 + c + 3), 0x3214);
-                        r[c + 3] = __byte_perm(__float_as_uint(__uint_as_float(r[c + 3]) + x.w), (uint32_t)(ch * 32 + c + 4), 0x3214);
+                        r[c] = __byte_perm(__float_as_uint(__uint_as_float(r[c]) + x.x), (uint32_t)(c + 1), 0x3214);
+                        r[c + 1] = __byte_perm(__float_as_uint(__uint_as_float(r[c + 1]) + x.y), (uint32_t)(c + 2), 0x3214);
+                        r[c + 2] = __byte_perm(__float_as_uint(__uint_as_float(r[c + 2]) + x.z), (uint32_t)(c + 3), 0x3214);
+                        r[c + 3] = __byte_perm(__float_as_uint(__uint_as_float(r[c + 3]) + x.w), (uint32_t)(c + 4), 0x3214);
                     }
-                    s3.chunk(r);
+                    s3.chunk(r, (uint32_t)(ch * 32));
                 }
-                if (ch < 3) tmem_ld_wait();
             }
             tc_fence_before();
             __syncwarp();
@@ -516,7 +526,8 @@ int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, 
     const int G = l2_tc_grid(ctx, P.MT, P.NT);
     {
         pm_prof_scope prof(ctx, 0);
-        l2_tc_kernel<<<G, TC_THREADS, SMEM_TOTAL, ctx->stream>>>(tq, tt, P);
+        cudaError_t le = pm_launch_pdl(l2_tc_kernel, dim3(G), dim3(TC_THREADS), (size_t)SMEM_TOTAL, ctx->stream, tq, tt, P);
+        if (le != cudaSuccess) return pm_fail(ctx, PM_CUDA_ERR, "l2_tc_kernel launch: %s", cudaGetErrorString(le));
     }
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;

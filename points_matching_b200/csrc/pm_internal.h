@@ -81,6 +81,31 @@ void *pm_ws(pm_ctx *ctx, int slot, size_t bytes);   // nullptr on failure (ctx->
     type var = (type)pm_ws(ctx, slot, bytes);                                           \
     if (!var) return PM_CUDA_ERR
 
+// Programmatic dependent launch (PDL): every kernel of a chain is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and begins with pm_pdl_prologue():
+// it lets the NEXT kernel of the stream start launching right away (its CTAs become
+// resident and run their own prologue), then waits until the PREVIOUS kernel has fully
+// completed and flushed.  Data order is unchanged; only launch latency overlaps.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pm_pdl_prologue()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                        cudaStream_t stream, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 static inline int pm_cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int pm_round_up(int a, int b) { return pm_cdiv(a, b) * b; }
 
