@@ -7,8 +7,10 @@
 //
 //   d^2(i,j) = ||a_i||^2 + ||b_j||^2 - 2 a_i.b_j
 // The -2 is folded into the packed train operand, ||a_i||^2 is row-constant and added
-// after selection, ||b_j||^2 is added in the epilogue.  Operands are bf16 "hi|lo" rows
-// written by K1 (l2.cu):
+// after selection, and ||b_j||^2 (plus the key bias) rides in the GEMM itself: one extra
+// K=16 MMA step multiplies a constant [1 1 1 0...] row block by the column norm split
+// exactly into three bf16 terms, so the epilogue does no arithmetic on the distance at all.
+// Operands are bf16 "hi|lo" rows written by K1 (l2.cu):
 //   exact-integer mode (SIFT, values 0..255): lo == 0, 2 k-blocks, the GEMM is exact
 //   split mode (general floats):  a.b ~ ah.bh + ah.bl + al.bh, 6 k-blocks
 //
@@ -19,14 +21,15 @@
 //                                accumulators double-buffered in TMEM (2 x 256 columns);
 //                                also allocates / frees TMEM
 //   warps 2-17  epilogue       : 4 warps per scheduler, each owns 32 rows x 64 columns of a
-//                                tile: tcgen05.ld 32x32b.x32, + ||b||^2 (staged in smem),
-//                                pack (value | column) into one u32 key, branch-free min/max
+//                                tile: tcgen05.ld 32x32b.x32, pack (value | column) into one
+//                                u32 key (IMAD / PRMT), branch-free min/max
 //                                tournament (VIMNMX/VIMNMX3) over adjacent column PAIRS: top-2
 //                                pair minima in exact mode, top-3 in split mode, kept in
 //                                registers across the sweep (K3 re-checks the partners exactly).
 // Each CTA walks a contiguous range of the (row-tile, column-tile) space; per row tile it
 // writes one "segment" of candidates which K3 merges, re-ranks in FP32 and certifies.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include "pm_internal.h"
 #include "l2_common.h"
 
@@ -47,8 +50,13 @@ constexpr int SMEM_A = 0;
 constexpr int SMEM_B = A_MAXBLK * A_BLK_BYTES;                 // 65536
 constexpr int SMEM_BAR = SMEM_B + NSTAGE * B_BLK_BYTES;        // 196608
 constexpr int SMEM_SCRATCH = SMEM_BAR + 256;                   // (NSLICE-1) x 128 rows x 3 candidates
-constexpr int SMEM_NORM = SMEM_SCRATCH + (NSLICE - 1) * BM * 3 * 8;   // 2 x 256 staged column norms
-constexpr int SMEM_TOTAL = SMEM_NORM + 2 * BN * 4 + 1024;      // + alignment slack
+// "ext" operands of the norm MMA step, K-major, no swizzle: core matrix = 8 rows x 16 B,
+// the two 8-element K halves 128 B apart (LBO), 8-row groups 256 B apart (SBO)
+constexpr int EXT_A_BYTES = BM * 32;                           // 4 KB, constant [1 1 1 0...] rows
+constexpr int EXT_B_BYTES = BN * 32;                           // 8 KB per tile, double buffered
+constexpr int SMEM_EXTA = SMEM_SCRATCH + (NSLICE - 1) * BM * 3 * 8;
+constexpr int SMEM_EXTB = SMEM_EXTA + EXT_A_BYTES;
+constexpr int SMEM_TOTAL = SMEM_EXTB + 2 * EXT_B_BYTES + 1024; // + alignment slack
 
 // instruction descriptor: D=F32, A=B=BF16, K-major both, N=256, M=128
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
@@ -105,6 +113,26 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr)
 {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
            (2ull << 61);
+}
+// K-major, no swizzle (ext operands): LBO = 128 B between the K halves, SBO = 256 B between 8-row groups
+__device__ __forceinline__ uint64_t make_sdesc_ext(uint32_t saddr)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint32_t ext_row_offset(int r) { return (uint32_t)((r >> 3) * 256 + (r & 7) * 16); }
+// exact three-term bf16 split of an fp32 value (24-bit mantissa = 3 x 8 bits)
+__device__ __forceinline__ uint4 bf16_split3(float v)
+{
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(m);
+    const __nv_bfloat16 l = __float2bfloat16_rn(r2);
+    uint4 o;
+    o.x = (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(m) << 16);
+    o.y = (uint32_t)__bfloat16_as_ushort(l);
+    o.z = 0u; o.w = 0u;
+    return o;
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
 {
@@ -246,7 +274,9 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     const uint32_t bar_full = sBar, bar_empty = sBar + 8 * NSTAGE;
     const uint32_t bar_afull = sBar + 16 * NSTAGE, bar_aempty = bar_afull + 8;
     const uint32_t bar_tfull = bar_aempty + 8, bar_tempty = bar_tfull + 16;
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(sgen + SMEM_BAR + 16 * NSTAGE + 48);
+    const uint32_t bar_ext = bar_tempty + 16;                    // [2]: norm operand of a tile staged
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(sgen + SMEM_BAR + 16 * NSTAGE + 64);
+    const uint32_t sExtA = sbase + SMEM_EXTA, sExtB = sbase + SMEM_EXTB;
     L2Cand *scratch = reinterpret_cast<L2Cand *>(sgen + SMEM_SCRATCH);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -269,13 +299,24 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
             for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
             mbar_init(bar_afull, 1);
             mbar_init(bar_aempty, 1);
-            for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, EPI_WARPS); }
+            for (int a = 0; a < 2; ++a) {
+                mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, EPI_WARPS);
+                mbar_init(bar_ext + 8 * a, BN / 32);             // one arrival per staging warp
+            }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32((const void *)tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= EPI_WARP0 && (int)threadIdx.x - EPI_WARP0 * 32 < BM) {
+        // constant A operand of the norm step: row r = [1 1 1 0 0 0 0 0 | 0 x 8] in bf16
+        const int r = (int)threadIdx.x - EPI_WARP0 * 32;
+        uint8_t *dst = sgen + SMEM_EXTA + ext_row_offset(r);
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -328,6 +369,10 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                     umma_commit(bar_empty + 8 * stage);
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
+                // norm step: acc += [1 1 1 0..] x split3(||b||^2 + bias)
+                mbar_wait(bar_ext + 8 * acc, acc_phase);
+                tc_fence_after();
+                umma_bf16(d_tmem, make_sdesc_ext(sExtA), make_sdesc_ext(sExtB + acc * EXT_B_BYTES), IDESC, 1u);
                 umma_commit(bar_tfull + 8 * acc);
                 if (tile + 1 < t_end && (tile + 1) / P.NT != m) umma_commit(bar_aempty);
                 acc ^= 1; if (acc == 0) acc_phase ^= 1;
@@ -340,12 +385,27 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         const int slice = e >> 2;              // which 64 of the tile's 256 columns
         const int row = quarter * 32 + lane;   // row within the 128-row tile
         const float shift = l2_split_shift(fl.max_qnorm_bits);
-        const float nb_off = exact ? L2_EXACT_BIAS : shift;            // folded into the staged column norms
-        float *snorm = reinterpret_cast<float *>(sgen + SMEM_NORM);    // [2][256] by accumulator parity
+        const float nb_off = exact ? L2_EXACT_BIAS : shift;            // bias folded into the norm operand
+        const float nb_pad = exact ? L2_EXACT_PAD : 3.0e38f;           // pad columns: never selected
         const uint32_t mul = P.mul256;
-        const int et = e * 32 + lane;                                  // threads 0..255 stage one column norm each
+        const int et = e * 32 + lane;                                  // threads 0..255 stage one column each
         uint32_t acc = 0, acc_phase = 0; int cur_m = -1;
-        float nb_pref = (et < BN && t_begin < t_end) ? __ldg(P.tnorm + (t_begin % P.NT) * BN + et) : 0.f;
+        // stage_ext(buf, nb): this thread's column of the norm operand, then one arrival per warp
+        auto stage_ext = [&](uint32_t buf, float nb) {
+            const float v = nb == __int_as_float(0x7f800000) ? nb_pad : nb + nb_off;
+            const uint4 s3 = bf16_split3(v);
+            uint8_t *dst = sgen + SMEM_EXTB + buf * EXT_B_BYTES + ext_row_offset(et);
+            *reinterpret_cast<uint4 *>(dst) = s3;
+            *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(0u, 0u, 0u, 0u);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // visible to the tensor core's proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_ext + 8 * buf);
+        };
+        float nb_pref = 0.f;
+        if (et < BN && t_begin < t_end) {
+            stage_ext(0u, __ldg(P.tnorm + (t_begin % P.NT) * BN + et));
+            if (t_begin + 1 < t_end) nb_pref = __ldg(P.tnorm + ((t_begin + 1) % P.NT) * BN + et);
+        }
         Sel2 s2; s2.reset();
         Sel3 s3; s3.reset();
 
@@ -385,17 +445,16 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         for (int tile = t_begin; tile < t_end; ++tile) {
             const int m = tile / P.NT, n = tile % P.NT;
             if (m != cur_m) { if (cur_m >= 0) flush(cur_m); cur_m = m; }
-            // stage this tile's 256 column norms in shared memory (prefetched one tile ahead),
-            // so the hot loop reads them with broadcast LDS.128 instead of waiting on L2
-            if (et < BN)
-                snorm[acc * BN + et] = (exact && nb_pref == __int_as_float(0x7f800000)) ? L2_EXACT_PAD : nb_pref + nb_off;
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-            if (et < BN && tile + 1 < t_end) nb_pref = __ldg(P.tnorm + ((tile + 1) % P.NT) * BN + et);
+            // stage the NEXT tile's norm operand (its buffer was last read by the MMA of tile-1,
+            // which this warp has already seen complete) and prefetch the one after
+            if (et < BN && tile + 1 < t_end) {
+                stage_ext(acc ^ 1u, nb_pref);
+                if (tile + 2 < t_end) nb_pref = __ldg(P.tnorm + ((tile + 2) % P.NT) * BN + et);
+            }
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             const int col0 = n * BN + slice * SLICE;
             const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + slice * SLICE;
-            const float4 *np = reinterpret_cast<const float4 *>(snorm + acc * BN + slice * SLICE);
 #pragma unroll 1
             for (int ch = 0; ch < SLICE / 32; ++ch) {
                 uint32_t r[32];
@@ -404,30 +463,15 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                 if (P.dump) {
                     float *drow = P.dump + (size_t)(m * BM + row) * P.nt_pad + col0 + ch * 32;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c)
-                        drow[c] = __uint_as_float(r[c]) + snorm[acc * BN + slice * SLICE + ch * 32 + c] - nb_off;
+                    for (int c = 0; c < 32; ++c) drow[c] = __uint_as_float(r[c]) - nb_off;
                 }
                 if (exact) {
 #pragma unroll
-                    for (int v = 0; v < 8; ++v) {
-                        const float4 x = np[ch * 8 + v];
-                        const int c = 4 * v;
-                        r[c] = __float_as_uint(__uint_as_float(r[c]) + x.x) * mul + (uint32_t)(c + 1);
-                        r[c + 1] = __float_as_uint(__uint_as_float(r[c + 1]) + x.y) * mul + (uint32_t)(c + 2);
-                        r[c + 2] = __float_as_uint(__uint_as_float(r[c + 2]) + x.z) * mul + (uint32_t)(c + 3);
-                        r[c + 3] = __float_as_uint(__uint_as_float(r[c + 3]) + x.w) * mul + (uint32_t)(c + 4);
-                    }
+                    for (int c = 0; c < 32; ++c) r[c] = r[c] * mul + (uint32_t)(c + 1);
                     s2.chunk(r, (uint32_t)(ch * 32));
                 } else {
 #pragma unroll
-                    for (int v = 0; v < 8; ++v) {
-                        const float4 x = np[ch * 8 + v];
-                        const int c = 4 * v;
-                        r[c] = __byte_perm(__float_as_uint(__uint_as_float(r[c]) + x.x), (uint32_t)(c + 1), 0x3214);
-                        r[c + 1] = __byte_perm(__float_as_uint(__uint_as_float(r[c + 1]) + x.y), (uint32_t)(c + 2), 0x3214);
-                        r[c + 2] = __byte_perm(__float_as_uint(__uint_as_float(r[c + 2]) + x.z), (uint32_t)(c + 3), 0x3214);
-                        r[c + 3] = __byte_perm(__float_as_uint(__uint_as_float(r[c + 3]) + x.w), (uint32_t)(c + 4), 0x3214);
-                    }
+                    for (int c = 0; c < 32; ++c) r[c] = __byte_perm(r[c], (uint32_t)(c + 1), 0x3214);
                     s3.chunk(r, (uint32_t)(ch * 32));
                 }
             }
