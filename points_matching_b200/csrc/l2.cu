@@ -325,8 +325,9 @@ int pmk_l2_knn2(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int
                 int q_index_base, pm_dmatch *dout)
 {
     if (nq <= 0) return PM_OK;
-    const int mq_pad = pm_round_up(nq, 128), nt_pad = pm_round_up(nt > 0 ? nt : 1, 256);
-    const int MT = mq_pad / 128, NT = nt_pad / 256;
+    // K2 work items are 256 query rows x 128 train columns
+    const int mq_pad = pm_round_up(nq, 256), nt_pad = pm_round_up(nt > 0 ? nt : 1, 256);
+    const int MT = mq_pad / 256, NT = nt_pad / 128;
     const int smax = l2_tc_smax(ctx, MT, NT);
     const bool use_tc = dim <= L2_KDIM && nt > 0 && !g_l2_force_exact;
     ctx->l2_stats[2] = 0; ctx->l2_stats[3] = 0;

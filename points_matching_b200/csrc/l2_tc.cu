@@ -14,14 +14,18 @@
 //   exact-integer mode (SIFT, values 0..255): lo == 0, 2 k-blocks, the GEMM is exact
 //   split mode (general floats):  a.b ~ ah.bh + ah.bl + al.bh, 6 k-blocks
 //
+// Work item = 256 query rows x 128 train columns: TWO 128-row A tiles stay resident in shared
+// memory and every B k-block that TMA brings in feeds both, which halves the L2 -> SM operand
+// traffic (the binding resource for K = 128: ncu measured 4.4 TB/s of TMA reads with one A tile).
+//
 // Structure (one persistent CTA per SM, 576 threads):
-//   warp 0      TMA producer   : A row-tile resident (<= 4 x 16 KB), B k-blocks through a
-//                                4-stage 32 KB ring (cp.async.bulk.tensor, SWIZZLE_128B)
-//   warp 1      MMA issuer     : tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16,
-//                                accumulators double-buffered in TMEM (2 x 256 columns);
-//                                also allocates / frees TMEM
+//   warp 0      TMA producer   : 2 A row-tiles resident (2 x <= 4 x 16 KB), B k-blocks through
+//                                a 4-stage 16 KB ring (cp.async.bulk.tensor, SWIZZLE_128B)
+//   warp 1      MMA issuer     : tcgen05.mma cta_group::1 kind::f16, M=128 N=128 K=16, one
+//                                accumulator per A tile, double-buffered in TMEM (2 x 2 x 128
+//                                columns); also allocates / frees TMEM
 //   warps 2-17  epilogue       : 4 warps per scheduler, each owns 32 rows x 64 columns of a
-//                                tile: tcgen05.ld 32x32b.x32, pack (value | column) into one
+//                                work item: tcgen05.ld 32x32b.x32, pack (value | column) into one
 //                                u32 key (IMAD / PRMT), branch-free min/max
 //                                tournament (VIMNMX/VIMNMX3) over adjacent column PAIRS: top-2
 //                                pair minima in exact mode, top-3 in split mode, kept in
@@ -35,30 +39,31 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int MH = 2;                        // A row-tiles (m-halves) per work item: 256 rows
 constexpr int A_BLK_BYTES = BM * BK * 2;     // 16 KB
-constexpr int B_BLK_BYTES = BN * BK * 2;     // 32 KB
+constexpr int B_BLK_BYTES = BN * BK * 2;     // 16 KB
 constexpr int NSTAGE = 4;
 constexpr int A_MAXBLK = 4;
 constexpr int EPI_WARP0 = 2;        // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-17 epilogue
 constexpr int EPI_WARPS = 16;       // 4 per scheduler: enough TLP to keep the issue slots busy
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int TC_THREADS = (EPI_WARP0 + EPI_WARPS) * 32;   // 576
-constexpr int NSLICE = EPI_WARPS / 4;                      // column slices per tile
-constexpr int SLICE = BN / NSLICE;                         // 64 columns of each tile per warp
+constexpr int NSLICE = EPI_WARPS / 4 / MH;                 // column slices per accumulator: 2
+constexpr int SLICE = BN / NSLICE;                         // 64 columns per warp
 constexpr int SMEM_A = 0;
-constexpr int SMEM_B = A_MAXBLK * A_BLK_BYTES;                 // 65536
+constexpr int SMEM_B = MH * A_MAXBLK * A_BLK_BYTES;            // 131072
 constexpr int SMEM_BAR = SMEM_B + NSTAGE * B_BLK_BYTES;        // 196608
-constexpr int SMEM_SCRATCH = SMEM_BAR + 256;                   // (NSLICE-1) x 128 rows x 3 candidates
+constexpr int SMEM_SCRATCH = SMEM_BAR + 256;                   // MH x (NSLICE-1) x 128 rows x 3 candidates
 // "ext" operands of the norm MMA step, K-major, no swizzle: core matrix = 8 rows x 16 B,
 // the two 8-element K halves 128 B apart (LBO), 8-row groups 256 B apart (SBO)
 constexpr int EXT_A_BYTES = BM * 32;                           // 4 KB, constant [1 1 1 0...] rows
 constexpr int EXT_B_BYTES = BN * 32;                           // 8 KB per tile, double buffered
-constexpr int SMEM_EXTA = SMEM_SCRATCH + (NSLICE - 1) * BM * 3 * 8;
+constexpr int SMEM_EXTA = SMEM_SCRATCH + MH * (NSLICE - 1) * BM * 3 * 8;
 constexpr int SMEM_EXTB = SMEM_EXTA + EXT_A_BYTES;
 constexpr int SMEM_TOTAL = SMEM_EXTB + 2 * EXT_B_BYTES + 1024; // + alignment slack
 
-// instruction descriptor: D=F32, A=B=BF16, K-major both, N=256, M=128
+// instruction descriptor: D=F32, A=B=BF16, K-major both, N=128, M=128
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                            ((uint32_t)(BM >> 4) << 24);
 
@@ -258,7 +263,7 @@ struct Cand3 {
 struct TcParams {
     const float *tnorm;          // [nt_pad] ||b||^2 (pad columns: +inf)
     const L2Flags *flags;
-    L2Cand *part;                // [mq_pad][smax][3]
+    L2Cand *part;                // [mq_pad][smax][3]; MT counts 256-row super tiles
     float *dump;                 // debug: [mq_pad][nt_pad] of (||b||^2 - 2ab), or null
     int MT, NT, smax, nt_pad;
     uint32_t mul256;             // == 256, passed at run time so the key pack stays an IMAD (FMA pipe), not an ALU LEA
@@ -331,9 +336,10 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                 const int m = tile / P.NT, n = tile % P.NT;
                 if (m != cur_m) {
                     if (cur_m >= 0) { mbar_wait(bar_aempty, apar); apar ^= 1; }
-                    mbar_expect_tx(bar_afull, (uint32_t)(nablk * A_BLK_BYTES));
-                    for (int b = 0; b < nablk; ++b)
-                        tma_load_2d(sA + b * A_BLK_BYTES, &tmap_q, bar_afull, b * BK, m * BM);
+                    mbar_expect_tx(bar_afull, (uint32_t)(MH * nablk * A_BLK_BYTES));
+                    for (int h = 0; h < MH; ++h)
+                        for (int b = 0; b < nablk; ++b)
+                            tma_load_2d(sA + (h * A_MAXBLK + b) * A_BLK_BYTES, &tmap_q, bar_afull, b * BK, (m * MH + h) * BM);
                     cur_m = m;
                 }
                 for (int kb = 0; kb < nkb; ++kb) {
@@ -355,24 +361,29 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                 if (m != cur_m) { mbar_wait(bar_afull, apar); apar ^= 1; cur_m = m; }
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = tmem_base + acc * (MH * BN);     // accumulator (acc, h) at + h * BN
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
                     // A block: hi for kb 0..3 (x B hi, x B lo), lo for kb 4,5 (x B hi)
                     const int ablk = kb < 4 ? (kb & 1) : 2 + (kb & 1);
-                    const uint64_t adesc = make_sdesc(sA + ablk * A_BLK_BYTES);
                     const uint64_t bdesc = make_sdesc(sB + stage * B_BLK_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)   // +32 B per K=16 step inside the swizzle span
-                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (uint32_t)((kb | k) != 0));
+                    for (int h = 0; h < MH; ++h) {      // the same B k-block feeds both A tiles
+                        const uint64_t adesc = make_sdesc(sA + (h * A_MAXBLK + ablk) * A_BLK_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)   // +32 B per K=16 step inside the swizzle span
+                            umma_bf16(d_tmem + h * BN, adesc + 2 * k, bdesc + 2 * k, IDESC, (uint32_t)((kb | k) != 0));
+                    }
                     umma_commit(bar_empty + 8 * stage);
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
                 // norm step: acc += [1 1 1 0..] x split3(||b||^2 + bias)
                 mbar_wait(bar_ext + 8 * acc, acc_phase);
                 tc_fence_after();
-                umma_bf16(d_tmem, make_sdesc_ext(sExtA), make_sdesc_ext(sExtB + acc * EXT_B_BYTES), IDESC, 1u);
+#pragma unroll
+                for (int h = 0; h < MH; ++h)
+                    umma_bf16(d_tmem + h * BN, make_sdesc_ext(sExtA), make_sdesc_ext(sExtB + acc * EXT_B_BYTES), IDESC, 1u);
                 umma_commit(bar_tfull + 8 * acc);
                 if (tile + 1 < t_end && (tile + 1) / P.NT != m) umma_commit(bar_aempty);
                 acc ^= 1; if (acc == 0) acc_phase ^= 1;
@@ -382,8 +393,9 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         // ===================== epilogue =====================
         const int e = warp - EPI_WARP0;
         const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-        const int slice = e >> 2;              // which 64 of the tile's 256 columns
-        const int row = quarter * 32 + lane;   // row within the 128-row tile
+        const int mh = (e >> 2) & (MH - 1);    // which A row-tile (accumulator) of the work item
+        const int slice = e >> 3;              // which 64 of the item's 128 columns
+        const int row = mh * BM + quarter * 32 + lane;   // row within the 256-row work item
         const float shift = l2_split_shift(fl.max_qnorm_bits);
         const float nb_off = exact ? L2_EXACT_BIAS : shift;            // bias folded into the norm operand
         const float nb_pad = exact ? L2_EXACT_PAD : 3.0e38f;           // pad columns: never selected
@@ -421,20 +433,20 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
             }
             if (slice > 0) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) scratch[((slice - 1) * BM + row) * 3 + k] = L2Cand{c.d[k], c.i[k]};
+                for (int k = 0; k < 3; ++k) scratch[((slice - 1) * MH * BM + row) * 3 + k] = L2Cand{c.d[k], c.i[k]};
             }
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             if (slice == 0) {
                 for (int sl = 0; sl < NSLICE - 1; ++sl)
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) { const L2Cand o = scratch[(sl * BM + row) * 3 + k]; c.insert(o.d, o.idx); }
+                    for (int k = 0; k < 3; ++k) { const L2Cand o = scratch[(sl * MH * BM + row) * 3 + k]; c.insert(o.d, o.idx); }
                 // segment slot = index of this CTA among the CTAs that touch row tile m
                 const long long first_tile = (long long)m * P.NT;
                 int c0 = (int)((first_tile * G) / T);
                 while ((T * (c0 + 1)) / G <= first_tile) ++c0;
                 while ((T * c0) / G > first_tile) --c0;
                 const int slot = (int)blockIdx.x - c0;
-                L2Cand *dst = P.part + ((size_t)(m * BM + row) * P.smax + slot) * 3;
+                L2Cand *dst = P.part + ((size_t)(m * MH * BM + row) * P.smax + slot) * 3;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) dst[k] = L2Cand{c.d[k], c.i[k]};
             }
@@ -454,14 +466,14 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             const int col0 = n * BN + slice * SLICE;
-            const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + slice * SLICE;
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (MH * BN) + mh * BN + slice * SLICE;
 #pragma unroll 1
             for (int ch = 0; ch < SLICE / 32; ++ch) {
                 uint32_t r[32];
                 tmem_ld32(taddr0 + ch * 32, r);
                 tmem_ld_wait();
                 if (P.dump) {
-                    float *drow = P.dump + (size_t)(m * BM + row) * P.nt_pad + col0 + ch * 32;
+                    float *drow = P.dump + (size_t)(m * MH * BM + row) * P.nt_pad + col0 + ch * 32;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) drow[c] = __uint_as_float(r[c]) - nb_off;
                 }
@@ -566,7 +578,7 @@ int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, 
     const CUtensorMap &tq = tmaps[0], &tt = tmaps[1];
     TcParams P;
     P.tnorm = tnorm; P.flags = flags; P.part = part; P.dump = dump;
-    P.MT = mq_pad / BM; P.NT = nt_pad / BN; P.smax = smax; P.nt_pad = nt_pad; P.mul256 = 256u;
+    P.MT = mq_pad / (MH * BM); P.NT = nt_pad / BN; P.smax = smax; P.nt_pad = nt_pad; P.mul256 = 256u;
     const int G = l2_tc_grid(ctx, P.MT, P.NT);
     {
         pm_prof_scope prof(ctx, 0);

@@ -23,7 +23,7 @@ def run(nq, nt, kind):
     else:
         q, t = synth.surf_pair(nq, nt, seed=5)
     dq, dt = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
-    mq_pad, nt_pad = (nq + 127) // 128 * 128, (nt + 255) // 256 * 256
+    mq_pad, nt_pad = (nq + 255) // 256 * 256, (nt + 255) // 256 * 256
     dump = torch.full((mq_pad, nt_pad), float("nan"), device="cuda", dtype=torch.float32)
     out = torch.zeros((nq, 2, 4), device="cuda", dtype=torch.int32)
     L.pm_debug_set_l2_dump(C.c_void_p(dump.data_ptr()))
