@@ -33,6 +33,7 @@
 // Each CTA walks a contiguous range of the (row-tile, column-tile) space; per row tile it
 // writes one "segment" of candidates which K3 merges, re-ranks in FP32 and certifies.
 #include <cuda.h>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include "pm_internal.h"
 #include "l2_common.h"
@@ -266,6 +267,8 @@ struct TcParams {
     L2Cand *part;                // [mq_pad][smax][3]; MT counts 256-row super tiles
     float *dump;                 // debug: [mq_pad][nt_pad] of (||b||^2 - 2ab), or null
     int MT, NT, smax, nt_pad;
+    long long *trace;            // PM_K2_DBG & 32: clock64 stamps of CTA 0, [tile][4]
+    uint32_t dbg;                // timing experiments only (PM_K2_DBG): 1 skip selection math, 2 skip main MMAs, 4 skip TMA of B
     uint32_t mul256;             // == 256, passed at run time so the key pack stays an IMAD (FMA pipe), not an ALU LEA
 };
 
@@ -344,6 +347,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                 }
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    if (P.dbg & 4u) { mbar_arrive(bar_full + 8 * stage); if (++stage == NSTAGE) { stage = 0; phase ^= 1; } continue; }
                     mbar_expect_tx(bar_full + 8 * stage, B_BLK_BYTES);
                     // k-blocks: hi0 hi1 | lo0 lo1 | hi0 hi1   (packed row = [hi 0..127 | lo 128..255])
                     const int kc = ((kb == 2 || kb == 3) ? 128 : 0) + (kb & 1) * BK;
@@ -356,18 +360,25 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         // ===================== MMA issuer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0, apar = 0, acc = 0, acc_phase = 0; int cur_m = -1;
+#define TR(slot) do { if (P.trace && blockIdx.x == 0 && tile - t_begin < 64) P.trace[(tile - t_begin) * 16 + (slot)] = clock64(); } while (0)
             for (int tile = t_begin; tile < t_end; ++tile) {
+                TR(0);
                 const int m = tile / P.NT;
                 if (m != cur_m) { mbar_wait(bar_afull, apar); apar ^= 1; cur_m = m; }
+                TR(1);
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                TR(2);
                 tc_fence_after();
+                TR(3);
                 const uint32_t d_tmem = tmem_base + acc * (MH * BN);     // accumulator (acc, h) at + h * BN
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
+                    if (kb == 0) TR(4); else if (kb == 1) TR(7);
                     // A block: hi for kb 0..3 (x B hi, x B lo), lo for kb 4,5 (x B hi)
                     const int ablk = kb < 4 ? (kb & 1) : 2 + (kb & 1);
                     const uint64_t bdesc = make_sdesc(sB + stage * B_BLK_BYTES);
+                    if (!(P.dbg & 2u))
 #pragma unroll
                     for (int h = 0; h < MH; ++h) {      // the same B k-block feeds both A tiles
                         const uint64_t adesc = make_sdesc(sA + (h * A_MAXBLK + ablk) * A_BLK_BYTES);
@@ -375,16 +386,23 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                         for (int k = 0; k < BK / 16; ++k)   // +32 B per K=16 step inside the swizzle span
                             umma_bf16(d_tmem + h * BN, adesc + 2 * k, bdesc + 2 * k, IDESC, (uint32_t)((kb | k) != 0));
                     }
+                    if (kb == 0) TR(5); else if (kb == 1) TR(8);
                     umma_commit(bar_empty + 8 * stage);
+                    if (kb == 0) TR(6); else if (kb == 1) TR(9);
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
                 // norm step: acc += [1 1 1 0..] x split3(||b||^2 + bias)
+                if (!(P.dbg & 8u)) {
                 mbar_wait(bar_ext + 8 * acc, acc_phase);
+                TR(10);
                 tc_fence_after();
 #pragma unroll
                 for (int h = 0; h < MH; ++h)
                     umma_bf16(d_tmem + h * BN, make_sdesc_ext(sExtA), make_sdesc_ext(sExtB + acc * EXT_B_BYTES), IDESC, 1u);
+                }
+                TR(11);
                 umma_commit(bar_tfull + 8 * acc);
+                TR(12);
                 if (tile + 1 < t_end && (tile + 1) / P.NT != m) umma_commit(bar_aempty);
                 acc ^= 1; if (acc == 0) acc_phase ^= 1;
             }
@@ -459,17 +477,19 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
             if (m != cur_m) { if (cur_m >= 0) flush(cur_m); cur_m = m; }
             // stage the NEXT tile's norm operand (its buffer was last read by the MMA of tile-1,
             // which this warp has already seen complete) and prefetch the one after
-            if (et < BN && tile + 1 < t_end) {
+            if (et < BN && tile + 1 < t_end && !(P.dbg & 8u)) {
                 stage_ext(acc ^ 1u, nb_pref);
                 if (tile + 2 < t_end) nb_pref = __ldg(P.tnorm + ((tile + 2) % P.NT) * BN + et);
             }
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
+            if (P.trace && blockIdx.x == 0 && e == 0 && lane == 0 && tile - t_begin < 64) P.trace[(tile - t_begin) * 16 + 13] = clock64();
             const int col0 = n * BN + slice * SLICE;
             const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (MH * BN) + mh * BN + slice * SLICE;
 #pragma unroll 1
             for (int ch = 0; ch < SLICE / 32; ++ch) {
                 uint32_t r[32];
+                if (P.dbg & 16u) continue;
                 tmem_ld32(taddr0 + ch * 32, r);
                 tmem_ld_wait();
                 if (P.dump) {
@@ -477,6 +497,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
 #pragma unroll
                     for (int c = 0; c < 32; ++c) drow[c] = __uint_as_float(r[c]) - nb_off;
                 }
+                if (P.dbg & 1u) { s2.m1 ^= r[0] ^ r[31]; continue; }
                 if (exact) {
 #pragma unroll
                     for (int c = 0; c < 32; ++c) r[c] = r[c] * mul + (uint32_t)(c + 1);
@@ -490,6 +511,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+            if (P.trace && blockIdx.x == 0 && e == 0 && lane == 0 && tile - t_begin < 64) P.trace[(tile - t_begin) * 16 + 14] = clock64();
             if (exact) s2.end_tile(col0); else s3.end_tile(col0);
             acc ^= 1; if (acc == 0) acc_phase ^= 1;
         }
@@ -531,6 +553,9 @@ int make_tmap(pm_ctx *ctx, CUtensorMap *tm, const void *base, int rows_pad, int 
 }
 
 }  // namespace
+
+static long long *g_k2_trace = nullptr;
+extern "C" void pm_debug_set_k2_trace(long long *p) { g_k2_trace = p; }
 
 int l2_tc_grid(pm_ctx *ctx, int MT, int NT)
 {
@@ -579,6 +604,8 @@ int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, 
     TcParams P;
     P.tnorm = tnorm; P.flags = flags; P.part = part; P.dump = dump;
     P.MT = mq_pad / (MH * BM); P.NT = nt_pad / BN; P.smax = smax; P.nt_pad = nt_pad; P.mul256 = 256u;
+    { const char *dv = getenv("PM_K2_DBG"); P.dbg = dv ? (uint32_t)atoi(dv) : 0u; }
+    P.trace = (P.dbg & 32u) ? g_k2_trace : nullptr;
     const int G = l2_tc_grid(ctx, P.MT, P.NT);
     {
         pm_prof_scope prof(ctx, 0);

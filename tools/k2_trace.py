@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""Per-tile clock64 stamps of CTA 0 in K2 (PM_K2_DBG must include 32)."""
+import ctypes as C, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import points_matching_b200 as pm
+from points_matching_b200 import _lib
+ctx = pm.Context(0)
+nq, nt = 148 * 256, 128 * 24
+rng = np.random.default_rng(0)
+q = torch.from_numpy(rng.integers(0, 200, (nq, 128)).astype(np.float32)).cuda()
+t = torch.from_numpy(rng.integers(0, 200, (nt, 128)).astype(np.float32)).cuda()
+out = torch.zeros((nq, 2, 4), dtype=torch.int32, device="cuda")
+tr = torch.zeros((64, 16), dtype=torch.int64, device="cuda")
+_lib.lib().pm_debug_set_k2_trace(C.c_void_p(tr.data_ptr()))
+for _ in range(3):
+    ctx.knn2_l2_f32_dev(q.data_ptr(), nq, t.data_ptr(), nt, 128, out.data_ptr())
+ctx.sync(); torch.cuda.synchronize()
+a = tr.cpu().numpy()[:24]
+print("dbg", os.environ.get("PM_K2_DBG"))
+names = ["top", "afull", "tempty_ok", "fence", "full0", "mma0", "commit0", "full1", "mma1", "commit1", "ext_ok", "ext_mma", "tfull_commit", "epi_full", "epi_arrive"]
+print("per-tile deltas between consecutive MMA-thread stamps (cycles), tiles 4..11:")
+print(" ".join(f"{n:>9s}" for n in names[1:13]), "| loop")
+for i in range(4, 12):
+    r = a[i]
+    d = [r[k] - r[k - 1] for k in range(1, 13)]
+    print(" ".join(f"{x:9d}" for x in d), "|", a[i + 1][0] - r[0], " epi: full@", r[13] - r[0], "arrive@", r[14] - r[0])
