@@ -80,3 +80,14 @@ def test_sass_is_blackwell_native():
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "POPC"):
         assert mnemonic in sass, mnemonic
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", SO_PATH], capture_output=True, text=True).stdout
+
+
+def test_cpp_host_layer_compiles_and_links(L):
+    """include/pm.hpp (the OpenCV look-alikes the reference's main.cpp would call) and the host
+    C++ example build with plain g++ against libpm.so -- no CUDA toolkit on the host side."""
+    import subprocess
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples"), "-s"])
+    exe = os.path.join(ROOT, "examples", "match_and_estimate")
+    assert os.path.exists(exe)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr

@@ -378,3 +378,48 @@ def test_opencv_lookalike_api(pm, golden):
     assert np.allclose(lines[:, 0] ** 2 + lines[:, 1] ** 2, 1.0, atol=1e-5)
     with pytest.raises(pm.PMError):
         pm.BFMatcher(pm.NORM_L2, crossCheck=True).knnMatch(d1, d2, k=2)
+
+
+@pytest.mark.parametrize("mode", ["literal", "ratio"])
+def test_cpp_host_example_matches_python_mirror(pm, golden, mode, tmp_path):
+    """examples/match_and_estimate (host C++ -> pm.hpp -> C ABI) on the reference's own image pair
+    (SIFT stand-in for SURF): same matches as the Python mirror, bit for bit; F of the same quality."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "match_and_estimate")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(root, "examples"), "-s"])
+    g = golden["image_pair"]
+    d1, d2 = g["desc1"].astype(np.float32), g["desc2"].astype(np.float32)
+    k1, k2 = g["kp1"].astype(np.float32), g["kp2"].astype(np.float32)
+    paths = []
+    for name, a in (("d1", d1), ("d2", d2), ("k1", k1), ("k2", k2)):
+        p = str(tmp_path / f"{name}.f32")
+        np.ascontiguousarray(a).tofile(p)
+        paths.append(p)
+    out = subprocess.run([exe, mode, paths[0], str(len(d1)), paths[1], str(len(d2)), "128", paths[2], paths[3]],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.splitlines()
+    good = np.array([[float(x) for x in ln.split()[1:]] for ln in lines if ln.startswith("g ")])
+    matcher = pm.BFMatcher(pm.NORM_L2)
+    if mode == "literal":
+        ref, mn, mx = pm.minmax_filter(matcher.match(d1, d2))       # main.cpp:46-69
+        head = [ln for ln in lines if ln.startswith("matches")][0].split()
+        assert float(head[3]) == mn and float(head[5]) == mx
+    else:
+        ref = pm.ratio_test(matcher.knnMatchArray(d1, d2), 0.75)
+    assert len(good) == len(ref) > 50
+    assert (good[:, 0] == ref["queryIdx"]).all() and (good[:, 1] == ref["trainIdx"]).all()
+    assert np.allclose(good[:, 2], ref["distance"], rtol=1e-7)
+    F = np.array([float(x) for x in [ln for ln in lines if ln.startswith("F ")][0].split()[1:]]).reshape(3, 3)
+    assert F[2, 2] == 1.0 or abs(F[2, 2] - 1) < 1e-12
+    assert abs(np.linalg.det(F)) < 1e-6 * np.abs(F).max() ** 3 + 1e-12                # rank 2
+    line0 = [float(x) for x in [ln for ln in lines if ln.startswith("line0")][0].split()[1:]]
+    assert abs(line0[0] ** 2 + line0[1] ** 2 - 1) < 1e-5
+    if mode == "ratio":
+        inl = int([ln for ln in lines if ln.startswith("inliers")][0].split()[1])
+        assert inl >= 0.9 * g["ransac_mask"].sum()
+        mean = float([ln for ln in lines if ln.startswith("mean_sampson")][0].split()[1])
+        assert np.isfinite(mean)

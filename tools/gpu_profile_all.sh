@@ -1,0 +1,19 @@
+#!/bin/bash
+# One gpurun call: parity tests, a full bench line, the ncu launch list of the bench command,
+# and one `ncu --set full` capture of each dominant kernel (K2 L2 GEMM, K4 Hamming, K7 scoring).
+# Usage (from the repo root, on the GPU box): bash tools/gpu_profile_all.sh <tag>
+set -u
+TAG=${1:-r1}
+O=gpurun_out
+mkdir -p $O
+python -m pytest tests -m gpu -x -q > $O/pytest_$TAG.log 2>&1; echo "pytest exit $?" >> $O/pytest_$TAG.log
+tail -3 $O/pytest_$TAG.log
+python bench.py --steps 1000 --warmup 10 > $O/bench_$TAG.json 2> $O/bench_$TAG.err; echo "bench exit $?"
+SHORT="python bench.py --steps 10 --warmup 3 --no-ramp --no-cpu --ransac-steps 2"
+$SHORT > $O/plain_$TAG.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_$TAG.csv $SHORT > $O/ncu_list_$TAG.log 2>&1
+echo "launch list exit $?"
+for K in l2_tc_kernel ham_knn2_kernel ransac_score_kernel; do
+  ncu --set full --clock-control none --import-source on -k regex:$K -s 4 -c 1 -o $O/prof_${K}_$TAG -f $SHORT > $O/ncu_${K}_$TAG.log 2>&1
+  echo "ncu $K exit $?"
+done
