@@ -148,7 +148,7 @@ int orc_cross_check(const orc_dmatch *knn, int nq, int knn_stride,
         const orc_dmatch *m = knn + (size_t)i * knn_stride;
         int j = m->trainIdx;
         if (j < 0 || j >= nt) continue;
-        if ((uint32_t)(col_best[j] & 0xFFFFFFFFu) == (uint32_t)i) out[n++] = *m;
+        if ((uint32_t)(col_best[j] & 0xFFFFFFFFu) == (uint32_t)m->queryIdx) out[n++] = *m;   /* queryIdx == i unless the rows are a shard */
     }
     return n;
 }

@@ -63,46 +63,66 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 l2_pack_kernel(const T *__restrict__ q, int nq, int mq_pad, const T *__restrict__ t, int nt, int nt_pad, int dim,
                int vec, __nv_bfloat16 *__restrict__ qpack, __nv_bfloat16 *__restrict__ tpack,
-               float *__restrict__ qnorm, float *__restrict__ tnorm, L2Flags *flags,
+               float *__restrict__ qnorm, uint8_t *__restrict__ text, L2Flags *flags,
                L2Cand *__restrict__ part, int part_per_row)
 {
+    __shared__ unsigned s_max[2][8];
+    __shared__ int s_nonint;
     pm_pdl_prologue();
-    const int lane = threadIdx.x & 31;
-    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const bool is_train = row >= mq_pad;
-    if (is_train) row -= mq_pad;
-    const int n = is_train ? nt : nq;
-    if (row >= (is_train ? nt_pad : mq_pad)) return;
-    float x[4] = {0.f, 0.f, 0.f, 0.f};
-    if (row < n) load_row4((is_train ? t : q) + (size_t)row * dim, lane, dim, vec != 0, x);
-    float s = 0.f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_nonint = 0;
+    unsigned mx_q = 0u, mx_t = 0u;          // running max of the norm bits (norms are >= 0: bits order like floats)
     bool integral = true;
+    const int total = mq_pad + nt_pad, stride = gridDim.x * (blockDim.x >> 5);
+    for (int grow = blockIdx.x * (blockDim.x >> 5) + warp; grow < total; grow += stride) {
+        const bool is_train = grow >= mq_pad;
+        const int row = is_train ? grow - mq_pad : grow;
+        const int n = is_train ? nt : nq;
+        float x[4] = {0.f, 0.f, 0.f, 0.f};
+        if (row < n) load_row4((is_train ? t : q) + (size_t)row * dim, lane, dim, vec != 0, x);
+        float s = 0.f;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        s = fmaf(x[e], x[e], s);
-        integral = integral && (x[e] == rintf(x[e])) && x[e] >= 0.f && x[e] <= 255.f;
-    }
-    s = warp_sum_butterfly(s);
-    const float scale = is_train ? -2.f : 1.f;
-    __nv_bfloat16 hi[4], lo[4];
+        for (int e = 0; e < 4; ++e) {
+            s = fmaf(x[e], x[e], s);
+            integral = integral && (x[e] == rintf(x[e])) && x[e] >= 0.f && x[e] <= 255.f;
+        }
+        s = warp_sum_butterfly(s);
+        const float scale = is_train ? -2.f : 1.f;
+        __nv_bfloat16 hi[4], lo[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const float v = x[e] * scale;
-        hi[e] = __float2bfloat16_rn(v);
-        lo[e] = __float2bfloat16_rn(v - __bfloat162float(hi[e]));
+        for (int e = 0; e < 4; ++e) {
+            const float v = x[e] * scale;
+            hi[e] = __float2bfloat16_rn(v);
+            lo[e] = __float2bfloat16_rn(v - __bfloat162float(hi[e]));
+        }
+        __nv_bfloat16 *dst = (is_train ? tpack : qpack) + (size_t)row * L2_PACK_COLS;
+        *reinterpret_cast<uint2 *>(dst + 4 * lane) = *reinterpret_cast<uint2 *>(hi);
+        *reinterpret_cast<uint2 *>(dst + L2_KDIM + 4 * lane) = *reinterpret_cast<uint2 *>(lo);
+        if (is_train) {
+            // K2's norm operand: [n_h n_m n_l 1 1 1 0 0 | 0 x 8] bf16 in the smem image of the row's column tile
+            if (lane < 2) {
+                const uint4 s3 = bf16_split3(row < n ? s : __uint_as_float(L2_PAD_NORM_BITS));
+                uint8_t *e = text + (size_t)(row >> 7) * L2_EXT_BYTES + ext_row_offset(row & 127) + lane * 128;
+                *reinterpret_cast<uint4 *>(e) = lane == 0 ? make_uint4(s3.x, s3.y | 0x3F800000u, 0x3F803F80u, 0u)
+                                                          : make_uint4(0u, 0u, 0u, 0u);
+            }
+            if (row < n) mx_t = max(mx_t, __float_as_uint(s));
+        } else {
+            if (lane == 0) qnorm[row] = row < n ? s : 0.f;
+            if (row < n) mx_q = max(mx_q, __float_as_uint(s));
+            for (int k = lane; k < part_per_row; k += 32) part[(size_t)row * part_per_row + k] = L2Cand{L2_INF, -1};
+        }
     }
-    __nv_bfloat16 *dst = (is_train ? tpack : qpack) + (size_t)row * L2_PACK_COLS;
-    *reinterpret_cast<uint2 *>(dst + 4 * lane) = *reinterpret_cast<uint2 *>(hi);
-    *reinterpret_cast<uint2 *>(dst + L2_KDIM + 4 * lane) = *reinterpret_cast<uint2 *>(lo);
-    if (lane == 0) {
-        (is_train ? tnorm : qnorm)[row] = row < n ? s : (is_train ? L2_INF : 0.f);
-        // same-address atomics serialise in L2: only rows that would raise the max issue one
-        unsigned *mx = is_train ? &flags->max_tnorm_bits : &flags->max_qnorm_bits;
-        if (row < n && __float_as_uint(s) > *reinterpret_cast<volatile unsigned *>(mx)) atomicMax(mx, __float_as_uint(s));
+    // one atomic per block and side (same-address traffic serialises in L2)
+    if (!__all_sync(0xffffffffu, integral) && lane == 0) s_nonint = 1;
+    if (lane == 0) { s_max[0][warp] = mx_q; s_max[1][warp] = mx_t; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        unsigned mx = 0u;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mx = max(mx, s_max[threadIdx.x][w]);
+        if (mx) atomicMax(threadIdx.x == 0 ? &flags->max_qnorm_bits : &flags->max_tnorm_bits, mx);
     }
-    if (!__all_sync(0xffffffffu, integral) && lane == 0) flags->nonexact = 1;
-    if (!is_train)
-        for (int k = lane; k < part_per_row; k += 32) part[(size_t)row * part_per_row + k] = L2Cand{L2_INF, -1};
+    if (threadIdx.x == 2 && s_nonint) flags->nonexact = 1;
 }
 
 // order-preserving float -> uint map (handles negatives; t = ||b||^2 - 2ab can be < 0)
@@ -343,21 +363,21 @@ int pmk_l2_knn2(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int
     PM_WS(ctx, qpack, __nv_bfloat16 *, WS_Q_PACK, (size_t)mq_pad * L2_PACK_COLS * 2);
     PM_WS(ctx, tpack, __nv_bfloat16 *, WS_T_PACK, (size_t)nt_pad * L2_PACK_COLS * 2);
     PM_WS(ctx, qnorm, float *, WS_Q_NORM, (size_t)mq_pad * 4);
-    PM_WS(ctx, tnorm, float *, WS_T_NORM, (size_t)nt_pad * 4);
+    PM_WS(ctx, text, uint8_t *, WS_T_NORM, (size_t)(nt_pad / 128) * L2_EXT_BYTES);
     PM_WS(ctx, part, L2Cand *, WS_L2_PART, (size_t)mq_pad * smax * 3 * sizeof(L2Cand));
     PM_WS(ctx, flagged, int *, WS_L2_FLAGGED, (size_t)nq * 4);
-    const int pack_blocks = pm_cdiv(mq_pad + nt_pad, 8);
+    const int pack_blocks = min(pm_cdiv(mq_pad + nt_pad, 8), 8 * ctx->num_sms);
     if (is_u8) {
         const int vec = dim == L2_KDIM && (((uintptr_t)dq | (uintptr_t)dt) & 3) == 0;
         PM_CUDA(ctx, pm_launch_pdl(l2_pack_kernel<uint8_t>, dim3(pack_blocks), dim3(256), 0, ctx->stream, (const uint8_t *)dq, nq, mq_pad,
-                                   (const uint8_t *)dt, nt, nt_pad, dim, vec, qpack, tpack, qnorm, tnorm, flags, part, smax * 3));
+                                   (const uint8_t *)dt, nt, nt_pad, dim, vec, qpack, tpack, qnorm, text, flags, part, smax * 3));
     } else {
         const int vec = dim == L2_KDIM && (((uintptr_t)dq | (uintptr_t)dt) & 15) == 0;
         PM_CUDA(ctx, pm_launch_pdl(l2_pack_kernel<float>, dim3(pack_blocks), dim3(256), 0, ctx->stream, (const float *)dq, nq, mq_pad,
-                                   (const float *)dt, nt, nt_pad, dim, vec, qpack, tpack, qnorm, tnorm, flags, part, smax * 3));
+                                   (const float *)dt, nt, nt_pad, dim, vec, qpack, tpack, qnorm, text, flags, part, smax * 3));
     }
     PM_CHECK_LAUNCH(ctx);
-    int st = l2_tc_launch(ctx, qpack, mq_pad, tpack, nt_pad, tnorm, flags, part, smax, g_l2_dump);
+    int st = l2_tc_launch(ctx, qpack, mq_pad, tpack, nt_pad, text, flags, part, smax, g_l2_dump);
     if (st != PM_OK) return st;
     if (is_u8)
         PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<uint8_t>, dim3(pm_cdiv(nq, 8)), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,

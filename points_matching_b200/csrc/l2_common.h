@@ -1,6 +1,9 @@
 // l2_common.h -- types shared by the L2 kernels (K1 pack, K2 tensor-core GEMM, K3 finish).
 #pragma once
 #include <cstdint>
+#ifdef __CUDACC__
+#include <cuda_bf16.h>
+#endif
 
 // Packed operand row: [hi bf16 x128 | lo bf16 x128] = 512 B (K padded to 128).
 #define L2_PACK_COLS 256
@@ -8,7 +11,10 @@
 // exact-integer mode: t + L2_EXACT_BIAS lies in [2^23, 2^24) -> unit spacing, so the low 24
 // bits of the float are (0x400000 + t) and order like the integers themselves
 #define L2_EXACT_BIAS 12582912.0f          /* 1.5 * 2^23 */
-#define L2_EXACT_PAD 16777215.0f           /* pad columns: largest value of that binade */
+/* ||b||^2 of pad columns: float bits 0x7EFFFFFF (1.7e38).  Absorbs any bias, is larger than every real
+ * value in split mode, and its exact-mode key (bits * 256) is 0xFFFFFF00 = "absent" */
+#define L2_PAD_NORM_BITS 0x7EFFFFFFu
+#define L2_EXT_BYTES 4096                  /* norm operand image per 128-column tile */
 #define L2_EXACT_NORM_LIMIT_BITS 0x4A800000u /* 2^22 as float bits: max ||.||^2 for exact mode */
 
 struct L2Cand {        // one candidate: approximate (||b||^2 - 2ab) and train index
@@ -35,10 +41,27 @@ static __device__ __forceinline__ float l2_split_shift(unsigned max_qnorm_bits)
 {
     return __uint_as_float(max_qnorm_bits) * 1.001f + 1e-30f;
 }
+// "ext" (norm step) operand layout, K-major, no swizzle: byte offset of row r's first 16 B;
+// the second K half (elements 8..15, all zero) sits 128 B further
+static __device__ __forceinline__ uint32_t ext_row_offset(int r) { return (uint32_t)((r >> 3) * 256 + (r & 7) * 16); }
+// exact three-term bf16 split of an fp32 value (24-bit mantissa = 3 x 8 bits): .x = h | m << 16, .y = l
+static __device__ __forceinline__ uint4 bf16_split3(float v)
+{
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(m);
+    const __nv_bfloat16 l = __float2bfloat16_rn(r2);
+    uint4 o;
+    o.x = (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(m) << 16);
+    o.y = (uint32_t)__bfloat16_as_ushort(l);
+    o.z = 0u; o.w = 0u;
+    return o;
+}
 #endif
 
 struct pm_ctx;
 int l2_tc_grid(pm_ctx *ctx, int MT, int NT);
 int l2_tc_smax(pm_ctx *ctx, int MT, int NT);
 int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, int nt_pad,
-                 const float *tnorm, const L2Flags *flags, L2Cand *part, int smax, float *dump);
+                 const void *text, const L2Flags *flags, L2Cand *part, int smax, float *dump);

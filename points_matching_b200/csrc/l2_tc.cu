@@ -42,27 +42,27 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int MH = 2;                        // A row-tiles (m-halves) per work item: 256 rows
-constexpr int A_BLK_BYTES = BM * BK * 2;     // 16 KB
-constexpr int B_BLK_BYTES = BN * BK * 2;     // 16 KB
-constexpr int NSTAGE = 4;
-constexpr int A_MAXBLK = 4;
+constexpr int BLK_BYTES = BM * BK * 2;       // 16 KB: one 128-row x 64-column bf16 k-block of A or B
+constexpr int EXT_BYTES = BN * 32;           // 4 KB: K=16 "ext" operand (norm step), K-major, no swizzle
+constexpr int STAGE_BYTES = 2 * BLK_BYTES + EXT_BYTES;   // a B stage: two k-blocks (K = 128) + the norm operand of the tile
+constexpr int AB_BYTES = 212992;             // A tiles + B ring: exact 64 KB + 4 x 36 KB, split 128 KB + 2 x 36 KB
 constexpr int EPI_WARP0 = 2;        // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-17 epilogue
 constexpr int EPI_WARPS = 16;       // 4 per scheduler: enough TLP to keep the issue slots busy
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int TC_THREADS = (EPI_WARP0 + EPI_WARPS) * 32;   // 576
+constexpr int ISS2_WARP = EPI_WARP0 + EPI_WARPS;           // warp 18: second MMA issuer (odd work items)
+constexpr int TC_THREADS = (ISS2_WARP + 1) * 32;           // 608
 constexpr int NSLICE = EPI_WARPS / 4 / MH;                 // column slices per accumulator: 2
 constexpr int SLICE = BN / NSLICE;                         // 64 columns per warp
 constexpr int SMEM_A = 0;
-constexpr int SMEM_B = MH * A_MAXBLK * A_BLK_BYTES;            // 131072
-constexpr int SMEM_BAR = SMEM_B + NSTAGE * B_BLK_BYTES;        // 196608
+constexpr int SMEM_BAR = AB_BYTES;
 constexpr int SMEM_SCRATCH = SMEM_BAR + 256;                   // MH x (NSLICE-1) x 128 rows x 3 candidates
 // "ext" operands of the norm MMA step, K-major, no swizzle: core matrix = 8 rows x 16 B,
-// the two 8-element K halves 128 B apart (LBO), 8-row groups 256 B apart (SBO)
-constexpr int EXT_A_BYTES = BM * 32;                           // 4 KB, constant [1 1 1 0...] rows
-constexpr int EXT_B_BYTES = BN * 32;                           // 8 KB per tile, double buffered
+// the two 8-element K halves 128 B apart (LBO), 8-row groups 256 B apart (SBO).
+//   A side (built here):  row = [1 1 1 bias_h bias_m bias_l 0 0 | 0 x 8]
+//   B side (K1, l2.cu):   row = [n_h n_m n_l 1 1 1 0 0 | 0 x 8],  n = ||b||^2 split exactly into three bf16
+// so the step adds ||b||^2 + bias to every accumulator element.
 constexpr int SMEM_EXTA = SMEM_SCRATCH + MH * (NSLICE - 1) * BM * 3 * 8;
-constexpr int SMEM_EXTB = SMEM_EXTA + EXT_A_BYTES;
-constexpr int SMEM_TOTAL = SMEM_EXTB + 2 * EXT_B_BYTES + 1024; // + alignment slack
+constexpr int SMEM_TOTAL = SMEM_EXTA + BM * 32 + 1024;         // + alignment slack
 
 // instruction descriptor: D=F32, A=B=BF16, K-major both, N=128, M=128
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
@@ -99,6 +99,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm,
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// one elected lane of a converged warp (the async-proxy instructions take warp-uniform operands:
+// issuing them from converged code lets the compiler keep descriptors in uniform registers)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar)
@@ -124,21 +137,6 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr)
 __device__ __forceinline__ uint64_t make_sdesc_ext(uint32_t saddr)
 {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ uint32_t ext_row_offset(int r) { return (uint32_t)((r >> 3) * 256 + (r & 7) * 16); }
-// exact three-term bf16 split of an fp32 value (24-bit mantissa = 3 x 8 bits)
-__device__ __forceinline__ uint4 bf16_split3(float v)
-{
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const float r1 = v - __bfloat162float(h);
-    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
-    const float r2 = r1 - __bfloat162float(m);
-    const __nv_bfloat16 l = __float2bfloat16_rn(r2);
-    uint4 o;
-    o.x = (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(m) << 16);
-    o.y = (uint32_t)__bfloat16_as_ushort(l);
-    o.z = 0u; o.w = 0u;
-    return o;
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
 {
@@ -262,15 +260,22 @@ struct Cand3 {
 };
 
 struct TcParams {
-    const float *tnorm;          // [nt_pad] ||b||^2 (pad columns: +inf)
+    const uint8_t *text;         // [NT][4 KB] norm operand images of the train column tiles (K1)
     const L2Flags *flags;
     L2Cand *part;                // [mq_pad][smax][3]; MT counts 256-row super tiles
     float *dump;                 // debug: [mq_pad][nt_pad] of (||b||^2 - 2ab), or null
     int MT, NT, smax, nt_pad;
-    long long *trace;            // PM_K2_DBG & 32: clock64 stamps of CTA 0, [tile][4]
-    uint32_t dbg;                // timing experiments only (PM_K2_DBG): 1 skip selection math, 2 skip main MMAs, 4 skip TMA of B
+    long long *trace;            // PM_K2_TRACE builds: clock64 stamps of CTA 0, [tile][16]
     uint32_t mul256;             // == 256, passed at run time so the key pack stays an IMAD (FMA pipe), not an ALU LEA
 };
+
+#ifdef PM_K2_TRACE
+#define TR(slot) do { if (P.trace && blockIdx.x == 0 && lane == 0 && lt < 64) P.trace[lt * 16 + (slot)] = clock64(); } while (0)
+#define TRE(slot) do { if (P.trace && blockIdx.x == 0 && e == 0 && lane == 0 && lt < 64) P.trace[lt * 16 + (slot)] = clock64(); } while (0)
+#else
+#define TR(slot) do { } while (0)
+#define TRE(slot) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t, TcParams P)
@@ -278,39 +283,33 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *sgen = smem_raw + (sbase - smem_u32(smem_raw));
-    const uint32_t sA = sbase + SMEM_A, sB = sbase + SMEM_B, sBar = sbase + SMEM_BAR;
-    const uint32_t bar_full = sBar, bar_empty = sBar + 8 * NSTAGE;
-    const uint32_t bar_afull = sBar + 16 * NSTAGE, bar_aempty = bar_afull + 8;
-    const uint32_t bar_tfull = bar_aempty + 8, bar_tempty = bar_tfull + 16;
-    const uint32_t bar_ext = bar_tempty + 16;                    // [2]: norm operand of a tile staged
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(sgen + SMEM_BAR + 16 * NSTAGE + 64);
-    const uint32_t sExtA = sbase + SMEM_EXTA, sExtB = sbase + SMEM_EXTB;
+    const uint32_t sA = sbase + SMEM_A, sBar = sbase + SMEM_BAR;
+    const uint32_t bar_full = sBar, bar_empty = sBar + 32;       // [4] each: B stage loaded / consumed
+    const uint32_t bar_afull = sBar + 64, bar_aempty = sBar + 72;
+    const uint32_t bar_tfull = sBar + 80, bar_tempty = sBar + 96;  // [2]: accumulator ready / drained
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(sgen + SMEM_BAR + 128);
+    const uint32_t sExtA = sbase + SMEM_EXTA;
     L2Cand *scratch = reinterpret_cast<L2Cand *>(sgen + SMEM_SCRATCH);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    pm_pdl_prologue();      // K1's outputs (flags, packed operands, norms) are complete past this point
-    const L2Flags fl = *P.flags;
-    const bool exact = l2_exact_mode(fl);
-    const int nkb = exact ? 2 : 6;
-    const int nablk = exact ? 2 : 4;
 
+    // ---- setup that does not depend on the previous kernel: overlaps its tail under PDL ----
     const long long T = (long long)P.MT * P.NT;
     const int G = gridDim.x;
     const int t_begin = (int)((T * blockIdx.x) / G), t_end = (int)((T * (blockIdx.x + 1)) / G);
-
+    const int ntiles = t_end - t_begin;
+    const int NT = P.NT;
+    const int m_first = t_begin / NT, n_first = t_begin - m_first * NT;   // the only divisions: per-role counters follow
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_q)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_t)) : "memory");
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+            for (int s = 0; s < 4; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
             mbar_init(bar_afull, 1);
-            mbar_init(bar_aempty, 1);
-            for (int a = 0; a < 2; ++a) {
-                mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, EPI_WARPS);
-                mbar_init(bar_ext + 8 * a, BN / 32);             // one arrival per staging warp
-            }
+            mbar_init(bar_aempty, 2);                       // one arrival from each MMA issuer
+            for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, EPI_WARPS); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -318,11 +317,22 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                      ::"r"(smem_u32((const void *)tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    pm_pdl_prologue();      // K1's outputs (flags, packed operands, norm images) are complete past this point
+    const L2Flags fl = *P.flags;
+    const bool exact = l2_exact_mode(fl);
+    const int nsp = exact ? 1 : 3;           // B stages (k-block pairs) per work item
+    const int nablk = exact ? 2 : 4;         // k-blocks per A row tile: hi0 hi1 (lo0 lo1)
+    const int nstage = exact ? 4 : 2;        // B ring depth
+    const uint32_t sB = sA + (uint32_t)(MH * nablk * BLK_BYTES);   // A: 64 KB (exact) / 128 KB (split)
+    const float shift = l2_split_shift(fl.max_qnorm_bits);
+    const float nb_off = exact ? L2_EXACT_BIAS : shift;            // bias folded into the norm step
+
     if (warp >= EPI_WARP0 && (int)threadIdx.x - EPI_WARP0 * 32 < BM) {
-        // constant A operand of the norm step: row r = [1 1 1 0 0 0 0 0 | 0 x 8] in bf16
+        // constant A operand of the norm step: row r = [1 1 1 bias_h bias_m bias_l 0 0 | 0 x 8] in bf16
         const int r = (int)threadIdx.x - EPI_WARP0 * 32;
+        const uint4 b3 = bf16_split3(nb_off);          // .x = h | m << 16, .y = l
         uint8_t *dst = sgen + SMEM_EXTA + ext_row_offset(r);
-        *reinterpret_cast<uint4 *>(dst) = make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(0x3F803F80u, 0x00003F80u | (b3.x << 16), (b3.x >> 16) | (b3.y << 16), 0u);
         *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(0u, 0u, 0u, 0u);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -332,80 +342,107 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0, apar = 0; int cur_m = -1;
-            for (int tile = t_begin; tile < t_end; ++tile) {
-                const int m = tile / P.NT, n = tile % P.NT;
+        // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
+        {
+            int m = m_first, n = n_first, cur_m = -1;
+            int stage = 0; uint32_t sphase = 0, apar = 0;
+            for (int lt = 0; lt < ntiles; ++lt) {
                 if (m != cur_m) {
-                    if (cur_m >= 0) { mbar_wait(bar_aempty, apar); apar ^= 1; }
-                    mbar_expect_tx(bar_afull, (uint32_t)(MH * nablk * A_BLK_BYTES));
-                    for (int h = 0; h < MH; ++h)
-                        for (int b = 0; b < nablk; ++b)
-                            tma_load_2d(sA + (h * A_MAXBLK + b) * A_BLK_BYTES, &tmap_q, bar_afull, b * BK, (m * MH + h) * BM);
+                    if (cur_m >= 0) { mbar_wait(bar_aempty, apar); apar ^= 1; }    // every MMA of the old row tile is done
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_afull, (uint32_t)(MH * nablk * BLK_BYTES));
+                        for (int h = 0; h < MH; ++h)
+                            for (int kb = 0; kb < nablk; ++kb)
+                                tma_load_2d(sA + (h * nablk + kb) * BLK_BYTES, &tmap_q, bar_afull, kb * BK, (m * MH + h) * BM);
+                    }
+                    __syncwarp();
                     cur_m = m;
                 }
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    if (P.dbg & 4u) { mbar_arrive(bar_full + 8 * stage); if (++stage == NSTAGE) { stage = 0; phase ^= 1; } continue; }
-                    mbar_expect_tx(bar_full + 8 * stage, B_BLK_BYTES);
-                    // k-blocks: hi0 hi1 | lo0 lo1 | hi0 hi1   (packed row = [hi 0..127 | lo 128..255])
-                    const int kc = ((kb == 2 || kb == 3) ? 128 : 0) + (kb & 1) * BK;
-                    tma_load_2d(sB + stage * B_BLK_BYTES, &tmap_t, bar_full + 8 * stage, kc, n * BN);
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                for (int sp = 0; sp < nsp; ++sp) {
+                    mbar_wait(bar_empty + 8 * stage, sphase ^ 1);
+                    if (elect_one()) {
+                        const uint32_t fb = bar_full + 8 * stage, dst = sB + stage * STAGE_BYTES;
+                        mbar_expect_tx(fb, sp == 0 ? STAGE_BYTES : 2 * BLK_BYTES);
+                        // stages: hi0 hi1 (+ norm image) | lo0 lo1 | hi0 hi1   (packed row = [hi 0..127 | lo 128..255])
+                        const int kc = sp == 1 ? 128 : 0;
+                        tma_load_2d(dst, &tmap_t, fb, kc, n * BN);
+                        tma_load_2d(dst + BLK_BYTES, &tmap_t, fb, kc + BK, n * BN);
+                        if (sp == 0) bulk_load_1d(dst + 2 * BLK_BYTES, P.text + (size_t)n * EXT_BYTES, EXT_BYTES, fb);
+                    }
+                    __syncwarp();
+                    if (++stage == nstage) { stage = 0; sphase ^= 1; }
                 }
+                if (++n == NT) { n = 0; ++m; }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0, apar = 0, acc = 0, acc_phase = 0; int cur_m = -1;
-#define TR(slot) do { if (P.trace && blockIdx.x == 0 && tile - t_begin < 64) P.trace[(tile - t_begin) * 16 + (slot)] = clock64(); } while (0)
-            for (int tile = t_begin; tile < t_end; ++tile) {
-                TR(0);
-                const int m = tile / P.NT;
-                if (m != cur_m) { mbar_wait(bar_afull, apar); apar ^= 1; cur_m = m; }
-                TR(1);
-                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
-                TR(2);
-                tc_fence_after();
-                TR(3);
-                const uint32_t d_tmem = tmem_base + acc * (MH * BN);     // accumulator (acc, h) at + h * BN
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(bar_full + 8 * stage, phase);
-                    tc_fence_after();
-                    if (kb == 0) TR(4); else if (kb == 1) TR(7);
-                    // A block: hi for kb 0..3 (x B hi, x B lo), lo for kb 4,5 (x B hi)
-                    const int ablk = kb < 4 ? (kb & 1) : 2 + (kb & 1);
-                    const uint64_t bdesc = make_sdesc(sB + stage * B_BLK_BYTES);
-                    if (!(P.dbg & 2u))
+    } else if (warp == 1 || warp == ISS2_WARP) {
+        // ===================== MMA issuers (whole warp converged, one elected lane issues) =====================
+        // Two issuer warps alternate work items (warp 1: even, warp 18: odd).  An mbarrier wait that follows
+        // tcgen05.commit in the same warp stalls until the committed MMAs drain; with two issuers those
+        // stalls (and the barrier round trips) of one warp hide behind the other warp's MMAs.  A pair of
+        // named barriers hands the issue order over, so MMAs still reach the tensor pipe in item order.
+        const int x = warp == 1 ? 0 : 1;
+        int m = m_first, n = n_first + x, cur_m = -1;
+        if (n >= NT) { n -= NT; ++m; }
+        const uint64_t extA = make_sdesc_ext(sExtA);
+        auto issue_stage = [&](int sp, uint32_t d_tmem, uint32_t sb) {
+            if (sp == 0) {
+                // norm step first (overwrites): acc = [1 1 1 bias..] x [split3(||b||^2) 1 1 1 ..]
+                const uint64_t extB = make_sdesc_ext(sb + 2 * BLK_BYTES);
 #pragma unroll
-                    for (int h = 0; h < MH; ++h) {      // the same B k-block feeds both A tiles
-                        const uint64_t adesc = make_sdesc(sA + (h * A_MAXBLK + ablk) * A_BLK_BYTES);
-#pragma unroll
-                        for (int k = 0; k < BK / 16; ++k)   // +32 B per K=16 step inside the swizzle span
-                            umma_bf16(d_tmem + h * BN, adesc + 2 * k, bdesc + 2 * k, IDESC, (uint32_t)((kb | k) != 0));
-                    }
-                    if (kb == 0) TR(5); else if (kb == 1) TR(8);
-                    umma_commit(bar_empty + 8 * stage);
-                    if (kb == 0) TR(6); else if (kb == 1) TR(9);
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                }
-                // norm step: acc += [1 1 1 0..] x split3(||b||^2 + bias)
-                if (!(P.dbg & 8u)) {
-                mbar_wait(bar_ext + 8 * acc, acc_phase);
-                TR(10);
-                tc_fence_after();
-#pragma unroll
-                for (int h = 0; h < MH; ++h)
-                    umma_bf16(d_tmem + h * BN, make_sdesc_ext(sExtA), make_sdesc_ext(sExtB + acc * EXT_B_BYTES), IDESC, 1u);
-                }
-                TR(11);
-                umma_commit(bar_tfull + 8 * acc);
-                TR(12);
-                if (tile + 1 < t_end && (tile + 1) / P.NT != m) umma_commit(bar_aempty);
-                acc ^= 1; if (acc == 0) acc_phase ^= 1;
+                for (int h = 0; h < MH; ++h) umma_bf16(d_tmem + h * BN, extA, extB, IDESC, 0u);
             }
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                // A block: hi for stages 0,1 (x B hi, x B lo), lo for stage 2 (x B hi)
+                const int ablk = (sp == 2 ? 2 : 0) + kk;
+                const uint64_t bdesc = make_sdesc(sb + kk * BLK_BYTES);
+#pragma unroll
+                for (int h = 0; h < MH; ++h) {      // the same B k-block feeds both A tiles
+                    const uint64_t adesc = make_sdesc(sA + (h * nablk + ablk) * BLK_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)   // +32 B per K=16 step inside the swizzle span
+                        umma_bf16(d_tmem + h * BN, adesc + 2 * k, bdesc + 2 * k, IDESC, 1u);
+                }
+            }
+        };
+        for (int lt = x; lt < ntiles; lt += 2) {
+            TR(0);
+            const uint32_t acc = (uint32_t)x, acc_phase = (uint32_t)((lt >> 1) & 1);
+            if (m != cur_m) { mbar_wait(bar_afull, (uint32_t)((m - m_first) & 1)); cur_m = m; }
+            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+            const uint32_t d_tmem = tmem_base + acc * (MH * BN);     // accumulator (acc, h) at + h * BN
+            const bool more = lt + 1 < ntiles;
+            for (int sp = 0; sp < nsp; ++sp) {
+                const int sidx = exact ? lt : 3 * lt + sp;           // running B stage index
+                const int st = exact ? (sidx & 3) : (sidx & 1);
+                mbar_wait(bar_full + 8 * st, (uint32_t)((exact ? (sidx >> 2) : (sidx >> 1)) & 1));
+                tc_fence_after();
+                if (sp == 0) {
+                    TR(1);
+                    if (lt > 0) asm volatile("bar.sync %0, 64;" ::"r"(2 + x) : "memory");   // item lt-1 has been issued
+                    TR(2);
+                }
+                if (elect_one()) issue_stage(sp, d_tmem, sB + st * STAGE_BYTES);
+                __syncwarp();
+                if (sp == nsp - 1) {
+                    TR(3);
+                    if (more) asm volatile("bar.arrive %0, 64;" ::"r"(3 - x) : "memory");
+                }
+                if (elect_one()) {
+                    umma_commit(bar_empty + 8 * st);
+                    if (sp == nsp - 1) {
+                        umma_commit(bar_tfull + 8 * acc);
+                        // the A tiles may be overwritten once the last TWO items of the row (one per issuer) are done
+                        if (n == NT - 1 && more) { umma_commit(bar_aempty); if (lt == 0) mbar_arrive(bar_aempty); }
+                        if (n == NT - 2 && lt + 2 < ntiles) umma_commit(bar_aempty);
+                    }
+                }
+                __syncwarp();
+            }
+            TR(4);
+            n += 2;
+            if (n >= NT) { n -= NT; ++m; }
         }
     } else {
         // ===================== epilogue =====================
@@ -414,40 +451,21 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         const int mh = (e >> 2) & (MH - 1);    // which A row-tile (accumulator) of the work item
         const int slice = e >> 3;              // which 64 of the item's 128 columns
         const int row = mh * BM + quarter * 32 + lane;   // row within the 256-row work item
-        const float shift = l2_split_shift(fl.max_qnorm_bits);
-        const float nb_off = exact ? L2_EXACT_BIAS : shift;            // bias folded into the norm operand
-        const float nb_pad = exact ? L2_EXACT_PAD : 3.0e38f;           // pad columns: never selected
         const uint32_t mul = P.mul256;
-        const int et = e * 32 + lane;                                  // threads 0..255 stage one column each
-        uint32_t acc = 0, acc_phase = 0; int cur_m = -1;
-        // stage_ext(buf, nb): this thread's column of the norm operand, then one arrival per warp
-        auto stage_ext = [&](uint32_t buf, float nb) {
-            const float v = nb == __int_as_float(0x7f800000) ? nb_pad : nb + nb_off;
-            const uint4 s3 = bf16_split3(v);
-            uint8_t *dst = sgen + SMEM_EXTB + buf * EXT_B_BYTES + ext_row_offset(et);
-            *reinterpret_cast<uint4 *>(dst) = s3;
-            *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(0u, 0u, 0u, 0u);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // visible to the tensor core's proxy
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_ext + 8 * buf);
-        };
-        float nb_pref = 0.f;
-        if (et < BN && t_begin < t_end) {
-            stage_ext(0u, __ldg(P.tnorm + (t_begin % P.NT) * BN + et));
-            if (t_begin + 1 < t_end) nb_pref = __ldg(P.tnorm + ((t_begin + 1) % P.NT) * BN + et);
-        }
+        int cur_m = -1;
+        int m = m_first, n = n_first;
         Sel2 s2; s2.reset();
         Sel3 s3; s3.reset();
 
-        auto flush = [&](int m) {
+        auto flush = [&](int mm) {
             Cand3 c; c.reset();
             if (exact) {
                 if ((s2.m1 >> 8) != 0xFFFFFFu) c.insert(s2.value(s2.m1), s2.i1);
                 if ((s2.m2 >> 8) != 0xFFFFFFu) c.insert(s2.value(s2.m2), s2.i2);
             } else {
-                if ((s3.m1 >> 8) != 0xFFFFFFu) c.insert(__uint_as_float(s3.m1) - shift, s3.i1);
-                if ((s3.m2 >> 8) != 0xFFFFFFu) c.insert(__uint_as_float(s3.m2) - shift, s3.i2);
-                if ((s3.m3 >> 8) != 0xFFFFFFu) c.insert(__uint_as_float(s3.m3) - shift, s3.i3);
+                if ((s3.m1 >> 8) < 0x7EFFFFu) c.insert(__uint_as_float(s3.m1) - shift, s3.i1);
+                if ((s3.m2 >> 8) < 0x7EFFFFu) c.insert(__uint_as_float(s3.m2) - shift, s3.i2);
+                if ((s3.m3 >> 8) < 0x7EFFFFu) c.insert(__uint_as_float(s3.m3) - shift, s3.i3);
             }
             if (slice > 0) {
 #pragma unroll
@@ -458,13 +476,13 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                 for (int sl = 0; sl < NSLICE - 1; ++sl)
 #pragma unroll
                     for (int k = 0; k < 3; ++k) { const L2Cand o = scratch[(sl * MH * BM + row) * 3 + k]; c.insert(o.d, o.idx); }
-                // segment slot = index of this CTA among the CTAs that touch row tile m
-                const long long first_tile = (long long)m * P.NT;
+                // segment slot = index of this CTA among the CTAs that touch row tile mm
+                const long long first_tile = (long long)mm * NT;
                 int c0 = (int)((first_tile * G) / T);
                 while ((T * (c0 + 1)) / G <= first_tile) ++c0;
                 while ((T * c0) / G > first_tile) --c0;
                 const int slot = (int)blockIdx.x - c0;
-                L2Cand *dst = P.part + ((size_t)(m * MH * BM + row) * P.smax + slot) * 3;
+                L2Cand *dst = P.part + ((size_t)(mm * MH * BM + row) * P.smax + slot) * 3;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) dst[k] = L2Cand{c.d[k], c.i[k]};
             }
@@ -472,24 +490,18 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
             s2.reset(); s3.reset();
         };
 
-        for (int tile = t_begin; tile < t_end; ++tile) {
-            const int m = tile / P.NT, n = tile % P.NT;
+        for (int lt = 0; lt < ntiles; ++lt) {
+            const uint32_t acc = (uint32_t)(lt & 1), acc_phase = (uint32_t)((lt >> 1) & 1);
             if (m != cur_m) { if (cur_m >= 0) flush(cur_m); cur_m = m; }
-            // stage the NEXT tile's norm operand (its buffer was last read by the MMA of tile-1,
-            // which this warp has already seen complete) and prefetch the one after
-            if (et < BN && tile + 1 < t_end && !(P.dbg & 8u)) {
-                stage_ext(acc ^ 1u, nb_pref);
-                if (tile + 2 < t_end) nb_pref = __ldg(P.tnorm + ((tile + 2) % P.NT) * BN + et);
-            }
+            TRE(12);
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
-            if (P.trace && blockIdx.x == 0 && e == 0 && lane == 0 && tile - t_begin < 64) P.trace[(tile - t_begin) * 16 + 13] = clock64();
+            TRE(13);
             const int col0 = n * BN + slice * SLICE;
             const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (MH * BN) + mh * BN + slice * SLICE;
 #pragma unroll 1
             for (int ch = 0; ch < SLICE / 32; ++ch) {
                 uint32_t r[32];
-                if (P.dbg & 16u) continue;
                 tmem_ld32(taddr0 + ch * 32, r);
                 tmem_ld_wait();
                 if (P.dump) {
@@ -497,7 +509,6 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
 #pragma unroll
                     for (int c = 0; c < 32; ++c) drow[c] = __uint_as_float(r[c]) - nb_off;
                 }
-                if (P.dbg & 1u) { s2.m1 ^= r[0] ^ r[31]; continue; }
                 if (exact) {
 #pragma unroll
                     for (int c = 0; c < 32; ++c) r[c] = r[c] * mul + (uint32_t)(c + 1);
@@ -511,9 +522,9 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-            if (P.trace && blockIdx.x == 0 && e == 0 && lane == 0 && tile - t_begin < 64) P.trace[(tile - t_begin) * 16 + 14] = clock64();
+            TRE(14);
             if (exact) s2.end_tile(col0); else s3.end_tile(col0);
-            acc ^= 1; if (acc == 0) acc_phase ^= 1;
+            if (++n == NT) { n = 0; ++m; }
         }
         if (cur_m >= 0) flush(cur_m);
     }
@@ -583,7 +594,7 @@ int l2_tc_smax(pm_ctx *ctx, int MT, int NT)
 }
 
 int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, int nt_pad,
-                 const float *tnorm, const L2Flags *flags, L2Cand *part, int smax, float *dump)
+                 const void *text, const L2Flags *flags, L2Cand *part, int smax, float *dump)
 {
     static bool attr_set = false;
     if (!attr_set) {
@@ -602,10 +613,9 @@ int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, 
         }
     const CUtensorMap &tq = tmaps[0], &tt = tmaps[1];
     TcParams P;
-    P.tnorm = tnorm; P.flags = flags; P.part = part; P.dump = dump;
+    P.text = (const uint8_t *)text; P.flags = flags; P.part = part; P.dump = dump;
     P.MT = mq_pad / (MH * BM); P.NT = nt_pad / BN; P.smax = smax; P.nt_pad = nt_pad; P.mul256 = 256u;
-    { const char *dv = getenv("PM_K2_DBG"); P.dbg = dv ? (uint32_t)atoi(dv) : 0u; }
-    P.trace = (P.dbg & 32u) ? g_k2_trace : nullptr;
+    P.trace = g_k2_trace;
     const int G = l2_tc_grid(ctx, P.MT, P.NT);
     {
         pm_prof_scope prof(ctx, 0);
