@@ -82,41 +82,58 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned 
 template <class Pred>
 __global__ void __launch_bounds__(FB) compact_lookback_kernel(Pred pred, int n, pm_dmatch *out, int32_t *n_out,
                                                               unsigned long long *status, unsigned *counter,
-                                                              unsigned epoch)
+                                                              unsigned epoch, int use_ticket, unsigned long long *span)
 {
     __shared__ int s_tile, s_prefix;
+    pm_span_mark(span, 12, false);
     pm_pdl_prologue();
-    if (threadIdx.x == 0) s_tile = (int)atomicAdd(&counter[epoch & 1u], 1u);
-    __syncthreads();
-    const int tile = s_tile;
+    pm_span_mark(span, 13, false);
+    int tile = (int)blockIdx.x;          // every tile of a small grid is resident: block order is safe
+    if (use_ticket) {                    // large grids: a tile may only wait on tiles that have started
+        if (threadIdx.x == 0) s_tile = (int)atomicAdd(&counter[epoch & 1u], 1u);
+        __syncthreads();
+        tile = s_tile;
+    }
     const int ntiles = (n + FB - 1) / FB;
     const int i = tile * FB + threadIdx.x;
     pm_dmatch m;
     const int f = i < n ? (int)pred(i, m) : 0;
     int total;
     const int ex = block_exclusive_scan(f, &total);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        // warp-wide decoupled look-back: 32 predecessors per round trip
+        const int lane = threadIdx.x;
         const unsigned long long tag = (unsigned long long)epoch << 34;
         int prefix = 0;
         if (tile == 0) {
-            counter[(epoch + 1u) & 1u] = 0u;
-            st_volatile_u64(&status[0], tag | (2ull << 32) | (unsigned)total);
-        } else {
-            st_volatile_u64(&status[tile], tag | (1ull << 32) | (unsigned)total);
-            for (int p = tile - 1; p >= 0;) {
-                const unsigned long long v = ld_volatile_u64(&status[p]);
-                if ((v >> 34) != (unsigned long long)epoch) continue;          // not published yet
-                prefix += (int)(unsigned)(v & 0xFFFFFFFFull);
-                if (((v >> 32) & 3ull) == 2ull) break;
-                --p;
+            if (lane == 0) {
+                if (use_ticket) counter[(epoch + 1u) & 1u] = 0u;
+                st_volatile_u64(&status[0], tag | (2ull << 32) | (unsigned)total);
             }
-            st_volatile_u64(&status[tile], tag | (2ull << 32) | (unsigned)(prefix + total));
+        } else {
+            if (lane == 0) st_volatile_u64(&status[tile], tag | (1ull << 32) | (unsigned)total);
+            for (int hi = tile - 1; hi >= 0;) {
+                const int p = hi - lane;
+                unsigned long long v = tag | (2ull << 32);                 // before tile 0: inclusive prefix 0
+                if (p >= 0) v = ld_volatile_u64(&status[p]);
+                const bool ready = (v >> 34) == (unsigned long long)epoch;
+                if (!__all_sync(0xffffffffu, ready)) continue;              // some predecessor not published yet
+                const unsigned incl = __ballot_sync(0xffffffffu, ((v >> 32) & 3ull) == 2ull);
+                const int stop = incl ? __ffs(incl) - 1 : 31;               // nearest predecessor with an inclusive prefix
+                prefix += __reduce_add_sync(0xffffffffu, lane <= stop ? (int)(unsigned)(v & 0xFFFFFFFFull) : 0);
+                if (incl) break;
+                hi -= 32;
+            }
+            if (lane == 0) st_volatile_u64(&status[tile], tag | (2ull << 32) | (unsigned)(prefix + total));
         }
-        s_prefix = prefix;
-        if (tile == ntiles - 1) *n_out = prefix + total;
+        if (lane == 0) {
+            s_prefix = prefix;
+            if (tile == ntiles - 1) *n_out = prefix + total;
+        }
     }
     __syncthreads();
     if (f) out[s_prefix + ex] = m;
+    pm_span_mark(span, 14, true);
 }
 
 template <class Pred>
@@ -141,8 +158,9 @@ int run_compact(pm_ctx *ctx, Pred pred, int n, pm_dmatch *dout, int32_t *dn_out)
         return run_compact(ctx, pred, n, dout, dn_out);
     }
     unsigned *counter = reinterpret_cast<unsigned *>(st);          // st[0]: two ticket counters
+    const int use_ticket = nb > ctx->num_sms;                      // <= 1 block per SM: all tiles resident at once
     PM_CUDA(ctx, pm_launch_pdl(compact_lookback_kernel<Pred>, dim3(nb), dim3(FB), 0, ctx->stream, pred, n, dout, dn_out, st + 1,
-                               counter, epoch));
+                               counter, epoch, use_ticket, g_pm_span));
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }

@@ -64,11 +64,13 @@ __global__ void __launch_bounds__(256)
 l2_pack_kernel(const T *__restrict__ q, int nq, int mq_pad, const T *__restrict__ t, int nt, int nt_pad, int dim,
                int vec, __nv_bfloat16 *__restrict__ qpack, __nv_bfloat16 *__restrict__ tpack,
                float *__restrict__ qnorm, uint8_t *__restrict__ text, L2Flags *flags,
-               L2Cand *__restrict__ part, int part_per_row)
+               L2Cand *__restrict__ part, int part_per_row, unsigned long long *span)
 {
     __shared__ unsigned s_max[2][8];
     __shared__ int s_nonint;
+    pm_span_mark(span, 0, false);
     pm_pdl_prologue();
+    pm_span_mark(span, 1, false);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_nonint = 0;
     unsigned mx_q = 0u, mx_t = 0u;          // running max of the norm bits (norms are >= 0: bits order like floats)
@@ -123,6 +125,7 @@ l2_pack_kernel(const T *__restrict__ q, int nq, int mq_pad, const T *__restrict_
         if (mx) atomicMax(threadIdx.x == 0 ? &flags->max_qnorm_bits : &flags->max_tnorm_bits, mx);
     }
     if (threadIdx.x == 2 && s_nonint) flags->nonexact = 1;
+    pm_span_mark(span, 2, true);
 }
 
 // order-preserving float -> uint map (handles negatives; t = ||b||^2 - 2ab can be < 0)
@@ -167,88 +170,197 @@ __device__ __forceinline__ float warp_l2sq_regs(const float (&a)[4], const T *__
 //               them is >= the third pair minimum, which certifies the top-2 (else the
 //               row goes to the exact kernel).
 // ---------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256)
-l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__restrict__ qnorm,
-                 const T *__restrict__ q, const T *__restrict__ t, int nq, int nt, int dim,
-                 L2Flags *flags, L2Flags *flags_next, int *__restrict__ flagged, int q_index_base,
-                 pm_dmatch *__restrict__ out)
+// ---- K3 works in groups of 8 lanes per query row (4 rows per warp) ----
+// group arg-min of unique 64-bit keys with two 32-bit redux.sync steps over the group's lanes
+__device__ __forceinline__ unsigned long long group_min_u64(unsigned gmask, unsigned long long k)
 {
-    pm_pdl_prologue();
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *flags_next = L2Flags{0, 0u, 0u, 0};   // the next call's block
-    if (i >= nq) return;
-    // lane-local sorted triple over this lane's strided share of the candidates, then three
-    // rounds of warp arg-min over the lane heads (keys are unique: distinct train indices)
-    unsigned long long h0 = ~0ull, h1 = ~0ull, h2 = ~0ull;
-    for (int c0 = lane; c0 < ncand; c0 += 32) {
-        const L2Cand c = part[(size_t)i * ncand + c0];
-        if (c.idx < 0 || c.idx >= nt) continue;          // absent, or a pad column
-        const unsigned long long key = ((unsigned long long)f2ord(c.d) << 32) | (unsigned)c.idx;
-        if (key < h2) {
-            if (key < h1) {
-                h2 = h1;
-                if (key < h0) { h1 = h0; h0 = key; } else h1 = key;
-            } else h2 = key;
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mh = __reduce_min_sync(gmask, hi);
+    const unsigned ml = __reduce_min_sync(gmask, hi == mh ? lo : 0xFFFFFFFFu);
+    return ((unsigned long long)mh << 32) | ml;
+}
+// A 128-wide row held by 8 lanes: lane s keeps the float4 chunks s, s+8, s+16, s+24, i.e. the elements
+// that "virtual lanes" l = s + 8e of the 32-lane re-rank order own.
+__device__ __forceinline__ void load_row8(const float *p, int sub, int dim, bool vec, float (&v)[4][4])
+{
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int l = sub + 8 * e;
+        if (vec) {
+            const float4 x = __ldg(reinterpret_cast<const float4 *>(p) + l);
+            v[e][0] = x.x; v[e][1] = x.y; v[e][2] = x.z; v[e][3] = x.w;
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[e][c] = 4 * l + c < dim ? __ldg(p + 4 * l + c) : 0.f;
         }
     }
-    unsigned long long k[3];
+}
+__device__ __forceinline__ void load_row8(const uint8_t *p, int sub, int dim, bool vec, float (&v)[4][4])
+{
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        k[r] = warp_min_u64(h0);
-        if (h0 == k[r] && h0 != ~0ull) { h0 = h1; h1 = h2; h2 = ~0ull; }
+    for (int e = 0; e < 4; ++e) {
+        const int l = sub + 8 * e;
+        if (vec) {
+            const uchar4 x = __ldg(reinterpret_cast<const uchar4 *>(p) + l);
+            v[e][0] = x.x; v[e][1] = x.y; v[e][2] = x.z; v[e][3] = x.w;
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[e][c] = 4 * l + c < dim ? (float)__ldg(p + 4 * l + c) : 0.f;
+        }
     }
-    const float na = qnorm[i];
-    const bool split = !l2_exact_mode(*flags);
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
+}
+// sum (a-b)^2 in the re-rank order: virtual-lane partials (fma chain over e = 0..3), then the xor
+// butterfly 16 | 8 (inside the lane) and 4 | 2 | 1 (across the group's lanes)
+__device__ __forceinline__ float group_l2sq(unsigned gmask, const float (&a)[4][4], const float (&b)[4][4], int sub, int dim)
+{
+    float p[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
-        if (4 * lane + e < dim) a[e] = load_elem(q, (size_t)i * dim + 4 * lane + e);
+    for (int e = 0; e < 4; ++e) {
+        p[e] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (4 * (sub + 8 * e) + c < dim) { const float d = a[e][c] - b[e][c]; p[e] = fmaf(d, d, p[e]); }
+    }
+    float r = (p[0] + p[2]) + (p[1] + p[3]);          // l ^ 16, then l ^ 8
+    r += __shfl_xor_sync(gmask, r, 4);
+    r += __shfl_xor_sync(gmask, r, 2);
+    r += __shfl_xor_sync(gmask, r, 1);
+    return r;
+}
 
-    // candidate list: pair minima (and their partners), exact FP32 distances
-    float d2[6]; int idx[6];
+template <typename T>
+__global__ void __launch_bounds__(256, 3)
+l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__restrict__ qnorm,
+                 const __nv_bfloat16 *__restrict__ qpack, const __nv_bfloat16 *__restrict__ tpack,
+                 const T *__restrict__ q, const T *__restrict__ t, int nq, int nt, int dim, int vec,
+                 L2Flags *flags, L2Flags *flags_next, int *__restrict__ flagged, int q_index_base,
+                 pm_dmatch *__restrict__ out, unsigned long long *span)
+{
+    pm_span_mark(span, 6, false);
+    pm_pdl_prologue();
+    pm_span_mark(span, 7, false);
+    const int lane = threadIdx.x & 31, sub = lane & 7;
+    const unsigned gmask = 0xFFu << (lane & 24);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *flags_next = L2Flags{0, 0u, 0u, 0};   // the next call's block
+    const int ngroups = gridDim.x * (blockDim.x >> 3);
+    const int nq_round = (nq + 3) & ~3;              // whole warps stay in the loop together (group shuffles)
+    for (int i = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); i < nq_round; i += ngroups) {
+        const bool live_row = i < nq;
+        const int ir = live_row ? i : nq - 1;
+        // every load that does not depend on the candidates goes out first
+        L2Cand c0v = L2Cand{L2_INF, -1};
+        if (sub < ncand) c0v = part[(size_t)ir * ncand + sub];
+        const float na = qnorm[ir];
+        const L2Flags fl = *flags;
+        const bool split = !l2_exact_mode(fl);
+        float a[4][4];
+        uint4 aq[2];
+        if (split) load_row8(q + (size_t)ir * dim, sub, dim, vec != 0, a);
+        else {
+            // exact mode works on the packed bf16 rows (exact there): 16 elements per lane
+            const uint4 *src = reinterpret_cast<const uint4 *>(qpack + (size_t)ir * L2_PACK_COLS);
+            aq[0] = __ldg(src + sub); aq[1] = __ldg(src + sub + 8);
+        }
+        // lane-local sorted triple over this lane's strided share of the candidates, then three
+        // rounds of group arg-min over the lane heads (keys are unique: distinct train indices)
+        unsigned long long h0 = ~0ull, h1 = ~0ull, h2 = ~0ull;
+        for (int c0 = sub; c0 < ncand; c0 += 8) {
+            const L2Cand c = c0 == sub ? c0v : part[(size_t)ir * ncand + c0];
+            if (c.idx < 0 || c.idx >= nt) continue;          // absent, or a pad column
+            const unsigned long long key = ((unsigned long long)f2ord(c.d) << 32) | (unsigned)c.idx;
+            if (key < h2) {
+                if (key < h1) {
+                    h2 = h1;
+                    if (key < h0) { h1 = h0; h0 = key; } else h1 = key;
+                } else h2 = key;
+            }
+        }
+        unsigned long long k[3];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) { d2[r] = L2_INF; idx[r] = -1; }
-    const float bound = k[2] == ~0ull ? L2_INF : ord2f((unsigned)(k[2] >> 32)) + na;   // approx d^2 of the 3rd pair minimum
-    const int npairs = split ? 3 : 2;
+        for (int r = 0; r < 3; ++r) {
+            k[r] = group_min_u64(gmask, h0);
+            if (h0 == k[r] && h0 != ~0ull) { h0 = h1; h1 = h2; h2 = ~0ull; }
+        }
+        // candidate list: pair minima (and their partners), exact FP32 distances
+        float d2[6]; int idx[6];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        if (r >= npairs || k[r] == ~0ull) continue;
-        const int j = (int)(k[r] & 0xFFFFFFFFu);
-        idx[2 * r] = j;
-        // exact mode: the GEMM value is already the exact integer; split mode: re-rank in FP32
-        d2[2 * r] = split ? warp_l2sq_regs(a, t + (size_t)j * dim, dim, lane) : ord2f((unsigned)(k[r] >> 32)) + na;
-        const int p = j ^ 1;                               // the other member of the column pair
-        if (p < nt && (split || r == 0)) {
-            idx[2 * r + 1] = p;
-            d2[2 * r + 1] = warp_l2sq_regs(a, t + (size_t)p * dim, dim, lane);
+        for (int r = 0; r < 6; ++r) { d2[r] = L2_INF; idx[r] = -1; }
+        const float bound = k[2] == ~0ull ? L2_INF : ord2f((unsigned)(k[2] >> 32)) + na;   // approx d^2 of the 3rd pair minimum
+        if (!split) {
+            // exact mode: the GEMM values are exact integers; the three other members of the best's column
+            // quad are re-computed from the packed rows (train rows are stored as -2 b: d = a + b'/2).
+            // Integer arithmetic below 2^24 in FP32 is exact in any order.
+            int j = 0;
+            if (k[0] != ~0ull) { j = (int)(k[0] & 0xFFFFFFFFu); idx[0] = j; d2[0] = ord2f((unsigned)(k[0] >> 32)) + na; }
+            if (k[1] != ~0ull) { idx[4] = (int)(k[1] & 0xFFFFFFFFu); d2[4] = ord2f((unsigned)(k[1] >> 32)) + na; }
+            uint4 bq[3][2];
+#pragma unroll
+            for (int e = 1; e <= 3; ++e) {
+                const int pj = min(j ^ e, nt - 1);
+                const uint4 *src = reinterpret_cast<const uint4 *>(tpack + (size_t)pj * L2_PACK_COLS);
+                bq[e - 1][0] = __ldg(src + sub); bq[e - 1][1] = __ldg(src + sub + 8);
+            }
+#pragma unroll
+            for (int e = 1; e <= 3; ++e) {
+                float pacc = 0.f;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const unsigned aw[4] = {aq[h].x, aq[h].y, aq[h].z, aq[h].w};
+                    const unsigned bw[4] = {bq[e - 1][h].x, bq[e - 1][h].y, bq[e - 1][h].z, bq[e - 1][h].w};
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        // two bf16 per word: low half << 16 and high half are the fp32 bit patterns
+                        const float d0 = fmaf(0.5f, __uint_as_float(bw[w] << 16), __uint_as_float(aw[w] << 16));
+                        const float d1 = fmaf(0.5f, __uint_as_float(bw[w] & 0xFFFF0000u), __uint_as_float(aw[w] & 0xFFFF0000u));
+                        pacc = fmaf(d0, d0, pacc);
+                        pacc = fmaf(d1, d1, pacc);
+                    }
+                }
+                pacc += __shfl_xor_sync(gmask, pacc, 4);
+                pacc += __shfl_xor_sync(gmask, pacc, 2);
+                pacc += __shfl_xor_sync(gmask, pacc, 1);
+                const int pj = j ^ e;
+                if (k[0] != ~0ull && pj < nt) { idx[e] = pj; d2[e] = pacc; }
+            }
+        } else {
+            // split mode: both members of the three best pairs are re-ranked in FP32
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const bool live = k[r] != ~0ull;
+                const int j = live ? (int)(k[r] & 0xFFFFFFFFu) : 0, pj = j ^ 1;
+                float b[4][4];
+                load_row8(t + (size_t)j * dim, sub, dim, vec != 0, b);
+                const float dj = group_l2sq(gmask, a, b, sub, dim);
+                load_row8(t + (size_t)(pj < nt ? pj : j) * dim, sub, dim, vec != 0, b);
+                const float dpj = group_l2sq(gmask, a, b, sub, dim);
+                if (live) { idx[2 * r] = j; d2[2 * r] = dj; if (pj < nt) { idx[2 * r + 1] = pj; d2[2 * r + 1] = dpj; } }
+            }
+        }
+        // the two smallest by (d^2, index)
+        float b0 = L2_INF, b1 = L2_INF; int j0 = -1, j1 = -1;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            if (idx[r] < 0) continue;
+            const float d = d2[r]; const int j = idx[r];
+            if (d < b0 || (d == b0 && (unsigned)j < (unsigned)j0)) { b1 = b0; j1 = j0; b0 = d; j0 = j; }
+            else if (d < b1 || (d == b1 && (unsigned)j < (unsigned)j1)) { b1 = d; j1 = j; }
+        }
+        bool certified = true;
+        if (split && k[2] != ~0ull) {
+            const float eps = L2_EPS_REL * sqrtf(na * __uint_as_float(fl.max_tnorm_bits));
+            certified = b1 < bound - eps;
+        }
+        if (live_row && sub < 2) {
+            // lanes 0 and 1 of the group write the two 16-byte DMatch records of the row
+            const int jj = sub == 0 ? j0 : j1;
+            const float dd = sub == 0 ? b0 : b1;
+            reinterpret_cast<uint4 *>(out + (size_t)i * 2)[sub] =
+                make_uint4((unsigned)(i + q_index_base), (unsigned)jj, 0u,
+                           __float_as_uint(jj < 0 ? 3.402823466e+38f : sqrtf(fmaxf(dd, 0.f))));
+            if (sub == 0 && !certified) flagged[atomicAdd(&flags->n_flagged, 1)] = i;
         }
     }
-    // the two smallest by (d^2, index)
-    float b0 = L2_INF, b1 = L2_INF; int j0 = -1, j1 = -1;
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-        if (idx[r] < 0) continue;
-        const float d = d2[r]; const int j = idx[r];
-        if (d < b0 || (d == b0 && (unsigned)j < (unsigned)j0)) { b1 = b0; j1 = j0; b0 = d; j0 = j; }
-        else if (d < b1 || (d == b1 && (unsigned)j < (unsigned)j1)) { b1 = d; j1 = j; }
-    }
-    bool certified = true;
-    if (split && k[2] != ~0ull) {
-        const float eps = L2_EPS_REL * sqrtf(na * __uint_as_float(flags->max_tnorm_bits));
-        certified = b1 < bound - eps;
-    }
-    if (lane == 0) {
-        pm_dmatch r0, r1;
-        r0.queryIdx = r1.queryIdx = i + q_index_base;
-        r0.imgIdx = r1.imgIdx = 0;
-        r0.trainIdx = j0; r0.distance = j0 < 0 ? 3.402823466e+38f : sqrtf(fmaxf(b0, 0.f));
-        r1.trainIdx = j1; r1.distance = j1 < 0 ? 3.402823466e+38f : sqrtf(fmaxf(b1, 0.f));
-        out[(size_t)i * 2] = r0;
-        out[(size_t)i * 2 + 1] = r1;
-        if (!certified) flagged[atomicAdd(&flags->n_flagged, 1)] = i;
-    }
+    pm_span_mark(span, 8, true);
 }
 
 // ---------------------------------------------------------------------------------
@@ -259,10 +371,12 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 l2_exact_kernel(const T *__restrict__ q, const T *__restrict__ t, int nq, int nt, int dim,
                 const int *__restrict__ row_list, const int *__restrict__ row_count,
-                int q_index_base, pm_dmatch *__restrict__ out)
+                int q_index_base, pm_dmatch *__restrict__ out, unsigned long long *span)
 {
     extern __shared__ float qs[];                 // [dim_pad] query row, then merge scratch
+    pm_span_mark(span, 9, false);
     pm_pdl_prologue();
+    pm_span_mark(span, 10, false);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int dim_pad = (dim + 127) / 128 * 128;
     float *md = qs + dim_pad;                     // [nwarps][2]
@@ -307,6 +421,7 @@ l2_exact_kernel(const T *__restrict__ q, const T *__restrict__ t, int nq, int nt
             out[(size_t)i * 2 + 1] = r1;
         }
     }
+    pm_span_mark(span, 11, true);
 }
 
 __global__ void l2_knn_to_colbest_kernel(const pm_dmatch *__restrict__ knn, int n, int base,
@@ -327,7 +442,7 @@ int run_exact(pm_ctx *ctx, const T *dq, const T *dt, int nq, int nt, int dim, co
     const size_t smem = (size_t)dim_pad * 4 + 8 * 4 * 4;
     const int grid = rows ? min(nq, ctx->num_sms) : min(nq, 8 * ctx->num_sms);
     PM_CUDA(ctx, pm_launch_pdl(l2_exact_kernel<T>, dim3(grid), dim3(256), smem, ctx->stream, dq, dt, nq, nt, dim, rows, count,
-                               base, dout));
+                               base, dout, g_pm_span));
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }
@@ -366,27 +481,33 @@ int pmk_l2_knn2(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int
     PM_WS(ctx, text, uint8_t *, WS_T_NORM, (size_t)(nt_pad / 128) * L2_EXT_BYTES);
     PM_WS(ctx, part, L2Cand *, WS_L2_PART, (size_t)mq_pad * smax * 3 * sizeof(L2Cand));
     PM_WS(ctx, flagged, int *, WS_L2_FLAGGED, (size_t)nq * 4);
+    const int vec_u8 = dim == L2_KDIM && (((uintptr_t)dq | (uintptr_t)dt) & 3) == 0;
+    const int vec_f32 = dim == L2_KDIM && (((uintptr_t)dq | (uintptr_t)dt) & 15) == 0;
+    // K3: one warp per row, at most one resident wave of blocks (a second wave would double its latency)
+    const int fin_blocks = min(pm_cdiv(nq, 32), 3 * ctx->num_sms);   // 8 lanes per row, 32 rows per block
     const int pack_blocks = min(pm_cdiv(mq_pad + nt_pad, 8), 8 * ctx->num_sms);
     if (is_u8) {
         const int vec = dim == L2_KDIM && (((uintptr_t)dq | (uintptr_t)dt) & 3) == 0;
         PM_CUDA(ctx, pm_launch_pdl(l2_pack_kernel<uint8_t>, dim3(pack_blocks), dim3(256), 0, ctx->stream, (const uint8_t *)dq, nq, mq_pad,
-                                   (const uint8_t *)dt, nt, nt_pad, dim, vec, qpack, tpack, qnorm, text, flags, part, smax * 3));
+                                   (const uint8_t *)dt, nt, nt_pad, dim, vec, qpack, tpack, qnorm, text, flags, part, smax * 3, g_pm_span));
     } else {
         const int vec = dim == L2_KDIM && (((uintptr_t)dq | (uintptr_t)dt) & 15) == 0;
         PM_CUDA(ctx, pm_launch_pdl(l2_pack_kernel<float>, dim3(pack_blocks), dim3(256), 0, ctx->stream, (const float *)dq, nq, mq_pad,
-                                   (const float *)dt, nt, nt_pad, dim, vec, qpack, tpack, qnorm, text, flags, part, smax * 3));
+                                   (const float *)dt, nt, nt_pad, dim, vec, qpack, tpack, qnorm, text, flags, part, smax * 3, g_pm_span));
     }
     PM_CHECK_LAUNCH(ctx);
     int st = l2_tc_launch(ctx, qpack, mq_pad, tpack, nt_pad, text, flags, part, smax, g_l2_dump);
     if (st != PM_OK) return st;
     if (is_u8)
-        PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<uint8_t>, dim3(pm_cdiv(nq, 8)), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,
-                                   (const float *)qnorm, (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, flags, flags_next, flagged,
-                                   q_index_base, dout));
+        PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<uint8_t>, dim3(fin_blocks), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,
+                                   (const float *)qnorm, (const __nv_bfloat16 *)qpack, (const __nv_bfloat16 *)tpack,
+                                   (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, vec_u8, flags, flags_next, flagged,
+                                   q_index_base, dout, g_pm_span));
     else
-        PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<float>, dim3(pm_cdiv(nq, 8)), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,
-                                   (const float *)qnorm, (const float *)dq, (const float *)dt, nq, nt, dim, flags, flags_next, flagged,
-                                   q_index_base, dout));
+        PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<float>, dim3(fin_blocks), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,
+                                   (const float *)qnorm, (const __nv_bfloat16 *)qpack, (const __nv_bfloat16 *)tpack,
+                                   (const float *)dq, (const float *)dt, nq, nt, dim, vec_f32, flags, flags_next, flagged,
+                                   q_index_base, dout, g_pm_span));
     PM_CHECK_LAUNCH(ctx);
     {   // rows K3 could not certify (split mode only; the count lives on the device)
         int s2 = is_u8 ? run_exact(ctx, (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, flagged, &flags->n_flagged, q_index_base, dout)

@@ -167,20 +167,23 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u32(a, b, c); }
 
-struct Sel2 {   // exact mode: running (best, second) pair minima
+struct Sel2 {   // exact mode: running (best, second) QUAD minima
     uint32_t m1, m2; int i1, i2;
     __device__ __forceinline__ void reset() { m1 = m2 = 0xFFFFFFFFu; i1 = i2 = -1; }
-    // 56 min/max ops per 32 elements; chb = column base of the chunk inside the slice
+    // 38 min/max ops per 32 elements (1.19 per element); chb = column base of the chunk inside the slice.
+    // Only the smallest key of each aligned group of four columns competes: the overall runner-up is either
+    // another group's minimum or one of the three other members of the winner's group, which K3 re-checks.
     __device__ __forceinline__ void chunk(uint32_t (&k)[32], uint32_t chb)
     {
-        uint32_t lo[8], hi[8];
+        uint32_t lo[4], hi[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint32_t p0 = min(k[4 * i], k[4 * i + 1]), p1 = min(k[4 * i + 2], k[4 * i + 3]);
-            lo[i] = min(p0, p1); hi[i] = max(p0, p1);
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t q0 = min(umin3(k[8 * j], k[8 * j + 1], k[8 * j + 2]), k[8 * j + 3]);
+            const uint32_t q1 = min(umin3(k[8 * j + 4], k[8 * j + 5], k[8 * j + 6]), k[8 * j + 7]);
+            lo[j] = min(q0, q1); hi[j] = max(q0, q1);
         }
 #pragma unroll
-        for (int w = 4; w >= 1; w >>= 1)
+        for (int w = 2; w >= 1; w >>= 1)
 #pragma unroll
             for (int i = 0; i < w; ++i) {
                 const uint32_t L = min(lo[i], lo[i + w]);
@@ -265,6 +268,8 @@ struct TcParams {
     L2Cand *part;                // [mq_pad][smax][3]; MT counts 256-row super tiles
     float *dump;                 // debug: [mq_pad][nt_pad] of (||b||^2 - 2ab), or null
     int MT, NT, smax, nt_pad;
+    int tq, tr;                  // work items per CTA: CTA c owns tq + (c < tr) consecutive items (T = G * tq + tr)
+    unsigned long long *span;    // debug timeline (pm_internal.h), or null
     long long *trace;            // PM_K2_TRACE builds: clock64 stamps of CTA 0, [tile][16]
     uint32_t mul256;             // == 256, passed at run time so the key pack stays an IMAD (FMA pipe), not an ALU LEA
 };
@@ -275,6 +280,11 @@ struct TcParams {
 #else
 #define TR(slot) do { } while (0)
 #define TRE(slot) do { } while (0)
+#endif
+#ifdef PM_K2_TRACE
+#define TRK(slot) do { if (P.trace && blockIdx.x == 0 && threadIdx.x == (slot >= 4 ? EPI_WARP0 * 32 : 32)) P.trace[63 * 16 + (slot)] = clock64(); } while (0)
+#else
+#define TRK(slot) do { } while (0)
 #endif
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -292,12 +302,12 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     L2Cand *scratch = reinterpret_cast<L2Cand *>(sgen + SMEM_SCRATCH);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    TRK(0);
 
     // ---- setup that does not depend on the previous kernel: overlaps its tail under PDL ----
-    const long long T = (long long)P.MT * P.NT;
-    const int G = gridDim.x;
-    const int t_begin = (int)((T * blockIdx.x) / G), t_end = (int)((T * (blockIdx.x + 1)) / G);
-    const int ntiles = t_end - t_begin;
+    const int cta = (int)blockIdx.x;
+    const int t_begin = cta * P.tq + min(cta, P.tr);
+    const int ntiles = P.tq + (cta < P.tr ? 1 : 0);
     const int NT = P.NT;
     const int m_first = t_begin / NT, n_first = t_begin - m_first * NT;   // the only divisions: per-role counters follow
     if (warp == 0 && lane == 0) {
@@ -317,7 +327,11 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                      ::"r"(smem_u32((const void *)tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    pm_pdl_prologue();      // K1's outputs (flags, packed operands, norm images) are complete past this point
+    TRK(1);
+    pm_span_mark(P.span, 3, false);
+    pm_pdl_prologue();
+    pm_span_mark(P.span, 4, false);      // K1's outputs (flags, packed operands, norm images) are complete past this point
+    TRK(2);
     const L2Flags fl = *P.flags;
     const bool exact = l2_exact_mode(fl);
     const int nsp = exact ? 1 : 3;           // B stages (k-block pairs) per work item
@@ -340,6 +354,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    TRK(3);
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
@@ -382,7 +397,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         // stalls (and the barrier round trips) of one warp hide behind the other warp's MMAs.  A pair of
         // named barriers hands the issue order over, so MMAs still reach the tensor pipe in item order.
         const int x = warp == 1 ? 0 : 1;
-        int m = m_first, n = n_first + x, cur_m = -1;
+        int m = m_first, n = n_first + x;
         if (n >= NT) { n -= NT; ++m; }
         const uint64_t extA = make_sdesc_ext(sExtA);
         auto issue_stage = [&](int sp, uint32_t d_tmem, uint32_t sb) {
@@ -406,13 +421,17 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                 }
             }
         };
+        int a_seen = 0;                      // A loads this warp has waited for (never skips a phase of bar_afull)
         for (int lt = x; lt < ntiles; lt += 2) {
             TR(0);
             const uint32_t acc = (uint32_t)x, acc_phase = (uint32_t)((lt >> 1) & 1);
-            if (m != cur_m) { mbar_wait(bar_afull, (uint32_t)((m - m_first) & 1)); cur_m = m; }
+            while (a_seen <= m - m_first) { mbar_wait(bar_afull, (uint32_t)(a_seen & 1)); ++a_seen; }
             mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
             const uint32_t d_tmem = tmem_base + acc * (MH * BN);     // accumulator (acc, h) at + h * BN
             const bool more = lt + 1 < ntiles;
+            // split mode: the B ring (2 stages) is shorter than one item (3 stages), so this warp may only look at
+            // the ring once the other issuer is done with it -- a wait two phases ahead would alias
+            if (!exact && lt > 0) asm volatile("bar.sync %0, 64;" ::"r"(2 + x) : "memory");
             for (int sp = 0; sp < nsp; ++sp) {
                 const int sidx = exact ? lt : 3 * lt + sp;           // running B stage index
                 const int st = exact ? (sidx & 3) : (sidx & 1);
@@ -420,7 +439,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                 tc_fence_after();
                 if (sp == 0) {
                     TR(1);
-                    if (lt > 0) asm volatile("bar.sync %0, 64;" ::"r"(2 + x) : "memory");   // item lt-1 has been issued
+                    if (exact && lt > 0) asm volatile("bar.sync %0, 64;" ::"r"(2 + x) : "memory");   // item lt-1 has been issued
                     TR(2);
                 }
                 if (elect_one()) issue_stage(sp, d_tmem, sB + st * STAGE_BYTES);
@@ -454,6 +473,9 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         const uint32_t mul = P.mul256;
         int cur_m = -1;
         int m = m_first, n = n_first;
+        // first CTA that owns an item of row tile m_first (inverse of the partition above)
+        const int ft = m_first * NT, big = P.tr * (P.tq + 1);
+        const int slot_first = cta - (ft < big ? ft / (P.tq + 1) : P.tr + (ft - big) / P.tq);
         Sel2 s2; s2.reset();
         Sel3 s3; s3.reset();
 
@@ -476,12 +498,9 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                 for (int sl = 0; sl < NSLICE - 1; ++sl)
 #pragma unroll
                     for (int k = 0; k < 3; ++k) { const L2Cand o = scratch[(sl * MH * BM + row) * 3 + k]; c.insert(o.d, o.idx); }
-                // segment slot = index of this CTA among the CTAs that touch row tile mm
-                const long long first_tile = (long long)mm * NT;
-                int c0 = (int)((first_tile * G) / T);
-                while ((T * (c0 + 1)) / G <= first_tile) ++c0;
-                while ((T * c0) / G > first_tile) --c0;
-                const int slot = (int)blockIdx.x - c0;
+                // segment slot = index of this CTA among the CTAs that touch row tile mm: only the
+                // CTA's first row tile can have started in an earlier CTA
+                const int slot = mm == m_first ? slot_first : 0;
                 L2Cand *dst = P.part + ((size_t)(mm * MH * BM + row) * P.smax + slot) * 3;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) dst[k] = L2Cand{c.d[k], c.i[k]};
@@ -497,6 +516,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             TRE(13);
+            if (lt == 0) TRK(4);
             const int col0 = n * BN + slice * SLICE;
             const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (MH * BN) + mh * BN + slice * SLICE;
 #pragma unroll 1
@@ -526,11 +546,15 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
             if (exact) s2.end_tile(col0); else s3.end_tile(col0);
             if (++n == NT) { n = 0; ++m; }
         }
+        TRK(5);
         if (cur_m >= 0) flush(cur_m);
+        TRK(6);
     }
 
     tc_fence_before();
     __syncthreads();
+    pm_span_mark(P.span, 5, true);
+    TRK(7);
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -574,20 +598,17 @@ int l2_tc_grid(pm_ctx *ctx, int MT, int NT)
     return (int)(T < ctx->num_sms ? T : ctx->num_sms);
 }
 
-// Max number of CTAs (segments) that can touch one row tile.
+// Max number of CTAs (segments) that can touch one row tile.  CTA c owns items
+// [c * tq + min(c, tr), ...) with tq = T / G, tr = T % G (the kernel uses the same formula).
 int l2_tc_smax(pm_ctx *ctx, int MT, int NT)
 {
-    const long long T = (long long)MT * NT;
+    const int T = MT * NT;
     const int G = l2_tc_grid(ctx, MT, NT);
+    const int tq = T / G, tr = T % G, big = tr * (tq + 1);
+    auto owner = [&](int item) { return item < big ? item / (tq + 1) : tr + (item - big) / tq; };
     int smax = 1;
     for (int m = 0; m < MT; ++m) {
-        const long long first = (long long)m * NT, last = first + NT - 1;
-        int c0 = (int)((first * G) / T);
-        while ((T * (c0 + 1)) / G <= first) ++c0;
-        while ((T * c0) / G > first) --c0;
-        int c1 = (int)((last * G) / T);
-        while ((T * (c1 + 1)) / G <= last) ++c1;
-        while ((T * c1) / G > last) --c1;
+        const int c0 = owner(m * NT), c1 = owner(m * NT + NT - 1);
         if (c1 - c0 + 1 > smax) smax = c1 - c0 + 1;
     }
     return smax;
@@ -615,8 +636,10 @@ int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, 
     TcParams P;
     P.text = (const uint8_t *)text; P.flags = flags; P.part = part; P.dump = dump;
     P.MT = mq_pad / (MH * BM); P.NT = nt_pad / BN; P.smax = smax; P.nt_pad = nt_pad; P.mul256 = 256u;
-    P.trace = g_k2_trace;
+    P.trace = g_k2_trace; P.span = g_pm_span;
+    if ((long long)P.MT * P.NT >= (1ll << 30)) return pm_fail(ctx, PM_BAD_ARG, "L2 matching: more than 2^30 work items");
     const int G = l2_tc_grid(ctx, P.MT, P.NT);
+    P.tq = (P.MT * P.NT) / G; P.tr = (P.MT * P.NT) % G;
     {
         pm_prof_scope prof(ctx, 0);
         cudaError_t le = pm_launch_pdl(l2_tc_kernel, dim3(G), dim3(TC_THREADS), (size_t)SMEM_TOTAL, ctx->stream, tq, tt, P);

@@ -9,6 +9,9 @@
 
 int pmk_ransac_pick(pm_ctx *ctx, const uint64_t *dkey, const float *dF32, int id_base, int n_models, float *dFw);
 
+unsigned long long *g_pm_span = nullptr;
+extern "C" void pm_debug_set_span(unsigned long long *p) { g_pm_span = p; }
+
 int pm_fail(pm_ctx *ctx, int status, const char *fmt, ...)
 {
     char buf[512];

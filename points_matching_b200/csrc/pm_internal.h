@@ -81,12 +81,25 @@ void *pm_ws(pm_ctx *ctx, int slot, size_t bytes);   // nullptr on failure (ctx->
     type var = (type)pm_ws(ctx, slot, bytes);                                           \
     if (!var) return PM_CUDA_ERR
 
+// Debug timeline (tools/step_timeline.py): when set, every kernel of the L2 chain records
+// span[3k+0] = min CTA entry, span[3k+1] = min time past griddepcontrol.wait, span[3k+2] = max CTA exit
+// (%globaltimer, ns).  nullptr in normal operation.
+extern unsigned long long *g_pm_span;
+
 // Programmatic dependent launch (PDL): every kernel of a chain is launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization and begins with pm_pdl_prologue():
 // it lets the NEXT kernel of the stream start launching right away (its CTAs become
 // resident and run their own prologue), then waits until the PREVIOUS kernel has fully
 // completed and flushed.  Data order is unchanged; only launch latency overlaps.
 #ifdef __CUDACC__
+__device__ __forceinline__ void pm_span_mark(unsigned long long *span, int slot, bool is_max)
+{
+    if (span && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (is_max) atomicMax(span + slot, t); else atomicMin(span + slot, t);
+    }
+}
 __device__ __forceinline__ void pm_pdl_prologue()
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
