@@ -89,7 +89,8 @@ int pm_knn2_hamming(pm_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int
 
 /* knnMatch(k=2) + Lowe ratio test in one call (the north_star flow for main.cpp:43-69):
  * knn_out (optional, [nq][2]) and the compacted good matches come back together, so the
- * kNN result never makes a host round trip between the two steps. */
+ * kNN result never makes a host round trip between the two steps.  good_out must hold nq
+ * entries; entries past *n_good are unspecified. */
 int pm_knn2_ratio_l2_f32(pm_ctx *ctx, const float *q, int nq, const float *t, int nt, int dim,
                          float ratio, pm_dmatch *knn_out, pm_dmatch *good_out, int *n_good);
 

@@ -43,6 +43,34 @@ __global__ void ham_pack_kernel(const uint8_t *__restrict__ src, int n, int byte
     dst[i] = v;
 }
 
+// Hamming distance of two W-word rows.  POPC runs on the 16-lane XU pipe, which bounds the kernel (ncu r1a:
+// XU 91.5% busy), while the 64-lane ALU pipe idles; carry-save adders (xor3 / majority = one LOP3 each)
+// fold three words into a "ones" and a "twos" word first, so 8 words cost 5 POPC + 6 LOP3 instead of 8 POPC.
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) { return a ^ b ^ c; }
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a | b)); }
+template <int W>
+__device__ __forceinline__ uint32_t ham_dist(const uint32_t (&q)[W], const uint32_t (&t)[W])
+{
+    uint32_t x[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) x[w] = q[w] ^ t[w];
+    uint32_t ones = 0, twos = 0;
+#pragma unroll
+    for (int g = 0; g + 8 <= W; g += 8) {
+        const uint32_t s1 = xor3(x[g], x[g + 1], x[g + 2]), c1 = maj3(x[g], x[g + 1], x[g + 2]);
+        const uint32_t s2 = xor3(x[g + 3], x[g + 4], x[g + 5]), c2 = maj3(x[g + 3], x[g + 4], x[g + 5]);
+        const uint32_t s3 = xor3(s1, s2, x[g + 6]), c3 = maj3(s1, s2, x[g + 6]);
+        ones += __popc(s3) + __popc(x[g + 7]);
+        twos += __popc(c1) + __popc(c2) + __popc(c3);
+    }
+    if (W % 8 == 4) {
+        constexpr int g = W - 4;
+        ones += __popc(xor3(x[g], x[g + 1], x[g + 2])) + __popc(x[g + 3]);
+        twos += __popc(maj3(x[g], x[g + 1], x[g + 2]));
+    }
+    return ones + 2u * twos;
+}
+
 // part[(chunk * nq + qi) * 2 + {0,1}] = (dist << 32 | global train index), ~0 if absent.
 template <int W>
 __global__ void __launch_bounds__(HAM_THREADS)
@@ -112,9 +140,7 @@ ham_knn2_kernel(const uint32_t *__restrict__ q, int nq, const uint32_t *__restri
             }
 #pragma unroll
             for (int r = 0; r < HAM_QPT; ++r) {
-                uint32_t d = 0;
-#pragma unroll
-                for (int w = 0; w < W; ++w) d += __popc(qr[r][w] ^ tw[w]);
+                const uint32_t d = ham_dist<W>(qr[r], tw);
                 uint32_t key = (d << 16) | (jbase + (uint32_t)j);
                 m2[r] = min(m2[r], max(m1[r], key));
                 m1[r] = min(m1[r], key);
@@ -228,8 +254,14 @@ int ham_run(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, i
 
     const bool fast = (W == 4 || W == 8 || W == 16);
     const int qblocks = fast ? pm_cdiv(nq, HAM_THREADS * HAM_QPT) : pm_cdiv(nq, 128);
-    // enough CTAs for >= ~4 waves, chunk a multiple of the tile, <= 65536 rows (16-bit local index)
-    int want = pm_cdiv(4 * ctx->num_sms, qblocks);
+    // One resident wave: as many CTAs as the GPU holds at once (occupancy x SMs), so every SM carries the
+    // same number of equal work units (4 CTAs per SM on 600 CTAs left SMs with 5 vs 4: 81% balance, ncu
+    // r1a).  Chunks are a multiple of the tile and <= 65536 rows (16-bit local index).
+    static int occ = 0;
+    if (!occ) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ham_knn2_kernel<8>, HAM_THREADS, 0) != cudaSuccess || occ < 1) occ = 4;
+    }
+    int want = max(1, (occ * ctx->num_sms) / qblocks);
     int chunks = nt > 0 ? max(1, min(want, pm_cdiv(nt, HAM_TT))) : 1;
     int chunk_rows = nt > 0 ? pm_round_up(pm_cdiv(nt, chunks), HAM_TT) : HAM_TT;
     if (chunk_rows > 65536) chunk_rows = 65536;

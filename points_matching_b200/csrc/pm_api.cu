@@ -279,11 +279,13 @@ int pm_knn2_ratio_l2_f32(pm_ctx *ctx, const float *q, int nq, const float *t, in
     int st;
     if ((st = pmk_l2_knn2(ctx, dq, nq, dt, nt, dim, 0, 0, dknn)) != PM_OK) return st;
     if ((st = pmk_ratio_filter(ctx, dknn, nq, ratio, dgood, dn)) != PM_OK) return st;
+    // one synchronisation: the count, the kNN rows and the (at most nq) survivors travel together --
+    // copying the unused tail of good_out (<= 16 B x nq) is cheaper than a second host round trip
     D2H(ctx, ctx->h_pinned, dn, 4);
     if (knn_out) D2H(ctx, knn_out, dknn, (size_t)nq * 2 * sizeof(pm_dmatch));
+    D2H(ctx, good_out, dgood, (size_t)nq * sizeof(pm_dmatch));
     PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *n_good = ctx->h_pinned[0];
-    if (*n_good) { D2H(ctx, good_out, dgood, (size_t)*n_good * sizeof(pm_dmatch)); PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); }
     return PM_OK;
 }
 
