@@ -311,6 +311,30 @@ def run_ours(args):
            "h2d_bytes_per_step": (NQ + NT) * DIM * 4, "d2h_bytes_per_step": NQ * 2 * 16 + NQ * 16 + 4,
            "api": "pm_knn2_ratio_l2_f32 (host buffers, pinned)", "steps": e_steps}
 
+    # ---- the same call with SIFT shipped as bytes (pm_knn2_l2_u8: 4x fewer PCIe bytes, identical matches) ----
+    import ctypes as C
+    from points_matching_b200 import _lib
+    hq8 = torch.from_numpy(q0.astype(np.uint8)).pin_memory()
+    ht8 = torch.from_numpy(t0.astype(np.uint8)).pin_memory()
+    L = _lib.lib()
+
+    def u8_call():
+        st = L.pm_knn2_l2_u8(ctx._h, C.c_void_p(hq8.data_ptr()), NQ, C.c_void_p(ht8.data_ptr()), NT, DIM, C.c_void_p(hknn.data_ptr()))
+        assert st == 0, st
+
+    for _ in range(3):
+        u8_call()
+    barrier()
+    ev0.record(stream)
+    for _ in range(e_steps):
+        u8_call()
+    ev1.record(stream)
+    barrier()
+    u8_ms = ev0.elapsed_time(ev1) / e_steps
+    e2e["u8_wire_format"] = {"value": world * NQ * NT / (u8_ms * 1e-3), "unit": UNIT, "ms_per_step": u8_ms,
+                             "h2d_bytes_per_step": (NQ + NT) * DIM, "d2h_bytes_per_step": NQ * 2 * 16,
+                             "api": "pm_knn2_l2_u8 (kNN-2 only, host buffers, pinned)"}
+
     # ---- secondary headline: RANSAC-F hypotheses/sec (config 4), hypotheses sharded by batch ----
     secondary = None
     if not args.no_ransac:

@@ -63,8 +63,9 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 l2_pack_kernel(const T *__restrict__ q, int nq, int mq_pad, const T *__restrict__ t, int nt, int nt_pad, int dim,
                int vec, __nv_bfloat16 *__restrict__ qpack, __nv_bfloat16 *__restrict__ tpack,
-               float *__restrict__ qnorm, uint8_t *__restrict__ text, L2Flags *flags,
-               L2Cand *__restrict__ part, int part_per_row, unsigned long long *span)
+               float *__restrict__ qnorm, uint8_t *__restrict__ text, uint8_t *__restrict__ q8, uint8_t *__restrict__ t8,
+               float *__restrict__ tnorm, L2Flags *flags,
+               L2Cand *__restrict__ part, int part_per_row, const L2Flags *tflags_in, unsigned long long *span)
 {
     __shared__ unsigned s_max[2][8];
     __shared__ int s_nonint;
@@ -100,7 +101,16 @@ l2_pack_kernel(const T *__restrict__ q, int nq, int mq_pad, const T *__restrict_
         __nv_bfloat16 *dst = (is_train ? tpack : qpack) + (size_t)row * L2_PACK_COLS;
         *reinterpret_cast<uint2 *>(dst + 4 * lane) = *reinterpret_cast<uint2 *>(hi);
         *reinterpret_cast<uint2 *>(dst + L2_KDIM + 4 * lane) = *reinterpret_cast<uint2 *>(lo);
+        {   // byte copy of the row for K3's exact-mode re-check (only meaningful when the data are 0..255 integers)
+            uchar4 b4;
+            b4.x = (unsigned char)__float2uint_rn(fminf(fmaxf(x[0], 0.f), 255.f));
+            b4.y = (unsigned char)__float2uint_rn(fminf(fmaxf(x[1], 0.f), 255.f));
+            b4.z = (unsigned char)__float2uint_rn(fminf(fmaxf(x[2], 0.f), 255.f));
+            b4.w = (unsigned char)__float2uint_rn(fminf(fmaxf(x[3], 0.f), 255.f));
+            reinterpret_cast<uchar4 *>((is_train ? t8 : q8) + (size_t)row * L2_KDIM)[lane] = b4;
+        }
         if (is_train) {
+            if (lane == 2) tnorm[row] = row < n ? s : 0.f;
             // K2's norm operand: [n_h n_m n_l 1 1 1 0 0 | 0 x 8] bf16 in the smem image of the row's column tile
             if (lane < 2) {
                 const uint4 s3 = bf16_split3(row < n ? s : __uint_as_float(L2_PAD_NORM_BITS));
@@ -125,6 +135,11 @@ l2_pack_kernel(const T *__restrict__ q, int nq, int mq_pad, const T *__restrict_
         if (mx) atomicMax(threadIdx.x == 0 ? &flags->max_qnorm_bits : &flags->max_tnorm_bits, mx);
     }
     if (threadIdx.x == 2 && s_nonint) flags->nonexact = 1;
+    // query-only launch of the chunked host path: fold in the train side's flags (packed earlier)
+    if (tflags_in && blockIdx.x == 0 && threadIdx.x == 3) {
+        if (tflags_in->nonexact) flags->nonexact = 1;
+        atomicMax(&flags->max_tnorm_bits, tflags_in->max_tnorm_bits);
+    }
     pm_span_mark(span, 2, true);
 }
 
@@ -171,13 +186,35 @@ __device__ __forceinline__ float warp_l2sq_regs(const float (&a)[4], const T *__
 //               row goes to the exact kernel).
 // ---------------------------------------------------------------------------------
 // ---- K3 works in groups of 8 lanes per query row (4 rows per warp) ----
-// group arg-min of unique 64-bit keys with two 32-bit redux.sync steps over the group's lanes
-__device__ __forceinline__ unsigned long long group_min_u64(unsigned gmask, unsigned long long k)
+// group (8 aligned lanes) minimum of 64-bit keys.  Full-mask xor butterflies stay inside the group; a
+// redux.sync with a sub-warp mask is serialised per group by the compiler (4 passes + a convergence loop).
+__device__ __forceinline__ unsigned long long group_min_u64(unsigned, unsigned long long k)
 {
-    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
-    const unsigned mh = __reduce_min_sync(gmask, hi);
-    const unsigned ml = __reduce_min_sync(gmask, hi == mh ? lo : 0xFFFFFFFFu);
-    return ((unsigned long long)mh << 32) | ml;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        const unsigned long long y = __shfl_xor_sync(0xffffffffu, k, o);
+        k = y < k ? y : k;
+    }
+    return k;
+}
+// Each of the 8 lanes of a group holds partial sums v[0..7]; returns sum over the group's lanes of v[sub]
+// (lane `sub` ends up with candidate `sub`): a transposing reduction, 4 + 2 + 1 shuffles instead of 8 x 3.
+__device__ __forceinline__ unsigned group_transpose_sum(unsigned (&v)[8], int sub)
+{
+    unsigned w[4], u[2];
+    const bool b4 = (sub & 4) != 0, b2 = (sub & 2) != 0, b1 = (sub & 1) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const unsigned keep = b4 ? v[i + 4] : v[i], send = b4 ? v[i] : v[i + 4];
+        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const unsigned keep = b2 ? w[i + 2] : w[i], send = b2 ? w[i] : w[i + 2];
+        u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    const unsigned keep = b1 ? u[1] : u[0], send = b1 ? u[0] : u[1];
+    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 // A 128-wide row held by 8 lanes: lane s keeps the float4 chunks s, s+8, s+16, s+24, i.e. the elements
 // that "virtual lanes" l = s + 8e of the 32-lane re-rank order own.
@@ -222,16 +259,24 @@ __device__ __forceinline__ float group_l2sq(unsigned gmask, const float (&a)[4][
             if (4 * (sub + 8 * e) + c < dim) { const float d = a[e][c] - b[e][c]; p[e] = fmaf(d, d, p[e]); }
     }
     float r = (p[0] + p[2]) + (p[1] + p[3]);          // l ^ 16, then l ^ 8
-    r += __shfl_xor_sync(gmask, r, 4);
-    r += __shfl_xor_sync(gmask, r, 2);
-    r += __shfl_xor_sync(gmask, r, 1);
+    r += __shfl_xor_sync(0xffffffffu, r, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
     return r;
 }
+
+__device__ __forceinline__ unsigned long long cand_key(const L2Cand c, int nt)
+{
+    const bool ok = c.idx >= 0 && c.idx < nt;                 // absent, or a pad column / pad quad
+    return ok ? (((unsigned long long)f2ord(c.d) << 32) | (unsigned)c.idx) : ~0ull;
+}
+__device__ __forceinline__ unsigned long long min_u64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+__device__ __forceinline__ unsigned long long max_u64(unsigned long long a, unsigned long long b) { return a < b ? b : a; }
 
 template <typename T>
 __global__ void __launch_bounds__(256, 3)
 l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__restrict__ qnorm,
-                 const __nv_bfloat16 *__restrict__ qpack, const __nv_bfloat16 *__restrict__ tpack,
+                 const uint8_t *__restrict__ q8, const uint8_t *__restrict__ t8, const float *__restrict__ tnorm,
                  const T *__restrict__ q, const T *__restrict__ t, int nq, int nt, int dim, int vec,
                  L2Flags *flags, L2Flags *flags_next, int *__restrict__ flagged, int q_index_base,
                  pm_dmatch *__restrict__ out, unsigned long long *span)
@@ -239,6 +284,7 @@ l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__rest
     pm_span_mark(span, 6, false);
     pm_pdl_prologue();
     pm_span_mark(span, 7, false);
+    if (span && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); span[32 + 2 * blockIdx.x] = tt; }
     const int lane = threadIdx.x & 31, sub = lane & 7;
     const unsigned gmask = 0xFFu << (lane & 24);
     if (blockIdx.x == 0 && threadIdx.x == 0) *flags_next = L2Flags{0, 0u, 0u, 0};   // the next call's block
@@ -247,83 +293,76 @@ l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__rest
     for (int i = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); i < nq_round; i += ngroups) {
         const bool live_row = i < nq;
         const int ir = live_row ? i : nq - 1;
-        // every load that does not depend on the candidates goes out first
-        L2Cand c0v = L2Cand{L2_INF, -1};
-        if (sub < ncand) c0v = part[(size_t)ir * ncand + sub];
+        // every load that does not depend on the candidates goes out first (two candidates per lane up front)
+        const L2Cand *prow = part + (size_t)ir * ncand;
+        L2Cand ca = L2Cand{L2_INF, -1}, cb = L2Cand{L2_INF, -1};
+        if (sub < ncand) ca = prow[sub];
+        if (sub + 8 < ncand) cb = prow[sub + 8];
         const float na = qnorm[ir];
         const L2Flags fl = *flags;
         const bool split = !l2_exact_mode(fl);
-        float a[4][4];
-        uint4 aq[2];
-        if (split) load_row8(q + (size_t)ir * dim, sub, dim, vec != 0, a);
-        else {
-            // exact mode works on the packed bf16 rows (exact there): 16 elements per lane
-            const uint4 *src = reinterpret_cast<const uint4 *>(qpack + (size_t)ir * L2_PACK_COLS);
-            aq[0] = __ldg(src + sub); aq[1] = __ldg(src + sub + 8);
-        }
-        // lane-local sorted triple over this lane's strided share of the candidates, then three
-        // rounds of group arg-min over the lane heads (keys are unique: distinct train indices)
-        unsigned long long h0 = ~0ull, h1 = ~0ull, h2 = ~0ull;
-        for (int c0 = sub; c0 < ncand; c0 += 8) {
-            const L2Cand c = c0 == sub ? c0v : part[(size_t)ir * ncand + c0];
-            if (c.idx < 0 || c.idx >= nt) continue;          // absent, or a pad column
-            const unsigned long long key = ((unsigned long long)f2ord(c.d) << 32) | (unsigned)c.idx;
-            if (key < h2) {
-                if (key < h1) {
-                    h2 = h1;
-                    if (key < h0) { h1 = h0; h0 = key; } else h1 = key;
-                } else h2 = key;
-            }
+        const uint4 aq = __ldg(reinterpret_cast<const uint4 *>(q8 + (size_t)ir * L2_KDIM) + sub);   // byte row, 16 per lane
+        // lane-local sorted triple (branch-free for the first two), then three rounds of group arg-min over
+        // the lane heads (keys are unique: distinct train indices)
+        const unsigned long long ka = cand_key(ca, nt), kb = cand_key(cb, nt);
+        unsigned long long h0 = min_u64(ka, kb), h1 = max_u64(ka, kb), h2 = ~0ull;
+        for (int c0 = sub + 16; c0 < ncand; c0 += 8) {       // more than 16 candidates: many CTAs share the row tile
+            const unsigned long long key = cand_key(prow[c0], nt);
+            h2 = min_u64(h2, max_u64(h1, key));
+            h1 = min_u64(max_u64(h0, key), h1);
+            h0 = min_u64(h0, key);
         }
         unsigned long long k[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             k[r] = group_min_u64(gmask, h0);
-            if (h0 == k[r] && h0 != ~0ull) { h0 = h1; h1 = h2; h2 = ~0ull; }
+            const bool pop = h0 == k[r] && h0 != ~0ull;
+            h0 = pop ? h1 : h0; h1 = pop ? h2 : h1; h2 = pop ? ~0ull : h2;
         }
-        // candidate list: pair minima (and their partners), exact FP32 distances
-        float d2[6]; int idx[6];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) { d2[r] = L2_INF; idx[r] = -1; }
-        const float bound = k[2] == ~0ull ? L2_INF : ord2f((unsigned)(k[2] >> 32)) + na;   // approx d^2 of the 3rd pair minimum
+        float b0 = L2_INF, b1 = L2_INF; int j0 = -1, j1 = -1;
+        bool certified = true;
         if (!split) {
-            // exact mode: the GEMM values are exact integers; the three other members of the best's column
-            // quad are re-computed from the packed rows (train rows are stored as -2 b: d = a + b'/2).
-            // Integer arithmetic below 2^24 in FP32 is exact in any order.
-            int j = 0;
-            if (k[0] != ~0ull) { j = (int)(k[0] & 0xFFFFFFFFu); idx[0] = j; d2[0] = ord2f((unsigned)(k[0] >> 32)) + na; }
-            if (k[1] != ~0ull) { idx[4] = (int)(k[1] & 0xFFFFFFFFu); d2[4] = ord2f((unsigned)(k[1] >> 32)) + na; }
-            uint4 bq[3][2];
+            // exact mode: K2 hands over the two best column QUADS (index = first column of the quad, value =
+            // exact minimum over its four columns).  All eight members are recomputed exactly in integers from
+            // the byte copies K1 keeps: d^2 = ||a||^2 + ||b||^2 - 2 a.b with a.b by dp4a (everything < 2^24, so
+            // the float results equal the re-rank-order distances bit for bit).
+            const int cand = sub >> 2, mem = sub & 3;                 // lane `sub` owns candidate (quad cand, member mem)
+            const bool live0 = k[0] != ~0ull, live1 = k[1] != ~0ull;
+            const int jq0 = live0 ? (int)(k[0] & 0xFFFFFFFFu) : 0, jq1 = live1 ? (int)(k[1] & 0xFFFFFFFFu) : 0;
+            const int my_col = (cand ? jq1 : jq0) + mem;
+            const float my_nb = tnorm[min(my_col, nt - 1)];
+            uint4 bq[8];
 #pragma unroll
-            for (int e = 1; e <= 3; ++e) {
-                const int pj = min(j ^ e, nt - 1);
-                const uint4 *src = reinterpret_cast<const uint4 *>(tpack + (size_t)pj * L2_PACK_COLS);
-                bq[e - 1][0] = __ldg(src + sub); bq[e - 1][1] = __ldg(src + sub + 8);
+            for (int c = 0; c < 8; ++c) {
+                const int col = (c >> 2 ? jq1 : jq0) + (c & 3);
+                bq[c] = __ldg(reinterpret_cast<const uint4 *>(t8 + (size_t)min(col, nt - 1) * L2_KDIM) + sub);
             }
+            unsigned dots[8];
 #pragma unroll
-            for (int e = 1; e <= 3; ++e) {
-                float pacc = 0.f;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const unsigned aw[4] = {aq[h].x, aq[h].y, aq[h].z, aq[h].w};
-                    const unsigned bw[4] = {bq[e - 1][h].x, bq[e - 1][h].y, bq[e - 1][h].z, bq[e - 1][h].w};
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        // two bf16 per word: low half << 16 and high half are the fp32 bit patterns
-                        const float d0 = fmaf(0.5f, __uint_as_float(bw[w] << 16), __uint_as_float(aw[w] << 16));
-                        const float d1 = fmaf(0.5f, __uint_as_float(bw[w] & 0xFFFF0000u), __uint_as_float(aw[w] & 0xFFFF0000u));
-                        pacc = fmaf(d0, d0, pacc);
-                        pacc = fmaf(d1, d1, pacc);
-                    }
-                }
-                pacc += __shfl_xor_sync(gmask, pacc, 4);
-                pacc += __shfl_xor_sync(gmask, pacc, 2);
-                pacc += __shfl_xor_sync(gmask, pacc, 1);
-                const int pj = j ^ e;
-                if (k[0] != ~0ull && pj < nt) { idx[e] = pj; d2[e] = pacc; }
+            for (int c = 0; c < 8; ++c) {
+                unsigned dot = __dp4a(aq.x, bq[c].x, 0u);
+                dot = __dp4a(aq.y, bq[c].y, dot);
+                dot = __dp4a(aq.z, bq[c].z, dot);
+                dots[c] = __dp4a(aq.w, bq[c].w, dot);
             }
+            const unsigned my_dot = group_transpose_sum(dots, sub);
+            const bool mine = (cand ? live1 : live0) && my_col < nt;
+            const float my_d = (float)((int)na + (int)my_nb - 2 * (int)my_dot);        // >= 0, exact
+            // two rounds of group arg-min over (d^2, column)
+            unsigned long long key = mine ? (((unsigned long long)__float_as_uint(my_d) << 32) | (unsigned)my_col) : ~0ull;
+            const unsigned long long w0 = group_min_u64(gmask, key);
+            key = key == w0 ? ~0ull : key;
+            const unsigned long long w1 = group_min_u64(gmask, key);
+            if (w0 != ~0ull) { j0 = (int)(w0 & 0xFFFFFFFFu); b0 = __uint_as_float((unsigned)(w0 >> 32)); }
+            if (w1 != ~0ull) { j1 = (int)(w1 & 0xFFFFFFFFu); b1 = __uint_as_float((unsigned)(w1 >> 32)); }
         } else {
-            // split mode: both members of the three best pairs are re-ranked in FP32
+            // split mode: both members of the three best pairs are re-ranked in FP32 (direct differences)
+            float a[4][4];
+            load_row8(q + (size_t)ir * dim, sub, dim, vec != 0, a);
+            float d2[6]; int idx[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { d2[r] = L2_INF; idx[r] = -1; }
+            const float bound = k[2] == ~0ull ? L2_INF : ord2f((unsigned)(k[2] >> 32)) + na;   // approx d^2 of the 3rd pair minimum
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const bool live = k[r] != ~0ull;
@@ -335,20 +374,18 @@ l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__rest
                 const float dpj = group_l2sq(gmask, a, b, sub, dim);
                 if (live) { idx[2 * r] = j; d2[2 * r] = dj; if (pj < nt) { idx[2 * r + 1] = pj; d2[2 * r + 1] = dpj; } }
             }
-        }
-        // the two smallest by (d^2, index)
-        float b0 = L2_INF, b1 = L2_INF; int j0 = -1, j1 = -1;
+            // the two smallest by (d^2, index)
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            if (idx[r] < 0) continue;
-            const float d = d2[r]; const int j = idx[r];
-            if (d < b0 || (d == b0 && (unsigned)j < (unsigned)j0)) { b1 = b0; j1 = j0; b0 = d; j0 = j; }
-            else if (d < b1 || (d == b1 && (unsigned)j < (unsigned)j1)) { b1 = d; j1 = j; }
-        }
-        bool certified = true;
-        if (split && k[2] != ~0ull) {
-            const float eps = L2_EPS_REL * sqrtf(na * __uint_as_float(fl.max_tnorm_bits));
-            certified = b1 < bound - eps;
+            for (int r = 0; r < 6; ++r) {
+                if (idx[r] < 0) continue;
+                const float d = d2[r]; const int j = idx[r];
+                if (d < b0 || (d == b0 && (unsigned)j < (unsigned)j0)) { b1 = b0; j1 = j0; b0 = d; j0 = j; }
+                else if (d < b1 || (d == b1 && (unsigned)j < (unsigned)j1)) { b1 = d; j1 = j; }
+            }
+            if (k[2] != ~0ull) {
+                const float eps = L2_EPS_REL * sqrtf(na * __uint_as_float(fl.max_tnorm_bits));
+                certified = b1 < bound - eps;
+            }
         }
         if (live_row && sub < 2) {
             // lanes 0 and 1 of the group write the two 16-byte DMatch records of the row
@@ -360,6 +397,7 @@ l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__rest
             if (sub == 0 && !certified) flagged[atomicAdd(&flags->n_flagged, 1)] = i;
         }
     }
+    if (span && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); span[33 + 2 * blockIdx.x] = tt; }
     pm_span_mark(span, 8, true);
 }
 
@@ -456,56 +494,80 @@ extern "C" void pm_debug_set_l2_dump(float *ddump) { g_l2_dump = ddump; }
 static int g_l2_force_exact = 0;
 extern "C" void pm_debug_force_exact(int on) { g_l2_force_exact = on; }
 
-int pmk_l2_knn2(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
-                int q_index_base, pm_dmatch *dout)
+// phase 0: pack query + train, K2, K3, fallback (one call).  The chunked host path (pm_api.cu) overlaps
+// the H2D copies with compute: phase 1 packs the train set only (flags -> the persistent train block),
+// phase 2 runs one query chunk against the train set packed by phase 1.
+int pmk_l2_knn2_phase(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
+                      int q_index_base, pm_dmatch *dout, int phase)
 {
-    if (nq <= 0) return PM_OK;
+    if (nq <= 0 && phase != 1) return PM_OK;
     // K2 work items are 256 query rows x 128 train columns
-    const int mq_pad = pm_round_up(nq, 256), nt_pad = pm_round_up(nt > 0 ? nt : 1, 256);
+    const int mq_pad = phase == 1 ? 0 : pm_round_up(nq, 256), nt_pad = pm_round_up(nt > 0 ? nt : 1, 256);
     const int MT = mq_pad / 256, NT = nt_pad / 128;
-    const int smax = l2_tc_smax(ctx, MT, NT);
+    const int smax = phase == 1 ? 1 : l2_tc_smax(ctx, MT, NT);
     const bool use_tc = dim <= L2_KDIM && nt > 0 && !g_l2_force_exact;
     ctx->l2_stats[2] = 0; ctx->l2_stats[3] = 0;
     if (!use_tc) {
+        if (phase == 1) return PM_OK;
         if (is_u8) return run_exact(ctx, (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, nullptr, nullptr, q_index_base, dout);
         return run_exact(ctx, (const float *)dq, (const float *)dt, nq, nt, dim, nullptr, nullptr, q_index_base, dout);
     }
     const bool fresh_flags = ctx->slot_ptr[WS_L2_FLAGS] == nullptr;
-    PM_WS(ctx, flags2, L2Flags *, WS_L2_FLAGS, 2 * sizeof(L2Flags));
-    if (fresh_flags) { PM_CUDA(ctx, cudaMemsetAsync(flags2, 0, 2 * sizeof(L2Flags), ctx->stream)); ctx->l2_parity = 0; }
-    // two flag blocks: this call uses one, K3 zeroes the other for the next call (no memset)
-    L2Flags *flags = flags2 + ctx->l2_parity, *flags_next = flags2 + (ctx->l2_parity ^ 1);
-    PM_WS(ctx, qpack, __nv_bfloat16 *, WS_Q_PACK, (size_t)mq_pad * L2_PACK_COLS * 2);
+    PM_WS(ctx, flags2, L2Flags *, WS_L2_FLAGS, 3 * sizeof(L2Flags));
+    if (fresh_flags) { PM_CUDA(ctx, cudaMemsetAsync(flags2, 0, 3 * sizeof(L2Flags), ctx->stream)); ctx->l2_parity = 0; }
+    // two flag blocks: this call uses one, K3 zeroes the other for the next call (no memset); the third
+    // block holds the train side's flags between phase 1 and the phase 2 calls
+    L2Flags *flags = flags2 + ctx->l2_parity, *flags_next = flags2 + (ctx->l2_parity ^ 1), *tflags = flags2 + 2;
     PM_WS(ctx, tpack, __nv_bfloat16 *, WS_T_PACK, (size_t)nt_pad * L2_PACK_COLS * 2);
-    PM_WS(ctx, qnorm, float *, WS_Q_NORM, (size_t)mq_pad * 4);
     PM_WS(ctx, text, uint8_t *, WS_T_NORM, (size_t)(nt_pad / 128) * L2_EXT_BYTES);
-    PM_WS(ctx, part, L2Cand *, WS_L2_PART, (size_t)mq_pad * smax * 3 * sizeof(L2Cand));
-    PM_WS(ctx, flagged, int *, WS_L2_FLAGGED, (size_t)nq * 4);
+    PM_WS(ctx, t8, uint8_t *, WS_T_U8, (size_t)nt_pad * L2_KDIM);
+    PM_WS(ctx, tnormf, float *, WS_T_NORMF, (size_t)nt_pad * 4);
     const int vec_u8 = dim == L2_KDIM && (((uintptr_t)dq | (uintptr_t)dt) & 3) == 0;
     const int vec_f32 = dim == L2_KDIM && (((uintptr_t)dq | (uintptr_t)dt) & 15) == 0;
-    // K3: one warp per row, at most one resident wave of blocks (a second wave would double its latency)
-    const int fin_blocks = min(pm_cdiv(nq, 32), 3 * ctx->num_sms);   // 8 lanes per row, 32 rows per block
-    const int pack_blocks = min(pm_cdiv(mq_pad + nt_pad, 8), 8 * ctx->num_sms);
-    if (is_u8) {
-        const int vec = dim == L2_KDIM && (((uintptr_t)dq | (uintptr_t)dt) & 3) == 0;
-        PM_CUDA(ctx, pm_launch_pdl(l2_pack_kernel<uint8_t>, dim3(pack_blocks), dim3(256), 0, ctx->stream, (const uint8_t *)dq, nq, mq_pad,
-                                   (const uint8_t *)dt, nt, nt_pad, dim, vec, qpack, tpack, qnorm, text, flags, part, smax * 3, g_pm_span));
-    } else {
-        const int vec = dim == L2_KDIM && (((uintptr_t)dq | (uintptr_t)dt) & 15) == 0;
-        PM_CUDA(ctx, pm_launch_pdl(l2_pack_kernel<float>, dim3(pack_blocks), dim3(256), 0, ctx->stream, (const float *)dq, nq, mq_pad,
-                                   (const float *)dt, nt, nt_pad, dim, vec, qpack, tpack, qnorm, text, flags, part, smax * 3, g_pm_span));
+    const int vec = is_u8 ? vec_u8 : vec_f32;
+    if (phase == 1) {
+        PM_CUDA(ctx, cudaMemsetAsync(tflags, 0, sizeof(L2Flags), ctx->stream));
+        const int blocks = min(pm_cdiv(nt_pad, 8), 8 * ctx->num_sms);
+        if (is_u8)
+            PM_CUDA(ctx, pm_launch_pdl(l2_pack_kernel<uint8_t>, dim3(blocks), dim3(256), 0, ctx->stream, (const uint8_t *)nullptr, 0, 0,
+                                       (const uint8_t *)dt, nt, nt_pad, dim, vec, (__nv_bfloat16 *)nullptr, tpack, (float *)nullptr, text,
+                                       (uint8_t *)nullptr, t8, tnormf, tflags, (L2Cand *)nullptr, 0, (const L2Flags *)nullptr, g_pm_span));
+        else
+            PM_CUDA(ctx, pm_launch_pdl(l2_pack_kernel<float>, dim3(blocks), dim3(256), 0, ctx->stream, (const float *)nullptr, 0, 0,
+                                       (const float *)dt, nt, nt_pad, dim, vec, (__nv_bfloat16 *)nullptr, tpack, (float *)nullptr, text,
+                                       (uint8_t *)nullptr, t8, tnormf, tflags, (L2Cand *)nullptr, 0, (const L2Flags *)nullptr, g_pm_span));
+        PM_CHECK_LAUNCH(ctx);
+        return PM_OK;
     }
+    PM_WS(ctx, qpack, __nv_bfloat16 *, WS_Q_PACK, (size_t)mq_pad * L2_PACK_COLS * 2);
+    PM_WS(ctx, qnorm, float *, WS_Q_NORM, (size_t)mq_pad * 4);
+    PM_WS(ctx, q8, uint8_t *, WS_Q_U8, (size_t)mq_pad * L2_KDIM);
+    PM_WS(ctx, part, L2Cand *, WS_L2_PART, (size_t)mq_pad * smax * 3 * sizeof(L2Cand));
+    PM_WS(ctx, flagged, int *, WS_L2_FLAGGED, (size_t)nq * 4);
+    // K3: 8 lanes per row, 32 rows per block, at most one resident wave (a second wave would double its latency)
+    const int fin_blocks = min(pm_cdiv(nq, 32), 3 * ctx->num_sms);
+    const int pack_nt = phase == 2 ? 0 : nt, pack_nt_pad = phase == 2 ? 0 : nt_pad;
+    const L2Flags *tflags_in = phase == 2 ? tflags : nullptr;
+    const int pack_blocks = min(pm_cdiv(mq_pad + pack_nt_pad, 8), 8 * ctx->num_sms);
+    if (is_u8)
+        PM_CUDA(ctx, pm_launch_pdl(l2_pack_kernel<uint8_t>, dim3(pack_blocks), dim3(256), 0, ctx->stream, (const uint8_t *)dq, nq, mq_pad,
+                                   (const uint8_t *)dt, pack_nt, pack_nt_pad, dim, vec, qpack, tpack, qnorm, text, q8, t8, tnormf, flags, part, smax * 3,
+                                   tflags_in, g_pm_span));
+    else
+        PM_CUDA(ctx, pm_launch_pdl(l2_pack_kernel<float>, dim3(pack_blocks), dim3(256), 0, ctx->stream, (const float *)dq, nq, mq_pad,
+                                   (const float *)dt, pack_nt, pack_nt_pad, dim, vec, qpack, tpack, qnorm, text, q8, t8, tnormf, flags, part, smax * 3,
+                                   tflags_in, g_pm_span));
     PM_CHECK_LAUNCH(ctx);
     int st = l2_tc_launch(ctx, qpack, mq_pad, tpack, nt_pad, text, flags, part, smax, g_l2_dump);
     if (st != PM_OK) return st;
     if (is_u8)
         PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<uint8_t>, dim3(fin_blocks), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,
-                                   (const float *)qnorm, (const __nv_bfloat16 *)qpack, (const __nv_bfloat16 *)tpack,
+                                   (const float *)qnorm, (const uint8_t *)q8, (const uint8_t *)t8, (const float *)tnormf,
                                    (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, vec_u8, flags, flags_next, flagged,
                                    q_index_base, dout, g_pm_span));
     else
         PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<float>, dim3(fin_blocks), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,
-                                   (const float *)qnorm, (const __nv_bfloat16 *)qpack, (const __nv_bfloat16 *)tpack,
+                                   (const float *)qnorm, (const uint8_t *)q8, (const uint8_t *)t8, (const float *)tnormf,
                                    (const float *)dq, (const float *)dt, nq, nt, dim, vec_f32, flags, flags_next, flagged,
                                    q_index_base, dout, g_pm_span));
     PM_CHECK_LAUNCH(ctx);
@@ -517,6 +579,12 @@ int pmk_l2_knn2(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int
     ctx->l2_parity ^= 1;
     ctx->l2_stats[3] = smax;
     return PM_OK;
+}
+
+int pmk_l2_knn2(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
+                int q_index_base, pm_dmatch *dout)
+{
+    return pmk_l2_knn2_phase(ctx, dq, nq, dt, nt, dim, is_u8, q_index_base, dout, 0);
 }
 
 int pm_l2_stats(pm_ctx *ctx, int32_t out[4])

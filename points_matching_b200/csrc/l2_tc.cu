@@ -170,16 +170,21 @@ __device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { 
 struct Sel2 {   // exact mode: running (best, second) QUAD minima
     uint32_t m1, m2; int i1, i2;
     __device__ __forceinline__ void reset() { m1 = m2 = 0xFFFFFFFFu; i1 = i2 = -1; }
-    // 38 min/max ops per 32 elements (1.19 per element); chb = column base of the chunk inside the slice.
-    // Only the smallest key of each aligned group of four columns competes: the overall runner-up is either
-    // another group's minimum or one of the three other members of the winner's group, which K3 re-checks.
-    __device__ __forceinline__ void chunk(uint32_t (&k)[32], uint32_t chb)
+    // In: the raw accumulator bits of 32 columns (integer-valued floats of one binade: they order like
+    // unsigned integers).  The minimum of each aligned group of four columns is taken on the raw bits
+    // (16 ops) and only then packed with its QUAD number: key = bits * 256 + (quad + 1), 8 IMADs instead
+    // of 32.  K3 recomputes the four members of the two winning quads exactly, so neither the column inside
+    // the quad nor ties inside it need to be tracked here.  38 ALU ops + 8 IMAD per 32 elements.
+    // qb = quad base of the chunk inside the slice (0 or 8).
+    __device__ __forceinline__ void chunk(const uint32_t (&k)[32], uint32_t qb, uint32_t mul)
     {
         uint32_t lo[4], hi[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t q0 = min(umin3(k[8 * j], k[8 * j + 1], k[8 * j + 2]), k[8 * j + 3]);
-            const uint32_t q1 = min(umin3(k[8 * j + 4], k[8 * j + 5], k[8 * j + 6]), k[8 * j + 7]);
+            uint32_t q0 = min(umin3(k[8 * j], k[8 * j + 1], k[8 * j + 2]), k[8 * j + 3]);
+            uint32_t q1 = min(umin3(k[8 * j + 4], k[8 * j + 5], k[8 * j + 6]), k[8 * j + 7]);
+            q0 = q0 * mul + (uint32_t)(2 * j + 1);
+            q1 = q1 * mul + (uint32_t)(2 * j + 2);
             lo[j] = min(q0, q1); hi[j] = max(q0, q1);
         }
 #pragma unroll
@@ -190,16 +195,16 @@ struct Sel2 {   // exact mode: running (best, second) QUAD minima
                 const uint32_t S = umin3(max(lo[i], lo[i + w]), hi[i], hi[i + w]);
                 lo[i] = L; hi[i] = S;
             }
-        // keys carry the column within the chunk (1..32); make it the column within the slice
-        const uint32_t L = lo[0] + chb, S = hi[0] + chb;
+        // keys carry the quad within the chunk (1..8); make it the quad within the slice (1..16)
+        const uint32_t L = lo[0] + qb, S = hi[0] + qb;
         m2 = umin3(m2, S, max(m1, L));
         m1 = min(m1, L);
     }
-    // after a tile: resolve the indices of entries that came from it, zero their column byte
+    // after a tile: resolve the quad base columns of entries that came from it, zero their low byte
     __device__ __forceinline__ void end_tile(int col0)
     {
         const uint32_t n1 = m1 & 0xFFu, n2 = m2 & 0xFFu;
-        const int g1 = col0 + (int)n1 - 1, g2 = col0 + (int)n2 - 1;
+        const int g1 = col0 + 4 * ((int)n1 - 1), g2 = col0 + 4 * ((int)n2 - 1);
         i2 = n2 ? g2 : (n1 ? i1 : i2);      // a carried second is the old best when a new best arrived
         i1 = n1 ? g1 : i1;
         m1 &= ~0xFFu; m2 &= ~0xFFu;
@@ -530,9 +535,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                     for (int c = 0; c < 32; ++c) drow[c] = __uint_as_float(r[c]) - nb_off;
                 }
                 if (exact) {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) r[c] = r[c] * mul + (uint32_t)(c + 1);
-                    s2.chunk(r, (uint32_t)(ch * 32));
+                    s2.chunk(r, (uint32_t)(ch * 8), mul);
                 } else {
 #pragma unroll
                     for (int c = 0; c < 32; ++c) r[c] = __byte_perm(r[c], (uint32_t)(c + 1), 0x3214);

@@ -79,6 +79,11 @@ int pm_destroy(pm_ctx *ctx)
             for (int i = 0; i < PM_PROF_RING; ++i)
                 for (int k = 0; k < 2; ++k) cudaEventDestroy(ctx->prof_ev[w][i][k]);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->copy_stream) {
+        cudaStreamDestroy(ctx->copy_stream);
+        cudaEventDestroy(ctx->ev_fence); cudaEventDestroy(ctx->ev_train);
+        for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev_chunk[i]);
+    }
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return PM_OK;
@@ -227,6 +232,52 @@ int pm_ransac_finish_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n,
 #define H2D(ctx, dst, src, bytes) PM_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (ctx)->stream))
 #define D2H(ctx, dst, src, bytes) PM_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (ctx)->stream))
 
+// Upload + L2 kNN-2 with the H2D copies overlapped with compute: the train set goes first and is packed
+// while the query chunks are still crossing PCIe; every query chunk is matched as soon as it lands.
+// The kNN result of row i does not depend on other query rows, so chunking changes nothing in the output.
+static int l2_upload_and_match(pm_ctx *ctx, const void *q, int nq, const void *t, int nt, int dim, size_t elem, int is_u8,
+                               uint8_t *dq, uint8_t *dt, pm_dmatch *dknn)
+{
+    const size_t row = (size_t)dim * elem;
+    int nchunks = nq / 2560;                         // >= 10 row tiles per chunk keeps K2's grid busy
+    if (nchunks > 8) nchunks = 8;
+    if (nchunks < 2 || nt == 0 || dim > 128) {       // small problem: plain upload
+        H2D(ctx, dq, q, (size_t)nq * row);
+        if (nt) H2D(ctx, dt, t, (size_t)nt * row);
+        return pmk_l2_knn2(ctx, dq, nq, dt, nt, dim, is_u8, 0, dknn);
+    }
+    if (!ctx->copy_stream) {
+        PM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        PM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fence, cudaEventDisableTiming));
+        PM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_train, cudaEventDisableTiming));
+        for (int i = 0; i < 8; ++i) PM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
+    }
+    const int chunk = pm_round_up(pm_cdiv(nq, nchunks), 256);
+    // the copy stream may not overwrite the raw buffers before earlier work on the compute stream is done
+    PM_CUDA(ctx, cudaEventRecord(ctx->ev_fence, ctx->stream));
+    PM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fence, 0));
+    PM_CUDA(ctx, cudaMemcpyAsync(dt, t, (size_t)nt * row, cudaMemcpyHostToDevice, ctx->copy_stream));
+    PM_CUDA(ctx, cudaEventRecord(ctx->ev_train, ctx->copy_stream));
+    int nc = 0;
+    for (int lo = 0; lo < nq; lo += chunk, ++nc) {
+        const int rows = nq - lo < chunk ? nq - lo : chunk;
+        PM_CUDA(ctx, cudaMemcpyAsync(dq + (size_t)lo * row, (const uint8_t *)q + (size_t)lo * row, (size_t)rows * row,
+                                     cudaMemcpyHostToDevice, ctx->copy_stream));
+        PM_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[nc], ctx->copy_stream));
+    }
+    PM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_train, 0));
+    int st = pmk_l2_knn2_phase(ctx, nullptr, 0, dt, nt, dim, is_u8, 0, nullptr, 1);
+    if (st != PM_OK) return st;
+    nc = 0;
+    for (int lo = 0; lo < nq; lo += chunk, ++nc) {
+        const int rows = nq - lo < chunk ? nq - lo : chunk;
+        PM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[nc], 0));
+        st = pmk_l2_knn2_phase(ctx, dq + (size_t)lo * row, rows, dt, nt, dim, is_u8, lo, dknn + (size_t)lo * 2, 2);
+        if (st != PM_OK) return st;
+    }
+    return PM_OK;
+}
+
 static int knn2_host(pm_ctx *ctx, const void *q, int nq, const void *t, int nt, int width, size_t elem, int kind,
                      pm_dmatch *out)
 {
@@ -240,12 +291,13 @@ static int knn2_host(pm_ctx *ctx, const void *q, int nq, const void *t, int nt, 
     PM_WS(ctx, dq, uint8_t *, WS_Q_RAW, qb);
     PM_WS(ctx, dt, uint8_t *, WS_T_RAW, tb);
     PM_WS(ctx, dout, pm_dmatch *, WS_OUT, (size_t)nq * 2 * sizeof(pm_dmatch));
-    H2D(ctx, dq, q, qb);
-    if (tb) H2D(ctx, dt, t, tb);
     int st;
-    if (kind == 0) st = pmk_l2_knn2(ctx, dq, nq, dt, nt, width, 0, 0, dout);
-    else if (kind == 1) st = pmk_l2_knn2(ctx, dq, nq, dt, nt, width, 1, 0, dout);
-    else st = pmk_hamming_knn2(ctx, dq, nq, dt, nt, width, 0, dout);
+    if (kind == 0 || kind == 1) st = l2_upload_and_match(ctx, q, nq, t, nt, width, elem, kind, dq, dt, dout);
+    else {
+        H2D(ctx, dq, q, qb);
+        if (tb) H2D(ctx, dt, t, tb);
+        st = pmk_hamming_knn2(ctx, dq, nq, dt, nt, width, 0, dout);
+    }
     if (st != PM_OK) return st;
     D2H(ctx, out, dout, (size_t)nq * 2 * sizeof(pm_dmatch));
     PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -274,10 +326,8 @@ int pm_knn2_ratio_l2_f32(pm_ctx *ctx, const float *q, int nq, const float *t, in
     PM_WS(ctx, dknn, pm_dmatch *, WS_OUT, (size_t)nq * 2 * sizeof(pm_dmatch));
     PM_WS(ctx, dgood, pm_dmatch *, WS_OUT2, (size_t)nq * sizeof(pm_dmatch));
     PM_WS(ctx, dn, int32_t *, WS_KEY, 64);
-    H2D(ctx, dq, q, qb);
-    if (tb) H2D(ctx, dt, t, tb);
     int st;
-    if ((st = pmk_l2_knn2(ctx, dq, nq, dt, nt, dim, 0, 0, dknn)) != PM_OK) return st;
+    if ((st = l2_upload_and_match(ctx, q, nq, t, nt, dim, 4, 0, (uint8_t *)dq, (uint8_t *)dt, dknn)) != PM_OK) return st;
     if ((st = pmk_ratio_filter(ctx, dknn, nq, ratio, dgood, dn)) != PM_OK) return st;
     // one synchronisation: the count, the kNN rows and the (at most nq) survivors travel together --
     // copying the unused tail of good_out (<= 16 B x nq) is cheaper than a second host round trip

@@ -8,7 +8,7 @@
 
 #include "../../include/pm.h"
 
-#define PM_NSLOTS 32
+#define PM_NSLOTS 40
 #define PM_PROF_RING 4096
 
 // Workspace slots (one growable device buffer each).
@@ -17,7 +17,8 @@ enum pm_slot {
     WS_Q_PACK, WS_T_PACK, WS_Q_NORM, WS_T_NORM, WS_L2_PART, WS_L2_FLAGS, WS_L2_FLAGGED,
     WS_HAM_Q, WS_HAM_T, WS_HAM_PART, WS_COLBEST,
     WS_P1, WS_P2, WS_SAMPLES, WS_F32, WS_COUNTS, WS_KEY, WS_MASK, WS_FOUT, WS_REFIT, WS_MISC,
-    WS_KNN, WS_KNN2, WS_IDX, WS_KP, WS_LINES
+    WS_KNN, WS_KNN2, WS_IDX, WS_KP, WS_LINES,
+    WS_Q_U8, WS_T_U8, WS_T_NORMF
 };
 
 struct pm_ctx {
@@ -38,6 +39,9 @@ struct pm_ctx {
     const void *tmap_base[2] = {nullptr, nullptr};
     int tmap_rows[2] = {0, 0};
     int32_t *h_pinned = nullptr;   // 4 KB pinned scratch for small D2H reads
+    // chunked host path (pm_api.cu): uploads run on their own stream, one event per query chunk
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_fence = nullptr, ev_train = nullptr, ev_chunk[8] = {};
     // optional device-side kernel timing (pm_profile_*): ring of event pairs per kernel class
     bool profile = false;
     cudaEvent_t prof_ev[3][PM_PROF_RING][2] = {};
@@ -141,6 +145,8 @@ int pmk_gather_matches(pm_ctx *ctx, const pm_dmatch *dm, const int32_t *dn, int 
 // l2.cu / l2_tc.cu
 int pmk_l2_knn2(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
                 int q_index_base, pm_dmatch *dout);
+int pmk_l2_knn2_phase(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
+                      int q_index_base, pm_dmatch *dout, int phase);
 int pmk_l2_col_best(pm_ctx *ctx, const float *dq, int nq, const float *dt, int nt, int dim,
                     int q_index_base, uint64_t *dcol_best);
 // ransac.cu

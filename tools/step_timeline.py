@@ -20,11 +20,11 @@ def step():
 for _ in range(200):
     step()
 torch.cuda.synchronize()
-span = torch.zeros(15, dtype=torch.int64, device="cuda")
+span = torch.zeros(15 + 17 + 2 * 1024, dtype=torch.int64, device="cuda")
 names = ["K1 pack", "K2 gemm", "K3 finish", "exact", "K5 filter"]
 rows = []
 for rep in range(5):
-    init = np.zeros(15, dtype=np.int64)
+    init = np.zeros(15 + 17 + 2 * 1024, dtype=np.int64)
     init[[0, 1, 3, 4, 6, 7, 9, 10, 12, 13]] = np.iinfo(np.int64).max
     span.copy_(torch.from_numpy(init)); torch.cuda.synchronize()
     _lib.lib().pm_debug_set_span(C.c_void_p(span.data_ptr()))
@@ -43,6 +43,11 @@ for rep in range(5):
         step()
     torch.cuda.synchronize()
     rows.append(span.cpu().numpy().copy())
+r = rows[-1]
+blk = r[32:32 + 2 * 313].reshape(-1, 2)
+st, en = (blk[:, 0] - r[7]) / 1e3, (blk[:, 1] - r[7]) / 1e3
+print("K3 per-block (us after the first block passed the wait): start min/med/max %.2f %.2f %.2f  end min/med/max %.2f %.2f %.2f  dur med %.2f max %.2f"
+      % (st.min(), np.median(st), st.max(), en.min(), np.median(en), en.max(), np.median(en - st), (en - st).max()))
 for r in rows:
     t0 = r[0]
     print(" | ".join(f"{n}: in {(r[3*k]-t0)/1e3:6.2f} dep {(r[3*k+1]-t0)/1e3:6.2f} out {(r[3*k+2]-t0)/1e3:6.2f}" for k, n in enumerate(names)), " (us)")
