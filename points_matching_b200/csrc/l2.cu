@@ -77,12 +77,27 @@ l2_pack_kernel(const T *__restrict__ q, int nq, int mq_pad, const T *__restrict_
     unsigned mx_q = 0u, mx_t = 0u;          // running max of the norm bits (norms are >= 0: bits order like floats)
     bool integral = true;
     const int total = mq_pad + nt_pad, stride = gridDim.x * (blockDim.x >> 5);
-    for (int grow = blockIdx.x * (blockDim.x >> 5) + warp; grow < total; grow += stride) {
+    constexpr int RU = 3;                    // rows per warp in flight: all loads of a pass are issued before any is used
+    for (int g0 = blockIdx.x * (blockDim.x >> 5) + warp; g0 < total; g0 += RU * stride) {
+        float xs[RU][4];
+#pragma unroll
+        for (int r = 0; r < RU; ++r) {
+            const int grow = g0 + r * stride;
+            xs[r][0] = xs[r][1] = xs[r][2] = xs[r][3] = 0.f;
+            if (grow < total) {
+                const bool is_train = grow >= mq_pad;
+                const int row = is_train ? grow - mq_pad : grow;
+                if (row < (is_train ? nt : nq)) load_row4((is_train ? t : q) + (size_t)row * dim, lane, dim, vec != 0, xs[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RU; ++r) {
+        const int grow = g0 + r * stride;
+        if (grow >= total) break;
         const bool is_train = grow >= mq_pad;
         const int row = is_train ? grow - mq_pad : grow;
         const int n = is_train ? nt : nq;
-        float x[4] = {0.f, 0.f, 0.f, 0.f};
-        if (row < n) load_row4((is_train ? t : q) + (size_t)row * dim, lane, dim, vec != 0, x);
+        const float (&x)[4] = xs[r];
         float s = 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -123,6 +138,7 @@ l2_pack_kernel(const T *__restrict__ q, int nq, int mq_pad, const T *__restrict_
             if (lane == 0) qnorm[row] = row < n ? s : 0.f;
             if (row < n) mx_q = max(mx_q, __float_as_uint(s));
             for (int k = lane; k < part_per_row; k += 32) part[(size_t)row * part_per_row + k] = L2Cand{L2_INF, -1};
+        }
         }
     }
     // one atomic per block and side (same-address traffic serialises in L2)
@@ -185,6 +201,52 @@ __device__ __forceinline__ float warp_l2sq_regs(const float (&a)[4], const T *__
 //               them is >= the third pair minimum, which certifies the top-2 (else the
 //               row goes to the exact kernel).
 // ---------------------------------------------------------------------------------
+// Exact FP32 kNN-2 of ONE query row by a whole CTA (256 threads): warps stride over the train rows,
+// lexicographic (d^2, index) top-2.  qs[dim_pad], md[16], mi[16] are shared-memory scratch.
+template <typename T>
+__device__ void l2_exact_row(const T *__restrict__ q, const T *__restrict__ t, int nt, int dim, int i,
+                             int q_index_base, pm_dmatch *__restrict__ out, float *qs, float *md, int *mi)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int dim_pad = (dim + 127) / 128 * 128;
+    __syncthreads();
+    for (int k = threadIdx.x; k < dim_pad; k += blockDim.x) qs[k] = k < dim ? load_elem(q, (size_t)i * dim + k) : 0.f;
+    __syncthreads();
+    float b0 = L2_INF, b1 = L2_INF; int i0 = -1, i1 = -1;
+    for (int j = warp; j < nt; j += nwarps) {
+        const T *b = t + (size_t)j * dim;
+        float p = 0.f;
+        for (int c = 0; c < dim_pad; c += 128) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int kk = c + 4 * lane + e;
+                if (kk < dim) { const float d = qs[kk] - load_elem(b, kk); p = fmaf(d, d, p); }
+            }
+        }
+        p = warp_sum_butterfly(p);
+        if (p < b0) { b1 = b0; i1 = i0; b0 = p; i0 = j; }      // j ascending within a warp
+        else if (p < b1) { b1 = p; i1 = j; }
+    }
+    if (lane == 0) { md[2 * warp] = b0; md[2 * warp + 1] = b1; mi[2 * warp] = i0; mi[2 * warp + 1] = i1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float d0 = L2_INF, d1 = L2_INF; int j0 = -1, j1 = -1;
+        for (int w = 0; w < 2 * nwarps; ++w) {
+            const float d = md[w]; const int j = mi[w];
+            if (j < 0) continue;
+            if (d < d0 || (d == d0 && (unsigned)j < (unsigned)j0)) { d1 = d0; j1 = j0; d0 = d; j0 = j; }
+            else if (d < d1 || (d == d1 && (unsigned)j < (unsigned)j1)) { d1 = d; j1 = j; }
+        }
+        pm_dmatch r0, r1;
+        r0.queryIdx = r1.queryIdx = i + q_index_base;
+        r0.imgIdx = r1.imgIdx = 0;
+        r0.trainIdx = j0; r0.distance = j0 < 0 ? 3.402823466e+38f : sqrtf(d0);
+        r1.trainIdx = j1; r1.distance = j1 < 0 ? 3.402823466e+38f : sqrtf(d1);
+        out[(size_t)i * 2] = r0;
+        out[(size_t)i * 2 + 1] = r1;
+    }
+}
+
 // ---- K3 works in groups of 8 lanes per query row (4 rows per warp) ----
 // group (8 aligned lanes) minimum of 64-bit keys.  Full-mask xor butterflies stay inside the group; a
 // redux.sync with a sub-warp mask is serialised per group by the compiler (4 passes + a convergence loop).
@@ -287,7 +349,7 @@ l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__rest
     if (span && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); span[32 + 2 * blockIdx.x] = tt; }
     const int lane = threadIdx.x & 31, sub = lane & 7;
     const unsigned gmask = 0xFFu << (lane & 24);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *flags_next = L2Flags{0, 0u, 0u, 0};   // the next call's block
+    if (blockIdx.x == 0 && threadIdx.x == 0) *flags_next = L2Flags{0, 0u, 0u, 0, 0u, {0, 0, 0}};   // the next call's block
     const int ngroups = gridDim.x * (blockDim.x >> 3);
     const int nq_round = (nq + 3) & ~3;              // whole warps stay in the loop together (group shuffles)
     for (int i = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); i < nq_round; i += ngroups) {
@@ -397,6 +459,25 @@ l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__rest
             if (sub == 0 && !certified) flagged[atomicAdd(&flags->n_flagged, 1)] = i;
         }
     }
+    // Split mode only: rows K3 could not certify get the exact scan, spread over the whole grid.  Every
+    // block of K3 is resident (the host launches at most one wave), so an atomic-counter grid barrier is safe;
+    // exact mode never flags a row and skips all of this.
+    if (!l2_exact_mode(*flags)) {
+        __shared__ float x_qs[128];
+        __shared__ float x_md[16];
+        __shared__ int x_mi[16];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(&flags->done_blocks, 1u);
+            while (*reinterpret_cast<volatile unsigned *>(&flags->done_blocks) < gridDim.x) { }
+            __threadfence();
+        }
+        __syncthreads();
+        const int nf = *reinterpret_cast<volatile int *>(&flags->n_flagged);
+        for (int r = blockIdx.x; r < nf; r += gridDim.x)
+            l2_exact_row(q, t, nt, dim, *reinterpret_cast<volatile int *>(&flagged[r]), q_index_base, out, x_qs, x_md, x_mi);
+    }
     if (span && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); span[33 + 2 * blockIdx.x] = tt; }
     pm_span_mark(span, 8, true);
 }
@@ -408,57 +489,16 @@ l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__rest
 template <typename T>
 __global__ void __launch_bounds__(256)
 l2_exact_kernel(const T *__restrict__ q, const T *__restrict__ t, int nq, int nt, int dim,
-                const int *__restrict__ row_list, const int *__restrict__ row_count,
                 int q_index_base, pm_dmatch *__restrict__ out, unsigned long long *span)
 {
     extern __shared__ float qs[];                 // [dim_pad] query row, then merge scratch
     pm_span_mark(span, 9, false);
     pm_pdl_prologue();
     pm_span_mark(span, 10, false);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int dim_pad = (dim + 127) / 128 * 128;
     float *md = qs + dim_pad;                     // [nwarps][2]
-    int *mi = reinterpret_cast<int *>(md + 2 * nwarps);
-    const int nrows = row_list ? *row_count : nq;
-    for (int r = blockIdx.x; r < nrows; r += gridDim.x) {
-        const int i = row_list ? row_list[r] : r;
-        __syncthreads();
-        for (int k = threadIdx.x; k < dim_pad; k += blockDim.x) qs[k] = k < dim ? load_elem(q, (size_t)i * dim + k) : 0.f;
-        __syncthreads();
-        float b0 = L2_INF, b1 = L2_INF; int i0 = -1, i1 = -1;
-        for (int j = warp; j < nt; j += nwarps) {
-            const T *b = t + (size_t)j * dim;
-            float p = 0.f;
-            for (int c = 0; c < dim_pad; c += 128) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int kk = c + 4 * lane + e;
-                    if (kk < dim) { const float d = qs[kk] - load_elem(b, kk); p = fmaf(d, d, p); }
-                }
-            }
-            p = warp_sum_butterfly(p);
-            if (p < b0) { b1 = b0; i1 = i0; b0 = p; i0 = j; }      // j ascending within a warp
-            else if (p < b1) { b1 = p; i1 = j; }
-        }
-        if (lane == 0) { md[2 * warp] = b0; md[2 * warp + 1] = b1; mi[2 * warp] = i0; mi[2 * warp + 1] = i1; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float d0 = L2_INF, d1 = L2_INF; int j0 = -1, j1 = -1;
-            for (int w = 0; w < 2 * nwarps; ++w) {
-                const float d = md[w]; const int j = mi[w];
-                if (j < 0) continue;
-                if (d < d0 || (d == d0 && (unsigned)j < (unsigned)j0)) { d1 = d0; j1 = j0; d0 = d; j0 = j; }
-                else if (d < d1 || (d == d1 && (unsigned)j < (unsigned)j1)) { d1 = d; j1 = j; }
-            }
-            pm_dmatch r0, r1;
-            r0.queryIdx = r1.queryIdx = i + q_index_base;
-            r0.imgIdx = r1.imgIdx = 0;
-            r0.trainIdx = j0; r0.distance = j0 < 0 ? 3.402823466e+38f : sqrtf(d0);
-            r1.trainIdx = j1; r1.distance = j1 < 0 ? 3.402823466e+38f : sqrtf(d1);
-            out[(size_t)i * 2] = r0;
-            out[(size_t)i * 2 + 1] = r1;
-        }
-    }
+    int *mi = reinterpret_cast<int *>(md + 2 * (blockDim.x >> 5));
+    for (int r = blockIdx.x; r < nq; r += gridDim.x) l2_exact_row(q, t, nt, dim, r, q_index_base, out, qs, md, mi);
     pm_span_mark(span, 11, true);
 }
 
@@ -473,13 +513,12 @@ __global__ void l2_knn_to_colbest_kernel(const pm_dmatch *__restrict__ knn, int 
 }
 
 template <typename T>
-int run_exact(pm_ctx *ctx, const T *dq, const T *dt, int nq, int nt, int dim, const int *rows, const int *count,
-              int base, pm_dmatch *dout)
+int run_exact(pm_ctx *ctx, const T *dq, const T *dt, int nq, int nt, int dim, int base, pm_dmatch *dout)
 {
     const int dim_pad = (dim + 127) / 128 * 128;
     const size_t smem = (size_t)dim_pad * 4 + 8 * 4 * 4;
-    const int grid = rows ? min(nq, ctx->num_sms) : min(nq, 8 * ctx->num_sms);
-    PM_CUDA(ctx, pm_launch_pdl(l2_exact_kernel<T>, dim3(grid), dim3(256), smem, ctx->stream, dq, dt, nq, nt, dim, rows, count,
+    const int grid = min(nq, 8 * ctx->num_sms);
+    PM_CUDA(ctx, pm_launch_pdl(l2_exact_kernel<T>, dim3(grid), dim3(256), smem, ctx->stream, dq, dt, nq, nt, dim,
                                base, dout, g_pm_span));
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
@@ -509,8 +548,8 @@ int pmk_l2_knn2_phase(pm_ctx *ctx, const void *dq, int nq, const void *dt, int n
     ctx->l2_stats[2] = 0; ctx->l2_stats[3] = 0;
     if (!use_tc) {
         if (phase == 1) return PM_OK;
-        if (is_u8) return run_exact(ctx, (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, nullptr, nullptr, q_index_base, dout);
-        return run_exact(ctx, (const float *)dq, (const float *)dt, nq, nt, dim, nullptr, nullptr, q_index_base, dout);
+        if (is_u8) return run_exact(ctx, (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, q_index_base, dout);
+        return run_exact(ctx, (const float *)dq, (const float *)dt, nq, nt, dim, q_index_base, dout);
     }
     const bool fresh_flags = ctx->slot_ptr[WS_L2_FLAGS] == nullptr;
     PM_WS(ctx, flags2, L2Flags *, WS_L2_FLAGS, 3 * sizeof(L2Flags));
@@ -571,11 +610,6 @@ int pmk_l2_knn2_phase(pm_ctx *ctx, const void *dq, int nq, const void *dt, int n
                                    (const float *)dq, (const float *)dt, nq, nt, dim, vec_f32, flags, flags_next, flagged,
                                    q_index_base, dout, g_pm_span));
     PM_CHECK_LAUNCH(ctx);
-    {   // rows K3 could not certify (split mode only; the count lives on the device)
-        int s2 = is_u8 ? run_exact(ctx, (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, flagged, &flags->n_flagged, q_index_base, dout)
-                       : run_exact(ctx, (const float *)dq, (const float *)dt, nq, nt, dim, flagged, &flags->n_flagged, q_index_base, dout);
-        if (s2 != PM_OK) return s2;
-    }
     ctx->l2_parity ^= 1;
     ctx->l2_stats[3] = smax;
     return PM_OK;

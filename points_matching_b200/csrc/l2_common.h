@@ -27,6 +27,8 @@ struct L2Flags {
     unsigned max_tnorm_bits;   // max ||b||^2 over real train rows (float bits)
     unsigned max_qnorm_bits;   // max ||a||^2 over real query rows (float bits)
     int n_flagged;             // rows K3 could not certify -> exact fallback
+    unsigned done_blocks;      // K3's in-kernel grid barrier (split mode): blocks that finished their rows
+    int pad[3];
 };
 
 // exact-integer mode: integer-valued data and norms small enough for the biased key

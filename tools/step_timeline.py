@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Timeline of one cfg2 step (K1 pack -> K2 GEMM -> K3 finish -> exact fallback -> K5 ratio filter) under the PDL
+"""Timeline of one cfg2 step (K1 pack -> K2 GEMM -> K3 finish (+ in-kernel fallback) -> K5 ratio filter) under the PDL
 launch chain: per kernel, first CTA entry / first CTA past griddepcontrol.wait / last CTA exit (globaltimer, ns)."""
 import ctypes as C, os, sys
 import numpy as np, torch
@@ -21,7 +21,7 @@ for _ in range(200):
     step()
 torch.cuda.synchronize()
 span = torch.zeros(15 + 17 + 2 * 1024, dtype=torch.int64, device="cuda")
-names = ["K1 pack", "K2 gemm", "K3 finish", "exact", "K5 filter"]
+names = ["K1 pack", "K2 gemm", "K3 finish", None, "K5 filter"]     # slot 3 (stand-alone exact kernel) is no longer in the chain
 rows = []
 for rep in range(5):
     init = np.zeros(15 + 17 + 2 * 1024, dtype=np.int64)
@@ -50,4 +50,4 @@ print("K3 per-block (us after the first block passed the wait): start min/med/ma
       % (st.min(), np.median(st), st.max(), en.min(), np.median(en), en.max(), np.median(en - st), (en - st).max()))
 for r in rows:
     t0 = r[0]
-    print(" | ".join(f"{n}: in {(r[3*k]-t0)/1e3:6.2f} dep {(r[3*k+1]-t0)/1e3:6.2f} out {(r[3*k+2]-t0)/1e3:6.2f}" for k, n in enumerate(names)), " (us)")
+    print(" | ".join(f"{n}: in {(r[3*k]-t0)/1e3:6.2f} dep {(r[3*k+1]-t0)/1e3:6.2f} out {(r[3*k+2]-t0)/1e3:6.2f}" for k, n in enumerate(names) if n), " (us)")
