@@ -344,6 +344,9 @@ def run_ours(args):
     if not args.no_hamming:
         extra = {"hamming": bench_hamming(ctx, torch, dev, world, rank, stream, barrier, peaks)}
 
+    if extra is not None and not args.no_cfg5:
+        extra["cfg5"] = bench_cfg5(ctx, torch, dev, world, rank, barrier)
+
     clocks = sampler.stop() if sampler else None
 
     cpu_baseline = None
@@ -414,6 +417,39 @@ def bench_hamming(ctx, torch, dev, world, rank, stream, barrier, peaks):
                          "peak_source": "nominal 148 SM x 16 POPC/clk x 1965 MHz / 8 POPC per pair",
                          "hbm_equivalent": {"bytes_per_pair": 64, "achieved_gbs": pairs * 64 / (k4_avg * 1e-3) / 1e9 if k4_n else None,
                                             "peak_gbs": peaks["hbm"]}}}
+
+
+def bench_cfg5(ctx, torch, dev, world, rank, barrier):
+    """BASELINE config 5 (1024 pairs x 8k SIFT, match + RANSAC-F per pair, pairs partitioned across ranks) on a
+    bounded sample: 32 pairs per rank cycling through 4 distinct synthetic pairs (8192 x 8192 x 128 f32, resident
+    in HBM), 4096 8-point hypotheses per pair, Sampson 1 px, refit.  Reports image pairs per second."""
+    from points_matching_b200 import synth
+    from points_matching_b200.pipeline import PairPipeline
+    n, pool = 8192, []
+    for k in range(4):
+        d1, d2, k1, k2, _ = synth.image_pair(n, n, seed=100 + 10 * rank + k)
+        pool.append(tuple(torch.from_numpy(a).to(dev) for a in (d1, d2, k1, k2)))
+    pipe = PairPipeline(ctx, dev, n, n_hyp=4096)
+    for k in range(4):
+        last = pipe.finish(pipe.run(*pool[k], seed=k))
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pairs = 32
+    ev0.record(torch.cuda.current_stream(dev))
+    for p in range(pairs):
+        last = pipe.finish(pipe.run(*pool[p % 4], seed=p % 4))
+    ev1.record(torch.cuda.current_stream(dev))
+    barrier()
+    tmax = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    return {"workload": "cfg5 sample: 32 image pairs per rank (of 1024 / world), 8192 x 8192 SIFT-like f32 descriptors resident in HBM, "
+                        "kNN-2 + ratio 0.75 + gather + RANSAC-F (4096 8-point hypotheses, Sampson 1 px, refit)",
+            "image_pairs_per_s": world * pairs / (ms * 1e-3), "ms_per_pair": ms / pairs,
+            "last_pair": {"n_matches": last["n_matches"], "n_inliers": last["n_inliers"]},
+            "est_full_config_s": 1024.0 / world * (ms / pairs) * 1e-3}
 
 
 def bench_ransac(ctx, torch, dist, dev, world, rank, stream, barrier, peaks, args):
@@ -516,6 +552,7 @@ def main():
     ap.add_argument("--no-ransac", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-hamming", action="store_true")
+    ap.add_argument("--no-cfg5", action="store_true")
     ap.add_argument("--ransac-steps", type=int, default=5)
     ap.add_argument("--no-ramp", action="store_true", help="skip the 1 s clock ramp (profiling runs under ncu)")
     args = ap.parse_args()

@@ -191,6 +191,18 @@ int pm_find_fundamental_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int
                             const pm_ransac_params *prm, double *dF /* [9] */, uint8_t *dmask,
                             int32_t *dn_inliers, uint64_t *dkey);
 
+/* LMedS over 7-point minimal samples -- what cv::findFundamentalMat(p1, p2, CV_FM_7POINT) actually runs when
+ * N > 7, i.e. the reference's literal call at main.cpp:95-98.  Per model the error is OpenCV's
+ * max(d(x2,Fx1)^2, d(x1,F^T x2)^2) in FP64 cast to float; the model with the smallest median wins (lowest
+ * model id = 3*hyp+k on ties); inliers are err <= (2.5*1.4826*(1+5/(n-7))*sqrt(median))^2; no refit.
+ * sample_idx: [n_hyp][7] HOST index sets or NULL (generated from seed).  PM_EMPTY when n < 8 or no model. */
+int pm_find_fundamental_lmeds(pm_ctx *ctx, const float *p1, const float *p2, int n, int n_hyp,
+                              const int32_t *sample_idx, uint64_t seed, double F[9], uint8_t *mask,
+                              int *n_inliers, float *median_out);
+/* The scoring stage alone: dmedians[m] = median error of model m (+inf for a NaN model). */
+int pm_lmeds_score_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dF32, int n_models,
+                       float *dmedians);
+
 /* N-point normalised 8-point (findFundamentalMat(..., FM_8POINT)); mask all ones. */
 int pm_fundamental_8point(pm_ctx *ctx, const float *p1, const float *p2, int n, double F[9]);
 

@@ -242,11 +242,10 @@ inline void KeyPoint::convert(const std::vector<KeyPoint> &keypoints, std::vecto
 
 // ---------------------------------------------------------------------------------------
 // cv::findFundamentalMat (main.cpp:95-98)
-//   N < 7 -> empty.  FM_8POINT: N-point normalised 8-point, mask all ones.  FM_RANSAC and --
-//   as OpenCV routes FM_7POINT / FM_LMEDS with N > 7 to a robust estimator -- every other
-//   method: GPU RANSAC in batches of minimal samples (8-point for FM_RANSAC with N >= 8,
-//   else 7-point) with OpenCV's adaptive stop  niters = log(1 - conf) / log(1 - w^m).
-//   param1 <= 0 -> 3, param2 outside (0, 1) -> 0.99 (OpenCV defaults).
+//   N < 7 -> empty.  FM_8POINT: N-point normalised 8-point, mask all ones.  FM_7POINT / FM_LMEDS with
+//   N > 7: LMedS over 7-point samples (what OpenCV dispatches to; no refit).  FM_RANSAC:
+//   GPU RANSAC in batches of minimal samples with OpenCV's adaptive stop
+//   niters = log(1 - conf) / log(1 - w^m).  param1 <= 0 -> 3, param2 outside (0, 1) -> 0.99.
 // ---------------------------------------------------------------------------------------
 struct FundamentalOptions {
     int metric = PM_METRIC_SAMPSON;   // PM_METRIC_SYMEPI reproduces OpenCV's mask rule exactly
@@ -273,6 +272,20 @@ inline Matx33d findFundamentalMat(const std::vector<Point2f> &points1, const std
         if (c.check(pm_fundamental_8point(c.handle(), p1, p2, n, F.val), true) == PM_OK) {
             F.is_empty = false;
             if (mask) mask->assign((size_t)n, 1);
+        }
+        return F;
+    }
+    if (method != FM_RANSAC && n > 7) {
+        // OpenCV routes FM_7POINT / FM_LMEDS with N > 7 to LMedS -- the reference's literal call at main.cpp:95-98
+        double num = 1. - param2 > DBL_MIN ? 1. - param2 : DBL_MIN;
+        int niters = (int)std::lround(std::log(num) / std::log(1. - std::pow(0.55, 7)));
+        niters = niters < 3 ? 3 : (niters > opt.maxIters ? opt.maxIters : niters);
+        std::vector<unsigned char> m((size_t)n);
+        int ninl = 0;
+        if (c.check(pm_find_fundamental_lmeds(c.handle(), p1, p2, n, niters, nullptr, opt.seed, F.val, m.data(), &ninl, nullptr),
+                    true) == PM_OK) {
+            F.is_empty = false;
+            if (mask) *mask = m;
         }
         return F;
     }

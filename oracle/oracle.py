@@ -174,6 +174,23 @@ def ransac_f(p1, p2, sample_idx, metric=METRIC_SAMPSON, thr=1.0, refit=True, nth
                 counts=counts, models=Fs)
 
 
+def lmeds_f(p1, p2, sample_idx, models=None):
+    """LMedS over caller-supplied 7-point samples (or over given f32 models [nhyp*3, 9]).  Returns a dict or None."""
+    p1, p2 = _f32(p1), _f32(p2)
+    idx = np.ascontiguousarray(sample_idx, dtype=np.int32)
+    nhyp = idx.shape[0]
+    F = np.zeros(9)
+    mask = np.zeros(p1.shape[0], dtype=np.uint8)
+    ninl, best = C.c_int(0), C.c_int64(-1)
+    med = np.zeros(nhyp * 3, dtype=np.float32)
+    Fs = np.zeros((nhyp * 3, 9), dtype=np.float32) if models is None else np.ascontiguousarray(models, dtype=np.float32)
+    ok = lib().orc_lmeds_f(_p(p1), _p(p2), p1.shape[0], _p(idx), nhyp, _p(F), _p(mask), C.byref(ninl), C.byref(best),
+                           _p(med), _p(Fs), int(models is not None))
+    if not ok:
+        return None
+    return dict(F=F.reshape(3, 3), mask=mask, n_inliers=ninl.value, best_model=best.value, medians=med, models=Fs)
+
+
 def find_fundamental_cv(p1, p2, method, param1=3.0, param2=0.99, max_iters=1000):
     """OpenCV-literal dispatch (FM_7POINT=1, FM_8POINT=2, FM_LMEDS=4, FM_RANSAC=8)."""
     p1, p2 = _f32(p1), _f32(p2)

@@ -780,6 +780,61 @@ done:
     return result;
 }
 
+/* LMedS over caller-supplied 7-point samples: the estimator cv::findFundamentalMat(..., CV_FM_7POINT) runs
+ * when N > 7 (main.cpp:95-98), with the product's conventions -- models rounded to f32 first, winner =
+ * smallest median (lowest model id 3*hyp+k on ties).  Fs32 in/out: when models_given != 0 the nhyp*3 models
+ * ([9] f32 each, NaN = absent) are taken from Fs32 instead of being solved here. */
+int orc_lmeds_f(const float *p1, const float *p2, int n, const int32_t *sample_idx, int nhyp,
+                double F[9], uint8_t *mask, int *n_inliers, int64_t *best_model, float *medians,
+                float *Fs32, int models_given)
+{
+    if (n < 8 || nhyp <= 0) return 0;
+    float *err = (float *)malloc(sizeof(float) * (size_t)n);
+    float *Fs = Fs32 ? Fs32 : (float *)malloc(sizeof(float) * 27 * (size_t)nhyp);
+    double best_med = DBL_MAX; int64_t bm = -1;
+    for (int h = 0; h < nhyp; ++h) {
+        double Fd[27];
+        int ns = 3;
+        if (!models_given) ns = orc_fm_7point_idx(p1, p2, sample_idx + (size_t)h * 7, Fd);
+        for (int k = 0; k < 3; ++k) {
+            float *Ff = Fs + ((size_t)h * 3 + k) * 9;
+            if (!models_given) for (int i = 0; i < 9; ++i) Ff[i] = k < ns ? (float)Fd[9 * k + i] : NAN;
+            float med = INFINITY;
+            int ok = 1;
+            for (int i = 0; i < 9; ++i) ok = ok && isfinite(Ff[i]);
+            if (ok) {
+                double Fw[9];
+                for (int i = 0; i < 9; ++i) Fw[i] = (double)Ff[i];
+                cv_compute_error(Fw, p1, p2, n, err);
+                for (int i = 0; i < n; ++i) if (!(err[i] >= 0.f)) ok = 0;
+                if (ok) { qsort(err, (size_t)n, sizeof(float), cmp_float); med = err[n / 2]; }
+            }
+            if (medians) medians[(size_t)h * 3 + k] = med;
+            if (med < INFINITY && (double)med < best_med) { best_med = med; bm = (int64_t)h * 3 + k; }
+        }
+    }
+    int result = 0;
+    if (bm >= 0) {
+        double Fw[9];
+        for (int i = 0; i < 9; ++i) Fw[i] = (double)Fs[(size_t)bm * 9 + i];
+        double sigma = 2.5 * 1.4826 * (1 + 5. / (n - 7)) * sqrt(best_med);
+        if (sigma < 0.001) sigma = 0.001;
+        cv_compute_error(Fw, p1, p2, n, err);
+        uint8_t *mk = mask ? mask : (uint8_t *)malloc((size_t)n);
+        float t = (float)(sigma * sigma);
+        int nz = 0;
+        for (int i = 0; i < n; ++i) { int f = err[i] <= t; mk[i] = (uint8_t)f; nz += f; }
+        if (!mask) free(mk);
+        memcpy(F, Fw, sizeof(Fw));
+        if (n_inliers) *n_inliers = nz;
+        if (best_model) *best_model = bm;
+        result = 1;
+    }
+    free(err);
+    if (!Fs32) free(Fs);
+    return result;
+}
+
 /* ------------------------------------------------------------------------- */
 /* epilines: main.cpp:127-132                                                 */
 /* ------------------------------------------------------------------------- */

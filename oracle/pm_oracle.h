@@ -102,6 +102,14 @@ int orc_ransac_f(const float *p1, const float *p2, int n,
                  double F[9], uint8_t *mask, int *n_inliers, int64_t *best_model,
                  int32_t *counts, float *Fs32, int nthreads);
 
+/* LMedS over caller-supplied 7-point samples (the estimator behind main.cpp:95-98's CV_FM_7POINT when
+ * N > 7): models rounded to f32, error = (float) max sym-epi distance in f64, median = sorted err[n/2],
+ * winner = smallest median (lowest model id 3*hyp+k on ties), inliers by the 2.5*1.4826*(1+5/(n-7))*sqrt(med)
+ * rule, no refit.  medians: [nhyp*3] or NULL; Fs32: [nhyp*3][9] models out (or in when models_given). */
+int orc_lmeds_f(const float *p1, const float *p2, int n, const int32_t *sample_idx, int nhyp,
+                double F[9], uint8_t *mask, int *n_inliers, int64_t *best_model, float *medians,
+                float *Fs32, int models_given);
+
 /* OpenCV-literal estimator restatement (cv::findFundamentalMat dispatch as probed in
  * SURVEY.md section 8 a6): cv::RNG(-1) sample stream, 7-point models, sym-epi metric in
  * double cast to float, adaptive iteration count, no refit.  method: 8 = FM_RANSAC,

@@ -225,6 +225,31 @@ class Context:
             return None
         return F.reshape(3, 3), mask, ninl.value
 
+    def find_fundamental_lmeds(self, p1, p2, n_hyp=512, sample_idx=None, seed=0):
+        """LMedS over 7-point samples (the estimator behind the reference's CV_FM_7POINT call when N > 7).
+        Returns (F[3,3] f64, mask[n] u8, n_inliers, median) or None."""
+        p1 = np.ascontiguousarray(p1, dtype=np.float32).reshape(-1, 2)
+        p2 = np.ascontiguousarray(p2, dtype=np.float32).reshape(-1, 2)
+        n = p1.shape[0]
+        keep = None
+        if sample_idx is not None:
+            keep = np.ascontiguousarray(sample_idx, dtype=np.int32)
+            if keep.ndim != 2 or keep.shape[1] != 7:
+                raise PMError(_lib.PM_BAD_ARG, "sample_idx must be [n_hyp, 7]")
+            n_hyp = keep.shape[0]
+        F = np.zeros(9, dtype=np.float64)
+        mask = np.zeros(n, dtype=np.uint8)
+        ninl, med = C.c_int(0), C.c_float(0)
+        st = self._chk(self._L.pm_find_fundamental_lmeds(self._h, _p(p1), _p(p2), n, n_hyp, _p(keep), C.c_uint64(seed),
+                                                         _p(F), _p(mask), C.byref(ninl), C.byref(med)), allow_empty=True)
+        if st == PM_EMPTY:
+            return None
+        return F.reshape(3, 3), mask, ninl.value, med.value
+
+    def lmeds_score_dev(self, dp1, dp2, n, dF32, n_models, dmedians):
+        self._chk(self._L.pm_lmeds_score_dev(self._h, C.c_void_p(dp1), C.c_void_p(dp2), n, C.c_void_p(dF32), n_models,
+                                             C.c_void_p(dmedians)))
+
     def fundamental_8point(self, p1, p2):
         p1 = np.ascontiguousarray(p1, dtype=np.float32).reshape(-1, 2)
         p2 = np.ascontiguousarray(p2, dtype=np.float32).reshape(-1, 2)
@@ -397,10 +422,10 @@ def findFundamentalMat(points1, points2, method=FM_RANSAC, ransacReprojThreshold
                        maxIters=1000, *, metric=METRIC_SAMPSON, refit=True, batch=1024, seed=0, ctx=None):
     """cv::findFundamentalMat look-alike (main.cpp:95-98).  Returns (F, mask) or (None, None).
 
-    method FM_8POINT: N-point normalised 8-point, mask of ones.  FM_RANSAC (and FM_7POINT /
-    FM_LMEDS with N > 7, which OpenCV routes to its robust estimators): GPU RANSAC in batches
+    method FM_8POINT: N-point normalised 8-point, mask of ones.  FM_RANSAC: GPU RANSAC in batches
     of `batch` minimal samples with OpenCV's adaptive stop  niters = log(1-conf)/log(1-w^m).
-    N < 7 -> (None, None) like OpenCV's empty Mat.
+    FM_7POINT / FM_LMEDS with N > 7: LMedS over 7-point samples, exactly the estimator OpenCV
+    dispatches to, no refit.  N < 7 -> (None, None) like OpenCV's empty Mat.
     """
     ctx = ctx or default_context()
     p1 = np.ascontiguousarray(points1, dtype=np.float32).reshape(-1, 2)
@@ -419,6 +444,14 @@ def findFundamentalMat(points1, points2, method=FM_RANSAC, ransacReprojThreshold
             return None, None
         F = ctx.fundamental_8point(p1, p2)
         return (F, np.ones(n, np.uint8)) if F is not None else (None, None)
+    if method != FM_RANSAC and n > 7:
+        # OpenCV routes FM_7POINT / FM_LMEDS with N > 7 to LMedS (the reference's literal call, main.cpp:95-98):
+        # niters = log(1 - conf) / log(1 - (1 - 0.45)^7), at least 3, at most maxIters
+        num = max(1.0 - confidence, np.finfo(np.float64).tiny)
+        niters = int(round(math.log(num) / math.log(1.0 - 0.55 ** 7)))
+        niters = max(3, min(niters, maxIters))
+        r = ctx.find_fundamental_lmeds(p1, p2, n_hyp=niters, seed=seed)
+        return (r[0], r[1]) if r is not None else (None, None)
     m = 8 if (method == FM_RANSAC and n >= 8) else 7
     best, done, need, b = None, 0, maxIters, 0
     while done < min(need, maxIters):

@@ -48,8 +48,10 @@ __global__ void ham_pack_kernel(const uint8_t *__restrict__ src, int n, int byte
 // fold three words into a "ones" and a "twos" word first, so 8 words cost 5 POPC + 6 LOP3 instead of 8 POPC.
 __device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) { return a ^ b ^ c; }
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a | b)); }
+// `one` is the constant 1 passed as a kernel argument: x * one + y stays an IMAD (FMA pipe) instead of an
+// IADD on the ALU pipe, which is the pipe that bounds the kernel once the POPC count is down (ncu r1c: ALU 89%).
 template <int W>
-__device__ __forceinline__ uint32_t ham_dist(const uint32_t (&q)[W], const uint32_t (&t)[W])
+__device__ __forceinline__ uint32_t ham_dist(const uint32_t (&q)[W], const uint32_t (&t)[W], uint32_t one)
 {
     uint32_t x[W];
 #pragma unroll
@@ -60,22 +62,22 @@ __device__ __forceinline__ uint32_t ham_dist(const uint32_t (&q)[W], const uint3
         const uint32_t s1 = xor3(x[g], x[g + 1], x[g + 2]), c1 = maj3(x[g], x[g + 1], x[g + 2]);
         const uint32_t s2 = xor3(x[g + 3], x[g + 4], x[g + 5]), c2 = maj3(x[g + 3], x[g + 4], x[g + 5]);
         const uint32_t s3 = xor3(s1, s2, x[g + 6]), c3 = maj3(s1, s2, x[g + 6]);
-        ones += __popc(s3) + __popc(x[g + 7]);
-        twos += __popc(c1) + __popc(c2) + __popc(c3);
+        ones = __popc(s3) * one + (__popc(x[g + 7]) * one + ones);
+        twos = __popc(c1) * one + (__popc(c2) * one + (__popc(c3) * one + twos));
     }
     if (W % 8 == 4) {
         constexpr int g = W - 4;
         ones += __popc(xor3(x[g], x[g + 1], x[g + 2])) + __popc(x[g + 3]);
         twos += __popc(maj3(x[g], x[g + 1], x[g + 2]));
     }
-    return ones + 2u * twos;
+    return twos * (one + one) + ones;
 }
 
 // part[(chunk * nq + qi) * 2 + {0,1}] = (dist << 32 | global train index), ~0 if absent.
 template <int W>
 __global__ void __launch_bounds__(HAM_THREADS)
 ham_knn2_kernel(const uint32_t *__restrict__ q, int nq, const uint32_t *__restrict__ t, int nt,
-                int chunk_rows, unsigned long long *__restrict__ part)
+                int chunk_rows, unsigned long long *__restrict__ part, uint32_t one)
 {
     __shared__ __align__(16) uint32_t tile[2][HAM_TT * W];
     const int tid = threadIdx.x;
@@ -140,8 +142,8 @@ ham_knn2_kernel(const uint32_t *__restrict__ q, int nq, const uint32_t *__restri
             }
 #pragma unroll
             for (int r = 0; r < HAM_QPT; ++r) {
-                const uint32_t d = ham_dist<W>(qr[r], tw);
-                uint32_t key = (d << 16) | (jbase + (uint32_t)j);
+                const uint32_t d = ham_dist<W>(qr[r], tw, one);
+                uint32_t key = d * (one << 16) + (jbase + (uint32_t)j);
                 m2[r] = min(m2[r], max(m1[r], key));
                 m1[r] = min(m1[r], key);
             }
@@ -271,9 +273,9 @@ int ham_run(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, i
     dim3 grid(qblocks, chunks);
     {
     pm_prof_scope prof(ctx, 1);
-    if (W == 4)       ham_knn2_kernel<4><<<grid, HAM_THREADS, 0, ctx->stream>>>(pq, nq, pt, nt, chunk_rows, part);
-    else if (W == 8)  ham_knn2_kernel<8><<<grid, HAM_THREADS, 0, ctx->stream>>>(pq, nq, pt, nt, chunk_rows, part);
-    else if (W == 16) ham_knn2_kernel<16><<<grid, HAM_THREADS, 0, ctx->stream>>>(pq, nq, pt, nt, chunk_rows, part);
+    if (W == 4)       ham_knn2_kernel<4><<<grid, HAM_THREADS, 0, ctx->stream>>>(pq, nq, pt, nt, chunk_rows, part, 1u);
+    else if (W == 8)  ham_knn2_kernel<8><<<grid, HAM_THREADS, 0, ctx->stream>>>(pq, nq, pt, nt, chunk_rows, part, 1u);
+    else if (W == 16) ham_knn2_kernel<16><<<grid, HAM_THREADS, 0, ctx->stream>>>(pq, nq, pt, nt, chunk_rows, part, 1u);
     else ham_knn2_generic_kernel<<<grid, 128, 0, ctx->stream>>>(pq, nq, pt, nt, W, chunk_rows, part);
     }
     PM_CHECK_LAUNCH(ctx);

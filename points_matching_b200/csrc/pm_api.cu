@@ -541,6 +541,59 @@ int pm_find_fundamental_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int
     return pmk_ransac_finish(ctx, dp1, dp2, n, dFw, prm->threshold, prm->metric, prm->refit, dF, dmask, dn_inliers);
 }
 
+int pm_lmeds_score_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dF32, int n_models, float *dmedians)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, n >= 0 && n_models >= 0, "bad argument");
+    return pmk_lmeds_score(ctx, dp1, dp2, n, dF32, n_models, dmedians);
+}
+
+int pm_find_fundamental_lmeds(pm_ctx *ctx, const float *p1, const float *p2, int n, int n_hyp, const int32_t *sample_idx,
+                              uint64_t seed, double F[9], uint8_t *mask, int *n_inliers, float *median_out)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, p1 && p2 && F && n >= 0 && n_hyp >= 0, "bad argument");
+    if (n_inliers) *n_inliers = 0;
+    if (n < 8 || n_hyp == 0) return PM_EMPTY;
+    PM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int nm = n_hyp * 3;
+    PM_WS(ctx, dp1, float *, WS_P1, (size_t)n * 8);
+    PM_WS(ctx, dp2, float *, WS_P2, (size_t)n * 8);
+    PM_WS(ctx, ds, int32_t *, WS_SAMPLES, (size_t)n_hyp * 7 * 4);
+    PM_WS(ctx, dF32, float *, WS_F32, ((size_t)nm + 1) * 12 * 4);
+    PM_WS(ctx, dmed, float *, WS_COUNTS, (size_t)nm * 4);
+    PM_WS(ctx, dkey, uint64_t *, WS_KEY, 64);
+    PM_WS(ctx, dmask, uint8_t *, WS_MASK, (size_t)n);
+    PM_WS(ctx, dFout, double *, WS_FOUT, 16 * 8);
+    float *dFw = dF32 + (size_t)nm * 12;
+    int32_t *dninl = reinterpret_cast<int32_t *>(dkey + 2);
+    H2D(ctx, dp1, p1, (size_t)n * 8);
+    H2D(ctx, dp2, p2, (size_t)n * 8);
+    std::vector<int32_t> gen;
+    const int32_t *hs = sample_idx;
+    if (!hs) {
+        gen.resize((size_t)n_hyp * 7);
+        pm_make_sample_sets(n, n_hyp, 7, seed, gen.data());
+        hs = gen.data();
+    }
+    H2D(ctx, ds, hs, (size_t)n_hyp * 7 * 4);
+    if (!sample_idx) PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int st;
+    if ((st = pmk_ransac_solve(ctx, dp1, dp2, n, ds, n_hyp, 7, dF32)) != PM_OK) return st;
+    if ((st = pmk_lmeds_score(ctx, dp1, dp2, n, dF32, nm, dmed)) != PM_OK) return st;
+    if ((st = pmk_lmeds_finish(ctx, dp1, dp2, n, dF32, dmed, nm, dFw, dFout, dmask, dninl, dkey)) != PM_OK) return st;
+    D2H(ctx, ctx->h_pinned, dkey, 32);
+    D2H(ctx, ctx->h_pinned + 16, dFout, 72);
+    PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint64_t key = *reinterpret_cast<const uint64_t *>(ctx->h_pinned);
+    if (key == ~0ull) return PM_EMPTY;
+    memcpy(F, ctx->h_pinned + 16, 72);
+    if (n_inliers) *n_inliers = ctx->h_pinned[4];
+    if (median_out) { const uint32_t b = (uint32_t)(key >> 32); memcpy(median_out, &b, 4); }
+    if (mask) { D2H(ctx, mask, dmask, (size_t)n); PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); }
+    return PM_OK;
+}
+
 int pm_fundamental_8point(pm_ctx *ctx, const float *p1, const float *p2, int n, double F[9])
 {
     if (!ctx) return PM_BAD_ARG;

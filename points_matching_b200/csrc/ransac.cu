@@ -688,6 +688,126 @@ residuals_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2, i
     }
 }
 
+// =====================================================================================
+// LMedS (what cv::findFundamentalMat(..., CV_FM_7POINT) runs when N > 7: the reference's literal call,
+// main.cpp:95-98).  Per model: err_i = (float) max(d(x2,Fx1)^2, d(x1,F^T x2)^2) in FP64
+// (OpenCV's computeError), median = sorted err[n / 2]; winner = smallest median (lowest model id on
+// ties); inliers = err <= (2.5 * 1.4826 * (1 + 5/(n-7)) * sqrt(median))^2.  No fused multiply-adds in the
+// error: the oracle (orc_symepi_f64, -ffp-contract=off) is matched bit for bit.
+// =====================================================================================
+__device__ __forceinline__ float symepi_err_f64(const double (&F)[9], const float4 p)
+{
+    const double x1 = p.x, y1 = p.y, x2 = p.z, y2 = p.w;
+    double a = __dadd_rn(__dadd_rn(__dmul_rn(F[0], x1), __dmul_rn(F[1], y1)), F[2]);
+    double b = __dadd_rn(__dadd_rn(__dmul_rn(F[3], x1), __dmul_rn(F[4], y1)), F[5]);
+    double c = __dadd_rn(__dadd_rn(__dmul_rn(F[6], x1), __dmul_rn(F[7], y1)), F[8]);
+    const double s2 = __ddiv_rn(1.0, __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(x2, a), __dmul_rn(y2, b)), c);
+    a = __dadd_rn(__dadd_rn(__dmul_rn(F[0], x2), __dmul_rn(F[3], y2)), F[6]);
+    b = __dadd_rn(__dadd_rn(__dmul_rn(F[1], x2), __dmul_rn(F[4], y2)), F[7]);
+    c = __dadd_rn(__dadd_rn(__dmul_rn(F[2], x2), __dmul_rn(F[5], y2)), F[8]);
+    const double s1 = __ddiv_rn(1.0, __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
+    const double d1 = __dadd_rn(__dadd_rn(__dmul_rn(x1, a), __dmul_rn(y1, b)), c);
+    const double e1 = __dmul_rn(__dmul_rn(d1, d1), s1), e2 = __dmul_rn(__dmul_rn(d2, d2), s2);
+    return (float)(e1 > e2 ? e1 : e2);
+}
+
+constexpr int LM_THREADS = 256;
+// One CTA per model.  errs: scratch [gridDim.x][n].  medians[model] = err bits of rank n/2 (NaN -> +inf
+// ordering: a model with a NaN coefficient or error gets median +inf and can never win).
+__global__ void __launch_bounds__(LM_THREADS)
+lmeds_median_kernel(const float4 *__restrict__ pts, int n, const float *__restrict__ Fm, int model0, int n_models,
+                    float *__restrict__ errs, float *__restrict__ medians)
+{
+    __shared__ unsigned hist[256];
+    __shared__ unsigned s_prefix, s_rank;
+    __shared__ int s_bad;
+    const int m = model0 + blockIdx.x;
+    if (m >= n_models) return;
+    double F[9];
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { const float v = Fm[(size_t)m * 12 + i]; ok = ok && isfinite(v); F[i] = (double)v; }
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    if (!ok) { if (threadIdx.x == 0) medians[m] = __int_as_float(0x7f800000); return; }
+    unsigned *e = reinterpret_cast<unsigned *>(errs + (size_t)blockIdx.x * n);
+    for (int i = threadIdx.x; i < n; i += LM_THREADS) {
+        const float err = symepi_err_f64(F, pts[i]);
+        if (!(err >= 0.f)) s_bad = 1;                 // NaN
+        e[i] = __float_as_uint(err);                  // err >= 0: the bits order like the values
+    }
+    __syncthreads();
+    if (s_bad) { if (threadIdx.x == 0) medians[m] = __int_as_float(0x7f800000); return; }
+    // radix select of rank n/2 (0-based): four 8-bit passes, most significant byte first
+    if (threadIdx.x == 0) { s_prefix = 0u; s_rank = (unsigned)(n / 2); }
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        hist[threadIdx.x] = 0u;
+        __syncthreads();
+        const unsigned prefix = s_prefix, himask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+        for (int i = threadIdx.x; i < n; i += LM_THREADS) {
+            const unsigned v = e[i];
+            if ((v & himask) == prefix) atomicAdd(&hist[(v >> shift) & 0xFFu], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned r = s_rank, b = 0;
+            for (; b < 255u; ++b) { if (r < hist[b]) break; r -= hist[b]; }
+            s_rank = r; s_prefix = prefix | (b << shift);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) medians[m] = __uint_as_float(s_prefix);
+}
+
+// key = median bits << 32 | model id: the minimum is the smallest median, lowest id on ties
+__global__ void __launch_bounds__(256)
+lmeds_best_kernel(const float *__restrict__ medians, int n_models, int id_base, unsigned long long *key)
+{
+    unsigned long long best = ~0ull;
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n_models; m += gridDim.x * blockDim.x) {
+        const unsigned b = __float_as_uint(medians[m]);
+        if (b < 0x7f800000u) {
+            const unsigned long long k = ((unsigned long long)b << 32) | (unsigned)(id_base + m);
+            best = k < best ? k : best;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long y = __shfl_xor_sync(0xffffffffu, best, o); best = y < best ? y : best; }
+    if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(key, best);
+}
+
+// winner -> Fw (12 floats), F (f64), sigma^2 (f32 at Fw[9]); key == ~0: no model
+__global__ void lmeds_pick_kernel(const unsigned long long *key, const float *__restrict__ Fm, int id_base, int n_models,
+                                  int n, float *Fw, double *Fout)
+{
+    if (threadIdx.x != 0) return;
+    const unsigned long long k = *key;
+    const long long m = (long long)(unsigned)(k & 0xFFFFFFFFull) - id_base;
+    if (k == ~0ull || m < 0 || m >= n_models) { for (int i = 0; i < 12; ++i) Fw[i] = __int_as_float(0x7fc00000); return; }
+    for (int i = 0; i < 9; ++i) { Fw[i] = Fm[(size_t)m * 12 + i]; Fout[i] = (double)Fw[i]; }
+    const double med = (double)__uint_as_float((unsigned)(k >> 32));
+    double sigma = 2.5 * 1.4826 * (1 + 5. / (n - 7)) * sqrt(med);
+    if (sigma < 0.001) sigma = 0.001;
+    Fw[9] = (float)(sigma * sigma);
+}
+
+__global__ void __launch_bounds__(256)
+lmeds_mask_kernel(const float4 *__restrict__ pts, int n, const float *__restrict__ Fw, uint8_t *__restrict__ mask,
+                  int32_t *n_inl)
+{
+    double F[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) F[i] = (double)Fw[i];
+    const float t = Fw[9];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool in = false;
+    if (i < n) { in = symepi_err_f64(F, pts[i]) <= t; mask[i] = in ? 1 : 0; }
+    const int c = __syncthreads_count(in);
+    if (threadIdx.x == 0 && c) atomicAdd(n_inl, c);
+}
+
 int get_pts4(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float4 **out)
 {
     PM_WS(ctx, pts, float4 *, WS_MISC, (size_t)(n > 0 ? n : 1) * sizeof(float4));
@@ -808,6 +928,48 @@ int pmk_fundamental_npoint(pm_ctx *ctx, const float *dp1, const float *dp2, int 
     int st = get_pts4(ctx, dp1, dp2, n, &pts);
     if (st != PM_OK) return st;
     return run_refit(ctx, pts, n, dmask, nullptr, dF, dok);
+}
+
+// medians of the symmetric-epipolar error, one per model (NaN models: +inf)
+int pmk_lmeds_score(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dF32, int n_models, float *dmedians)
+{
+    if (n_models <= 0 || n <= 0) return PM_OK;
+    const float4 *pts;
+    int st = get_pts4(ctx, dp1, dp2, n, &pts);
+    if (st != PM_OK) return st;
+    // error scratch: at most ~64 MB, models in batches
+    int batch = (int)((16ll << 20) / n);
+    if (batch < 1) batch = 1;
+    if (batch > n_models) batch = n_models;
+    PM_WS(ctx, errs, float *, WS_LINES, (size_t)batch * n * sizeof(float));
+    for (int m0 = 0; m0 < n_models; m0 += batch) {
+        lmeds_median_kernel<<<min(batch, n_models - m0), LM_THREADS, 0, ctx->stream>>>(pts, n, dF32, m0, n_models, errs, dmedians);
+        PM_CHECK_LAUNCH(ctx);
+    }
+    return PM_OK;
+}
+
+// winner of the medians -> F (f64[9], no refit: OpenCV returns the minimal model), mask, inlier count;
+// *dkey = median bits << 32 | model id, ~0 when no model
+int pmk_lmeds_finish(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dF32, const float *dmedians,
+                     int n_models, float *dFw, double *dF, uint8_t *dmask, int32_t *dn_inl, uint64_t *dkey)
+{
+    const float4 *pts;
+    int st = get_pts4(ctx, dp1, dp2, n, &pts);
+    if (st != PM_OK) return st;
+    PM_CUDA(ctx, cudaMemsetAsync(dkey, 0xFF, 8, ctx->stream));
+    PM_CUDA(ctx, cudaMemsetAsync(dn_inl, 0, 4, ctx->stream));
+    if (n_models > 0) {
+        lmeds_best_kernel<<<min(pm_cdiv(n_models, 256), 4 * ctx->num_sms), 256, 0, ctx->stream>>>(dmedians, n_models, 0, (unsigned long long *)dkey);
+        PM_CHECK_LAUNCH(ctx);
+    }
+    lmeds_pick_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long *)dkey, dF32, 0, n_models, n, dFw, dF);
+    PM_CHECK_LAUNCH(ctx);
+    if (n > 0) {
+        lmeds_mask_kernel<<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>(pts, n, dFw, dmask, dn_inl);
+        PM_CHECK_LAUNCH(ctx);
+    }
+    return PM_OK;
 }
 
 int pmk_epilines(pm_ctx *ctx, const float *dpts, int n, int which, const double *dF, float *dlines)

@@ -115,3 +115,23 @@ def sample_index_sets(n_points, n_hyp, m=8, seed=99):
                 break
             idx[bad] = rng.integers(0, n_points, (bad.size, m), dtype=np.int64)
     return idx.astype(np.int32)
+
+
+def image_pair(n1, n2, seed=0, planted=0.5, outlier_frac=0.0):
+    """One synthetic image pair for the end-to-end flow (BASELINE config 5): SIFT-like descriptors with
+    `planted` of the queries copied (noisily) into the train set, and keypoint coordinates that obey a
+    known two-view geometry on the planted matches (random elsewhere).
+    Returns desc1 [n1,128], desc2 [n2,128], kp1 [n1,2], kp2 [n2,2], (qi, ti) planted index lists."""
+    rng = np.random.default_rng(seed + 13)
+    d1 = sift_like(n1, seed)
+    d2 = sift_like(n2, seed + 1)
+    k = min(int(planted * n1), n2)
+    qi = rng.permutation(n1)[:k]
+    ti = rng.permutation(n2)[:k]
+    d2[ti] = np.clip(d1[qi] + np.round(rng.normal(0, 4.0, (k, d1.shape[1]))), 0, 255)
+    x1, x2, _ = correspondences(k, seed=seed + 2, outlier_frac=outlier_frac)
+    kp1 = np.stack([rng.uniform(0, 1920, n1), rng.uniform(0, 1080, n1)], 1).astype(np.float32)
+    kp2 = np.stack([rng.uniform(0, 1920, n2), rng.uniform(0, 1080, n2)], 1).astype(np.float32)
+    kp1[qi] = x1
+    kp2[ti] = x2
+    return d1, d2.astype(np.float32), kp1, kp2, (qi, ti)

@@ -423,3 +423,69 @@ def test_cpp_host_example_matches_python_mirror(pm, golden, mode, tmp_path):
         assert inl >= 0.9 * g["ransac_mask"].sum()
         mean = float([ln for ln in lines if ln.startswith("mean_sampson")][0].split()[1])
         assert np.isfinite(mean)
+
+
+def test_pair_pipeline_end_to_end(pm, orc):
+    """BASELINE config 5 flow for one pair, device resident: knnMatch(k=2) -> ratio 0.75 -> KeyPoint::convert ->
+    findFundamentalMat(RANSAC).  Matches are bit-exact vs the oracle; F is as good as the oracle's on the same
+    hypothesis index sets."""
+    import torch
+    from points_matching_b200 import synth
+    from points_matching_b200.api import make_sample_sets
+    from points_matching_b200.pipeline import PairPipeline, match_and_estimate_batch
+    d1, d2, k1, k2, (qi, ti) = synth.image_pair(3000, 3300, seed=3)
+    ctx = pm.Context(0)
+    pipe = PairPipeline(ctx, "cuda:0", 4096, n_hyp=2048)
+    dev = [torch.from_numpy(a).cuda() for a in (d1, d2, k1, k2)]
+    res = pipe.finish(pipe.run(*dev, seed=5))
+    knn = orc.knn2_l2(d1, d2)
+    good = orc.ratio_filter(knn, 0.75)
+    assert res["n_matches"] == len(good) > 1000
+    g = pipe.good[: len(good)].cpu().numpy().view(pm.DMATCH).reshape(-1)
+    assert (g["queryIdx"] == good["queryIdx"]).all() and (g["trainIdx"] == good["trainIdx"]).all()
+    p1, p2 = k1[good["queryIdx"]], k2[good["trainIdx"]]
+    assert np.array_equal(pipe.p1[: len(good)].cpu().numpy(), p1) and np.array_equal(pipe.p2[: len(good)].cpu().numpy(), p2)
+    idx = make_sample_sets(len(good), 2048, 8, 5)
+    r = orc.ransac_f(p1, p2, idx, 0, 1.0, True)
+    assert abs(res["n_inliers"] - r["n_inliers"]) <= 3
+    planted = np.isin(good["queryIdx"], qi)
+    s = orc.sampson_f64(res["F"], p1[planted][:2000], p2[planted][:2000]).mean()
+    s_ref = orc.sampson_f64(r["F"], p1[planted][:2000], p2[planted][:2000]).mean()
+    assert s <= s_ref + 1e-3 and s < 0.5
+    # batched form (single rank): every pair processed, same answer for the same pair
+    out = match_and_estimate_batch(pipe, [tuple(dev)] * 3)
+    assert [p for p, _ in out] == [0, 1, 2] and all(o["n_matches"] == len(good) for _, o in out)
+    ctx.close()
+
+
+def test_lmeds_scoring_bit_exact_and_end_to_end(ctx, pm, orc):
+    """LMedS (the reference's literal estimator, main.cpp:95-98 with N > 7): medians bit-exact vs the oracle on
+    identical model bits; end to end on identical 7-point index sets the same winner / mask up to the solver's
+    last-bit differences."""
+    import torch
+    p1, p2, gt = synth.correspondences(1500, seed=6, outlier_frac=0.35)
+    idx = synth.sample_index_sets(1500, 200, 7, seed=12)
+    dev = torch.device("cuda:0")
+    d1, d2, ds = (torch.from_numpy(a).to(dev) for a in (p1, p2, idx))
+    dF = torch.zeros((600, 12), dtype=torch.float32, device=dev)
+    ctx.ransac_solve_dev(d1.data_ptr(), d2.data_ptr(), 1500, ds.data_ptr(), 200, 7, dF.data_ptr())
+    dmed = torch.zeros(600, dtype=torch.float32, device=dev)
+    ctx.lmeds_score_dev(d1.data_ptr(), d2.data_ptr(), 1500, dF.data_ptr(), 600, dmed.data_ptr())
+    ctx.sync()
+    models = dF[:, :9].cpu().numpy()
+    ref = orc.lmeds_f(p1, p2, idx, models=models)
+    med = dmed.cpu().numpy()
+    assert np.array_equal(med.view(np.uint32), ref["medians"].view(np.uint32))          # bit-exact, NaN models -> +inf
+    # end to end through the host call (solver on the GPU)
+    F, mask, ninl, m = ctx.find_fundamental_lmeds(p1, p2, sample_idx=idx)
+    assert np.float32(m) == ref["medians"][ref["best_model"]] and ninl == ref["n_inliers"]
+    assert np.array_equal(mask, ref["mask"]) and np.allclose(F, ref["F"], rtol=0, atol=0)
+    assert mask[gt].mean() > 0.9 and mask[~gt].mean() < 0.1
+    # vs the oracle solving the same samples itself (f64 solver there): same winner unless medians nearly tie
+    r2 = orc.lmeds_f(p1, p2, idx)
+    assert abs(float(m) - float(r2["medians"][r2["best_model"]])) <= 1e-4 * float(m)
+    assert (mask == r2["mask"]).mean() > 0.995
+    # the OpenCV look-alike routes FM_7POINT with N > 7 here
+    F2, mask2 = pm.findFundamentalMat(p1, p2, pm.FM_7POINT, ctx=ctx)
+    assert F2 is not None and mask2[gt].mean() > 0.85 and mask2[~gt].mean() < 0.15
+    assert ctx.find_fundamental_lmeds(p1[:7], p2[:7], n_hyp=4) is None

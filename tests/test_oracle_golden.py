@@ -183,3 +183,29 @@ def test_image_pair_config1(golden, orc):
     assert (lit["queryIdx"] == g["lit_q"]).all() and (lit["trainIdx"] == g["lit_t"]).all()
     F, mask = orc.find_fundamental_cv(g["kp1"][g["lit_q"]], g["kp2"][g["lit_t"]], 1)
     assert _rel(F, g["lit_F"]) < 1e-6 and (mask == g["lit_mask"]).all()
+
+
+def test_lmeds_given_samples(orc):
+    """orc_lmeds_f (the estimator behind main.cpp:95-98's CV_FM_7POINT with N > 7, on caller-supplied samples):
+    medians equal a plain numpy restatement, the winner has the smallest median, the mask follows OpenCV's
+    sigma rule, and the planted motion is recovered."""
+    from points_matching_b200 import synth
+    p1, p2, gt = synth.correspondences(400, seed=3, outlier_frac=0.3)
+    idx = synth.sample_index_sets(400, 60, 7, seed=8)
+    r = orc.lmeds_f(p1, p2, idx)
+    assert r is not None
+    med, models = r["medians"], r["models"]
+    finite = np.isfinite(med)
+    assert finite.sum() >= 60
+    for m in np.nonzero(finite)[0][:25]:
+        e = orc.symepi_f64(models[m].astype(np.float64), p1, p2).astype(np.float32)
+        assert np.sort(e)[400 // 2] == med[m]
+    best = int(np.argmin(np.where(finite, med, np.inf)))
+    assert r["best_model"] == best
+    sigma = max(2.5 * 1.4826 * (1 + 5.0 / (400 - 7)) * np.sqrt(float(med[best])), 0.001)
+    e = orc.symepi_f64(models[best].astype(np.float64), p1, p2).astype(np.float32)
+    assert np.array_equal(r["mask"], (e <= np.float32(sigma * sigma)).astype(np.uint8))
+    assert r["mask"][gt].mean() > 0.9 and r["mask"][~gt].mean() < 0.1
+    # given models reproduce the same answer
+    r2 = orc.lmeds_f(p1, p2, idx, models=models)
+    assert r2["best_model"] == best and np.array_equal(r2["mask"], r["mask"])

@@ -9,7 +9,7 @@ mkdir -p $O
 python -m pytest tests -m gpu -x -q > $O/pytest_$TAG.log 2>&1; echo "pytest exit $?" >> $O/pytest_$TAG.log
 tail -3 $O/pytest_$TAG.log
 python bench.py --steps 1000 --warmup 10 > $O/bench_$TAG.json 2> $O/bench_$TAG.err; echo "bench exit $?"
-SHORT="python bench.py --steps 10 --warmup 3 --no-ramp --no-cpu --ransac-steps 2"
+SHORT="python bench.py --steps 10 --warmup 3 --no-ramp --no-cpu --no-cfg5 --ransac-steps 2"
 $SHORT > $O/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/launches_$TAG.csv $SHORT > $O/ncu_list_$TAG.log 2>&1
 echo "launch list exit $?"
