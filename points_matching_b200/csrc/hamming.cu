@@ -11,7 +11,9 @@
 // network -- keys are unique, so the lowest train index wins ties exactly like OpenCV.
 // Train rows are split into chunks across blockIdx.y; a finalize kernel merges the
 // per-chunk (best, second) pairs.
+#include <cuda_bf16.h>
 #include "pm_internal.h"
+#include "l2_common.h"
 
 namespace {
 
@@ -221,6 +223,162 @@ __global__ void ham_finalize_kernel(const unsigned long long *__restrict__ part,
     }
 }
 
+// =====================================================================================
+// Tensor-core Hamming.  For 0/1 vectors ||a - b||^2 IS the Hamming distance, so K2
+// (l2_tc.cu) runs unchanged on E4M3 operands: bits are expanded to bytes (query 1.0 = 0x38, train
+// -2.0 = 0xC0), ||b||^2 = popc(b) rides in the norm step, everything is an exact small integer.
+// The POPC kernel above is pinned at its pipe limits (ncu r1c: ALU 89%, XU 68%); this path is bound by
+// K2's MMA rate instead.  Rows of up to 256 bits.
+// =====================================================================================
+constexpr int HT_W = 8;          // words per row (256 bits)
+
+// one warp per row: lane l expands byte l of the row into 8 operand bytes
+__global__ void __launch_bounds__(256)
+ham_expand_kernel(const uint32_t *__restrict__ q, int nq, int mq_pad, const uint32_t *__restrict__ t, int nt, int nt_pad,
+                  uint8_t *__restrict__ qx, uint8_t *__restrict__ tx, float *__restrict__ qnorm, uint8_t *__restrict__ text,
+                  L2Flags *flags, L2Cand *__restrict__ part, int part_per_row)
+{
+    pm_pdl_prologue();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int total = mq_pad + nt_pad, stride = gridDim.x * (blockDim.x >> 5);
+    for (int grow = blockIdx.x * (blockDim.x >> 5) + warp; grow < total; grow += stride) {
+        const bool is_train = grow >= mq_pad;
+        const int row = is_train ? grow - mq_pad : grow;
+        const int n = is_train ? nt : nq;
+        uint32_t w = 0u;
+        if (row < n && lane < HT_W) w = (is_train ? t : q)[(size_t)row * HT_W + lane];
+        int pc = __popc(w);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
+        pc = __shfl_sync(0xffffffffu, pc, 0);
+        const uint32_t word = __shfl_sync(0xffffffffu, w, lane >> 2);
+        const uint32_t byte = (word >> (8 * (lane & 3))) & 0xFFu;
+        const uint32_t one = is_train ? 0xC0u : 0x38u;                 // E4M3 -2.0 / 1.0
+        uint32_t lo = 0u, hi = 0u;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            lo |= ((byte >> b) & 1u) ? one << (8 * b) : 0u;
+            hi |= ((byte >> (b + 4)) & 1u) ? one << (8 * b) : 0u;
+        }
+        reinterpret_cast<uint2 *>((is_train ? tx : qx) + (size_t)row * L2_PACK_COLS)[lane] = make_uint2(lo, hi);
+        if (is_train) {
+            if (lane < 2) {
+                const uint4 s3 = bf16_split3(row < n ? (float)pc : __uint_as_float(L2_PAD_NORM_BITS));
+                uint8_t *e = text + (size_t)(row >> 7) * L2_EXT_BYTES + ext_row_offset(row & 127) + lane * 128;
+                *reinterpret_cast<uint4 *>(e) = lane == 0 ? make_uint4(s3.x, s3.y | 0x3F800000u, 0x3F803F80u, 0u)
+                                                          : make_uint4(0u, 0u, 0u, 0u);
+            }
+        } else {
+            if (lane == 0) qnorm[row] = (float)pc;
+            for (int k = lane; k < part_per_row; k += 32) part[(size_t)row * part_per_row + k] = L2Cand{L2_INF, -1};
+        }
+    }
+    // integer data with tiny norms: K2 / the finish kernel run in exact mode
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        flags->nonexact = 0;
+        flags->max_tnorm_bits = __float_as_uint(256.f);
+        flags->max_qnorm_bits = __float_as_uint(256.f);
+    }
+}
+
+// 8 lanes per query row: merge K2's quad candidates, recompute the 8 columns of the two best quads with
+// popc on the raw rows (lane s owns word s), top-2 by (distance, index).  mode 0: DMatch rows; mode 1:
+// packed column minimum float_bits(dist) << 32 | (index + base) for the cross-check exchange.
+__global__ void __launch_bounds__(256)
+ham_tc_finish_kernel(const L2Cand *__restrict__ part, int ncand, const uint32_t *__restrict__ q, const uint32_t *__restrict__ t,
+                     int nq, int nt, L2Flags *flags_next, int q_index_base, int mode, pm_dmatch *__restrict__ out,
+                     unsigned long long *__restrict__ col_best)
+{
+    pm_pdl_prologue();
+    const int lane = threadIdx.x & 31, sub = lane & 7;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *flags_next = L2Flags{0, 0u, 0u, 0, 0u, {0, 0, 0}};
+    const int ngroups = gridDim.x * (blockDim.x >> 3);
+    const int nq_round = (nq + 3) & ~3;
+    for (int i = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); i < nq_round; i += ngroups) {
+        const bool live_row = i < nq;
+        const int ir = live_row ? i : nq - 1;
+        const L2Cand *prow = part + (size_t)ir * ncand;
+        L2Cand ca = L2Cand{L2_INF, -1}, cb = L2Cand{L2_INF, -1};
+        if (sub < ncand) ca = prow[sub];
+        if (sub + 8 < ncand) cb = prow[sub + 8];
+        const uint32_t aw = q[(size_t)ir * HT_W + sub];
+        const unsigned long long ka = cand_key(ca, nt), kb = cand_key(cb, nt);
+        unsigned long long h0 = min_u64(ka, kb), h1 = max_u64(ka, kb), h2 = ~0ull;
+        for (int c0 = sub + 16; c0 < ncand; c0 += 8) {
+            const unsigned long long key = cand_key(prow[c0], nt);
+            h2 = min_u64(h2, max_u64(h1, key));
+            h1 = min_u64(max_u64(h0, key), h1);
+            h0 = min_u64(h0, key);
+        }
+        unsigned long long k[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            k[r] = group_min_u64(0u, h0);
+            const bool pop = h0 == k[r] && h0 != ~0ull;
+            h0 = pop ? h1 : h0; h1 = pop ? h2 : h1; h2 = pop ? ~0ull : h2;
+        }
+        const int cand = sub >> 2, mem = sub & 3;
+        const bool live0 = k[0] != ~0ull, live1 = k[1] != ~0ull;
+        const int jq0 = live0 ? (int)(k[0] & 0xFFFFFFFFu) : 0, jq1 = live1 ? (int)(k[1] & 0xFFFFFFFFu) : 0;
+        const int my_col = (cand ? jq1 : jq0) + mem;
+        unsigned dots[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int col = (c >> 2 ? jq1 : jq0) + (c & 3);
+            dots[c] = (unsigned)__popc(aw ^ __ldg(t + (size_t)min(col, nt - 1) * HT_W + sub));
+        }
+        const unsigned my_d = group_transpose_sum(dots, sub);
+        const bool mine = (cand ? live1 : live0) && my_col < nt;
+        unsigned long long key = mine ? (((unsigned long long)__float_as_uint((float)my_d) << 32) | (unsigned)my_col) : ~0ull;
+        const unsigned long long w0 = group_min_u64(0u, key);
+        key = key == w0 ? ~0ull : key;
+        const unsigned long long w1 = group_min_u64(0u, key);
+        if (!live_row) continue;
+        if (mode == 0) {
+            if (sub < 2) {
+                const unsigned long long w = sub == 0 ? w0 : w1;
+                reinterpret_cast<uint4 *>(out + (size_t)i * 2)[sub] =
+                    w == ~0ull ? make_uint4((unsigned)(i + q_index_base), 0xFFFFFFFFu, 0u, __float_as_uint(3.402823466e+38f))
+                               : make_uint4((unsigned)(i + q_index_base), (unsigned)(w & 0xFFFFFFFFull), 0u, (unsigned)(w >> 32));
+            }
+        } else if (sub == 0) {
+            // here the "query" rows are the train set and the neighbours are query indices of this shard
+            col_best[i] = w0 == ~0ull ? ~0ull : ((w0 & 0xFFFFFFFF00000000ull) | (unsigned)((int)(w0 & 0xFFFFFFFFull) + q_index_base));
+        }
+    }
+}
+
+static int g_ham_path = 0;       // 0 auto, 1 POPC kernel, 2 tensor-core kernel (debug / bench switch)
+
+int ham_tc_run(pm_ctx *ctx, const uint32_t *pq, int nq, const uint32_t *pt, int nt, int q_index_base, int mode,
+               pm_dmatch *dout, uint64_t *dcol)
+{
+    const int mq_pad = pm_round_up(nq, 256), nt_pad = pm_round_up(nt, 256);
+    const int MT = mq_pad / 256, NT = nt_pad / 128;
+    const int smax = l2_tc_smax(ctx, MT, NT);
+    const bool fresh_flags = ctx->slot_ptr[WS_L2_FLAGS] == nullptr;
+    PM_WS(ctx, flags2, L2Flags *, WS_L2_FLAGS, 3 * sizeof(L2Flags));
+    if (fresh_flags) { PM_CUDA(ctx, cudaMemsetAsync(flags2, 0, 3 * sizeof(L2Flags), ctx->stream)); ctx->l2_parity = 0; }
+    L2Flags *flags = flags2 + ctx->l2_parity, *flags_next = flags2 + (ctx->l2_parity ^ 1);
+    PM_WS(ctx, qx, uint8_t *, WS_Q_PACK, (size_t)mq_pad * L2_PACK_COLS);
+    PM_WS(ctx, tx, uint8_t *, WS_T_PACK, (size_t)nt_pad * L2_PACK_COLS);
+    PM_WS(ctx, qnorm, float *, WS_Q_NORM, (size_t)mq_pad * 4);
+    PM_WS(ctx, text, uint8_t *, WS_T_NORM, (size_t)(nt_pad / 128) * L2_EXT_BYTES);
+    PM_WS(ctx, part, L2Cand *, WS_L2_PART, (size_t)mq_pad * smax * 3 * sizeof(L2Cand));
+    const int xblocks = min(pm_cdiv(mq_pad + nt_pad, 8), 8 * ctx->num_sms);
+    PM_CUDA(ctx, pm_launch_pdl(ham_expand_kernel, dim3(xblocks), dim3(256), 0, ctx->stream, pq, nq, mq_pad, pt, nt, nt_pad, qx, tx,
+                               qnorm, text, flags, part, smax * 3));
+    PM_CHECK_LAUNCH(ctx);
+    int st = l2_tc_launch(ctx, qx, mq_pad, tx, nt_pad, text, flags, part, smax, pm_l2_dump_ptr(), 1);
+    if (st != PM_OK) return st;
+    const int fblocks = min(pm_cdiv(nq, 32), 4 * ctx->num_sms);
+    PM_CUDA(ctx, pm_launch_pdl(ham_tc_finish_kernel, dim3(fblocks), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3, pq, pt,
+                               nq, nt, flags_next, q_index_base, mode, dout, (unsigned long long *)dcol));
+    PM_CHECK_LAUNCH(ctx);
+    ctx->l2_parity ^= 1;
+    return PM_OK;
+}
+
 int padded_words(int bytes)
 {
     int w = (bytes + 3) / 4;
@@ -248,12 +406,16 @@ int ham_run(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, i
             int q_index_base, int mode, pm_dmatch *dout, uint64_t *dcol)
 {
     if (nq <= 0) return PM_OK;
-    const int W = padded_words(bytes);
+    // tensor-core path: rows of up to 256 bits and enough pairs to fill the persistent GEMM
+    const bool tc_ok = bytes <= 4 * HT_W && nt > 0;
+    const bool use_tc = tc_ok && (g_ham_path == 2 || (g_ham_path == 0 && (long long)nq * nt >= (1ll << 22)));
+    const int W = use_tc ? HT_W : padded_words(bytes);
     const uint32_t *pq, *pt;
     int st;
     if ((st = ham_prepare(ctx, dq, nq, bytes, W, WS_HAM_Q, &pq)) != PM_OK) return st;
     if ((st = ham_prepare(ctx, dt, nt, bytes, W, WS_HAM_T, &pt)) != PM_OK) return st;
 
+    if (use_tc) return ham_tc_run(ctx, pq, nq, pt, nt, q_index_base, mode, dout, dcol);
     const bool fast = (W == 4 || W == 8 || W == 16);
     const int qblocks = fast ? pm_cdiv(nq, HAM_THREADS * HAM_QPT) : pm_cdiv(nq, 128);
     // One resident wave: as many CTAs as the GPU holds at once (occupancy x SMs), so every SM carries the
@@ -286,6 +448,9 @@ int ham_run(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, i
 }
 
 }  // namespace
+
+// Debug / bench switch: 0 auto (tensor cores for large problems), 1 force the POPC kernel, 2 force tensor cores.
+extern "C" void pm_debug_hamming_path(int path) { g_ham_path = path; }
 
 int pmk_hamming_knn2(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, int bytes,
                      int q_index_base, pm_dmatch *dout)

@@ -159,27 +159,6 @@ l2_pack_kernel(const T *__restrict__ q, int nq, int mq_pad, const T *__restrict_
     pm_span_mark(span, 2, true);
 }
 
-// order-preserving float -> uint map (handles negatives; t = ||b||^2 - 2ab can be < 0)
-__device__ __forceinline__ unsigned f2ord(float f)
-{
-    const unsigned b = __float_as_uint(f);
-    return b ^ ((unsigned)((int)b >> 31) | 0x80000000u);
-}
-__device__ __forceinline__ float ord2f(unsigned u)
-{
-    const unsigned b = (u & 0x80000000u) ? (u ^ 0x80000000u) : ~u;
-    return __uint_as_float(b);
-}
-__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long k)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long y = __shfl_xor_sync(0xffffffffu, k, o);
-        k = y < k ? y : k;
-    }
-    return k;
-}
-
 // exact FP32 squared distance between the query chunk held in registers (dim <= 128) and a train row
 template <typename T>
 __device__ __forceinline__ float warp_l2sq_regs(const float (&a)[4], const T *__restrict__ b, int dim, int lane)
@@ -248,36 +227,6 @@ __device__ void l2_exact_row(const T *__restrict__ q, const T *__restrict__ t, i
 }
 
 // ---- K3 works in groups of 8 lanes per query row (4 rows per warp) ----
-// group (8 aligned lanes) minimum of 64-bit keys.  Full-mask xor butterflies stay inside the group; a
-// redux.sync with a sub-warp mask is serialised per group by the compiler (4 passes + a convergence loop).
-__device__ __forceinline__ unsigned long long group_min_u64(unsigned, unsigned long long k)
-{
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-        const unsigned long long y = __shfl_xor_sync(0xffffffffu, k, o);
-        k = y < k ? y : k;
-    }
-    return k;
-}
-// Each of the 8 lanes of a group holds partial sums v[0..7]; returns sum over the group's lanes of v[sub]
-// (lane `sub` ends up with candidate `sub`): a transposing reduction, 4 + 2 + 1 shuffles instead of 8 x 3.
-__device__ __forceinline__ unsigned group_transpose_sum(unsigned (&v)[8], int sub)
-{
-    unsigned w[4], u[2];
-    const bool b4 = (sub & 4) != 0, b2 = (sub & 2) != 0, b1 = (sub & 1) != 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const unsigned keep = b4 ? v[i + 4] : v[i], send = b4 ? v[i] : v[i + 4];
-        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const unsigned keep = b2 ? w[i + 2] : w[i], send = b2 ? w[i] : w[i + 2];
-        u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    const unsigned keep = b1 ? u[1] : u[0], send = b1 ? u[0] : u[1];
-    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
-}
 // A 128-wide row held by 8 lanes: lane s keeps the float4 chunks s, s+8, s+16, s+24, i.e. the elements
 // that "virtual lanes" l = s + 8e of the 32-lane re-rank order own.
 __device__ __forceinline__ void load_row8(const float *p, int sub, int dim, bool vec, float (&v)[4][4])
@@ -326,14 +275,6 @@ __device__ __forceinline__ float group_l2sq(unsigned gmask, const float (&a)[4][
     r += __shfl_xor_sync(0xffffffffu, r, 1);
     return r;
 }
-
-__device__ __forceinline__ unsigned long long cand_key(const L2Cand c, int nt)
-{
-    const bool ok = c.idx >= 0 && c.idx < nt;                 // absent, or a pad column / pad quad
-    return ok ? (((unsigned long long)f2ord(c.d) << 32) | (unsigned)c.idx) : ~0ull;
-}
-__device__ __forceinline__ unsigned long long min_u64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
-__device__ __forceinline__ unsigned long long max_u64(unsigned long long a, unsigned long long b) { return a < b ? b : a; }
 
 template <typename T>
 __global__ void __launch_bounds__(256, 3)
@@ -529,6 +470,7 @@ int run_exact(pm_ctx *ctx, const T *dq, const T *dt, int nq, int nt, int dim, in
 // Debug hook (tools/gpu_debug.py): dump of (||b||^2 - 2ab) from the tensor-core kernel.
 static float *g_l2_dump = nullptr;
 extern "C" void pm_debug_set_l2_dump(float *ddump) { g_l2_dump = ddump; }
+float *pm_l2_dump_ptr() { return g_l2_dump; }
 // Force the exact FP32 kernel for every row (parity cross-check of the two paths).
 static int g_l2_force_exact = 0;
 extern "C" void pm_debug_force_exact(int on) { g_l2_force_exact = on; }
@@ -597,7 +539,7 @@ int pmk_l2_knn2_phase(pm_ctx *ctx, const void *dq, int nq, const void *dt, int n
                                    (const float *)dt, pack_nt, pack_nt_pad, dim, vec, qpack, tpack, qnorm, text, q8, t8, tnormf, flags, part, smax * 3,
                                    tflags_in, g_pm_span));
     PM_CHECK_LAUNCH(ctx);
-    int st = l2_tc_launch(ctx, qpack, mq_pad, tpack, nt_pad, text, flags, part, smax, g_l2_dump);
+    int st = l2_tc_launch(ctx, qpack, mq_pad, tpack, nt_pad, text, flags, part, smax, g_l2_dump, 0);
     if (st != PM_OK) return st;
     if (is_u8)
         PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<uint8_t>, dim3(fin_blocks), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,

@@ -62,8 +62,75 @@ static __device__ __forceinline__ uint4 bf16_split3(float v)
 }
 #endif
 
+#ifdef __CUDACC__
+#ifndef L2_INF
+#define L2_INF __int_as_float(0x7f800000)
+#endif
+// ---- helpers shared by the finish kernels (l2.cu, hamming.cu) ----
+// order-preserving float -> uint map (handles negatives; t = ||b||^2 - 2ab can be < 0)
+static __device__ __forceinline__ unsigned f2ord(float f)
+{
+    const unsigned b = __float_as_uint(f);
+    return b ^ ((unsigned)((int)b >> 31) | 0x80000000u);
+}
+static __device__ __forceinline__ float ord2f(unsigned u)
+{
+    const unsigned b = (u & 0x80000000u) ? (u ^ 0x80000000u) : ~u;
+    return __uint_as_float(b);
+}
+static __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long k)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long y = __shfl_xor_sync(0xffffffffu, k, o);
+        k = y < k ? y : k;
+    }
+    return k;
+}
+
+// group (8 aligned lanes) minimum of 64-bit keys.  Full-mask xor butterflies stay inside the group; a
+// redux.sync with a sub-warp mask is serialised per group by the compiler (4 passes + a convergence loop).
+static __device__ __forceinline__ unsigned long long group_min_u64(unsigned, unsigned long long k)
+{
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        const unsigned long long y = __shfl_xor_sync(0xffffffffu, k, o);
+        k = y < k ? y : k;
+    }
+    return k;
+}
+// Each of the 8 lanes of a group holds partial sums v[0..7]; returns sum over the group's lanes of v[sub]
+// (lane `sub` ends up with candidate `sub`): a transposing reduction, 4 + 2 + 1 shuffles instead of 8 x 3.
+static __device__ __forceinline__ unsigned group_transpose_sum(unsigned (&v)[8], int sub)
+{
+    unsigned w[4], u[2];
+    const bool b4 = (sub & 4) != 0, b2 = (sub & 2) != 0, b1 = (sub & 1) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const unsigned keep = b4 ? v[i + 4] : v[i], send = b4 ? v[i] : v[i + 4];
+        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const unsigned keep = b2 ? w[i + 2] : w[i], send = b2 ? w[i] : w[i + 2];
+        u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    const unsigned keep = b1 ? u[1] : u[0], send = b1 ? u[0] : u[1];
+    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+static __device__ __forceinline__ unsigned long long cand_key(const L2Cand c, int nt)
+{
+    const bool ok = c.idx >= 0 && c.idx < nt;                 // absent, or a pad column / pad quad
+    return ok ? (((unsigned long long)f2ord(c.d) << 32) | (unsigned)c.idx) : ~0ull;
+}
+static __device__ __forceinline__ unsigned long long min_u64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+static __device__ __forceinline__ unsigned long long max_u64(unsigned long long a, unsigned long long b) { return a < b ? b : a; }
+
+#endif
+
 struct pm_ctx;
+float *pm_l2_dump_ptr();      // debug: K2 dumps its (||b||^2 - 2ab) tile values here when set
 int l2_tc_grid(pm_ctx *ctx, int MT, int NT);
 int l2_tc_smax(pm_ctx *ctx, int MT, int NT);
 int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, int nt_pad,
-                 const void *text, const L2Flags *flags, L2Cand *part, int smax, float *dump);
+                 const void *text, const L2Flags *flags, L2Cand *part, int smax, float *dump, int fp8);

@@ -118,6 +118,16 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// kind::f8f6f4, A = B = E4M3 (format code 0), D = F32: the Hamming path feeds 0/1 (and 0/-2) bytes, K = 32 per instruction
+constexpr uint32_t IDESC_E4M3 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__device__ __forceinline__ void umma_e4m3(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
 {
     asm volatile(
@@ -292,6 +302,10 @@ struct TcParams {
 #define TRK(slot) do { } while (0)
 #endif
 
+// FP8 = false: bf16 hi|lo operands (L2, K = 128 per stage).  FP8 = true: E4M3 0/1 operands, 256 per row
+// (binary descriptors expanded by hamming.cu: ||a-b||^2 of 0/1 vectors IS the Hamming distance), always
+// exact mode; the two 128-byte k-blocks of a stage then hold K = 256.
+template <bool FP8>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t, TcParams P)
 {
@@ -373,7 +387,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                         mbar_expect_tx(bar_afull, (uint32_t)(MH * nablk * BLK_BYTES));
                         for (int h = 0; h < MH; ++h)
                             for (int kb = 0; kb < nablk; ++kb)
-                                tma_load_2d(sA + (h * nablk + kb) * BLK_BYTES, &tmap_q, bar_afull, kb * BK, (m * MH + h) * BM);
+                                tma_load_2d(sA + (h * nablk + kb) * BLK_BYTES, &tmap_q, bar_afull, kb * (FP8 ? 2 * BK : BK), (m * MH + h) * BM);
                     }
                     __syncwarp();
                     cur_m = m;
@@ -386,7 +400,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                         // stages: hi0 hi1 (+ norm image) | lo0 lo1 | hi0 hi1   (packed row = [hi 0..127 | lo 128..255])
                         const int kc = sp == 1 ? 128 : 0;
                         tma_load_2d(dst, &tmap_t, fb, kc, n * BN);
-                        tma_load_2d(dst + BLK_BYTES, &tmap_t, fb, kc + BK, n * BN);
+                        tma_load_2d(dst + BLK_BYTES, &tmap_t, fb, kc + (FP8 ? 2 * BK : BK), n * BN);
                         if (sp == 0) bulk_load_1d(dst + 2 * BLK_BYTES, P.text + (size_t)n * EXT_BYTES, EXT_BYTES, fb);
                     }
                     __syncwarp();
@@ -421,8 +435,10 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                 for (int h = 0; h < MH; ++h) {      // the same B k-block feeds both A tiles
                     const uint64_t adesc = make_sdesc(sA + (h * nablk + ablk) * BLK_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)   // +32 B per K=16 step inside the swizzle span
-                        umma_bf16(d_tmem + h * BN, adesc + 2 * k, bdesc + 2 * k, IDESC, 1u);
+                    for (int k = 0; k < BK / 16; ++k) { // +32 B per MMA (K=16 bf16 / K=32 e4m3) inside the swizzle span
+                        if (FP8) umma_e4m3(d_tmem + h * BN, adesc + 2 * k, bdesc + 2 * k, IDESC_E4M3, 1u);
+                        else umma_bf16(d_tmem + h * BN, adesc + 2 * k, bdesc + 2 * k, IDESC, 1u);
+                    }
                 }
             }
         };
@@ -568,7 +584,7 @@ typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_
                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_tmap(pm_ctx *ctx, CUtensorMap *tm, const void *base, int rows_pad, int box_rows)
+int make_tmap(pm_ctx *ctx, CUtensorMap *tm, const void *base, int rows_pad, int box_rows, int fp8)
 {
     if (!ctx->tmap_encode) {
         cudaDriverEntryPointQueryResult qres;
@@ -578,11 +594,12 @@ int make_tmap(pm_ctx *ctx, CUtensorMap *tm, const void *base, int rows_pad, int 
             return pm_fail(ctx, PM_CUDA_ERR, "cuTensorMapEncodeTiled entry point not found");
         ctx->tmap_encode = fn;
     }
+    // bf16: rows of 256 elements (hi|lo), boxes of 64; e4m3: rows of 256 bytes, boxes of 128 -- 128-byte spans either way
     cuuint64_t dims[2] = {(cuuint64_t)L2_PACK_COLS, (cuuint64_t)rows_pad};
-    cuuint64_t strides[1] = {(cuuint64_t)L2_PACK_COLS * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)L2_PACK_COLS * (fp8 ? 1 : 2)};
+    cuuint32_t box[2] = {(cuuint32_t)(fp8 ? 2 * BK : BK), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = ((tmap_encode_fn)ctx->tmap_encode)(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base),
+    CUresult r = ((tmap_encode_fn)ctx->tmap_encode)(tm, fp8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base),
                                                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -618,11 +635,12 @@ int l2_tc_smax(pm_ctx *ctx, int MT, int NT)
 }
 
 int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, int nt_pad,
-                 const void *text, const L2Flags *flags, L2Cand *part, int smax, float *dump)
+                 const void *text, const L2Flags *flags, L2Cand *part, int smax, float *dump, int fp8)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        PM_CUDA(ctx, cudaFuncSetAttribute(l2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        PM_CUDA(ctx, cudaFuncSetAttribute(l2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        PM_CUDA(ctx, cudaFuncSetAttribute(l2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
         attr_set = true;
     }
     static_assert(sizeof(CUtensorMap) == 128, "tmap_store size");
@@ -630,10 +648,10 @@ int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, 
     const void *bases[2] = {qpack, tpack};
     const int rows[2] = {mq_pad, nt_pad}, boxes[2] = {BM, BN};
     for (int k = 0; k < 2; ++k)
-        if (ctx->tmap_base[k] != bases[k] || ctx->tmap_rows[k] != rows[k]) {   // re-encode only when the operand moved
-            int st = make_tmap(ctx, &tmaps[k], bases[k], rows[k], boxes[k]);
+        if (ctx->tmap_base[k] != bases[k] || ctx->tmap_rows[k] != rows[k] || ctx->tmap_fp8[k] != fp8) {   // re-encode only when the operand moved
+            int st = make_tmap(ctx, &tmaps[k], bases[k], rows[k], boxes[k], fp8);
             if (st != PM_OK) return st;
-            ctx->tmap_base[k] = bases[k]; ctx->tmap_rows[k] = rows[k];
+            ctx->tmap_base[k] = bases[k]; ctx->tmap_rows[k] = rows[k]; ctx->tmap_fp8[k] = fp8;
         }
     const CUtensorMap &tq = tmaps[0], &tt = tmaps[1];
     TcParams P;
@@ -644,8 +662,9 @@ int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, 
     const int G = l2_tc_grid(ctx, P.MT, P.NT);
     P.tq = (P.MT * P.NT) / G; P.tr = (P.MT * P.NT) % G;
     {
-        pm_prof_scope prof(ctx, 0);
-        cudaError_t le = pm_launch_pdl(l2_tc_kernel, dim3(G), dim3(TC_THREADS), (size_t)SMEM_TOTAL, ctx->stream, tq, tt, P);
+        pm_prof_scope prof(ctx, fp8 ? 1 : 0);       // profile class 1 = the Hamming matching kernel
+        cudaError_t le = fp8 ? pm_launch_pdl(l2_tc_kernel<true>, dim3(G), dim3(TC_THREADS), (size_t)SMEM_TOTAL, ctx->stream, tq, tt, P)
+                             : pm_launch_pdl(l2_tc_kernel<false>, dim3(G), dim3(TC_THREADS), (size_t)SMEM_TOTAL, ctx->stream, tq, tt, P);
         if (le != cudaSuccess) return pm_fail(ctx, PM_CUDA_ERR, "l2_tc_kernel launch: %s", cudaGetErrorString(le));
     }
     PM_CHECK_LAUNCH(ctx);

@@ -20,6 +20,7 @@ enum pm_slot {
     WS_KNN, WS_KNN2, WS_IDX, WS_KP, WS_LINES,
     WS_Q_U8, WS_T_U8, WS_T_NORMF
 };
+static_assert(WS_T_NORMF < PM_NSLOTS, "workspace slots");
 
 struct pm_ctx {
     int device = 0;
@@ -38,6 +39,7 @@ struct pm_ctx {
     alignas(64) unsigned char tmap_store[2][128] = {};
     const void *tmap_base[2] = {nullptr, nullptr};
     int tmap_rows[2] = {0, 0};
+    int tmap_fp8[2] = {-1, -1};
     int32_t *h_pinned = nullptr;   // 4 KB pinned scratch for small D2H reads
     // chunked host path (pm_api.cu): uploads run on their own stream, one event per query chunk
     cudaStream_t copy_stream = nullptr;

@@ -489,3 +489,28 @@ def test_lmeds_scoring_bit_exact_and_end_to_end(ctx, pm, orc):
     F2, mask2 = pm.findFundamentalMat(p1, p2, pm.FM_7POINT, ctx=ctx)
     assert F2 is not None and mask2[gt].mean() > 0.85 and mask2[~gt].mean() < 0.15
     assert ctx.find_fundamental_lmeds(p1[:7], p2[:7], n_hyp=4) is None
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_hamming_both_kernels_bit_exact(ctx, pm, orc, path):
+    """The POPC kernel (path 1, the north_star's named design) and the tensor-core kernel (path 2: bits expanded
+    to E4M3 0/1 operands, K2's GEMM + fused top-k) give the oracle's matches bit for bit, ragged sizes, ties,
+    short rows and the cross-check included."""
+    from points_matching_b200 import _lib
+    L = _lib.lib()
+    L.pm_debug_hamming_path(path)
+    try:
+        for nq, nt, nb, seed in ((1, 1, 32, 1), (257, 300, 32, 2), (1000, 2049, 32, 3), (700, 513, 16, 4), (300, 200, 5, 5),
+                                 (3000, 5000, 32, 6)):
+            q, t = synth.orb_pair(nq, nt, seed=seed, nbytes=nb)
+            if seed == 3:                       # forced ties: duplicate train rows and a duplicated query
+                t[100:140] = t[60:100]
+                q[5] = t[60]
+            knn = ctx.knn2(q, t, pm.NORM_HAMMING)
+            ref = orc.knn2_hamming(q, t)
+            _same_knn(knn, ref)
+            x = ctx.match_cross(q, t, pm.NORM_HAMMING)
+            xr = orc.cross_check(ref, orc.col_best_hamming(q, t))
+            assert np.array_equal(x, xr)
+    finally:
+        L.pm_debug_hamming_path(0)

@@ -19,7 +19,15 @@ def show_bench(path):
         print('ransac %.3e hyp/s ms %.2f e2e %.3e k7_ms %.2f frac %.3f inl %s' % (s['value'], s['ms_per_step'], s['e2e']['value'], s['roofline']['kernel_ms'], s['roofline']['frac'], s['config']['winner_inliers']), s.get('cpu_baseline', {}).get('value'))
     x = (d.get('extra') or {}).get('hamming')
     if x:
-        print('hamming step ms %.3f kernel ms %.3f pairs/s(kernel) %.3e frac_popc %.3f mutual %d' % (x['ms_per_step'], x['kernel_ms'], x['pairs_per_s_knn_kernel'], x['roofline']['frac'], x['mutual_matches']))
+        for k in ('popc', 'tensor'):
+            if k in x:
+                y = x[k]
+                print('hamming[%s] step ms %.3f kernel ms %.3f pairs/s(kernel) %.3e frac %.3f mutual %d' % (k, y['ms_per_step'], y['kernel_ms'], y['pairs_per_s_knn_kernel'], y['roofline']['frac'], y['mutual_matches']))
+        if 'popc' not in x:
+            print('hamming step ms %.3f kernel ms %.3f pairs/s(kernel) %.3e frac %.3f mutual %d' % (x['ms_per_step'], x['kernel_ms'], x['pairs_per_s_knn_kernel'], x['roofline']['frac'], x['mutual_matches']))
+    c5 = (d.get('extra') or {}).get('cfg5')
+    if c5:
+        print('cfg5 %.1f image pairs/s (%.3f ms/pair) last %s' % (c5['image_pairs_per_s'], c5['ms_per_pair'], c5['last_pair']))
 
 
 def show_launches(path):
