@@ -382,20 +382,30 @@ def bench_hamming(ctx, torch, dev, world, rank, stream, barrier, peaks):
     import points_matching_b200 as pm   # noqa: F401
     from points_matching_b200 import _lib, synth
     nq, nt = 12500, 100000
-    q, t = synth.orb_pair(nq, nt, seed=4321 + rank)
+    qall, t = synth.orb_pair(nq * world, nt, seed=4321)          # train set replicated, query rows sharded
+    q = np.ascontiguousarray(qall[rank * nq:(rank + 1) * nq])
     dq, dt_ = torch.from_numpy(q).to(dev), torch.from_numpy(t).to(dev)
     knn = torch.zeros((nq, 2, 4), dtype=torch.int32, device=dev)
     col = torch.zeros(nt, dtype=torch.int64, device=dev)
     out = torch.zeros((nq, 4), dtype=torch.int32, device=dev)
     cnt = torch.zeros(4, dtype=torch.int32, device=dev)
 
+    i64max = torch.iinfo(torch.int64).max
+
     def step():
         ctx.knn2_hamming_dev(dq.data_ptr(), nq, dt_.data_ptr(), nt, 32, knn.data_ptr(), rank * nq)
         ctx.col_best_hamming_dev(dq.data_ptr(), nq, dt_.data_ptr(), nt, 32, col.data_ptr(), rank * nq)
+        if world > 1:
+            # the one exchange of the sharded cross-check: min over ranks of the packed column minima
+            import torch.distributed as dist
+            col.copy_(torch.where(col < 0, torch.full_like(col, i64max), col))
+            dist.all_reduce(col, op=dist.ReduceOp.MIN)
+            col.copy_(torch.where(col == i64max, torch.full_like(col, -1), col))
         ctx.cross_check_dev(knn.data_ptr(), nq, 2, col.data_ptr(), nt, out.data_ptr(), cnt.data_ptr())
 
     pairs = float(nq) * nt
-    res = {"workload": "cfg3 shard: ORB-like 256-bit, 12500 x 100000, kNN-2 + column minima + cross-check"}
+    res = {"workload": "cfg3 shard: ORB-like 256-bit, 12500 query rows per rank x 100000 train rows, kNN-2 + column minima "
+                       "+ (N > 1: all_reduce(MIN) of the 800 KB packed column minima) + cross-check"}
     for name, path in (("popc", 1), ("tensor", 2)):
         _lib.lib().pm_debug_hamming_path(path)
         for _ in range(2):

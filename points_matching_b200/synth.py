@@ -66,12 +66,12 @@ def orb_pair(nq, nt, seed=4321, planted=0.5, nbytes=32):
     if k > 0:
         qi = rng.permutation(nq)[:k]
         ti = rng.permutation(nt)[:k]
-        rows = q[qi].copy()
         nbits = nbytes * 8
-        for r in range(k):
-            flips = rng.choice(nbits, size=int(rng.integers(16, 41)), replace=False)
-            for b in flips:
-                rows[r, b >> 3] ^= np.uint8(1 << (b & 7))
+        nflip = rng.integers(16, 41, size=k)
+        order = np.argsort(rng.random((k, nbits)), axis=1)              # a random permutation of the bit positions per row
+        flip = np.zeros((k, nbits), dtype=np.uint8)
+        np.put_along_axis(flip, order, (np.arange(nbits)[None, :] < nflip[:, None]).astype(np.uint8), axis=1)
+        rows = q[qi] ^ np.packbits(flip, axis=1, bitorder="little")
         t[ti] = rows
     return q, t
 
