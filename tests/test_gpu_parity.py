@@ -514,3 +514,29 @@ def test_hamming_both_kernels_bit_exact(ctx, pm, orc, path):
             assert np.array_equal(x, xr)
     finally:
         L.pm_debug_hamming_path(0)
+
+
+def test_device_engine_sharded_api_single_rank(pm, orc):
+    """points_matching_b200/sharded.py with the product engine (libpm on CUDA tensors) at world size 1: the same
+    answers as the host calls / the oracle (the multi-rank protocol itself is covered over gloo on CPU)."""
+    import torch
+    from points_matching_b200 import sharded
+    ctx = pm.Context(0)
+    eng = sharded.DeviceEngine(ctx, "cuda:0")
+    q, t = synth.sift_pair(900, 1100, seed=31)
+    m = sharded.ShardedMatcher(eng, pm.NORM_L2)
+    knn = m.knn2(eng.tensor(q), eng.tensor(t)).cpu().numpy().view(pm.DMATCH).reshape(900, 2)
+    _same_knn(knn, orc.knn2_l2(q, t))
+    qb, tb = synth.orb_pair(800, 2100, seed=32)
+    mh = sharded.ShardedMatcher(eng, pm.NORM_HAMMING)
+    x = mh.match_cross(eng.tensor(qb), eng.tensor(tb)).cpu().numpy().view(pm.DMATCH).reshape(-1)
+    ref = orc.knn2_hamming(qb, tb)
+    assert np.array_equal(x, orc.cross_check(ref, orc.col_best_hamming(qb, tb)))
+    p1, p2, gt = synth.correspondences(2000, seed=33)
+    idx = synth.sample_index_sets(2000, 512, 8, seed=34)
+    F, mask, ninl, winner = sharded.sharded_find_fundamental(eng, eng.tensor(p1), eng.tensor(p2), eng.tensor(idx), 8,
+                                                             pm.METRIC_SAMPSON, 1.0, True)
+    r = orc.ransac_f(p1, p2, idx, 0, 1.0, True)
+    assert winner == r["best_model"] and abs(ninl - r["n_inliers"]) <= 3
+    assert (mask.cpu().numpy() == r["mask"]).mean() > 0.998
+    ctx.close()
