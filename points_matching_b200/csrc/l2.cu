@@ -59,6 +59,30 @@ __device__ __forceinline__ void load_row4(const uint8_t *p, int lane, int dim, b
     }
 }
 
+// chunk e of a 128-wide row for lane `sub` of an 8-lane group: elements 4 * (sub + 8e) .. + 3
+__device__ __forceinline__ void load_chunk4(const float *p, int l, int dim, bool vec, float (&x)[4])
+{
+    if (vec) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(p) + l);
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) x[c] = 4 * l + c < dim ? __ldg(p + 4 * l + c) : 0.f;
+    }
+}
+__device__ __forceinline__ void load_chunk4(const uint8_t *p, int l, int dim, bool vec, float (&x)[4])
+{
+    if (vec) {
+        const uchar4 v = __ldg(reinterpret_cast<const uchar4 *>(p) + l);
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) x[c] = 4 * l + c < dim ? (float)__ldg(p + 4 * l + c) : 0.f;
+    }
+}
+
+// K1: 8 lanes per row (4 rows per warp: the per-row bookkeeping -- reduction, norm image, flags -- is
+// amortised over four rows; one warp per row was instruction bound at ~230 warp instructions per row).
 template <typename T>
 __global__ void __launch_bounds__(256)
 l2_pack_kernel(const T *__restrict__ q, int nq, int mq_pad, const T *__restrict__ t, int nt, int nt_pad, int dim,
@@ -72,73 +96,68 @@ l2_pack_kernel(const T *__restrict__ q, int nq, int mq_pad, const T *__restrict_
     pm_span_mark(span, 0, false);
     pm_pdl_prologue();
     pm_span_mark(span, 1, false);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 7;
     if (threadIdx.x == 0) s_nonint = 0;
     unsigned mx_q = 0u, mx_t = 0u;          // running max of the norm bits (norms are >= 0: bits order like floats)
     bool integral = true;
-    const int total = mq_pad + nt_pad, stride = gridDim.x * (blockDim.x >> 5);
-    constexpr int RU = 3;                    // rows per warp in flight: all loads of a pass are issued before any is used
-    for (int g0 = blockIdx.x * (blockDim.x >> 5) + warp; g0 < total; g0 += RU * stride) {
-        float xs[RU][4];
-#pragma unroll
-        for (int r = 0; r < RU; ++r) {
-            const int grow = g0 + r * stride;
-            xs[r][0] = xs[r][1] = xs[r][2] = xs[r][3] = 0.f;
-            if (grow < total) {
-                const bool is_train = grow >= mq_pad;
-                const int row = is_train ? grow - mq_pad : grow;
-                if (row < (is_train ? nt : nq)) load_row4((is_train ? t : q) + (size_t)row * dim, lane, dim, vec != 0, xs[r]);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < RU; ++r) {
-        const int grow = g0 + r * stride;
-        if (grow >= total) break;
+    // mq_pad and nt_pad are multiples of 4, so the four rows of a warp are all query rows or all train rows
+    const int total = mq_pad + nt_pad, stride = gridDim.x * (blockDim.x >> 3);
+    for (int grow = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); grow < total; grow += stride) {
         const bool is_train = grow >= mq_pad;
         const int row = is_train ? grow - mq_pad : grow;
         const int n = is_train ? nt : nq;
-        const float (&x)[4] = xs[r];
+        const bool live = row < n;
+        const T *src = (is_train ? t : q) + (size_t)(live ? row : 0) * dim;
+        float x[4][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            load_chunk4(src, sub + 8 * e, dim, vec != 0, x[e]);
+            if (!live) { x[e][0] = x[e][1] = x[e][2] = x[e][3] = 0.f; }
+        }
+        const float scale = is_train ? -2.f : 1.f;
+        __nv_bfloat16 *dst = (is_train ? tpack : qpack) + (size_t)row * L2_PACK_COLS;
+        unsigned *dst8 = reinterpret_cast<unsigned *>((is_train ? t8 : q8) + (size_t)row * L2_KDIM);
         float s = 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            s = fmaf(x[e], x[e], s);
-            integral = integral && (x[e] == rintf(x[e])) && x[e] >= 0.f && x[e] <= 255.f;
-        }
-        s = warp_sum_butterfly(s);
-        const float scale = is_train ? -2.f : 1.f;
-        __nv_bfloat16 hi[4], lo[4];
+            // byte copy for K3's exact-mode re-check; the row is "integral" (0..255 integers) iff the saturating
+            // conversion round-trips
+            unsigned ub[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float v = x[e] * scale;
-            hi[e] = __float2bfloat16_rn(v);
-            lo[e] = __float2bfloat16_rn(v - __bfloat162float(hi[e]));
-        }
-        __nv_bfloat16 *dst = (is_train ? tpack : qpack) + (size_t)row * L2_PACK_COLS;
-        *reinterpret_cast<uint2 *>(dst + 4 * lane) = *reinterpret_cast<uint2 *>(hi);
-        *reinterpret_cast<uint2 *>(dst + L2_KDIM + 4 * lane) = *reinterpret_cast<uint2 *>(lo);
-        {   // byte copy of the row for K3's exact-mode re-check (only meaningful when the data are 0..255 integers)
-            uchar4 b4;
-            b4.x = (unsigned char)__float2uint_rn(fminf(fmaxf(x[0], 0.f), 255.f));
-            b4.y = (unsigned char)__float2uint_rn(fminf(fmaxf(x[1], 0.f), 255.f));
-            b4.z = (unsigned char)__float2uint_rn(fminf(fmaxf(x[2], 0.f), 255.f));
-            b4.w = (unsigned char)__float2uint_rn(fminf(fmaxf(x[3], 0.f), 255.f));
-            reinterpret_cast<uchar4 *>((is_train ? t8 : q8) + (size_t)row * L2_KDIM)[lane] = b4;
-        }
-        if (is_train) {
-            if (lane == 2) tnorm[row] = row < n ? s : 0.f;
-            // K2's norm operand: [n_h n_m n_l 1 1 1 0 0 | 0 x 8] bf16 in the smem image of the row's column tile
-            if (lane < 2) {
-                const uint4 s3 = bf16_split3(row < n ? s : __uint_as_float(L2_PAD_NORM_BITS));
-                uint8_t *e = text + (size_t)(row >> 7) * L2_EXT_BYTES + ext_row_offset(row & 127) + lane * 128;
-                *reinterpret_cast<uint4 *>(e) = lane == 0 ? make_uint4(s3.x, s3.y | 0x3F800000u, 0x3F803F80u, 0u)
-                                                          : make_uint4(0u, 0u, 0u, 0u);
+            for (int c = 0; c < 4; ++c) {
+                s = fmaf(x[e][c], x[e][c], s);
+                ub[c] = __float2uint_rn(fminf(fmaxf(x[e][c], 0.f), 255.f));
+                integral = integral && (float)ub[c] == x[e][c];
             }
-            if (row < n) mx_t = max(mx_t, __float_as_uint(s));
-        } else {
-            if (lane == 0) qnorm[row] = row < n ? s : 0.f;
-            if (row < n) mx_q = max(mx_q, __float_as_uint(s));
-            for (int k = lane; k < part_per_row; k += 32) part[(size_t)row * part_per_row + k] = L2Cand{L2_INF, -1};
+            // [hi | lo] bf16 split, two elements per conversion instruction
+            const float v0 = x[e][0] * scale, v1 = x[e][1] * scale, v2 = x[e][2] * scale, v3 = x[e][3] * scale;
+            const __nv_bfloat162 h01 = __floats2bfloat162_rn(v0, v1), h23 = __floats2bfloat162_rn(v2, v3);
+            const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+            const __nv_bfloat162 l01 = __floats2bfloat162_rn(v0 - f01.x, v1 - f01.y), l23 = __floats2bfloat162_rn(v2 - f23.x, v3 - f23.y);
+            const int l = sub + 8 * e;
+            *reinterpret_cast<uint2 *>(dst + 4 * l) =
+                make_uint2(*reinterpret_cast<const unsigned *>(&h01), *reinterpret_cast<const unsigned *>(&h23));
+            *reinterpret_cast<uint2 *>(dst + L2_KDIM + 4 * l) =
+                make_uint2(*reinterpret_cast<const unsigned *>(&l01), *reinterpret_cast<const unsigned *>(&l23));
+            dst8[l] = ub[0] | (ub[1] << 8) | (ub[2] << 16) | (ub[3] << 24);
         }
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (is_train) {
+            if (sub == 2) tnorm[row] = live ? s : 0.f;
+            // K2's norm operand: [n_h n_m n_l 1 1 1 0 0 | 0 x 8] bf16 in the smem image of the row's column tile
+            if (sub < 2) {
+                const uint4 s3 = bf16_split3(live ? s : __uint_as_float(L2_PAD_NORM_BITS));
+                uint8_t *e = text + (size_t)(row >> 7) * L2_EXT_BYTES + ext_row_offset(row & 127) + sub * 128;
+                *reinterpret_cast<uint4 *>(e) = sub == 0 ? make_uint4(s3.x, s3.y | 0x3F800000u, 0x3F803F80u, 0u)
+                                                         : make_uint4(0u, 0u, 0u, 0u);
+            }
+            if (live) mx_t = max(mx_t, __float_as_uint(s));
+        } else {
+            if (sub == 0) qnorm[row] = live ? s : 0.f;
+            if (live) mx_q = max(mx_q, __float_as_uint(s));
+            for (int k = sub; k < part_per_row; k += 8) part[(size_t)row * part_per_row + k] = L2Cand{L2_INF, -1};
         }
     }
     // one atomic per block and side (same-address traffic serialises in L2)
@@ -508,7 +527,7 @@ int pmk_l2_knn2_phase(pm_ctx *ctx, const void *dq, int nq, const void *dt, int n
     const int vec = is_u8 ? vec_u8 : vec_f32;
     if (phase == 1) {
         PM_CUDA(ctx, cudaMemsetAsync(tflags, 0, sizeof(L2Flags), ctx->stream));
-        const int blocks = min(pm_cdiv(nt_pad, 8), 8 * ctx->num_sms);
+        const int blocks = min(pm_cdiv(nt_pad, 32), 8 * ctx->num_sms);
         if (is_u8)
             PM_CUDA(ctx, pm_launch_pdl(l2_pack_kernel<uint8_t>, dim3(blocks), dim3(256), 0, ctx->stream, (const uint8_t *)nullptr, 0, 0,
                                        (const uint8_t *)dt, nt, nt_pad, dim, vec, (__nv_bfloat16 *)nullptr, tpack, (float *)nullptr, text,
@@ -529,7 +548,7 @@ int pmk_l2_knn2_phase(pm_ctx *ctx, const void *dq, int nq, const void *dt, int n
     const int fin_blocks = min(pm_cdiv(nq, 32), 3 * ctx->num_sms);
     const int pack_nt = phase == 2 ? 0 : nt, pack_nt_pad = phase == 2 ? 0 : nt_pad;
     const L2Flags *tflags_in = phase == 2 ? tflags : nullptr;
-    const int pack_blocks = min(pm_cdiv(mq_pad + pack_nt_pad, 8), 8 * ctx->num_sms);
+    const int pack_blocks = min(pm_cdiv(mq_pad + pack_nt_pad, 32), 8 * ctx->num_sms);
     if (is_u8)
         PM_CUDA(ctx, pm_launch_pdl(l2_pack_kernel<uint8_t>, dim3(pack_blocks), dim3(256), 0, ctx->stream, (const uint8_t *)dq, nq, mq_pad,
                                    (const uint8_t *)dt, pack_nt, pack_nt_pad, dim, vec, qpack, tpack, qnorm, text, q8, t8, tnormf, flags, part, smax * 3,
