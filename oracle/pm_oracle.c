@@ -515,15 +515,16 @@ int orc_is_inlier_f32(const float F[9], float x1, float y1, float x2, float y2,
     float r  = fmaf(x2, a, fmaf(y2, b, c));
     float at = fmaf(F[0], x2, fmaf(F[3], y2, F[6]));
     float bt = fmaf(F[1], x2, fmaf(F[4], y2, F[7]));
-    float r2 = r * r;
+    float nr2 = -(r * r);
+    /* margin form (one fused multiply-add, sign = outlier): the product's "scoring op order" */
     if (metric == ORC_METRIC_SAMPSON) {
         float den = fmaf(a, a, fmaf(b, b, fmaf(at, at, bt * bt)));
-        return r2 <= thr2 * den;
+        return fmaf(thr2, den, nr2) >= 0.0f;
     } else {
         /* max(d1^2 s1, d2^2 s2) <= thr^2, division-free; x1^T F^T x2 == x2^T F x1 */
         float n2 = fmaf(a, a, b * b);
         float n1 = fmaf(at, at, bt * bt);
-        return (r2 <= thr2 * n2) && (r2 <= thr2 * n1);
+        return (fmaf(thr2, n2, nr2) >= 0.0f) && (fmaf(thr2, n1, nr2) >= 0.0f);
     }
 }
 

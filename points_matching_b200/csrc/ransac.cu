@@ -328,9 +328,12 @@ __global__ void pack_points_kernel(const float2 *__restrict__ p1, const float2 *
     out[i] = make_float4(a.x, a.y, b.x, b.y);
 }
 
-// The FP32 inlier test, operation for operation (DESIGN.md "scoring op order").
+// The FP32 inlier test, operation for operation (DESIGN.md "scoring op order"): the margin
+//   Sampson: m = fma(thr2, den, -r*r)            inlier <=> m >= 0
+//   sym-epi: m1 = fma(thr2, a*a+b*b, -r*r), m2 likewise with the transposed line; inlier <=> both >= 0
+// is returned as float bits whose SIGN bit says "outlier" (m is never -0: x - x rounds to +0).
 template <int METRIC>
-__device__ __forceinline__ bool is_inlier(const float (&F)[9], const float4 p, const float thr2)
+__device__ __forceinline__ unsigned outlier_bits(const float (&F)[9], const float4 p, const float thr2)
 {
     const float a = fmaf(F[0], p.x, fmaf(F[1], p.y, F[2]));
     const float b = fmaf(F[3], p.x, fmaf(F[4], p.y, F[5]));
@@ -338,14 +341,39 @@ __device__ __forceinline__ bool is_inlier(const float (&F)[9], const float4 p, c
     const float r = fmaf(p.z, a, fmaf(p.w, b, c));
     const float at = fmaf(F[0], p.z, fmaf(F[3], p.w, F[6]));
     const float bt = fmaf(F[1], p.z, fmaf(F[4], p.w, F[7]));
-    const float r2 = __fmul_rn(r, r);
+    const float nr2 = -__fmul_rn(r, r);
     if (METRIC == PM_METRIC_SAMPSON) {
         const float den = fmaf(a, a, fmaf(b, b, fmaf(at, at, __fmul_rn(bt, bt))));
-        return r2 <= __fmul_rn(thr2, den);
+        return __float_as_uint(fmaf(thr2, den, nr2));
     } else {
         const float n2 = fmaf(a, a, __fmul_rn(b, b));
         const float n1 = fmaf(at, at, __fmul_rn(bt, bt));
-        return (r2 <= __fmul_rn(thr2, n2)) && (r2 <= __fmul_rn(thr2, n1));
+        return __float_as_uint(fmaf(thr2, n2, nr2)) | __float_as_uint(fmaf(thr2, n1, nr2));
+    }
+}
+template <int METRIC>
+__device__ __forceinline__ bool is_inlier(const float (&F)[9], const float4 p, const float thr2)
+{
+    return (outlier_bits<METRIC>(F, p, thr2) >> 31) == 0u;
+}
+// out += bits >> 31 in ONE instruction on the FMA pipe (IMAD.HI: hi32(bits * 2) + out) instead of FSETP + IADD
+__device__ __forceinline__ unsigned add_sign(unsigned bits, unsigned out)
+{
+    unsigned r;
+    asm("mad.hi.u32 %0, %1, 2, %2;" : "=r"(r) : "r"(bits), "r"(out));
+    return r;
+}
+// A model with a NaN / infinite coefficient (degenerate sample) is replaced by F = e9: a = b = a' = b' = 0, r = 1,
+// margin = -1 for every point -> count 0, exactly what "no model" must score.
+__device__ __forceinline__ void sanitize_model(float (&F)[9])
+{
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ok = ok && (fabsf(F[i]) < 3.0e38f);
+    if (!ok) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) F[i] = 0.f;
+        F[8] = 1.f;
     }
 }
 
@@ -372,9 +400,11 @@ ransac_score_kernel(const float4 *__restrict__ pts, int n, int chunk_pts, const 
         F[r][0] = u.x; F[r][1] = u.y; F[r][2] = u.z; F[r][3] = u.w;
         F[r][4] = v.x; F[r][5] = v.y; F[r][6] = v.z; F[r][7] = v.w; F[r][8] = w.x;
     }
-    int cnt[SC_MPT];
 #pragma unroll
-    for (int r = 0; r < SC_MPT; ++r) cnt[r] = 0;
+    for (int r = 0; r < SC_MPT; ++r) sanitize_model(F[r]);
+    unsigned outl[SC_MPT];                   // OUTLIERS seen so far (one IMAD.HI per evaluation)
+#pragma unroll
+    for (int r = 0; r < SC_MPT; ++r) outl[r] = 0u;
 
     const int p0 = blockIdx.y * chunk_pts, p1 = min(n, p0 + chunk_pts);
     const int ntiles = (p1 - p0 + SC_TILE - 1) / SC_TILE;
@@ -395,16 +425,18 @@ ransac_score_kernel(const float4 *__restrict__ pts, int n, int chunk_pts, const 
         for (int j = 0; j < cntp; ++j) {
             const float4 p = tile[buf][j];
 #pragma unroll
-            for (int r = 0; r < SC_MPT; ++r) cnt[r] += is_inlier<METRIC>(F[r], p, thr2) ? 1 : 0;
+            for (int r = 0; r < SC_MPT; ++r) outl[r] = add_sign(outlier_bits<METRIC>(F[r], p, thr2), outl[r]);
         }
         __syncthreads();
     }
+    const int seen = max(p1 - p0, 0);
 #pragma unroll
     for (int r = 0; r < SC_MPT; ++r) {
         const int m = m0 + r * SC_THREADS + tid;
         if (m < n_models) {
-            if (use_atomic) atomicAdd(&counts[m], cnt[r]);
-            else counts[m] = cnt[r];
+            const int c = seen - (int)outl[r];
+            if (use_atomic) atomicAdd(&counts[m], c);
+            else counts[m] = c;
         }
     }
 }
@@ -450,6 +482,7 @@ ransac_mask_kernel(const float4 *__restrict__ pts, int n, const float *__restric
     float F[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) F[i] = Fw[i];
+    sanitize_model(F);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool in = false;
     if (i < n) { in = is_inlier<METRIC>(F, pts[i], thr2); mask[i] = in ? 1 : 0; }
