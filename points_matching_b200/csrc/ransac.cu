@@ -316,7 +316,16 @@ ransac_solve_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2
 // K7: scoring
 // =====================================================================================
 constexpr int SC_THREADS = 128;
-constexpr int SC_MPT = 4;          // models per thread
+#ifndef SC_MPT_V
+#define SC_MPT_V 4
+#endif
+#ifndef SC_UNROLL_V
+#define SC_UNROLL_V 16
+#endif
+#define PM_STR2(x) #x
+#define PM_STR(x) PM_STR2(x)
+#define PM_UNROLL(n) _Pragma(PM_STR(unroll n))
+constexpr int SC_MPT = SC_MPT_V;     // models per thread
 constexpr int SC_TILE = 512;       // correspondences per shared-memory tile (8 KB)
 
 __global__ void pack_points_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2, int n,
@@ -421,7 +430,7 @@ ransac_score_kernel(const float4 *__restrict__ pts, int n, int chunk_pts, const 
         else asm volatile("cp.async.wait_group 0;");
         __syncthreads();
         const int cntp = min(SC_TILE, p1 - (p0 + ti * SC_TILE));
-#pragma unroll 4
+        PM_UNROLL(SC_UNROLL_V)
         for (int j = 0; j < cntp; ++j) {
             const float4 p = tile[buf][j];
 #pragma unroll
