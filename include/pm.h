@@ -167,6 +167,8 @@ int pm_find_fundamental(pm_ctx *ctx, const float *p1 /* [n][2] */, const float *
 /* Deterministic minimal-sample index sets ([n_hyp][m], distinct within a row); the
  * same (n_points, n_hyp, m, seed) gives the same sets on every rank. */
 int pm_make_sample_sets(int n_points, int n_hyp, int m, uint64_t seed, int32_t *out);
+/* The same sets generated on the device (one thread per hypothesis), asynchronous on the ctx stream. */
+int pm_make_sample_sets_dev(pm_ctx *ctx, int n_points, int n_hyp, int m, uint64_t seed, int32_t *dout);
 
 /* Staged device API (what pm_find_fundamental runs; exposed for shards and tests).
  *  solve : dF32 [n_hyp][models][12] f32 (9 used; NaN = no model), models = 1 or 3

@@ -16,9 +16,13 @@
  *   main.cpp:127-132 cv::computeCorrespondEpilines
  * Each function below cites the call site it stands in for and restates the
  * published OpenCV algorithm behind it.  Parity pin: the reference ships no
- * tests or golden vectors, so the oracle is pinned against
- * OpenCV 4.13 (cv2, same algorithms) by tests/golden/make_golden.py, whose
- * outputs are committed under tests/golden/.
+ * tests or golden vectors and its OpenCV 2.4.13 Windows
+ * binaries cannot run here, so PARITY WITH THE REFERENCE'S OWN BINARY IS
+ * UNPINNED.  What pins the oracle instead is OpenCV 4.13 (cv2 -- the same
+ * library, same algorithms, importable in the build container):
+ * tests/golden/make_golden.py generated the vectors committed under
+ * tests/golden/ and tests/test_oracle_golden.py checks every function here
+ * against them.
  */
 #ifndef PM_ORACLE_H
 #define PM_ORACLE_H

@@ -320,6 +320,9 @@ class Context:
                                                   C.c_void_p(dF), C.c_void_p(dmask), C.c_void_p(dn_inl),
                                                   C.c_void_p(dkey)))
 
+    def make_sample_sets_dev(self, n_points, n_hyp, m, seed, dout):
+        self._chk(self._L.pm_make_sample_sets_dev(self._h, n_points, n_hyp, m, C.c_uint64(seed), C.c_void_p(dout)))
+
     def ransac_solve_dev(self, dp1, dp2, n, dsamples, n_hyp, sample_size, dF32):
         self._chk(self._L.pm_ransac_solve_dev(self._h, C.c_void_p(dp1), C.c_void_p(dp2), n, C.c_void_p(dsamples),
                                               n_hyp, sample_size, C.c_void_p(dF32)))

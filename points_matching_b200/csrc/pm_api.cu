@@ -469,6 +469,13 @@ int pm_make_sample_sets(int n_points, int n_hyp, int m, uint64_t seed, int32_t *
     return PM_OK;
 }
 
+int pm_make_sample_sets_dev(pm_ctx *ctx, int n_points, int n_hyp, int m, uint64_t seed, int32_t *dout)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, n_points >= m && m > 0 && m <= 8 && n_hyp >= 0 && dout, "need n_points >= m, 0 < m <= 8");
+    return pmk_sample_sets(ctx, n_points, n_hyp, m, seed, dout);
+}
+
 int pm_find_fundamental(pm_ctx *ctx, const float *p1, const float *p2, int n, const pm_ransac_params *prm,
                         double F[9], uint8_t *mask, int *n_inliers)
 {
@@ -494,16 +501,9 @@ int pm_find_fundamental(pm_ctx *ctx, const float *p1, const float *p2, int n, co
     int32_t *dninl = reinterpret_cast<int32_t *>(dkey + 2);
     H2D(ctx, dp1, p1, (size_t)n * 8);
     H2D(ctx, dp2, p2, (size_t)n * 8);
-    std::vector<int32_t> gen;
-    const int32_t *hs = prm->sample_idx;
-    if (!hs) {
-        gen.resize((size_t)nh * m);
-        pm_make_sample_sets(n, nh, m, prm->seed, gen.data());
-        hs = gen.data();
-    }
-    H2D(ctx, ds, hs, (size_t)nh * m * 4);
-    if (!prm->sample_idx) PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // gen goes out of scope later; keep simple
     int st;
+    if (prm->sample_idx) H2D(ctx, ds, prm->sample_idx, (size_t)nh * m * 4);
+    else if ((st = pmk_sample_sets(ctx, n, nh, m, prm->seed, ds)) != PM_OK) return st;   // same sets as pm_make_sample_sets
     if ((st = pmk_ransac_solve(ctx, dp1, dp2, n, ds, nh, m, dF32)) != PM_OK) return st;
     if ((st = pmk_ransac_score(ctx, dp1, dp2, n, dF32, nh * per, prm->threshold, prm->metric, dcounts)) != PM_OK) return st;
     if ((st = pmk_ransac_best(ctx, dcounts, nh * per, 0, dkey)) != PM_OK) return st;

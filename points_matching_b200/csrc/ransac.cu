@@ -1016,6 +1016,37 @@ int pmk_lmeds_finish(pm_ctx *ctx, const float *dp1, const float *dp2, int n, con
     return PM_OK;
 }
 
+// Device twin of pm_make_sample_sets (pm_api.cu): same splitmix64 stream, same rejection of repeats, so the
+// sets are identical to the host generator's -- one thread per hypothesis.
+__global__ void sample_sets_kernel(int n_points, int n_hyp, int m, unsigned long long seed, int32_t *__restrict__ out)
+{
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n_hyp) return;
+    unsigned long long s = seed ^ (0xD1B54A32D192ED03ull * (unsigned long long)(h + 1));
+    int32_t row[8];
+    for (int i = 0; i < m; ++i) {
+        for (;;) {
+            unsigned long long z = (s += 0x9E3779B97F4A7C15ull);
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            z ^= z >> 31;
+            const int32_t v = (int32_t)(z % (unsigned long long)n_points);
+            bool dup = false;
+            for (int k = 0; k < i; ++k) dup = dup || row[k] == v;
+            if (!dup) { row[i] = v; break; }
+        }
+    }
+    for (int i = 0; i < m; ++i) out[(size_t)h * m + i] = row[i];
+}
+
+int pmk_sample_sets(pm_ctx *ctx, int n_points, int n_hyp, int m, uint64_t seed, int32_t *dout)
+{
+    if (n_hyp <= 0) return PM_OK;
+    sample_sets_kernel<<<pm_cdiv(n_hyp, 128), 128, 0, ctx->stream>>>(n_points, n_hyp, m, (unsigned long long)seed, dout);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}
+
 int pmk_epilines(pm_ctx *ctx, const float *dpts, int n, int which, const double *dF, float *dlines)
 {
     if (n <= 0) return PM_OK;

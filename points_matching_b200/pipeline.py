@@ -11,7 +11,7 @@ count (the RANSAC launch geometry depends on it); F and the inlier count are rea
 import numpy as np
 import torch
 
-from .api import METRIC_SAMPSON, make_sample_sets
+from .api import METRIC_SAMPSON
 from .sharded import _world, shard_bounds
 
 
@@ -36,10 +36,14 @@ class PairPipeline:
         self.ninl = torch.zeros(4, **i32)
         self.key = torch.zeros(2, dtype=torch.int64, device=self.dev)
         self.h_count = torch.zeros(4, dtype=torch.int32).pin_memory()
-        self._sets = {}                       # host sample sets per match count (deterministic in (n, seed))
+        self.res_dev = torch.zeros(16, dtype=torch.float64, device=self.dev)
+        self.h_res = torch.zeros(16, dtype=torch.float64).pin_memory()
+        self._ev = torch.cuda.Event()
 
-    def run(self, desc1, desc2, kp1, kp2, seed=0):
-        """desc*/kp*: CUDA tensors ([n,128] f32 or u8, [n,2] f32).  Returns dict(n_matches, n_inliers, F [3,3] or None)."""
+    # The flow is split into three host stages so that several pipelines (one ctx + stream each) can be
+    # interleaved: while one waits for its 4-byte match count, the GPU runs another pair's kernels.
+    def start(self, desc1, desc2, kp1, kp2, seed=0):
+        """Stage 1: enqueue matching + ratio filter + gather and the asynchronous read of the match count."""
         c, n1, n2 = self.ctx, desc1.shape[0], desc2.shape[0]
         self.stream.wait_stream(torch.cuda.current_stream(self.dev))     # inputs produced on the caller's stream
         if desc1.dtype == torch.uint8:
@@ -51,40 +55,60 @@ class PairPipeline:
                              self.p1.data_ptr(), self.p2.data_ptr())
         with torch.cuda.stream(self.stream):
             self.h_count.copy_(self.ngood, non_blocking=True)
-        self.stream.synchronize()
+            self._ev.record(self.stream)
+        return dict(seed=seed, stage=1)
+
+    def estimate(self, res):
+        """Stage 2: wait for the match count, enqueue RANSAC-F and the asynchronous read of its result."""
+        c = self.ctx
+        self._ev.synchronize()
         n = int(self.h_count[0])
+        res.update(n_matches=n, stage=2, pending=n >= 8)
         if n < 8:
-            return dict(n_matches=n, n_inliers=0, F=None)
-        sets = self._sets.get((n, seed))
-        if sets is None:
-            sets = torch.from_numpy(make_sample_sets(n, self.n_hyp, 8, seed)).pin_memory()
-            if len(self._sets) < 64:
-                self._sets[(n, seed)] = sets
-        with torch.cuda.stream(self.stream):
-            self.samples.copy_(sets, non_blocking=True)
+            return res
+        c.make_sample_sets_dev(n, self.n_hyp, 8, res["seed"], self.samples.data_ptr())   # == the host generator's sets
         c.find_fundamental_dev(self.p1.data_ptr(), self.p2.data_ptr(), n, self.samples.data_ptr(), self.n_hyp, 8, self.metric,
                                self.thr, self.refit, self.F.data_ptr(), self.mask.data_ptr(), self.ninl.data_ptr(),
                                self.key.data_ptr(), 0)
-        return dict(n_matches=n, pending=True)
+        with torch.cuda.stream(self.stream):
+            # one packed read: [key, n_inliers, F(9)] as 11 doubles
+            self.res_dev[0] = self.key[0].to(torch.float64)          # key != 0 <=> a model exists (exact for the test)
+            self.res_dev[1] = self.ninl[0].to(torch.float64)
+            self.res_dev[2:11] = self.F[:9]
+            self.h_res.copy_(self.res_dev, non_blocking=True)
+            self._ev.record(self.stream)
+        return res
 
     def finish(self, res):
-        """Reads F / inlier count of the pair whose RANSAC was enqueued last."""
+        """Stage 3: read F / inlier count of the pair whose RANSAC was enqueued by estimate()."""
+        if res.get("stage") == 1:
+            res = self.estimate(res)
         if not res.get("pending"):
-            return res
-        self.stream.synchronize()
-        ok = int(self.key[0].item()) != 0
-        return dict(n_matches=res["n_matches"], n_inliers=int(self.ninl[0].item()) if ok else 0,
-                    F=self.F[:9].cpu().numpy().reshape(3, 3).copy() if ok else None)
+            return dict(n_matches=res["n_matches"], n_inliers=0, F=None)
+        self._ev.synchronize()
+        h = self.h_res.numpy()
+        ok = h[0] != 0.0
+        return dict(n_matches=res["n_matches"], n_inliers=int(h[1]) if ok else 0, F=h[2:11].reshape(3, 3).copy() if ok else None)
+
+    def run(self, desc1, desc2, kp1, kp2, seed=0):
+        """desc*/kp*: CUDA tensors ([n,128] f32 or u8, [n,2] f32).  Returns the dict finish() completes."""
+        return self.estimate(self.start(desc1, desc2, kp1, kp2, seed))
 
 
-def match_and_estimate_batch(pipeline, pairs, group=None):
+def match_and_estimate_batch(pipelines, pairs, group=None):
     """pairs: list of (desc1, desc2, kp1, kp2) CUDA tensors, identical on every rank.  Rank r processes the
     pairs of its contiguous shard; returns this rank's list of (pair_index, result dict).  No collective is
-    needed on the data path (the pairs are independent); gather the small results if every rank wants all."""
+    needed on the data path (the pairs are independent); gather the small results if every rank wants all.
+    `pipelines` is one PairPipeline or a list of them (each with its own ctx): with two or more, the pairs are
+    software-pipelined so one pipeline's host round trip hides behind another's kernels."""
+    if isinstance(pipelines, PairPipeline):
+        pipelines = [pipelines]
     world, rank = _world(group)
     lo, hi = shard_bounds(len(pairs), world, rank)
-    out = []
-    for p in range(lo, hi):
-        d1, d2, k1, k2 = pairs[p]
-        out.append((p, pipeline.finish(pipeline.run(d1, d2, k1, k2, seed=p))))
+    k, out = len(pipelines), []
+    for base in range(lo, hi, k):                 # rounds of k pairs, one per pipeline (a pipeline holds one pair in flight)
+        chunk = list(range(base, min(base + k, hi)))
+        st = [pipelines[i].start(*pairs[p], seed=p) for i, p in enumerate(chunk)]
+        st = [pipelines[i].estimate(r) for i, r in enumerate(st)]
+        out += [(p, pipelines[i].finish(st[i])) for i, p in enumerate(chunk)]
     return out

@@ -540,3 +540,14 @@ def test_device_engine_sharded_api_single_rank(pm, orc):
     assert winner == r["best_model"] and abs(ninl - r["n_inliers"]) <= 3
     assert (mask.cpu().numpy() == r["mask"]).mean() > 0.998
     ctx.close()
+
+
+def test_device_sample_sets_equal_host_generator(ctx, pm):
+    """pm_make_sample_sets_dev is the device twin of the host generator: identical index sets."""
+    import torch
+    from points_matching_b200.api import make_sample_sets
+    for n, nh, m, seed in ((4096, 4096, 8, 7), (9, 300, 8, 1), (1000, 777, 7, 12345678901)):
+        d = torch.zeros((nh, m), dtype=torch.int32, device="cuda:0")
+        ctx.make_sample_sets_dev(n, nh, m, seed, d.data_ptr())
+        ctx.sync()
+        assert np.array_equal(d.cpu().numpy(), make_sample_sets(n, nh, m, seed))

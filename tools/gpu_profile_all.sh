@@ -11,10 +11,13 @@ tail -3 $O/pytest_$TAG.log
 python bench.py --steps 1000 --warmup 10 > $O/bench_$TAG.json 2> $O/bench_$TAG.err; echo "bench exit $?"
 SHORT="python bench.py --steps 10 --warmup 3 --no-ramp --no-cpu --no-cfg5 --ransac-steps 2"
 $SHORT > $O/plain_$TAG.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/launches_$TAG.csv $SHORT > $O/ncu_list_$TAG.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $O/launches_$TAG.csv $SHORT > $O/ncu_list_$TAG.log 2>&1
 echo "launch list exit $?"
 python tools/step_timeline.py > $O/timeline_$TAG.txt 2>&1
 for K in l2_tc_kernel ham_knn2_kernel ransac_score_kernel l2_pack_kernel l2_finish_kernel compact_lookback_kernel; do
   ncu --set full --clock-control none --import-source on -k regex:$K -s 4 -c 1 -o $O/prof_${K}_$TAG -f $SHORT > $O/ncu_${K}_$TAG.log 2>&1
   echo "ncu $K exit $?"
 done
+python tools/ham_only.py > $O/plain_ham_$TAG.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:l2_tc_kernel -s 2 -c 1 -o $O/prof_l2_tc_kernel_fp8_$TAG -f python tools/ham_only.py > $O/ncu_l2_tc_kernel_fp8_$TAG.log 2>&1
+echo "ncu l2_tc_kernel<FP8> exit $?"
