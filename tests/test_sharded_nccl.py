@@ -1,0 +1,73 @@
+"""Two-rank NCCL run of the multi-GPU protocol with the product engine (libpm on CUDA tensors): results must be
+byte-identical to the single-GPU / oracle answer (sharding must not change tie-breaks).  Needs >= 2 GPUs; the
+CPU (gloo) twin of this test is tests/test_sharded_gloo.py."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import points_matching_b200 as pm
+        from points_matching_b200 import sharded, synth
+        ctx = pm.Context(rank)
+        stream = torch.cuda.Stream()
+        torch.cuda.set_stream(stream)
+        eng = sharded.DeviceEngine(ctx, f"cuda:{rank}")
+        res = {}
+        q, t = synth.sift_pair(2003, 1500, seed=11)
+        res["l2_knn"] = sharded.ShardedMatcher(eng, pm.NORM_L2).knn2(eng.tensor(q), eng.tensor(t)).cpu().numpy()
+        qb, tb = synth.orb_pair(3001, 2570, seed=12)
+        mh = sharded.ShardedMatcher(eng, pm.NORM_HAMMING)
+        res["ham_knn"] = mh.knn2(eng.tensor(qb), eng.tensor(tb)).cpu().numpy()
+        res["ham_cross"] = mh.match_cross(eng.tensor(qb), eng.tensor(tb)).cpu().numpy()
+        p1, p2, _ = synth.correspondences(3000, seed=5)
+        idx = synth.sample_index_sets(3000, 1001, 8, seed=48)
+        F, mask, ninl, winner = sharded.sharded_find_fundamental(eng, eng.tensor(p1), eng.tensor(p2), eng.tensor(idx), 8,
+                                                                 pm.METRIC_SAMPSON, 1.0, True)
+        res["ransac_F"], res["ransac_mask"] = F.cpu().numpy(), mask.cpu().numpy()
+        res["ransac_meta"] = np.array([ninl, winner])
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **res)
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_nccl_equals_single_gpu(tmp_path, orc):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    import points_matching_b200 as pm
+    from points_matching_b200 import synth
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (np.load(os.path.join(str(tmp_path), f"rank{r}.npz")) for r in range(2))
+    for k in r0.files:
+        assert np.array_equal(r0[k], r1[k]), k
+    q, t = synth.sift_pair(2003, 1500, seed=11)
+    assert np.array_equal(r0["l2_knn"].view(pm.DMATCH).reshape(2003, 2), orc.knn2_l2(q, t))
+    qb, tb = synth.orb_pair(3001, 2570, seed=12)
+    refh = orc.knn2_hamming(qb, tb)
+    assert np.array_equal(r0["ham_knn"].view(pm.DMATCH).reshape(3001, 2), refh)
+    assert np.array_equal(r0["ham_cross"].view(pm.DMATCH).reshape(-1), orc.cross_check(refh, orc.col_best_hamming(qb, tb)))
+    p1, p2, _ = synth.correspondences(3000, seed=5)
+    idx = synth.sample_index_sets(3000, 1001, 8, seed=48)
+    r = orc.ransac_f(p1, p2, idx, 0, 1.0, True)
+    assert int(r0["ransac_meta"][1]) == r["best_model"] and abs(int(r0["ransac_meta"][0]) - r["n_inliers"]) <= 3
+    assert (r0["ransac_mask"] == r["mask"]).mean() > 0.998
