@@ -144,8 +144,9 @@ __device__ __forceinline__ void store_model(float *dst, const double (&F)[9], bo
 // =====================================================================================
 // K6: minimal solvers, 8 lanes per hypothesis
 // =====================================================================================
+constexpr int SOLVE_THREADS = 256;    // 32 hypotheses per block
 template <int M>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(SOLVE_THREADS)
 ransac_solve_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2, int n,
                     const int32_t *__restrict__ samples, int n_hyp, float *__restrict__ Fout)
 {
@@ -231,12 +232,27 @@ ransac_solve_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2
 #pragma unroll
         for (int i = k; i < 9; ++i) { z[i] -= s * v[i]; if (M == 7) z2[i] -= t * v[i]; }
     }
-    if (!live || sub != 0) return;
-
     if (M == 8) {
+        // The rank-2 projection (3x3 Jacobi with FP64 divides and square roots) is the long tail of the
+        // solve and runs on ONE lane per hypothesis: hand the 32 hypotheses of the block to the 32 lanes
+        // of warp 0 through shared memory instead of running it 8 times with 4 active lanes each.
+        __shared__ double hand[SOLVE_THREADS / 8][16];
+        const int slot = threadIdx.x >> 3;
+        if (sub == 0) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) hand[slot][i] = z[i];
+            hand[slot][9] = s1; hand[slot][10] = s2; hand[slot][11] = c1x; hand[slot][12] = c1y;
+            hand[slot][13] = c2x; hand[slot][14] = c2y; hand[slot][15] = (live && valid) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        if (threadIdx.x >= SOLVE_THREADS / 8) return;
+        const int hh = blockIdx.x * (SOLVE_THREADS / 8) + threadIdx.x;
+        if (hh >= n_hyp) return;
         double F0[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) F0[i] = z[i];
+        for (int i = 0; i < 9; ++i) F0[i] = hand[threadIdx.x][i];
+        s1 = hand[threadIdx.x][9]; s2 = hand[threadIdx.x][10]; c1x = hand[threadIdx.x][11]; c1y = hand[threadIdx.x][12];
+        c2x = hand[threadIdx.x][13]; c2y = hand[threadIdx.x][14]; valid = hand[threadIdx.x][15] != 0.0;
         rank2_project3(F0);
         // F = T2^T F0 T1, T = [s 0 -s cx; 0 s -s cy; 0 0 1]
         double Mx[9];
@@ -259,8 +275,9 @@ ransac_solve_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2
         }
 #pragma unroll
         for (int i = 0; i < 9; ++i) valid = valid && isfinite(F[i]);
-        store_model(Fout + (size_t)h * 12, F, valid);
+        store_model(Fout + (size_t)hh * 12, F, valid);
     } else {
+        if (!live || sub != 0) return;
         // 7-point: det(lambda*f1 + (1-lambda)*f2) = 0  (OpenCV run7Point)
         double f1[9], f2[9];
 #pragma unroll
@@ -887,11 +904,11 @@ int pmk_ransac_solve(pm_ctx *ctx, const float *dp1, const float *dp2, int n, con
                      int m, float *dF32)
 {
     if (n_hyp <= 0) return PM_OK;
-    const int blocks = pm_cdiv(n_hyp * 8, 128);
+    const int blocks = pm_cdiv(n_hyp * 8, SOLVE_THREADS);
     if (m == 8)
-        ransac_solve_kernel<8><<<blocks, 128, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dsamples, n_hyp, dF32);
+        ransac_solve_kernel<8><<<blocks, SOLVE_THREADS, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dsamples, n_hyp, dF32);
     else
-        ransac_solve_kernel<7><<<blocks, 128, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dsamples, n_hyp, dF32);
+        ransac_solve_kernel<7><<<blocks, SOLVE_THREADS, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dsamples, n_hyp, dF32);
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }
