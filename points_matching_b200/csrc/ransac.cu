@@ -638,29 +638,52 @@ refit_solve_kernel(const double *__restrict__ partial, const double *__restrict_
             for (int j = i + 1; j < 9; ++j) off += A[i * 9 + j] * A[i * 9 + j];
         }
         if (off <= 1e-34 * diag || off == 0) break;
-        for (int p = 0; p < 8; ++p)
-            for (int q = p + 1; q < 9; ++q) {
+        // parallel-order Jacobi: round r rotates the four disjoint pairs {i, j} with i + j = r (mod 9) at once
+        // (every pair appears in exactly one of the nine rounds); lane g < 4 computes the rotation of pair g
+        for (int r = 0; r < 9; ++r) {
+            int p = 0, q = 0;
+            double c = 1.0, s = 0.0;
+            if (lane < 4) {
+                int seen = 0;
+                for (int i = 0; i < 9; ++i) {
+                    const int j = (r - i + 9) % 9;
+                    if (i < j) { if (seen == lane) { p = i; q = j; } ++seen; }
+                }
                 const double apq = A[p * 9 + q];
-                if (apq == 0) continue;                       // uniform across lanes
-                const double theta = (A[q * 9 + q] - A[p * 9 + p]) / (2 * apq);
-                const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
-                const double c = 1 / sqrt(tt * tt + 1), s = tt * c;
-                __syncwarp();
-                if (lane < 9) {
-                    const int k = lane;
-                    const double akp = A[k * 9 + p], akq = A[k * 9 + q];
-                    A[k * 9 + p] = c * akp - s * akq; A[k * 9 + q] = s * akp + c * akq;
+                if (apq != 0) {
+                    const double theta = (A[q * 9 + q] - A[p * 9 + p]) / (2 * apq);
+                    const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
+                    c = 1 / sqrt(tt * tt + 1); s = tt * c;
                 }
-                __syncwarp();
-                if (lane < 9) {
-                    const int k = lane;
-                    const double apk = A[p * 9 + k], aqk = A[q * 9 + k];
-                    A[p * 9 + k] = c * apk - s * aqk; A[q * 9 + k] = s * apk + c * aqk;
-                    const double vpk = V[p * 9 + k], vqk = V[q * 9 + k];
-                    V[p * 9 + k] = c * vpk - s * vqk; V[q * 9 + k] = s * vpk + c * vqk;
-                }
-                __syncwarp();
             }
+            int pg[4], qg[4]; double cg[4], sg[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                pg[g] = __shfl_sync(0xffffffffu, p, g); qg[g] = __shfl_sync(0xffffffffu, q, g);
+                cg[g] = __shfl_sync(0xffffffffu, c, g); sg[g] = __shfl_sync(0xffffffffu, s, g);
+            }
+            __syncwarp();
+            if (lane < 9) {
+                const int k = lane;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {      // columns p, q of row k (disjoint across the four pairs)
+                    const double akp = A[k * 9 + pg[g]], akq = A[k * 9 + qg[g]];
+                    A[k * 9 + pg[g]] = cg[g] * akp - sg[g] * akq; A[k * 9 + qg[g]] = sg[g] * akp + cg[g] * akq;
+                }
+            }
+            __syncwarp();
+            if (lane < 9) {
+                const int k = lane;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {      // rows p, q (and the eigenvector accumulation)
+                    const double apk = A[pg[g] * 9 + k], aqk = A[qg[g] * 9 + k];
+                    A[pg[g] * 9 + k] = cg[g] * apk - sg[g] * aqk; A[qg[g] * 9 + k] = sg[g] * apk + cg[g] * aqk;
+                    const double vpk = V[pg[g] * 9 + k], vqk = V[qg[g] * 9 + k];
+                    V[pg[g] * 9 + k] = cg[g] * vpk - sg[g] * vqk; V[qg[g] * 9 + k] = sg[g] * vpk + cg[g] * vqk;
+                }
+            }
+            __syncwarp();
+        }
     }
     if (lane != 0) return;
     double F[9];
