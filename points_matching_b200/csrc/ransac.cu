@@ -409,17 +409,17 @@ __device__ __forceinline__ void sc_cp_async16(void *smem, const void *gmem)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
 }
 
-template <int METRIC>
+template <int METRIC, int MPT>
 __global__ void __launch_bounds__(SC_THREADS)
 ransac_score_kernel(const float4 *__restrict__ pts, int n, int chunk_pts, const float *__restrict__ Fm,
                     int n_models, float thr2, int32_t *__restrict__ counts, int use_atomic)
 {
     __shared__ __align__(16) float4 tile[2][SC_TILE];
     const int tid = threadIdx.x;
-    const int m0 = blockIdx.x * (SC_THREADS * SC_MPT);
-    float F[SC_MPT][9];
+    const int m0 = blockIdx.x * (SC_THREADS * MPT);
+    float F[MPT][9];
 #pragma unroll
-    for (int r = 0; r < SC_MPT; ++r) {
+    for (int r = 0; r < MPT; ++r) {
         const int m = m0 + r * SC_THREADS + tid;
         const float4 *src = reinterpret_cast<const float4 *>(Fm + (size_t)min(m, n_models - 1) * 12);
         const float4 u = __ldg(src), v = __ldg(src + 1), w = __ldg(src + 2);
@@ -427,10 +427,10 @@ ransac_score_kernel(const float4 *__restrict__ pts, int n, int chunk_pts, const 
         F[r][4] = v.x; F[r][5] = v.y; F[r][6] = v.z; F[r][7] = v.w; F[r][8] = w.x;
     }
 #pragma unroll
-    for (int r = 0; r < SC_MPT; ++r) sanitize_model(F[r]);
-    unsigned outl[SC_MPT];                   // OUTLIERS seen so far (one IMAD.HI per evaluation)
+    for (int r = 0; r < MPT; ++r) sanitize_model(F[r]);
+    unsigned outl[MPT];                   // OUTLIERS seen so far (one IMAD.HI per evaluation)
 #pragma unroll
-    for (int r = 0; r < SC_MPT; ++r) outl[r] = 0u;
+    for (int r = 0; r < MPT; ++r) outl[r] = 0u;
 
     const int p0 = blockIdx.y * chunk_pts, p1 = min(n, p0 + chunk_pts);
     const int ntiles = (p1 - p0 + SC_TILE - 1) / SC_TILE;
@@ -451,13 +451,13 @@ ransac_score_kernel(const float4 *__restrict__ pts, int n, int chunk_pts, const 
         for (int j = 0; j < cntp; ++j) {
             const float4 p = tile[buf][j];
 #pragma unroll
-            for (int r = 0; r < SC_MPT; ++r) outl[r] = add_sign(outlier_bits<METRIC>(F[r], p, thr2), outl[r]);
+            for (int r = 0; r < MPT; ++r) outl[r] = add_sign(outlier_bits<METRIC>(F[r], p, thr2), outl[r]);
         }
         __syncthreads();
     }
     const int seen = max(p1 - p0, 0);
 #pragma unroll
-    for (int r = 0; r < SC_MPT; ++r) {
+    for (int r = 0; r < MPT; ++r) {
         const int m = m0 + r * SC_THREADS + tid;
         if (m < n_models) {
             const int c = seen - (int)outl[r];
@@ -943,13 +943,18 @@ int pmk_ransac_score(pm_ctx *ctx, const float *dp1, const float *dp2, int n, con
     const float4 *pts;
     int st = get_pts4(ctx, dp1, dp2, n, &pts);
     if (st != PM_OK) return st;
-    const int mblocks = pm_cdiv(n_models, SC_THREADS * SC_MPT);
+    // 4 models per thread when there are enough models to fill the GPU; 1 model per thread for small batches
+    // (e.g. 4096 hypotheses x 4096 matches per image pair in config 5), where 4 would leave most SMs idle
+    int mpt = SC_MPT;
+    if (pm_cdiv(n_models, SC_THREADS * SC_MPT) * pm_cdiv(n > 0 ? n : 1, SC_TILE) < 2 * ctx->num_sms) mpt = 1;
+    const int mblocks = pm_cdiv(n_models, SC_THREADS * mpt);
     // split the correspondences across blockIdx.y when the model blocks alone would leave the SMs unevenly
     // loaded: aim at >= 8 CTAs per SM so the tail imbalance stays below ~10% (256 model blocks on 148 SMs ran
     // at 1.73 CTAs per SM = 86% balance on the 8-GPU shard of cfg4)
+    const int min_chunk = mpt == 1 ? SC_TILE : 4 * SC_TILE;
     int chunks = 1;
-    if (mblocks < 8 * ctx->num_sms && n > 4 * SC_TILE)
-        chunks = min(pm_cdiv(8 * ctx->num_sms, mblocks), pm_cdiv(n, 4 * SC_TILE));
+    if (mblocks < 8 * ctx->num_sms && n > min_chunk)
+        chunks = min(pm_cdiv(8 * ctx->num_sms, mblocks), pm_cdiv(n, min_chunk));
     int chunk_pts = pm_round_up(pm_cdiv(n > 0 ? n : 1, chunks), SC_TILE);
     chunks = pm_cdiv(n > 0 ? n : 1, chunk_pts);
     const int use_atomic = chunks > 1;
@@ -958,10 +963,13 @@ int pmk_ransac_score(pm_ctx *ctx, const float *dp1, const float *dp2, int n, con
     dim3 grid(mblocks, chunks);
     {
         pm_prof_scope prof(ctx, 2);
-        if (metric == PM_METRIC_SAMPSON)
-            ransac_score_kernel<PM_METRIC_SAMPSON><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic);
-        else
-            ransac_score_kernel<PM_METRIC_SYMEPI><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic);
+        if (metric == PM_METRIC_SAMPSON) {
+            if (mpt == 1) ransac_score_kernel<PM_METRIC_SAMPSON, 1><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic);
+            else ransac_score_kernel<PM_METRIC_SAMPSON, SC_MPT><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic);
+        } else {
+            if (mpt == 1) ransac_score_kernel<PM_METRIC_SYMEPI, 1><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic);
+            else ransac_score_kernel<PM_METRIC_SYMEPI, SC_MPT><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic);
+        }
     }
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
