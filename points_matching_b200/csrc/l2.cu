@@ -295,13 +295,16 @@ __device__ __forceinline__ float group_l2sq(unsigned gmask, const float (&a)[4][
     return r;
 }
 
+constexpr int FB_CHUNK = 256;    // train rows per fallback work item
+constexpr int FB_ROWS = 1024;    // flagged rows per fallback batch (bounds the scratch: FB_ROWS x chunks x 16 B)
+
 template <typename T>
 __global__ void __launch_bounds__(256, 3)
 l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__restrict__ qnorm,
                  const uint8_t *__restrict__ q8, const uint8_t *__restrict__ t8, const float *__restrict__ tnorm,
                  const T *__restrict__ q, const T *__restrict__ t, int nq, int nt, int dim, int vec,
-                 L2Flags *flags, L2Flags *flags_next, int *__restrict__ flagged, int q_index_base,
-                 pm_dmatch *__restrict__ out, unsigned long long *span)
+                 L2Flags *flags, L2Flags *flags_next, int *__restrict__ flagged, unsigned long long *fb_part,
+                 int q_index_base, pm_dmatch *__restrict__ out, unsigned long long *span)
 {
     pm_span_mark(span, 6, false);
     pm_pdl_prologue();
@@ -419,24 +422,95 @@ l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__rest
             if (sub == 0 && !certified) flagged[atomicAdd(&flags->n_flagged, 1)] = i;
         }
     }
-    // Split mode only: rows K3 could not certify get the exact scan, spread over the whole grid.  Every
-    // block of K3 is resident (the host launches at most one wave), so an atomic-counter grid barrier is safe;
+    // Split mode only: rows K3 could not certify get an exact FP32 scan of the whole train set, spread over
+    // the grid as (flagged row, 256-train-row chunk) work items and merged per row afterwards.  Every block
+    // of K3 is resident (the host launches at most one wave), so an atomic-counter grid barrier is safe;
     // exact mode never flags a row and skips all of this.
     if (!l2_exact_mode(*flags)) {
-        __shared__ float x_qs[128];
-        __shared__ float x_md[16];
-        __shared__ int x_mi[16];
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            atomicAdd(&flags->done_blocks, 1u);
-            while (*reinterpret_cast<volatile unsigned *>(&flags->done_blocks) < gridDim.x) { }
-            __threadfence();
-        }
-        __syncthreads();
+        __shared__ float x_qs[L2_KDIM];
+        __shared__ unsigned long long x_k[8][2];
+        unsigned epoch = 0;
+        auto grid_barrier = [&]() {
+            ++epoch;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(&flags->done_blocks, 1u);
+                while (*reinterpret_cast<volatile unsigned *>(&flags->done_blocks) < epoch * gridDim.x) { }
+                __threadfence();
+            }
+            __syncthreads();
+        };
+        grid_barrier();
         const int nf = *reinterpret_cast<volatile int *>(&flags->n_flagged);
-        for (int r = blockIdx.x; r < nf; r += gridDim.x)
-            l2_exact_row(q, t, nt, dim, *reinterpret_cast<volatile int *>(&flagged[r]), q_index_base, out, x_qs, x_md, x_mi);
+        const int nchunk = (nt + FB_CHUNK - 1) / FB_CHUNK;
+        const int warp = threadIdx.x >> 5, g = lane >> 3;
+        for (int r0 = 0; r0 < nf; r0 += FB_ROWS) {                 // batches bound the scratch
+            const int nb = min(FB_ROWS, nf - r0);
+            for (int item = blockIdx.x; item < nb * nchunk; item += gridDim.x) {
+                const int r = item / nchunk, ch = item - r * nchunk;
+                const int i = *reinterpret_cast<volatile int *>(&flagged[r0 + r]);
+                __syncthreads();
+                if (threadIdx.x < L2_KDIM) x_qs[threadIdx.x] = threadIdx.x < dim ? load_elem(q, (size_t)i * dim + threadIdx.x) : 0.f;
+                __syncthreads();
+                float a[4][4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) a[e][c] = x_qs[4 * (sub + 8 * e) + c];
+                unsigned long long k0 = ~0ull, k1 = ~0ull;
+                const int j0 = ch * FB_CHUNK + warp * 32;
+#pragma unroll 2
+                for (int it = 0; it < 8; ++it) {                    // 4 train rows per warp and iteration
+                    const int j = j0 + it * 4 + g;
+                    float b[4][4];
+                    load_row8(t + (size_t)min(j, nt - 1) * dim, sub, dim, vec != 0, b);
+                    const float d = group_l2sq(gmask, a, b, sub, dim);
+                    const unsigned long long key = j < nt ? (((unsigned long long)__float_as_uint(d) << 32) | (unsigned)j) : ~0ull;
+                    k1 = min_u64(k1, max_u64(k0, key));
+                    k0 = min_u64(k0, key);
+                }
+                // merge the 4 groups of the warp (lanes of a group hold identical keys), then the 8 warps
+#pragma unroll
+                for (int o = 8; o <= 16; o <<= 1) {
+                    const unsigned long long y0 = __shfl_xor_sync(0xffffffffu, k0, o), y1 = __shfl_xor_sync(0xffffffffu, k1, o);
+                    const unsigned long long lo = min_u64(k0, y0), hi = max_u64(k0, y0);
+                    k1 = min_u64(min_u64(k1, y1), hi); k0 = lo;
+                }
+                if (lane == 0) { x_k[warp][0] = k0; x_k[warp][1] = k1; }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    unsigned long long m0 = ~0ull, m1 = ~0ull;
+                    for (int w = 0; w < 8; ++w)
+                        for (int e = 0; e < 2; ++e) { const unsigned long long key = x_k[w][e]; m1 = min_u64(m1, max_u64(m0, key)); m0 = min_u64(m0, key); }
+                    fb_part[((size_t)r * nchunk + ch) * 2] = m0;
+                    fb_part[((size_t)r * nchunk + ch) * 2 + 1] = m1;
+                }
+            }
+            grid_barrier();
+            for (int r = blockIdx.x * 8 + warp; r < nb; r += gridDim.x * 8) {   // one warp merges a row's chunks
+                const int i = *reinterpret_cast<volatile int *>(&flagged[r0 + r]);
+                unsigned long long m0 = ~0ull, m1 = ~0ull;
+                for (int c = lane; c < 2 * nchunk; c += 32) {
+                    const unsigned long long key = *reinterpret_cast<volatile unsigned long long *>(&fb_part[(size_t)r * nchunk * 2 + c]);
+                    m1 = min_u64(m1, max_u64(m0, key)); m0 = min_u64(m0, key);
+                }
+#pragma unroll
+                for (int o = 1; o <= 16; o <<= 1) {
+                    const unsigned long long y0 = __shfl_xor_sync(0xffffffffu, m0, o), y1 = __shfl_xor_sync(0xffffffffu, m1, o);
+                    const unsigned long long lo = min_u64(m0, y0), hi = max_u64(m0, y0);
+                    m1 = min_u64(min_u64(m1, y1), hi); m0 = lo;
+                }
+                if (lane < 2) {
+                    const unsigned long long w = lane == 0 ? m0 : m1;
+                    reinterpret_cast<uint4 *>(out + (size_t)i * 2)[lane] =
+                        w == ~0ull ? make_uint4((unsigned)(i + q_index_base), 0xFFFFFFFFu, 0u, __float_as_uint(3.402823466e+38f))
+                                   : make_uint4((unsigned)(i + q_index_base), (unsigned)(w & 0xFFFFFFFFull), 0u,
+                                                __float_as_uint(sqrtf(__uint_as_float((unsigned)(w >> 32)))));
+                }
+            }
+            if (r0 + FB_ROWS < nf) grid_barrier();                  // the scratch is reused by the next batch
+        }
     }
     if (span && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); span[33 + 2 * blockIdx.x] = tt; }
     pm_span_mark(span, 8, true);
@@ -544,6 +618,7 @@ int pmk_l2_knn2_phase(pm_ctx *ctx, const void *dq, int nq, const void *dt, int n
     PM_WS(ctx, q8, uint8_t *, WS_Q_U8, (size_t)mq_pad * L2_KDIM);
     PM_WS(ctx, part, L2Cand *, WS_L2_PART, (size_t)mq_pad * smax * 3 * sizeof(L2Cand));
     PM_WS(ctx, flagged, int *, WS_L2_FLAGGED, (size_t)nq * 4);
+    PM_WS(ctx, fbpart, unsigned long long *, WS_L2_FBPART, (size_t)FB_ROWS * pm_cdiv(nt, FB_CHUNK) * 16);
     // K3: 8 lanes per row, 32 rows per block, at most one resident wave (a second wave would double its latency)
     const int fin_blocks = min(pm_cdiv(nq, 32), 3 * ctx->num_sms);
     const int pack_nt = phase == 2 ? 0 : nt, pack_nt_pad = phase == 2 ? 0 : nt_pad;
@@ -563,12 +638,12 @@ int pmk_l2_knn2_phase(pm_ctx *ctx, const void *dq, int nq, const void *dt, int n
     if (is_u8)
         PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<uint8_t>, dim3(fin_blocks), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,
                                    (const float *)qnorm, (const uint8_t *)q8, (const uint8_t *)t8, (const float *)tnormf,
-                                   (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, vec_u8, flags, flags_next, flagged,
+                                   (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, vec_u8, flags, flags_next, flagged, fbpart,
                                    q_index_base, dout, g_pm_span));
     else
         PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<float>, dim3(fin_blocks), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,
                                    (const float *)qnorm, (const uint8_t *)q8, (const uint8_t *)t8, (const float *)tnormf,
-                                   (const float *)dq, (const float *)dt, nq, nt, dim, vec_f32, flags, flags_next, flagged,
+                                   (const float *)dq, (const float *)dt, nq, nt, dim, vec_f32, flags, flags_next, flagged, fbpart,
                                    q_index_base, dout, g_pm_span));
     PM_CHECK_LAUNCH(ctx);
     ctx->l2_parity ^= 1;

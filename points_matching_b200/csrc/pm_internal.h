@@ -18,9 +18,9 @@ enum pm_slot {
     WS_HAM_Q, WS_HAM_T, WS_HAM_PART, WS_COLBEST,
     WS_P1, WS_P2, WS_SAMPLES, WS_F32, WS_COUNTS, WS_KEY, WS_MASK, WS_FOUT, WS_REFIT, WS_MISC,
     WS_KNN, WS_KNN2, WS_IDX, WS_KP, WS_LINES,
-    WS_Q_U8, WS_T_U8, WS_T_NORMF
+    WS_Q_U8, WS_T_U8, WS_T_NORMF, WS_L2_FBPART
 };
-static_assert(WS_T_NORMF < PM_NSLOTS, "workspace slots");
+static_assert(WS_L2_FBPART < PM_NSLOTS, "workspace slots");
 
 struct pm_ctx {
     int device = 0;
