@@ -344,6 +344,8 @@ def run_ours(args):
     if not args.no_hamming:
         extra = {"hamming": bench_hamming(ctx, torch, dev, world, rank, stream, barrier, peaks)}
 
+    if extra is not None:
+        extra["l2_general_floats"] = bench_split_mode(ctx, torch, dev, rank, stream, barrier)
     if extra is not None and not args.no_cfg5:
         extra["cfg5"] = bench_cfg5(ctx, torch, dev, world, rank, barrier)
 
@@ -448,6 +450,38 @@ def bench_hamming(ctx, torch, dev, world, rank, stream, barrier, peaks):
                 "pairs_per_s_step": d["pairs_per_s_step"], "mutual_matches": d["mutual_matches"], "roofline": d["roofline"],
                 "default_path": "tensor"})
     return res
+
+
+def bench_split_mode(ctx, torch, dev, rank, stream, barrier):
+    """The same cfg2-sized step on SURF-like descriptors (unit-norm signed floats -- what the reference's SURF extractor
+    produces, main.cpp:37-40): bf16 is lossy there, so K2 runs three bf16 products per pair and K3 re-ranks in FP32 and
+    certifies; uncertified rows get an exact scan."""
+    from points_matching_b200 import synth
+    q, t = synth.surf_pair(NQ, NT, seed=77 + rank)
+    dq, dt_ = torch.from_numpy(q).to(dev), torch.from_numpy(t).to(dev)
+    knn = torch.zeros((NQ, 2, 4), dtype=torch.int32, device=dev)
+    good = torch.zeros((NQ, 4), dtype=torch.int32, device=dev)
+    ng = torch.zeros(4, dtype=torch.int32, device=dev)
+
+    def step():
+        ctx.knn2_l2_f32_dev(dq.data_ptr(), NQ, dt_.data_ptr(), NT, DIM, knn.data_ptr(), 0)
+        ctx.ratio_filter_dev(knn.data_ptr(), NQ, RATIO, good.data_ptr(), ng.data_ptr())
+
+    for _ in range(20):
+        step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 200
+    ev0.record(stream)
+    for _ in range(n):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1) / n
+    st = ctx.l2_stats()
+    return {"workload": "SURF-like unit-norm float descriptors 10000 x 10000 x 128, L2 kNN-2 + ratio 0.75 (same inputs every step: L2-resident)",
+            "ms_per_step": ms, "pairs_per_s": NQ * NT / (ms * 1e-3), "exact_integer_mode": st["exact_mode"],
+            "mma_k_blocks_per_tile": st["k_blocks"], "exact_fallback_rows": st["fallback_rows"]}
 
 
 def bench_cfg5(ctx, torch, dev, world, rank, barrier):

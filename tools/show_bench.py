@@ -25,6 +25,9 @@ def show_bench(path):
                 print('hamming[%s] step ms %.3f kernel ms %.3f pairs/s(kernel) %.3e frac %.3f mutual %d' % (k, y['ms_per_step'], y['kernel_ms'], y['pairs_per_s_knn_kernel'], y['roofline']['frac'], y['mutual_matches']))
         if 'popc' not in x:
             print('hamming step ms %.3f kernel ms %.3f pairs/s(kernel) %.3e frac %.3f mutual %d' % (x['ms_per_step'], x['kernel_ms'], x['pairs_per_s_knn_kernel'], x['roofline']['frac'], x['mutual_matches']))
+    sf = (d.get('extra') or {}).get('l2_general_floats')
+    if sf:
+        print('surf-like floats: step %.1f us %.3e pairs/s fallback rows %d' % (sf['ms_per_step'] * 1e3, sf['pairs_per_s'], sf['exact_fallback_rows']))
     c5 = (d.get('extra') or {}).get('cfg5')
     if c5:
         print('cfg5 %.1f image pairs/s (%.3f ms/pair) last %s' % (c5['image_pairs_per_s'], c5['ms_per_pair'], c5['last_pair']))
