@@ -59,6 +59,14 @@ int  pm_destroy(pm_ctx *ctx);
 /* Run on an existing cudaStream_t (e.g. torch's current stream); NULL = ctx-owned stream. */
 int  pm_set_stream(pm_ctx *ctx, void *cuda_stream);
 int  pm_sync(pm_ctx *ctx);
+/* Opt-in overlap of consecutive pm_knn2_ratio_l2_*_dev calls of equal shapes (default off).  With it on,
+ * the pack kernel of call i+1 starts while the finish / filter kernels of call i still run (it skips the
+ * stream-order wait; the library orders the two chains itself and every intermediate buffer exists twice).
+ * Contract: the input descriptors of such a call must be complete and visible when the call is enqueued
+ * (host-synchronised, or ordered by an event the ctx stream waits on) -- NOT produced by a kernel enqueued
+ * on the ctx stream right before it.  Outputs are ordered as usual: call i+1 never writes before call i
+ * has finished.  Results are identical with and without it. */
+int  pm_set_pipelining(pm_ctx *ctx, int on);
 const char *pm_last_error(pm_ctx *ctx);
 /* Number of libpm kernels launched by this ctx since creation (bench "gpu_launches"). */
 uint64_t pm_launch_count(pm_ctx *ctx);
@@ -100,6 +108,16 @@ int pm_knn2_l2_u8_dev(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt,
                       int q_index_base, pm_dmatch *dout);
 int pm_knn2_hamming_dev(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt,
                         int bytes, int q_index_base, pm_dmatch *dout);
+/* Device-resident knnMatch(k=2) + Lowe ratio test (main.cpp:43-69 as the north_star restates it) in
+ * ONE call: the whole chain pack -> GEMM/top-2 -> re-rank -> filter is enqueued together.  Same results
+ * as pm_knn2_l2_f32_dev followed by pm_ratio_filter_dev.  dknn [nq][2], dgood [nq], dn_good [1], all
+ * device memory. */
+int pm_knn2_ratio_l2_f32_dev(pm_ctx *ctx, const float *dq, int nq, const float *dt, int nt, int dim,
+                             float ratio, int q_index_base, pm_dmatch *dknn, pm_dmatch *dgood,
+                             int32_t *dn_good);
+int pm_knn2_ratio_l2_u8_dev(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, int dim,
+                            float ratio, int q_index_base, pm_dmatch *dknn, pm_dmatch *dgood,
+                            int32_t *dn_good);
 
 /* ---- good-match filters (main.cpp:49-69) -------------------------------------
  * Lowe ratio test over a [nq][2] kNN result: keep knn[i][0] iff both neighbours

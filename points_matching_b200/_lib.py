@@ -25,10 +25,11 @@ class RansacParams(C.Structure):
 
 # every symbol include/pm.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
-    "pm_version", "pm_create", "pm_destroy", "pm_set_stream", "pm_sync", "pm_last_error",
+    "pm_version", "pm_create", "pm_destroy", "pm_set_stream", "pm_sync", "pm_last_error", "pm_set_pipelining",
     "pm_launch_count", "pm_l2_stats", "pm_profile_enable", "pm_profile_read",
     "pm_knn2_l2_f32", "pm_knn2_l2_u8", "pm_knn2_hamming", "pm_knn2_ratio_l2_f32",
     "pm_knn2_l2_f32_dev", "pm_knn2_l2_u8_dev", "pm_knn2_hamming_dev",
+    "pm_knn2_ratio_l2_f32_dev", "pm_knn2_ratio_l2_u8_dev",
     "pm_ratio_filter", "pm_ratio_filter_dev", "pm_minmax_filter", "pm_minmax_filter_dev",
     "pm_match_cross_l2_f32", "pm_match_cross_hamming",
     "pm_col_best_hamming_dev", "pm_col_best_l2_f32_dev", "pm_cross_check_dev",

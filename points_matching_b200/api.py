@@ -70,6 +70,10 @@ class Context:
     def sync(self):
         self._chk(self._L.pm_sync(self._h))
 
+    def set_pipelining(self, on):
+        """Opt-in overlap of consecutive knn2_ratio_l2_*_dev calls (see pm_set_pipelining in include/pm.h)."""
+        self._chk(self._L.pm_set_pipelining(self._h, 1 if on else 0))
+
     def launch_count(self):
         return int(self._L.pm_launch_count(self._h))
 
@@ -277,6 +281,15 @@ class Context:
     def knn2_l2_f32_dev(self, dq, nq, dt, nt, dim, dout, q_index_base=0):
         self._chk(self._L.pm_knn2_l2_f32_dev(self._h, C.c_void_p(dq), nq, C.c_void_p(dt), nt, dim, q_index_base,
                                              C.c_void_p(dout)))
+
+    def knn2_ratio_l2_f32_dev(self, dq, nq, dt, nt, dim, ratio, dknn, dgood, dn_good, q_index_base=0):
+        """kNN-2 + ratio test enqueued as one chain (pack -> GEMM/top-2 -> re-rank -> filter)."""
+        self._chk(self._L.pm_knn2_ratio_l2_f32_dev(self._h, C.c_void_p(dq), nq, C.c_void_p(dt), nt, dim, C.c_float(ratio),
+                                                   q_index_base, C.c_void_p(dknn), C.c_void_p(dgood), C.c_void_p(dn_good)))
+
+    def knn2_ratio_l2_u8_dev(self, dq, nq, dt, nt, dim, ratio, dknn, dgood, dn_good, q_index_base=0):
+        self._chk(self._L.pm_knn2_ratio_l2_u8_dev(self._h, C.c_void_p(dq), nq, C.c_void_p(dt), nt, dim, C.c_float(ratio),
+                                                  q_index_base, C.c_void_p(dknn), C.c_void_p(dgood), C.c_void_p(dn_good)))
 
     def knn2_l2_u8_dev(self, dq, nq, dt, nt, dim, dout, q_index_base=0):
         self._chk(self._L.pm_knn2_l2_u8_dev(self._h, C.c_void_p(dq), nq, C.c_void_p(dt), nt, dim, q_index_base,

@@ -82,7 +82,9 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned 
 template <class Pred>
 __global__ void __launch_bounds__(FB) compact_lookback_kernel(Pred pred, int n, pm_dmatch *out, int32_t *n_out,
                                                               unsigned long long *status, unsigned *counter,
-                                                              unsigned epoch, int use_ticket, unsigned long long *span)
+                                                              unsigned epoch, int use_ticket, unsigned long long *span,
+                                                              unsigned long long *chain_done, unsigned *chain_ctr,
+                                                              unsigned long long chain_seq)
 {
     __shared__ int s_tile, s_prefix;
     pm_span_mark(span, 12, false);
@@ -133,11 +135,13 @@ __global__ void __launch_bounds__(FB) compact_lookback_kernel(Pred pred, int n, 
     }
     __syncthreads();
     if (f) out[s_prefix + ex] = m;
+    pm_chain_signal(chain_done, chain_ctr, chain_seq);
     pm_span_mark(span, 14, true);
 }
 
 template <class Pred>
-int run_compact(pm_ctx *ctx, Pred pred, int n, pm_dmatch *dout, int32_t *dn_out)
+int run_compact(pm_ctx *ctx, Pred pred, int n, pm_dmatch *dout, int32_t *dn_out, unsigned long long *chain_done = nullptr,
+                unsigned *chain_ctr = nullptr, unsigned long long chain_seq = 0)
 {
     if (n <= 0) {
         PM_CUDA(ctx, cudaMemsetAsync(dn_out, 0, sizeof(int32_t), ctx->stream));
@@ -155,12 +159,12 @@ int run_compact(pm_ctx *ctx, Pred pred, int n, pm_dmatch *dout, int32_t *dn_out)
     if (epoch >= (1u << 29)) {   // keep the 30-bit tag from wrapping into a stale match
         PM_CUDA(ctx, cudaMemsetAsync(st, 0, ctx->slot_bytes[WS_COUNT], ctx->stream));
         ctx->compact_epoch = 0;
-        return run_compact(ctx, pred, n, dout, dn_out);
+        return run_compact(ctx, pred, n, dout, dn_out, chain_done, chain_ctr, chain_seq);
     }
     unsigned *counter = reinterpret_cast<unsigned *>(st);          // st[0]: two ticket counters
     const int use_ticket = nb > ctx->num_sms;                      // <= 1 block per SM: all tiles resident at once
     PM_CUDA(ctx, pm_launch_pdl(compact_lookback_kernel<Pred>, dim3(nb), dim3(FB), 0, ctx->stream, pred, n, dout, dn_out, st + 1,
-                               counter, epoch, use_ticket, g_pm_span));
+                               counter, epoch, use_ticket, g_pm_span, chain_done, chain_ctr, chain_seq));
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }
@@ -212,6 +216,12 @@ __global__ void gather_matches_kernel(const pm_dmatch *__restrict__ m, const int
 int pmk_ratio_filter(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout, int32_t *dn_out)
 {
     return run_compact(ctx, RatioPred{dknn, ratio}, nq, dout, dn_out);
+}
+
+int pmk_ratio_filter_tail(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout, int32_t *dn_out,
+                          unsigned long long *chain_done, unsigned *chain_ctr, unsigned long long seq)
+{
+    return run_compact(ctx, RatioPred{dknn, ratio}, nq, dout, dn_out, chain_done, chain_ctr, seq);
 }
 
 int pmk_cross_check(pm_ctx *ctx, const pm_dmatch *dknn, int nq, int stride, const uint64_t *dcol_best, int nt,

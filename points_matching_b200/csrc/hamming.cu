@@ -356,10 +356,8 @@ int ham_tc_run(pm_ctx *ctx, const uint32_t *pq, int nq, const uint32_t *pt, int 
     const int mq_pad = pm_round_up(nq, 256), nt_pad = pm_round_up(nt, 256);
     const int MT = mq_pad / 256, NT = nt_pad / 128;
     const int smax = l2_tc_smax(ctx, MT, NT);
-    const bool fresh_flags = ctx->slot_ptr[WS_L2_FLAGS] == nullptr;
-    PM_WS(ctx, flags2, L2Flags *, WS_L2_FLAGS, 3 * sizeof(L2Flags));
-    if (fresh_flags) { PM_CUDA(ctx, cudaMemsetAsync(flags2, 0, 3 * sizeof(L2Flags), ctx->stream)); ctx->l2_parity = 0; }
-    L2Flags *flags = flags2 + ctx->l2_parity, *flags_next = flags2 + (ctx->l2_parity ^ 1);
+    L2Flags *flags, *flags_next, *tflags_unused;
+    { int fst = l2_flags_acquire(ctx, &flags, &flags_next, &tflags_unused); if (fst != PM_OK) return fst; }
     PM_WS(ctx, qx, uint8_t *, WS_Q_PACK, (size_t)mq_pad * L2_PACK_COLS);
     PM_WS(ctx, tx, uint8_t *, WS_T_PACK, (size_t)nt_pad * L2_PACK_COLS);
     PM_WS(ctx, qnorm, float *, WS_Q_NORM, (size_t)mq_pad * 4);
@@ -375,7 +373,6 @@ int ham_tc_run(pm_ctx *ctx, const uint32_t *pq, int nq, const uint32_t *pt, int 
     PM_CUDA(ctx, pm_launch_pdl(ham_tc_finish_kernel, dim3(fblocks), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3, pq, pt,
                                nq, nt, flags_next, q_index_base, mode, dout, (unsigned long long *)dcol));
     PM_CHECK_LAUNCH(ctx);
-    ctx->l2_parity ^= 1;
     return PM_OK;
 }
 

@@ -89,12 +89,23 @@ l2_pack_kernel(const T *__restrict__ q, int nq, int mq_pad, const T *__restrict_
                int vec, __nv_bfloat16 *__restrict__ qpack, __nv_bfloat16 *__restrict__ tpack,
                float *__restrict__ qnorm, uint8_t *__restrict__ text, uint8_t *__restrict__ q8, uint8_t *__restrict__ t8,
                float *__restrict__ tnorm, L2Flags *flags,
-               L2Cand *__restrict__ part, int part_per_row, const L2Flags *tflags_in, unsigned long long *span)
+               L2Cand *__restrict__ part, int part_per_row, const L2Flags *tflags_in, unsigned long long *span,
+               const unsigned long long *chain_done, unsigned long long wait_seq)
 {
     __shared__ unsigned s_max[2][8];
     __shared__ int s_nonint;
     pm_span_mark(span, 0, false);
-    pm_pdl_prologue();
+    if (chain_done) {
+        // pipelined chain (pm_set_pipelining): this launch does NOT wait for its stream predecessors -- it
+        // overlaps the finish / filter kernels of the previous chain.  It reads only the caller's inputs and
+        // writes only this chain's buffer set and flags block, which the previous chain does not touch; it
+        // waits for "K2 of the previous chain is past its waits" = everything before that chain is complete.
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        pm_chain_wait(chain_done, wait_seq);
+        __syncthreads();
+    } else {
+        pm_pdl_prologue();
+    }
     pm_span_mark(span, 1, false);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 7;
     if (threadIdx.x == 0) s_nonint = 0;
@@ -568,13 +579,37 @@ float *pm_l2_dump_ptr() { return g_l2_dump; }
 static int g_l2_force_exact = 0;
 extern "C" void pm_debug_force_exact(int on) { g_l2_force_exact = on; }
 
-// phase 0: pack query + train, K2, K3, fallback (one call).  The chunked host path (pm_api.cu) overlaps
-// the H2D copies with compute: phase 1 packs the train set only (flags -> the persistent train block),
-// phase 2 runs one query chunk against the train set packed by phase 1.
-int pmk_l2_knn2_phase(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
-                      int q_index_base, pm_dmatch *dout, int phase)
+int l2_flags_acquire(pm_ctx *ctx, L2Flags **cur, L2Flags **zero_next, L2Flags **tflags, bool advance)
 {
-    if (nq <= 0 && phase != 1) return PM_OK;
+    const bool fresh = ctx->slot_ptr[WS_L2_FLAGS] == nullptr;
+    PM_WS(ctx, f, L2Flags *, WS_L2_FLAGS, 4 * sizeof(L2Flags) + 64);
+    if (fresh) { PM_CUDA(ctx, cudaMemsetAsync(f, 0, 4 * sizeof(L2Flags) + 64, ctx->stream)); ctx->l2_rot = 0; }
+    *cur = f + ctx->l2_rot;
+    *zero_next = f + (ctx->l2_rot + 2) % 3;
+    *tflags = f + 3;
+    if (advance) ctx->l2_rot = (ctx->l2_rot + 1) % 3;      // only calls whose finish kernel zeroes *zero_next may advance
+    return PM_OK;
+}
+
+// One chain K1 -> K2 -> K3 (-> K5 when dgood is given).  phase 0: pack query + train, match (one call).  The
+// chunked host path (pm_api.cu) overlaps the H2D copies with compute: phase 1 packs the train set only
+// (flags -> the train-side block), phase 2 runs one query chunk against the train set packed by phase 1.
+//
+// Chain pipelining (opt-in, pm_set_pipelining; one-call kNN-2 + ratio chains only): every buffer K1 writes
+// exists twice and chains alternate between the sets, so K1 of chain s+1 may start while K3 / K5 of chain s
+// still run -- it skips griddepcontrol.wait when the previous kernel on the stream is the tail of chain s
+// with the same shapes.  Ordering is then carried by two device words: K2 of every signalling chain stores
+// its number to chain_mark once past its waits (= K1 of that chain and everything enqueued before the chain
+// have completed), the tail K5 stores it to chain_done.  K1(s+1) spins for chain_mark >= s, K2(s+1) spins
+// for chain_done >= s after its own griddepcontrol.wait, and K3 / K5 follow K2 by PDL.  (K3 applying the ratio test itself was tried as well: with 313 32-row tiles the
+// ordered prefix inside K3 cost 8-10 us against 3.8 us for K5 behind one PDL boundary.)
+static int l2_chain(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
+                    int q_index_base, pm_dmatch *dout, int phase, float ratio, pm_dmatch *dgood, int32_t *dn_good)
+{
+    if (nq <= 0 && phase != 1) {
+        if (dgood) PM_CUDA(ctx, cudaMemsetAsync(dn_good, 0, sizeof(int32_t), ctx->stream));
+        return PM_OK;
+    }
     // K2 work items are 256 query rows x 128 train columns
     const int mq_pad = phase == 1 ? 0 : pm_round_up(nq, 256), nt_pad = pm_round_up(nt > 0 ? nt : 1, 256);
     const int MT = mq_pad / 256, NT = nt_pad / 128;
@@ -583,57 +618,80 @@ int pmk_l2_knn2_phase(pm_ctx *ctx, const void *dq, int nq, const void *dt, int n
     ctx->l2_stats[2] = 0; ctx->l2_stats[3] = 0;
     if (!use_tc) {
         if (phase == 1) return PM_OK;
-        if (is_u8) return run_exact(ctx, (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, q_index_base, dout);
-        return run_exact(ctx, (const float *)dq, (const float *)dt, nq, nt, dim, q_index_base, dout);
+        int st = is_u8 ? run_exact(ctx, (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, q_index_base, dout)
+                       : run_exact(ctx, (const float *)dq, (const float *)dt, nq, nt, dim, q_index_base, dout);
+        if (st != PM_OK || !dgood) return st;
+        return pmk_ratio_filter(ctx, dout, nq, ratio, dgood, dn_good);
     }
-    const bool fresh_flags = ctx->slot_ptr[WS_L2_FLAGS] == nullptr;
-    PM_WS(ctx, flags2, L2Flags *, WS_L2_FLAGS, 3 * sizeof(L2Flags));
-    if (fresh_flags) { PM_CUDA(ctx, cudaMemsetAsync(flags2, 0, 3 * sizeof(L2Flags), ctx->stream)); ctx->l2_parity = 0; }
-    // two flag blocks: this call uses one, K3 zeroes the other for the next call (no memset); the third
-    // block holds the train side's flags between phase 1 and the phase 2 calls
-    L2Flags *flags = flags2 + ctx->l2_parity, *flags_next = flags2 + (ctx->l2_parity ^ 1), *tflags = flags2 + 2;
-    PM_WS(ctx, tpack, __nv_bfloat16 *, WS_T_PACK, (size_t)nt_pad * L2_PACK_COLS * 2);
-    PM_WS(ctx, text, uint8_t *, WS_T_NORM, (size_t)(nt_pad / 128) * L2_EXT_BYTES);
-    PM_WS(ctx, t8, uint8_t *, WS_T_U8, (size_t)nt_pad * L2_KDIM);
-    PM_WS(ctx, tnormf, float *, WS_T_NORMF, (size_t)nt_pad * 4);
+    // ---- chain pipelining state ----
+    const bool signalling = ctx->pipelining && phase == 0 && dgood != nullptr;     // this chain's tail stores its number
+    const bool same_shape = ctx->chain_shape[0] == nq && ctx->chain_shape[1] == nt && ctx->chain_shape[2] == dim &&
+                            ctx->chain_shape[3] == is_u8;
+    const bool run_ahead = signalling && ctx->tail_is_chain && same_shape;          // K1 skips griddepcontrol.wait
+    const unsigned long long seq = signalling ? ctx->chain_seq + 1 : 0;
+    const int set = signalling ? (int)(seq & 1) : 0;                                // buffer set of this chain
+    const int nset = ctx->pipelining ? 2 : 1;
+    L2Flags *flags, *flags_next, *tflags;
+    { int fst = l2_flags_acquire(ctx, &flags, &flags_next, &tflags, phase != 1); if (fst != PM_OK) return fst; }
+    unsigned long long *chain_done = reinterpret_cast<unsigned long long *>(tflags + 1);   // [0] done, [1] mark, [2] block counter
+    unsigned long long *chain_mark = chain_done + 1;
+    unsigned *chain_ctr = reinterpret_cast<unsigned *>(chain_done + 2);
+    // every workspace K1 writes, sized for `nset` copies; `set` selects one
+    auto ws2 = [&](int slot, size_t bytes) -> uint8_t * {
+        const size_t each = (bytes + 255) & ~(size_t)255;
+        uint8_t *base = (uint8_t *)pm_ws(ctx, slot, each * nset);
+        return base ? base + each * set : nullptr;
+    };
+#define L2_WS2(var, type, slot, bytes) type var = (type)ws2(slot, bytes); if (!var) return PM_CUDA_ERR
+    L2_WS2(tpack, __nv_bfloat16 *, WS_T_PACK, (size_t)nt_pad * L2_PACK_COLS * 2);
+    L2_WS2(text, uint8_t *, WS_T_NORM, (size_t)(nt_pad / 128) * L2_EXT_BYTES);
+    L2_WS2(t8, uint8_t *, WS_T_U8, (size_t)nt_pad * L2_KDIM);
+    L2_WS2(tnormf, float *, WS_T_NORMF, (size_t)nt_pad * 4);
     const int vec_u8 = dim == L2_KDIM && (((uintptr_t)dq | (uintptr_t)dt) & 3) == 0;
     const int vec_f32 = dim == L2_KDIM && (((uintptr_t)dq | (uintptr_t)dt) & 15) == 0;
     const int vec = is_u8 ? vec_u8 : vec_f32;
+    const unsigned long long *no_chain = nullptr;
     if (phase == 1) {
         PM_CUDA(ctx, cudaMemsetAsync(tflags, 0, sizeof(L2Flags), ctx->stream));
         const int blocks = min(pm_cdiv(nt_pad, 32), 8 * ctx->num_sms);
         if (is_u8)
             PM_CUDA(ctx, pm_launch_pdl(l2_pack_kernel<uint8_t>, dim3(blocks), dim3(256), 0, ctx->stream, (const uint8_t *)nullptr, 0, 0,
                                        (const uint8_t *)dt, nt, nt_pad, dim, vec, (__nv_bfloat16 *)nullptr, tpack, (float *)nullptr, text,
-                                       (uint8_t *)nullptr, t8, tnormf, tflags, (L2Cand *)nullptr, 0, (const L2Flags *)nullptr, g_pm_span));
+                                       (uint8_t *)nullptr, t8, tnormf, tflags, (L2Cand *)nullptr, 0, (const L2Flags *)nullptr, g_pm_span,
+                                       no_chain, 0ull));
         else
             PM_CUDA(ctx, pm_launch_pdl(l2_pack_kernel<float>, dim3(blocks), dim3(256), 0, ctx->stream, (const float *)nullptr, 0, 0,
                                        (const float *)dt, nt, nt_pad, dim, vec, (__nv_bfloat16 *)nullptr, tpack, (float *)nullptr, text,
-                                       (uint8_t *)nullptr, t8, tnormf, tflags, (L2Cand *)nullptr, 0, (const L2Flags *)nullptr, g_pm_span));
+                                       (uint8_t *)nullptr, t8, tnormf, tflags, (L2Cand *)nullptr, 0, (const L2Flags *)nullptr, g_pm_span,
+                                       no_chain, 0ull));
         PM_CHECK_LAUNCH(ctx);
         return PM_OK;
     }
-    PM_WS(ctx, qpack, __nv_bfloat16 *, WS_Q_PACK, (size_t)mq_pad * L2_PACK_COLS * 2);
-    PM_WS(ctx, qnorm, float *, WS_Q_NORM, (size_t)mq_pad * 4);
-    PM_WS(ctx, q8, uint8_t *, WS_Q_U8, (size_t)mq_pad * L2_KDIM);
-    PM_WS(ctx, part, L2Cand *, WS_L2_PART, (size_t)mq_pad * smax * 3 * sizeof(L2Cand));
-    PM_WS(ctx, flagged, int *, WS_L2_FLAGGED, (size_t)nq * 4);
-    PM_WS(ctx, fbpart, unsigned long long *, WS_L2_FBPART, (size_t)FB_ROWS * pm_cdiv(nt, FB_CHUNK) * 16);
+    L2_WS2(qpack, __nv_bfloat16 *, WS_Q_PACK, (size_t)mq_pad * L2_PACK_COLS * 2);
+    L2_WS2(qnorm, float *, WS_Q_NORM, (size_t)mq_pad * 4);
+    L2_WS2(q8, uint8_t *, WS_Q_U8, (size_t)mq_pad * L2_KDIM);
+    L2_WS2(part, L2Cand *, WS_L2_PART, (size_t)mq_pad * smax * 3 * sizeof(L2Cand));
+    L2_WS2(flagged, int *, WS_L2_FLAGGED, (size_t)nq * 4);
+    L2_WS2(fbpart, unsigned long long *, WS_L2_FBPART, (size_t)FB_ROWS * pm_cdiv(nt, FB_CHUNK) * 16);
+#undef L2_WS2
     // K3: 8 lanes per row, 32 rows per block, at most one resident wave (a second wave would double its latency)
     const int fin_blocks = min(pm_cdiv(nq, 32), 3 * ctx->num_sms);
     const int pack_nt = phase == 2 ? 0 : nt, pack_nt_pad = phase == 2 ? 0 : nt_pad;
     const L2Flags *tflags_in = phase == 2 ? tflags : nullptr;
     const int pack_blocks = min(pm_cdiv(mq_pad + pack_nt_pad, 32), 8 * ctx->num_sms);
+    const unsigned long long *k1_done = run_ahead ? chain_mark : nullptr;
+    const unsigned long long k1_wait = run_ahead ? seq - 1 : 0;
     if (is_u8)
         PM_CUDA(ctx, pm_launch_pdl(l2_pack_kernel<uint8_t>, dim3(pack_blocks), dim3(256), 0, ctx->stream, (const uint8_t *)dq, nq, mq_pad,
                                    (const uint8_t *)dt, pack_nt, pack_nt_pad, dim, vec, qpack, tpack, qnorm, text, q8, t8, tnormf, flags, part, smax * 3,
-                                   tflags_in, g_pm_span));
+                                   tflags_in, g_pm_span, k1_done, k1_wait));
     else
         PM_CUDA(ctx, pm_launch_pdl(l2_pack_kernel<float>, dim3(pack_blocks), dim3(256), 0, ctx->stream, (const float *)dq, nq, mq_pad,
                                    (const float *)dt, pack_nt, pack_nt_pad, dim, vec, qpack, tpack, qnorm, text, q8, t8, tnormf, flags, part, smax * 3,
-                                   tflags_in, g_pm_span));
+                                   tflags_in, g_pm_span, k1_done, k1_wait));
     PM_CHECK_LAUNCH(ctx);
-    int st = l2_tc_launch(ctx, qpack, mq_pad, tpack, nt_pad, text, flags, part, smax, g_l2_dump, 0);
+    int st = l2_tc_launch(ctx, qpack, mq_pad, tpack, nt_pad, text, flags, part, smax, g_l2_dump, 0, set,
+                          run_ahead ? chain_done : nullptr, run_ahead ? seq - 1 : 0, signalling ? chain_mark : nullptr, seq);
     if (st != PM_OK) return st;
     if (is_u8)
         PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<uint8_t>, dim3(fin_blocks), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,
@@ -646,9 +704,27 @@ int pmk_l2_knn2_phase(pm_ctx *ctx, const void *dq, int nq, const void *dt, int n
                                    (const float *)dq, (const float *)dt, nq, nt, dim, vec_f32, flags, flags_next, flagged, fbpart,
                                    q_index_base, dout, g_pm_span));
     PM_CHECK_LAUNCH(ctx);
-    ctx->l2_parity ^= 1;
     ctx->l2_stats[3] = smax;
+    if (!dgood) return PM_OK;
+    if (!signalling) return pmk_ratio_filter(ctx, dout, nq, ratio, dgood, dn_good);
+    st = pmk_ratio_filter_tail(ctx, dout, nq, ratio, dgood, dn_good, chain_done, chain_ctr, seq);
+    if (st != PM_OK) return st;
+    ctx->chain_seq = seq;
+    ctx->tail_is_chain = true;              // cleared by the next launch of any other kind (PM_CHECK_LAUNCH)
+    ctx->chain_shape[0] = nq; ctx->chain_shape[1] = nt; ctx->chain_shape[2] = dim; ctx->chain_shape[3] = is_u8;
     return PM_OK;
+}
+
+int pmk_l2_knn2_fused(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
+                      int q_index_base, pm_dmatch *dout, int phase, float ratio, pm_dmatch *dgood, int32_t *dn_good)
+{
+    return l2_chain(ctx, dq, nq, dt, nt, dim, is_u8, q_index_base, dout, phase, ratio, dgood, dn_good);
+}
+
+int pmk_l2_knn2_phase(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
+                      int q_index_base, pm_dmatch *dout, int phase)
+{
+    return l2_chain(ctx, dq, nq, dt, nt, dim, is_u8, q_index_base, dout, phase, 0.f, nullptr, nullptr);
 }
 
 int pmk_l2_knn2(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
@@ -663,7 +739,7 @@ int pm_l2_stats(pm_ctx *ctx, int32_t out[4])
     L2Flags h = {};
     if (ctx->slot_ptr[WS_L2_FLAGS]) {     // the block the last call used (parity was flipped after it)
         PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        PM_CUDA(ctx, cudaMemcpy(&h, (const L2Flags *)ctx->slot_ptr[WS_L2_FLAGS] + (ctx->l2_parity ^ 1), sizeof(h),
+        PM_CUDA(ctx, cudaMemcpy(&h, (const L2Flags *)ctx->slot_ptr[WS_L2_FLAGS] + (ctx->l2_rot + 2) % 3, sizeof(h),
                                 cudaMemcpyDeviceToHost));
     }
     const bool exact = l2_exact_mode(h);

@@ -133,4 +133,10 @@ float *pm_l2_dump_ptr();      // debug: K2 dumps its (||b||^2 - 2ab) tile values
 int l2_tc_grid(pm_ctx *ctx, int MT, int NT);
 int l2_tc_smax(pm_ctx *ctx, int MT, int NT);
 int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, int nt_pad,
-                 const void *text, const L2Flags *flags, L2Cand *part, int smax, float *dump, int fp8);
+                 const void *text, const L2Flags *flags, L2Cand *part, int smax, float *dump, int fp8,
+                 int tmap_set = 0, const unsigned long long *chain_done = nullptr, unsigned long long wait_seq = 0,
+                 unsigned long long *chain_mark = nullptr, unsigned long long mark_seq = 0);
+// This call's flags block (zero on entry), the block its finish kernel must zero (it serves the call after
+// the next: three blocks rotate so that a pipelined chain never touches a block the previous chain still
+// uses) and the train-side block of the chunked host path.
+int l2_flags_acquire(pm_ctx *ctx, L2Flags **cur, L2Flags **zero_next, L2Flags **tflags, bool advance = true);

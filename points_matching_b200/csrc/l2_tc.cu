@@ -284,6 +284,10 @@ struct TcParams {
     float *dump;                 // debug: [mq_pad][nt_pad] of (||b||^2 - 2ab), or null
     int MT, NT, smax, nt_pad;
     int tq, tr;                  // work items per CTA: CTA c owns tq + (c < tr) consecutive items (T = G * tq + tr)
+    const unsigned long long *chain_done;   // chain pipelining: spin until *chain_done >= wait_seq (null: no spin)
+    unsigned long long wait_seq;
+    unsigned long long *chain_mark;         // signalling chains: store mark_seq once past the waits (null: none)
+    unsigned long long mark_seq;
     unsigned long long *span;    // debug timeline (pm_internal.h), or null
     long long *trace;            // PM_K2_TRACE builds: clock64 stamps of CTA 0, [tile][16]
     uint32_t mul256;             // == 256, passed at run time so the key pack stays an IMAD (FMA pipe), not an ALU LEA
@@ -349,6 +353,13 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     TRK(1);
     pm_span_mark(P.span, 3, false);
     pm_pdl_prologue();
+    // pipelined chains: K1 of this chain ran ahead of the previous chain's tail; nothing below may start
+    // before that chain has completed (the __syncthreads further down holds the other threads)
+    pm_chain_wait(P.chain_done, P.wait_seq);
+    // "K2 of chain s is past its waits" = K1(s) and everything enqueued before chain s have completed: the
+    // word K1 of chain s+1 spins on when it runs ahead
+    if (P.chain_mark && blockIdx.x == 0 && threadIdx.x == 0)
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(P.chain_mark), "l"(P.mark_seq) : "memory");
     pm_span_mark(P.span, 4, false);      // K1's outputs (flags, packed operands, norm images) are complete past this point
     TRK(2);
     const L2Flags fl = *P.flags;
@@ -635,7 +646,9 @@ int l2_tc_smax(pm_ctx *ctx, int MT, int NT)
 }
 
 int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, int nt_pad,
-                 const void *text, const L2Flags *flags, L2Cand *part, int smax, float *dump, int fp8)
+                 const void *text, const L2Flags *flags, L2Cand *part, int smax, float *dump, int fp8,
+                 int tmap_set, const unsigned long long *chain_done, unsigned long long wait_seq,
+                 unsigned long long *chain_mark, unsigned long long mark_seq)
 {
     static bool attr_set = false;
     if (!attr_set) {
@@ -644,20 +657,23 @@ int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, 
         attr_set = true;
     }
     static_assert(sizeof(CUtensorMap) == 128, "tmap_store size");
-    CUtensorMap *tmaps = reinterpret_cast<CUtensorMap *>(ctx->tmap_store);
+    CUtensorMap *tmaps = reinterpret_cast<CUtensorMap *>(ctx->tmap_store) + 2 * tmap_set;   // one cached pair per buffer set
     const void *bases[2] = {qpack, tpack};
     const int rows[2] = {mq_pad, nt_pad}, boxes[2] = {BM, BN};
-    for (int k = 0; k < 2; ++k)
-        if (ctx->tmap_base[k] != bases[k] || ctx->tmap_rows[k] != rows[k] || ctx->tmap_fp8[k] != fp8) {   // re-encode only when the operand moved
+    for (int k = 0; k < 2; ++k) {
+        const int c = 2 * tmap_set + k;
+        if (ctx->tmap_base[c] != bases[k] || ctx->tmap_rows[c] != rows[k] || ctx->tmap_fp8[c] != fp8) {   // re-encode only when the operand moved
             int st = make_tmap(ctx, &tmaps[k], bases[k], rows[k], boxes[k], fp8);
             if (st != PM_OK) return st;
-            ctx->tmap_base[k] = bases[k]; ctx->tmap_rows[k] = rows[k]; ctx->tmap_fp8[k] = fp8;
+            ctx->tmap_base[c] = bases[k]; ctx->tmap_rows[c] = rows[k]; ctx->tmap_fp8[c] = fp8;
         }
+    }
     const CUtensorMap &tq = tmaps[0], &tt = tmaps[1];
     TcParams P;
     P.text = (const uint8_t *)text; P.flags = flags; P.part = part; P.dump = dump;
     P.MT = mq_pad / (MH * BM); P.NT = nt_pad / BN; P.smax = smax; P.nt_pad = nt_pad; P.mul256 = 256u;
     P.trace = g_k2_trace; P.span = g_pm_span;
+    P.chain_done = chain_done; P.wait_seq = wait_seq; P.chain_mark = chain_mark; P.mark_seq = mark_seq;
     if ((long long)P.MT * P.NT >= (1ll << 30)) return pm_fail(ctx, PM_BAD_ARG, "L2 matching: more than 2^30 work items");
     const int G = l2_tc_grid(ctx, P.MT, P.NT);
     P.tq = (P.MT * P.NT) / G; P.tr = (P.MT * P.NT) % G;

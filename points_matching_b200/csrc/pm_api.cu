@@ -93,6 +93,20 @@ int pm_set_stream(pm_ctx *ctx, void *s)
 {
     if (!ctx) return PM_BAD_ARG;
     ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    ctx->tail_is_chain = false;
+    return PM_OK;
+}
+
+int pm_set_pipelining(pm_ctx *ctx, int on)
+{
+    if (!ctx) return PM_BAD_ARG;
+    if ((on != 0) != (ctx->pipelining != 0)) {
+        // the workspace layout changes (one buffer set <-> two): drain the stream first
+        PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->pipelining = on != 0;
+        ctx->tail_is_chain = false;
+        for (int k = 0; k < 4; ++k) ctx->tmap_base[k] = nullptr;
+    }
     return PM_OK;
 }
 
@@ -155,6 +169,22 @@ int pm_knn2_l2_u8_dev(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt,
     PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && dim > 0, "negative size or dim <= 0");
     PM_REQUIRE(ctx, nq == 0 || (dq && dout), "null pointer");
     return pmk_l2_knn2(ctx, dq, nq, dt, nt, dim, 1, base, dout);
+}
+int pm_knn2_ratio_l2_f32_dev(pm_ctx *ctx, const float *dq, int nq, const float *dt, int nt, int dim, float ratio, int base,
+                             pm_dmatch *dknn, pm_dmatch *dgood, int32_t *dn_good)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && dim > 0 && dn_good, "negative size, dim <= 0 or null count");
+    PM_REQUIRE(ctx, nq == 0 || (dq && dknn && dgood), "null pointer");
+    return pmk_l2_knn2_fused(ctx, dq, nq, dt, nt, dim, 0, base, dknn, 0, ratio, dgood, dn_good);
+}
+int pm_knn2_ratio_l2_u8_dev(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, int dim, float ratio, int base,
+                            pm_dmatch *dknn, pm_dmatch *dgood, int32_t *dn_good)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && dim > 0 && dn_good, "negative size, dim <= 0 or null count");
+    PM_REQUIRE(ctx, nq == 0 || (dq && dknn && dgood), "null pointer");
+    return pmk_l2_knn2_fused(ctx, dq, nq, dt, nt, dim, 1, base, dknn, 0, ratio, dgood, dn_good);
 }
 int pm_knn2_hamming_dev(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, int bytes, int base, pm_dmatch *dout)
 {

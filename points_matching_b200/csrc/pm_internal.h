@@ -33,13 +33,18 @@ struct pm_ctx {
     std::string err;
     int32_t l2_stats[4] = {0, 0, 0, 0};
     unsigned compact_epoch = 0;    // filter.cu: tag of the current compaction call
-    int l2_parity = 0;             // l2.cu: which of the two L2Flags blocks this call uses
+    int l2_rot = 0;                // l2.cu: which of the three rotating L2Flags blocks the next call uses
+    // opt-in chain pipelining (pm_set_pipelining, l2.cu): consecutive one-call kNN-2 + ratio chains overlap
+    int pipelining = 0;
+    bool tail_is_chain = false;    // the last kernel enqueued through this ctx is the tail of signalling chain `chain_seq`
+    unsigned long long chain_seq = 0;   // signalling chains enqueued so far (the tail of chain s stores s to chain_done)
+    int chain_shape[4] = {0, 0, 0, 0};  // nq, nt, dim, is_u8 of the last signalling chain
     void *tmap_encode = nullptr;   // cuTensorMapEncodeTiled entry point
-    // cached TMA descriptors (l2_tc.cu): [0] query operand, [1] train operand
-    alignas(64) unsigned char tmap_store[2][128] = {};
-    const void *tmap_base[2] = {nullptr, nullptr};
-    int tmap_rows[2] = {0, 0};
-    int tmap_fp8[2] = {-1, -1};
+    // cached TMA descriptors (l2_tc.cu): [2 * set + 0] query operand, [2 * set + 1] train operand
+    alignas(64) unsigned char tmap_store[4][128] = {};
+    const void *tmap_base[4] = {nullptr, nullptr, nullptr, nullptr};
+    int tmap_rows[4] = {0, 0, 0, 0};
+    int tmap_fp8[4] = {-1, -1, -1, -1};
     int32_t *h_pinned = nullptr;   // 4 KB pinned scratch for small D2H reads
     // chunked host path (pm_api.cu): uploads run on their own stream, one event per query chunk
     cudaStream_t copy_stream = nullptr;
@@ -77,6 +82,7 @@ void *pm_ws(pm_ctx *ctx, int slot, size_t bytes);   // nullptr on failure (ctx->
 #define PM_CHECK_LAUNCH(ctx)                                                            \
     do {                                                                                \
         (ctx)->launches++;                                                              \
+        (ctx)->tail_is_chain = false;                                                   \
         cudaError_t e__ = cudaGetLastError();                                           \
         if (e__ != cudaSuccess)                                                         \
             return pm_fail(ctx, PM_CUDA_ERR, "%s:%d launch: %s", __FILE__, __LINE__,    \
@@ -111,6 +117,33 @@ __device__ __forceinline__ void pm_pdl_prologue()
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// Chain pipelining (pm_set_pipelining): the tail kernel of signalling chain s stores s to *chain_done once its
+// last block is done; a kernel of a later chain that may run ahead of its stream predecessors spins here
+// (one thread; the caller follows with __syncthreads) until chain `seq` has completed.  Every CTA of the
+// awaited chain was started before the spinning kernel could launch (PDL launches cascade in stream
+// order), so the spin cannot starve it.
+__device__ __forceinline__ void pm_chain_wait(const unsigned long long *chain_done, unsigned long long seq)
+{
+    if (chain_done && threadIdx.x == 0) {
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(chain_done) : "memory");
+        } while (v < seq);
+    }
+}
+// tail of a chain: the last block to arrive publishes the sequence number (ctr returns to 0)
+__device__ __forceinline__ void pm_chain_signal(unsigned long long *chain_done, unsigned *ctr, unsigned long long seq)
+{
+    if (!chain_done) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ctr, 1u) == gridDim.x - 1) {
+            *ctr = 0u;
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(chain_done), "l"(seq) : "memory");
+        }
+    }
+}
 template <typename... KArgs, typename... Args>
 static inline cudaError_t pm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                         cudaStream_t stream, Args... args)
@@ -137,6 +170,9 @@ int pmk_hamming_col_best(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *
 // filter.cu
 int pmk_ratio_filter(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout,
                      int32_t *dn_out);
+// same, as the tail of signalling chain `seq` (stores seq to chain_done when the last block is done)
+int pmk_ratio_filter_tail(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout,
+                          int32_t *dn_out, unsigned long long *chain_done, unsigned *chain_ctr, unsigned long long seq);
 int pmk_cross_check(pm_ctx *ctx, const pm_dmatch *dknn, int nq, int stride, const uint64_t *dcol_best,
                     int nt, pm_dmatch *dout, int32_t *dn_out);
 int pmk_minmax_filter(pm_ctx *ctx, const pm_dmatch *dm, int n, int stride, pm_dmatch *dout,
@@ -149,6 +185,8 @@ int pmk_l2_knn2(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int
                 int q_index_base, pm_dmatch *dout);
 int pmk_l2_knn2_phase(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
                       int q_index_base, pm_dmatch *dout, int phase);
+int pmk_l2_knn2_fused(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
+                      int q_index_base, pm_dmatch *dout, int phase, float ratio, pm_dmatch *dgood, int32_t *dn_good);
 int pmk_l2_col_best(pm_ctx *ctx, const float *dq, int nq, const float *dt, int nt, int dim,
                     int q_index_base, uint64_t *dcol_best);
 // ransac.cu

@@ -219,6 +219,103 @@ def test_filters_vs_oracle(ctx, pm, orc):
     assert mn == 1.0
 
 
+@pytest.mark.parametrize("kind,nq,nt", [("sift", 10000, 10000), ("sift", 1, 300), ("sift", 31, 129), ("sift", 15000, 700),
+                                        ("sift", 32768, 300), ("sift", 33000, 300), ("surf", 5000, 6000),
+                                        ("surf", 20000, 1000), ("wide", 700, 900)])
+def test_fused_knn2_ratio_equals_two_calls(ctx, pm, kind, nq, nt):
+    """pm_knn2_ratio_l2_f32_dev (one call, one chain) == pm_knn2_l2_f32_dev + pm_ratio_filter_dev, bit for
+    bit, in exact mode, split mode (fallback rows are filtered after the fallback), multi-pass sizes and
+    dim > 128 (no tensor path)."""
+    torch = _dev(ctx)
+    if kind == "sift":
+        q, t = synth.sift_pair(nq, nt, seed=nq + 3)
+    elif kind == "surf":
+        q, t = synth.surf_pair(nq, nt, seed=nq + 5)
+    else:
+        rng = np.random.default_rng(1)
+        q, t = rng.normal(0, 1, (nq, 200)).astype(np.float32), rng.normal(0, 1, (nt, 200)).astype(np.float32)
+    dim = q.shape[1]
+    dq, dt = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    knn_a = torch.zeros((nq, 2, 4), dtype=torch.int32, device="cuda"); knn_b = torch.zeros_like(knn_a)
+    good_a = torch.zeros((nq, 4), dtype=torch.int32, device="cuda"); good_b = torch.zeros_like(good_a)
+    n_a = torch.full((1,), -1, dtype=torch.int32, device="cuda"); n_b = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+    for ratio in (0.75, 0.9):
+        ctx.knn2_l2_f32_dev(dq.data_ptr(), nq, dt.data_ptr(), nt, dim, knn_a.data_ptr(), 7)
+        ctx.ratio_filter_dev(knn_a.data_ptr(), nq, ratio, good_a.data_ptr(), n_a.data_ptr())
+        for _ in range(3):          # repeated calls: epoch-tagged status words / ping-pong buffers are never cleared
+            good_b.zero_(); n_b.fill_(-1)
+            ctx.knn2_ratio_l2_f32_dev(dq.data_ptr(), nq, dt.data_ptr(), nt, dim, ratio, knn_b.data_ptr(), good_b.data_ptr(),
+                                      n_b.data_ptr(), 7)
+            torch.cuda.synchronize()
+            na, nb = int(n_a.item()), int(n_b.item())
+            assert na == nb and (kind == "wide" or nq < 100 or 0 < na < nq)
+            assert torch.equal(knn_a, knn_b)
+            assert torch.equal(good_a[:na], good_b[:nb])
+    if kind == "surf":
+        assert not ctx.l2_stats()["exact_mode"]
+
+
+@pytest.mark.parametrize("kind,nq,nt,calls", [("sift", 10000, 10000, 40), ("sift", 300, 500, 300), ("sift", 2000, 700, 100),
+                                              ("surf", 3000, 4000, 40), ("surf", 257, 300, 200)])
+def test_pipelined_chains_equal_serial(ctx, pm, kind, nq, nt, calls):
+    """pm_set_pipelining: back-to-back one-call chains overlap (K1 of call i+1 runs ahead of K3/K5 of call i, two
+    buffer sets) and still give the serial results bit for bit -- distinct input sets per call, outputs into
+    per-call buffers and into one shared buffer, with other libpm calls (kNN only, another shape, Hamming on
+    the tensor path, which shares the workspaces) interleaved."""
+    torch = _dev(ctx)
+    gen = synth.sift_pair if kind == "sift" else synth.surf_pair
+    sets = []
+    for k in range(4):
+        q, t = gen(nq, nt, seed=100 + k)
+        sets.append((torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()))
+    new = lambda: (torch.zeros((nq, 2, 4), dtype=torch.int32, device="cuda"), torch.zeros((nq, 4), dtype=torch.int32, device="cuda"),
+                   torch.full((1,), -1, dtype=torch.int32, device="cuda"))
+    serial = []
+    for dq, dt in sets:
+        o = new()
+        ctx.knn2_ratio_l2_f32_dev(dq.data_ptr(), nq, dt.data_ptr(), nt, 128, 0.8, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), 3)
+        serial.append(o)
+    torch.cuda.synchronize()
+    hq = torch.randint(0, 256, (5000, 32), dtype=torch.uint8, device="cuda")
+    hknn = torch.zeros((5000, 2, 4), dtype=torch.int32, device="cuda")
+    oq, ot = sets[0][0][: max(1, nq // 2)].contiguous(), sets[1][1][: max(2, nt // 3)].contiguous()
+    oknn = torch.zeros((oq.shape[0], 2, 4), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.set_pipelining(True)
+    try:
+        outs = [new() for _ in range(calls)]
+        shared = new()
+        for i in range(calls):
+            dq, dt = sets[i % 4]
+            o = outs[i]
+            ctx.knn2_ratio_l2_f32_dev(dq.data_ptr(), nq, dt.data_ptr(), nt, 128, 0.8, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), 3)
+            if i % 11 == 5:      # a kNN-only call of another shape in between (not a signalling chain)
+                ctx.knn2_l2_f32_dev(oq.data_ptr(), oq.shape[0], ot.data_ptr(), ot.shape[0], 128, oknn.data_ptr(), 0)
+            if i % 17 == 9:      # Hamming on the tensor path: same workspaces, another chain
+                ctx.knn2_hamming_dev(hq.data_ptr(), 5000, hq.data_ptr(), 5000, 32, hknn.data_ptr(), 0)
+        for i in range(calls):   # and everything into ONE set of output buffers
+            dq, dt = sets[i % 4]
+            ctx.knn2_ratio_l2_f32_dev(dq.data_ptr(), nq, dt.data_ptr(), nt, 128, 0.8, shared[0].data_ptr(), shared[1].data_ptr(),
+                                      shared[2].data_ptr(), 3)
+        torch.cuda.synchronize()
+    finally:
+        ctx.set_pipelining(False)
+    for i in range(calls):
+        ref, o = serial[i % 4], outs[i]
+        n = int(ref[2].item())
+        assert int(o[2].item()) == n, i
+        assert torch.equal(o[0], ref[0]), i
+        assert torch.equal(o[1][:n], ref[1][:n]), i
+    ref = serial[(calls - 1) % 4]
+    n = int(ref[2].item())
+    assert int(shared[2].item()) == n and torch.equal(shared[0], ref[0]) and torch.equal(shared[1][:n], ref[1][:n])
+    # the interleaved calls were not disturbed either
+    chk = torch.zeros_like(oknn)
+    ctx.knn2_l2_f32_dev(oq.data_ptr(), oq.shape[0], ot.data_ptr(), ot.shape[0], 128, chk.data_ptr(), 0)
+    torch.cuda.synchronize()
+    assert torch.equal(chk, oknn)
+
+
 # --------------------------------------------------------------------------- RANSAC
 def _dev(ctx):
     import torch

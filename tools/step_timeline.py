@@ -14,7 +14,13 @@ dq, dt = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
 knn = torch.zeros((NQ, 2, 4), dtype=torch.int32, device="cuda")
 good = torch.zeros((NQ, 4), dtype=torch.int32, device="cuda")
 ng = torch.zeros(4, dtype=torch.int32, device="cuda")
+FUSED = os.environ.get("PM_FUSED", "1") != "0"
+if os.environ.get("PM_PIPE", "0") != "0":
+    ctx.set_pipelining(True)
 def step():
+    if FUSED:      # one call, same chain
+        ctx.knn2_ratio_l2_f32_dev(dq.data_ptr(), NQ, dt.data_ptr(), NT, 128, 0.75, knn.data_ptr(), good.data_ptr(), ng.data_ptr(), 0)
+        return
     ctx.knn2_l2_f32_dev(dq.data_ptr(), NQ, dt.data_ptr(), NT, 128, knn.data_ptr(), 0)
     ctx.ratio_filter_dev(knn.data_ptr(), NQ, 0.75, good.data_ptr(), ng.data_ptr())
 for _ in range(200):
@@ -48,6 +54,14 @@ blk = r[32:32 + 2 * 313].reshape(-1, 2)
 st, en = (blk[:, 0] - r[7]) / 1e3, (blk[:, 1] - r[7]) / 1e3
 print("K3 per-block (us after the first block passed the wait): start min/med/max %.2f %.2f %.2f  end min/med/max %.2f %.2f %.2f  dur med %.2f max %.2f"
       % (st.min(), np.median(st), st.max(), en.min(), np.median(en), en.max(), np.median(en - st), (en - st).max()))
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for _ in range(200):
+    step()
+ev0.record(stream)
+for _ in range(2000):
+    step()
+ev1.record(stream); torch.cuda.synchronize()
+print("fused" if FUSED else "two calls", "step %.2f us (2000 back-to-back steps, one input set)" % (ev0.elapsed_time(ev1) / 2000 * 1e3))
 for r in rows:
     t0 = r[0]
     print(" | ".join(f"{n}: in {(r[3*k]-t0)/1e3:6.2f} dep {(r[3*k+1]-t0)/1e3:6.2f} out {(r[3*k+2]-t0)/1e3:6.2f}" for k, n in enumerate(names) if n), " (us)")
