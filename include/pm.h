@@ -211,6 +211,37 @@ int pm_find_fundamental_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int
                             const pm_ransac_params *prm, double *dF /* [9] */, uint8_t *dmask,
                             int32_t *dn_inliers, uint64_t *dkey);
 
+/* ---- whole pairs, device-resident and asynchronous (BASELINE config 5; main.cpp:43-98 end to end) ----
+ * knnMatch(k=2) -> ratio test -> KeyPoint::convert on both sides -> findFundamentalMat(RANSAC) for one image
+ * pair, enqueued on the ctx stream WITHOUT any host round trip: the number of good matches stays on the
+ * device and every RANSAC kernel reads it there.  ddesc1/ddesc2: [n1|n2][dim] f32 (is_u8 = 0) or u8 (1)
+ * descriptors, dkp1/dkp2: [n1|n2][2] f32 keypoint coordinates, all device memory.  prm->sample_idx is
+ * ignored: the minimal-sample index sets are generated on the device from `seed` (the sets
+ * pm_make_sample_sets(n_matches, n_hyp, m, seed) returns).  *dresult (device) is complete once the stream
+ * has passed the call; has_model = 0 when fewer than sample_size matches survive or no sample gave a model. */
+typedef struct pm_pair_result {
+    double   F[9];          /* row-major 3x3, F[8] = 1 (zeros when has_model == 0)       */
+    uint64_t key;           /* winner key: inliers << 32 | (0xFFFFFFFF - model id); 0 = none */
+    int32_t  n_matches;     /* good matches after the ratio test                          */
+    int32_t  n_inliers;     /* inliers of the winning model                               */
+    int32_t  has_model;
+    int32_t  reserved;
+} pm_pair_result;           /* 96 bytes */
+int pm_match_estimate_pair_dev(pm_ctx *ctx, const void *ddesc1, int n1, const void *ddesc2, int n2, int dim,
+                               int is_u8, const float *dkp1, const float *dkp2, float ratio,
+                               const pm_ransac_params *prm, uint64_t seed, pm_pair_result *dresult);
+/* The batched form: n_pairs independent pairs given as HOST arrays of device pointers and counts; pair p
+ * uses seed prm->seed + p and writes dresults[p].  Everything is enqueued before the call returns; nothing
+ * is synchronised.  Ranks of a multi-GPU job call it on their own slice of the pairs (no collective). */
+int pm_match_estimate_batched_dev(pm_ctx *ctx, int n_pairs, const void *const *ddesc1, const int32_t *n1,
+                                  const void *const *ddesc2, const int32_t *n2, int dim, int is_u8,
+                                  const float *const *dkp1, const float *const *dkp2, float ratio,
+                                  const pm_ransac_params *prm, pm_pair_result *dresults);
+
+/* Number of pairs the batched call keeps in flight (1..8 internal streams with their own workspaces;
+ * default 4, one host thread enqueues each).  Results do not depend on it. */
+int pm_set_batch_lanes(pm_ctx *ctx, int lanes);
+
 /* LMedS over 7-point minimal samples -- what cv::findFundamentalMat(p1, p2, CV_FM_7POINT) actually runs when
  * N > 7, i.e. the reference's literal call at main.cpp:95-98.  Per model the error is OpenCV's
  * max(d(x2,Fx1)^2, d(x1,F^T x2)^2) in FP64 cast to float; the model with the smallest median wins (lowest

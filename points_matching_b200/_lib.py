@@ -15,6 +15,9 @@ SO_PATH = os.path.join(_HERE, "libpm.so")
 PM_OK, PM_EMPTY, PM_BAD_ARG, PM_CUDA_ERR, PM_NCCL_ERR, PM_NO_DEVICE = 0, 1, -1, -2, -3, -4
 DMATCH = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
 assert DMATCH.itemsize == 16
+PAIR_RESULT = np.dtype([("F", "<f8", (9,)), ("key", "<u8"), ("n_matches", "<i4"), ("n_inliers", "<i4"),
+                        ("has_model", "<i4"), ("reserved", "<i4")])
+assert PAIR_RESULT.itemsize == 96
 
 
 class RansacParams(C.Structure):
@@ -36,6 +39,7 @@ EXPORTS = [
     "pm_gather_points", "pm_gather_matches_dev",
     "pm_find_fundamental", "pm_find_fundamental_dev", "pm_make_sample_sets",
     "pm_ransac_solve_dev", "pm_ransac_score_dev", "pm_ransac_best_dev", "pm_ransac_finish_dev",
+    "pm_match_estimate_pair_dev", "pm_match_estimate_batched_dev", "pm_set_batch_lanes",
     "pm_fundamental_8point", "pm_epilines", "pm_residuals", "pm_find_fundamental_lmeds", "pm_lmeds_score_dev", "pm_make_sample_sets_dev",
 ]
 

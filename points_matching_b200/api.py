@@ -17,7 +17,7 @@ import math
 import numpy as np
 
 from . import _lib
-from ._lib import DMATCH, PM_EMPTY, PM_OK, RansacParams
+from ._lib import DMATCH, PAIR_RESULT, PM_EMPTY, PM_OK, RansacParams  # noqa: F401
 
 NORM_L2 = 4          # cv::NORM_L2
 NORM_HAMMING = 6     # cv::NORM_HAMMING
@@ -332,6 +332,36 @@ class Context:
         self._chk(self._L.pm_find_fundamental_dev(self._h, C.c_void_p(dp1), C.c_void_p(dp2), n, C.byref(prm),
                                                   C.c_void_p(dF), C.c_void_p(dmask), C.c_void_p(dn_inl),
                                                   C.c_void_p(dkey)))
+
+    @staticmethod
+    def _pair_params(n_hyp, sample_size, metric, threshold, refit, seed):
+        prm = RansacParams()
+        prm.sample_size, prm.metric, prm.threshold = sample_size, metric, threshold
+        prm.n_hyp, prm.refit, prm.sample_idx, prm.seed, prm.hyp_id_base = n_hyp, int(bool(refit)), None, seed, 0
+        return prm
+
+    def match_estimate_pair_dev(self, ddesc1, n1, ddesc2, n2, dim, is_u8, dkp1, dkp2, ratio, dresult, n_hyp,
+                                sample_size=8, metric=0, threshold=1.0, refit=True, seed=0):
+        """main.cpp:43-98 for one image pair, asynchronous on the ctx stream (no host round trip);
+        dresult: device pointer to one PAIR_RESULT record."""
+        prm = self._pair_params(n_hyp, sample_size, metric, threshold, refit, seed)
+        self._chk(self._L.pm_match_estimate_pair_dev(self._h, C.c_void_p(ddesc1), n1, C.c_void_p(ddesc2), n2, dim, int(is_u8),
+                                                     C.c_void_p(dkp1), C.c_void_p(dkp2), C.c_float(ratio), C.byref(prm),
+                                                     C.c_uint64(seed), C.c_void_p(dresult)))
+
+    def match_estimate_batched_dev(self, ddesc1, n1, ddesc2, n2, dim, is_u8, dkp1, dkp2, ratio, dresults, n_hyp,
+                                   sample_size=8, metric=0, threshold=1.0, refit=True, seed=0):
+        """The batched form: sequences of device pointers / counts, one entry per pair; pair p uses seed + p and
+        writes record p of dresults (device, [n_pairs] PAIR_RESULT).  Nothing is synchronised."""
+        k = len(ddesc1)
+        assert len(n1) == len(ddesc2) == len(n2) == len(dkp1) == len(dkp2) == k
+        vp, i32 = C.c_void_p * max(k, 1), C.c_int32 * max(k, 1)
+        prm = self._pair_params(n_hyp, sample_size, metric, threshold, refit, seed)
+        self._chk(self._L.pm_match_estimate_batched_dev(self._h, k, vp(*ddesc1), i32(*n1), vp(*ddesc2), i32(*n2), dim, int(is_u8),
+                                                        vp(*dkp1), vp(*dkp2), C.c_float(ratio), C.byref(prm), C.c_void_p(dresults)))
+
+    def set_batch_lanes(self, lanes):
+        self._chk(self._L.pm_set_batch_lanes(self._h, lanes))
 
     def make_sample_sets_dev(self, n_points, n_hyp, m, seed, dout):
         self._chk(self._L.pm_make_sample_sets_dev(self._h, n_points, n_hyp, m, C.c_uint64(seed), C.c_void_p(dout)))

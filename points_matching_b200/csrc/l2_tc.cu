@@ -35,6 +35,7 @@
 #include <cuda.h>
 #include <cstdlib>
 #include <cuda_bf16.h>
+#include <atomic>
 #include "pm_internal.h"
 #include "l2_common.h"
 
@@ -650,11 +651,11 @@ int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, 
                  int tmap_set, const unsigned long long *chain_done, unsigned long long wait_seq,
                  unsigned long long *chain_mark, unsigned long long mark_seq)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<bool> attr_set{false};           // lanes of the batched pair call launch from several host threads
+    if (!attr_set.load(std::memory_order_acquire)) {
         PM_CUDA(ctx, cudaFuncSetAttribute(l2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
         PM_CUDA(ctx, cudaFuncSetAttribute(l2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        attr_set = true;
+        attr_set.store(true, std::memory_order_release);
     }
     static_assert(sizeof(CUtensorMap) == 128, "tmap_store size");
     CUtensorMap *tmaps = reinterpret_cast<CUtensorMap *>(ctx->tmap_store) + 2 * tmap_set;   // one cached pair per buffer set

@@ -5,6 +5,8 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <vector>
+#include <thread>
+#include <vector>
 #include "pm_internal.h"
 
 int pmk_ransac_pick(pm_ctx *ctx, const uint64_t *dkey, const float *dF32, int id_base, int n_models, float *dFw);
@@ -84,8 +86,21 @@ int pm_destroy(pm_ctx *ctx)
         cudaEventDestroy(ctx->ev_fence); cudaEventDestroy(ctx->ev_train);
         for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev_chunk[i]);
     }
+    for (int k = 0; k < PM_MAX_LANES; ++k) {
+        if (ctx->lane[k]) pm_destroy(ctx->lane[k]);
+        if (ctx->ev_lane[k]) cudaEventDestroy(ctx->ev_lane[k]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
+    return PM_OK;
+}
+
+int pm_set_batch_lanes(pm_ctx *ctx, int lanes)
+{
+    if (!ctx) return PM_BAD_ARG;
+    if (lanes < 1 || lanes > PM_MAX_LANES) return pm_fail(ctx, PM_BAD_ARG, "pm_set_batch_lanes: 1..%d lanes", PM_MAX_LANES);
+    ctx->batch_lanes = lanes;
     return PM_OK;
 }
 
@@ -569,6 +584,126 @@ int pm_find_fundamental_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int
     if ((st = pmk_ransac_best(ctx, dcounts, nh * per, prm->hyp_id_base * per, dkey)) != PM_OK) return st;
     if ((st = pmk_ransac_pick(ctx, dkey, dF32, prm->hyp_id_base * per, nh * per, dFw)) != PM_OK) return st;
     return pmk_ransac_finish(ctx, dp1, dp2, n, dFw, prm->threshold, prm->metric, prm->refit, dF, dmask, dn_inliers);
+}
+
+// main.cpp:43-98 for one image pair, entirely in stream order (no host round trip): the match count stays on
+// the device (dn_good) and bounds every RANSAC kernel through its n_dev argument.
+static int pair_enqueue(pm_ctx *ctx, const void *dd1, int n1, const void *dd2, int n2, int dim, int is_u8, const float *dkp1,
+                        const float *dkp2, float ratio, const pm_ransac_params *prm, uint64_t seed, pm_pair_result *dres)
+{
+    const int m = prm->sample_size, per = m == 8 ? 1 : 3, nh = prm->n_hyp;
+    const int nmax = n1 > 0 ? n1 : 1;
+    PM_WS(ctx, dknn, pm_dmatch *, WS_KNN, (size_t)nmax * 2 * sizeof(pm_dmatch));
+    PM_WS(ctx, dgood, pm_dmatch *, WS_OUT2, (size_t)nmax * sizeof(pm_dmatch));
+    PM_WS(ctx, dkey, uint64_t *, WS_KEY, 64);
+    int32_t *dn_good = reinterpret_cast<int32_t *>(dkey + 2), *dn_inl = dn_good + 1;
+    PM_WS(ctx, dp1, float *, WS_P1, (size_t)nmax * 8);
+    PM_WS(ctx, dp2, float *, WS_P2, (size_t)nmax * 8);
+    PM_WS(ctx, ds, int32_t *, WS_SAMPLES, (size_t)nh * m * 4);
+    PM_WS(ctx, dF32, float *, WS_F32, ((size_t)nh * per + 1) * 12 * 4);
+    PM_WS(ctx, dcounts, int32_t *, WS_COUNTS, (size_t)nh * per * 4);
+    PM_WS(ctx, dmask, uint8_t *, WS_MASK, (size_t)nmax);
+    PM_WS(ctx, dF, double *, WS_FOUT, 16 * 8);
+    float *dFw = dF32 + (size_t)nh * per * 12;
+    int st;
+    if ((st = pmk_l2_knn2_fused(ctx, dd1, n1, dd2, n2, dim, is_u8, 0, dknn, 0, ratio, dgood, dn_good)) != PM_OK) return st;
+    if ((st = pmk_gather_matches(ctx, dgood, dn_good, n1, dkp1, n1, dkp2, n2, dp1, dp2)) != PM_OK) return st;
+    if ((st = pmk_sample_sets(ctx, nmax, nh, m, seed, ds, dn_good)) != PM_OK) return st;
+    if ((st = pmk_ransac_solve(ctx, dp1, dp2, nmax, ds, nh, m, dF32, dn_good)) != PM_OK) return st;
+    if ((st = pmk_ransac_score(ctx, dp1, dp2, nmax, dF32, nh * per, prm->threshold, prm->metric, dcounts, dn_good)) != PM_OK) return st;
+    if ((st = pmk_ransac_best(ctx, dcounts, nh * per, 0, dkey)) != PM_OK) return st;
+    if ((st = pmk_ransac_pick(ctx, dkey, dF32, 0, nh * per, dFw)) != PM_OK) return st;
+    if ((st = pmk_ransac_finish(ctx, dp1, dp2, nmax, dFw, prm->threshold, prm->metric, prm->refit, dF, dmask, dn_inl, dn_good)) != PM_OK) return st;
+    return pmk_pair_result(ctx, dkey, dn_good, dn_inl, dF, nmax, m, dres);
+}
+
+static int pair_check(pm_ctx *ctx, int dim, const pm_ransac_params *prm)
+{
+    PM_REQUIRE(ctx, prm != nullptr && dim > 0, "null parameters or dim <= 0");
+    PM_REQUIRE(ctx, prm->sample_size == 7 || prm->sample_size == 8, "sample_size must be 7 or 8");
+    PM_REQUIRE(ctx, prm->metric == PM_METRIC_SAMPSON || prm->metric == PM_METRIC_SYMEPI, "unknown metric");
+    PM_REQUIRE(ctx, prm->n_hyp > 0, "n_hyp must be positive");
+    return PM_OK;
+}
+
+int pm_match_estimate_pair_dev(pm_ctx *ctx, const void *dd1, int n1, const void *dd2, int n2, int dim, int is_u8,
+                               const float *dkp1, const float *dkp2, float ratio, const pm_ransac_params *prm, uint64_t seed,
+                               pm_pair_result *dres)
+{
+    if (!ctx) return PM_BAD_ARG;
+    int st = pair_check(ctx, dim, prm);
+    if (st != PM_OK) return st;
+    PM_REQUIRE(ctx, n1 >= 0 && n2 >= 0 && dres, "negative size or null result");
+    PM_REQUIRE(ctx, (n1 == 0 || (dd1 && dkp1)) && (n2 == 0 || (dd2 && dkp2)), "null pointer");
+    return pair_enqueue(ctx, dd1, n1, dd2, n2, dim, is_u8, dkp1, dkp2, ratio, prm, seed, dres);
+}
+
+int pm_match_estimate_batched_dev(pm_ctx *ctx, int n_pairs, const void *const *dd1, const int32_t *n1, const void *const *dd2,
+                                  const int32_t *n2, int dim, int is_u8, const float *const *dkp1, const float *const *dkp2,
+                                  float ratio, const pm_ransac_params *prm, pm_pair_result *dres)
+{
+    if (!ctx) return PM_BAD_ARG;
+    int st = pair_check(ctx, dim, prm);
+    if (st != PM_OK) return st;
+    PM_REQUIRE(ctx, n_pairs >= 0, "negative pair count");
+    if (n_pairs == 0) return PM_OK;
+    PM_REQUIRE(ctx, dd1 && n1 && dd2 && n2 && dkp1 && dkp2 && dres, "null pointer");
+    for (int p = 0; p < n_pairs; ++p) {
+        PM_REQUIRE(ctx, n1[p] >= 0 && n2[p] >= 0, "negative size");
+        PM_REQUIRE(ctx, (n1[p] == 0 || (dd1[p] && dkp1[p])) && (n2[p] == 0 || (dd2[p] && dkp2[p])), "null pointer");
+    }
+    const int L = n_pairs < ctx->batch_lanes ? n_pairs : ctx->batch_lanes;
+    if (L <= 1) {
+        for (int p = 0; p < n_pairs; ++p) {
+            st = pair_enqueue(ctx, dd1[p], n1[p], dd2[p], n2[p], dim, is_u8, dkp1[p], dkp2[p], ratio, prm, prm->seed + (uint64_t)p, dres + p);
+            if (st != PM_OK) return st;
+        }
+        return PM_OK;
+    }
+    // Pairs are independent: pair p runs on lane p % L (a child context with its own stream and workspaces), so
+    // the single-warp / single-wave kernels of one pair (minimal solves, the refit eigen-solve) overlap the
+    // other lanes' matching.  The lanes fork from and join the ctx stream through events: to the caller the
+    // call still behaves like one stream-ordered operation.
+    PM_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->ev_fork) PM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    for (int k = 0; k < L; ++k) {
+        if (!ctx->lane[k]) {
+            st = pm_create(&ctx->lane[k], ctx->device);
+            if (st != PM_OK) return pm_fail(ctx, st, "pm_match_estimate_batched_dev: cannot create lane %d", k);
+            PM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_lane[k], cudaEventDisableTiming));
+        }
+    }
+    PM_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    for (int k = 0; k < L; ++k) PM_CUDA(ctx, cudaStreamWaitEvent(ctx->lane[k]->stream, ctx->ev_fork, 0));
+    // one host thread per lane: a pair is ~20 launches, and a single thread enqueues them more slowly than four
+    // lanes execute them.  Each lane context is touched by exactly one thread.
+    uint64_t before[PM_MAX_LANES];
+    int lane_st[PM_MAX_LANES];
+    for (int k = 0; k < L; ++k) { before[k] = ctx->lane[k]->launches; lane_st[k] = PM_OK; }
+    auto run_lane = [&](int k) {
+        cudaSetDevice(ctx->device);
+        for (int p = k; p < n_pairs && lane_st[k] == PM_OK; p += L)
+            lane_st[k] = pair_enqueue(ctx->lane[k], dd1[p], n1[p], dd2[p], n2[p], dim, is_u8, dkp1[p], dkp2[p], ratio, prm,
+                                      prm->seed + (uint64_t)p, dres + p);
+    };
+    if (n_pairs >= 2 * L) {
+        std::vector<std::thread> workers;
+        for (int k = 1; k < L; ++k) workers.emplace_back(run_lane, k);
+        run_lane(0);
+        for (auto &w : workers) w.join();
+    } else {
+        for (int k = 0; k < L; ++k) run_lane(k);
+    }
+    for (int k = 0; k < L; ++k) {
+        ctx->launches += ctx->lane[k]->launches - before[k];
+        if (lane_st[k] != PM_OK) return pm_fail(ctx, lane_st[k], "lane %d: %s", k, ctx->lane[k]->err.c_str());
+    }
+    for (int k = 0; k < L; ++k) {
+        PM_CUDA(ctx, cudaEventRecord(ctx->ev_lane[k], ctx->lane[k]->stream));
+        PM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_lane[k], 0));
+    }
+    ctx->tail_is_chain = false;
+    return PM_OK;
 }
 
 int pm_lmeds_score_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dF32, int n_models, float *dmedians)

@@ -10,6 +10,7 @@
 
 #define PM_NSLOTS 40
 #define PM_PROF_RING 4096
+#define PM_MAX_LANES 8
 
 // Workspace slots (one growable device buffer each).
 enum pm_slot {
@@ -46,6 +47,12 @@ struct pm_ctx {
     int tmap_rows[4] = {0, 0, 0, 0};
     int tmap_fp8[4] = {-1, -1, -1, -1};
     int32_t *h_pinned = nullptr;   // 4 KB pinned scratch for small D2H reads
+    // batched pair pipeline (pm_match_estimate_batched_dev): child contexts (own stream + workspaces) so that
+    // the latency-bound kernels of one pair overlap the other pairs' work
+    pm_ctx *lane[PM_MAX_LANES] = {};
+    cudaEvent_t ev_lane[PM_MAX_LANES] = {};
+    cudaEvent_t ev_fork = nullptr;
+    int batch_lanes = 4;
     // chunked host path (pm_api.cu): uploads run on their own stream, one event per query chunk
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_fence = nullptr, ev_train = nullptr, ev_chunk[8] = {};
@@ -190,14 +197,20 @@ int pmk_l2_knn2_fused(pm_ctx *ctx, const void *dq, int nq, const void *dt, int n
 int pmk_l2_col_best(pm_ctx *ctx, const float *dq, int nq, const float *dt, int nt, int dim,
                     int q_index_base, uint64_t *dcol_best);
 // ransac.cu
+// dn (optional, device): the point count is read from *dn by the kernels; n then only bounds it
 int pmk_ransac_solve(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const int32_t *dsamples,
-                     int n_hyp, int m, float *dF32);
+                     int n_hyp, int m, float *dF32, const int32_t *dn = nullptr);
 int pmk_ransac_score(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dF32,
-                     int n_models, float thr, int metric, int32_t *dcounts);
+                     int n_models, float thr, int metric, int32_t *dcounts, const int32_t *dn = nullptr);
 int pmk_ransac_best(pm_ctx *ctx, const int32_t *dcounts, int n_models, int id_base, uint64_t *dkey);
 int pmk_ransac_finish(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dFw,
-                      float thr, int metric, int refit, double *dF, uint8_t *dmask, int32_t *dn_inl);
-int pmk_sample_sets(pm_ctx *ctx, int n_points, int n_hyp, int m, uint64_t seed, int32_t *dout);
+                      float thr, int metric, int refit, double *dF, uint8_t *dmask, int32_t *dn_inl,
+                      const int32_t *dn = nullptr);
+int pmk_sample_sets(pm_ctx *ctx, int n_points, int n_hyp, int m, uint64_t seed, int32_t *dout,
+                    const int32_t *dn = nullptr);
+int pmk_pair_result(pm_ctx *ctx, const uint64_t *dkey, const int32_t *dn_good, const int32_t *dn_inl, const double *dF,
+                    int n_max, int m, pm_pair_result *dres);
+int pmk_ransac_pick(pm_ctx *ctx, const uint64_t *dkey, const float *dF32, int id_base, int n_models, float *dFw);
 int pmk_lmeds_score(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dF32, int n_models, float *dmedians);
 int pmk_lmeds_finish(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dF32, const float *dmedians,
                      int n_models, float *dFw, double *dF, uint8_t *dmask, int32_t *dn_inl, uint64_t *dkey);

@@ -141,6 +141,14 @@ __device__ __forceinline__ void store_model(float *dst, const double (&F)[9], bo
     dst[9] = dst[10] = dst[11] = 0.f;
 }
 
+// Device-side point count (asynchronous pair pipeline, pm_match_estimate_*_dev): when n_dev is given, the
+// number of correspondences is *n_dev (written by the ratio filter earlier in the stream), bounded by the
+// host's n, which only sizes the launch.
+__device__ __forceinline__ int eff_n(int n, const int32_t *n_dev)
+{
+    return n_dev ? min(n, max(*n_dev, 0)) : n;
+}
+
 // =====================================================================================
 // K6: minimal solvers, 8 lanes per hypothesis
 // =====================================================================================
@@ -148,12 +156,13 @@ constexpr int SOLVE_THREADS = 256;    // 32 hypotheses per block
 template <int M>
 __global__ void __launch_bounds__(SOLVE_THREADS)
 ransac_solve_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2, int n,
-                    const int32_t *__restrict__ samples, int n_hyp, float *__restrict__ Fout)
+                    const int32_t *__restrict__ samples, int n_hyp, float *__restrict__ Fout, const int32_t *n_dev)
 {
+    n = eff_n(n, n_dev);
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int h = gtid >> 3, sub = threadIdx.x & 7;
     const bool live = h < n_hyp;
-    const bool has_pt = live && sub < M;
+    const bool has_pt = live && sub < M && n >= M;       // fewer points than a minimal sample: no model
     double x1 = 0, y1 = 0, x2 = 0, y2 = 0;
     if (has_pt) {
         int k = samples[(size_t)h * M + sub];
@@ -161,7 +170,7 @@ ransac_solve_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2
         const float2 a = p1[k], b = p2[k];
         x1 = a.x; y1 = a.y; x2 = b.x; y2 = b.y;
     }
-    bool valid = true;
+    bool valid = n >= M;
     double c1x = 0, c1y = 0, c2x = 0, c2y = 0, s1 = 1, s2 = 1;
     if (M == 8) {
         // Hartley normalisation: centroid to origin, mean distance sqrt(2)
@@ -346,8 +355,9 @@ constexpr int SC_MPT = SC_MPT_V;     // models per thread
 constexpr int SC_TILE = 512;       // correspondences per shared-memory tile (8 KB)
 
 __global__ void pack_points_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2, int n,
-                                   float4 *__restrict__ out)
+                                   float4 *__restrict__ out, const int32_t *n_dev)
 {
+    n = eff_n(n, n_dev);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float2 a = p1[i], b = p2[i];
@@ -412,9 +422,10 @@ __device__ __forceinline__ void sc_cp_async16(void *smem, const void *gmem)
 template <int METRIC, int MPT>
 __global__ void __launch_bounds__(SC_THREADS)
 ransac_score_kernel(const float4 *__restrict__ pts, int n, int chunk_pts, const float *__restrict__ Fm,
-                    int n_models, float thr2, int32_t *__restrict__ counts, int use_atomic)
+                    int n_models, float thr2, int32_t *__restrict__ counts, int use_atomic, const int32_t *n_dev)
 {
     __shared__ __align__(16) float4 tile[2][SC_TILE];
+    n = eff_n(n, n_dev);
     const int tid = threadIdx.x;
     const int m0 = blockIdx.x * (SC_THREADS * MPT);
     float F[MPT][9];
@@ -503,8 +514,9 @@ __global__ void ransac_pick_kernel(const unsigned long long *key, const float *_
 template <int METRIC>
 __global__ void __launch_bounds__(256)
 ransac_mask_kernel(const float4 *__restrict__ pts, int n, const float *__restrict__ Fw, float thr2,
-                   uint8_t *__restrict__ mask, int32_t *n_inl)
+                   uint8_t *__restrict__ mask, int32_t *n_inl, const int32_t *n_dev)
 {
+    n = eff_n(n, n_dev);
     float F[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) F[i] = Fw[i];
@@ -542,8 +554,9 @@ __device__ void block_reduce_store(double (&v)[NV], double *dst)
 
 // pass 1: sums of x1,y1,x2,y2 and the count over the selected points
 __global__ void __launch_bounds__(RF_THREADS)
-refit_sum_kernel(const float4 *__restrict__ pts, int n, const uint8_t *__restrict__ mask, double *partial)
+refit_sum_kernel(const float4 *__restrict__ pts, int n, const uint8_t *__restrict__ mask, double *partial, const int32_t *n_dev)
 {
+    n = eff_n(n, n_dev);
     double v[5] = {0, 0, 0, 0, 0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         if (!mask || mask[i]) { const float4 p = pts[i]; v[0] += p.x; v[1] += p.y; v[2] += p.z; v[3] += p.w; v[4] += 1.0; }
@@ -552,19 +565,22 @@ refit_sum_kernel(const float4 *__restrict__ pts, int n, const uint8_t *__restric
 // stats: [0..3] centroid, [4] count, [5] s1, [6] s2
 __global__ void refit_mean_kernel(const double *partial, double *stats)
 {
-    if (threadIdx.x != 0) return;
-    double s[5] = {0, 0, 0, 0, 0};
-    for (int b = 0; b < RF_BLOCKS; ++b)
-        for (int k = 0; k < 5; ++k) s[k] += partial[b * 5 + k];
-    const double inv = s[4] > 0 ? 1.0 / s[4] : 0.0;
-    for (int k = 0; k < 4; ++k) stats[k] = s[k] * inv;
-    stats[4] = s[4];
+    // lane k sums entry k over the blocks in ascending order (the order a single thread would use)
+    const int k = threadIdx.x;
+    double s = 0;
+    if (k < 5)
+        for (int b = 0; b < RF_BLOCKS; ++b) s += partial[b * 5 + k];
+    const double cnt = __shfl_sync(0xffffffffu, s, 4);
+    const double inv = cnt > 0 ? 1.0 / cnt : 0.0;
+    if (k < 4) stats[k] = s * inv;
+    if (k == 4) stats[4] = s;
 }
 // pass 2: mean distances to the centroids
 __global__ void __launch_bounds__(RF_THREADS)
 refit_scale_kernel(const float4 *__restrict__ pts, int n, const uint8_t *__restrict__ mask,
-                   const double *__restrict__ stats, double *partial)
+                   const double *__restrict__ stats, double *partial, const int32_t *n_dev)
 {
+    n = eff_n(n, n_dev);
     const double c1x = stats[0], c1y = stats[1], c2x = stats[2], c2y = stats[3];
     double v[2] = {0, 0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -577,19 +593,20 @@ refit_scale_kernel(const float4 *__restrict__ pts, int n, const uint8_t *__restr
 }
 __global__ void refit_scale_final_kernel(const double *partial, double *stats)
 {
-    if (threadIdx.x != 0) return;
-    double a = 0, b = 0;
-    for (int k = 0; k < RF_BLOCKS; ++k) { a += partial[k * 2]; b += partial[k * 2 + 1]; }
+    const int e = threadIdx.x;
+    if (e >= 2) return;
+    double a = 0;
+    for (int k = 0; k < RF_BLOCKS; ++k) a += partial[k * 2 + e];
     const double cnt = stats[4];
-    a = cnt > 0 ? a / cnt : 0; b = cnt > 0 ? b / cnt : 0;
-    stats[5] = a >= FLT_EPSILON ? sqrt(2.) / a : 0.0;
-    stats[6] = b >= FLT_EPSILON ? sqrt(2.) / b : 0.0;
+    a = cnt > 0 ? a / cnt : 0;
+    stats[5 + e] = a >= FLT_EPSILON ? sqrt(2.) / a : 0.0;
 }
 // pass 3: upper triangle of the 9x9 normal matrix sum r r^T (45 entries)
 __global__ void __launch_bounds__(RF_THREADS)
 refit_ata_kernel(const float4 *__restrict__ pts, int n, const uint8_t *__restrict__ mask,
-                 const double *__restrict__ stats, double *partial)
+                 const double *__restrict__ stats, double *partial, const int32_t *n_dev)
 {
+    n = eff_n(n, n_dev);
     const double c1x = stats[0], c1y = stats[1], c2x = stats[2], c2y = stats[3], s1 = stats[5], s2 = stats[6];
     double acc[45];
 #pragma unroll
@@ -619,14 +636,13 @@ refit_solve_kernel(const double *__restrict__ partial, const double *__restrict_
     const int lane = threadIdx.x;
     for (int e = lane; e < 81; e += 32) { A[e] = 0; V[e] = (e % 10 == 0) ? 1.0 : 0.0; }
     __syncwarp();
-    if (lane == 0) {
-        int k = 0;
-        for (int a = 0; a < 9; ++a)
-            for (int b = a; b < 9; ++b, ++k) {
-                double s = 0;
-                for (int blk = 0; blk < RF_BLOCKS; ++blk) s += partial[blk * 45 + k];
-                A[a * 9 + b] = s; A[b * 9 + a] = s;
-            }
+    for (int k = lane; k < 45; k += 32) {       // entry k of the upper triangle, blocks summed in ascending order
+        int a = 0, rem = k;
+        while (rem >= 9 - a) { rem -= 9 - a; ++a; }
+        const int b = a + rem;
+        double s = 0;
+        for (int blk = 0; blk < RF_BLOCKS; ++blk) s += partial[blk * 45 + k];
+        A[a * 9 + b] = s; A[b * 9 + a] = s;
     }
     __syncwarp();
     const double cnt = stats[4], s1 = stats[5], s2 = stats[6];
@@ -890,11 +906,11 @@ lmeds_mask_kernel(const float4 *__restrict__ pts, int n, const float *__restrict
     if (threadIdx.x == 0 && c) atomicAdd(n_inl, c);
 }
 
-int get_pts4(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float4 **out)
+int get_pts4(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float4 **out, const int32_t *dn = nullptr)
 {
     PM_WS(ctx, pts, float4 *, WS_MISC, (size_t)(n > 0 ? n : 1) * sizeof(float4));
     if (n > 0) {
-        pack_points_kernel<<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, pts);
+        pack_points_kernel<<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, pts, dn);
         PM_CHECK_LAUNCH(ctx);
     }
     *out = pts;
@@ -902,19 +918,19 @@ int get_pts4(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float
 }
 
 int run_refit(pm_ctx *ctx, const float4 *pts, int n, const uint8_t *dmask, const float *dFfallback, double *dF,
-              int32_t *dok)
+              int32_t *dok, const int32_t *dn = nullptr)
 {
     PM_WS(ctx, ws, double *, WS_REFIT, (size_t)(RF_BLOCKS * 45 + 16) * sizeof(double));
     double *stats = ws + RF_BLOCKS * 45;
-    refit_sum_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, ws);
+    refit_sum_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, ws, dn);
     PM_CHECK_LAUNCH(ctx);
     refit_mean_kernel<<<1, 32, 0, ctx->stream>>>(ws, stats);
     PM_CHECK_LAUNCH(ctx);
-    refit_scale_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, stats, ws);
+    refit_scale_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, stats, ws, dn);
     PM_CHECK_LAUNCH(ctx);
     refit_scale_final_kernel<<<1, 32, 0, ctx->stream>>>(ws, stats);
     PM_CHECK_LAUNCH(ctx);
-    refit_ata_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, stats, ws);
+    refit_ata_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, stats, ws, dn);
     PM_CHECK_LAUNCH(ctx);
     refit_solve_kernel<<<1, 32, 0, ctx->stream>>>(ws, stats, dFfallback, dF, dok);
     PM_CHECK_LAUNCH(ctx);
@@ -924,24 +940,24 @@ int run_refit(pm_ctx *ctx, const float4 *pts, int n, const uint8_t *dmask, const
 }  // namespace
 
 int pmk_ransac_solve(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const int32_t *dsamples, int n_hyp,
-                     int m, float *dF32)
+                     int m, float *dF32, const int32_t *dn)
 {
     if (n_hyp <= 0) return PM_OK;
     const int blocks = pm_cdiv(n_hyp * 8, SOLVE_THREADS);
     if (m == 8)
-        ransac_solve_kernel<8><<<blocks, SOLVE_THREADS, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dsamples, n_hyp, dF32);
+        ransac_solve_kernel<8><<<blocks, SOLVE_THREADS, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dsamples, n_hyp, dF32, dn);
     else
-        ransac_solve_kernel<7><<<blocks, SOLVE_THREADS, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dsamples, n_hyp, dF32);
+        ransac_solve_kernel<7><<<blocks, SOLVE_THREADS, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dsamples, n_hyp, dF32, dn);
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }
 
 int pmk_ransac_score(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dF32, int n_models,
-                     float thr, int metric, int32_t *dcounts)
+                     float thr, int metric, int32_t *dcounts, const int32_t *dn)
 {
     if (n_models <= 0) return PM_OK;
     const float4 *pts;
-    int st = get_pts4(ctx, dp1, dp2, n, &pts);
+    int st = get_pts4(ctx, dp1, dp2, n, &pts, dn);
     if (st != PM_OK) return st;
     // 4 models per thread when there are enough models to fill the GPU; 1 model per thread for small batches
     // (e.g. 4096 hypotheses x 4096 matches per image pair in config 5), where 4 would leave most SMs idle
@@ -964,11 +980,11 @@ int pmk_ransac_score(pm_ctx *ctx, const float *dp1, const float *dp2, int n, con
     {
         pm_prof_scope prof(ctx, 2);
         if (metric == PM_METRIC_SAMPSON) {
-            if (mpt == 1) ransac_score_kernel<PM_METRIC_SAMPSON, 1><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic);
-            else ransac_score_kernel<PM_METRIC_SAMPSON, SC_MPT><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic);
+            if (mpt == 1) ransac_score_kernel<PM_METRIC_SAMPSON, 1><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic, dn);
+            else ransac_score_kernel<PM_METRIC_SAMPSON, SC_MPT><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic, dn);
         } else {
-            if (mpt == 1) ransac_score_kernel<PM_METRIC_SYMEPI, 1><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic);
-            else ransac_score_kernel<PM_METRIC_SYMEPI, SC_MPT><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic);
+            if (mpt == 1) ransac_score_kernel<PM_METRIC_SYMEPI, 1><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic, dn);
+            else ransac_score_kernel<PM_METRIC_SYMEPI, SC_MPT><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic, dn);
         }
     }
     PM_CHECK_LAUNCH(ctx);
@@ -993,21 +1009,21 @@ int pmk_ransac_pick(pm_ctx *ctx, const uint64_t *dkey, const float *dF32, int id
 }
 
 int pmk_ransac_finish(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dFw, float thr, int metric,
-                      int refit, double *dF, uint8_t *dmask, int32_t *dn_inl)
+                      int refit, double *dF, uint8_t *dmask, int32_t *dn_inl, const int32_t *dn)
 {
     const float4 *pts;
-    int st = get_pts4(ctx, dp1, dp2, n, &pts);
+    int st = get_pts4(ctx, dp1, dp2, n, &pts, dn);
     if (st != PM_OK) return st;
     PM_CUDA(ctx, cudaMemsetAsync(dn_inl, 0, 4, ctx->stream));
     const float thr2 = thr * thr;
     if (n > 0) {
         if (metric == PM_METRIC_SAMPSON)
-            ransac_mask_kernel<PM_METRIC_SAMPSON><<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>(pts, n, dFw, thr2, dmask, dn_inl);
+            ransac_mask_kernel<PM_METRIC_SAMPSON><<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>(pts, n, dFw, thr2, dmask, dn_inl, dn);
         else
-            ransac_mask_kernel<PM_METRIC_SYMEPI><<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>(pts, n, dFw, thr2, dmask, dn_inl);
+            ransac_mask_kernel<PM_METRIC_SYMEPI><<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>(pts, n, dFw, thr2, dmask, dn_inl, dn);
         PM_CHECK_LAUNCH(ctx);
     }
-    if (refit) return run_refit(ctx, pts, n, dmask, dFw, dF, nullptr);
+    if (refit) return run_refit(ctx, pts, n, dmask, dFw, dF, nullptr, dn);
     copy_f32_to_f64_kernel<<<1, 32, 0, ctx->stream>>>(dFw, dF, 9);
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
@@ -1066,10 +1082,16 @@ int pmk_lmeds_finish(pm_ctx *ctx, const float *dp1, const float *dp2, int n, con
 
 // Device twin of pm_make_sample_sets (pm_api.cu): same splitmix64 stream, same rejection of repeats, so the
 // sets are identical to the host generator's -- one thread per hypothesis.
-__global__ void sample_sets_kernel(int n_points, int n_hyp, int m, unsigned long long seed, int32_t *__restrict__ out)
+__global__ void sample_sets_kernel(int n_points, int n_hyp, int m, unsigned long long seed, int32_t *__restrict__ out,
+                                   const int32_t *n_dev)
 {
+    n_points = eff_n(n_points, n_dev);
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= n_hyp) return;
+    if (n_points < m) {                  // no minimal sample exists (the solver writes "no model" for this case)
+        for (int i = 0; i < m; ++i) out[(size_t)h * m + i] = 0;
+        return;
+    }
     unsigned long long s = seed ^ (0xD1B54A32D192ED03ull * (unsigned long long)(h + 1));
     int32_t row[8];
     for (int i = 0; i < m; ++i) {
@@ -1087,10 +1109,30 @@ __global__ void sample_sets_kernel(int n_points, int n_hyp, int m, unsigned long
     for (int i = 0; i < m; ++i) out[(size_t)h * m + i] = row[i];
 }
 
-int pmk_sample_sets(pm_ctx *ctx, int n_points, int n_hyp, int m, uint64_t seed, int32_t *dout)
+int pmk_sample_sets(pm_ctx *ctx, int n_points, int n_hyp, int m, uint64_t seed, int32_t *dout, const int32_t *dn)
 {
     if (n_hyp <= 0) return PM_OK;
-    sample_sets_kernel<<<pm_cdiv(n_hyp, 128), 128, 0, ctx->stream>>>(n_points, n_hyp, m, (unsigned long long)seed, dout);
+    sample_sets_kernel<<<pm_cdiv(n_hyp, 128), 128, 0, ctx->stream>>>(n_points, n_hyp, m, (unsigned long long)seed, dout, dn);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}
+
+// One record per image pair of the asynchronous pair pipeline (pm_match_estimate_*_dev).
+__global__ void pair_result_kernel(const unsigned long long *key, const int32_t *n_good, const int32_t *n_inl,
+                                   const double *F, int n_max, int m, pm_pair_result *res)
+{
+    const int i = threadIdx.x;
+    const unsigned long long k = *key;
+    const int n = min(max(*n_good, 0), n_max);
+    const bool ok = k != 0ull && n >= m;
+    if (i < 9) res->F[i] = ok ? F[i] : 0.0;
+    if (i == 9) { res->key = ok ? k : 0ull; res->n_matches = n; res->n_inliers = ok ? *n_inl : 0; res->has_model = ok; res->reserved = 0; }
+}
+
+int pmk_pair_result(pm_ctx *ctx, const uint64_t *dkey, const int32_t *dn_good, const int32_t *dn_inl, const double *dF,
+                    int n_max, int m, pm_pair_result *dres)
+{
+    pair_result_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long *)dkey, dn_good, dn_inl, dF, n_max, m, dres);
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }

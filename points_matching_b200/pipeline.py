@@ -95,6 +95,35 @@ class PairPipeline:
         return self.estimate(self.start(desc1, desc2, kp1, kp2, seed))
 
 
+def match_and_estimate_batch_native(ctx, pairs, n_hyp=4096, ratio=0.75, threshold=1.0, metric=METRIC_SAMPSON, refit=True,
+                                    group=None, sync=True):
+    """The same flow through the C ABI's batched entry (pm_match_estimate_batched_dev): rank r enqueues its
+    contiguous shard of `pairs` in ONE call, nothing returns to the host between the stages of a pair (the
+    match count stays on the device), and the per-pair records are read once at the end.  Pair p uses seed p,
+    like match_and_estimate_batch.  Returns [(pair_index, result dict)], or (lo, device records) when
+    sync=False (records are complete once the ctx stream has drained)."""
+    from ._lib import PAIR_RESULT
+    world, rank = _world(group)
+    lo, hi = shard_bounds(len(pairs), world, rank)
+    mine = pairs[lo:hi]
+    dev = mine[0][0].device if mine else torch.device("cuda")
+    res = torch.zeros((max(len(mine), 1), PAIR_RESULT.itemsize), dtype=torch.uint8, device=dev)
+    torch.cuda.current_stream(dev).synchronize()      # inputs / records made on torch's stream; libpm uses the ctx stream
+    if mine:
+        is_u8 = mine[0][0].dtype == torch.uint8
+        ctx.match_estimate_batched_dev([p[0].data_ptr() for p in mine], [p[0].shape[0] for p in mine],
+                                       [p[1].data_ptr() for p in mine], [p[1].shape[0] for p in mine],
+                                       mine[0][0].shape[1], is_u8, [p[2].data_ptr() for p in mine],
+                                       [p[3].data_ptr() for p in mine], ratio, res.data_ptr(), n_hyp, 8, metric, threshold,
+                                       refit, seed=lo)
+    if not sync:
+        return lo, res
+    ctx.sync()
+    rec = res.cpu().numpy().view(PAIR_RESULT).reshape(-1)[: len(mine)]
+    return [(lo + i, dict(n_matches=int(r["n_matches"]), n_inliers=int(r["n_inliers"]),
+                          F=r["F"].reshape(3, 3).copy() if r["has_model"] else None)) for i, r in enumerate(rec)]
+
+
 def match_and_estimate_batch(pipelines, pairs, group=None):
     """pairs: list of (desc1, desc2, kp1, kp2) CUDA tensors, identical on every rank.  Rank r processes the
     pairs of its contiguous shard; returns this rank's list of (pair_index, result dict).  No collective is

@@ -555,6 +555,61 @@ def test_pair_pipeline_end_to_end(pm, orc):
     ctx.close()
 
 
+def test_native_batched_pairs_equal_python_pipeline(pm):
+    """pm_match_estimate_batched_dev (no host round trip: the match count stays on the device and bounds every RANSAC
+    kernel) gives exactly what the staged Python pipeline gives pair by pair -- including pairs with too few
+    matches for a model, empty sides, u8 descriptors, and the single-pair entry."""
+    import torch
+    from points_matching_b200 import synth
+    from points_matching_b200._lib import PAIR_RESULT
+    from points_matching_b200.pipeline import PairPipeline, match_and_estimate_batch, match_and_estimate_batch_native
+    ctx, ctx2 = pm.Context(0), pm.Context(0)
+    pipe = PairPipeline(ctx, "cuda:0", 4096, n_hyp=1024)
+    pairs = []
+    for k, (n1, n2) in enumerate([(3000, 3300), (2500, 2000), (4096, 4096), (700, 900)]):
+        d1, d2, k1, k2, _ = synth.image_pair(n1, n2, seed=11 + k)
+        pairs.append(tuple(torch.from_numpy(a).cuda() for a in (d1, d2, k1, k2)))
+    # unrelated descriptors: (almost) nothing passes the ratio test -> no model
+    q, _ = synth.sift_pair(600, 10, seed=1, planted=0.0)
+    t, _ = synth.sift_pair(800, 10, seed=2, planted=0.0)
+    rng = np.random.default_rng(0)
+    pairs.append((torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda(),
+                  torch.from_numpy(rng.uniform(0, 1000, (600, 2)).astype(np.float32)).cuda(),
+                  torch.from_numpy(rng.uniform(0, 1000, (800, 2)).astype(np.float32)).cuda()))
+    pairs.append(tuple(a[:5].contiguous() for a in pairs[0]))            # fewer rows than a minimal sample
+    ref = match_and_estimate_batch(pipe, pairs)
+    for lanes in (4, 1, 3):          # pairs in flight (internal streams): results do not depend on it
+        ctx2.set_batch_lanes(lanes)
+        out = match_and_estimate_batch_native(ctx2, pairs * 2, n_hyp=1024)
+        assert [p for p, _ in out] == list(range(2 * len(pairs)))
+        n_models = 0
+        for i, (_, b) in enumerate(out):
+            a = ref[i % len(pairs)][1]
+            if i >= len(pairs):      # pair p uses seed p: the second copy of a pair draws other samples
+                assert a["n_matches"] == b["n_matches"]
+                continue
+            assert a["n_matches"] == b["n_matches"] and a["n_inliers"] == b["n_inliers"]
+            assert (a["F"] is None) == (b["F"] is None)
+            if a["F"] is not None:
+                assert np.array_equal(a["F"], b["F"])
+                n_models += 1
+    ctx2.set_batch_lanes(4)
+    assert n_models >= 4 and ref[4][1]["n_matches"] < 100 and ref[5][1]["F"] is None
+    # u8 descriptors (SIFT as bytes) and the single-pair entry
+    p0 = pairs[0]
+    u8 = (p0[0].to(torch.uint8), p0[1].to(torch.uint8), p0[2], p0[3])
+    r8 = match_and_estimate_batch_native(ctx2, [u8], n_hyp=1024)[0][1]
+    assert r8["n_matches"] == ref[0][1]["n_matches"] and np.array_equal(r8["F"], ref[0][1]["F"])
+    rec = torch.zeros(PAIR_RESULT.itemsize, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx2.match_estimate_pair_dev(p0[0].data_ptr(), p0[0].shape[0], p0[1].data_ptr(), p0[1].shape[0], 128, False, p0[2].data_ptr(),
+                                 p0[3].data_ptr(), 0.75, rec.data_ptr(), 1024, seed=0)
+    ctx2.sync()
+    r = rec.cpu().numpy().view(PAIR_RESULT)[0]
+    assert r["has_model"] == 1 and np.array_equal(r["F"].reshape(3, 3), ref[0][1]["F"]) and r["n_inliers"] == ref[0][1]["n_inliers"]
+    ctx.close(); ctx2.close()
+
+
 def test_lmeds_scoring_bit_exact_and_end_to_end(ctx, pm, orc):
     """LMedS (the reference's literal estimator, main.cpp:95-98 with N > 7): medians bit-exact vs the oracle on
     identical model bits; end to end on identical 7-point index sets the same winner / mask up to the solver's
