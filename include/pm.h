@@ -238,7 +238,7 @@ int pm_match_estimate_batched_dev(pm_ctx *ctx, int n_pairs, const void *const *d
                                   const float *const *dkp1, const float *const *dkp2, float ratio,
                                   const pm_ransac_params *prm, pm_pair_result *dresults);
 
-/* Number of pairs the batched call keeps in flight (1..8 internal streams with their own workspaces;
+/* Number of pairs the batched call keeps in flight (1..4 internal streams with their own workspaces;
  * default 4, one host thread enqueues each).  Results do not depend on it. */
 int pm_set_batch_lanes(pm_ctx *ctx, int lanes);
 

@@ -10,7 +10,7 @@
 
 #define PM_NSLOTS 40
 #define PM_PROF_RING 4096
-#define PM_MAX_LANES 8
+#define PM_MAX_LANES 4   /* more lanes than hardware work queues left over (CUDA_DEVICE_MAX_CONNECTIONS = 8) serialise: 6 lanes ran 8x slower */
 
 // Workspace slots (one growable device buffer each).
 enum pm_slot {
