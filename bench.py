@@ -266,6 +266,33 @@ def run_ours(args):
     ctx.profile_enable(False)
     n_good_last = int(ngood[0].item())
     stats = ctx.l2_stats()
+    # the same kernel inside the undisturbed chain: %globaltimer stamps written by K2 itself (first CTA past its
+    # waits -> last CTA out) for ONE step in the middle of a running loop, 15 repetitions, median
+    k2_chain_us = None
+    try:
+        import ctypes as C0
+        from points_matching_b200 import _lib as _l0
+        L0 = _l0.lib()
+        span = torch.zeros(15 + 17 + 2 * 1024, dtype=torch.int64, device=dev)
+        init = np.zeros(span.numel(), dtype=np.int64)
+        init[[0, 1, 3, 4, 6, 7, 9, 10, 12, 13]] = np.iinfo(np.int64).max
+        init_d = torch.from_numpy(init).to(dev)
+        durs = []
+        for rep in range(15):
+            span.copy_(init_d)
+            for i in range(20):
+                step(i)
+            L0.pm_debug_set_span(C0.c_void_p(span.data_ptr()))
+            step(20)
+            L0.pm_debug_set_span(C0.c_void_p(0))
+            for i in range(3):
+                step(21 + i)
+            torch.cuda.synchronize()
+            r = span.cpu().numpy()
+            durs.append((int(r[5]) - int(r[4])) / 1e3)
+        k2_chain_us = float(np.median(durs))
+    except Exception as e:      # instrumentation only
+        print("bench.py: in-chain K2 timing unavailable:", e, file=sys.stderr)
     ctx.set_pipelining(False)
     tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -288,6 +315,12 @@ def run_ours(args):
                 "kernel": "l2_tc_kernel (tcgen05.mma cta_group::1 kind::f16 bf16, M128 N128 K16, 256x128 work items, fused top-2 epilogue)",
                 "kernel_ms": k2_avg_ms, "kernel_share_of_step": k2_avg_ms / ms_step if ms_step else None,
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step loop)",
+                "in_chain": None if not k2_chain_us else {
+                    "kernel_ms": k2_chain_us * 1e-3, "achieved": flops / (k2_chain_us * 1e-6) / 1e12,
+                    "frac": flops / (k2_chain_us * 1e-6) / 1e12 / peaks["bf16_sustained"],
+                    "how": "K2's own %globaltimer stamps (first CTA past griddepcontrol.wait -> last CTA out) inside the "
+                           "programmatic-dependent-launch chain, median of 15 single steps; the event pair above breaks the "
+                           "chain, so `kernel_ms` also contains K2's launch latency and prologue"},
                 "algorithmic_flops_per_launch": flops, "mma_k_blocks_per_tile": stats["k_blocks"],
                 "exact_integer_mode": stats["exact_mode"], "exact_fallback_rows": stats["fallback_rows"]}
 
@@ -302,20 +335,27 @@ def run_ours(args):
     n_host_good = 0
     for i in range(3):
         ctx.knn2_ratio_l2_ptr(hq[i % 4].data_ptr(), NQ, ht[i % 4].data_ptr(), NT, DIM, RATIO, hknn.data_ptr(), hgood.data_ptr())
-    barrier()
-    ev0.record(stream)
-    for i in range(e_steps):
-        n_host_good = ctx.knn2_ratio_l2_ptr(hq[i % 4].data_ptr(), NQ, ht[i % 4].data_ptr(), NT, DIM, RATIO,
-                                            hknn.data_ptr(), hgood.data_ptr())
-    ev1.record(stream)
-    barrier()
-    emax = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(emax, op=dist.ReduceOp.MAX)
-    e_ms = float(emax.item()) / e_steps
+    # five blocks of e_steps / 5 calls; the reported figure is the MEDIAN block (host-side interference -- other
+    # tenants on the PCIe switch, the nvidia-smi sampler -- moved single blocks by 2x between otherwise equal runs)
+    e_blocks, e_per = [], max(1, e_steps // 5)
+    for b in range(5):
+        barrier()
+        ev0.record(stream)
+        for i in range(e_per):
+            n_host_good = ctx.knn2_ratio_l2_ptr(hq[i % 4].data_ptr(), NQ, ht[i % 4].data_ptr(), NT, DIM, RATIO,
+                                                hknn.data_ptr(), hgood.data_ptr())
+        ev1.record(stream)
+        barrier()
+        emax = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(emax, op=dist.ReduceOp.MAX)
+        e_blocks.append(float(emax.item()) / e_per)
+    e_steps = 5 * e_per
+    e_ms = float(np.median(e_blocks))
     e2e = {"value": world * NQ * NT / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
            "h2d_bytes_per_step": (NQ + NT) * DIM * 4, "d2h_bytes_per_step": NQ * 2 * 16 + NQ * 16 + 4,
-           "api": "pm_knn2_ratio_l2_f32 (host buffers, pinned)", "steps": e_steps}
+           "api": "pm_knn2_ratio_l2_f32 (host buffers, pinned)", "steps": e_steps,
+           "ms_per_step_blocks": e_blocks, "timing": "median of 5 blocks, max over ranks per block"}
 
     # ---- the same call with SIFT shipped as bytes (pm_knn2_l2_u8: 4x fewer PCIe bytes, identical matches) ----
     import ctypes as C

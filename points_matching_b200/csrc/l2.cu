@@ -601,7 +601,12 @@ int l2_flags_acquire(pm_ctx *ctx, L2Flags **cur, L2Flags **zero_next, L2Flags **
 // with the same shapes.  Ordering is then carried by two device words: K2 of every signalling chain stores
 // its number to chain_mark once past its waits (= K1 of that chain and everything enqueued before the chain
 // have completed), the tail K5 stores it to chain_done.  K1(s+1) spins for chain_mark >= s, K2(s+1) spins
-// for chain_done >= s after its own griddepcontrol.wait, and K3 / K5 follow K2 by PDL.  (K3 applying the ratio test itself was tried as well: with 313 32-row tiles the
+// for chain_done >= s after its own griddepcontrol.wait, and K3 / K5 follow K2 by PDL.
+// Measured on the B200: grid completion is transitive along a PDL chain -- K2(s+1)'s griddepcontrol.wait is not
+// released when K1(s+1) exits but when K5(s), K1's own stream predecessor, has completed (a dependent that
+// never executes griddepcontrol.wait gets it at its exit).  So K2(s+1) cannot be started under K3(s) / K5(s)
+// on one stream (tried: K3 carrying the chain wait and a 128-thread K5 that fits beside a K2 CTA only made
+// K5 slower, 36.1 vs 33.6 us per step); what the mode buys is K1's 4 us.  (K3 applying the ratio test itself was tried as well: with 313 32-row tiles the
 // ordered prefix inside K3 cost 8-10 us against 3.8 us for K5 behind one PDL boundary.)
 static int l2_chain(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
                     int q_index_base, pm_dmatch *dout, int phase, float ratio, pm_dmatch *dgood, int32_t *dn_good)

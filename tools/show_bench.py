@@ -11,6 +11,8 @@ def show_bench(path):
     print('value %.3e %s  ms_step %.4f  launches %d  n_gpus %d' % (d['value'], d['unit'], d['ms_per_step'], d['gpu_launches'], d['n_gpus']))
     e = d['e2e']; print('e2e %.3e ms %.4f' % (e['value'], e['ms_per_step']))
     r = d['roofline']; print('K2 ms %.4f achieved %.1f TF frac %.3f share %.2f exact=%s fb=%s' % (r['kernel_ms'], r['achieved'], r['frac'], r['kernel_share_of_step'], r['exact_integer_mode'], r['exact_fallback_rows']))
+    if r.get('in_chain'): print('   in chain: K2 %.2f us, %.1f TF, frac %.3f' % (r['in_chain']['kernel_ms'] * 1e3, r['in_chain']['achieved'], r['in_chain']['frac']))
+    if d['e2e'].get('ms_per_step_blocks'): print('   e2e blocks (ms):', ' '.join('%.3f' % x for x in d['e2e']['ms_per_step_blocks']))
     print('clocks', d['clocks'])
     if d.get('cpu_baseline'):
         print('cpu %.3e cores %d' % (d['cpu_baseline']['value'], d['cpu_baseline']['cores']))
