@@ -42,10 +42,28 @@ def _worker(rank, world, port, out_dir):
                                                                  pm.METRIC_SAMPSON, 1.0, True)
         res["ransac_F"], res["ransac_mask"] = F.cpu().numpy(), mask.cpu().numpy()
         res["ransac_meta"] = np.array([ninl, winner])
+        # BASELINE config 5: image pairs partitioned across ranks, each rank's shard through the batched C-ABI entry
+        from points_matching_b200.pipeline import match_and_estimate_batch_native
+        mine = match_and_estimate_batch_native(ctx, _pairs(torch, f"cuda:{rank}"), n_hyp=512)
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        allp = sorted((p, o) for part in everyone for p, o in part)
+        res["pairs_idx"] = np.array([p for p, _ in allp])
+        res["pairs_meta"] = np.array([[o["n_matches"], o["n_inliers"]] for _, o in allp])
+        res["pairs_F"] = np.stack([o["F"] if o["F"] is not None else np.zeros((3, 3)) for _, o in allp])
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **res)
         ctx.close()
     finally:
         dist.destroy_process_group()
+
+
+def _pairs(torch, device):
+    from points_matching_b200 import synth
+    out = []
+    for k, (n1, n2) in enumerate([(1500, 1700), (900, 800), (2048, 2048), (600, 1000), (1200, 1300)]):
+        d1, d2, k1, k2, _ = synth.image_pair(n1, n2, seed=40 + k)
+        out.append(tuple(torch.from_numpy(a).to(device) for a in (d1, d2, k1, k2)))
+    return out
 
 
 def test_two_rank_nccl_equals_single_gpu(tmp_path, orc):
@@ -71,3 +89,12 @@ def test_two_rank_nccl_equals_single_gpu(tmp_path, orc):
     r = orc.ransac_f(p1, p2, idx, 0, 1.0, True)
     assert int(r0["ransac_meta"][1]) == r["best_model"] and abs(int(r0["ransac_meta"][0]) - r["n_inliers"]) <= 3
     assert (r0["ransac_mask"] == r["mask"]).mean() > 0.998
+    # the partitioned pair batch equals the same batch on one GPU, pair by pair and bit for bit
+    from points_matching_b200.pipeline import match_and_estimate_batch_native
+    ctx = pm.Context(0)
+    one = match_and_estimate_batch_native(ctx, _pairs(torch, "cuda:0"), n_hyp=512)
+    ctx.close()
+    assert list(r0["pairs_idx"]) == [p for p, _ in one] == list(range(5))
+    for i, (_, o) in enumerate(one):
+        assert list(r0["pairs_meta"][i]) == [o["n_matches"], o["n_inliers"]] and o["F"] is not None
+        assert np.array_equal(r0["pairs_F"][i], o["F"])

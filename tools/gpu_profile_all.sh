@@ -21,3 +21,8 @@ done
 python tools/ham_only.py > $O/plain_ham_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:l2_tc_kernel -s 2 -c 1 -o $O/prof_l2_tc_kernel_fp8_$TAG -f python tools/ham_only.py > $O/ncu_l2_tc_kernel_fp8_$TAG.log 2>&1
 echo "ncu l2_tc_kernel<FP8> exit $?"
+PM_PAIRS=6 python tools/pair_profile.py > $O/plain_pair_$TAG.log 2>&1 &&
+PM_PAIRS=6 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_pair_$TAG.csv python tools/pair_profile.py > $O/ncu_pair_$TAG.log 2>&1
+echo "pair launch list exit $?"
+PM_PAIRS=64 python tools/pair_profile.py | tee $O/pair_$TAG.log
+PM_PIPE=1 python tools/step_timeline.py > $O/timeline_pipe_$TAG.txt 2>&1
