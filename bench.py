@@ -15,6 +15,9 @@ The second headline metric, RANSAC-F hypotheses/sec (configs[3]: 100k correspond
 outliers, 8-point, Sampson 1 px), is reported in the "secondary" object of the same line.
 Prints ONE JSON line on rank 0.
 """
+import os as _os
+# the batched pair call (cfg5 leg) keeps several pairs in flight on internal streams: give them work queues of their own
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import argparse
 import json
 import os
@@ -386,14 +389,13 @@ def run_ours(args):
     if not args.no_ransac:
         secondary = bench_ransac(ctx, torch, dist, dev, world, rank, stream, barrier, peaks, args)
 
-    extra = None
+    extra = {}
     if not args.no_hamming:
-        extra = {"hamming": bench_hamming(ctx, torch, dev, world, rank, stream, barrier, peaks)}
-
-    if extra is not None:
+        extra["hamming"] = bench_hamming(ctx, torch, dev, world, rank, stream, barrier, peaks)
         extra["l2_general_floats"] = bench_split_mode(ctx, torch, dev, rank, stream, barrier)
-    if extra is not None and not args.no_cfg5:
+    if not args.no_cfg5:
         extra["cfg5"] = bench_cfg5(ctx, torch, dev, world, rank, barrier)
+    extra = extra or None
 
     clocks = sampler.stop() if sampler else None
 
@@ -563,6 +565,10 @@ def bench_cfg5(ctx, torch, dev, world, rank, barrier):
 
     # (a) the C ABI's batched entry: one call enqueues every pair, no host round trip inside a pair
     nctx = pm.Context(dev.index)
+    # pairs in flight: 4 when this process drives the GPU alone; with the NCCL communicator of a multi-rank run
+    # alive in the process more than 2 lanes serialise badly (measured: 141 us per pair at 2 lanes, 360+ at 4)
+    lanes = 4 if world == 1 else 2
+    nctx.set_batch_lanes(lanes)
     match_and_estimate_batch_native(nctx, plist[:6], n_hyp=4096)
     ms_n, last_n = timed(lambda: match_and_estimate_batch_native(nctx, plist, n_hyp=4096)[-1][1])
     # (b) the staged Python pipeline: three pipelines (own ctx + stream each), one pair's host round trip for
@@ -575,7 +581,7 @@ def bench_cfg5(ctx, torch, dev, world, rank, barrier):
     return {"workload": "cfg5 sample: 33 image pairs per rank (of 1024 / world), 8192 x 8192 SIFT-like f32 descriptors resident in HBM, "
                         "kNN-2 + ratio 0.75 + gather + RANSAC-F (4096 8-point hypotheses, Sampson 1 px, refit) per pair; host wall clock",
             "image_pairs_per_s": world * pairs / (ms * 1e-3), "ms_per_pair": ms / pairs,
-            "native_batched": {"api": "pm_match_estimate_batched_dev (one call, match count stays on the device)",
+            "native_batched": {"api": "pm_match_estimate_batched_dev (one call, match count stays on the device)", "lanes": lanes,
                                "ms_per_pair": ms_n / pairs, "image_pairs_per_s": world * pairs / (ms_n * 1e-3)},
             "staged_python": {"api": "pipeline.PairPipeline x 3 interleaved (one host round trip per pair)",
                               "ms_per_pair": ms_s / pairs, "image_pairs_per_s": world * pairs / (ms_s * 1e-3)},

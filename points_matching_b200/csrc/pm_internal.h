@@ -10,7 +10,7 @@
 
 #define PM_NSLOTS 40
 #define PM_PROF_RING 4096
-#define PM_MAX_LANES 4   /* more lanes than hardware work queues left over (CUDA_DEVICE_MAX_CONNECTIONS = 8) serialise: 6 lanes ran 8x slower */
+#define PM_MAX_LANES 4   /* measured, us per cfg5 pair: 1 / 2 / 3 / 4 lanes = 226 / 140 / 117 / 94; 6 lanes 167-555, 8 lanes 540-860; with an NCCL communicator alive in the process 230 / 141 / 219 / 360-900: 2 is the robust default */
 
 // Workspace slots (one growable device buffer each).
 enum pm_slot {
@@ -52,7 +52,7 @@ struct pm_ctx {
     pm_ctx *lane[PM_MAX_LANES] = {};
     cudaEvent_t ev_lane[PM_MAX_LANES] = {};
     cudaEvent_t ev_fork = nullptr;
-    int batch_lanes = 4;
+    int batch_lanes = 2;
     // chunked host path (pm_api.cu): uploads run on their own stream, one event per query chunk
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_fence = nullptr, ev_train = nullptr, ev_chunk[8] = {};
@@ -110,6 +110,10 @@ extern unsigned long long *g_pm_span;
 // it lets the NEXT kernel of the stream start launching right away (its CTAs become
 // resident and run their own prologue), then waits until the PREVIOUS kernel has fully
 // completed and flushed.  Data order is unchanged; only launch latency overlaps.
+// Set (per host thread) while a lane of the batched pair call enqueues: its kernels are launched WITHOUT the
+// programmatic attribute.  With several lanes, pre-launched CTAs that only wait (a K2 CTA holds a whole SM's
+// shared memory and TMEM) squat on the SMs the other lanes' running kernels need.
+extern thread_local int g_pm_tls_no_pdl;
 #ifdef __CUDACC__
 __device__ __forceinline__ void pm_span_mark(unsigned long long *span, int slot, bool is_max)
 {
@@ -160,7 +164,7 @@ static inline cudaError_t pm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_pm_tls_no_pdl ? 0 : 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 #endif

@@ -8,12 +8,18 @@ import points_matching_b200 as pm
 from points_matching_b200 import synth
 from points_matching_b200.pipeline import match_and_estimate_batch_native
 N = int(os.environ.get("PM_PAIR_N", "8192")); NP = int(os.environ.get("PM_PAIRS", "16")); NH = int(os.environ.get("PM_PAIR_HYP", "4096"))
-ctx = pm.Context(0)
+if os.environ.get("PM_INIT_DIST"):        # mimic bench.py under torchrun: NCCL process group in the same process
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    dist.barrier()
+DEV = int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("PM_INIT_DIST") else 0
+ctx = pm.Context(DEV)
 ctx.set_batch_lanes(int(os.environ.get("PM_LANES", "4")))
 pool = []
 for k in range(4):
     d1, d2, k1, k2, _ = synth.image_pair(N, N, seed=100 + k)
-    pool.append(tuple(torch.from_numpy(a).cuda() for a in (d1, d2, k1, k2)))
+    pool.append(tuple(torch.from_numpy(a).to(f"cuda:{DEV}") for a in (d1, d2, k1, k2)))
 plist = [pool[p % 4] for p in range(NP)]
 match_and_estimate_batch_native(ctx, plist[:4], n_hyp=NH)
 torch.cuda.synchronize(); t0 = time.perf_counter()
