@@ -198,17 +198,21 @@ __global__ void gather_points_kernel(const float2 *__restrict__ kp, int nkp, con
     out[i] = (k >= 0 && k < nkp) ? kp[k] : make_float2(0.f, 0.f);
 }
 
+// pts4 (optional): the same correspondences once more as {x1, y1, x2, y2}, the layout the scoring / mask / refit
+// kernels read -- saves the pack launches of the pair pipeline
 __global__ void gather_matches_kernel(const pm_dmatch *__restrict__ m, const int32_t *__restrict__ n_ptr,
                                       int max_matches, const float2 *__restrict__ kp1, int nkp1,
                                       const float2 *__restrict__ kp2, int nkp2,
-                                      float2 *__restrict__ p1, float2 *__restrict__ p2)
+                                      float2 *__restrict__ p1, float2 *__restrict__ p2, float4 *__restrict__ pts4)
 {
     const int n = min(*n_ptr, max_matches);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const pm_dmatch d = m[i];
-    p1[i] = (d.queryIdx >= 0 && d.queryIdx < nkp1) ? kp1[d.queryIdx] : make_float2(0.f, 0.f);
-    p2[i] = (d.trainIdx >= 0 && d.trainIdx < nkp2) ? kp2[d.trainIdx] : make_float2(0.f, 0.f);
+    const float2 a = (d.queryIdx >= 0 && d.queryIdx < nkp1) ? kp1[d.queryIdx] : make_float2(0.f, 0.f);
+    const float2 b = (d.trainIdx >= 0 && d.trainIdx < nkp2) ? kp2[d.trainIdx] : make_float2(0.f, 0.f);
+    p1[i] = a; p2[i] = b;
+    if (pts4) pts4[i] = make_float4(a.x, a.y, b.x, b.y);
 }
 
 }  // namespace
@@ -257,11 +261,11 @@ int pmk_gather_points(pm_ctx *ctx, const float *dkp, int nkp, const int32_t *did
 }
 
 int pmk_gather_matches(pm_ctx *ctx, const pm_dmatch *dm, const int32_t *dn, int max_matches, const float *dkp1,
-                       int nkp1, const float *dkp2, int nkp2, float *dp1, float *dp2)
+                       int nkp1, const float *dkp2, int nkp2, float *dp1, float *dp2, float *dpts4)
 {
     if (max_matches <= 0) return PM_OK;
     gather_matches_kernel<<<pm_cdiv(max_matches, 256), 256, 0, ctx->stream>>>(
-        dm, dn, max_matches, (const float2 *)dkp1, nkp1, (const float2 *)dkp2, nkp2, (float2 *)dp1, (float2 *)dp2);
+        dm, dn, max_matches, (const float2 *)dkp1, nkp1, (const float2 *)dkp2, nkp2, (float2 *)dp1, (float2 *)dp2, (float4 *)dpts4);
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }

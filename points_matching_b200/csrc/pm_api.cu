@@ -608,16 +608,17 @@ static int pair_enqueue(pm_ctx *ctx, const void *dd1, int n1, const void *dd2, i
     PM_WS(ctx, dcounts, int32_t *, WS_COUNTS, (size_t)nh * per * 4);
     PM_WS(ctx, dmask, uint8_t *, WS_MASK, (size_t)nmax);
     PM_WS(ctx, dF, double *, WS_FOUT, 16 * 8);
+    PM_WS(ctx, dpts, float *, WS_MISC, (size_t)nmax * 16);      // the matches as {x1, y1, x2, y2}, written by the gather
     float *dFw = dF32 + (size_t)nh * per * 12;
     int st;
     if ((st = pmk_l2_knn2_fused(ctx, dd1, n1, dd2, n2, dim, is_u8, 0, dknn, 0, ratio, dgood, dn_good)) != PM_OK) return st;
-    if ((st = pmk_gather_matches(ctx, dgood, dn_good, n1, dkp1, n1, dkp2, n2, dp1, dp2)) != PM_OK) return st;
+    if ((st = pmk_gather_matches(ctx, dgood, dn_good, n1, dkp1, n1, dkp2, n2, dp1, dp2, dpts)) != PM_OK) return st;
     if ((st = pmk_sample_sets(ctx, nmax, nh, m, seed, ds, dn_good)) != PM_OK) return st;
     if ((st = pmk_ransac_solve(ctx, dp1, dp2, nmax, ds, nh, m, dF32, dn_good)) != PM_OK) return st;
-    if ((st = pmk_ransac_score(ctx, dp1, dp2, nmax, dF32, nh * per, prm->threshold, prm->metric, dcounts, dn_good)) != PM_OK) return st;
-    if ((st = pmk_ransac_best(ctx, dcounts, nh * per, 0, dkey)) != PM_OK) return st;
-    if ((st = pmk_ransac_pick(ctx, dkey, dF32, 0, nh * per, dFw)) != PM_OK) return st;
-    if ((st = pmk_ransac_finish(ctx, dp1, dp2, nmax, dFw, prm->threshold, prm->metric, prm->refit, dF, dmask, dn_inl, dn_good)) != PM_OK) return st;
+    if ((st = pmk_ransac_score(ctx, dp1, dp2, nmax, dF32, nh * per, prm->threshold, prm->metric, dcounts, dn_good, dpts)) != PM_OK) return st;
+    if ((st = pmk_ransac_best_pick(ctx, dcounts, nh * per, 0, dF32, dkey, dFw, dn_inl)) != PM_OK) return st;
+    if ((st = pmk_ransac_finish(ctx, dp1, dp2, nmax, dFw, prm->threshold, prm->metric, prm->refit, dF, dmask, dn_inl, dn_good,
+                                dpts, 1)) != PM_OK) return st;
     return pmk_pair_result(ctx, dkey, dn_good, dn_inl, dF, nmax, m, dres);
 }
 

@@ -190,7 +190,8 @@ int pmk_minmax_filter(pm_ctx *ctx, const pm_dmatch *dm, int n, int stride, pm_dm
                       int32_t *dn_out, double *dminmax);
 int pmk_gather_points(pm_ctx *ctx, const float *dkp, int nkp, const int32_t *didx, int n, float *dout);
 int pmk_gather_matches(pm_ctx *ctx, const pm_dmatch *dm, const int32_t *dn, int max_matches,
-                       const float *dkp1, int nkp1, const float *dkp2, int nkp2, float *dp1, float *dp2);
+                       const float *dkp1, int nkp1, const float *dkp2, int nkp2, float *dp1, float *dp2,
+                       float *dpts4 = nullptr);
 // l2.cu / l2_tc.cu
 int pmk_l2_knn2(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
                 int q_index_base, pm_dmatch *dout);
@@ -205,11 +206,14 @@ int pmk_l2_col_best(pm_ctx *ctx, const float *dq, int nq, const float *dt, int n
 int pmk_ransac_solve(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const int32_t *dsamples,
                      int n_hyp, int m, float *dF32, const int32_t *dn = nullptr);
 int pmk_ransac_score(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dF32,
-                     int n_models, float thr, int metric, int32_t *dcounts, const int32_t *dn = nullptr);
+                     int n_models, float thr, int metric, int32_t *dcounts, const int32_t *dn = nullptr,
+                     const float *dpts4 = nullptr);
+int pmk_ransac_best_pick(pm_ctx *ctx, const int32_t *dcounts, int n_models, int id_base, const float *dF32, uint64_t *dkey,
+                         float *dFw, int32_t *dn_inl);
 int pmk_ransac_best(pm_ctx *ctx, const int32_t *dcounts, int n_models, int id_base, uint64_t *dkey);
 int pmk_ransac_finish(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dFw,
                       float thr, int metric, int refit, double *dF, uint8_t *dmask, int32_t *dn_inl,
-                      const int32_t *dn = nullptr);
+                      const int32_t *dn = nullptr, const float *dpts4 = nullptr, int ninl_is_zero = 0);
 int pmk_sample_sets(pm_ctx *ctx, int n_points, int n_hyp, int m, uint64_t seed, int32_t *dout,
                     const int32_t *dn = nullptr);
 int pmk_pair_result(pm_ctx *ctx, const uint64_t *dkey, const int32_t *dn_good, const int32_t *dn_inl, const double *dF,

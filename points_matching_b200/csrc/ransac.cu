@@ -498,6 +498,44 @@ ransac_best_kernel(const int32_t *__restrict__ counts, int n_models, int id_base
     if ((threadIdx.x & 31) == 0 && best) atomicMax(key, best);
 }
 
+// Small model sets (the pair pipeline: a few thousand hypotheses): ONE block finds the winner key, copies the
+// winning model and zeroes the inlier counter -- one launch instead of memset + best + pick + memset.  Same key,
+// same winner as ransac_best_kernel + ransac_pick_kernel (max over the same keys).
+__global__ void __launch_bounds__(1024)
+ransac_best_pick_kernel(const int32_t *__restrict__ counts, int n_models, int id_base, const float *__restrict__ Fm,
+                        unsigned long long *key_out, float *Fw, int32_t *n_inl)
+{
+    __shared__ unsigned long long sh[32];
+    unsigned long long best = 0;
+    for (int m = threadIdx.x; m < n_models; m += blockDim.x) {
+        const int c = counts[m];
+        if (c > 0) {
+            const unsigned long long k = ((unsigned long long)(unsigned)c << 32) | (0xFFFFFFFFu - (unsigned)(id_base + m));
+            best = k > best ? k : best;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long y = __shfl_xor_sync(0xffffffffu, best, o);
+        best = y > best ? y : best;
+    }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long y = __shfl_xor_sync(0xffffffffu, best, o);
+            best = y > best ? y : best;
+        }
+        if (threadIdx.x == 0) { *key_out = best; if (n_inl) *n_inl = 0; }
+        if (threadIdx.x < 12) {
+            const long long m = (long long)(0xFFFFFFFFu - (unsigned)(best & 0xFFFFFFFFu)) - id_base;
+            Fw[threadIdx.x] = (best != 0 && m >= 0 && m < n_models) ? Fm[(size_t)m * 12 + threadIdx.x] : __int_as_float(0x7fc00000);
+        }
+    }
+}
+
 __global__ void ransac_pick_kernel(const unsigned long long *key, const float *__restrict__ Fm, int id_base,
                                    int n_models, float *Fw)
 {
@@ -563,25 +601,49 @@ refit_sum_kernel(const float4 *__restrict__ pts, int n, const uint8_t *__restric
     block_reduce_store<5>(v, partial + blockIdx.x * 5);
 }
 // stats: [0..3] centroid, [4] count, [5] s1, [6] s2
-__global__ void refit_mean_kernel(const double *partial, double *stats)
+// The finalize steps between the passes (centroids from pass 1's partial sums, scales from pass 2's) are a few dozen
+// additions: every block of the NEXT pass repeats them itself, entry k summed over the blocks in ascending order,
+// and block 0 publishes them -- no single-warp kernels between the passes.
+__device__ __forceinline__ void refit_mean_inblock(const double *__restrict__ partial, double *sh, double *stats_out)
 {
-    // lane k sums entry k over the blocks in ascending order (the order a single thread would use)
     const int k = threadIdx.x;
-    double s = 0;
-    if (k < 5)
-        for (int b = 0; b < RF_BLOCKS; ++b) s += partial[b * 5 + k];
-    const double cnt = __shfl_sync(0xffffffffu, s, 4);
-    const double inv = cnt > 0 ? 1.0 / cnt : 0.0;
-    if (k < 4) stats[k] = s * inv;
-    if (k == 4) stats[4] = s;
+    if (k < 32) {
+        double s = 0;
+        if (k < 5)
+            for (int b = 0; b < RF_BLOCKS; ++b) s += partial[b * 5 + k];
+        const double cnt = __shfl_sync(0xffffffffu, s, 4);
+        const double inv = cnt > 0 ? 1.0 / cnt : 0.0;
+        if (k < 4) sh[k] = s * inv;
+        if (k == 4) sh[4] = s;
+        if (blockIdx.x == 0 && k < 5) stats_out[k] = k < 4 ? s * inv : s;
+    }
+    __syncthreads();
 }
-// pass 2: mean distances to the centroids
+__device__ __forceinline__ void refit_scale_inblock(const double *__restrict__ partial, const double cnt, double *sh,
+                                                    double *stats_out)
+{
+    const int e = threadIdx.x;
+    if (e < 2) {
+        double a = 0;
+        for (int k = 0; k < RF_BLOCKS; ++k) a += partial[k * 2 + e];
+        a = cnt > 0 ? a / cnt : 0;
+        const double sc = a >= FLT_EPSILON ? sqrt(2.) / a : 0.0;
+        sh[5 + e] = sc;
+        if (blockIdx.x == 0) stats_out[5 + e] = sc;
+    }
+    __syncthreads();
+}
+
+// pass 2: mean distances to the centroids.  fused != 0: the centroids come from pass 1's partial sums (partial_in)
 __global__ void __launch_bounds__(RF_THREADS)
 refit_scale_kernel(const float4 *__restrict__ pts, int n, const uint8_t *__restrict__ mask,
-                   const double *__restrict__ stats, double *partial, const int32_t *n_dev)
+                   double *__restrict__ stats, double *partial, const int32_t *n_dev, const double *partial_in)
 {
+    __shared__ double sst[8];
     n = eff_n(n, n_dev);
-    const double c1x = stats[0], c1y = stats[1], c2x = stats[2], c2y = stats[3];
+    if (partial_in) refit_mean_inblock(partial_in, sst, stats);
+    else { if (threadIdx.x < 5) sst[threadIdx.x] = stats[threadIdx.x]; __syncthreads(); }
+    const double c1x = sst[0], c1y = sst[1], c2x = sst[2], c2y = sst[3];
     double v[2] = {0, 0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         if (!mask || mask[i]) {
@@ -591,23 +653,18 @@ refit_scale_kernel(const float4 *__restrict__ pts, int n, const uint8_t *__restr
         }
     block_reduce_store<2>(v, partial + blockIdx.x * 2);
 }
-__global__ void refit_scale_final_kernel(const double *partial, double *stats)
-{
-    const int e = threadIdx.x;
-    if (e >= 2) return;
-    double a = 0;
-    for (int k = 0; k < RF_BLOCKS; ++k) a += partial[k * 2 + e];
-    const double cnt = stats[4];
-    a = cnt > 0 ? a / cnt : 0;
-    stats[5 + e] = a >= FLT_EPSILON ? sqrt(2.) / a : 0.0;
-}
 // pass 3: upper triangle of the 9x9 normal matrix sum r r^T (45 entries)
 __global__ void __launch_bounds__(RF_THREADS)
 refit_ata_kernel(const float4 *__restrict__ pts, int n, const uint8_t *__restrict__ mask,
-                 const double *__restrict__ stats, double *partial, const int32_t *n_dev)
+                 double *__restrict__ stats, double *partial, const int32_t *n_dev, const double *partial_in)
 {
+    __shared__ double sst[8];
     n = eff_n(n, n_dev);
-    const double c1x = stats[0], c1y = stats[1], c2x = stats[2], c2y = stats[3], s1 = stats[5], s2 = stats[6];
+    if (threadIdx.x < 5) sst[threadIdx.x] = stats[threadIdx.x];      // centroids and count (pass 2's block 0 wrote them)
+    __syncthreads();
+    if (partial_in) refit_scale_inblock(partial_in, sst[4], sst, stats);
+    else { if (threadIdx.x < 2) sst[5 + threadIdx.x] = stats[5 + threadIdx.x]; __syncthreads(); }
+    const double c1x = sst[0], c1y = sst[1], c2x = sst[2], c2y = sst[3], s1 = sst[5], s2 = sst[6];
     double acc[45];
 #pragma unroll
     for (int k = 0; k < 45; ++k) acc[k] = 0;
@@ -920,19 +977,16 @@ int get_pts4(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float
 int run_refit(pm_ctx *ctx, const float4 *pts, int n, const uint8_t *dmask, const float *dFfallback, double *dF,
               int32_t *dok, const int32_t *dn = nullptr)
 {
-    PM_WS(ctx, ws, double *, WS_REFIT, (size_t)(RF_BLOCKS * 45 + 16) * sizeof(double));
-    double *stats = ws + RF_BLOCKS * 45;
-    refit_sum_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, ws, dn);
+    // one partial-sum region per pass (a pass reads the previous pass's partials while it writes its own)
+    PM_WS(ctx, ws, double *, WS_REFIT, (size_t)(RF_BLOCKS * (5 + 2 + 45) + 16) * sizeof(double));
+    double *part1 = ws, *part2 = ws + RF_BLOCKS * 5, *part3 = part2 + RF_BLOCKS * 2, *stats = part3 + RF_BLOCKS * 45;
+    refit_sum_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, part1, dn);
     PM_CHECK_LAUNCH(ctx);
-    refit_mean_kernel<<<1, 32, 0, ctx->stream>>>(ws, stats);
+    refit_scale_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, stats, part2, dn, part1);
     PM_CHECK_LAUNCH(ctx);
-    refit_scale_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, stats, ws, dn);
+    refit_ata_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, stats, part3, dn, part2);
     PM_CHECK_LAUNCH(ctx);
-    refit_scale_final_kernel<<<1, 32, 0, ctx->stream>>>(ws, stats);
-    PM_CHECK_LAUNCH(ctx);
-    refit_ata_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, stats, ws, dn);
-    PM_CHECK_LAUNCH(ctx);
-    refit_solve_kernel<<<1, 32, 0, ctx->stream>>>(ws, stats, dFfallback, dF, dok);
+    refit_solve_kernel<<<1, 32, 0, ctx->stream>>>(part3, stats, dFfallback, dF, dok);
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }
@@ -953,12 +1007,14 @@ int pmk_ransac_solve(pm_ctx *ctx, const float *dp1, const float *dp2, int n, con
 }
 
 int pmk_ransac_score(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dF32, int n_models,
-                     float thr, int metric, int32_t *dcounts, const int32_t *dn)
+                     float thr, int metric, int32_t *dcounts, const int32_t *dn, const float *dpts4)
 {
     if (n_models <= 0) return PM_OK;
-    const float4 *pts;
-    int st = get_pts4(ctx, dp1, dp2, n, &pts, dn);
-    if (st != PM_OK) return st;
+    const float4 *pts = reinterpret_cast<const float4 *>(dpts4);       // already packed {x1, y1, x2, y2}, or null
+    if (!pts) {
+        int st = get_pts4(ctx, dp1, dp2, n, &pts, dn);
+        if (st != PM_OK) return st;
+    }
     // 4 models per thread when there are enough models to fill the GPU; 1 model per thread for small batches
     // (e.g. 4096 hypotheses x 4096 matches per image pair in config 5), where 4 would leave most SMs idle
     int mpt = SC_MPT;
@@ -1001,6 +1057,15 @@ int pmk_ransac_best(pm_ctx *ctx, const int32_t *dcounts, int n_models, int id_ba
     return PM_OK;
 }
 
+// winner key + winning model + zeroed inlier counter in one single-block launch (small model sets)
+int pmk_ransac_best_pick(pm_ctx *ctx, const int32_t *dcounts, int n_models, int id_base, const float *dF32, uint64_t *dkey,
+                         float *dFw, int32_t *dn_inl)
+{
+    ransac_best_pick_kernel<<<1, 1024, 0, ctx->stream>>>(dcounts, n_models, id_base, dF32, (unsigned long long *)dkey, dFw, dn_inl);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}
+
 int pmk_ransac_pick(pm_ctx *ctx, const uint64_t *dkey, const float *dF32, int id_base, int n_models, float *dFw)
 {
     ransac_pick_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long *)dkey, dF32, id_base, n_models, dFw);
@@ -1009,12 +1074,15 @@ int pmk_ransac_pick(pm_ctx *ctx, const uint64_t *dkey, const float *dF32, int id
 }
 
 int pmk_ransac_finish(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dFw, float thr, int metric,
-                      int refit, double *dF, uint8_t *dmask, int32_t *dn_inl, const int32_t *dn)
+                      int refit, double *dF, uint8_t *dmask, int32_t *dn_inl, const int32_t *dn, const float *dpts4,
+                      int ninl_is_zero)
 {
-    const float4 *pts;
-    int st = get_pts4(ctx, dp1, dp2, n, &pts, dn);
-    if (st != PM_OK) return st;
-    PM_CUDA(ctx, cudaMemsetAsync(dn_inl, 0, 4, ctx->stream));
+    const float4 *pts = reinterpret_cast<const float4 *>(dpts4);
+    if (!pts) {
+        int st = get_pts4(ctx, dp1, dp2, n, &pts, dn);
+        if (st != PM_OK) return st;
+    }
+    if (!ninl_is_zero) PM_CUDA(ctx, cudaMemsetAsync(dn_inl, 0, 4, ctx->stream));
     const float thr2 = thr * thr;
     if (n > 0) {
         if (metric == PM_METRIC_SAMPSON)

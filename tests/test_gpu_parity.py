@@ -256,24 +256,29 @@ def test_fused_knn2_ratio_equals_two_calls(ctx, pm, kind, nq, nt):
 
 
 @pytest.mark.parametrize("kind,nq,nt,calls", [("sift", 10000, 10000, 40), ("sift", 300, 500, 300), ("sift", 2000, 700, 100),
-                                              ("surf", 3000, 4000, 40), ("surf", 257, 300, 200)])
+                                              ("surf", 3000, 4000, 40), ("surf", 257, 300, 200), ("sift", 40000, 300, 24),
+                                              ("u8", 5000, 3000, 60)])
 def test_pipelined_chains_equal_serial(ctx, pm, kind, nq, nt, calls):
     """pm_set_pipelining: back-to-back one-call chains overlap (K1 of call i+1 runs ahead of K3/K5 of call i, two
     buffer sets) and still give the serial results bit for bit -- distinct input sets per call, outputs into
     per-call buffers and into one shared buffer, with other libpm calls (kNN only, another shape, Hamming on
     the tensor path, which shares the workspaces) interleaved."""
     torch = _dev(ctx)
-    gen = synth.sift_pair if kind == "sift" else synth.surf_pair
+    gen = synth.surf_pair if kind == "surf" else synth.sift_pair
     sets = []
     for k in range(4):
         q, t = gen(nq, nt, seed=100 + k)
+        if kind == "u8":             # SIFT shipped as bytes: the u8 entry of the same chain
+            q, t = q.astype(np.uint8), t.astype(np.uint8)
         sets.append((torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()))
+    chain = ctx.knn2_ratio_l2_u8_dev if kind == "u8" else ctx.knn2_ratio_l2_f32_dev
+    knn_only = ctx.knn2_l2_u8_dev if kind == "u8" else ctx.knn2_l2_f32_dev
     new = lambda: (torch.zeros((nq, 2, 4), dtype=torch.int32, device="cuda"), torch.zeros((nq, 4), dtype=torch.int32, device="cuda"),
                    torch.full((1,), -1, dtype=torch.int32, device="cuda"))
     serial = []
     for dq, dt in sets:
         o = new()
-        ctx.knn2_ratio_l2_f32_dev(dq.data_ptr(), nq, dt.data_ptr(), nt, 128, 0.8, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), 3)
+        chain(dq.data_ptr(), nq, dt.data_ptr(), nt, 128, 0.8, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), 3)
         serial.append(o)
     torch.cuda.synchronize()
     hq = torch.randint(0, 256, (5000, 32), dtype=torch.uint8, device="cuda")
@@ -288,14 +293,14 @@ def test_pipelined_chains_equal_serial(ctx, pm, kind, nq, nt, calls):
         for i in range(calls):
             dq, dt = sets[i % 4]
             o = outs[i]
-            ctx.knn2_ratio_l2_f32_dev(dq.data_ptr(), nq, dt.data_ptr(), nt, 128, 0.8, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), 3)
+            chain(dq.data_ptr(), nq, dt.data_ptr(), nt, 128, 0.8, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), 3)
             if i % 11 == 5:      # a kNN-only call of another shape in between (not a signalling chain)
-                ctx.knn2_l2_f32_dev(oq.data_ptr(), oq.shape[0], ot.data_ptr(), ot.shape[0], 128, oknn.data_ptr(), 0)
+                knn_only(oq.data_ptr(), oq.shape[0], ot.data_ptr(), ot.shape[0], 128, oknn.data_ptr(), 0)
             if i % 17 == 9:      # Hamming on the tensor path: same workspaces, another chain
                 ctx.knn2_hamming_dev(hq.data_ptr(), 5000, hq.data_ptr(), 5000, 32, hknn.data_ptr(), 0)
         for i in range(calls):   # and everything into ONE set of output buffers
             dq, dt = sets[i % 4]
-            ctx.knn2_ratio_l2_f32_dev(dq.data_ptr(), nq, dt.data_ptr(), nt, 128, 0.8, shared[0].data_ptr(), shared[1].data_ptr(),
+            chain(dq.data_ptr(), nq, dt.data_ptr(), nt, 128, 0.8, shared[0].data_ptr(), shared[1].data_ptr(),
                                       shared[2].data_ptr(), 3)
         torch.cuda.synchronize()
     finally:
@@ -311,7 +316,7 @@ def test_pipelined_chains_equal_serial(ctx, pm, kind, nq, nt, calls):
     assert int(shared[2].item()) == n and torch.equal(shared[0], ref[0]) and torch.equal(shared[1][:n], ref[1][:n])
     # the interleaved calls were not disturbed either
     chk = torch.zeros_like(oknn)
-    ctx.knn2_l2_f32_dev(oq.data_ptr(), oq.shape[0], ot.data_ptr(), ot.shape[0], 128, chk.data_ptr(), 0)
+    knn_only(oq.data_ptr(), oq.shape[0], ot.data_ptr(), ot.shape[0], 128, chk.data_ptr(), 0)
     torch.cuda.synchronize()
     assert torch.equal(chk, oknn)
 
