@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(FB) compact_lookback_kernel(Pred pred, int n, 
                                                               unsigned long long *status, unsigned *counter,
                                                               unsigned epoch, int use_ticket, unsigned long long *span,
                                                               unsigned long long *chain_done, unsigned *chain_ctr,
-                                                              unsigned long long chain_seq)
+                                                              unsigned long long chain_seq, pm_gather_out g)
 {
     __shared__ int s_tile, s_prefix;
     pm_span_mark(span, 12, false);
@@ -134,15 +134,26 @@ __global__ void __launch_bounds__(FB) compact_lookback_kernel(Pred pred, int n, 
         }
     }
     __syncthreads();
-    if (f) out[s_prefix + ex] = m;
+    if (f) {
+        const int pos = s_prefix + ex;
+        out[pos] = m;
+        if (g.kp1) {         // fused KeyPoint::convert on both sides (same bounds rule as gather_matches_kernel)
+            const float2 a = (m.queryIdx >= 0 && m.queryIdx < g.nkp1) ? reinterpret_cast<const float2 *>(g.kp1)[m.queryIdx] : make_float2(0.f, 0.f);
+            const float2 b = (m.trainIdx >= 0 && m.trainIdx < g.nkp2) ? reinterpret_cast<const float2 *>(g.kp2)[m.trainIdx] : make_float2(0.f, 0.f);
+            reinterpret_cast<float2 *>(g.p1)[pos] = a;
+            reinterpret_cast<float2 *>(g.p2)[pos] = b;
+            if (g.pts4) reinterpret_cast<float4 *>(g.pts4)[pos] = make_float4(a.x, a.y, b.x, b.y);
+        }
+    }
     pm_chain_signal(chain_done, chain_ctr, chain_seq);
     pm_span_mark(span, 14, true);
 }
 
 template <class Pred>
 int run_compact(pm_ctx *ctx, Pred pred, int n, pm_dmatch *dout, int32_t *dn_out, unsigned long long *chain_done = nullptr,
-                unsigned *chain_ctr = nullptr, unsigned long long chain_seq = 0)
+                unsigned *chain_ctr = nullptr, unsigned long long chain_seq = 0, const pm_gather_out *gather = nullptr)
 {
+    const pm_gather_out g = gather ? *gather : pm_gather_out{nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr};
     if (n <= 0) {
         PM_CUDA(ctx, cudaMemsetAsync(dn_out, 0, sizeof(int32_t), ctx->stream));
         return PM_OK;
@@ -159,12 +170,12 @@ int run_compact(pm_ctx *ctx, Pred pred, int n, pm_dmatch *dout, int32_t *dn_out,
     if (epoch >= (1u << 29)) {   // keep the 30-bit tag from wrapping into a stale match
         PM_CUDA(ctx, cudaMemsetAsync(st, 0, ctx->slot_bytes[WS_COUNT], ctx->stream));
         ctx->compact_epoch = 0;
-        return run_compact(ctx, pred, n, dout, dn_out, chain_done, chain_ctr, chain_seq);
+        return run_compact(ctx, pred, n, dout, dn_out, chain_done, chain_ctr, chain_seq, gather);
     }
     unsigned *counter = reinterpret_cast<unsigned *>(st);          // st[0]: two ticket counters
     const int use_ticket = nb > ctx->num_sms;                      // <= 1 block per SM: all tiles resident at once
     PM_CUDA(ctx, pm_launch_pdl(compact_lookback_kernel<Pred>, dim3(nb), dim3(FB), 0, ctx->stream, pred, n, dout, dn_out, st + 1,
-                               counter, epoch, use_ticket, g_pm_span, chain_done, chain_ctr, chain_seq));
+                               counter, epoch, use_ticket, g_pm_span, chain_done, chain_ctr, chain_seq, g));
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }
@@ -217,15 +228,16 @@ __global__ void gather_matches_kernel(const pm_dmatch *__restrict__ m, const int
 
 }  // namespace
 
-int pmk_ratio_filter(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout, int32_t *dn_out)
+int pmk_ratio_filter(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout, int32_t *dn_out,
+                     const pm_gather_out *gather)
 {
-    return run_compact(ctx, RatioPred{dknn, ratio}, nq, dout, dn_out);
+    return run_compact(ctx, RatioPred{dknn, ratio}, nq, dout, dn_out, nullptr, nullptr, 0, gather);
 }
 
 int pmk_ratio_filter_tail(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout, int32_t *dn_out,
-                          unsigned long long *chain_done, unsigned *chain_ctr, unsigned long long seq)
+                          unsigned long long *chain_done, unsigned *chain_ctr, unsigned long long seq, const pm_gather_out *gather)
 {
-    return run_compact(ctx, RatioPred{dknn, ratio}, nq, dout, dn_out, chain_done, chain_ctr, seq);
+    return run_compact(ctx, RatioPred{dknn, ratio}, nq, dout, dn_out, chain_done, chain_ctr, seq, gather);
 }
 
 int pmk_cross_check(pm_ctx *ctx, const pm_dmatch *dknn, int nq, int stride, const uint64_t *dcol_best, int nt,

@@ -609,7 +609,8 @@ int l2_flags_acquire(pm_ctx *ctx, L2Flags **cur, L2Flags **zero_next, L2Flags **
 // K5 slower, 36.1 vs 33.6 us per step); what the mode buys is K1's 4 us.  (K3 applying the ratio test itself was tried as well: with 313 32-row tiles the
 // ordered prefix inside K3 cost 8-10 us against 3.8 us for K5 behind one PDL boundary.)
 static int l2_chain(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
-                    int q_index_base, pm_dmatch *dout, int phase, float ratio, pm_dmatch *dgood, int32_t *dn_good)
+                    int q_index_base, pm_dmatch *dout, int phase, float ratio, pm_dmatch *dgood, int32_t *dn_good,
+                    const pm_gather_out *gather = nullptr)
 {
     if (nq <= 0 && phase != 1) {
         if (dgood) PM_CUDA(ctx, cudaMemsetAsync(dn_good, 0, sizeof(int32_t), ctx->stream));
@@ -626,7 +627,7 @@ static int l2_chain(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt,
         int st = is_u8 ? run_exact(ctx, (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, q_index_base, dout)
                        : run_exact(ctx, (const float *)dq, (const float *)dt, nq, nt, dim, q_index_base, dout);
         if (st != PM_OK || !dgood) return st;
-        return pmk_ratio_filter(ctx, dout, nq, ratio, dgood, dn_good);
+        return pmk_ratio_filter(ctx, dout, nq, ratio, dgood, dn_good, gather);
     }
     // ---- chain pipelining state ----
     const bool signalling = ctx->pipelining && phase == 0 && dgood != nullptr;     // this chain's tail stores its number
@@ -711,8 +712,8 @@ static int l2_chain(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt,
     PM_CHECK_LAUNCH(ctx);
     ctx->l2_stats[3] = smax;
     if (!dgood) return PM_OK;
-    if (!signalling) return pmk_ratio_filter(ctx, dout, nq, ratio, dgood, dn_good);
-    st = pmk_ratio_filter_tail(ctx, dout, nq, ratio, dgood, dn_good, chain_done, chain_ctr, seq);
+    if (!signalling) return pmk_ratio_filter(ctx, dout, nq, ratio, dgood, dn_good, gather);
+    st = pmk_ratio_filter_tail(ctx, dout, nq, ratio, dgood, dn_good, chain_done, chain_ctr, seq, gather);
     if (st != PM_OK) return st;
     ctx->chain_seq = seq;
     ctx->tail_is_chain = true;              // cleared by the next launch of any other kind (PM_CHECK_LAUNCH)
@@ -721,9 +722,10 @@ static int l2_chain(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt,
 }
 
 int pmk_l2_knn2_fused(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
-                      int q_index_base, pm_dmatch *dout, int phase, float ratio, pm_dmatch *dgood, int32_t *dn_good)
+                      int q_index_base, pm_dmatch *dout, int phase, float ratio, pm_dmatch *dgood, int32_t *dn_good,
+                      const pm_gather_out *gather)
 {
-    return l2_chain(ctx, dq, nq, dt, nt, dim, is_u8, q_index_base, dout, phase, ratio, dgood, dn_good);
+    return l2_chain(ctx, dq, nq, dt, nt, dim, is_u8, q_index_base, dout, phase, ratio, dgood, dn_good, gather);
 }
 
 int pmk_l2_knn2_phase(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,

@@ -591,7 +591,9 @@ int pm_find_fundamental_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int
 }
 
 // main.cpp:43-98 for one image pair, entirely in stream order (no host round trip): the match count stays on
-// the device (dn_good) and bounds every RANSAC kernel through its n_dev argument.
+// the device (dn_good) and bounds every RANSAC kernel through its n_dev argument.  13 launches: K1, K2, K3, K5 (which
+// also gathers the keypoint coordinates of the survivors), sample sets, K6, K7, best+pick, mask, three refit passes
+// and the refit solve, which writes the result record.
 static int pair_enqueue(pm_ctx *ctx, const void *dd1, int n1, const void *dd2, int n2, int dim, int is_u8, const float *dkp1,
                         const float *dkp2, float ratio, const pm_ransac_params *prm, uint64_t seed, pm_pair_result *dres)
 {
@@ -603,23 +605,23 @@ static int pair_enqueue(pm_ctx *ctx, const void *dd1, int n1, const void *dd2, i
     int32_t *dn_good = reinterpret_cast<int32_t *>(dkey + 2), *dn_inl = dn_good + 1;
     PM_WS(ctx, dp1, float *, WS_P1, (size_t)nmax * 8);
     PM_WS(ctx, dp2, float *, WS_P2, (size_t)nmax * 8);
+    PM_WS(ctx, dpts, float *, WS_MISC, (size_t)nmax * 16);      // the matches as {x1, y1, x2, y2}
     PM_WS(ctx, ds, int32_t *, WS_SAMPLES, (size_t)nh * m * 4);
     PM_WS(ctx, dF32, float *, WS_F32, ((size_t)nh * per + 1) * 12 * 4);
     PM_WS(ctx, dcounts, int32_t *, WS_COUNTS, (size_t)nh * per * 4);
     PM_WS(ctx, dmask, uint8_t *, WS_MASK, (size_t)nmax);
     PM_WS(ctx, dF, double *, WS_FOUT, 16 * 8);
-    PM_WS(ctx, dpts, float *, WS_MISC, (size_t)nmax * 16);      // the matches as {x1, y1, x2, y2}, written by the gather
     float *dFw = dF32 + (size_t)nh * per * 12;
     int st;
-    if ((st = pmk_l2_knn2_fused(ctx, dd1, n1, dd2, n2, dim, is_u8, 0, dknn, 0, ratio, dgood, dn_good)) != PM_OK) return st;
-    if ((st = pmk_gather_matches(ctx, dgood, dn_good, n1, dkp1, n1, dkp2, n2, dp1, dp2, dpts)) != PM_OK) return st;
+    // K5 gathers while it scatters: the good matches leave as DMatch records AND as the two point lists
+    const pm_gather_out g = {dkp1, n1, dkp2, n2, dp1, dp2, dpts};
+    if ((st = pmk_l2_knn2_fused(ctx, dd1, n1, dd2, n2, dim, is_u8, 0, dknn, 0, ratio, dgood, dn_good, &g)) != PM_OK) return st;
     if ((st = pmk_sample_sets(ctx, nmax, nh, m, seed, ds, dn_good)) != PM_OK) return st;
     if ((st = pmk_ransac_solve(ctx, dp1, dp2, nmax, ds, nh, m, dF32, dn_good)) != PM_OK) return st;
     if ((st = pmk_ransac_score(ctx, dp1, dp2, nmax, dF32, nh * per, prm->threshold, prm->metric, dcounts, dn_good, dpts)) != PM_OK) return st;
     if ((st = pmk_ransac_best_pick(ctx, dcounts, nh * per, 0, dF32, dkey, dFw, dn_inl)) != PM_OK) return st;
-    if ((st = pmk_ransac_finish(ctx, dp1, dp2, nmax, dFw, prm->threshold, prm->metric, prm->refit, dF, dmask, dn_inl, dn_good,
-                                dpts, 1)) != PM_OK) return st;
-    return pmk_pair_result(ctx, dkey, dn_good, dn_inl, dF, nmax, m, dres);
+    return pmk_ransac_finish(ctx, dp1, dp2, nmax, dFw, prm->threshold, prm->metric, prm->refit, dF, dmask, dn_inl, dn_good,
+                             dpts, 1, dkey, m, dres);      // its last kernel writes the pair's result record
 }
 
 static int pair_check(pm_ctx *ctx, int dim, const pm_ransac_params *prm)
@@ -680,8 +682,10 @@ int pm_match_estimate_batched_dev(pm_ctx *ctx, int n_pairs, const void *const *d
     }
     PM_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     for (int k = 0; k < L; ++k) PM_CUDA(ctx, cudaStreamWaitEvent(ctx->lane[k]->stream, ctx->ev_fork, 0));
-    // one host thread per lane: a pair is ~20 launches, and a single thread enqueues them more slowly than four
-    // lanes execute them.  Each lane context is touched by exactly one thread.
+    // one host thread per lane (a pair is 13 launches; a single thread enqueuing four lanes measured 109 instead of
+    // 94 us per pair).  1 / 2 / 4 lanes fit T = a + b / L with a = 58 us per pair that does not overlap -- it did not
+    // move when the chain went from 20 to 13 launches, nor with a two-stage schedule (every matching chain on the ctx
+    // stream, only the RANSAC tails on the lanes): it is GPU work, K2 alone needs every SM for ~20 us per pair.
     uint64_t before[PM_MAX_LANES];
     int lane_st[PM_MAX_LANES];
     for (int k = 0; k < L; ++k) { before[k] = ctx->lane[k]->launches; lane_st[k] = PM_OK; }

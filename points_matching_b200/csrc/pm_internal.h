@@ -172,6 +172,12 @@ static inline cudaError_t pm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim
 static inline int pm_cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int pm_round_up(int a, int b) { return pm_cdiv(a, b) * b; }
 
+// Optional gather fused into the ratio filter's scatter (pair pipeline): survivor i also leaves as the two
+// keypoint coordinates (KeyPoint::convert, main.cpp:89-91) and as the packed {x1, y1, x2, y2}.
+struct pm_gather_out {
+    const float *kp1; int nkp1; const float *kp2; int nkp2; float *p1; float *p2; float *pts4;
+};
+
 // ---- kernels-by-file entry points (host launchers) --------------------------------
 // hamming.cu
 int pmk_hamming_knn2(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, int bytes,
@@ -180,10 +186,11 @@ int pmk_hamming_col_best(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *
                          int q_index_base, uint64_t *dcol_best);
 // filter.cu
 int pmk_ratio_filter(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout,
-                     int32_t *dn_out);
+                     int32_t *dn_out, const pm_gather_out *gather = nullptr);
 // same, as the tail of signalling chain `seq` (stores seq to chain_done when the last block is done)
 int pmk_ratio_filter_tail(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout,
-                          int32_t *dn_out, unsigned long long *chain_done, unsigned *chain_ctr, unsigned long long seq);
+                          int32_t *dn_out, unsigned long long *chain_done, unsigned *chain_ctr, unsigned long long seq,
+                          const pm_gather_out *gather = nullptr);
 int pmk_cross_check(pm_ctx *ctx, const pm_dmatch *dknn, int nq, int stride, const uint64_t *dcol_best,
                     int nt, pm_dmatch *dout, int32_t *dn_out);
 int pmk_minmax_filter(pm_ctx *ctx, const pm_dmatch *dm, int n, int stride, pm_dmatch *dout,
@@ -198,7 +205,8 @@ int pmk_l2_knn2(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int
 int pmk_l2_knn2_phase(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
                       int q_index_base, pm_dmatch *dout, int phase);
 int pmk_l2_knn2_fused(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int dim, int is_u8,
-                      int q_index_base, pm_dmatch *dout, int phase, float ratio, pm_dmatch *dgood, int32_t *dn_good);
+                      int q_index_base, pm_dmatch *dout, int phase, float ratio, pm_dmatch *dgood, int32_t *dn_good,
+                      const pm_gather_out *gather = nullptr);
 int pmk_l2_col_best(pm_ctx *ctx, const float *dq, int nq, const float *dt, int nt, int dim,
                     int q_index_base, uint64_t *dcol_best);
 // ransac.cu
@@ -213,7 +221,8 @@ int pmk_ransac_best_pick(pm_ctx *ctx, const int32_t *dcounts, int n_models, int 
 int pmk_ransac_best(pm_ctx *ctx, const int32_t *dcounts, int n_models, int id_base, uint64_t *dkey);
 int pmk_ransac_finish(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dFw,
                       float thr, int metric, int refit, double *dF, uint8_t *dmask, int32_t *dn_inl,
-                      const int32_t *dn = nullptr, const float *dpts4 = nullptr, int ninl_is_zero = 0);
+                      const int32_t *dn = nullptr, const float *dpts4 = nullptr, int ninl_is_zero = 0,
+                      const uint64_t *dkey = nullptr, int sample_size = 0, pm_pair_result *dres = nullptr);
 int pmk_sample_sets(pm_ctx *ctx, int n_points, int n_hyp, int m, uint64_t seed, int32_t *dout,
                     const int32_t *dn = nullptr);
 int pmk_pair_result(pm_ctx *ctx, const uint64_t *dkey, const int32_t *dn_good, const int32_t *dn_inl, const double *dF,

@@ -682,12 +682,26 @@ refit_ata_kernel(const float4 *__restrict__ pts, int n, const uint8_t *__restric
     block_reduce_store<45>(acc, partial + blockIdx.x * 45);
 }
 
+// The pair pipeline's result record, written by the last kernel of the chain (null res: none).
+struct PairOut {
+    const unsigned long long *key; const int32_t *n_good; const int32_t *n_inl; int n_max; int m; pm_pair_result *res;
+};
+__device__ __forceinline__ void write_pair_result(const PairOut &po, const double *F)
+{
+    const unsigned long long k = *po.key;
+    const int n = min(max(*po.n_good, 0), po.n_max);
+    const bool ok = k != 0ull && n >= po.m;
+    for (int i = 0; i < 9; ++i) po.res->F[i] = ok ? F[i] : 0.0;
+    po.res->key = ok ? k : 0ull; po.res->n_matches = n; po.res->n_inliers = ok ? *po.n_inl : 0;
+    po.res->has_model = ok; po.res->reserved = 0;
+}
+
 // pass 4 (one warp): 9x9 cyclic Jacobi (lanes 0..8 each own index k of the rotation
 // updates), smallest eigenvector, rank-2 projection, de-normalisation.  Falls back to the
 // winning minimal model when there are < 8 points or the system is degenerate.
 __global__ void __launch_bounds__(32)
 refit_solve_kernel(const double *__restrict__ partial, const double *__restrict__ stats,
-                   const float *__restrict__ Ffallback, double *__restrict__ Fout, int32_t *ok_out)
+                   const float *__restrict__ Ffallback, double *__restrict__ Fout, int32_t *ok_out, PairOut po)
 {
     __shared__ double A[81], V[81];
     const int lane = threadIdx.x;
@@ -788,6 +802,7 @@ refit_solve_kernel(const double *__restrict__ partial, const double *__restrict_
     if (!ok && Ffallback) for (int i = 0; i < 9; ++i) F[i] = (double)Ffallback[i];
     if (ok || Ffallback) for (int i = 0; i < 9; ++i) Fout[i] = F[i];
     if (ok_out) *ok_out = ok ? 1 : 0;
+    if (po.res) write_pair_result(po, F);      // (F is only read when a model exists, and then ok || Ffallback holds)
 }
 
 __global__ void copy_f32_to_f64_kernel(const float *src, double *dst, int n)
@@ -975,7 +990,7 @@ int get_pts4(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float
 }
 
 int run_refit(pm_ctx *ctx, const float4 *pts, int n, const uint8_t *dmask, const float *dFfallback, double *dF,
-              int32_t *dok, const int32_t *dn = nullptr)
+              int32_t *dok, const int32_t *dn = nullptr, PairOut po = PairOut{nullptr, nullptr, nullptr, 0, 0, nullptr})
 {
     // one partial-sum region per pass (a pass reads the previous pass's partials while it writes its own)
     PM_WS(ctx, ws, double *, WS_REFIT, (size_t)(RF_BLOCKS * (5 + 2 + 45) + 16) * sizeof(double));
@@ -986,7 +1001,7 @@ int run_refit(pm_ctx *ctx, const float4 *pts, int n, const uint8_t *dmask, const
     PM_CHECK_LAUNCH(ctx);
     refit_ata_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, stats, part3, dn, part2);
     PM_CHECK_LAUNCH(ctx);
-    refit_solve_kernel<<<1, 32, 0, ctx->stream>>>(part3, stats, dFfallback, dF, dok);
+    refit_solve_kernel<<<1, 32, 0, ctx->stream>>>(part3, stats, dFfallback, dF, dok, po);
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }
@@ -1075,7 +1090,7 @@ int pmk_ransac_pick(pm_ctx *ctx, const uint64_t *dkey, const float *dF32, int id
 
 int pmk_ransac_finish(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dFw, float thr, int metric,
                       int refit, double *dF, uint8_t *dmask, int32_t *dn_inl, const int32_t *dn, const float *dpts4,
-                      int ninl_is_zero)
+                      int ninl_is_zero, const uint64_t *dkey, int sample_size, pm_pair_result *dres)
 {
     const float4 *pts = reinterpret_cast<const float4 *>(dpts4);
     if (!pts) {
@@ -1091,9 +1106,12 @@ int pmk_ransac_finish(pm_ctx *ctx, const float *dp1, const float *dp2, int n, co
             ransac_mask_kernel<PM_METRIC_SYMEPI><<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>(pts, n, dFw, thr2, dmask, dn_inl, dn);
         PM_CHECK_LAUNCH(ctx);
     }
-    if (refit) return run_refit(ctx, pts, n, dmask, dFw, dF, nullptr, dn);
+    // dres: the pair pipeline's record; with a refit its last kernel writes it, else a kernel of its own
+    if (refit) return run_refit(ctx, pts, n, dmask, dFw, dF, nullptr, dn,
+                                PairOut{(const unsigned long long *)dkey, dn, dn_inl, n, sample_size, dres});
     copy_f32_to_f64_kernel<<<1, 32, 0, ctx->stream>>>(dFw, dF, 9);
     PM_CHECK_LAUNCH(ctx);
+    if (dres) return pmk_pair_result(ctx, dkey, dn, dn_inl, dF, n, sample_size, dres);
     return PM_OK;
 }
 
