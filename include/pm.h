@@ -56,7 +56,8 @@ typedef enum pm_status {
 int  pm_version(void);
 int  pm_create(pm_ctx **ctx, int device);
 int  pm_destroy(pm_ctx *ctx);
-/* Run on an existing cudaStream_t (e.g. torch's current stream); NULL = ctx-owned stream. */
+/* Run on an existing cudaStream_t (e.g. torch's current stream); NULL = ctx-owned stream.  Changing the
+ * stream first waits for the work this ctx enqueued on the old one (the workspaces are shared). */
 int  pm_set_stream(pm_ctx *ctx, void *cuda_stream);
 int  pm_sync(pm_ctx *ctx);
 /* Opt-in overlap of consecutive pm_knn2_ratio_l2_*_dev calls of equal shapes (default off).  With it on,

@@ -108,7 +108,13 @@ int pm_set_batch_lanes(pm_ctx *ctx, int lanes)
 int pm_set_stream(pm_ctx *ctx, void *s)
 {
     if (!ctx) return PM_BAD_ARG;
-    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    cudaStream_t ns = s ? (cudaStream_t)s : ctx->own_stream;
+    if (ns != ctx->stream) {
+        // the workspaces are shared by everything this ctx enqueues: work still running on the old stream must not
+        // meet work enqueued on the new one
+        PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->stream = ns;
+    }
     ctx->tail_is_chain = false;
     return PM_OK;
 }
