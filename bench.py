@@ -15,9 +15,6 @@ The second headline metric, RANSAC-F hypotheses/sec (configs[3]: 100k correspond
 outliers, 8-point, Sampson 1 px), is reported in the "secondary" object of the same line.
 Prints ONE JSON line on rank 0.
 """
-import os as _os
-# the batched pair call (cfg5 leg) keeps several pairs in flight on internal streams: give them work queues of their own
-_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import argparse
 import json
 import os
@@ -573,8 +570,8 @@ def bench_cfg5(ctx, torch, dev, world, rank, barrier):
         pool.append(tuple(torch.from_numpy(a).to(dev) for a in (d1, d2, k1, k2)))
     import points_matching_b200 as pm
     from points_matching_b200.pipeline import match_and_estimate_batch, match_and_estimate_batch_native
-    plist = [pool[p % 4] for p in range(1024 // world)]      # this rank's contiguous share of the 1024 pairs
-    pairs = len(plist)
+    plist = [pool[p % 4] for p in range(1024)]      # the whole batch, identical on every rank: the calls below take
+    pairs = len(plist) // world                     # this rank's contiguous share (shard_bounds) and nothing else
 
     def timed(fn):
         barrier()
@@ -591,16 +588,14 @@ def bench_cfg5(ctx, torch, dev, world, rank, barrier):
 
     # (a) the C ABI's batched entry: one call enqueues every pair, no host round trip inside a pair
     nctx = pm.Context(dev.index)
-    # pairs in flight: 4 when this process drives the GPU alone; with the NCCL communicator of a multi-rank run
-    # alive in the process more than 2 lanes serialise badly (measured: 141 us per pair at 2 lanes, 360+ at 4)
-    lanes = 4 if world == 1 else 2
+    lanes = int(os.environ.get("PM_BENCH_LANES", "0")) or 8       # pairs in flight (internal streams of the batched call)
     nctx.set_batch_lanes(lanes)
-    match_and_estimate_batch_native(nctx, plist[:6], n_hyp=4096)
+    match_and_estimate_batch_native(nctx, plist[:8 * world], n_hyp=4096)      # warm-up: 8 pairs on every rank
     ms_n, last_n = timed(lambda: match_and_estimate_batch_native(nctx, plist, n_hyp=4096)[-1][1])
     # (b) the staged Python pipeline: three pipelines (own ctx + stream each), one pair's host round trip for
     #     the match count hides behind the others' kernels
     pipes = [PairPipeline(pm.Context(dev.index), dev, n, n_hyp=4096) for _ in range(3)]
-    match_and_estimate_batch(pipes, plist[:6])
+    match_and_estimate_batch(pipes, plist[:8 * world])
     ms_s, last_s = timed(lambda: match_and_estimate_batch(pipes, plist)[-1][1])   # each finish() synchronises its stream
     same = last_n["n_matches"] == last_s["n_matches"] and last_n["n_inliers"] == last_s["n_inliers"]
     ms = min(ms_n, ms_s)

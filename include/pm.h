@@ -239,13 +239,12 @@ int pm_match_estimate_batched_dev(pm_ctx *ctx, int n_pairs, const void *const *d
                                   const float *const *dkp1, const float *const *dkp2, float ratio,
                                   const pm_ransac_params *prm, pm_pair_result *dresults);
 
-/* Number of pairs the batched call keeps in flight (1..4 internal streams with their own workspaces, one
- * host thread enqueues each; default 2).  Results do not depend on it.  Measured per 8192 x 8192 pair with 4096
- * hypotheses: 1 / 2 / 3 / 4 lanes = 226 / 140 / 117 / 94 us in a process that drives the GPU alone, but
- * 230 / 141 / 219 / 360+ us when an NCCL communicator is alive in the same process -- more concurrently
- * active streams than the GPU front end schedules well serialise badly -- so 2 is the default and 4 is
- * worth setting only for a process without other CUDA users.  PM_BATCH_THREADS=0 (environment) makes one
- * host thread enqueue all lanes. */
+/* Number of pairs the batched call keeps in flight (1..8 internal streams with their own workspaces, one
+ * host thread enqueues each; default 4).  Results do not depend on it.  Measured per 8192 x 8192 pair with 4096
+ * hypotheses: 1 / 2 / 4 / 6 / 8 lanes = 207 / 130 / 86 / 71 / 67 us.  A lane and its workspaces are created
+ * the first time it is used (cudaMalloc synchronises the device), so the first batch after a change of lanes or
+ * shapes is slow: warm up once.  PM_BATCH_THREADS=0 (environment) makes one host thread enqueue all lanes
+ * (94 us per pair at 8 lanes). */
 int pm_set_batch_lanes(pm_ctx *ctx, int lanes);
 
 /* LMedS over 7-point minimal samples -- what cv::findFundamentalMat(p1, p2, CV_FM_7POINT) actually runs when

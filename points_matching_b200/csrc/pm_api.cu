@@ -688,10 +688,10 @@ int pm_match_estimate_batched_dev(pm_ctx *ctx, int n_pairs, const void *const *d
     }
     PM_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     for (int k = 0; k < L; ++k) PM_CUDA(ctx, cudaStreamWaitEvent(ctx->lane[k]->stream, ctx->ev_fork, 0));
-    // one host thread per lane (a pair is 13 launches; a single thread enqueuing four lanes measured 109 instead of
-    // 94 us per pair).  1 / 2 / 4 lanes fit T = a + b / L with a = 58 us per pair that does not overlap -- it did not
-    // move when the chain went from 20 to 13 launches, nor with a two-stage schedule (every matching chain on the ctx
-    // stream, only the RANSAC tails on the lanes): it is GPU work, K2 alone needs every SM for ~20 us per pair.
+    // one host thread per lane: a pair is 13 launches, and a single thread enqueuing eight lanes measured 94 instead
+    // of 67 us per pair.  (Lanes and their workspaces are created on first use -- cudaMalloc synchronises the device --
+    // so a batch that meets a cold lane is slow; an earlier measurement without a warm-up made 6 and 8 lanes look 5x
+    // slower than 4.)
     uint64_t before[PM_MAX_LANES];
     int lane_st[PM_MAX_LANES];
     for (int k = 0; k < L; ++k) { before[k] = ctx->lane[k]->launches; lane_st[k] = PM_OK; }

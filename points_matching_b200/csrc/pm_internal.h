@@ -10,7 +10,7 @@
 
 #define PM_NSLOTS 40
 #define PM_PROF_RING 4096
-#define PM_MAX_LANES 4   /* measured, us per cfg5 pair: 1 / 2 / 3 / 4 lanes = 226 / 140 / 117 / 94; 6 lanes 167-555, 8 lanes 540-860; with an NCCL communicator alive in the process 230 / 141 / 219 / 360-900: 2 is the robust default */
+#define PM_MAX_LANES 8   /* measured, us per cfg5 pair (every lane warmed up first): 1 / 2 / 4 / 6 / 8 lanes = 207 / 130 / 86 / 71 / 67 */
 
 // Workspace slots (one growable device buffer each).
 enum pm_slot {
@@ -52,7 +52,7 @@ struct pm_ctx {
     pm_ctx *lane[PM_MAX_LANES] = {};
     cudaEvent_t ev_lane[PM_MAX_LANES] = {};
     cudaEvent_t ev_fork = nullptr;
-    int batch_lanes = 2;
+    int batch_lanes = 4;
     // chunked host path (pm_api.cu): uploads run on their own stream, one event per query chunk
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_fence = nullptr, ev_train = nullptr, ev_chunk[8] = {};

@@ -21,9 +21,10 @@ for k in range(4):
     d1, d2, k1, k2, _ = synth.image_pair(N, N, seed=100 + k)
     pool.append(tuple(torch.from_numpy(a).to(f"cuda:{DEV}") for a in (d1, d2, k1, k2)))
 plist = [pool[p % 4] for p in range(NP)]
-match_and_estimate_batch_native(ctx, plist[:4], n_hyp=NH)
+WORLD = int(os.environ.get("WORLD_SIZE", "1")) if os.environ.get("PM_INIT_DIST") else 1
+match_and_estimate_batch_native(ctx, plist[:16 * WORLD], n_hyp=NH)      # warm-up: 16 pairs on every rank, so every lane exists and owns its workspaces
 torch.cuda.synchronize(); t0 = time.perf_counter()
 out = match_and_estimate_batch_native(ctx, plist, n_hyp=NH)
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
-print("native batched: %.1f us per pair (%d pairs of %d x %d, %d hypotheses); last: %d matches, %d inliers; %d launches"
-      % (dt / NP * 1e6, NP, N, N, NH, out[-1][1]["n_matches"], out[-1][1]["n_inliers"], ctx.launch_count()))
+print("native batched: %.1f us per pair and rank (%d pairs in all, %d x %d, %d hypotheses); last: %d matches, %d inliers; %d launches"
+      % (dt / (NP // WORLD) * 1e6, NP, N, N, NH, out[-1][1]["n_matches"], out[-1][1]["n_inliers"], ctx.launch_count()))
