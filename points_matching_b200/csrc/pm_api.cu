@@ -12,7 +12,6 @@
 int pmk_ransac_pick(pm_ctx *ctx, const uint64_t *dkey, const float *dF32, int id_base, int n_models, float *dFw);
 
 unsigned long long *g_pm_span = nullptr;
-thread_local int g_pm_tls_no_pdl = 0;
 extern "C" void pm_debug_set_span(unsigned long long *p) { g_pm_span = p; }
 
 int pm_fail(pm_ctx *ctx, int status, const char *fmt, ...)
@@ -695,14 +694,11 @@ int pm_match_estimate_batched_dev(pm_ctx *ctx, int n_pairs, const void *const *d
     uint64_t before[PM_MAX_LANES];
     int lane_st[PM_MAX_LANES];
     for (int k = 0; k < L; ++k) { before[k] = ctx->lane[k]->launches; lane_st[k] = PM_OK; }
-    const int no_pdl = 1;      // lanes launch without the programmatic attribute (see g_pm_tls_no_pdl)
     auto run_lane = [&](int k) {
         cudaSetDevice(ctx->device);
-        g_pm_tls_no_pdl = no_pdl;
         for (int p = k; p < n_pairs && lane_st[k] == PM_OK; p += L)
             lane_st[k] = pair_enqueue(ctx->lane[k], dd1[p], n1[p], dd2[p], n2[p], dim, is_u8, dkp1[p], dkp2[p], ratio, prm,
                                       prm->seed + (uint64_t)p, dres + p);
-        g_pm_tls_no_pdl = 0;
     };
     static const bool lane_threads = !(getenv("PM_BATCH_THREADS") && atoi(getenv("PM_BATCH_THREADS")) == 0);
     if (n_pairs >= 2 * L && lane_threads) {

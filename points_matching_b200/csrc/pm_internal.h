@@ -110,10 +110,6 @@ extern unsigned long long *g_pm_span;
 // it lets the NEXT kernel of the stream start launching right away (its CTAs become
 // resident and run their own prologue), then waits until the PREVIOUS kernel has fully
 // completed and flushed.  Data order is unchanged; only launch latency overlaps.
-// Set (per host thread) while a lane of the batched pair call enqueues: its kernels are launched WITHOUT the
-// programmatic attribute.  With several lanes, pre-launched CTAs that only wait (a K2 CTA holds a whole SM's
-// shared memory and TMEM) squat on the SMs the other lanes' running kernels need.
-extern thread_local int g_pm_tls_no_pdl;
 #ifdef __CUDACC__
 __device__ __forceinline__ void pm_span_mark(unsigned long long *span, int slot, bool is_max)
 {
@@ -164,7 +160,7 @@ static inline cudaError_t pm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = g_pm_tls_no_pdl ? 0 : 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 #endif

@@ -26,5 +26,10 @@ match_and_estimate_batch_native(ctx, plist[:16 * WORLD], n_hyp=NH)      # warm-u
 torch.cuda.synchronize(); t0 = time.perf_counter()
 out = match_and_estimate_batch_native(ctx, plist, n_hyp=NH)
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
+torch.cuda.synchronize(); t0 = time.perf_counter()
+match_and_estimate_batch_native(ctx, plist, n_hyp=NH, sync=False)
+t_enq = time.perf_counter() - t0
+torch.cuda.synchronize(); t_all = time.perf_counter() - t0
+print("  enqueue returns after %.1f us per pair, everything done after %.1f us per pair" % (t_enq / (NP // WORLD) * 1e6, t_all / (NP // WORLD) * 1e6))
 print("native batched: %.1f us per pair and rank (%d pairs in all, %d x %d, %d hypotheses); last: %d matches, %d inliers; %d launches"
       % (dt / (NP // WORLD) * 1e6, NP, N, N, NH, out[-1][1]["n_matches"], out[-1][1]["n_inliers"], ctx.launch_count()))
