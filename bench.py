@@ -333,8 +333,10 @@ def run_ours(args):
     hgood = torch.zeros((NQ, 4), dtype=torch.int32).pin_memory()
     e_steps = max(3, min(steps, 200))
     n_host_good = 0
-    for i in range(60):          # warm-up: the first ~50 calls run up to 1.4x slower (PCIe link / host side ramping up)
+    t_warm, i = time.perf_counter() + 0.3, 0    # warm-up by time: the first few hundred calls run up to 1.4x slower (host / PCIe side ramping up)
+    while time.perf_counter() < t_warm or i < 3:
         ctx.knn2_ratio_l2_ptr(hq[i % 4].data_ptr(), NQ, ht[i % 4].data_ptr(), NT, DIM, RATIO, hknn.data_ptr(), hgood.data_ptr())
+        i += 1
     # five blocks of e_steps / 5 calls; the reported figure is the MEDIAN block (host-side interference -- other
     # tenants on the PCIe switch, the nvidia-smi sampler -- moved single blocks by 2x between otherwise equal runs)
     e_blocks, e_per = [], max(1, e_steps // 5)
