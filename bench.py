@@ -413,12 +413,13 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": dict(config_dict(world), step_overlap=(
-                "none: every step waits for the previous one" if args.no_pipelining else
-                "pm_set_pipelining: K1 (pack) of step i+1 overlaps K3/K5 (re-rank, filter) of step i; every step runs all four kernels")),
+            "config": config_dict(world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "secondary": secondary, "extra": extra,
             "notes": {"good_matches_last_step": n_good_last, "clock_ramp_steps": ramp,
+                      "step_overlap": ("none: every step waits for the previous one" if args.no_pipelining else
+                                       "pm_set_pipelining: K1 (pack) of step i+1 overlaps K3/K5 (re-rank, filter) of step i; "
+                                       "every step runs all four kernels"),
                       "dtype_detail": "bf16 operands (exact for 0..255 integers), fp32 accumulate in TMEM, "
                                       "fp32 norms / selection / output"}}
     sys.stdout.flush()
