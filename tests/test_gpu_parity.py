@@ -615,6 +615,27 @@ def test_native_batched_pairs_equal_python_pipeline(pm):
     ctx.close(); ctx2.close()
 
 
+def test_pair_entry_on_reference_image_pair(pm, golden, orc):
+    """BASELINE config 1 through the whole-pair C-ABI entry: the reference's own image pair (img01 / img02.JPG, SIFT
+    stand-in, descriptors as bytes), knnMatch(k=2) + ratio 0.75 + KeyPoint::convert + findFundamentalMat(RANSAC), one
+    device-resident call.  The match count equals OpenCV's; F is at least as good as OpenCV's RANSAC F on OpenCV's
+    own inlier set (north_star tolerance: 1e-3 mean Sampson error)."""
+    import torch
+    from points_matching_b200.pipeline import match_and_estimate_batch_native
+    g = golden["image_pair"]
+    ctx = pm.Context(0)
+    pair = tuple(torch.from_numpy(np.ascontiguousarray(g[k])).cuda() for k in ("desc1", "desc2", "kp1", "kp2"))
+    res = match_and_estimate_batch_native(ctx, [pair], n_hyp=4096, ratio=0.75)[0][1]
+    ctx.close()
+    assert res["n_matches"] == len(g["ratio_q"]) and res["F"] is not None
+    inl = g["ransac_mask"].astype(bool)
+    p1, p2 = g["kp1"][g["ratio_q"]][inl], g["kp2"][g["ratio_t"]][inl]
+    s_ours = orc.sampson_f64(res["F"], p1, p2).mean()
+    s_cv = orc.sampson_f64(g["ransac_F"], p1, p2).mean()
+    assert s_ours <= s_cv + 1e-3, (s_ours, s_cv)
+    assert res["n_inliers"] >= 0.9 * inl.sum()
+
+
 def test_lmeds_scoring_bit_exact_and_end_to_end(ctx, pm, orc):
     """LMedS (the reference's literal estimator, main.cpp:95-98 with N > 7): medians bit-exact vs the oracle on
     identical model bits; end to end on identical 7-point index sets the same winner / mask up to the solver's
