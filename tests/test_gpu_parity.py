@@ -607,6 +607,14 @@ def test_native_batched_pairs_equal_python_pipeline(pm):
     assert r8["n_matches"] == ref[0][1]["n_matches"] and np.array_equal(r8["F"], ref[0][1]["F"])
     rec = torch.zeros(PAIR_RESULT.itemsize, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
+    # argument errors come back as PM_BAD_ARG (OpenCV: cv::Exception -215), nothing is enqueued
+    for bad in (dict(n_hyp=0), dict(n_hyp=64, sample_size=6), dict(n_hyp=64, metric=7)):
+        with pytest.raises(pm.PMError):
+            ctx2.match_estimate_pair_dev(p0[0].data_ptr(), p0[0].shape[0], p0[1].data_ptr(), p0[1].shape[0], 128, False,
+                                         p0[2].data_ptr(), p0[3].data_ptr(), 0.75, rec.data_ptr(), **bad)
+    for lanes in (0, 9):
+        with pytest.raises(pm.PMError):
+            ctx2.set_batch_lanes(lanes)
     ctx2.match_estimate_pair_dev(p0[0].data_ptr(), p0[0].shape[0], p0[1].data_ptr(), p0[1].shape[0], 128, False, p0[2].data_ptr(),
                                  p0[3].data_ptr(), 0.75, rec.data_ptr(), 1024, seed=0)
     ctx2.sync()
