@@ -108,7 +108,8 @@ def match_and_estimate_batch_native(ctx, pairs, n_hyp=4096, ratio=0.75, threshol
     mine = pairs[lo:hi]
     dev = mine[0][0].device if mine else torch.device("cuda")
     res = torch.zeros((max(len(mine), 1), PAIR_RESULT.itemsize), dtype=torch.uint8, device=dev)
-    torch.cuda.current_stream(dev).synchronize()      # inputs / records made on torch's stream; libpm uses the ctx stream
+    if dev.type == "cuda":
+        torch.cuda.current_stream(dev).synchronize()  # inputs / records made on torch's stream; libpm uses the ctx stream
     if mine:
         is_u8 = mine[0][0].dtype == torch.uint8
         ctx.match_estimate_batched_dev([p[0].data_ptr() for p in mine], [p[0].shape[0] for p in mine],

@@ -68,6 +68,28 @@ class OracleEngine:
                 torch.from_numpy(r["mask"].copy()), torch.tensor([r["n_inliers"]], dtype=torch.int32))
 
 
+class StubPairCtx:
+    """Stands in for libpm's batched pair entry (pm_match_estimate_batched_dev): records what a rank asks for and
+    fills the PAIR_RESULT records so that the host-side sharding of BASELINE config 5 can be checked without a GPU:
+    pair p must be processed exactly once, by the rank that owns it, with seed p."""
+    def __init__(self):
+        self.calls = []
+
+    def match_estimate_batched_dev(self, d1, n1, d2, n2, dim, is_u8, kp1, kp2, ratio, dresults, n_hyp, sample_size=8,
+                                   metric=0, threshold=1.0, refit=True, seed=0):
+        import ctypes
+        from points_matching_b200._lib import PAIR_RESULT
+        self.calls.append((len(d1), seed))
+        buf = (ctypes.c_uint8 * (len(d1) * PAIR_RESULT.itemsize)).from_address(dresults)
+        rec = np.frombuffer(buf, dtype=PAIR_RESULT)
+        for i in range(len(d1)):
+            rec[i]["F"] = np.arange(9) + 100.0 * (seed + i)          # the pair's seed = its global index
+            rec[i]["n_matches"], rec[i]["n_inliers"], rec[i]["has_model"] = n1[i], n2[i], 1 if n1[i] >= 8 else 0
+
+    def sync(self):
+        pass
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -105,6 +127,19 @@ def _worker(rank, world, port, out_dir):
             res[f"ransac{m}_F"] = F.numpy()
             res[f"ransac{m}_mask"] = mask.numpy()
             res[f"ransac{m}_meta"] = np.array([ninl, winner])
+        # BASELINE config 5: a batch of image pairs partitioned across the ranks (ragged: 7 pairs)
+        import torch
+        from points_matching_b200.pipeline import match_and_estimate_batch_native
+        pairs = [(torch.zeros((5 + k, 128)), torch.zeros((9 + k, 128)), torch.zeros((5 + k, 2)), torch.zeros((9 + k, 2)))
+                 for k in range(7)]
+        stub = StubPairCtx()
+        mine = match_and_estimate_batch_native(stub, pairs, n_hyp=64)
+        assert len(stub.calls) == 1 and stub.calls[0] == (len(mine), mine[0][0] if mine else stub.calls[0][1])
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        allp = sorted((p, o["n_matches"], o["n_inliers"], float(o["F"][0, 0]) if o["F"] is not None else -1.0)
+                      for part in everyone for p, o in part)
+        res["pairs"] = np.array(allp)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **res)
     finally:
         dist.destroy_process_group()
@@ -140,6 +175,9 @@ def test_sharded_protocol_matches_single_rank(world, tmp_path, orc):
         assert int(got[f"ransac{m}_meta"][0]) == r["n_inliers"]
         assert np.array_equal(got[f"ransac{m}_mask"], r["mask"])
         assert np.allclose(got[f"ransac{m}_F"], r["F"].reshape(9), rtol=1e-12, atol=0)
+    # the pair batch: every pair exactly once, processed with its own index as the seed, model only from 8 matches up
+    exp = [(k, 5 + k, 9 + k, 100.0 * k if 5 + k >= 8 else -1.0) for k in range(7)]
+    assert np.array_equal(got["pairs"], np.array(exp))
     # shard bounds tile the range exactly
     for n in (0, 1, 7, 203, 10000):
         b = [shard_bounds(n, world, r) for r in range(world)]
