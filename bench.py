@@ -593,6 +593,7 @@ def bench_cfg5(ctx, torch, dev, world, rank, barrier):
     nctx = pm.Context(dev.index)
     lanes = int(os.environ.get("PM_BENCH_LANES", "0")) or 8       # pairs in flight (internal streams of the batched call)
     nctx.set_batch_lanes(lanes)
+    nctx.batch_warmup(n, n, 128, False, 4096)       # lanes and their workspaces exist before anything is timed
     match_and_estimate_batch_native(nctx, plist[:8 * world], n_hyp=4096)      # warm-up: 8 pairs on every rank
     ms_n, last_n = timed(lambda: match_and_estimate_batch_native(nctx, plist, n_hyp=4096)[-1][1])
     # (b) the staged Python pipeline: three pipelines (own ctx + stream each), one pair's host round trip for

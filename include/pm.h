@@ -246,6 +246,9 @@ int pm_match_estimate_batched_dev(pm_ctx *ctx, int n_pairs, const void *const *d
  * shapes is slow: warm up once.  PM_BATCH_THREADS=0 (environment) makes one host thread enqueue all lanes
  * (94 us per pair at 8 lanes). */
 int pm_set_batch_lanes(pm_ctx *ctx, int lanes);
+/* Optional: create the lanes and their workspaces for pairs of up to n1 x n2 descriptors now (a throw-away batch
+ * of empty pairs; synchronises), so that the first real batch does not pay for it. */
+int pm_batch_warmup(pm_ctx *ctx, int n1, int n2, int dim, int is_u8, const pm_ransac_params *prm);
 
 /* LMedS over 7-point minimal samples -- what cv::findFundamentalMat(p1, p2, CV_FM_7POINT) actually runs when
  * N > 7, i.e. the reference's literal call at main.cpp:95-98.  Per model the error is OpenCV's

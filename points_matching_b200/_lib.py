@@ -39,7 +39,7 @@ EXPORTS = [
     "pm_gather_points", "pm_gather_matches_dev",
     "pm_find_fundamental", "pm_find_fundamental_dev", "pm_make_sample_sets",
     "pm_ransac_solve_dev", "pm_ransac_score_dev", "pm_ransac_best_dev", "pm_ransac_finish_dev",
-    "pm_match_estimate_pair_dev", "pm_match_estimate_batched_dev", "pm_set_batch_lanes",
+    "pm_match_estimate_pair_dev", "pm_match_estimate_batched_dev", "pm_set_batch_lanes", "pm_batch_warmup",
     "pm_fundamental_8point", "pm_epilines", "pm_residuals", "pm_find_fundamental_lmeds", "pm_lmeds_score_dev", "pm_make_sample_sets_dev",
 ]
 

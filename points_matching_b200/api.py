@@ -363,6 +363,11 @@ class Context:
     def set_batch_lanes(self, lanes):
         self._chk(self._L.pm_set_batch_lanes(self._h, lanes))
 
+    def batch_warmup(self, n1, n2, dim, is_u8, n_hyp, sample_size=8, metric=0, threshold=1.0, refit=True):
+        """Create the lanes of the batched pair call and their workspaces ahead of the first real batch."""
+        prm = self._pair_params(n_hyp, sample_size, metric, threshold, refit, 0)
+        self._chk(self._L.pm_batch_warmup(self._h, n1, n2, dim, int(is_u8), C.byref(prm)))
+
     def make_sample_sets_dev(self, n_points, n_hyp, m, seed, dout):
         self._chk(self._L.pm_make_sample_sets_dev(self._h, n_points, n_hyp, m, C.c_uint64(seed), C.c_void_p(dout)))
 

@@ -721,6 +721,36 @@ int pm_match_estimate_batched_dev(pm_ctx *ctx, int n_pairs, const void *const *d
     return PM_OK;
 }
 
+// Creates the lanes and lets every one of them allocate its workspaces for pairs of up to n1 x n2 descriptors: a
+// throw-away batch of all-zero descriptors (no match survives the ratio test, so the RANSAC kernels run empty).
+int pm_batch_warmup(pm_ctx *ctx, int n1, int n2, int dim, int is_u8, const pm_ransac_params *prm)
+{
+    if (!ctx) return PM_BAD_ARG;
+    int st = pair_check(ctx, dim, prm);
+    if (st != PM_OK) return st;
+    PM_REQUIRE(ctx, n1 > 0 && n2 > 0, "sizes must be positive");
+    PM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t elem = is_u8 ? 1 : 4, b1 = (size_t)n1 * dim * elem, b2 = (size_t)n2 * dim * elem;
+    const int np = 2 * ctx->batch_lanes;
+    uint8_t *buf = nullptr;
+    const size_t off_d2 = (b1 + 255) & ~(size_t)255, off_k1 = off_d2 + ((b2 + 255) & ~(size_t)255),
+                 off_k2 = off_k1 + (((size_t)n1 * 8 + 255) & ~(size_t)255), off_res = off_k2 + (((size_t)n2 * 8 + 255) & ~(size_t)255),
+                 total = off_res + (size_t)np * sizeof(pm_pair_result);
+    PM_CUDA(ctx, cudaMalloc((void **)&buf, total));
+    cudaError_t e = cudaMemsetAsync(buf, 0, total, ctx->stream);
+    std::vector<const void *> d1(np, buf), d2(np, buf + off_d2);
+    std::vector<const float *> k1(np, (const float *)(buf + off_k1)), k2(np, (const float *)(buf + off_k2));
+    std::vector<int32_t> c1(np, n1), c2(np, n2);
+    if (e == cudaSuccess)
+        st = pm_match_estimate_batched_dev(ctx, np, d1.data(), c1.data(), d2.data(), c2.data(), dim, is_u8, k1.data(), k2.data(), 0.75f, prm,
+                                           (pm_pair_result *)(buf + off_res));
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(buf);
+    if (e != cudaSuccess || e2 != cudaSuccess)
+        return pm_fail(ctx, PM_CUDA_ERR, "pm_batch_warmup: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return st;
+}
+
 int pm_lmeds_score_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dF32, int n_models, float *dmedians)
 {
     if (!ctx) return PM_BAD_ARG;

@@ -583,6 +583,7 @@ def test_native_batched_pairs_equal_python_pipeline(pm):
                   torch.from_numpy(rng.uniform(0, 1000, (800, 2)).astype(np.float32)).cuda()))
     pairs.append(tuple(a[:5].contiguous() for a in pairs[0]))            # fewer rows than a minimal sample
     ref = match_and_estimate_batch(pipe, pairs)
+    ctx2.batch_warmup(4096, 4096, 128, False, 1024)       # lanes and workspaces ahead of the first batch (optional)
     for lanes in (4, 1, 7):          # pairs in flight (internal streams): results do not depend on it
         ctx2.set_batch_lanes(lanes)
         out = match_and_estimate_batch_native(ctx2, pairs * 2, n_hyp=1024)

@@ -22,7 +22,8 @@ for k in range(4):
     pool.append(tuple(torch.from_numpy(a).to(f"cuda:{DEV}") for a in (d1, d2, k1, k2)))
 plist = [pool[p % 4] for p in range(NP)]
 WORLD = int(os.environ.get("WORLD_SIZE", "1")) if os.environ.get("PM_INIT_DIST") else 1
-match_and_estimate_batch_native(ctx, plist[:16 * WORLD], n_hyp=NH)      # warm-up: 16 pairs on every rank, so every lane exists and owns its workspaces
+ctx.batch_warmup(N, N, 128, False, NH)       # every lane exists and owns its workspaces before anything is timed
+match_and_estimate_batch_native(ctx, plist[:4 * WORLD], n_hyp=NH)
 torch.cuda.synchronize(); t0 = time.perf_counter()
 out = match_and_estimate_batch_native(ctx, plist, n_hyp=NH)
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
