@@ -360,50 +360,56 @@ def run_ours(args):
            "ms_per_step_blocks": e_blocks, "timing": "median of 5 blocks, max over ranks per block"}
 
     # ---- the same call with SIFT shipped as bytes (pm_knn2_l2_u8: 4x fewer PCIe bytes, identical matches) ----
-    import ctypes as C
-    from points_matching_b200 import _lib
-    hq8 = torch.from_numpy(q0.astype(np.uint8)).pin_memory()
-    ht8 = torch.from_numpy(t0.astype(np.uint8)).pin_memory()
-    L = _lib.lib()
+    def u8_leg():
+        import ctypes as C
+        from points_matching_b200 import _lib
+        hq8 = torch.from_numpy(q0.astype(np.uint8)).pin_memory()
+        ht8 = torch.from_numpy(t0.astype(np.uint8)).pin_memory()
+        L = _lib.lib()
 
-    def u8_call():
-        st = L.pm_knn2_l2_u8(ctx._h, C.c_void_p(hq8.data_ptr()), NQ, C.c_void_p(ht8.data_ptr()), NT, DIM, C.c_void_p(hknn.data_ptr()))
-        assert st == 0, st
+        def u8_call():
+            st = L.pm_knn2_l2_u8(ctx._h, C.c_void_p(hq8.data_ptr()), NQ, C.c_void_p(ht8.data_ptr()), NT, DIM, C.c_void_p(hknn.data_ptr()))
+            assert st == 0, st
 
-    for _ in range(3):
-        u8_call()
-    barrier()
-    ev0.record(stream)
-    for _ in range(e_steps):
-        u8_call()
-    ev1.record(stream)
-    barrier()
-    u8_ms = ev0.elapsed_time(ev1) / e_steps
-    e2e["u8_wire_format"] = {"value": world * NQ * NT / (u8_ms * 1e-3), "unit": UNIT, "ms_per_step": u8_ms,
-                             "h2d_bytes_per_step": (NQ + NT) * DIM, "d2h_bytes_per_step": NQ * 2 * 16,
-                             "api": "pm_knn2_l2_u8 (kNN-2 only, host buffers, pinned)"}
+        for _ in range(3):
+            u8_call()
+        barrier()
+        ev0.record(stream)
+        for _ in range(e_steps):
+            u8_call()
+        ev1.record(stream)
+        barrier()
+        u8_ms = ev0.elapsed_time(ev1) / e_steps
+        e2e["u8_wire_format"] = {"value": world * NQ * NT / (u8_ms * 1e-3), "unit": UNIT, "ms_per_step": u8_ms,
+                                 "h2d_bytes_per_step": (NQ + NT) * DIM, "d2h_bytes_per_step": NQ * 2 * 16,
+                                 "api": "pm_knn2_l2_u8 (kNN-2 only, host buffers, pinned)"}
+        return None
+
+    guarded("e2e.u8_wire_format", world, u8_leg)
 
     # ---- secondary headline: RANSAC-F hypotheses/sec (config 4), hypotheses sharded by batch ----
     secondary = None
     if not args.no_ransac:
-        secondary = bench_ransac(ctx, torch, dist, dev, world, rank, stream, barrier, peaks, args)
+        secondary = guarded("ransac", world, lambda: bench_ransac(ctx, torch, dist, dev, world, rank, stream, barrier, peaks, args))
 
     extra = {}
     if not args.no_hamming:
-        extra["hamming"] = bench_hamming(ctx, torch, dev, world, rank, stream, barrier, peaks)
-        extra["l2_general_floats"] = bench_split_mode(ctx, torch, dev, rank, stream, barrier)
+        extra["hamming"] = guarded("hamming", world, lambda: bench_hamming(ctx, torch, dev, world, rank, stream, barrier, peaks))
+        extra["l2_general_floats"] = guarded("l2_general_floats", world, lambda: bench_split_mode(ctx, torch, dev, rank, stream, barrier))
     if not args.no_cfg5:
-        extra["cfg5"] = bench_cfg5(ctx, torch, dev, world, rank, barrier)
+        extra["cfg5"] = guarded("cfg5", world, lambda: bench_cfg5(ctx, torch, dev, world, rank, barrier))
     extra = extra or None
 
     clocks = sampler.stop() if sampler else None
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        fn, kind, cores, desc = cpu_match_fn()
-        rows, best = time_cpu_sample(fn, q0, t0, budget_s=4.0, reps=3)
-        cpu_baseline = {"value": rows * NT / best, "unit": UNIT, "cores": cores, "kind": kind,
-                        "sample": f"{rows} of {NQ} query rows x {NT} train rows, best of 3; {desc}"}
+        def cpu_leg():
+            fn, kind, cores, desc = cpu_match_fn()
+            rows, best = time_cpu_sample(fn, q0, t0, budget_s=4.0, reps=3)
+            return {"value": rows * NT / best, "unit": UNIT, "cores": cores, "kind": kind,
+                    "sample": f"{rows} of {NQ} query rows x {NT} train rows, best of 3; {desc}"}
+        cpu_baseline = guarded("cpu_baseline", world, cpu_leg)
 
     if world > 1:
         dist.barrier()
@@ -425,6 +431,19 @@ def run_ours(args):
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     return 0
+
+
+def guarded(name, world, fn):
+    """The legs after the headline (RANSAC, Hamming, general floats, cfg5) must not cost the JSON line: on a single GPU a
+    failing leg is reported in its place.  With several ranks an exception on one of them would leave the others in a
+    barrier, so there it propagates and the run fails fast."""
+    if world > 1:
+        return fn()
+    try:
+        return fn()
+    except Exception as e:      # noqa: BLE001
+        print(f"bench.py: leg '{name}' failed: {e!r}", file=sys.stderr)
+        return {"error": repr(e)}
 
 
 def measure_fp8_peak(torch, dev):
