@@ -318,6 +318,7 @@ def run_ours(args):
                 "in_chain": None if not k2_chain_us else {
                     "kernel_ms": k2_chain_us * 1e-3, "achieved": flops / (k2_chain_us * 1e-6) / 1e12,
                     "frac": flops / (k2_chain_us * 1e-6) / 1e12 / peaks["bf16_sustained"],
+                    "share_of_step": k2_chain_us * 1e-3 / ms_step if ms_step else None,
                     "how": "K2's own %globaltimer stamps (first CTA past griddepcontrol.wait -> last CTA out) inside the "
                            "programmatic-dependent-launch chain, median of 15 single steps; the event pair above breaks the "
                            "chain, so `kernel_ms` also contains K2's launch latency and prologue"},
