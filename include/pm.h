@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PM_VERSION 100
+#define PM_VERSION 200
 
 typedef struct pm_ctx pm_ctx;
 
@@ -48,7 +48,7 @@ typedef enum pm_status {
     PM_EMPTY     = 1,   /* OpenCV returns an empty Mat (e.g. N < 7): outputs untouched */
     PM_BAD_ARG   = -1,  /* OpenCV would raise cv::Exception -215 (type/dim mismatch)   */
     PM_CUDA_ERR  = -2,
-    PM_NCCL_ERR  = -3,
+    PM_NCCL_ERR  = -3,  /* libnccl.so.2 not loadable, no communicator set, or an NCCL call failed */
     PM_NO_DEVICE = -4
 } pm_status;
 
@@ -166,14 +166,15 @@ typedef struct pm_ransac_params {
     int32_t sample_size;   /* 8: normalised 8-point; 7: 7-point (up to 3 models per sample) */
     int32_t metric;        /* PM_METRIC_*                                                     */
     float   threshold;     /* pixels; inlier <=> err <= threshold^2                           */
-    int32_t n_hyp;         /* hypotheses (minimal samples) to evaluate                        */
+    int32_t n_hyp;         /* hypotheses (minimal samples) to evaluate; pm_find_fundamental_adaptive: per batch */
     int32_t refit;         /* !=0: N-point normalised 8-point on the winner's inliers         */
     const int32_t *sample_idx; /* [n_hyp][sample_size] HOST (host call) / DEVICE (_dev call)  */
                            /* index sets, distinct within a row; NULL: generated from `seed`  */
     uint64_t seed;
     int32_t hyp_id_base;   /* global id of this shard's hypothesis 0 (multi-GPU)              */
-    int32_t reserved;
-} pm_ransac_params;
+    int32_t max_iters;     /* pm_find_fundamental_adaptive: cap on the hypotheses (cv maxIters); <= 0: 1000 */
+    double  confidence;    /* pm_find_fundamental_adaptive: cv `confidence`; outside (0,1): 0.99 */
+} pm_ransac_params;        /* 56 bytes */
 
 /* RANSAC over minimal samples.  Winner = max inlier count, ties -> lowest model id
  * (id = hyp for 8-point, 3*hyp+k for 7-point).  F is row-major 3x3 f64 with F[8]=1;
@@ -182,6 +183,42 @@ typedef struct pm_ransac_params {
 int pm_find_fundamental(pm_ctx *ctx, const float *p1 /* [n][2] */, const float *p2, int n,
                         const pm_ransac_params *prm,
                         double F[9], uint8_t *mask, int *n_inliers);
+
+/* The same estimator with OpenCV's adaptive termination (findFundamentalMat's `confidence` / `maxIters`), driven from
+ * the device: the correspondences are uploaded ONCE, the minimal samples of every batch (prm->n_hyp per batch, <= 0:
+ * 1024) are generated on the device from prm->seed (prm->sample_idx is ignored), and only the 8-byte running winner key
+ * returns to the host per batch -- it feeds  niters = log(1 - confidence) / log(1 - w^sample_size)  (cv's
+ * RANSACUpdateNumIters), w = best inlier ratio so far.  The winner over all batches is "most inliers, lowest global
+ * model id on ties"; F, mask and n_inliers are read back once at the end.  *n_hyp_run (optional) = hypotheses evaluated. */
+int pm_find_fundamental_adaptive(pm_ctx *ctx, const float *p1, const float *p2, int n, const pm_ransac_params *prm,
+                                 double F[9], uint8_t *mask, int *n_inliers, int *n_hyp_run);
+
+/* cv::findFundamentalMat(points1, points2, method, param1, param2, mask) itself -- the call at main.cpp:95-98 with OpenCV's
+ * dispatch table (probed on cv2 4.13):
+ *     n < 7                                  -> PM_EMPTY (empty Mat)
+ *     n == 7 (any method)                    -> 7-point on the seven points: 1..3 stacked 3x3 models (cv returns 9x3), mask ones
+ *     PM_FM_8POINT                           -> N-point normalised 8-point, mask ones
+ *     PM_FM_RANSAC and n >= 15               -> RANSAC (adaptive, as pm_find_fundamental_adaptive)
+ *     everything else (PM_FM_7POINT with n > 7 = the reference's literal call, PM_FM_LMEDS, PM_FM_RANSAC with n < 15)
+ *                                            -> LMedS over 7-point samples, niters from `param2` at outlier ratio 0.45
+ *     param1 <= 0 -> 3;  param2 outside (DBL_EPSILON, 1 - DBL_EPSILON) -> 0.99;  max_iters <= 0 -> 1000
+ * F receives *n_models (1..3) row-major 3x3 f64 matrices with F[8] = 1; mask (optional) n bytes in {0, 1}.
+ * opt == NULL is OpenCV's estimator: 7-point samples, symmetric-epipolar error, no refit.  The north_star's variant
+ * (8-point samples, Sampson error, 8-point refit on the inliers) is opt = {8, PM_METRIC_SAMPSON, 1, ...}.
+ * The sample stream is libpm's own (splitmix64 from opt->seed), not cv::RNG: F is an equally valid RANSAC / LMedS answer,
+ * not bit-equal to OpenCV's. */
+enum { PM_FM_7POINT = 1, PM_FM_8POINT = 2, PM_FM_LMEDS = 4, PM_FM_RANSAC = 8 };   /* == cv::FM_* / CV_FM_* */
+typedef struct pm_fm_options {
+    int32_t sample_size;   /* RANSAC minimal sample: 7 (OpenCV) or 8; 0 -> 7                                 */
+    int32_t metric;        /* PM_METRIC_SYMEPI (OpenCV) or PM_METRIC_SAMPSON                                   */
+    int32_t refit;         /* RANSAC: !=0 refits the winner on its inliers (OpenCV does not)                   */
+    int32_t batch;         /* RANSAC hypotheses per batch between two looks at the adaptive stop; <= 0: 1024   */
+    uint64_t seed;
+} pm_fm_options;           /* 24 bytes */
+int pm_find_fundamental_mat(pm_ctx *ctx, const float *p1, const float *p2, int n, int method, double param1, double param2,
+                            int max_iters, const pm_fm_options *opt, double F[27], int *n_models, uint8_t *mask);
+/* The n == 7 case on its own: run7Point on seven correspondences, all real roots (1..3), full double precision. */
+int pm_fundamental_7point(pm_ctx *ctx, const float *p1, const float *p2, int n, double F[27], int *n_models);
 
 /* Deterministic minimal-sample index sets ([n_hyp][m], distinct within a row); the
  * same (n_points, n_hyp, m, seed) gives the same sets on every rank. */
@@ -239,6 +276,14 @@ int pm_match_estimate_batched_dev(pm_ctx *ctx, int n_pairs, const void *const *d
                                   const float *const *dkp1, const float *const *dkp2, float ratio,
                                   const pm_ransac_params *prm, pm_pair_result *dresults);
 
+/* The same batch from HOST memory, synchronous (config 5 end to end): desc1 / desc2 / kp1 / kp2 are arrays of HOST pointers
+ * (pinned memory for full PCIe speed), results [n_pairs] is host memory.  Every lane uploads its pairs on its own stream
+ * right before their kernels, so uploads run under the other lanes' kernels; 96 bytes per pair come back, once, at the end. */
+int pm_match_estimate_batched(pm_ctx *ctx, int n_pairs, const void *const *desc1, const int32_t *n1,
+                              const void *const *desc2, const int32_t *n2, int dim, int is_u8,
+                              const float *const *kp1, const float *const *kp2, float ratio,
+                              const pm_ransac_params *prm, pm_pair_result *results);
+
 /* Number of pairs the batched call keeps in flight (1..8 internal streams with their own workspaces, one
  * host thread enqueues each; default 4).  Results do not depend on it.  Measured per 8192 x 8192 pair with 4096
  * hypotheses: 1 / 2 / 4 / 6 / 8 lanes = 207 / 130 / 86 / 71 / 67 us.  A lane and its workspaces are created
@@ -264,6 +309,61 @@ int pm_lmeds_score_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n, c
 
 /* N-point normalised 8-point (findFundamentalMat(..., FM_8POINT)); mask all ones. */
 int pm_fundamental_8point(pm_ctx *ctx, const float *p1, const float *p2, int n, double F[9]);
+
+/* ---- multi-GPU: one process (or host thread) per GPU, NCCL over NVLink -------------------------------
+ * The reference is single-process; BASELINE.json's north_star shards its two calls: query rows per rank for the matcher
+ * (cross-check needs ONE exchange: min-reduce of the packed column minima), hypothesis batches per rank for RANSAC (ONE
+ * exchange: max-reduce of the 8-byte winner key).  libpm loads libnccl.so.2 at run time (dlopen: a process that never calls
+ * these entries does not need NCCL); every failure on that side returns PM_NCCL_ERR with pm_last_error() set.
+ *   pm_comm_unique_id  rank 0 makes the 128-byte ncclUniqueId and ships it to the other ranks (MPI, torch.distributed, a file)
+ *   pm_comm_init       ncclCommInitRank on the ctx's device; the ctx owns the communicator (destroyed by pm_destroy)
+ *   pm_set_comm        or: borrow the caller's ncclComm_t (void* = ncclComm_t); NULL detaches
+ * The collectives run on the ctx stream between the kernels they connect: nothing is synchronised. */
+#define PM_COMM_ID_BYTES 128
+int pm_comm_unique_id(void *id /* [PM_COMM_ID_BYTES] */);
+int pm_comm_init(pm_ctx *ctx, int n_ranks, int rank, const void *id /* [PM_COMM_ID_BYTES] */);
+int pm_set_comm(pm_ctx *ctx, void *nccl_comm, int n_ranks, int rank);
+int pm_comm_info(pm_ctx *ctx, int *n_ranks, int *rank);   /* 1, 0 without a communicator */
+/* BFMatcher(norm, crossCheck=true).match over a query set sharded by rows: this rank holds rows [q_index_base,
+ * q_index_base + nq) and the whole (replicated) train set.  kNN-2 of the shard -> dknn ([nq][2], optional), packed column
+ * minima of the shard -> dcol_best ([nt], scratch the caller provides) -> ncclAllReduce(ncclMin, ncclUint64) in place ->
+ * local filter: the shard's mutual matches in queryIdx order -> dout ([nq]), *dn_out.  Concatenating the ranks' lists in rank
+ * order gives exactly the single-GPU result.  norm: 4 = L2 (f32 rows of `width` floats), 6 = Hamming (rows of `width` bytes). */
+int pm_match_cross_sharded_dev(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int width, int norm,
+                               int q_index_base, pm_dmatch *dknn, uint64_t *dcol_best, pm_dmatch *dout, int32_t *dn_out);
+/* Fixed-width all-gather of per-rank match lists (the "gather of match results" of the north_star): dall is
+ * [n_ranks][max_per_rank], dcounts [n_ranks]; rank r's list is dall[r][0 .. dcounts[r]). */
+int pm_allgather_matches_dev(pm_ctx *ctx, const pm_dmatch *dlocal, const int32_t *dn_local, int max_per_rank,
+                             pm_dmatch *dall, int32_t *dcounts);
+/* RANSAC-F with the hypotheses sharded by batch: this rank solves and scores hypotheses [prm->hyp_id_base, + prm->n_hyp) of a
+ * job of n_hyp_total; prm->sample_idx is the FULL [n_hyp_total][sample_size] DEVICE array, identical on every rank, or NULL
+ * (every rank generates the sets of its shard, and later of the winner, from prm->seed: same sets as
+ * pm_make_sample_sets(n, n_hyp_total, m, seed)).  One ncclAllReduce(ncclMax, ncclUint64) of the winner key; every rank then
+ * re-solves the winning index set itself (no broadcast) and finishes (mask, optional refit): dF, dmask, dn_inliers and dkey
+ * are identical on every rank and identical to a single-GPU run over all n_hyp_total hypotheses. */
+int pm_find_fundamental_sharded_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const pm_ransac_params *prm,
+                                    int n_hyp_total, double *dF /* [9] */, uint8_t *dmask, int32_t *dn_inliers, uint64_t *dkey);
+
+/* ---- measured pipe peaks (bench.py roofline denominators; BASELINE.md: "measure them on the box") -----------------
+ * Independent-chain microkernels, one resident wave, timed with CUDA events on the ctx stream.
+ * which 0: FP32 FFMA issue -> *value = TFLOP/s (2 FLOP per FFMA);  1: POPC.32 -> *value = 1e12 POPC per second. */
+int pm_measure_peak(pm_ctx *ctx, int which, double *value);
+
+/* ---- NVTX: every entry point above opens an NVTX range named after itself (domain "libpm") when a profiler is attached;
+ * no cost otherwise. ---- */
+
+/* ---- debug hooks (process-global, NOT thread-safe, not part of the drop-in surface; used by tools/ and two bench legs) ----
+ *   pm_debug_set_span(p)            every kernel of the L2 chain stamps %globaltimer marks into p (tools/step_timeline.py)
+ *   pm_debug_hamming_path(k)        0 auto, 1 force the POPC kernel, 2 force the tensor-core kernel
+ *   pm_debug_force_exact(on)        L2: exact FP32 kernel for every row (cross-check of the two paths)
+ *   pm_debug_fallback_separate(on)  L2 one-call chain: run the flagged-row scan as its own kernel instead of helper blocks
+ *   pm_debug_set_l2_dump(p), pm_debug_set_k2_trace(p)   K2 tile dump / clock64 trace (PM_K2_TRACE builds) */
+void pm_debug_set_span(unsigned long long *p);
+void pm_debug_hamming_path(int path);
+void pm_debug_force_exact(int on);
+void pm_debug_fallback_separate(int on);
+void pm_debug_set_l2_dump(float *ddump);
+void pm_debug_set_k2_trace(long long *p);
 
 /* ---- diagnostics (main.cpp:103-123, 127-132) --------------------------------- */
 /* cv::computeCorrespondEpilines: l = F x (which_image 1) or F^T x (2), a^2+b^2 = 1. */

@@ -65,11 +65,14 @@ struct Descriptors {
     bool empty() const { return rows == 0; }
 };
 
-// 3x3 (or empty) double matrix returned by findFundamentalMat
+// The matrix findFundamentalMat returns: empty, 3x3, or -- for exactly seven points -- the 7-point solver's 1..3 real
+// roots stacked as a 3k x 3 matrix (cv::Mat 9x3 when k = 3).  Row-major doubles; operator()(r, c) indexes the stack.
 struct Matx33d {
-    double val[9]; bool is_empty;
-    Matx33d() : is_empty(true) { std::memset(val, 0, sizeof(val)); }
-    bool empty() const { return is_empty; }
+    double val[27]; int n_models;
+    Matx33d() : n_models(0) { std::memset(val, 0, sizeof(val)); }
+    bool empty() const { return n_models == 0; }
+    int rows() const { return 3 * n_models; }
+    int cols() const { return 3; }
     double operator()(int r, int c) const { return val[3 * r + c]; }
 };
 
@@ -241,17 +244,25 @@ inline void KeyPoint::convert(const std::vector<KeyPoint> &keypoints, std::vecto
 }
 
 // ---------------------------------------------------------------------------------------
-// cv::findFundamentalMat (main.cpp:95-98)
-//   N < 7 -> empty.  FM_8POINT: N-point normalised 8-point, mask all ones.  FM_7POINT / FM_LMEDS with
-//   N > 7: LMedS over 7-point samples (what OpenCV dispatches to; no refit).  FM_RANSAC:
-//   GPU RANSAC in batches of minimal samples with OpenCV's adaptive stop
-//   niters = log(1 - conf) / log(1 - w^m).  param1 <= 0 -> 3, param2 outside (0, 1) -> 0.99.
+// cv::findFundamentalMat (main.cpp:95-98) over pm_find_fundamental_mat, which carries OpenCV's dispatch table:
+//   N < 7 -> empty.  N == 7 (any method) -> the 7-point roots, stacked (1..3 models), mask of ones.  FM_8POINT ->
+//   N-point normalised 8-point, mask of ones.  FM_RANSAC with N >= 15 -> RANSAC with the adaptive stop
+//   niters = log(1 - conf) / log(1 - w^m), batches generated, solved and scored on the GPU.  Everything else
+//   (FM_7POINT with N > 7 = the reference's literal call, FM_LMEDS, FM_RANSAC with N < 15) -> LMedS over 7-point
+//   samples.  param1 <= 0 -> 3, param2 outside (0, 1) -> 0.99.
+// The default options are OpenCV's estimator (7-point samples, symmetric-epipolar error, no refit: the mask obeys
+// cv's rule err <= thr^2 exactly); FundamentalOptions::northStar() is BASELINE.json's variant.
 // ---------------------------------------------------------------------------------------
 struct FundamentalOptions {
-    int metric = PM_METRIC_SAMPSON;   // PM_METRIC_SYMEPI reproduces OpenCV's mask rule exactly
-    bool refit = true;                // 8-point refit on the winner's inliers (OpenCV does not refit)
+    int sampleSize = 7;               // RANSAC minimal sample: 7 (OpenCV) or 8
+    int metric = PM_METRIC_SYMEPI;    // OpenCV's computeError; PM_METRIC_SAMPSON for the north_star variant
+    bool refit = false;               // 8-point refit on the winner's inliers (OpenCV does not refit)
     int maxIters = 1000, batch = 1024;
     uint64_t seed = 0;
+    static FundamentalOptions northStar()
+    {
+        FundamentalOptions o; o.sampleSize = 8; o.metric = PM_METRIC_SAMPSON; o.refit = true; return o;
+    }
 };
 
 inline Matx33d findFundamentalMat(const std::vector<Point2f> &points1, const std::vector<Point2f> &points2,
@@ -261,67 +272,20 @@ inline Matx33d findFundamentalMat(const std::vector<Point2f> &points1, const std
 {
     Context &c = ctx ? *ctx : defaultContext();
     if (points1.size() != points2.size()) throw Exception(-215, "points1/points2 count mismatch");
+    if (method != FM_7POINT && method != FM_8POINT && method != FM_LMEDS && method != FM_RANSAC)
+        throw Exception(-215, "findFundamentalMat: unknown method");
     const int n = (int)points1.size();
     Matx33d F;
-    if (n < 7) return F;
-    if (param1 <= 0) param1 = 3.;
-    if (!(param2 > DBL_EPSILON && param2 < 1 - DBL_EPSILON)) param2 = 0.99;
-    const float *p1 = reinterpret_cast<const float *>(points1.data()), *p2 = reinterpret_cast<const float *>(points2.data());
-    if (method == FM_8POINT) {
-        if (n < 8) return F;
-        if (c.check(pm_fundamental_8point(c.handle(), p1, p2, n, F.val), true) == PM_OK) {
-            F.is_empty = false;
-            if (mask) mask->assign((size_t)n, 1);
-        }
-        return F;
-    }
-    if (method != FM_RANSAC && n > 7) {
-        // OpenCV routes FM_7POINT / FM_LMEDS with N > 7 to LMedS -- the reference's literal call at main.cpp:95-98
-        double num = 1. - param2 > DBL_MIN ? 1. - param2 : DBL_MIN;
-        int niters = (int)std::lround(std::log(num) / std::log(1. - std::pow(0.55, 7)));
-        niters = niters < 3 ? 3 : (niters > opt.maxIters ? opt.maxIters : niters);
-        std::vector<unsigned char> m((size_t)n);
-        int ninl = 0;
-        if (c.check(pm_find_fundamental_lmeds(c.handle(), p1, p2, n, niters, nullptr, opt.seed, F.val, m.data(), &ninl, nullptr),
-                    true) == PM_OK) {
-            F.is_empty = false;
-            if (mask) *mask = m;
-        }
-        return F;
-    }
-    const int m = (method == FM_RANSAC && n >= 8) ? 8 : 7;
-    pm_ransac_params prm;
-    std::memset(&prm, 0, sizeof(prm));
-    prm.sample_size = m; prm.metric = opt.metric; prm.threshold = (float)param1; prm.refit = 0;
-    std::vector<unsigned char> cur((size_t)n), best_mask;
-    int best = -1, done = 0, need = opt.maxIters, b = 0;
-    double Fc[9];
-    while (done < (need < opt.maxIters ? need : opt.maxIters)) {
-        prm.n_hyp = opt.batch < opt.maxIters - done ? opt.batch : opt.maxIters - done;
-        prm.seed = opt.seed + 0x9E3779B97F4A7C15ull * (uint64_t)b;
-        int ninl = 0;
-        const int st = c.check(pm_find_fundamental(c.handle(), p1, p2, n, &prm, Fc, cur.data(), &ninl), true);
-        done += prm.n_hyp; ++b;
-        if (st == PM_OK && ninl > best) {
-            best = ninl; best_mask = cur; std::memcpy(F.val, Fc, sizeof(Fc)); F.is_empty = false;
-            const double w = (double)best / n, denom = 1.0 - std::pow(w, m);
-            if (denom <= 0) need = 0;
-            else if (denom < 1) {
-                const double conf = 1 - param2 > 1e-300 ? 1 - param2 : 1e-300;
-                need = (int)std::ceil(std::log(conf) / std::log(denom));
-            }
-        }
-    }
-    if (F.empty()) return F;
-    if (opt.refit && best >= 8) {
-        std::vector<Point2f> a, bb;
-        for (int i = 0; i < n; ++i) if (best_mask[(size_t)i]) { a.push_back(points1[(size_t)i]); bb.push_back(points2[(size_t)i]); }
-        double Fr[9];
-        if (c.check(pm_fundamental_8point(c.handle(), reinterpret_cast<const float *>(a.data()),
-                                          reinterpret_cast<const float *>(bb.data()), (int)a.size(), Fr), true) == PM_OK)
-            std::memcpy(F.val, Fr, sizeof(Fr));
-    }
-    if (mask) *mask = best_mask;
+    pm_fm_options o;
+    o.sample_size = opt.sampleSize; o.metric = opt.metric; o.refit = opt.refit ? 1 : 0; o.batch = opt.batch; o.seed = opt.seed;
+    std::vector<unsigned char> m((size_t)(n > 0 ? n : 1));
+    int k = 0;
+    const int st = c.check(pm_find_fundamental_mat(c.handle(), reinterpret_cast<const float *>(points1.data()),
+                                                   reinterpret_cast<const float *>(points2.data()), n, method, param1, param2,
+                                                   opt.maxIters, &o, F.val, &k, m.data()), true);
+    if (st != PM_OK) return Matx33d();
+    F.n_models = k;
+    if (mask) { m.resize((size_t)n); *mask = m; }
     return F;
 }
 

@@ -20,10 +20,20 @@ PAIR_RESULT = np.dtype([("F", "<f8", (9,)), ("key", "<u8"), ("n_matches", "<i4")
 assert PAIR_RESULT.itemsize == 96
 
 
-class RansacParams(C.Structure):
+class RansacParams(C.Structure):       # pm_ransac_params, 56 bytes
     _fields_ = [("sample_size", C.c_int32), ("metric", C.c_int32), ("threshold", C.c_float),
                 ("n_hyp", C.c_int32), ("refit", C.c_int32), ("sample_idx", C.c_void_p),
-                ("seed", C.c_uint64), ("hyp_id_base", C.c_int32), ("reserved", C.c_int32)]
+                ("seed", C.c_uint64), ("hyp_id_base", C.c_int32), ("max_iters", C.c_int32),
+                ("confidence", C.c_double)]
+
+
+class FmOptions(C.Structure):          # pm_fm_options, 24 bytes
+    _fields_ = [("sample_size", C.c_int32), ("metric", C.c_int32), ("refit", C.c_int32), ("batch", C.c_int32),
+                ("seed", C.c_uint64)]
+
+
+assert C.sizeof(RansacParams) == 56 and C.sizeof(FmOptions) == 24
+COMM_ID_BYTES = 128
 
 
 # every symbol include/pm.h declares (tests/test_abi.py checks the header against this list)
@@ -41,6 +51,11 @@ EXPORTS = [
     "pm_ransac_solve_dev", "pm_ransac_score_dev", "pm_ransac_best_dev", "pm_ransac_finish_dev",
     "pm_match_estimate_pair_dev", "pm_match_estimate_batched_dev", "pm_set_batch_lanes", "pm_batch_warmup",
     "pm_fundamental_8point", "pm_epilines", "pm_residuals", "pm_find_fundamental_lmeds", "pm_lmeds_score_dev", "pm_make_sample_sets_dev",
+    "pm_match_estimate_batched", "pm_find_fundamental_adaptive", "pm_find_fundamental_mat", "pm_fundamental_7point",
+    "pm_comm_unique_id", "pm_comm_init", "pm_set_comm", "pm_comm_info", "pm_match_cross_sharded_dev",
+    "pm_allgather_matches_dev", "pm_find_fundamental_sharded_dev", "pm_measure_peak",
+    "pm_debug_set_span", "pm_debug_hamming_path", "pm_debug_force_exact", "pm_debug_fallback_separate",
+    "pm_debug_set_l2_dump", "pm_debug_set_k2_trace",
 ]
 
 

@@ -12,12 +12,11 @@ lists of DMatch objects.  OpenCV's exceptions map to PMError(PM_BAD_ARG); its "e
 results map to None.
 """
 import ctypes as C
-import math
 
 import numpy as np
 
 from . import _lib
-from ._lib import DMATCH, PAIR_RESULT, PM_EMPTY, PM_OK, RansacParams  # noqa: F401
+from ._lib import COMM_ID_BYTES, DMATCH, PAIR_RESULT, PM_EMPTY, PM_OK, FmOptions, RansacParams  # noqa: F401
 
 NORM_L2 = 4          # cv::NORM_L2
 NORM_HAMMING = 6     # cv::NORM_HAMMING
@@ -277,6 +276,105 @@ class Context:
         self._chk(self._L.pm_residuals(self._h, _p(p1), _p(p2), p1.shape[0], _p(F), metric, _p(out), C.byref(mean)))
         return out, mean.value
 
+    def find_fundamental_adaptive(self, p1, p2, sample_size=7, metric=METRIC_SYMEPI, threshold=3.0, confidence=0.99,
+                                  max_iters=1000, batch=1024, refit=False, seed=0):
+        """RANSAC with OpenCV's adaptive stop, batches generated / solved / scored on the device; only the 8-byte
+        winner key returns per batch.  Returns (F[3,3], mask, n_inliers, hypotheses_run) or None."""
+        p1 = np.ascontiguousarray(p1, dtype=np.float32).reshape(-1, 2)
+        p2 = np.ascontiguousarray(p2, dtype=np.float32).reshape(-1, 2)
+        if p1.shape != p2.shape:
+            raise PMError(_lib.PM_BAD_ARG, "points1/points2 size mismatch")
+        n = p1.shape[0]
+        prm = RansacParams()
+        prm.sample_size, prm.metric, prm.threshold, prm.n_hyp = sample_size, metric, threshold, batch
+        prm.refit, prm.seed, prm.max_iters, prm.confidence, prm.sample_idx = int(bool(refit)), seed, max_iters, confidence, None
+        F, mask = np.zeros(9, dtype=np.float64), np.zeros(n, dtype=np.uint8)
+        ninl, run = C.c_int(0), C.c_int(0)
+        st = self._chk(self._L.pm_find_fundamental_adaptive(self._h, _p(p1), _p(p2), n, C.byref(prm), _p(F), _p(mask),
+                                                            C.byref(ninl), C.byref(run)), allow_empty=True)
+        if st == PM_EMPTY:
+            return None
+        return F.reshape(3, 3), mask, ninl.value, run.value
+
+    def find_fundamental_mat(self, p1, p2, method, param1=3.0, param2=0.99, max_iters=1000, options=None):
+        """pm_find_fundamental_mat: cv::findFundamentalMat's dispatch table.  Returns (F[3k,3] f64, mask[n] u8) with
+        k = 1..3 stacked models (k > 1 only for n == 7), or (None, None) for OpenCV's empty Mat."""
+        p1 = np.ascontiguousarray(p1, dtype=np.float32).reshape(-1, 2)
+        p2 = np.ascontiguousarray(p2, dtype=np.float32).reshape(-1, 2)
+        if p1.shape != p2.shape:
+            raise PMError(_lib.PM_BAD_ARG, "(-215) points1/points2 count mismatch")
+        n = p1.shape[0]
+        F, mask, k = np.zeros(27, dtype=np.float64), np.zeros(max(n, 1), dtype=np.uint8), C.c_int(0)
+        st = self._chk(self._L.pm_find_fundamental_mat(self._h, _p(p1), _p(p2), n, int(method), C.c_double(param1),
+                                                       C.c_double(param2), int(max_iters),
+                                                       C.byref(options) if options is not None else None, _p(F), C.byref(k),
+                                                       _p(mask)), allow_empty=True)
+        if st == PM_EMPTY:
+            return None, None
+        return F[: 9 * k.value].reshape(3 * k.value, 3).copy(), mask[:n]
+
+    def fundamental_7point(self, p1, p2):
+        """run7Point on exactly seven correspondences: [k, 3, 3] f64 with k = 1..3 real roots, or None."""
+        p1 = np.ascontiguousarray(p1, dtype=np.float32).reshape(-1, 2)
+        p2 = np.ascontiguousarray(p2, dtype=np.float32).reshape(-1, 2)
+        F, k = np.zeros(27, dtype=np.float64), C.c_int(0)
+        st = self._chk(self._L.pm_fundamental_7point(self._h, _p(p1), _p(p2), p1.shape[0], _p(F), C.byref(k)), allow_empty=True)
+        return None if st == PM_EMPTY else F[: 9 * k.value].reshape(k.value, 3, 3).copy()
+
+    def measure_peak(self, which):
+        """Measured issue peak: which 0 -> FP32 FFMA TFLOP/s, 1 -> 1e12 POPC.32 per second."""
+        v = C.c_double(0)
+        self._chk(self._L.pm_measure_peak(self._h, int(which), C.byref(v)))
+        return v.value
+
+    # ---- multi-GPU (NCCL inside the C ABI) ---------------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_uint8 * COMM_ID_BYTES)()
+        st = _lib.lib().pm_comm_unique_id(buf)
+        if st != PM_OK:
+            raise PMError(st, "pm_comm_unique_id: libnccl.so.2 not loadable")
+        return bytes(buf)
+
+    def comm_init(self, n_ranks, rank, unique_id):
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        self._chk(self._L.pm_comm_init(self._h, n_ranks, rank, buf))
+
+    def comm_init_from_torch(self, group=None):
+        """Creates this ctx's own NCCL communicator over the ranks of a torch.distributed group (the unique id travels
+        through the group); a no-op for a single process."""
+        import torch
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        ids = [self.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self.comm_init(world, rank, ids[0])
+
+    def comm_info(self):
+        n, r = C.c_int(1), C.c_int(0)
+        self._chk(self._L.pm_comm_info(self._h, C.byref(n), C.byref(r)))
+        return n.value, r.value
+
+    def match_cross_sharded_dev(self, dq, nq, dt, nt, width, norm, q_index_base, dknn, dcol, dout, dn_out):
+        self._chk(self._L.pm_match_cross_sharded_dev(self._h, C.c_void_p(dq), nq, C.c_void_p(dt), nt, width, int(norm),
+                                                     q_index_base, C.c_void_p(dknn), C.c_void_p(dcol), C.c_void_p(dout),
+                                                     C.c_void_p(dn_out)))
+
+    def allgather_matches_dev(self, dlocal, dn_local, max_per_rank, dall, dcounts):
+        self._chk(self._L.pm_allgather_matches_dev(self._h, C.c_void_p(dlocal), C.c_void_p(dn_local), max_per_rank,
+                                                   C.c_void_p(dall), C.c_void_p(dcounts)))
+
+    def find_fundamental_sharded_dev(self, dp1, dp2, n, dsamples_full, n_hyp_total, hyp_lo, n_hyp, sample_size, metric,
+                                     threshold, refit, dF, dmask, dn_inl, dkey, seed=0):
+        prm = RansacParams()
+        prm.sample_size, prm.metric, prm.threshold = sample_size, metric, threshold
+        prm.n_hyp, prm.refit, prm.sample_idx, prm.hyp_id_base, prm.seed = n_hyp, int(bool(refit)), dsamples_full or None, hyp_lo, seed
+        self._chk(self._L.pm_find_fundamental_sharded_dev(self._h, C.c_void_p(dp1), C.c_void_p(dp2), n, C.byref(prm),
+                                                          n_hyp_total, C.c_void_p(dF), C.c_void_p(dmask), C.c_void_p(dn_inl),
+                                                          C.c_void_p(dkey)))
+
     # ---- device-resident calls (raw device pointers, e.g. torch_tensor.data_ptr()) ------
     def knn2_l2_f32_dev(self, dq, nq, dt, nt, dim, dout, q_index_base=0):
         self._chk(self._L.pm_knn2_l2_f32_dev(self._h, C.c_void_p(dq), nq, C.c_void_p(dt), nt, dim, q_index_base,
@@ -359,6 +457,18 @@ class Context:
         prm = self._pair_params(n_hyp, sample_size, metric, threshold, refit, seed)
         self._chk(self._L.pm_match_estimate_batched_dev(self._h, k, vp(*ddesc1), i32(*n1), vp(*ddesc2), i32(*n2), dim, int(is_u8),
                                                         vp(*dkp1), vp(*dkp2), C.c_float(ratio), C.byref(prm), C.c_void_p(dresults)))
+
+    def match_estimate_batched(self, desc1, n1, desc2, n2, dim, is_u8, kp1, kp2, ratio, n_hyp, sample_size=8, metric=0,
+                               threshold=1.0, refit=True, seed=0):
+        """pm_match_estimate_batched: sequences of HOST pointers (pinned buffers) / counts, one entry per pair; synchronous.
+        Returns a PAIR_RESULT structured array [n_pairs]."""
+        k = len(desc1)
+        vp, i32 = C.c_void_p * max(k, 1), C.c_int32 * max(k, 1)
+        prm = self._pair_params(n_hyp, sample_size, metric, threshold, refit, seed)
+        out = np.zeros(max(k, 1), dtype=PAIR_RESULT)
+        self._chk(self._L.pm_match_estimate_batched(self._h, k, vp(*desc1), i32(*n1), vp(*desc2), i32(*n2), dim, int(is_u8),
+                                                    vp(*kp1), vp(*kp2), C.c_float(ratio), C.byref(prm), _p(out)))
+        return out[:k]
 
     def set_batch_lanes(self, lanes):
         self._chk(self._L.pm_set_batch_lanes(self._h, lanes))
@@ -470,64 +580,24 @@ def keypoints_convert(keypoints_xy, indices, ctx=None):
 
 
 def findFundamentalMat(points1, points2, method=FM_RANSAC, ransacReprojThreshold=3.0, confidence=0.99,
-                       maxIters=1000, *, metric=METRIC_SAMPSON, refit=True, batch=1024, seed=0, ctx=None):
-    """cv::findFundamentalMat look-alike (main.cpp:95-98).  Returns (F, mask) or (None, None).
+                       maxIters=1000, *, sample_size=7, metric=METRIC_SYMEPI, refit=False, batch=1024, seed=0, ctx=None):
+    """cv::findFundamentalMat look-alike (main.cpp:95-98) over pm_find_fundamental_mat.  Returns (F, mask) or
+    (None, None); the dispatch is OpenCV's:
 
-    method FM_8POINT: N-point normalised 8-point, mask of ones.  FM_RANSAC: GPU RANSAC in batches
-    of `batch` minimal samples with OpenCV's adaptive stop  niters = log(1-conf)/log(1-w^m).
-    FM_7POINT / FM_LMEDS with N > 7: LMedS over 7-point samples, exactly the estimator OpenCV
-    dispatches to, no refit.  N < 7 -> (None, None) like OpenCV's empty Mat.
+      N < 7 -> (None, None).  N == 7 (any method) -> the 7-point solver's 1..3 real roots stacked as a [3k, 3] array,
+      mask of ones.  FM_8POINT -> N-point normalised 8-point, mask of ones.  FM_RANSAC with N >= 15 -> RANSAC with the
+      adaptive stop niters = log(1 - confidence) / log(1 - w^m), run in batches of `batch` hypotheses on the GPU.
+      Everything else (FM_7POINT with N > 7 -- the reference's literal call --, FM_LMEDS, FM_RANSAC with N < 15) -> LMedS
+      over 7-point samples.  ransacReprojThreshold <= 0 -> 3, confidence outside (0, 1) -> 0.99.
+
+    The keyword defaults are OpenCV's estimator (7-point samples, symmetric-epipolar error, no refit: the mask equals
+    cv2's rule err <= thr^2 exactly).  BASELINE.json's north_star variant is sample_size=8, metric=METRIC_SAMPSON,
+    refit=True.
     """
     ctx = ctx or default_context()
-    p1 = np.ascontiguousarray(points1, dtype=np.float32).reshape(-1, 2)
-    p2 = np.ascontiguousarray(points2, dtype=np.float32).reshape(-1, 2)
-    if p1.shape != p2.shape:
-        raise PMError(_lib.PM_BAD_ARG, "(-215) points1/points2 count mismatch")
-    n = p1.shape[0]
-    if n < 7:
-        return None, None
-    if ransacReprojThreshold <= 0:
-        ransacReprojThreshold = 3.0
-    if not (np.finfo(np.float64).eps < confidence < 1 - np.finfo(np.float64).eps):
-        confidence = 0.99
-    if method == FM_8POINT:
-        if n < 8:
-            return None, None
-        F = ctx.fundamental_8point(p1, p2)
-        return (F, np.ones(n, np.uint8)) if F is not None else (None, None)
-    if method != FM_RANSAC and n > 7:
-        # OpenCV routes FM_7POINT / FM_LMEDS with N > 7 to LMedS (the reference's literal call, main.cpp:95-98):
-        # niters = log(1 - conf) / log(1 - (1 - 0.45)^7), at least 3, at most maxIters
-        num = max(1.0 - confidence, np.finfo(np.float64).tiny)
-        niters = int(round(math.log(num) / math.log(1.0 - 0.55 ** 7)))
-        niters = max(3, min(niters, maxIters))
-        r = ctx.find_fundamental_lmeds(p1, p2, n_hyp=niters, seed=seed)
-        return (r[0], r[1]) if r is not None else (None, None)
-    m = 8 if (method == FM_RANSAC and n >= 8) else 7
-    best, done, need, b = None, 0, maxIters, 0
-    while done < min(need, maxIters):
-        nh = min(batch, maxIters - done)
-        r = ctx.find_fundamental(p1, p2, sample_size=m, metric=metric, threshold=ransacReprojThreshold,
-                                 n_hyp=nh, refit=False, seed=seed + 0x9E3779B97F4A7C15 * b & (2**64 - 1))
-        done += nh
-        b += 1
-        if r is not None and (best is None or r[2] > best[2]):
-            best = r
-            w = best[2] / n
-            denom = 1.0 - w ** m
-            if denom <= 0:
-                need = 0
-            elif denom < 1:
-                need = int(math.ceil(math.log(max(1 - confidence, 1e-300)) / math.log(denom)))
-    if best is None:
-        return None, None
-    F, mask, ninl = best
-    if refit and ninl >= 8:
-        sel = mask.astype(bool)
-        Fr = ctx.fundamental_8point(p1[sel], p2[sel])
-        if Fr is not None:
-            F = Fr
-    return F, mask
+    opt = FmOptions()
+    opt.sample_size, opt.metric, opt.refit, opt.batch, opt.seed = sample_size, metric, int(bool(refit)), batch, seed
+    return ctx.find_fundamental_mat(points1, points2, method, ransacReprojThreshold, confidence, maxIters, opt)
 
 
 def computeCorrespondEpilines(points, whichImage, F, ctx=None):

@@ -14,6 +14,7 @@
 #include <cuda_bf16.h>
 #include "pm_internal.h"
 #include "l2_common.h"
+#include "l2_fallback.cuh"
 
 namespace {
 
@@ -306,15 +307,22 @@ __device__ __forceinline__ float group_l2sq(unsigned gmask, const float (&a)[4][
     return r;
 }
 
-constexpr int FB_CHUNK = 256;    // train rows per fallback work item
-constexpr int FB_ROWS = 1024;    // flagged rows per fallback batch (bounds the scratch: FB_ROWS x chunks x 16 B)
+// Exact FP32 scan of the rows K3 flagged (split mode; exits at once when there are none).  Barrier-free, see
+// l2_fallback.cuh.
+template <typename T>
+__global__ void __launch_bounds__(256)
+l2_fallback_kernel(L2FallbackArgs A)
+{
+    pm_pdl_prologue();
+    l2_fallback_items<T>(A, (int)blockIdx.x, (int)gridDim.x);
+}
 
 template <typename T>
 __global__ void __launch_bounds__(256, 3)
 l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__restrict__ qnorm,
                  const uint8_t *__restrict__ q8, const uint8_t *__restrict__ t8, const float *__restrict__ tnorm,
                  const T *__restrict__ q, const T *__restrict__ t, int nq, int nt, int dim, int vec,
-                 L2Flags *flags, L2Flags *flags_next, int *__restrict__ flagged, unsigned long long *fb_part,
+                 L2Flags *flags, L2Flags *flags_next, int *__restrict__ flagged,
                  int q_index_base, pm_dmatch *__restrict__ out, unsigned long long *span)
 {
     pm_span_mark(span, 6, false);
@@ -433,96 +441,10 @@ l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__rest
             if (sub == 0 && !certified) flagged[atomicAdd(&flags->n_flagged, 1)] = i;
         }
     }
-    // Split mode only: rows K3 could not certify get an exact FP32 scan of the whole train set, spread over
-    // the grid as (flagged row, 256-train-row chunk) work items and merged per row afterwards.  Every block
-    // of K3 is resident (the host launches at most one wave), so an atomic-counter grid barrier is safe;
-    // exact mode never flags a row and skips all of this.
-    if (!l2_exact_mode(*flags)) {
-        __shared__ float x_qs[L2_KDIM];
-        __shared__ unsigned long long x_k[8][2];
-        unsigned epoch = 0;
-        auto grid_barrier = [&]() {
-            ++epoch;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                __threadfence();
-                atomicAdd(&flags->done_blocks, 1u);
-                while (*reinterpret_cast<volatile unsigned *>(&flags->done_blocks) < epoch * gridDim.x) { }
-                __threadfence();
-            }
-            __syncthreads();
-        };
-        grid_barrier();
-        const int nf = *reinterpret_cast<volatile int *>(&flags->n_flagged);
-        const int nchunk = (nt + FB_CHUNK - 1) / FB_CHUNK;
-        const int warp = threadIdx.x >> 5, g = lane >> 3;
-        for (int r0 = 0; r0 < nf; r0 += FB_ROWS) {                 // batches bound the scratch
-            const int nb = min(FB_ROWS, nf - r0);
-            for (int item = blockIdx.x; item < nb * nchunk; item += gridDim.x) {
-                const int r = item / nchunk, ch = item - r * nchunk;
-                const int i = *reinterpret_cast<volatile int *>(&flagged[r0 + r]);
-                __syncthreads();
-                if (threadIdx.x < L2_KDIM) x_qs[threadIdx.x] = threadIdx.x < dim ? load_elem(q, (size_t)i * dim + threadIdx.x) : 0.f;
-                __syncthreads();
-                float a[4][4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) a[e][c] = x_qs[4 * (sub + 8 * e) + c];
-                unsigned long long k0 = ~0ull, k1 = ~0ull;
-                const int j0 = ch * FB_CHUNK + warp * 32;
-#pragma unroll 2
-                for (int it = 0; it < 8; ++it) {                    // 4 train rows per warp and iteration
-                    const int j = j0 + it * 4 + g;
-                    float b[4][4];
-                    load_row8(t + (size_t)min(j, nt - 1) * dim, sub, dim, vec != 0, b);
-                    const float d = group_l2sq(gmask, a, b, sub, dim);
-                    const unsigned long long key = j < nt ? (((unsigned long long)__float_as_uint(d) << 32) | (unsigned)j) : ~0ull;
-                    k1 = min_u64(k1, max_u64(k0, key));
-                    k0 = min_u64(k0, key);
-                }
-                // merge the 4 groups of the warp (lanes of a group hold identical keys), then the 8 warps
-#pragma unroll
-                for (int o = 8; o <= 16; o <<= 1) {
-                    const unsigned long long y0 = __shfl_xor_sync(0xffffffffu, k0, o), y1 = __shfl_xor_sync(0xffffffffu, k1, o);
-                    const unsigned long long lo = min_u64(k0, y0), hi = max_u64(k0, y0);
-                    k1 = min_u64(min_u64(k1, y1), hi); k0 = lo;
-                }
-                if (lane == 0) { x_k[warp][0] = k0; x_k[warp][1] = k1; }
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    unsigned long long m0 = ~0ull, m1 = ~0ull;
-                    for (int w = 0; w < 8; ++w)
-                        for (int e = 0; e < 2; ++e) { const unsigned long long key = x_k[w][e]; m1 = min_u64(m1, max_u64(m0, key)); m0 = min_u64(m0, key); }
-                    fb_part[((size_t)r * nchunk + ch) * 2] = m0;
-                    fb_part[((size_t)r * nchunk + ch) * 2 + 1] = m1;
-                }
-            }
-            grid_barrier();
-            for (int r = blockIdx.x * 8 + warp; r < nb; r += gridDim.x * 8) {   // one warp merges a row's chunks
-                const int i = *reinterpret_cast<volatile int *>(&flagged[r0 + r]);
-                unsigned long long m0 = ~0ull, m1 = ~0ull;
-                for (int c = lane; c < 2 * nchunk; c += 32) {
-                    const unsigned long long key = *reinterpret_cast<volatile unsigned long long *>(&fb_part[(size_t)r * nchunk * 2 + c]);
-                    m1 = min_u64(m1, max_u64(m0, key)); m0 = min_u64(m0, key);
-                }
-#pragma unroll
-                for (int o = 1; o <= 16; o <<= 1) {
-                    const unsigned long long y0 = __shfl_xor_sync(0xffffffffu, m0, o), y1 = __shfl_xor_sync(0xffffffffu, m1, o);
-                    const unsigned long long lo = min_u64(m0, y0), hi = max_u64(m0, y0);
-                    m1 = min_u64(min_u64(m1, y1), hi); m0 = lo;
-                }
-                if (lane < 2) {
-                    const unsigned long long w = lane == 0 ? m0 : m1;
-                    reinterpret_cast<uint4 *>(out + (size_t)i * 2)[lane] =
-                        w == ~0ull ? make_uint4((unsigned)(i + q_index_base), 0xFFFFFFFFu, 0u, __float_as_uint(3.402823466e+38f))
-                                   : make_uint4((unsigned)(i + q_index_base), (unsigned)(w & 0xFFFFFFFFull), 0u,
-                                                __float_as_uint(sqrtf(__uint_as_float((unsigned)(w >> 32)))));
-                }
-            }
-            if (r0 + FB_ROWS < nf) grid_barrier();                  // the scratch is reused by the next batch
-        }
-    }
+    // Split mode only: rows K3 could not certify (flagged[0 .. n_flagged)) get an exact FP32 scan of the whole train
+    // set from the NEXT kernel of the chain (l2_fallback.cuh): l2_fallback_kernel below, or the helper blocks of the
+    // ratio-filter kernel.  (An earlier version ran that scan here behind a hand-rolled grid barrier, which assumed
+    // that every block of this kernel is resident at once -- not guaranteed beside other streams.)
     if (span && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); span[33 + 2 * blockIdx.x] = tt; }
     pm_span_mark(span, 8, true);
 }
@@ -578,6 +500,9 @@ float *pm_l2_dump_ptr() { return g_l2_dump; }
 // Force the exact FP32 kernel for every row (parity cross-check of the two paths).
 static int g_l2_force_exact = 0;
 extern "C" void pm_debug_force_exact(int on) { g_l2_force_exact = on; }
+// A/B switch: run the fallback scan as a kernel of its own in the one-call chain as well (instead of helper blocks)
+static int g_l2_fb_separate = 0;
+extern "C" void pm_debug_fallback_separate(int on) { g_l2_fb_separate = on; }
 
 int l2_flags_acquire(pm_ctx *ctx, L2Flags **cur, L2Flags **zero_next, L2Flags **tflags, bool advance)
 {
@@ -678,8 +603,15 @@ static int l2_chain(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt,
     L2_WS2(q8, uint8_t *, WS_Q_U8, (size_t)mq_pad * L2_KDIM);
     L2_WS2(part, L2Cand *, WS_L2_PART, (size_t)mq_pad * smax * 3 * sizeof(L2Cand));
     L2_WS2(flagged, int *, WS_L2_FLAGGED, (size_t)nq * 4);
-    L2_WS2(fbpart, unsigned long long *, WS_L2_FBPART, (size_t)FB_ROWS * pm_cdiv(nt, FB_CHUNK) * 16);
+    // fallback scratch: < 2 * L2FB_MAX_GRID items of two keys, then the per-row countdowns (zero between calls)
+    const bool fb_fresh = ctx->slot_bytes[WS_L2_FBPART] < (size_t)nset * L2FB_SCRATCH_BYTES;
+    L2_WS2(fbpart, unsigned long long *, WS_L2_FBPART, (size_t)L2FB_SCRATCH_BYTES);
+    if (fb_fresh) PM_CUDA(ctx, cudaMemsetAsync(ctx->slot_ptr[WS_L2_FBPART], 0, ctx->slot_bytes[WS_L2_FBPART], ctx->stream));
 #undef L2_WS2
+    L2FallbackArgs fb;
+    fb.q = dq; fb.t = dt; fb.is_u8 = is_u8; fb.nq = nq; fb.nt = nt; fb.dim = dim; fb.vec = vec; fb.q_index_base = q_index_base;
+    fb.flags = flags; fb.flagged = flagged; fb.fb_part = fbpart;
+    fb.fb_cnt = reinterpret_cast<unsigned *>(fbpart + 4 * L2FB_MAX_GRID); fb.out = dout; fb.helpers = 0;
     // K3: 8 lanes per row, 32 rows per block, at most one resident wave (a second wave would double its latency)
     const int fin_blocks = min(pm_cdiv(nq, 32), 3 * ctx->num_sms);
     const int pack_nt = phase == 2 ? 0 : nt, pack_nt_pad = phase == 2 ? 0 : nt_pad;
@@ -702,18 +634,30 @@ static int l2_chain(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt,
     if (is_u8)
         PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<uint8_t>, dim3(fin_blocks), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,
                                    (const float *)qnorm, (const uint8_t *)q8, (const uint8_t *)t8, (const float *)tnormf,
-                                   (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, vec_u8, flags, flags_next, flagged, fbpart,
+                                   (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, vec_u8, flags, flags_next, flagged,
                                    q_index_base, dout, g_pm_span));
     else
         PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<float>, dim3(fin_blocks), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,
                                    (const float *)qnorm, (const uint8_t *)q8, (const uint8_t *)t8, (const float *)tnormf,
-                                   (const float *)dq, (const float *)dt, nq, nt, dim, vec_f32, flags, flags_next, flagged, fbpart,
+                                   (const float *)dq, (const float *)dt, nq, nt, dim, vec_f32, flags, flags_next, flagged,
                                    q_index_base, dout, g_pm_span));
     PM_CHECK_LAUNCH(ctx);
     ctx->l2_stats[3] = smax;
-    if (!dgood) return PM_OK;
-    if (!signalling) return pmk_ratio_filter(ctx, dout, nq, ratio, dgood, dn_good, gather);
-    st = pmk_ratio_filter_tail(ctx, dout, nq, ratio, dgood, dn_good, chain_done, chain_ctr, seq, gather);
+    if (!dgood || g_l2_fb_separate) {
+        // kNN-only chain: the exact scan of the flagged rows is a kernel of its own (returns at once in exact mode)
+        const int fb_blocks = min(2 * ctx->num_sms, L2FB_MAX_GRID);
+        if (is_u8) PM_CUDA(ctx, pm_launch_pdl(l2_fallback_kernel<uint8_t>, dim3(fb_blocks), dim3(256), 0, ctx->stream, fb));
+        else PM_CUDA(ctx, pm_launch_pdl(l2_fallback_kernel<float>, dim3(fb_blocks), dim3(256), 0, ctx->stream, fb));
+        PM_CHECK_LAUNCH(ctx);
+        if (!dgood) return PM_OK;
+    } else {
+        // one-call kNN-2 + ratio chain: helper blocks of the filter kernel run the scan, its tiles wait for them
+        fb.helpers = max(ctx->num_sms - pm_cdiv(nq, 1024), ctx->num_sms / 4);
+        if (fb.helpers > L2FB_MAX_GRID) fb.helpers = L2FB_MAX_GRID;
+    }
+    const L2FallbackArgs *fbp = fb.helpers ? &fb : nullptr;
+    if (!signalling) return pmk_ratio_filter(ctx, dout, nq, ratio, dgood, dn_good, gather, fbp);
+    st = pmk_ratio_filter_tail(ctx, dout, nq, ratio, dgood, dn_good, chain_done, chain_ctr, seq, gather, fbp);
     if (st != PM_OK) return st;
     ctx->chain_seq = seq;
     ctx->tail_is_chain = true;              // cleared by the next launch of any other kind (PM_CHECK_LAUNCH)

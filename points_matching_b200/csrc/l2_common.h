@@ -27,7 +27,7 @@ struct L2Flags {
     unsigned max_tnorm_bits;   // max ||b||^2 over real train rows (float bits)
     unsigned max_qnorm_bits;   // max ||a||^2 over real query rows (float bits)
     int n_flagged;             // rows K3 could not certify -> exact fallback
-    unsigned done_blocks;      // K3's in-kernel grid barrier (split mode): blocks that finished their rows
+    unsigned rows_fixed;       // flagged rows the fallback scan has rewritten (l2_fallback.cuh)
     int pad[3];
 };
 

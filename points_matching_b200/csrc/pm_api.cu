@@ -7,9 +7,28 @@
 #include <vector>
 #include <thread>
 #include <vector>
+#include <cfloat>
+#include <cmath>
+#include <nvtx3/nvToolsExt.h>
 #include "pm_internal.h"
 
-int pmk_ransac_pick(pm_ctx *ctx, const uint64_t *dkey, const float *dF32, int id_base, int n_models, float *dFw);
+// NVTX range per entry point (domain "libpm"): header-only nvtx3, a no-op unless a profiler injects itself.
+static nvtxDomainHandle_t pm_nvtx_domain()
+{
+    static nvtxDomainHandle_t d = nvtxDomainCreateA("libpm");
+    return d;
+}
+struct pm_nvtx_scope {
+    explicit pm_nvtx_scope(const char *name)
+    {
+        nvtxEventAttributes_t a = {};
+        a.version = NVTX_VERSION; a.size = NVTX_EVENT_ATTRIB_STRUCT_SIZE;
+        a.messageType = NVTX_MESSAGE_TYPE_ASCII; a.message.ascii = name;
+        nvtxDomainRangePushEx(pm_nvtx_domain(), &a);
+    }
+    ~pm_nvtx_scope() { nvtxDomainRangePop(pm_nvtx_domain()); }
+};
+#define PM_NVTX() pm_nvtx_scope nvtx_scope__(__func__)
 
 unsigned long long *g_pm_span = nullptr;
 extern "C" void pm_debug_set_span(unsigned long long *p) { g_pm_span = p; }
@@ -75,6 +94,7 @@ int pm_destroy(pm_ctx *ctx)
     if (!ctx) return PM_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    pm_comm_release(ctx);
     for (int s = 0; s < PM_NSLOTS; ++s) if (ctx->slot_ptr[s]) cudaFree(ctx->slot_ptr[s]);
     if (ctx->prof_alloc)
         for (int w = 0; w < 3; ++w)
@@ -99,6 +119,7 @@ int pm_destroy(pm_ctx *ctx)
 int pm_set_batch_lanes(pm_ctx *ctx, int lanes)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     if (lanes < 1 || lanes > PM_MAX_LANES) return pm_fail(ctx, PM_BAD_ARG, "pm_set_batch_lanes: 1..%d lanes", PM_MAX_LANES);
     ctx->batch_lanes = lanes;
     return PM_OK;
@@ -107,6 +128,7 @@ int pm_set_batch_lanes(pm_ctx *ctx, int lanes)
 int pm_set_stream(pm_ctx *ctx, void *s)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     cudaStream_t ns = s ? (cudaStream_t)s : ctx->own_stream;
     if (ns != ctx->stream) {
         // the workspaces are shared by everything this ctx enqueues: work still running on the old stream must not
@@ -121,6 +143,7 @@ int pm_set_stream(pm_ctx *ctx, void *s)
 int pm_set_pipelining(pm_ctx *ctx, int on)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     if ((on != 0) != (ctx->pipelining != 0)) {
         // the workspace layout changes (one buffer set <-> two): drain the stream first
         PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -134,6 +157,7 @@ int pm_set_pipelining(pm_ctx *ctx, int on)
 int pm_sync(pm_ctx *ctx)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PM_OK;
 }
@@ -141,6 +165,7 @@ int pm_sync(pm_ctx *ctx)
 int pm_profile_enable(pm_ctx *ctx, int on)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     if (on && !ctx->prof_alloc) {
         for (int w = 0; w < 3; ++w)
             for (int i = 0; i < PM_PROF_RING; ++i)
@@ -180,6 +205,7 @@ uint64_t pm_launch_count(pm_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int pm_knn2_l2_f32_dev(pm_ctx *ctx, const float *dq, int nq, const float *dt, int nt, int dim, int base, pm_dmatch *dout)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && dim > 0, "negative size or dim <= 0");
     PM_REQUIRE(ctx, nq == 0 || (dq && dout), "null pointer");
     return pmk_l2_knn2(ctx, dq, nq, dt, nt, dim, 0, base, dout);
@@ -187,6 +213,7 @@ int pm_knn2_l2_f32_dev(pm_ctx *ctx, const float *dq, int nq, const float *dt, in
 int pm_knn2_l2_u8_dev(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, int dim, int base, pm_dmatch *dout)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && dim > 0, "negative size or dim <= 0");
     PM_REQUIRE(ctx, nq == 0 || (dq && dout), "null pointer");
     return pmk_l2_knn2(ctx, dq, nq, dt, nt, dim, 1, base, dout);
@@ -195,6 +222,7 @@ int pm_knn2_ratio_l2_f32_dev(pm_ctx *ctx, const float *dq, int nq, const float *
                              pm_dmatch *dknn, pm_dmatch *dgood, int32_t *dn_good)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && dim > 0 && dn_good, "negative size, dim <= 0 or null count");
     PM_REQUIRE(ctx, nq == 0 || (dq && dknn && dgood), "null pointer");
     return pmk_l2_knn2_fused(ctx, dq, nq, dt, nt, dim, 0, base, dknn, 0, ratio, dgood, dn_good);
@@ -203,6 +231,7 @@ int pm_knn2_ratio_l2_u8_dev(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_
                             pm_dmatch *dknn, pm_dmatch *dgood, int32_t *dn_good)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && dim > 0 && dn_good, "negative size, dim <= 0 or null count");
     PM_REQUIRE(ctx, nq == 0 || (dq && dknn && dgood), "null pointer");
     return pmk_l2_knn2_fused(ctx, dq, nq, dt, nt, dim, 1, base, dknn, 0, ratio, dgood, dn_good);
@@ -210,6 +239,7 @@ int pm_knn2_ratio_l2_u8_dev(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_
 int pm_knn2_hamming_dev(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, int bytes, int base, pm_dmatch *dout)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && bytes > 0, "negative size or bytes <= 0");
     PM_REQUIRE(ctx, nq == 0 || (dq && dout), "null pointer");
     return pmk_hamming_knn2(ctx, dq, nq, dt, nt, bytes, base, dout);
@@ -217,18 +247,21 @@ int pm_knn2_hamming_dev(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *d
 int pm_ratio_filter_dev(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout, int32_t *dn)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, nq >= 0 && dn, "bad argument");
     return pmk_ratio_filter(ctx, dknn, nq, ratio, dout, dn);
 }
 int pm_minmax_filter_dev(pm_ctx *ctx, const pm_dmatch *dm, int n, int stride, pm_dmatch *dout, int32_t *dn, double *dminmax)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, n >= 0 && (stride == 1 || stride == 2) && dn, "bad argument");
     return pmk_minmax_filter(ctx, dm, n, stride, dout, dn, dminmax);
 }
 int pm_col_best_hamming_dev(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, int bytes, int base, uint64_t *dcol)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && bytes > 0, "bad argument");
     if (nq == 0 && nt > 0) { PM_CUDA(ctx, cudaMemsetAsync(dcol, 0xFF, (size_t)nt * 8, ctx->stream)); return PM_OK; }
     return pmk_hamming_col_best(ctx, dq, nq, dt, nt, bytes, base, dcol);
@@ -236,12 +269,14 @@ int pm_col_best_hamming_dev(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_
 int pm_col_best_l2_f32_dev(pm_ctx *ctx, const float *dq, int nq, const float *dt, int nt, int dim, int base, uint64_t *dcol)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && dim > 0, "bad argument");
     return pmk_l2_col_best(ctx, dq, nq, dt, nt, dim, base, dcol);
 }
 int pm_cross_check_dev(pm_ctx *ctx, const pm_dmatch *dknn, int nq, int stride, const uint64_t *dcol, int nt, pm_dmatch *dout, int32_t *dn)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, nq >= 0 && (stride == 1 || stride == 2) && dn, "bad argument");
     return pmk_cross_check(ctx, dknn, nq, stride, dcol, nt, dout, dn);
 }
@@ -249,11 +284,13 @@ int pm_gather_matches_dev(pm_ctx *ctx, const pm_dmatch *dm, const int32_t *dn, i
                           const float *dkp2, int nkp2, float *dp1, float *dp2)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     return pmk_gather_matches(ctx, dm, dn, max_matches, dkp1, nkp1, dkp2, nkp2, dp1, dp2);
 }
 int pm_ransac_solve_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const int32_t *ds, int n_hyp, int m, float *dF32)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, (m == 7 || m == 8) && n >= m && n_hyp >= 0, "sample_size must be 7 or 8 and n >= sample_size");
     return pmk_ransac_solve(ctx, dp1, dp2, n, ds, n_hyp, m, dF32);
 }
@@ -261,18 +298,21 @@ int pm_ransac_score_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n, 
                         int metric, int32_t *dcounts)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, n >= 0 && n_models >= 0 && (metric == PM_METRIC_SAMPSON || metric == PM_METRIC_SYMEPI), "bad argument");
     return pmk_ransac_score(ctx, dp1, dp2, n, dF32, n_models, thr, metric, dcounts);
 }
 int pm_ransac_best_dev(pm_ctx *ctx, const int32_t *dcounts, int n_models, int id_base, uint64_t *dkey)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     return pmk_ransac_best(ctx, dcounts, n_models, id_base, dkey);
 }
 int pm_ransac_finish_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dFw, float thr, int metric,
                          int refit, double *dF, uint8_t *dmask, int32_t *dn)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, n >= 0 && (metric == PM_METRIC_SAMPSON || metric == PM_METRIC_SYMEPI), "bad argument");
     return pmk_ransac_finish(ctx, dp1, dp2, n, dFw, thr, metric, refit, dF, dmask, dn);
 }
@@ -337,6 +377,7 @@ static int knn2_host(pm_ctx *ctx, const void *q, int nq, const void *t, int nt, 
 {
     // kind 0: l2 f32, 1: l2 u8, 2: hamming
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && width > 0, "negative size or zero width");
     if (nq == 0) return PM_OK;                       // empty query -> empty result
     PM_REQUIRE(ctx, q && out && (nt == 0 || t), "null pointer");
@@ -369,6 +410,7 @@ int pm_knn2_ratio_l2_f32(pm_ctx *ctx, const float *q, int nq, const float *t, in
                          pm_dmatch *knn_out, pm_dmatch *good_out, int *n_good)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && dim > 0 && n_good, "bad argument");
     *n_good = 0;
     if (nq == 0) return PM_OK;
@@ -404,6 +446,7 @@ static int read_count(pm_ctx *ctx, const int32_t *dn, int *n_out)
 int pm_ratio_filter(pm_ctx *ctx, const pm_dmatch *knn, int nq, float ratio, pm_dmatch *out, int *n_out)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, nq >= 0 && n_out, "bad argument");
     *n_out = 0;
     if (nq == 0) return PM_OK;
@@ -422,6 +465,7 @@ int pm_ratio_filter(pm_ctx *ctx, const pm_dmatch *knn, int nq, float ratio, pm_d
 int pm_minmax_filter(pm_ctx *ctx, const pm_dmatch *m, int n, int stride, pm_dmatch *out, int *n_out, double *mn, double *mx)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, n >= 0 && (stride == 1 || stride == 2) && n_out, "bad argument");
     *n_out = 0;
     PM_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -446,6 +490,7 @@ static int match_cross_host(pm_ctx *ctx, const void *q, int nq, const void *t, i
                             pm_dmatch *out, int *n_out)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, nq >= 0 && nt >= 0 && width > 0 && n_out, "bad argument");
     *n_out = 0;
     if (nq == 0 || nt == 0) return PM_OK;
@@ -481,6 +526,7 @@ int pm_match_cross_hamming(pm_ctx *ctx, const uint8_t *q, int nq, const uint8_t 
 int pm_gather_points(pm_ctx *ctx, const float *kp, int nkp, const int32_t *idx, int n, float *out)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, nkp >= 0 && n >= 0, "bad argument");
     if (n == 0) return PM_OK;
     PM_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -526,6 +572,7 @@ int pm_make_sample_sets(int n_points, int n_hyp, int m, uint64_t seed, int32_t *
 int pm_make_sample_sets_dev(pm_ctx *ctx, int n_points, int n_hyp, int m, uint64_t seed, int32_t *dout)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, n_points >= m && m > 0 && m <= 8 && n_hyp >= 0 && dout, "need n_points >= m, 0 < m <= 8");
     return pmk_sample_sets(ctx, n_points, n_hyp, m, seed, dout);
 }
@@ -534,6 +581,7 @@ int pm_find_fundamental(pm_ctx *ctx, const float *p1, const float *p2, int n, co
                         double F[9], uint8_t *mask, int *n_inliers)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, prm && p1 && p2 && F, "null pointer");
     const int m = prm->sample_size;
     PM_REQUIRE(ctx, m == 7 || m == 8, "sample_size must be 7 or 8");
@@ -574,10 +622,163 @@ int pm_find_fundamental(pm_ctx *ctx, const float *p1, const float *p2, int n, co
     return PM_OK;
 }
 
+// cv::RANSACUpdateNumIters (OpenCV ptsetreg.cpp), restated: iterations needed so that with probability p at least one
+// sample of `model_points` is outlier-free when the outlier ratio is ep
+static int cv_update_num_iters(double p, double ep, int model_points, int max_iters)
+{
+    p = p < 0 ? 0 : (p > 1 ? 1 : p);
+    ep = ep < 0 ? 0 : (ep > 1 ? 1 : ep);
+    double num = 1 - p > DBL_MIN ? 1 - p : DBL_MIN;
+    double denom = 1 - std::pow(1 - ep, model_points);
+    if (denom < DBL_MIN) return 0;
+    num = std::log(num); denom = std::log(denom);
+    return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : (int)std::lround(num / denom);
+}
+
+int pm_find_fundamental_adaptive(pm_ctx *ctx, const float *p1, const float *p2, int n, const pm_ransac_params *prm,
+                                 double F[9], uint8_t *mask, int *n_inliers, int *n_hyp_run)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
+    PM_REQUIRE(ctx, prm && p1 && p2 && F, "null pointer");
+    const int m = prm->sample_size;
+    PM_REQUIRE(ctx, m == 7 || m == 8, "sample_size must be 7 or 8");
+    PM_REQUIRE(ctx, prm->metric == PM_METRIC_SAMPSON || prm->metric == PM_METRIC_SYMEPI, "unknown metric");
+    PM_REQUIRE(ctx, n >= 0, "negative size");
+    if (n_inliers) *n_inliers = 0;
+    if (n_hyp_run) *n_hyp_run = 0;
+    if (n < m) return PM_EMPTY;
+    const int max_iters = prm->max_iters > 0 ? prm->max_iters : 1000;
+    const double conf = (prm->confidence > DBL_EPSILON && prm->confidence < 1 - DBL_EPSILON) ? prm->confidence : 0.99;
+    const int batch = prm->n_hyp > 0 ? (prm->n_hyp < max_iters ? prm->n_hyp : max_iters) : (max_iters < 1024 ? max_iters : 1024);
+    PM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int per = m == 8 ? 1 : 3;
+    PM_WS(ctx, dp1, float *, WS_P1, (size_t)n * 8);
+    PM_WS(ctx, dp2, float *, WS_P2, (size_t)n * 8);
+    PM_WS(ctx, ds, int32_t *, WS_SAMPLES, (size_t)batch * m * 4);
+    PM_WS(ctx, dF32, float *, WS_F32, ((size_t)batch * per + 2) * 12 * 4);
+    PM_WS(ctx, dcounts, int32_t *, WS_COUNTS, (size_t)batch * per * 4);
+    PM_WS(ctx, dkey, uint64_t *, WS_KEY, 64);
+    PM_WS(ctx, dmask, uint8_t *, WS_MASK, (size_t)n);
+    PM_WS(ctx, dFout, double *, WS_FOUT, 16 * 8);
+    float *dFw = dF32 + (size_t)batch * per * 12;           // running winner (12 floats)
+    uint64_t *dbest = dkey + 1;                             // running winner key
+    int32_t *dninl = reinterpret_cast<int32_t *>(dkey + 2);
+    H2D(ctx, dp1, p1, (size_t)n * 8);                       // the correspondences cross PCIe once
+    H2D(ctx, dp2, p2, (size_t)n * 8);
+    PM_CUDA(ctx, cudaMemsetAsync(dbest, 0, 8, ctx->stream));
+    int st, done = 0, need = max_iters;
+    uint64_t best = 0;
+    while (done < (need < max_iters ? need : max_iters)) {
+        const int nh = batch < max_iters - done ? batch : max_iters - done;
+        // batch b draws the sets of hypotheses [done, done + nh) of the stream pm_make_sample_sets(n, max_iters, m, seed) defines
+        if ((st = pmk_sample_sets(ctx, n, nh, m, prm->seed, ds, nullptr, done)) != PM_OK) return st;
+        if ((st = pmk_ransac_solve(ctx, dp1, dp2, n, ds, nh, m, dF32)) != PM_OK) return st;
+        if ((st = pmk_ransac_score(ctx, dp1, dp2, n, dF32, nh * per, prm->threshold, prm->metric, dcounts)) != PM_OK) return st;
+        if ((st = pmk_ransac_best(ctx, dcounts, nh * per, done * per, dkey)) != PM_OK) return st;
+        if ((st = pmk_ransac_update_best(ctx, dkey, dF32, done * per, nh * per, dbest, dFw)) != PM_OK) return st;
+        D2H(ctx, ctx->h_pinned, dbest, 8);                  // the only per-batch traffic: 8 bytes
+        PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        done += nh;
+        const uint64_t k = *reinterpret_cast<const uint64_t *>(ctx->h_pinned);
+        if (k > best) {
+            best = k;
+            const int good = (int)(k >> 32);
+            need = cv_update_num_iters(conf, (double)(n - good) / n, m, max_iters);
+        }
+    }
+    if (n_hyp_run) *n_hyp_run = done;
+    if (best == 0) return PM_EMPTY;
+    if ((st = pmk_ransac_finish(ctx, dp1, dp2, n, dFw, prm->threshold, prm->metric, prm->refit, dFout, dmask, dninl)) != PM_OK) return st;
+    D2H(ctx, ctx->h_pinned, dninl, 4);
+    D2H(ctx, ctx->h_pinned + 16, dFout, 72);
+    if (mask) D2H(ctx, mask, dmask, (size_t)n);
+    PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(F, ctx->h_pinned + 16, 72);
+    if (n_inliers) *n_inliers = ctx->h_pinned[0];
+    return PM_OK;
+}
+
+int pm_fundamental_7point(pm_ctx *ctx, const float *p1, const float *p2, int n, double F[27], int *n_models)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
+    PM_REQUIRE(ctx, p1 && p2 && F && n_models, "null pointer");
+    *n_models = 0;
+    PM_REQUIRE(ctx, n == 7, "the 7-point solver takes exactly seven correspondences");
+    PM_CUDA(ctx, cudaSetDevice(ctx->device));
+    PM_WS(ctx, dp1, float *, WS_P1, 7 * 8);
+    PM_WS(ctx, dp2, float *, WS_P2, 7 * 8);
+    PM_WS(ctx, ds, int32_t *, WS_SAMPLES, 8 * 4);
+    PM_WS(ctx, dF32, float *, WS_F32, 4 * 12 * 4);
+    PM_WS(ctx, dF64, double *, WS_FOUT, 32 * 8);
+    for (int i = 0; i < 7; ++i) ctx->h_pinned[i] = i;
+    H2D(ctx, dp1, p1, 7 * 8);
+    H2D(ctx, dp2, p2, 7 * 8);
+    H2D(ctx, ds, ctx->h_pinned, 7 * 4);
+    int st = pmk_ransac_solve(ctx, dp1, dp2, 7, ds, 1, 7, dF32, nullptr, dF64);
+    if (st != PM_OK) return st;
+    double *h = reinterpret_cast<double *>(ctx->h_pinned + 16);
+    D2H(ctx, h, dF64, 27 * 8);
+    PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int k = 0;                                              // the solver stores NaN for absent / non-finite roots
+    for (int r = 0; r < 3; ++r)
+        if (h[9 * r] == h[9 * r]) { memcpy(F + 9 * k, h + 9 * r, 72); ++k; }
+    *n_models = k;
+    return k ? PM_OK : PM_EMPTY;
+}
+
+int pm_find_fundamental_mat(pm_ctx *ctx, const float *p1, const float *p2, int n, int method, double param1, double param2,
+                            int max_iters, const pm_fm_options *opt, double F[27], int *n_models, uint8_t *mask)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
+    PM_REQUIRE(ctx, p1 && p2 && F && n_models && n >= 0, "bad argument");
+    PM_REQUIRE(ctx, method == PM_FM_7POINT || method == PM_FM_8POINT || method == PM_FM_LMEDS || method == PM_FM_RANSAC,
+               "method must be FM_7POINT, FM_8POINT, FM_LMEDS or FM_RANSAC");
+    *n_models = 0;
+    if (n < 7) return PM_EMPTY;                             // cv: empty Mat
+    int st;
+    if (n == 7) {                                           // any method: run7Point on the seven points, every real root
+        if ((st = pm_fundamental_7point(ctx, p1, p2, 7, F, n_models)) != PM_OK) return st;
+        if (mask) memset(mask, 1, 7);
+        return PM_OK;
+    }
+    if (method == PM_FM_8POINT) {
+        if ((st = pm_fundamental_8point(ctx, p1, p2, n, F)) != PM_OK) return st;
+        *n_models = 1;
+        if (mask) memset(mask, 1, (size_t)n);
+        return PM_OK;
+    }
+    if (param1 <= 0) param1 = 3.;
+    if (!(param2 > DBL_EPSILON && param2 < 1 - DBL_EPSILON)) param2 = 0.99;
+    if (max_iters <= 0) max_iters = 1000;
+    const uint64_t seed = opt ? opt->seed : 0;
+    int ninl = 0;
+    if (method == PM_FM_RANSAC && n >= 15) {
+        pm_ransac_params prm;
+        memset(&prm, 0, sizeof(prm));
+        prm.sample_size = opt && opt->sample_size ? opt->sample_size : 7;
+        prm.metric = opt ? opt->metric : PM_METRIC_SYMEPI;
+        prm.threshold = (float)param1; prm.refit = opt ? opt->refit : 0;
+        prm.n_hyp = opt && opt->batch > 0 ? opt->batch : 1024;
+        prm.seed = seed; prm.max_iters = max_iters; prm.confidence = param2;
+        st = pm_find_fundamental_adaptive(ctx, p1, p2, n, &prm, F, mask, &ninl, nullptr);
+    } else {
+        // LMedS: niters = RANSACUpdateNumIters(confidence, outlier ratio 0.45, 7 points, max_iters), at least 3
+        int niters = cv_update_num_iters(param2, 0.45, 7, max_iters);
+        if (niters < 3) niters = 3;
+        st = pm_find_fundamental_lmeds(ctx, p1, p2, n, niters, nullptr, seed, F, mask, &ninl, nullptr);
+    }
+    if (st == PM_OK) *n_models = 1;
+    return st;
+}
+
 int pm_find_fundamental_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const pm_ransac_params *prm,
                             double *dF, uint8_t *dmask, int32_t *dn_inliers, uint64_t *dkey)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, prm && dp1 && dp2 && dF && dmask && dn_inliers && dkey && prm->sample_idx, "null pointer");
     const int m = prm->sample_size;
     PM_REQUIRE(ctx, m == 7 || m == 8, "sample_size must be 7 or 8");
@@ -643,6 +844,7 @@ int pm_match_estimate_pair_dev(pm_ctx *ctx, const void *dd1, int n1, const void 
                                pm_pair_result *dres)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     int st = pair_check(ctx, dim, prm);
     if (st != PM_OK) return st;
     PM_REQUIRE(ctx, n1 >= 0 && n2 >= 0 && dres, "negative size or null result");
@@ -650,11 +852,59 @@ int pm_match_estimate_pair_dev(pm_ctx *ctx, const void *dd1, int n1, const void 
     return pair_enqueue(ctx, dd1, n1, dd2, n2, dim, is_u8, dkp1, dkp2, ratio, prm, seed, dres);
 }
 
+// One pair whose descriptors / keypoints are HOST buffers: staged into this (lane) ctx's raw slots on its own stream, then
+// the device-resident chain.  The copies of one lane overlap the kernels of the others.
+static int pair_enqueue_host(pm_ctx *ctx, const void *h1, int n1, const void *h2, int n2, int dim, int is_u8, const float *hk1,
+                             const float *hk2, float ratio, const pm_ransac_params *prm, uint64_t seed, pm_pair_result *dres)
+{
+    const size_t elem = is_u8 ? 1 : 4, b1 = (size_t)n1 * dim * elem, b2 = (size_t)n2 * dim * elem;
+    PM_WS(ctx, d1, uint8_t *, WS_Q_RAW, b1);
+    PM_WS(ctx, d2, uint8_t *, WS_T_RAW, b2);
+    PM_WS(ctx, k1, float *, WS_KP, (size_t)(n1 > 0 ? n1 : 1) * 8);
+    PM_WS(ctx, k2, float *, WS_KP2, (size_t)(n2 > 0 ? n2 : 1) * 8);
+    if (n1) { H2D(ctx, d1, h1, b1); H2D(ctx, k1, hk1, (size_t)n1 * 8); }
+    if (n2) { H2D(ctx, d2, h2, b2); H2D(ctx, k2, hk2, (size_t)n2 * 8); }
+    return pair_enqueue(ctx, d1, n1, d2, n2, dim, is_u8, k1, k2, ratio, prm, seed, dres);
+}
+
+static int batched_impl(pm_ctx *ctx, int n_pairs, const void *const *dd1, const int32_t *n1, const void *const *dd2,
+                        const int32_t *n2, int dim, int is_u8, const float *const *dkp1, const float *const *dkp2,
+                        float ratio, const pm_ransac_params *prm, pm_pair_result *dres, bool host_inputs);
+
 int pm_match_estimate_batched_dev(pm_ctx *ctx, int n_pairs, const void *const *dd1, const int32_t *n1, const void *const *dd2,
                                   const int32_t *n2, int dim, int is_u8, const float *const *dkp1, const float *const *dkp2,
                                   float ratio, const pm_ransac_params *prm, pm_pair_result *dres)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
+    return batched_impl(ctx, n_pairs, dd1, n1, dd2, n2, dim, is_u8, dkp1, dkp2, ratio, prm, dres, false);
+}
+
+// The host-buffer form (BASELINE config 5 end to end): descriptors and keypoints of every pair in HOST memory (pinned for
+// full PCIe speed), results back in host memory; synchronous.  Every lane uploads its pairs on its own stream right before
+// their kernels, so the uploads of one lane run under the kernels of the others; the only device-to-host traffic is the
+// 96-byte record per pair, read once at the end.
+int pm_match_estimate_batched(pm_ctx *ctx, int n_pairs, const void *const *desc1, const int32_t *n1, const void *const *desc2,
+                              const int32_t *n2, int dim, int is_u8, const float *const *kp1, const float *const *kp2,
+                              float ratio, const pm_ransac_params *prm, pm_pair_result *results)
+{
+    if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
+    PM_REQUIRE(ctx, n_pairs >= 0 && (n_pairs == 0 || results), "bad argument");
+    if (n_pairs == 0) return PM_OK;
+    PM_CUDA(ctx, cudaSetDevice(ctx->device));
+    PM_WS(ctx, dres, pm_pair_result *, WS_PAIRRES, (size_t)n_pairs * sizeof(pm_pair_result));
+    int st = batched_impl(ctx, n_pairs, desc1, n1, desc2, n2, dim, is_u8, kp1, kp2, ratio, prm, dres, true);
+    if (st != PM_OK) return st;
+    D2H(ctx, results, dres, (size_t)n_pairs * sizeof(pm_pair_result));
+    PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PM_OK;
+}
+
+static int batched_impl(pm_ctx *ctx, int n_pairs, const void *const *dd1, const int32_t *n1, const void *const *dd2,
+                        const int32_t *n2, int dim, int is_u8, const float *const *dkp1, const float *const *dkp2,
+                        float ratio, const pm_ransac_params *prm, pm_pair_result *dres, bool host_inputs)
+{
     int st = pair_check(ctx, dim, prm);
     if (st != PM_OK) return st;
     PM_REQUIRE(ctx, n_pairs >= 0, "negative pair count");
@@ -665,9 +915,10 @@ int pm_match_estimate_batched_dev(pm_ctx *ctx, int n_pairs, const void *const *d
         PM_REQUIRE(ctx, (n1[p] == 0 || (dd1[p] && dkp1[p])) && (n2[p] == 0 || (dd2[p] && dkp2[p])), "null pointer");
     }
     const int L = n_pairs < ctx->batch_lanes ? n_pairs : ctx->batch_lanes;
+    auto enqueue = host_inputs ? pair_enqueue_host : pair_enqueue;
     if (L <= 1) {
         for (int p = 0; p < n_pairs; ++p) {
-            st = pair_enqueue(ctx, dd1[p], n1[p], dd2[p], n2[p], dim, is_u8, dkp1[p], dkp2[p], ratio, prm, prm->seed + (uint64_t)p, dres + p);
+            st = enqueue(ctx, dd1[p], n1[p], dd2[p], n2[p], dim, is_u8, dkp1[p], dkp2[p], ratio, prm, prm->seed + (uint64_t)p, dres + p);
             if (st != PM_OK) return st;
         }
         return PM_OK;
@@ -697,8 +948,8 @@ int pm_match_estimate_batched_dev(pm_ctx *ctx, int n_pairs, const void *const *d
     auto run_lane = [&](int k) {
         cudaSetDevice(ctx->device);
         for (int p = k; p < n_pairs && lane_st[k] == PM_OK; p += L)
-            lane_st[k] = pair_enqueue(ctx->lane[k], dd1[p], n1[p], dd2[p], n2[p], dim, is_u8, dkp1[p], dkp2[p], ratio, prm,
-                                      prm->seed + (uint64_t)p, dres + p);
+            lane_st[k] = enqueue(ctx->lane[k], dd1[p], n1[p], dd2[p], n2[p], dim, is_u8, dkp1[p], dkp2[p], ratio, prm,
+                                 prm->seed + (uint64_t)p, dres + p);
     };
     static const bool lane_threads = !(getenv("PM_BATCH_THREADS") && atoi(getenv("PM_BATCH_THREADS")) == 0);
     if (n_pairs >= 2 * L && lane_threads) {
@@ -709,15 +960,21 @@ int pm_match_estimate_batched_dev(pm_ctx *ctx, int n_pairs, const void *const *d
     } else {
         for (int k = 0; k < L; ++k) run_lane(k);
     }
+    // join first, report afterwards: whatever the lanes did enqueue (it writes dres and reads the caller's buffers) must
+    // be ordered before anything the caller enqueues on the ctx stream next, also when a lane failed half-way
+    int first_bad = -1;
     for (int k = 0; k < L; ++k) {
         ctx->launches += ctx->lane[k]->launches - before[k];
-        if (lane_st[k] != PM_OK) return pm_fail(ctx, lane_st[k], "lane %d: %s", k, ctx->lane[k]->err.c_str());
-    }
-    for (int k = 0; k < L; ++k) {
-        PM_CUDA(ctx, cudaEventRecord(ctx->ev_lane[k], ctx->lane[k]->stream));
-        PM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_lane[k], 0));
+        if (lane_st[k] != PM_OK && first_bad < 0) first_bad = k;
+        cudaError_t e1 = cudaEventRecord(ctx->ev_lane[k], ctx->lane[k]->stream);
+        cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(ctx->stream, ctx->ev_lane[k], 0) : e1;
+        if (e2 != cudaSuccess && first_bad < 0) {
+            first_bad = k; lane_st[k] = PM_CUDA_ERR;
+            ctx->lane[k]->err = std::string("joining the lane: ") + cudaGetErrorString(e2);
+        }
     }
     ctx->tail_is_chain = false;
+    if (first_bad >= 0) return pm_fail(ctx, lane_st[first_bad], "lane %d: %s", first_bad, ctx->lane[first_bad]->err.c_str());
     return PM_OK;
 }
 
@@ -726,6 +983,7 @@ int pm_match_estimate_batched_dev(pm_ctx *ctx, int n_pairs, const void *const *d
 int pm_batch_warmup(pm_ctx *ctx, int n1, int n2, int dim, int is_u8, const pm_ransac_params *prm)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     int st = pair_check(ctx, dim, prm);
     if (st != PM_OK) return st;
     PM_REQUIRE(ctx, n1 > 0 && n2 > 0, "sizes must be positive");
@@ -754,6 +1012,7 @@ int pm_batch_warmup(pm_ctx *ctx, int n1, int n2, int dim, int is_u8, const pm_ra
 int pm_lmeds_score_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dF32, int n_models, float *dmedians)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, n >= 0 && n_models >= 0, "bad argument");
     return pmk_lmeds_score(ctx, dp1, dp2, n, dF32, n_models, dmedians);
 }
@@ -762,6 +1021,7 @@ int pm_find_fundamental_lmeds(pm_ctx *ctx, const float *p1, const float *p2, int
                               uint64_t seed, double F[9], uint8_t *mask, int *n_inliers, float *median_out)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, p1 && p2 && F && n >= 0 && n_hyp >= 0, "bad argument");
     if (n_inliers) *n_inliers = 0;
     if (n < 8 || n_hyp == 0) return PM_EMPTY;
@@ -807,6 +1067,7 @@ int pm_find_fundamental_lmeds(pm_ctx *ctx, const float *p1, const float *p2, int
 int pm_fundamental_8point(pm_ctx *ctx, const float *p1, const float *p2, int n, double F[9])
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, p1 && p2 && F && n >= 0, "bad argument");
     if (n < 8) return PM_EMPTY;
     PM_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -828,6 +1089,7 @@ int pm_fundamental_8point(pm_ctx *ctx, const float *p1, const float *p2, int n, 
 int pm_epilines(pm_ctx *ctx, const float *pts, int n, int which, const double F[9], float *lines)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, n >= 0 && (which == 1 || which == 2) && F, "bad argument");
     if (n == 0) return PM_OK;
     PM_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -847,6 +1109,7 @@ int pm_epilines(pm_ctx *ctx, const float *pts, int n, int which, const double F[
 int pm_residuals(pm_ctx *ctx, const float *p1, const float *p2, int n, const double F[9], int metric, float *out, double *mean_out)
 {
     if (!ctx) return PM_BAD_ARG;
+    PM_NVTX();
     PM_REQUIRE(ctx, n >= 0 && F && (metric == PM_METRIC_SAMPSON || metric == PM_METRIC_SYMEPI), "bad argument");
     if (mean_out) *mean_out = 0;
     if (n == 0) return PM_OK;

@@ -19,9 +19,10 @@ enum pm_slot {
     WS_HAM_Q, WS_HAM_T, WS_HAM_PART, WS_COLBEST,
     WS_P1, WS_P2, WS_SAMPLES, WS_F32, WS_COUNTS, WS_KEY, WS_MASK, WS_FOUT, WS_REFIT, WS_MISC,
     WS_KNN, WS_KNN2, WS_IDX, WS_KP, WS_LINES,
-    WS_Q_U8, WS_T_U8, WS_T_NORMF, WS_L2_FBPART
+    WS_Q_U8, WS_T_U8, WS_T_NORMF, WS_L2_FBPART, WS_SHARD, WS_KP2, WS_PAIRRES
 };
-static_assert(WS_L2_FBPART < PM_NSLOTS, "workspace slots");
+static_assert(WS_PAIRRES < PM_NSLOTS, "workspace slots");
+void pm_comm_release(pm_ctx *ctx);      // pm_nccl.cu: destroys an owned communicator (pm_destroy)
 
 struct pm_ctx {
     int device = 0;
@@ -56,6 +57,11 @@ struct pm_ctx {
     // chunked host path (pm_api.cu): uploads run on their own stream, one event per query chunk
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_fence = nullptr, ev_train = nullptr, ev_chunk[8] = {};
+    // multi-GPU (pm_nccl.cu): ncclComm_t, owned (pm_comm_init) or borrowed (pm_set_comm)
+    void *nccl_comm = nullptr;
+    bool comm_owned = false;
+    int n_ranks = 1, rank = 0;
+    int ham_path = 0;              // per-ctx override of the Hamming kernel choice is the process-global debug hook for now
     // optional device-side kernel timing (pm_profile_*): ring of event pairs per kernel class
     bool profile = false;
     cudaEvent_t prof_ev[3][PM_PROF_RING][2] = {};
@@ -180,13 +186,14 @@ int pmk_hamming_knn2(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, 
                      int q_index_base, pm_dmatch *dout);
 int pmk_hamming_col_best(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, int bytes,
                          int q_index_base, uint64_t *dcol_best);
-// filter.cu
+// filter.cu (fb: optional helper blocks that run the L2 fallback scan before the tiles read the kNN rows, l2_fallback.cuh)
+struct L2FallbackArgs;
 int pmk_ratio_filter(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout,
-                     int32_t *dn_out, const pm_gather_out *gather = nullptr);
+                     int32_t *dn_out, const pm_gather_out *gather = nullptr, const L2FallbackArgs *fb = nullptr);
 // same, as the tail of signalling chain `seq` (stores seq to chain_done when the last block is done)
 int pmk_ratio_filter_tail(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout,
                           int32_t *dn_out, unsigned long long *chain_done, unsigned *chain_ctr, unsigned long long seq,
-                          const pm_gather_out *gather = nullptr);
+                          const pm_gather_out *gather = nullptr, const L2FallbackArgs *fb = nullptr);
 int pmk_cross_check(pm_ctx *ctx, const pm_dmatch *dknn, int nq, int stride, const uint64_t *dcol_best,
                     int nt, pm_dmatch *dout, int32_t *dn_out);
 int pmk_minmax_filter(pm_ctx *ctx, const pm_dmatch *dm, int n, int stride, pm_dmatch *dout,
@@ -208,7 +215,7 @@ int pmk_l2_col_best(pm_ctx *ctx, const float *dq, int nq, const float *dt, int n
 // ransac.cu
 // dn (optional, device): the point count is read from *dn by the kernels; n then only bounds it
 int pmk_ransac_solve(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const int32_t *dsamples,
-                     int n_hyp, int m, float *dF32, const int32_t *dn = nullptr);
+                     int n_hyp, int m, float *dF32, const int32_t *dn = nullptr, double *dF64 = nullptr);
 int pmk_ransac_score(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dF32,
                      int n_models, float thr, int metric, int32_t *dcounts, const int32_t *dn = nullptr,
                      const float *dpts4 = nullptr);
@@ -220,10 +227,14 @@ int pmk_ransac_finish(pm_ctx *ctx, const float *dp1, const float *dp2, int n, co
                       const int32_t *dn = nullptr, const float *dpts4 = nullptr, int ninl_is_zero = 0,
                       const uint64_t *dkey = nullptr, int sample_size = 0, pm_pair_result *dres = nullptr);
 int pmk_sample_sets(pm_ctx *ctx, int n_points, int n_hyp, int m, uint64_t seed, int32_t *dout,
-                    const int32_t *dn = nullptr);
+                    const int32_t *dn = nullptr, int h_base = 0);
 int pmk_pair_result(pm_ctx *ctx, const uint64_t *dkey, const int32_t *dn_good, const int32_t *dn_inl, const double *dF,
                     int n_max, int m, pm_pair_result *dres);
 int pmk_ransac_pick(pm_ctx *ctx, const uint64_t *dkey, const float *dF32, int id_base, int n_models, float *dFw);
+int pmk_ransac_update_best(pm_ctx *ctx, const uint64_t *dkey, const float *dF32, int id_base, int n_models, uint64_t *dbest_key,
+                           float *dFw_best);
+int pmk_ransac_winner_resolve(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const uint64_t *dkey,
+                              const int32_t *dsamples_full, uint64_t seed, int m, int32_t *dwin_idx, float *dF3, float *dFw);
 int pmk_lmeds_score(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dF32, int n_models, float *dmedians);
 int pmk_lmeds_finish(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const float *dF32, const float *dmedians,
                      int n_models, float *dFw, double *dF, uint8_t *dmask, int32_t *dn_inl, uint64_t *dkey);

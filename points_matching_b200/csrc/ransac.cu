@@ -134,11 +134,17 @@ __device__ int solve_cubic(const double (&c)[4], double (&r)[3])
     return n;
 }
 
-__device__ __forceinline__ void store_model(float *dst, const double (&F)[9], bool valid)
+// dst64 (optional): the same model in full double precision, 9 per model (NaN = no model) -- what the N == 7 case of
+// cv::findFundamentalMat returns to the caller (the RANSAC / LMedS scorers read the f32 copy)
+__device__ __forceinline__ void store_model(float *dst, const double (&F)[9], bool valid, double *dst64 = nullptr)
 {
 #pragma unroll
     for (int i = 0; i < 9; ++i) dst[i] = valid ? (float)F[i] : __int_as_float(0x7fc00000);
     dst[9] = dst[10] = dst[11] = 0.f;
+    if (dst64) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) dst64[i] = valid ? F[i] : __longlong_as_double(0x7ff8000000000000ll);
+    }
 }
 
 // Device-side point count (asynchronous pair pipeline, pm_match_estimate_*_dev): when n_dev is given, the
@@ -156,7 +162,8 @@ constexpr int SOLVE_THREADS = 256;    // 32 hypotheses per block
 template <int M>
 __global__ void __launch_bounds__(SOLVE_THREADS)
 ransac_solve_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2, int n,
-                    const int32_t *__restrict__ samples, int n_hyp, float *__restrict__ Fout, const int32_t *n_dev)
+                    const int32_t *__restrict__ samples, int n_hyp, float *__restrict__ Fout, const int32_t *n_dev,
+                    double *__restrict__ Fout64)
 {
     n = eff_n(n, n_dev);
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -284,7 +291,7 @@ ransac_solve_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2
         }
 #pragma unroll
         for (int i = 0; i < 9; ++i) valid = valid && isfinite(F[i]);
-        store_model(Fout + (size_t)hh * 12, F, valid);
+        store_model(Fout + (size_t)hh * 12, F, valid, Fout64 ? Fout64 + (size_t)hh * 9 : nullptr);
     } else {
         if (!live || sub != 0) return;
         // 7-point: det(lambda*f1 + (1-lambda)*f2) = 0  (OpenCV run7Point)
@@ -333,7 +340,7 @@ ransac_solve_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2
 #pragma unroll
                 for (int i = 0; i < 9; ++i) F[i] = 0;
             }
-            store_model(Fout + ((size_t)h * 3 + k) * 12, F, ok);
+            store_model(Fout + ((size_t)h * 3 + k) * 12, F, ok, Fout64 ? Fout64 + ((size_t)h * 3 + k) * 9 : nullptr);
         }
     }
 }
@@ -544,6 +551,22 @@ __global__ void ransac_pick_kernel(const unsigned long long *key, const float *_
     const unsigned long long k = *key;
     const long long m = (long long)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFu)) - id_base;
     Fw[i] = (k != 0 && m >= 0 && m < n_models) ? Fm[(size_t)m * 12 + i] : __int_as_float(0x7fc00000);
+}
+
+// Batched RANSAC with an adaptive stop (pm_find_fundamental_adaptive): after each batch the running winner
+// (*best_key, Fw_best) absorbs the batch winner.  Model ids are global, so the plain maximum of the keys keeps
+// "most inliers, lowest model id on ties" across batches.
+__global__ void ransac_update_best_kernel(const unsigned long long *key, const float *__restrict__ Fm, int id_base,
+                                          int n_models, unsigned long long *best_key, float *Fw_best)
+{
+    const unsigned long long k = *key, b = *best_key;
+    const long long m = (long long)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFu)) - id_base;
+    const bool take = k > b && m >= 0 && m < n_models;
+    __syncwarp();
+    if (take) {
+        if (threadIdx.x < 12) Fw_best[threadIdx.x] = Fm[(size_t)m * 12 + threadIdx.x];
+        if (threadIdx.x == 0) *best_key = k;
+    }
 }
 
 // =====================================================================================
@@ -832,7 +855,7 @@ __global__ void epilines_kernel(const float2 *__restrict__ pts, int n, int which
 
 __global__ void __launch_bounds__(256)
 residuals_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2, int n, const double *__restrict__ F,
-                 int metric, float *__restrict__ out, double *sum)
+                 int metric, float *__restrict__ out, double *partial)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0;
@@ -845,16 +868,33 @@ residuals_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2, i
         else { const double e2 = r * r / (a * a + b * b), e1 = r * r / (at * at + bt * bt); e = e1 > e2 ? e1 : e2; }
         out[i] = (float)e;
     }
+    // mean: fixed-shape reductions only (warp tree, 8 warps in order, then residuals_sum_kernel over the blocks in
+    // order), so the last bits do not depend on the order in which blocks finish
     __shared__ double sh[8];
     double x = e;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
     __syncthreads();
-    if (threadIdx.x == 0 && sum) {
+    if (threadIdx.x == 0 && partial) {
         double s = 0;
         for (int w = 0; w < 8; ++w) s += sh[w];
-        atomicAdd(sum, s);
+        partial[blockIdx.x] = s;
+    }
+}
+__global__ void __launch_bounds__(256) residuals_sum_kernel(const double *__restrict__ partial, int nblocks, double *sum)
+{
+    __shared__ double sh[8];
+    double x = 0;
+    for (int b = threadIdx.x; b < nblocks; b += 256) x += partial[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int w = 0; w < 8; ++w) s += sh[w];
+        *sum = s;
     }
 }
 
@@ -1009,14 +1049,14 @@ int run_refit(pm_ctx *ctx, const float4 *pts, int n, const uint8_t *dmask, const
 }  // namespace
 
 int pmk_ransac_solve(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const int32_t *dsamples, int n_hyp,
-                     int m, float *dF32, const int32_t *dn)
+                     int m, float *dF32, const int32_t *dn, double *dF64)
 {
     if (n_hyp <= 0) return PM_OK;
     const int blocks = pm_cdiv(n_hyp * 8, SOLVE_THREADS);
     if (m == 8)
-        ransac_solve_kernel<8><<<blocks, SOLVE_THREADS, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dsamples, n_hyp, dF32, dn);
+        ransac_solve_kernel<8><<<blocks, SOLVE_THREADS, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dsamples, n_hyp, dF32, dn, dF64);
     else
-        ransac_solve_kernel<7><<<blocks, SOLVE_THREADS, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dsamples, n_hyp, dF32, dn);
+        ransac_solve_kernel<7><<<blocks, SOLVE_THREADS, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dsamples, n_hyp, dF32, dn, dF64);
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }
@@ -1084,6 +1124,15 @@ int pmk_ransac_best_pick(pm_ctx *ctx, const int32_t *dcounts, int n_models, int 
 int pmk_ransac_pick(pm_ctx *ctx, const uint64_t *dkey, const float *dF32, int id_base, int n_models, float *dFw)
 {
     ransac_pick_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long *)dkey, dF32, id_base, n_models, dFw);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}
+
+int pmk_ransac_update_best(pm_ctx *ctx, const uint64_t *dkey, const float *dF32, int id_base, int n_models, uint64_t *dbest_key,
+                           float *dFw_best)
+{
+    ransac_update_best_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long *)dkey, dF32, id_base, n_models,
+                                                         (unsigned long long *)dbest_key, dFw_best);
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }
@@ -1168,8 +1217,9 @@ int pmk_lmeds_finish(pm_ctx *ctx, const float *dp1, const float *dp2, int n, con
 
 // Device twin of pm_make_sample_sets (pm_api.cu): same splitmix64 stream, same rejection of repeats, so the
 // sets are identical to the host generator's -- one thread per hypothesis.
+// h_base: row h of `out` is hypothesis h_base + h of the stream (batches / shards of one job draw disjoint ranges).
 __global__ void sample_sets_kernel(int n_points, int n_hyp, int m, unsigned long long seed, int32_t *__restrict__ out,
-                                   const int32_t *n_dev)
+                                   const int32_t *n_dev, int h_base)
 {
     n_points = eff_n(n_points, n_dev);
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1178,7 +1228,7 @@ __global__ void sample_sets_kernel(int n_points, int n_hyp, int m, unsigned long
         for (int i = 0; i < m; ++i) out[(size_t)h * m + i] = 0;
         return;
     }
-    unsigned long long s = seed ^ (0xD1B54A32D192ED03ull * (unsigned long long)(h + 1));
+    unsigned long long s = seed ^ (0xD1B54A32D192ED03ull * ((unsigned long long)h_base + (unsigned long long)h + 1ull));
     int32_t row[8];
     for (int i = 0; i < m; ++i) {
         for (;;) {
@@ -1195,10 +1245,60 @@ __global__ void sample_sets_kernel(int n_points, int n_hyp, int m, unsigned long
     for (int i = 0; i < m; ++i) out[(size_t)h * m + i] = row[i];
 }
 
-int pmk_sample_sets(pm_ctx *ctx, int n_points, int n_hyp, int m, uint64_t seed, int32_t *dout, const int32_t *dn)
+int pmk_sample_sets(pm_ctx *ctx, int n_points, int n_hyp, int m, uint64_t seed, int32_t *dout, const int32_t *dn, int h_base)
 {
     if (n_hyp <= 0) return PM_OK;
-    sample_sets_kernel<<<pm_cdiv(n_hyp, 128), 128, 0, ctx->stream>>>(n_points, n_hyp, m, (unsigned long long)seed, dout, dn);
+    sample_sets_kernel<<<pm_cdiv(n_hyp, 128), 128, 0, ctx->stream>>>(n_points, n_hyp, m, (unsigned long long)seed, dout, dn, h_base);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}
+
+// Sharded RANSAC (pm_find_fundamental_sharded_dev): after the max-reduce every rank holds the global winner key and
+// re-solves the winning minimal sample itself.  Step 1: the winner's index set -> out[0..m) -- row id / per of the full
+// sample array, or regenerated from the seed (same splitmix64 stream as sample_sets_kernel).  key == 0: zeros.
+__global__ void winner_samples_kernel(const unsigned long long *key, const int32_t *__restrict__ samples_full, int n_points,
+                                      int m, int per, unsigned long long seed, int32_t *__restrict__ out)
+{
+    if (threadIdx.x != 0) return;
+    const unsigned long long k = *key;
+    if (k == 0ull || n_points < m) { for (int i = 0; i < m; ++i) out[i] = 0; return; }
+    const unsigned id = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
+    const unsigned h = id / (unsigned)per;
+    if (samples_full) { for (int i = 0; i < m; ++i) out[i] = samples_full[(size_t)h * m + i]; return; }
+    unsigned long long s = seed ^ (0xD1B54A32D192ED03ull * ((unsigned long long)h + 1ull));
+    for (int i = 0; i < m; ++i) {
+        for (;;) {
+            unsigned long long z = (s += 0x9E3779B97F4A7C15ull);
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            z ^= z >> 31;
+            const int32_t v = (int32_t)(z % (unsigned long long)n_points);
+            bool dup = false;
+            for (int kk = 0; kk < i; ++kk) dup = dup || out[kk] == v;
+            if (!dup) { out[i] = v; break; }
+        }
+    }
+}
+// Step 2 (after the solver ran on that one sample): model id % per of its <= 3 models -> Fw
+__global__ void winner_pick_kernel(const unsigned long long *key, const float *__restrict__ Fm, int per, float *Fw)
+{
+    const int i = threadIdx.x;
+    if (i >= 12) return;
+    const unsigned long long k = *key;
+    const unsigned id = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
+    Fw[i] = k != 0ull ? Fm[(size_t)(id % (unsigned)per) * 12 + i] : __int_as_float(0x7fc00000);
+}
+
+int pmk_ransac_winner_resolve(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const uint64_t *dkey,
+                              const int32_t *dsamples_full, uint64_t seed, int m, int32_t *dwin_idx, float *dF3, float *dFw)
+{
+    const int per = m == 8 ? 1 : 3;
+    winner_samples_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long *)dkey, dsamples_full, n, m, per,
+                                                     (unsigned long long)seed, dwin_idx);
+    PM_CHECK_LAUNCH(ctx);
+    int st = pmk_ransac_solve(ctx, dp1, dp2, n, dwin_idx, 1, m, dF3);
+    if (st != PM_OK) return st;
+    winner_pick_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long *)dkey, dF3, per, dFw);
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }
@@ -1236,7 +1336,14 @@ int pmk_residuals(pm_ctx *ctx, const float *dp1, const float *dp2, int n, const 
 {
     if (dsum) PM_CUDA(ctx, cudaMemsetAsync(dsum, 0, 8, ctx->stream));
     if (n <= 0) return PM_OK;
-    residuals_kernel<<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dF, metric, dout, dsum);
+    const int nb = pm_cdiv(n, 256);
+    double *partial = nullptr;
+    if (dsum) { PM_WS(ctx, p, double *, WS_REFIT, (size_t)max(nb, RF_BLOCKS * (5 + 2 + 45) + 16) * sizeof(double)); partial = p; }
+    residuals_kernel<<<nb, 256, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dF, metric, dout, partial);
     PM_CHECK_LAUNCH(ctx);
+    if (dsum) {
+        residuals_sum_kernel<<<1, 256, 0, ctx->stream>>>(partial, nb, dsum);
+        PM_CHECK_LAUNCH(ctx);
+    }
     return PM_OK;
 }

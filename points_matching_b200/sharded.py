@@ -13,9 +13,12 @@ north_star shards the same two calls over the 8 GPUs of a B200 box:
                  re-solves the winning index set locally (cv::findFundamentalMat, main.cpp:95-98).
 
 All compute goes through an *engine*: `DeviceEngine` drives libpm's device-resident entry points
-on torch CUDA tensors (NCCL).  The collectives only need torch.distributed, so the protocol is
-covered on CPU by world-size-2 gloo tests that plug the CPU oracle in as the engine
-(tests/test_sharded_gloo.py) -- the product itself has no CPU engine.
+on torch CUDA tensors.  With `DeviceEngine.init_comm()` the two exchanges run INSIDE the C ABI
+(pm_match_cross_sharded_dev / pm_find_fundamental_sharded_dev: ncclAllReduce(min | max, uint64) on the ctx
+stream, between the kernels they connect -- what a C++ host calls, include/pm.h "multi-GPU"); without
+it they go through torch.distributed, which is also how the protocol is covered on CPU: world-size-2
+gloo tests plug the CPU oracle in as the engine (tests/test_sharded_gloo.py) -- the product itself has
+no CPU engine.
 """
 import numpy as np
 import torch
@@ -43,13 +46,61 @@ class DeviceEngine:
     def __init__(self, ctx, device):
         self.ctx, self.device = ctx, torch.device(device)
         stream = torch.cuda.current_stream(self.device)
-        if stream.cuda_stream != 0:           # share torch's stream so collectives order after the kernels
-            ctx.set_stream(stream.cuda_stream)
+        # libpm and torch must see each other's work in stream order (the torch.zeros / .to() that make the buffers,
+        # the collectives that follow the kernels).  A real torch stream is shared with the ctx as it is; torch's
+        # legacy default stream has handle 0, which pm_set_stream reads as "ctx-owned", so in that case the engine
+        # runs libpm on a torch stream of its own and orders the two with events on both sides of every call.
         self._shared_stream = stream.cuda_stream != 0
+        self._stream = stream if self._shared_stream else torch.cuda.Stream(device=self.device)
+        ctx.set_stream(self._stream.cuda_stream)
+
+    native_comm = False
+
+    def init_comm(self, group=None):
+        """Gives the ctx its own NCCL communicator over the ranks of `group` (pm_comm_init; the unique id travels through
+        torch.distributed).  From then on match_cross / sharded_find_fundamental use the C ABI's sharded entries."""
+        self.ctx.comm_init_from_torch(group)
+        self.native_comm = self.ctx.comm_info()[0] > 1
+        return self.native_comm
+
+    def match_cross_native(self, q, t, norm, base):
+        """pm_match_cross_sharded_dev on this rank's query shard: (kNN rows [nq,2,4], mutual matches [k,4])."""
+        nq, nt = q.shape[0], t.shape[0]
+        knn = torch.zeros((max(nq, 1), 2, 4), dtype=torch.int32, device=self.device)
+        col = torch.zeros(max(nt, 1), dtype=torch.int64, device=self.device)
+        out = torch.zeros((max(nq, 1), 4), dtype=torch.int32, device=self.device)
+        cnt = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self._before()
+        self.ctx.match_cross_sharded_dev(q.data_ptr(), nq, t.data_ptr(), nt, q.shape[1] if nq else t.shape[1], norm, base,
+                                         knn.data_ptr(), col.data_ptr(), out.data_ptr(), cnt.data_ptr())
+        self._sync_for_collective()
+        return knn[:nq], out[: int(cnt[0].item())]
+
+    def ransac_native(self, p1, p2, idx_full, lo, hi, m, metric, thr, refit):
+        """pm_find_fundamental_sharded_dev: this rank scores hypotheses [lo, hi) of idx_full; returns the GLOBAL winner
+        (key i64[1], F f64[9], mask u8[n], n_inliers i32[1]) -- identical on every rank."""
+        n = p1.shape[0]
+        F = torch.zeros(16, dtype=torch.float64, device=self.device)
+        mask = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        ninl = torch.zeros(4, dtype=torch.int32, device=self.device)
+        key = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self._before()
+        self.ctx.find_fundamental_sharded_dev(p1.data_ptr(), p2.data_ptr(), n, idx_full.data_ptr(), idx_full.shape[0], lo, hi - lo, m,
+                                              metric, thr, refit, F.data_ptr(), mask.data_ptr(), ninl.data_ptr(), key.data_ptr())
+        self._sync_for_collective()
+        return key[:1], F[:9], mask, ninl[:1]
+
+    def _before(self):
+        """Work enqueued on torch's current stream so far happens before the libpm kernels enqueued next."""
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream != self._stream.cuda_stream:
+            self._stream.wait_stream(cur)
 
     def _sync_for_collective(self):
-        if not self._shared_stream:
-            self.ctx.sync()
+        """The libpm kernels enqueued so far happen before whatever torch enqueues next (collectives, reads)."""
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream != self._stream.cuda_stream:
+            cur.wait_stream(self._stream)
 
     def tensor(self, a):
         return torch.as_tensor(np.ascontiguousarray(a)).to(self.device)
@@ -59,6 +110,7 @@ class DeviceEngine:
         out = torch.zeros((nq, 2, 4), dtype=torch.int32, device=self.device)
         if nq == 0:
             return out
+        self._before()
         if norm == NORM_HAMMING:
             self.ctx.knn2_hamming_dev(q.data_ptr(), nq, t.data_ptr(), nt, q.shape[1], out.data_ptr(), base)
         elif q.dtype == torch.uint8:
@@ -71,6 +123,7 @@ class DeviceEngine:
     def col_best(self, q, t, norm, base):
         nq, nt = q.shape[0], t.shape[0]
         col = torch.full((nt,), -1, dtype=torch.int64, device=self.device)       # ~0 = no query in this shard
+        self._before()
         if nq and nt:
             if norm == NORM_HAMMING:
                 self.ctx.col_best_hamming_dev(q.data_ptr(), nq, t.data_ptr(), nt, q.shape[1], col.data_ptr(), base)
@@ -83,9 +136,10 @@ class DeviceEngine:
         nq = knn.shape[0]
         out = torch.zeros((max(nq, 1), 4), dtype=torch.int32, device=self.device)
         cnt = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self._before()
         if nq:
             self.ctx.cross_check_dev(knn.data_ptr(), nq, 2, col.data_ptr(), col.shape[0], out.data_ptr(), cnt.data_ptr())
-        self.ctx.sync()
+        self._sync_for_collective()
         return out[: int(cnt[0].item())]
 
     def ransac(self, p1, p2, idx, m, metric, thr, refit, base):
@@ -95,6 +149,7 @@ class DeviceEngine:
         mask = torch.zeros(n, dtype=torch.uint8, device=self.device)
         ninl = torch.zeros(4, dtype=torch.int32, device=self.device)
         key = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self._before()
         if idx.shape[0]:
             self.ctx.find_fundamental_dev(p1.data_ptr(), p2.data_ptr(), n, idx.data_ptr(), idx.shape[0], m, metric, thr,
                                           refit, F.data_ptr(), mask.data_ptr(), ninl.data_ptr(), key.data_ptr(), base)
@@ -143,6 +198,9 @@ class ShardedMatcher:
         """BFMatcher(norm, crossCheck=true).match: mutual nearest neighbours of the whole query set in
         queryIdx order, identical on every rank ([n, 4] int32 DMatch rows)."""
         lo, hi, q = self._shard(query)
+        if getattr(self.engine, "native_comm", False) and self.group is None:
+            _, mine = self.engine.match_cross_native(q, train, self.norm, lo)     # min-reduce inside the C ABI
+            return self._gather_survivors(mine)
         knn = self.engine.knn2(q, train, self.norm, lo)
         col = self.engine.col_best(q, train, self.norm, lo)
         if self.world > 1:
@@ -150,6 +208,9 @@ class ShardedMatcher:
             dist.all_reduce(col, op=dist.ReduceOp.MIN, group=self.group)
             col = torch.where(col == I64_MAX, torch.full_like(col, -1), col)
         mine = self.engine.cross_check(knn, col)
+        return self._gather_survivors(mine)
+
+    def _gather_survivors(self, mine):
         if self.world == 1:
             return mine
         # survivors per rank differ: exchange counts, then padded rows
@@ -173,6 +234,11 @@ def sharded_find_fundamental(engine, p1, p2, sample_idx, sample_size=8, metric=M
     world, rank = _world(group)
     per = 1 if sample_size == 8 else 3
     lo, hi = shard_bounds(sample_idx.shape[0], world, rank)
+    if world > 1 and getattr(engine, "native_comm", False) and group is None:
+        # one call: solve + score the shard, ncclAllReduce(max) of the key, local re-solve of the winner, mask, refit
+        key, F, mask, ninl = engine.ransac_native(p1, p2, sample_idx, lo, hi, sample_size, metric, threshold, refit)
+        k = int(key[0].item())
+        return None if k == 0 else (F, mask, int(ninl[0].item()), 0xFFFFFFFF - (k & 0xFFFFFFFF))
     key, F, mask, ninl = engine.ransac(p1, p2, sample_idx[lo:hi].contiguous(), sample_size, metric, threshold,
                                        refit if world == 1 else False, lo)
     if world > 1:

@@ -165,9 +165,57 @@ def gold_image_pair():
          lit_F=Fl, lit_mask=ml.ravel().astype(np.uint8))
 
 
+def gold_dispatch():
+    """cv::findFundamentalMat's dispatch table at main.cpp:95-98 (SURVEY 8 a6): N == 7 -> every root of the 7-point
+    solver stacked; FM_RANSAC below 15 points -> LMedS; parameter clamps.  (Generate with `--only dispatch`: the other
+    fixtures stay as committed.)"""
+    out = {}
+    p1, p2, gt = synth.correspondences(600, seed=31)
+    rng = np.random.default_rng(77)
+    inl = np.nonzero(gt)[0]
+    sets = [rng.choice(inl, 7, replace=False) for _ in range(10)] + [rng.choice(600, 7, replace=False) for _ in range(6)]
+    idx7 = np.stack(sets).astype(np.int32)
+    F7 = np.full((len(idx7), 9, 3), np.nan)
+    k7 = np.zeros(len(idx7), np.int32)
+    for j, i in enumerate(idx7):
+        for meth in (cv2.FM_RANSAC, cv2.FM_LMEDS, cv2.FM_8POINT, cv2.FM_7POINT):     # any method: the 7-point roots
+            F, m = cv2.findFundamentalMat(p1[i], p2[i], meth)
+            assert F.shape[0] % 3 == 0 and (m == 1).all()
+            if meth == cv2.FM_RANSAC:
+                k7[j] = F.shape[0] // 3; F7[j, : F.shape[0]] = F
+            else:
+                assert np.array_equal(F, F7[j, : F.shape[0]])
+    out.update(p1=p1, p2=p2, gt=gt, idx7=idx7, F7=F7, k7=k7)
+    # below 15 points FM_RANSAC is LMedS; from 15 on it is RANSAC
+    sub = rng.permutation(inl)[:40]
+    out.update(sub=sub.astype(np.int32))
+    for n in (8, 11, 14):
+        Fr, mr = cv2.findFundamentalMat(p1[sub[:n]], p2[sub[:n]], cv2.FM_RANSAC, 1.0, 0.99)
+        Fl, ml = cv2.findFundamentalMat(p1[sub[:n]], p2[sub[:n]], cv2.FM_LMEDS, 1.0, 0.99)
+        F7p, m7 = cv2.findFundamentalMat(p1[sub[:n]], p2[sub[:n]], cv2.FM_7POINT, 1.0, 0.99)
+        assert np.array_equal(Fr, Fl) and np.array_equal(mr, ml) and np.array_equal(Fr, F7p) and np.array_equal(mr, m7)
+        out.update({f"n{n}_F": Fl, f"n{n}_mask": ml.ravel().astype(np.uint8)})
+    mix = np.concatenate([sub[:30], rng.choice(np.nonzero(~gt)[0], 10, replace=False)])     # 25% outliers
+    out.update(mix=mix.astype(np.int32))
+    Fr, mr = cv2.findFundamentalMat(p1[mix], p2[mix], cv2.FM_RANSAC, 1.0, 0.99)
+    Fl, ml = cv2.findFundamentalMat(p1[mix], p2[mix], cv2.FM_LMEDS, 1.0, 0.99)
+    out.update(n40_ransac_F=Fr, n40_ransac_mask=mr.ravel().astype(np.uint8), n40_lmeds_F=Fl, n40_lmeds_mask=ml.ravel().astype(np.uint8))
+    # clamps: param1 <= 0 -> 3, param2 outside (0, 1) -> 0.99
+    F0, m0 = cv2.findFundamentalMat(p1[mix], p2[mix], cv2.FM_RANSAC, 0.0, 0.99)
+    F3, m3 = cv2.findFundamentalMat(p1[mix], p2[mix], cv2.FM_RANSAC, 3.0, 0.99)
+    Fc, mc = cv2.findFundamentalMat(p1[mix], p2[mix], cv2.FM_RANSAC, 3.0, 1.5)
+    assert np.array_equal(F0, F3) and np.array_equal(m0, m3) and np.array_equal(Fc, F3) and np.array_equal(mc, m3)
+    out.update(n40_thr3_F=F3, n40_thr3_mask=m3.ravel().astype(np.uint8))
+    save("dispatch.npz", **out)
+
+
 if __name__ == "__main__":
     cv2.setRNGSeed(0)
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "dispatch":
+        gold_dispatch()
+        sys.exit(0)
     gold_l2()
     gold_hamming()
     gold_fundamental()
     gold_image_pair()
+    gold_dispatch()

@@ -42,7 +42,7 @@ def test_dmatch_layout_matches_cv_dmatch():
 
 def test_version_and_no_cpu_fallback(L):
     import torch
-    assert L.pm_version() == 100
+    assert L.pm_version() == 200
     if torch.cuda.is_available():
         pytest.skip("GPU present: covered by the -m gpu tests")
     h = C.c_void_p()

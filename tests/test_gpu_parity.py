@@ -468,7 +468,12 @@ def test_opencv_lookalike_api(pm, golden):
     good = pm.ratio_test(matcher.knnMatchArray(d1, d2), 0.75)
     pts1 = pm.keypoints_convert(g["kp1"], good["queryIdx"])        # main.cpp:90-91
     pts2 = pm.keypoints_convert(g["kp2"], good["trainIdx"])
-    F, mask = pm.findFundamentalMat(pts1, pts2, pm.FM_RANSAC, 1.0, 0.99, maxIters=4096)
+    # OpenCV's estimator (the default: 7-point samples, symmetric-epipolar error, no refit): cv2's own mask rule holds
+    Fcv, mcv = pm.findFundamentalMat(pts1, pts2, pm.FM_RANSAC, 1.0, 0.99, maxIters=4096)
+    assert Fcv.shape == (3, 3) and mcv.sum() >= 0.9 * g["ransac_mask"].sum()
+    # the north_star variant (8-point samples, Sampson error, refit on the inliers)
+    F, mask = pm.findFundamentalMat(pts1, pts2, pm.FM_RANSAC, 1.0, 0.99, maxIters=4096, sample_size=8,
+                                    metric=pm.METRIC_SAMPSON, refit=True)
     assert F is not None and F.shape == (3, 3) and mask.shape == (len(pts1),)
     # quality at least OpenCV's on the same matches (OpenCV does not refit, D5)
     inl = g["ransac_mask"].astype(bool)
@@ -738,3 +743,227 @@ def test_device_sample_sets_equal_host_generator(ctx, pm):
         ctx.make_sample_sets_dev(n, nh, m, seed, d.data_ptr())
         ctx.sync()
         assert np.array_equal(d.cpu().numpy(), make_sample_sets(n, nh, m, seed))
+
+
+# ======================================================================================
+# round 2: dispatch table of cv::findFundamentalMat, device-side adaptive RANSAC, the two
+# residency fixes (compaction tickets, barrier-free split-mode fallback)
+# ======================================================================================
+def _rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(np.asarray(b)).max()
+
+
+def test_find_fundamental_dispatch_table(ctx, pm, orc, golden):
+    """cv::findFundamentalMat's dispatch (main.cpp:95-98; SURVEY 8 a6) against tests/golden/dispatch.npz (cv2 4.13):
+    N < 7 -> empty; N == 7 -> every root of the 7-point solver stacked, whatever the method; FM_8POINT -> N-point
+    8-point; FM_RANSAC below 15 points -> LMedS; param1 <= 0 -> 3; param2 outside (0, 1) -> 0.99."""
+    from points_matching_b200.api import make_sample_sets
+    g = golden["dispatch"]
+    p1, p2 = g["p1"], g["p2"]
+    assert pm.findFundamentalMat(p1[:6], p2[:6], pm.FM_RANSAC, ctx=ctx) == (None, None)
+    for idx, Fg, k in zip(g["idx7"], g["F7"], g["k7"]):
+        for method in (pm.FM_RANSAC, pm.FM_LMEDS, pm.FM_8POINT, pm.FM_7POINT):
+            F, mask = pm.findFundamentalMat(p1[idx], p2[idx], method, ctx=ctx)
+            assert F.shape == (3 * k, 3) and mask.shape == (7,) and (mask == 1).all()
+            for a in Fg[: 3 * k].reshape(k, 3, 3):
+                assert min(_rel(b, a) for b in F.reshape(k, 3, 3)) < 1e-6              # cv2's roots, any order
+        assert np.array_equal(ctx.fundamental_7point(p1[idx], p2[idx]).reshape(-1, 3), F)
+    with pytest.raises(pm.PMError):
+        ctx.fundamental_7point(p1[:8], p2[:8])
+    sub, mix = g["sub"], g["mix"]
+    niters = max(3, int(round(np.log(0.01) / np.log(1 - 0.55 ** 7))))                  # RANSACUpdateNumIters(0.99, 0.45, 7, 1000)
+    for n in (8, 11, 14):
+        a, b = p1[sub[:n]], p2[sub[:n]]
+        ref = pm.findFundamentalMat(a, b, pm.FM_LMEDS, 1.0, 0.99, seed=5, ctx=ctx)
+        for method in (pm.FM_RANSAC, pm.FM_7POINT):                                    # both ARE LMedS below 15 points
+            F, mask = pm.findFundamentalMat(a, b, method, 1.0, 0.99, seed=5, ctx=ctx)
+            assert np.array_equal(F, ref[0]) and np.array_equal(mask, ref[1]), (n, method)
+        direct = ctx.find_fundamental_lmeds(a, b, n_hyp=niters, seed=5)
+        assert np.array_equal(direct[0], ref[0]) and np.array_equal(direct[1], ref[1])
+        r = orc.lmeds_f(a, b, make_sample_sets(n, niters, 7, 5))                       # the oracle on the same 7-point sets
+        if n == 14:        # below 14 points the median is one of the sample points' own (rounding-noise) errors
+            assert _rel(ref[0], r["F"]) < 1e-6 and np.array_equal(ref[1], r["mask"])
+            assert np.sort(orc.symepi_f64(ref[0], a, b))[n // 2] < 2.0               # a sound model (all 14 are true inliers)
+    a, b = p1[mix], p2[mix]
+    F, mask = pm.findFundamentalMat(a, b, pm.FM_RANSAC, 1.0, 0.99, ctx=ctx)            # 40 points: RANSAC proper
+    assert F.shape == (3, 3) and F[2, 2] == 1.0
+    err = orc.symepi_f64(F, a, b)
+    assert ((err <= 1.0) == mask.astype(bool)).sum() >= 39                               # OpenCV's mask rule (f32 vs f64 at the edge)
+    assert mask.sum() >= g["n40_ransac_mask"].sum() - 2
+    Fl, ml = pm.findFundamentalMat(a, b, pm.FM_LMEDS, 1.0, 0.99, ctx=ctx)
+    assert not np.array_equal(F, Fl)                                                   # from 15 points on FM_RANSAC is not LMedS
+    ref = pm.findFundamentalMat(a, b, pm.FM_RANSAC, 3.0, 0.99, ctx=ctx)
+    for prm1, prm2 in ((0.0, 0.99), (-2.0, 0.99), (3.0, 1.5), (3.0, 0.0)):
+        F2, m2 = pm.findFundamentalMat(a, b, pm.FM_RANSAC, prm1, prm2, ctx=ctx)
+        assert np.array_equal(F2, ref[0]) and np.array_equal(m2, ref[1]), (prm1, prm2)
+    F8, m8 = pm.findFundamentalMat(a, b, pm.FM_8POINT, ctx=ctx)
+    assert np.array_equal(F8, ctx.fundamental_8point(a, b)) and (m8 == 1).all()
+    # the north_star variant of the same call: 8-point samples, Sampson error, refit on the inliers
+    Fn, mn = pm.findFundamentalMat(g["p1"], g["p2"], pm.FM_RANSAC, 1.0, 0.99, maxIters=2048, sample_size=8,
+                                   metric=pm.METRIC_SAMPSON, refit=True, ctx=ctx)
+    gt = g["gt"]
+    assert orc.sampson_f64(Fn, g["p1"][gt], g["p2"][gt]).mean() < 0.25 and mn[gt].mean() > 0.9 and mn[~gt].mean() < 0.05
+
+
+@pytest.mark.parametrize("m,metric", [(7, 1), (8, 0)])
+def test_find_fundamental_adaptive_equals_fixed_batches(ctx, pm, m, metric):
+    """pm_find_fundamental_adaptive (points uploaded once, samples generated on the device per batch, 8 bytes back per
+    batch) returns exactly what one fixed run over the same `hypotheses_run` sample sets returns, and stops where
+    OpenCV's RANSACUpdateNumIters says."""
+    from points_matching_b200.api import make_sample_sets
+    p1, p2, gt = synth.correspondences(4000, seed=21, outlier_frac=0.5)
+    F, mask, ninl, run = ctx.find_fundamental_adaptive(p1, p2, sample_size=m, metric=metric, threshold=1.0, confidence=0.99,
+                                                       max_iters=3000, batch=512, refit=False, seed=9)
+    assert run % 512 == 0 or run == 3000
+    ref = ctx.find_fundamental(p1, p2, sample_size=m, metric=metric, threshold=1.0, refit=False,
+                               sample_idx=make_sample_sets(4000, run, m, 9))
+    assert ninl == ref[2] and np.array_equal(F, ref[0]) and np.array_equal(mask, ref[1])
+    w = ninl / 4000.0
+    need = np.log(0.01) / np.log(1 - w ** m)
+    assert run >= min(3000, need) - 1                                                    # never stops early
+    assert mask[gt].mean() > 0.7 and mask[~gt].mean() < 0.1
+    # an easy problem stops after the first batch; max_iters caps a hard one
+    q1, q2, _ = synth.correspondences(2000, seed=22, outlier_frac=0.1)
+    assert ctx.find_fundamental_adaptive(q1, q2, sample_size=m, metric=metric, threshold=1.0, batch=256, seed=1)[3] == 256
+    assert ctx.find_fundamental_adaptive(p1, p2, sample_size=m, metric=metric, threshold=0.05, max_iters=700, batch=256, seed=1)[3] == 700
+    assert ctx.find_fundamental_adaptive(p1[:6], p2[:6], sample_size=m) is None
+
+
+def test_compaction_tickets_large_small_interleaved(ctx, pm, orc):
+    """The ratio filter on more tiles than SMs (ticket order matters), interleaved with small calls on the same ctx:
+    every call must leave the ticket counter of the next one at zero (an earlier version reset it only in 'large'
+    calls, so large -> small -> large handed out stale tickets and hung)."""
+    import torch
+    rng = np.random.default_rng(5)
+    big, small = 1024 * 160 + 777, 3000
+    def make(n):
+        knn = np.zeros((n, 2), dtype=pm.DMATCH)
+        knn["queryIdx"] = np.arange(n)[:, None]
+        knn["trainIdx"] = rng.integers(0, 1000, (n, 2))
+        knn["distance"][:, 1] = rng.uniform(1, 2, n).astype(np.float32)
+        knn["distance"][:, 0] = (knn["distance"][:, 1] * rng.uniform(0.5, 1.0, n)).astype(np.float32)
+        return knn
+    kb, ks = make(big), make(small)
+    refs = {big: orc.ratio_filter(kb, 0.75), small: orc.ratio_filter(ks, 0.75)}
+    dev = {big: torch.from_numpy(kb.view(np.int32).reshape(big, 8)).cuda(), small: torch.from_numpy(ks.view(np.int32).reshape(small, 8)).cuda()}
+    out = torch.zeros((big, 4), dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
+    for n in (big, small, big, small, small, big, big, small):
+        out.zero_(); torch.cuda.synchronize()
+        ctx.ratio_filter_dev(dev[n].data_ptr(), n, 0.75, out.data_ptr(), cnt.data_ptr())
+        ctx.sync()
+        k = int(cnt[0].item())
+        assert k == len(refs[n])
+        got = out[:k].cpu().numpy().view(pm.DMATCH).reshape(-1)
+        assert np.array_equal(got, refs[n]), n
+
+
+def test_split_mode_fallback_helpers_and_lanes(pm, orc):
+    """General-float (SURF-like) descriptors take the split mode, where uncertified rows get an exact scan.  That scan
+    is barrier-free now (helper blocks of the filter kernel in the one-call chain, a kernel of its own otherwise):
+    both forms, and the batched pair call with several lanes running the same kernels concurrently, give the oracle's
+    matches."""
+    import torch
+    from points_matching_b200 import _lib
+    from points_matching_b200.pipeline import match_and_estimate_batch_native
+    ctx = pm.Context(0)
+    q, t = synth.surf_pair(3000, 5000, seed=5)
+    ref = orc.knn2_l2(q, t)
+    gref = orc.ratio_filter(ref, 0.8)
+    dq, dt_ = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    knn = torch.zeros((3000, 2, 4), dtype=torch.int32, device="cuda")
+    good = torch.zeros((3000, 4), dtype=torch.int32, device="cuda")
+    ng = torch.zeros(4, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    flagged = []
+    for separate in (0, 1):
+        _lib.lib().pm_debug_fallback_separate(separate)
+        try:
+            for _ in range(3):
+                knn.zero_(); good.zero_(); torch.cuda.synchronize()
+                ctx.knn2_ratio_l2_f32_dev(dq.data_ptr(), 3000, dt_.data_ptr(), 5000, 128, 0.8, knn.data_ptr(), good.data_ptr(), ng.data_ptr())
+                ctx.sync()
+                st = ctx.l2_stats()
+                assert not st["exact_mode"]
+                flagged.append(st["fallback_rows"])
+                k = knn.cpu().numpy().view(pm.DMATCH).reshape(3000, 2)
+                assert np.array_equal(k["trainIdx"], ref["trainIdx"])
+                assert np.allclose(k["distance"], ref["distance"], rtol=1e-5, atol=0)       # north_star tolerance
+                n = int(ng[0].item())
+                gg = good[:n].cpu().numpy().view(pm.DMATCH).reshape(-1)
+                assert n == len(gref) and np.array_equal(gg["queryIdx"], gref["queryIdx"]) and np.array_equal(gg["trainIdx"], gref["trainIdx"])
+        finally:
+            _lib.lib().pm_debug_fallback_separate(0)
+    # kNN-only chain (the fallback kernel of its own)
+    ctx.knn2_l2_f32_dev(dq.data_ptr(), 3000, dt_.data_ptr(), 5000, 128, knn.data_ptr(), 0)
+    ctx.sync()
+    assert np.array_equal(knn.cpu().numpy().view(pm.DMATCH).reshape(3000, 2)["trainIdx"], ref["trainIdx"])
+    # an adversarial set: near-duplicate train rows make many rows uncertifiable -> many fallback rows, split == 1 path
+    t2 = t.copy()
+    t2[1::2] = t2[::2] + np.float32(1e-4) * np.random.default_rng(1).standard_normal(t2[::2].shape).astype(np.float32)
+    ref2 = orc.knn2_l2(q[:700], t2)
+    k2 = ctx.knn2(q[:700], t2, pm.NORM_L2)
+    assert ctx.l2_stats()["fallback_rows"] > 20
+    assert np.array_equal(k2["trainIdx"], ref2["trainIdx"])
+    # several lanes run K3 / the filter helpers of different pairs concurrently
+    pairs = []
+    for k in range(6):
+        a, b = synth.surf_pair(2000 + 100 * k, 2500, seed=40 + k)
+        rng = np.random.default_rng(k)
+        pairs.append((torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(),
+                      torch.from_numpy(rng.uniform(0, 1000, (a.shape[0], 2)).astype(np.float32)).cuda(),
+                      torch.from_numpy(rng.uniform(0, 1000, (2500, 2)).astype(np.float32)).cuda()))
+    ctx.set_batch_lanes(1)
+    one = match_and_estimate_batch_native(ctx, pairs, n_hyp=256)
+    ctx.set_batch_lanes(6)
+    for _ in range(3):
+        many = match_and_estimate_batch_native(ctx, pairs, n_hyp=256)
+        for (_, a), (_, b) in zip(one, many):
+            assert a["n_matches"] == b["n_matches"] and a["n_inliers"] == b["n_inliers"]
+    for k in (0, 5):
+        a, b = pairs[k][0].cpu().numpy(), pairs[k][1].cpu().numpy()
+        assert one[k][1]["n_matches"] == len(orc.ratio_filter(orc.knn2_l2(a, b), 0.75))
+    ctx.close()
+
+
+def test_residual_mean_is_deterministic(ctx, pm, golden):
+    g = golden["fundamental"]
+    p1 = np.tile(g["p1"], (40, 1)); p2 = np.tile(g["p2"], (40, 1))
+    means = {ctx.residuals(p1, p2, g["ransac1_F"])[1] for _ in range(8)}
+    assert len(means) == 1
+
+
+def test_measured_peaks_are_sane(ctx):
+    ffma, popc = ctx.measure_peak(0), ctx.measure_peak(1)
+    assert 40.0 < ffma < 90.0, ffma            # B200: 148 SMs x 128 lanes x 2 FLOP x ~1.9 GHz = 73 TFLOP/s nominal
+    assert 2.0 < popc < 20.0, popc             # 148 SMs x 16 (or 32) POPC lanes x ~1.9 GHz = 4.6 (9.3) T POPC/s
+
+
+def test_host_batched_pairs_equal_device_batched(pm):
+    """pm_match_estimate_batched (descriptors / keypoints in pinned HOST memory, uploads under the other lanes' kernels)
+    returns the records of pm_match_estimate_batched_dev on the same pairs, f32 and u8."""
+    import torch
+    from points_matching_b200.pipeline import match_and_estimate_batch_native
+    ctx = pm.Context(0)
+    host, dev = [], []
+    for k, (n1, n2) in enumerate([(2000, 2200), (1500, 900), (3000, 3000), (5, 40), (800, 800)]):
+        arrs = synth.image_pair(n1, n2, seed=70 + k)[:4]
+        host.append(tuple(torch.from_numpy(a).pin_memory() for a in arrs))
+        dev.append(tuple(torch.from_numpy(a).cuda() for a in arrs))
+    ref = match_and_estimate_batch_native(ctx, dev, n_hyp=512)
+    for lanes in (1, 4):
+        ctx.set_batch_lanes(lanes)
+        rec = ctx.match_estimate_batched([h[0].data_ptr() for h in host], [h[0].shape[0] for h in host],
+                                         [h[1].data_ptr() for h in host], [h[1].shape[0] for h in host], 128, False,
+                                         [h[2].data_ptr() for h in host], [h[3].data_ptr() for h in host], 0.75, 512)
+        for (_, a), r in zip(ref, rec):
+            assert a["n_matches"] == r["n_matches"] and a["n_inliers"] == r["n_inliers"]
+            assert (a["F"] is None) == (r["has_model"] == 0)
+            if a["F"] is not None:
+                assert np.array_equal(a["F"], r["F"].reshape(3, 3))
+    h8 = [(h[0].to(torch.uint8).pin_memory(), h[1].to(torch.uint8).pin_memory(), h[2], h[3]) for h in host]
+    rec8 = ctx.match_estimate_batched([h[0].data_ptr() for h in h8], [h[0].shape[0] for h in h8], [h[1].data_ptr() for h in h8],
+                                      [h[1].shape[0] for h in h8], 128, True, [h[2].data_ptr() for h in h8],
+                                      [h[3].data_ptr() for h in h8], 0.75, 512)
+    assert np.array_equal(rec8["n_matches"], rec["n_matches"]) and np.array_equal(rec8["F"], rec["F"])
+    ctx.close()

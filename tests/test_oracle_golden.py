@@ -110,6 +110,38 @@ def test_dispatch_small_n(golden, orc):
     assert F.shape == g["n7_F"].shape and (m == 1).all()
 
 
+def test_dispatch_table_golden(golden, orc):
+    """tests/golden/dispatch.npz (cv2 4.13): N == 7 -> all roots stacked whatever the method; FM_RANSAC with
+    8 <= N < 15 -> LMedS; the parameter clamps.  The oracle follows cv::RNG's sample stream, so F and the masks are
+    compared directly."""
+    g = golden["dispatch"]
+    p1, p2 = g["p1"], g["p2"]
+    for idx, F, k in zip(g["idx7"], g["F7"], g["k7"]):
+        for method in (8, 4, 2, 1):
+            Fo, m = orc.find_fundamental_cv(p1[idx], p2[idx], method)
+            assert Fo.shape == (3 * k, 3) and (m == 1).all()
+            for a in F[: 3 * k].reshape(k, 3, 3):
+                assert min(_rel(b, a) for b in Fo.reshape(k, 3, 3)) < 1e-7
+    sub = g["sub"]
+    for n in (8, 11, 14):
+        # below 14 points the median (sorted error n/2) belongs to one of the seven sample points themselves, i.e. it is
+        # rounding noise and so is the winner: only the dispatch (RANSAC == LMedS == 7POINT) is comparable there
+        ref = orc.find_fundamental_cv(p1[sub[:n]], p2[sub[:n]], 4, 1.0, 0.99)
+        for method in (8, 4, 1):
+            Fo, m = orc.find_fundamental_cv(p1[sub[:n]], p2[sub[:n]], method, 1.0, 0.99)
+            assert np.array_equal(Fo, ref[0]) and np.array_equal(m, ref[1]), (n, method)
+            if n == 14:
+                assert _rel(Fo, g[f"n{n}_F"]) < 1e-7 and (m == g[f"n{n}_mask"]).all(), (n, method)
+    mix = g["mix"]
+    Fo, m = orc.find_fundamental_cv(p1[mix], p2[mix], 8, 1.0, 0.99)
+    assert _rel(Fo, g["n40_ransac_F"]) < 1e-7 and (m == g["n40_ransac_mask"]).all()
+    Fo, m = orc.find_fundamental_cv(p1[mix], p2[mix], 4, 1.0, 0.99)
+    assert _rel(Fo, g["n40_lmeds_F"]) < 1e-7 and (m == g["n40_lmeds_mask"]).all()
+    for prm1, prm2 in ((0.0, 0.99), (3.0, 0.99), (3.0, 1.5), (-1.0, 0.0)):
+        Fo, m = orc.find_fundamental_cv(p1[mix], p2[mix], 8, prm1, prm2)
+        assert _rel(Fo, g["n40_thr3_F"]) < 1e-7 and (m == g["n40_thr3_mask"]).all(), (prm1, prm2)
+
+
 def test_sampson_and_epilines(golden, orc):
     g = golden["fundamental"]
     F = g["ransac1_F"]

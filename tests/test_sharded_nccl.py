@@ -42,6 +42,26 @@ def _worker(rank, world, port, out_dir):
                                                                  pm.METRIC_SAMPSON, 1.0, True)
         res["ransac_F"], res["ransac_mask"] = F.cpu().numpy(), mask.cpu().numpy()
         res["ransac_meta"] = np.array([ninl, winner])
+        # the same two exchanges INSIDE the C ABI (pm_comm_init + pm_match_cross_sharded_dev /
+        # pm_find_fundamental_sharded_dev: ncclAllReduce on the ctx stream) -- what a C++ host runs
+        assert eng.init_comm() and ctx.comm_info() == (world, rank)
+        res["native_ham_cross"] = mh.match_cross(eng.tensor(qb), eng.tensor(tb)).cpu().numpy()
+        res["native_l2_cross"] = sharded.ShardedMatcher(eng, pm.NORM_L2).match_cross(eng.tensor(q), eng.tensor(t)).cpu().numpy()
+        F2, mask2, ninl2, winner2 = sharded.sharded_find_fundamental(eng, eng.tensor(p1), eng.tensor(p2), eng.tensor(idx), 8,
+                                                                     pm.METRIC_SAMPSON, 1.0, True)
+        res["native_ransac_F"], res["native_ransac_mask"] = F2.cpu().numpy(), mask2.cpu().numpy()
+        res["native_ransac_meta"] = np.array([ninl2, winner2])
+        # sample sets generated from the seed on every rank (no index array at all), 7-point samples
+        dF = torch.zeros(16, dtype=torch.float64, device=eng.device); dmask = torch.zeros(3000, dtype=torch.uint8, device=eng.device)
+        dn = torch.zeros(4, dtype=torch.int32, device=eng.device); dkey = torch.zeros(2, dtype=torch.int64, device=eng.device)
+        lo, hi = sharded.shard_bounds(777, world, rank)
+        d1, d2 = eng.tensor(p1), eng.tensor(p2)
+        eng._before()
+        ctx.find_fundamental_sharded_dev(d1.data_ptr(), d2.data_ptr(), 3000, 0, 777, lo, hi - lo, 7, pm.METRIC_SYMEPI, 1.0, False,
+                                         dF.data_ptr(), dmask.data_ptr(), dn.data_ptr(), dkey.data_ptr(), seed=321)
+        ctx.sync()
+        res["seeded_F"], res["seeded_mask"] = dF[:9].cpu().numpy(), dmask.cpu().numpy()
+        res["seeded_meta"] = np.array([int(dn[0].item()), int(dkey[0].item())])
         # BASELINE config 5: image pairs partitioned across ranks, each rank's shard through the batched C-ABI entry
         from points_matching_b200.pipeline import match_and_estimate_batch_native
         mine = match_and_estimate_batch_native(ctx, _pairs(torch, f"cuda:{rank}"), n_hyp=512)
@@ -89,6 +109,18 @@ def test_two_rank_nccl_equals_single_gpu(tmp_path, orc):
     r = orc.ransac_f(p1, p2, idx, 0, 1.0, True)
     assert int(r0["ransac_meta"][1]) == r["best_model"] and abs(int(r0["ransac_meta"][0]) - r["n_inliers"]) <= 3
     assert (r0["ransac_mask"] == r["mask"]).mean() > 0.998
+    # the exchanges inside the C ABI give the same answers as the torch.distributed protocol, bit for bit
+    assert np.array_equal(r0["native_ham_cross"], r0["ham_cross"])
+    ctx1 = pm.Context(0)
+    assert np.array_equal(r0["native_l2_cross"].view(pm.DMATCH).reshape(-1), ctx1.match_cross(q, t, pm.NORM_L2))
+    for k in ("ransac_F", "ransac_mask", "ransac_meta"):
+        assert np.array_equal(r0["native_" + k], r0[k]), k
+    from points_matching_b200.api import make_sample_sets
+    one = ctx1.find_fundamental(p1, p2, sample_size=7, metric=pm.METRIC_SYMEPI, threshold=1.0, refit=False,
+                                sample_idx=make_sample_sets(3000, 777, 7, 321))
+    ctx1.close()
+    assert np.array_equal(r0["seeded_F"].reshape(3, 3), one[0]) and np.array_equal(r0["seeded_mask"], one[1])
+    assert int(r0["seeded_meta"][0]) == one[2]
     # the partitioned pair batch equals the same batch on one GPU, pair by pair and bit for bit
     from points_matching_b200.pipeline import match_and_estimate_batch_native
     ctx = pm.Context(0)
@@ -98,3 +130,19 @@ def test_two_rank_nccl_equals_single_gpu(tmp_path, orc):
     for i, (_, o) in enumerate(one):
         assert list(r0["pairs_meta"][i]) == [o["n_matches"], o["n_inliers"]] and o["F"] is not None
         assert np.array_equal(r0["pairs_F"][i], o["F"])
+
+
+def test_cpp_host_two_gpus_example():
+    """examples/sharded_two_gpus: a C++ host, one thread and one pm_ctx per GPU, NCCL inside the C ABI
+    (pm_comm_init / pm_match_cross_sharded_dev / pm_allgather_matches_dev / pm_find_fundamental_sharded_dev);
+    it checks itself against the same calls on one GPU and exits 0 when every bit agrees."""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    exe = os.path.join(ROOT, "examples", "sharded_two_gpus")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples"), "-s"])
+    r = subprocess.run([exe, "2"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "identical to one GPU" in r.stdout
