@@ -356,14 +356,15 @@ int pm_measure_peak(pm_ctx *ctx, int which, double *value);
  *   pm_debug_set_span(p)            every kernel of the L2 chain stamps %globaltimer marks into p (tools/step_timeline.py)
  *   pm_debug_hamming_path(k)        0 auto, 1 force the POPC kernel, 2 force the tensor-core kernel
  *   pm_debug_force_exact(on)        L2: exact FP32 kernel for every row (cross-check of the two paths)
- *   pm_debug_fallback_separate(on)  L2 one-call chain: run the flagged-row scan as its own kernel instead of helper blocks
+ *   pm_debug_fallback_no_helpers(on) L2 split mode: no helper blocks, the last row block of K3 runs the flagged-row scan alone
  *   pm_debug_set_l2_dump(p), pm_debug_set_k2_trace(p)   K2 tile dump / clock64 trace (PM_K2_TRACE builds) */
 void pm_debug_set_span(unsigned long long *p);
 void pm_debug_hamming_path(int path);
 void pm_debug_force_exact(int on);
-void pm_debug_fallback_separate(int on);
+void pm_debug_fallback_no_helpers(int on);
 void pm_debug_set_l2_dump(float *ddump);
 void pm_debug_set_k2_trace(long long *p);
+void pm_debug_set_k2_trace_cta(int cta);
 
 /* ---- diagnostics (main.cpp:103-123, 127-132) --------------------------------- */
 /* cv::computeCorrespondEpilines: l = F x (which_image 1) or F^T x (2), a^2+b^2 = 1. */

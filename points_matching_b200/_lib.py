@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libpm.so")
+SO_PATH = os.environ.get("PM_LIBPM_SO") or os.path.join(_HERE, "libpm.so")      # PM_LIBPM_SO: an instrumented build (tools/)
 
 PM_OK, PM_EMPTY, PM_BAD_ARG, PM_CUDA_ERR, PM_NCCL_ERR, PM_NO_DEVICE = 0, 1, -1, -2, -3, -4
 DMATCH = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
@@ -54,8 +54,8 @@ EXPORTS = [
     "pm_match_estimate_batched", "pm_find_fundamental_adaptive", "pm_find_fundamental_mat", "pm_fundamental_7point",
     "pm_comm_unique_id", "pm_comm_init", "pm_set_comm", "pm_comm_info", "pm_match_cross_sharded_dev",
     "pm_allgather_matches_dev", "pm_find_fundamental_sharded_dev", "pm_measure_peak",
-    "pm_debug_set_span", "pm_debug_hamming_path", "pm_debug_force_exact", "pm_debug_fallback_separate",
-    "pm_debug_set_l2_dump", "pm_debug_set_k2_trace",
+    "pm_debug_set_span", "pm_debug_hamming_path", "pm_debug_force_exact", "pm_debug_fallback_no_helpers",
+    "pm_debug_set_l2_dump", "pm_debug_set_k2_trace", "pm_debug_set_k2_trace_cta",
 ]
 
 

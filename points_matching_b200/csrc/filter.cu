@@ -9,7 +9,6 @@
 // (decoupled look-back across tiles) and scatter; output stays in queryIdx order, exactly
 // like the reference's push_back loop.
 #include "pm_internal.h"
-#include "l2_fallback.cuh"
 
 namespace {
 
@@ -63,15 +62,15 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *total)
     return base + x - v;
 }
 
-// Single-pass order-preserving compaction (decoupled look-back).  Tiles ALWAYS take tickets from
-// an atomic counter, so a tile only ever waits on tiles that have already started -- no assumption
-// about how many CTAs are resident at once or in which order the hardware dispatches them (other
-// streams, the lanes of the batched pair call and other processes may share the GPU).  status[t] =
-// epoch << 34 | state << 32 | value with state 1 = tile aggregate, 2 = inclusive prefix; the
-// epoch (one per call) makes stale words from earlier calls invisible, so nothing is cleared
-// between calls.  counter[epoch & 1] hands out tickets; the tile with ticket 0 zeroes the other
-// counter for the next call -- unconditionally, on every call (every call advances the epoch, so
-// every call must leave the next call's counter at zero).
+// Single-pass order-preserving compaction (decoupled look-back).  Tiles ALWAYS take tickets from an atomic counter, so
+// a tile only ever waits on tiles that have already started -- no assumption about how many CTAs are resident at once
+// or in which order the hardware dispatches them (other streams, the lanes of the batched pair call and other
+// processes may share the GPU).  The counter is never reset: it counts the tiles of ALL calls of this ctx, and the host
+// passes the number handed out before this call (ticket_base; 64 bits), so tile = ticket - ticket_base.  A block takes
+// its ticket BEFORE it lets the next kernel of the stream launch (griddepcontrol.launch_dependents), so the tickets of
+// consecutive calls cannot interleave, and before its own griddepcontrol.wait, so the atomic's round trip hides under the
+// predecessor's tail.  status[t] = epoch << 34 | state << 32 | value with state 1 = tile aggregate, 2 = inclusive prefix;
+// the epoch (one per call) makes stale words from earlier calls invisible, so nothing is cleared between calls.
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
 {
     unsigned long long v;
@@ -83,46 +82,25 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned 
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// WITH_FB (the one-call L2 kNN-2 + ratio chain, l2.cu): the first fb.helpers tickets are "helper" blocks that run the
-// exact scan of the rows K3 flagged (l2_fallback.cuh) and rewrite those kNN rows; the tiles wait until rows_fixed has
-// reached n_flagged before they read the kNN rows.  A tile's ticket is larger than every helper's, so it only waits
-// on blocks that have already started, and helpers never wait: no residency assumption.  In exact-integer mode K3
-// flags nothing: helpers return at once, tiles do not wait.
-template <class Pred, bool WITH_FB>
+template <class Pred>
 __global__ void __launch_bounds__(FB) compact_lookback_kernel(Pred pred, int n, pm_dmatch *out, int32_t *n_out,
-                                                              unsigned long long *status, unsigned *counter,
-                                                              unsigned epoch, unsigned long long *span,
-                                                              unsigned long long *chain_done, unsigned *chain_ctr,
-                                                              unsigned long long chain_seq, pm_gather_out g, L2FallbackArgs fb)
+                                                              unsigned long long *status, unsigned long long *counter,
+                                                              unsigned long long ticket_base, unsigned epoch,
+                                                              unsigned long long *span, unsigned long long *chain_done,
+                                                              unsigned *chain_ctr, unsigned long long chain_seq, pm_gather_out g)
 {
     __shared__ int s_tile, s_prefix;
     pm_span_mark(span, 12, false);
+    if (threadIdx.x == 0) s_tile = (int)(atomicAdd(counter, 1ull) - ticket_base);
     pm_pdl_prologue();
     pm_span_mark(span, 13, false);
-    if (threadIdx.x == 0) {
-        s_tile = (int)atomicAdd(&counter[epoch & 1u], 1u);
-        if (s_tile == 0) counter[(epoch + 1u) & 1u] = 0u;   // the next call's tickets (it starts after this kernel: stream order / PDL wait)
-    }
     __syncthreads();
-    int tile = s_tile;
-    if (WITH_FB) {
-        if (tile < fb.helpers) {
-            if (fb.is_u8) l2_fallback_items<uint8_t>(fb, tile, fb.helpers);
-            else l2_fallback_items<float>(fb, tile, fb.helpers);
-            pm_chain_signal(chain_done, chain_ctr, chain_seq);
-            return;
-        }
-        tile -= fb.helpers;
-        if (threadIdx.x == 0) {
-            const unsigned nf = (unsigned)max(fb.flags->n_flagged, 0);      // final: K3 completed before the wait above returned
-            if (nf) {
-                unsigned v;
-                do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&fb.flags->rows_fixed) : "memory"); } while (v < nf);
-            }
-        }
-        __syncthreads();
-    }
+    const int tile = s_tile;
     const int ntiles = (n + FB - 1) / FB;
+    if ((unsigned)tile >= (unsigned)ntiles) {      // cannot happen while host and device ticket counts agree; never spin on it
+        pm_chain_signal(chain_done, chain_ctr, chain_seq);
+        return;
+    }
     const int i = tile * FB + threadIdx.x;
     pm_dmatch m;
     const int f = i < n ? (int)pred(i, m) : 0;
@@ -176,8 +154,7 @@ __global__ void __launch_bounds__(FB) compact_lookback_kernel(Pred pred, int n, 
 
 template <class Pred>
 int run_compact(pm_ctx *ctx, Pred pred, int n, pm_dmatch *dout, int32_t *dn_out, unsigned long long *chain_done = nullptr,
-                unsigned *chain_ctr = nullptr, unsigned long long chain_seq = 0, const pm_gather_out *gather = nullptr,
-                const L2FallbackArgs *fbp = nullptr)
+                unsigned *chain_ctr = nullptr, unsigned long long chain_seq = 0, const pm_gather_out *gather = nullptr)
 {
     const pm_gather_out g = gather ? *gather : pm_gather_out{nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr};
     if (n <= 0) {
@@ -188,23 +165,30 @@ int run_compact(pm_ctx *ctx, Pred pred, int n, pm_dmatch *dout, int32_t *dn_out,
     const size_t need = (size_t)(nb + 2) * 8;
     const bool fresh = ctx->slot_bytes[WS_COUNT] < need;
     PM_WS(ctx, st, unsigned long long *, WS_COUNT, need);
-    if (fresh) {        // newly (re)allocated: all epochs 0 / counters 0
+    if (fresh) {        // newly (re)allocated: all epochs 0, ticket counter 0
         PM_CUDA(ctx, cudaMemsetAsync(st, 0, ctx->slot_bytes[WS_COUNT], ctx->stream));
         ctx->compact_epoch = 0;
+        ctx->compact_tickets = 0;
     }
     const unsigned epoch = ++ctx->compact_epoch;
     if (epoch >= (1u << 29)) {   // keep the 30-bit tag from wrapping into a stale match
         PM_CUDA(ctx, cudaMemsetAsync(st, 0, ctx->slot_bytes[WS_COUNT], ctx->stream));
         ctx->compact_epoch = 0;
-        return run_compact(ctx, pred, n, dout, dn_out, chain_done, chain_ctr, chain_seq, gather, fbp);
+        ctx->compact_tickets = 0;
+        return run_compact(ctx, pred, n, dout, dn_out, chain_done, chain_ctr, chain_seq, gather);
     }
-    unsigned *counter = reinterpret_cast<unsigned *>(st);          // st[0]: two ticket counters
-    if (fbp && fbp->helpers > 0)
-        PM_CUDA(ctx, pm_launch_pdl(compact_lookback_kernel<Pred, true>, dim3(nb + fbp->helpers), dim3(FB), 0, ctx->stream, pred, n, dout, dn_out,
-                                   st + 1, counter, epoch, g_pm_span, chain_done, chain_ctr, chain_seq, g, *fbp));
-    else
-        PM_CUDA(ctx, pm_launch_pdl(compact_lookback_kernel<Pred, false>, dim3(nb), dim3(FB), 0, ctx->stream, pred, n, dout, dn_out,
-                                   st + 1, counter, epoch, g_pm_span, chain_done, chain_ctr, chain_seq, g, L2FallbackArgs{}));
+    const unsigned long long base = ctx->compact_tickets;          // st[0]: the ticket counter of this ctx, never reset
+    const bool after_memset = base == 0;                            // the counter was just cleared by a memset on the stream
+    ctx->compact_tickets += (unsigned long long)nb;
+    if (after_memset) {
+        // the tickets are taken BEFORE griddepcontrol.wait: the first launch after the memset must not start early (a
+        // programmatic launch could take a ticket before the memset's stores are visible) -> plain stream order
+        compact_lookback_kernel<Pred><<<nb, FB, 0, ctx->stream>>>(pred, n, dout, dn_out, st + 1, st, base, epoch, g_pm_span,
+                                                                   chain_done, chain_ctr, chain_seq, g);
+    } else {
+        PM_CUDA(ctx, pm_launch_pdl(compact_lookback_kernel<Pred>, dim3(nb), dim3(FB), 0, ctx->stream, pred, n, dout, dn_out, st + 1,
+                                   st, base, epoch, g_pm_span, chain_done, chain_ctr, chain_seq, g));
+    }
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }
@@ -258,16 +242,15 @@ __global__ void gather_matches_kernel(const pm_dmatch *__restrict__ m, const int
 }  // namespace
 
 int pmk_ratio_filter(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout, int32_t *dn_out,
-                     const pm_gather_out *gather, const L2FallbackArgs *fb)
+                     const pm_gather_out *gather)
 {
-    return run_compact(ctx, RatioPred{dknn, ratio}, nq, dout, dn_out, nullptr, nullptr, 0, gather, fb);
+    return run_compact(ctx, RatioPred{dknn, ratio}, nq, dout, dn_out, nullptr, nullptr, 0, gather);
 }
 
 int pmk_ratio_filter_tail(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout, int32_t *dn_out,
-                          unsigned long long *chain_done, unsigned *chain_ctr, unsigned long long seq, const pm_gather_out *gather,
-                          const L2FallbackArgs *fb)
+                          unsigned long long *chain_done, unsigned *chain_ctr, unsigned long long seq, const pm_gather_out *gather)
 {
-    return run_compact(ctx, RatioPred{dknn, ratio}, nq, dout, dn_out, chain_done, chain_ctr, seq, gather, fb);
+    return run_compact(ctx, RatioPred{dknn, ratio}, nq, dout, dn_out, chain_done, chain_ctr, seq, gather);
 }
 
 int pmk_cross_check(pm_ctx *ctx, const pm_dmatch *dknn, int nq, int stride, const uint64_t *dcol_best, int nt,

@@ -291,7 +291,7 @@ ham_tc_finish_kernel(const L2Cand *__restrict__ part, int ncand, const uint32_t 
 {
     pm_pdl_prologue();
     const int lane = threadIdx.x & 31, sub = lane & 7;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *flags_next = L2Flags{0, 0u, 0u, 0, 0u, {0, 0, 0}};
+    if (blockIdx.x == 0 && threadIdx.x == 0) *flags_next = L2Flags{0, 0u, 0u, 0, 0u, 0u, 0, {0}};
     const int ngroups = gridDim.x * (blockDim.x >> 3);
     const int nq_round = (nq + 3) & ~3;
     for (int i = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); i < nq_round; i += ngroups) {

@@ -34,9 +34,9 @@ __device__ __forceinline__ float warp_sum_butterfly(float p)
 template <typename T> __device__ __forceinline__ float load_elem(const T *p, size_t i) { return (float)p[i]; }
 
 // ---------------------------------------------------------------------------------
-// K1: one warp per row, query and train rows in ONE launch (rows [0, mq_pad) are query
+// K1: 8 lanes per row, query and train rows in ONE launch (rows [0, mq_pad) are query
 // rows, the rest train rows).  Writes [hi|lo] bf16 (train rows pre-scaled by -2),
-// ||row||^2 (train pad rows: +inf), the integer-valued flag, the max norms, and (query
+// ||row||^2 (train pad rows: 1.7e38 inside K2's norm image), the integer-valued flag, the max norms, and (query
 // side) the +inf candidate init.  Pure streaming: 16 B loads, 8 B stores per lane.
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void load_row4(const float *p, int lane, int dim, bool vec, float (&x)[4])
@@ -307,32 +307,59 @@ __device__ __forceinline__ float group_l2sq(unsigned gmask, const float (&a)[4][
     return r;
 }
 
-// Exact FP32 scan of the rows K3 flagged (split mode; exits at once when there are none).  Barrier-free, see
-// l2_fallback.cuh.
-template <typename T>
-__global__ void __launch_bounds__(256)
-l2_fallback_kernel(L2FallbackArgs A)
-{
-    pm_pdl_prologue();
-    l2_fallback_items<T>(A, (int)blockIdx.x, (int)gridDim.x);
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256, 3)
 l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__restrict__ qnorm,
                  const uint8_t *__restrict__ q8, const uint8_t *__restrict__ t8, const float *__restrict__ tnorm,
                  const T *__restrict__ q, const T *__restrict__ t, int nq, int nt, int dim, int vec,
                  L2Flags *flags, L2Flags *flags_next, int *__restrict__ flagged,
-                 int q_index_base, pm_dmatch *__restrict__ out, unsigned long long *span)
+                 int q_index_base, pm_dmatch *__restrict__ out, unsigned long long *span, int row_blocks, L2FallbackArgs fb)
 {
+    // Blocks [0, row_blocks) classify the rows; blocks past them are HELPERS of the split-mode fallback scan (see the tail
+    // of this kernel).  A row block announces itself before the wait below, so that a helper -- which looks after its
+    // own wait -- sees every row block that was resident by then.
+    __shared__ int s_role;
+    const bool is_helper = (int)blockIdx.x >= row_blocks;
+    if (!is_helper && threadIdx.x == 0) atomicAdd(&flags->rows_started, 1u);
     pm_span_mark(span, 6, false);
     pm_pdl_prologue();
     pm_span_mark(span, 7, false);
+    if (is_helper) {
+        if (l2_exact_mode(*flags)) return;                 // exact-integer data: no row is ever flagged
+        if (threadIdx.x == 0) {
+            // stay only if EVERY row block has started (then waiting for them cannot starve them); else the last row
+            // block to finish, which takes the same work queue, completes the scan without this helper.  The row blocks'
+            // announcements may still be in flight when a helper dispatched right behind them looks, so it looks for a
+            // bounded time (~50 us at most, then it leaves: a bounded wait cannot deadlock anything)
+            unsigned v = 0;
+            for (int spin = 0; spin < 512; ++spin) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&flags->rows_started) : "memory");
+                if (v >= (unsigned)row_blocks) break;
+                __nanosleep(100);
+            }
+            int stay = v >= (unsigned)row_blocks;
+            if (stay) {
+                // every row block is running: they finish in a few microseconds.  (Bounded all the same -- ~0.3 s -- so
+                // that no fault elsewhere can turn this wait into a hang; a helper that gives up leaves the scan to the
+                // last row block.)
+                int spin = 0;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&flags->rows_done) : "memory");
+                    if (v < (unsigned)row_blocks) __nanosleep(64);
+                } while (v < (unsigned)row_blocks && ++spin < (1 << 22));
+                stay = v >= (unsigned)row_blocks;
+            }
+            s_role = stay;
+        }
+        __syncthreads();
+        if (s_role) l2_fallback_items<T>(fb);
+        return;
+    }
     if (span && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); span[32 + 2 * blockIdx.x] = tt; }
     const int lane = threadIdx.x & 31, sub = lane & 7;
     const unsigned gmask = 0xFFu << (lane & 24);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *flags_next = L2Flags{0, 0u, 0u, 0, 0u, {0, 0, 0}};   // the next call's block
-    const int ngroups = gridDim.x * (blockDim.x >> 3);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *flags_next = L2Flags{0, 0u, 0u, 0, 0u, 0u, 0, {0}};   // the next call's block
+    const int ngroups = row_blocks * (blockDim.x >> 3);
     const int nq_round = (nq + 3) & ~3;              // whole warps stay in the loop together (group shuffles)
     for (int i = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); i < nq_round; i += ngroups) {
         const bool live_row = i < nq;
@@ -441,10 +468,22 @@ l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__rest
             if (sub == 0 && !certified) flagged[atomicAdd(&flags->n_flagged, 1)] = i;
         }
     }
-    // Split mode only: rows K3 could not certify (flagged[0 .. n_flagged)) get an exact FP32 scan of the whole train
-    // set from the NEXT kernel of the chain (l2_fallback.cuh): l2_fallback_kernel below, or the helper blocks of the
-    // ratio-filter kernel.  (An earlier version ran that scan here behind a hand-rolled grid barrier, which assumed
-    // that every block of this kernel is resident at once -- not guaranteed beside other streams.)
+    // Split mode only: rows that could not be certified (flagged[0 .. n_flagged)) get an exact FP32 scan of the whole
+    // train set (l2_fallback.cuh).  The list is complete once every row block has passed the counter below; the helper
+    // blocks wait for exactly that, and the last row block to arrive takes part as well, so the scan completes whatever
+    // the helpers did.  Nobody waits for a block that may not have started.  (An earlier version ran the scan behind a
+    // hand-rolled grid barrier, which assumed that the whole grid is resident at once -- not guaranteed beside other
+    // streams, e.g. the lanes of the batched pair call.)
+    if (!l2_exact_mode(*flags)) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_role = atomicAdd(&flags->rows_done, 1u) == (unsigned)(row_blocks - 1);
+            if (s_role) __threadfence();
+        }
+        __syncthreads();
+        if (s_role) l2_fallback_items<T>(fb);
+    }
     if (span && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); span[33 + 2 * blockIdx.x] = tt; }
     pm_span_mark(span, 8, true);
 }
@@ -500,9 +539,10 @@ float *pm_l2_dump_ptr() { return g_l2_dump; }
 // Force the exact FP32 kernel for every row (parity cross-check of the two paths).
 static int g_l2_force_exact = 0;
 extern "C" void pm_debug_force_exact(int on) { g_l2_force_exact = on; }
-// A/B switch: run the fallback scan as a kernel of its own in the one-call chain as well (instead of helper blocks)
-static int g_l2_fb_separate = 0;
-extern "C" void pm_debug_fallback_separate(int on) { g_l2_fb_separate = on; }
+// A/B switch: no helper blocks -- the last row block of K3 runs the whole fallback scan alone (the path taken when the
+// helpers find that not every row block is resident)
+static int g_l2_fb_no_helpers = 0;
+extern "C" void pm_debug_fallback_no_helpers(int on) { g_l2_fb_no_helpers = on; }
 
 int l2_flags_acquire(pm_ctx *ctx, L2Flags **cur, L2Flags **zero_next, L2Flags **tflags, bool advance)
 {
@@ -611,9 +651,12 @@ static int l2_chain(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt,
     L2FallbackArgs fb;
     fb.q = dq; fb.t = dt; fb.is_u8 = is_u8; fb.nq = nq; fb.nt = nt; fb.dim = dim; fb.vec = vec; fb.q_index_base = q_index_base;
     fb.flags = flags; fb.flagged = flagged; fb.fb_part = fbpart;
-    fb.fb_cnt = reinterpret_cast<unsigned *>(fbpart + 4 * L2FB_MAX_GRID); fb.out = dout; fb.helpers = 0;
-    // K3: 8 lanes per row, 32 rows per block, at most one resident wave (a second wave would double its latency)
+    fb.fb_cnt = reinterpret_cast<unsigned *>(fbpart + 4 * L2FB_MAX_GRID); fb.out = dout;
+    // K3: 8 lanes per row, 32 rows per block, at most one resident wave of row blocks (a second wave would double its
+    // latency), plus the helper blocks of the split-mode fallback scan (they leave at once in exact-integer mode)
     const int fin_blocks = min(pm_cdiv(nq, 32), 3 * ctx->num_sms);
+    const int fin_helpers = g_l2_fb_no_helpers ? 0 : min(max(3 * ctx->num_sms - fin_blocks, ctx->num_sms), L2FB_MAX_GRID - 1);
+    fb.workers = fin_helpers + 1;
     const int pack_nt = phase == 2 ? 0 : nt, pack_nt_pad = phase == 2 ? 0 : nt_pad;
     const L2Flags *tflags_in = phase == 2 ? tflags : nullptr;
     const int pack_blocks = min(pm_cdiv(mq_pad + pack_nt_pad, 32), 8 * ctx->num_sms);
@@ -632,32 +675,20 @@ static int l2_chain(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt,
                           run_ahead ? chain_done : nullptr, run_ahead ? seq - 1 : 0, signalling ? chain_mark : nullptr, seq);
     if (st != PM_OK) return st;
     if (is_u8)
-        PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<uint8_t>, dim3(fin_blocks), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,
+        PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<uint8_t>, dim3(fin_blocks + fin_helpers), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,
                                    (const float *)qnorm, (const uint8_t *)q8, (const uint8_t *)t8, (const float *)tnormf,
                                    (const uint8_t *)dq, (const uint8_t *)dt, nq, nt, dim, vec_u8, flags, flags_next, flagged,
-                                   q_index_base, dout, g_pm_span));
+                                   q_index_base, dout, g_pm_span, fin_blocks, fb));
     else
-        PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<float>, dim3(fin_blocks), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,
+        PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<float>, dim3(fin_blocks + fin_helpers), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,
                                    (const float *)qnorm, (const uint8_t *)q8, (const uint8_t *)t8, (const float *)tnormf,
                                    (const float *)dq, (const float *)dt, nq, nt, dim, vec_f32, flags, flags_next, flagged,
-                                   q_index_base, dout, g_pm_span));
+                                   q_index_base, dout, g_pm_span, fin_blocks, fb));
     PM_CHECK_LAUNCH(ctx);
     ctx->l2_stats[3] = smax;
-    if (!dgood || g_l2_fb_separate) {
-        // kNN-only chain: the exact scan of the flagged rows is a kernel of its own (returns at once in exact mode)
-        const int fb_blocks = min(2 * ctx->num_sms, L2FB_MAX_GRID);
-        if (is_u8) PM_CUDA(ctx, pm_launch_pdl(l2_fallback_kernel<uint8_t>, dim3(fb_blocks), dim3(256), 0, ctx->stream, fb));
-        else PM_CUDA(ctx, pm_launch_pdl(l2_fallback_kernel<float>, dim3(fb_blocks), dim3(256), 0, ctx->stream, fb));
-        PM_CHECK_LAUNCH(ctx);
-        if (!dgood) return PM_OK;
-    } else {
-        // one-call kNN-2 + ratio chain: helper blocks of the filter kernel run the scan, its tiles wait for them
-        fb.helpers = max(ctx->num_sms - pm_cdiv(nq, 1024), ctx->num_sms / 4);
-        if (fb.helpers > L2FB_MAX_GRID) fb.helpers = L2FB_MAX_GRID;
-    }
-    const L2FallbackArgs *fbp = fb.helpers ? &fb : nullptr;
-    if (!signalling) return pmk_ratio_filter(ctx, dout, nq, ratio, dgood, dn_good, gather, fbp);
-    st = pmk_ratio_filter_tail(ctx, dout, nq, ratio, dgood, dn_good, chain_done, chain_ctr, seq, gather, fbp);
+    if (!dgood) return PM_OK;
+    if (!signalling) return pmk_ratio_filter(ctx, dout, nq, ratio, dgood, dn_good, gather);
+    st = pmk_ratio_filter_tail(ctx, dout, nq, ratio, dgood, dn_good, chain_done, chain_ctr, seq, gather);
     if (st != PM_OK) return st;
     ctx->chain_seq = seq;
     ctx->tail_is_chain = true;              // cleared by the next launch of any other kind (PM_CHECK_LAUNCH)

@@ -27,8 +27,10 @@ struct L2Flags {
     unsigned max_tnorm_bits;   // max ||b||^2 over real train rows (float bits)
     unsigned max_qnorm_bits;   // max ||a||^2 over real query rows (float bits)
     int n_flagged;             // rows K3 could not certify -> exact fallback
-    unsigned rows_fixed;       // flagged rows the fallback scan has rewritten (l2_fallback.cuh)
-    int pad[3];
+    unsigned rows_done;        // K3 (split mode): row blocks that have finished classifying their rows
+    unsigned rows_started;     // K3 (split mode): row blocks that have started
+    int next_item;             // work queue of the fallback scan (l2_fallback.cuh)
+    int pad[1];
 };
 
 // exact-integer mode: integer-valued data and norms small enough for the biased key

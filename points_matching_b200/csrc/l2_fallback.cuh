@@ -1,12 +1,10 @@
 // l2_fallback.cuh -- exact FP32 kNN-2 scan for the query rows the split-mode finish kernel (K3, l2.cu) could not
-// certify.  Barrier-free: the work is a list of (flagged row, train segment) items taken with a grid stride, every
-// item leaves its top-2 in a scratch slot, and the block that completes a row's LAST segment merges the row (a
-// per-row countdown), so no block ever waits for another one -- the kernels that run this never assume that their
-// whole grid is resident at once.  Two callers:
-//   l2_fallback_kernel (l2.cu)           a kernel of its own after K3 in the kNN-only chain
-//   compact_lookback_kernel (filter.cu)  "helper" blocks of the ratio-filter kernel in the one-call kNN-2 + ratio
-//                                        chain: the first H tickets run this, the tiles wait until every flagged row
-//                                        has been fixed (they only wait on blocks that have already started)
+// certify.  Barrier-free in the sense that matters: no block ever waits for a block that may not have started.  The work
+// is a list of (flagged row, train segment) items handed out by an atomic counter to whatever blocks take part; every item
+// leaves its top-2 in a scratch slot and the block that completes a row's LAST segment merges the row (a per-row
+// countdown).  K3 runs it in its own tail (l2_finish_kernel): extra "helper" blocks that first check that every row block
+// has STARTED (else they leave), then wait for the row blocks to finish; the last row block to finish takes part as well,
+// so the scan completes even if no helper stayed.
 // Distances follow the "re-rank order" of l2.cu / DESIGN.md bit for bit (the same group_l2sq).
 #pragma once
 #include "pm_internal.h"
@@ -15,12 +13,12 @@
 struct L2FallbackArgs {
     const void *q, *t;            // raw descriptors (f32 or u8 rows of `dim` elements)
     int is_u8, nq, nt, dim, vec, q_index_base;
-    L2Flags *flags;               // n_flagged (K3 wrote it), rows_fixed (counted up here)
+    L2Flags *flags;               // n_flagged (the row blocks wrote it), next_item (the work queue)
     const int *flagged;           // [n_flagged] query rows
     unsigned long long *fb_part;  // [<= 2 * items] per-item (best, second) keys
     unsigned *fb_cnt;             // [n_flagged when a row is split] segments done; returns to zero
     pm_dmatch *out;               // [nq][2]
-    int helpers;                  // filter.cu: number of helper blocks (0: none)
+    int workers;                  // blocks expected to take part (sizes the split of a row into segments)
 };
 
 // the scan runs on at most this many blocks (grid stride); bounds the scratch: < 2 * L2FB_MAX_GRID items of two
@@ -85,14 +83,17 @@ __device__ __forceinline__ uint4 l2fb_record(int qidx, unsigned long long w)
                                    __float_as_uint(sqrtf(__uint_as_float((unsigned)(w >> 32)))));
 }
 
-// Runs the items `first, first + stride, ...` (whole block; blockDim.x a multiple of 32, <= 1024).
+// Takes items from the queue until it is empty (whole block; blockDim.x a multiple of 32, <= 1024).  n_flagged must be
+// final: call it only once every row block is known to have finished.
 template <typename T>
-__device__ void l2_fallback_items(const L2FallbackArgs &A, int first, int stride)
+__device__ void l2_fallback_items(const L2FallbackArgs &A)
 {
     __shared__ float x_qs[L2_KDIM];
     __shared__ unsigned long long x_k[L2FB_MAX_WARPS][2];
+    __shared__ int x_item;
     const int nf = *reinterpret_cast<volatile int *>(&A.flags->n_flagged);
     if (nf <= 0) return;
+    const int stride = A.workers > 0 ? A.workers : 1;
     const T *q = reinterpret_cast<const T *>(A.q), *t = reinterpret_cast<const T *>(A.t);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, sub = lane & 7, g = lane >> 3;
     const int chunk = nwarps * 32;                                  // train rows per pass of the block
@@ -103,10 +104,14 @@ __device__ void l2_fallback_items(const L2FallbackArgs &A, int first, int stride
     const int seg_chunks = (nchunk + split - 1) / split;
     split = (nchunk + seg_chunks - 1) / seg_chunks;
     const int items = nf * split;
-    for (int item = first; item < items; item += stride) {
-        const int r = item / split, sg = item - r * split;
-        const int i = A.flagged[r];
+    for (;;) {
         __syncthreads();
+        if (threadIdx.x == 0) x_item = atomicAdd(&A.flags->next_item, 1);
+        __syncthreads();
+        const int item = x_item;
+        if (item >= items) break;
+        const int r = item / split, sg = item - r * split;
+        const int i = *reinterpret_cast<volatile const int *>(&A.flagged[r]);
         if (threadIdx.x < L2_KDIM) x_qs[threadIdx.x] = (int)threadIdx.x < A.dim ? (float)q[(size_t)i * A.dim + threadIdx.x] : 0.f;
         __syncthreads();
         float a[4][4];
@@ -162,8 +167,6 @@ __device__ void l2_fallback_items(const L2FallbackArgs &A, int first, int stride
                 uint4 *o = reinterpret_cast<uint4 *>(A.out + (size_t)i * 2);
                 o[0] = l2fb_record(i + A.q_index_base, m0);
                 o[1] = l2fb_record(i + A.q_index_base, m1);
-                __threadfence();
-                atomicAdd(&A.flags->rows_fixed, 1u);
             }
         }
     }

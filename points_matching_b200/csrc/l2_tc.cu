@@ -10,6 +10,10 @@
 // after selection, and ||b_j||^2 (plus the key bias) rides in the GEMM itself: one extra
 // K=16 MMA step multiplies a constant [1 1 1 0...] row block by the column norm split
 // exactly into three bf16 terms, so the epilogue does no arithmetic on the distance at all.
+// (Measured alternative: letting the epilogue warps write the column constants into the drained accumulator with
+// tcgen05.st and accumulating from there saves those 2 of 18 tensor-pipe dispatches per item but doubles the
+// epilogue's TMEM traffic -- 1090 instead of 1230 cycles of MMA issue per item, 1300-1700 instead of 880 cycles of
+// epilogue: the kernel went from 21.4 to 27.2 us.)
 // Operands are bf16 "hi|lo" rows written by K1 (l2.cu):
 //   exact-integer mode (SIFT, values 0..255): lo == 0, 2 k-blocks, the GEMM is exact
 //   split mode (general floats):  a.b ~ ah.bh + ah.bl + al.bh, 6 k-blocks
@@ -18,24 +22,24 @@
 // memory and every B k-block that TMA brings in feeds both, which halves the L2 -> SM operand
 // traffic (the binding resource for K = 128: ncu measured 4.4 TB/s of TMA reads with one A tile).
 //
-// Structure (one persistent CTA per SM, 576 threads):
-//   warp 0      TMA producer   : 2 A row-tiles resident (2 x <= 4 x 16 KB), B k-blocks through
-//                                a 4-stage 16 KB ring (cp.async.bulk.tensor, SWIZZLE_128B)
-//   warp 1      MMA issuer     : tcgen05.mma cta_group::1 kind::f16, M=128 N=128 K=16, one
-//                                accumulator per A tile, double-buffered in TMEM (2 x 2 x 128
-//                                columns); also allocates / frees TMEM
-//   warps 2-17  epilogue       : 4 warps per scheduler, each owns 32 rows x 64 columns of a
-//                                work item: tcgen05.ld 32x32b.x32, pack (value | column) into one
-//                                u32 key (IMAD / PRMT), branch-free min/max
-//                                tournament (VIMNMX/VIMNMX3) over adjacent column PAIRS: top-2
-//                                pair minima in exact mode, top-3 in split mode, kept in
-//                                registers across the sweep (K3 re-checks the partners exactly).
+// Structure (one persistent CTA per SM, 608 threads):
+//   warp 0      TMA producer   : 2 A row-tiles resident (k-block major, one mbarrier per k-block pair so the first
+//                                MMAs start when half of A has landed), B stages (two 16 KB k-blocks + the 4 KB norm
+//                                image) through a ring; the first loads go out right after griddepcontrol.wait,
+//                                before anything else of the prologue
+//   warps 1, 18 MMA issuers    : tcgen05.mma cta_group::1 kind::f16, M=128 N=128 K=16, one accumulator per A tile,
+//                                double-buffered in TMEM (2 x 2 x 128 columns); warp 1 allocates / frees TMEM
+//   warps 2-17  epilogue       : 4 warps per scheduler, each owns 32 rows x 64 columns of a work item:
+//                                tcgen05.ld 32x32b.x32, quad minima on the raw bits, branch-free min/max
+//                                tournament (VIMNMX/VIMNMX3): top-2 quad minima in exact mode, top-3 pair minima in
+//                                split mode, kept in registers across the sweep (K3 re-checks the members exactly).
 // Each CTA walks a contiguous range of the (row-tile, column-tile) space; per row tile it
 // writes one "segment" of candidates which K3 merges, re-ranks in FP32 and certifies.
 #include <cuda.h>
 #include <cstdlib>
 #include <cuda_bf16.h>
 #include <atomic>
+#include <vector>
 #include "pm_internal.h"
 #include "l2_common.h"
 
@@ -46,7 +50,10 @@ constexpr int MH = 2;                        // A row-tiles (m-halves) per work 
 constexpr int BLK_BYTES = BM * BK * 2;       // 16 KB: one 128-row x 64-column bf16 k-block of A or B
 constexpr int EXT_BYTES = BN * 32;           // 4 KB: K=16 "ext" operand (norm step), K-major, no swizzle
 constexpr int STAGE_BYTES = 2 * BLK_BYTES + EXT_BYTES;   // a B stage: two k-blocks (K = 128) + the norm operand of the tile
-constexpr int AB_BYTES = 212992;             // A tiles + B ring: exact 64 KB + 4 x 36 KB, split 128 KB + 2 x 36 KB
+// A blocks (k-block major: block (kb, h) at (kb * MH + h) * 16 KB) grow up from 0: 64 KB exact, 128 KB split.
+// B stages grow DOWN from the top: stage s at AB_BYTES - (s + 1) * 36 KB, so stages 0 and 1 sit at the same
+// addresses in both modes (the first loads are issued before the mode is known); exact: 4 stages, split: 2.
+constexpr int AB_BYTES = 212992;
 constexpr int EPI_WARP0 = 2;        // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-17 epilogue
 constexpr int EPI_WARPS = 16;       // 4 per scheduler: enough TLP to keep the issue slots busy
 constexpr int EPI_THREADS = EPI_WARPS * 32;
@@ -284,7 +291,8 @@ struct TcParams {
     L2Cand *part;                // [mq_pad][smax][3]; MT counts 256-row super tiles
     float *dump;                 // debug: [mq_pad][nt_pad] of (||b||^2 - 2ab), or null
     int MT, NT, smax, nt_pad;
-    int tq, tr;                  // work items per CTA: CTA c owns tq + (c < tr) consecutive items (T = G * tq + tr)
+    const int *sched;            // [G][4]: first item, item count, segment slot of the CTA's first row tile (l2_tc_schedule)
+    int trace_cta;               // PM_K2_TRACE builds: the CTA that stamps
     const unsigned long long *chain_done;   // chain pipelining: spin until *chain_done >= wait_seq (null: no spin)
     unsigned long long wait_seq;
     unsigned long long *chain_mark;         // signalling chains: store mark_seq once past the waits (null: none)
@@ -295,14 +303,14 @@ struct TcParams {
 };
 
 #ifdef PM_K2_TRACE
-#define TR(slot) do { if (P.trace && blockIdx.x == 0 && lane == 0 && lt < 64) P.trace[lt * 16 + (slot)] = clock64(); } while (0)
-#define TRE(slot) do { if (P.trace && blockIdx.x == 0 && e == 0 && lane == 0 && lt < 64) P.trace[lt * 16 + (slot)] = clock64(); } while (0)
+#define TR(slot) do { if (P.trace && (int)blockIdx.x == P.trace_cta && lane == 0 && lt < 64) P.trace[lt * 16 + (slot)] = clock64(); } while (0)
+#define TRE(slot) do { if (P.trace && (int)blockIdx.x == P.trace_cta && e == 0 && lane == 0 && lt < 64) P.trace[lt * 16 + (slot)] = clock64(); } while (0)
 #else
 #define TR(slot) do { } while (0)
 #define TRE(slot) do { } while (0)
 #endif
 #ifdef PM_K2_TRACE
-#define TRK(slot) do { if (P.trace && blockIdx.x == 0 && threadIdx.x == (slot >= 4 ? EPI_WARP0 * 32 : 32)) P.trace[63 * 16 + (slot)] = clock64(); } while (0)
+#define TRK(slot) do { if (P.trace && (int)blockIdx.x == P.trace_cta && threadIdx.x == (slot >= 4 ? EPI_WARP0 * 32 : 32)) P.trace[63 * 16 + (slot)] = clock64(); } while (0)
 #else
 #define TRK(slot) do { } while (0)
 #endif
@@ -319,34 +327,36 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     uint8_t *sgen = smem_raw + (sbase - smem_u32(smem_raw));
     const uint32_t sA = sbase + SMEM_A, sBar = sbase + SMEM_BAR;
     const uint32_t bar_full = sBar, bar_empty = sBar + 32;       // [4] each: B stage loaded / consumed
-    const uint32_t bar_afull = sBar + 64, bar_aempty = sBar + 72;
-    const uint32_t bar_tfull = sBar + 80, bar_tempty = sBar + 96;  // [2]: accumulator ready / drained
+    const uint32_t bar_ak0 = sBar + 64, bar_ak1 = sBar + 72;     // A hi k-block 0 / 1 (both row tiles) loaded
+    const uint32_t bar_alo = sBar + 80, bar_aempty = sBar + 88;  // A lo k-blocks loaded (split mode) / A consumed
+    const uint32_t bar_tfull = sBar + 96, bar_tempty = sBar + 112;  // [2]: accumulator ready / drained
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(sgen + SMEM_BAR + 128);
     const uint32_t sExtA = sbase + SMEM_EXTA;
     L2Cand *scratch = reinterpret_cast<L2Cand *>(sgen + SMEM_SCRATCH);
+    auto stage_addr = [&](int st) { return sA + (uint32_t)(AB_BYTES - (st + 1) * STAGE_BYTES); };
+    constexpr int KBW = FP8 ? 2 * BK : BK;     // tensor-map columns per k-block (elements)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TRK(0);
 
     // ---- setup that does not depend on the previous kernel: overlaps its tail under PDL ----
     const int cta = (int)blockIdx.x;
-    const int t_begin = cta * P.tq + min(cta, P.tr);
-    const int ntiles = P.tq + (cta < P.tr ? 1 : 0);
+    const int4 sch = __ldg(reinterpret_cast<const int4 *>(P.sched) + cta);     // written by the host before this chain was enqueued
+    const int t_begin = sch.x, ntiles = sch.y;
     const int NT = P.NT;
     const int m_first = t_begin / NT, n_first = t_begin - m_first * NT;   // the only divisions: per-role counters follow
     if (warp == 0 && lane == 0) {
+        // the producer initialises the barriers itself: it is their first user (the loads below), everybody else
+        // meets them after the block-wide sync further down
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_q)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_t)) : "memory");
+        for (int s = 0; s < 4; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_ak0, 1); mbar_init(bar_ak1, 1); mbar_init(bar_alo, 1);
+        mbar_init(bar_aempty, 2);                       // one arrival from each MMA issuer
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        if (lane == 0) {
-            for (int s = 0; s < 4; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-            mbar_init(bar_afull, 1);
-            mbar_init(bar_aempty, 2);                       // one arrival from each MMA issuer
-            for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, EPI_WARPS); }
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32((const void *)tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -362,13 +372,23 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     if (P.chain_mark && blockIdx.x == 0 && threadIdx.x == 0)
         asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(P.chain_mark), "l"(P.mark_seq) : "memory");
     pm_span_mark(P.span, 4, false);      // K1's outputs (flags, packed operands, norm images) are complete past this point
+    // First loads, issued by the thread that waited above, before the flags are even read: the hi k-blocks of the first
+    // row tile's A and the first B stage (hi k-blocks + norm image) have the same shared-memory addresses in both modes.
+    if (warp == 0 && lane == 0 && ntiles > 0) {
+        mbar_expect_tx(bar_full, (uint32_t)STAGE_BYTES);
+        bulk_load_1d(stage_addr(0) + 2 * BLK_BYTES, P.text + (size_t)n_first * EXT_BYTES, EXT_BYTES, bar_full);
+        mbar_expect_tx(bar_ak0, (uint32_t)(MH * BLK_BYTES));
+        for (int h = 0; h < MH; ++h) tma_load_2d(sA + (0 * MH + h) * BLK_BYTES, &tmap_q, bar_ak0, 0, (m_first * MH + h) * BM);
+        tma_load_2d(stage_addr(0), &tmap_t, bar_full, 0, n_first * BN);
+        mbar_expect_tx(bar_ak1, (uint32_t)(MH * BLK_BYTES));
+        for (int h = 0; h < MH; ++h) tma_load_2d(sA + (1 * MH + h) * BLK_BYTES, &tmap_q, bar_ak1, KBW, (m_first * MH + h) * BM);
+        tma_load_2d(stage_addr(0) + BLK_BYTES, &tmap_t, bar_full, KBW, n_first * BN);
+    }
     TRK(2);
     const L2Flags fl = *P.flags;
     const bool exact = l2_exact_mode(fl);
     const int nsp = exact ? 1 : 3;           // B stages (k-block pairs) per work item
-    const int nablk = exact ? 2 : 4;         // k-blocks per A row tile: hi0 hi1 (lo0 lo1)
     const int nstage = exact ? 4 : 2;        // B ring depth
-    const uint32_t sB = sA + (uint32_t)(MH * nablk * BLK_BYTES);   // A: 64 KB (exact) / 128 KB (split)
     const float shift = l2_split_shift(fl.max_qnorm_bits);
     const float nb_off = exact ? L2_EXACT_BIAS : shift;            // bias folded into the norm step
 
@@ -389,37 +409,45 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
-        {
-            int m = m_first, n = n_first, cur_m = -1;
-            int stage = 0; uint32_t sphase = 0, apar = 0;
-            for (int lt = 0; lt < ntiles; ++lt) {
-                if (m != cur_m) {
-                    if (cur_m >= 0) { mbar_wait(bar_aempty, apar); apar ^= 1; }    // every MMA of the old row tile is done
-                    if (elect_one()) {
-                        mbar_expect_tx(bar_afull, (uint32_t)(MH * nablk * BLK_BYTES));
-                        for (int h = 0; h < MH; ++h)
-                            for (int kb = 0; kb < nablk; ++kb)
-                                tma_load_2d(sA + (h * nablk + kb) * BLK_BYTES, &tmap_q, bar_afull, kb * (FP8 ? 2 * BK : BK), (m * MH + h) * BM);
+        int m = m_first, n = n_first, cur_m = -1;
+        int stage = 0; uint32_t sphase = 0, apar = 0;
+        for (int lt = 0; lt < ntiles; ++lt) {
+            if (m != cur_m) {
+                if (cur_m >= 0) { mbar_wait(bar_aempty, apar); apar ^= 1; }    // every MMA of the old row tile is done
+                if (elect_one()) {
+                    if (lt > 0) {                                               // (the first row tile's hi blocks are on their way)
+                        mbar_expect_tx(bar_ak0, (uint32_t)(MH * BLK_BYTES));
+                        for (int h = 0; h < MH; ++h) tma_load_2d(sA + (0 * MH + h) * BLK_BYTES, &tmap_q, bar_ak0, 0, (m * MH + h) * BM);
+                        mbar_expect_tx(bar_ak1, (uint32_t)(MH * BLK_BYTES));
+                        for (int h = 0; h < MH; ++h) tma_load_2d(sA + (1 * MH + h) * BLK_BYTES, &tmap_q, bar_ak1, KBW, (m * MH + h) * BM);
                     }
-                    __syncwarp();
-                    cur_m = m;
+                    if (!exact) {
+                        mbar_expect_tx(bar_alo, (uint32_t)(2 * MH * BLK_BYTES));
+                        for (int kb = 2; kb < 4; ++kb)
+                            for (int h = 0; h < MH; ++h)
+                                tma_load_2d(sA + (kb * MH + h) * BLK_BYTES, &tmap_q, bar_alo, kb * KBW, (m * MH + h) * BM);
+                    }
                 }
-                for (int sp = 0; sp < nsp; ++sp) {
-                    mbar_wait(bar_empty + 8 * stage, sphase ^ 1);
-                    if (elect_one()) {
-                        const uint32_t fb = bar_full + 8 * stage, dst = sB + stage * STAGE_BYTES;
+                __syncwarp();
+                cur_m = m;
+            }
+            for (int sp = 0; sp < nsp; ++sp) {
+                mbar_wait(bar_empty + 8 * stage, sphase ^ 1);
+                if (elect_one()) {
+                    const uint32_t fb = bar_full + 8 * stage, dst = stage_addr(stage);
+                    if (lt > 0 || sp > 0) {                                     // (the very first stage is on its way)
                         mbar_expect_tx(fb, sp == 0 ? STAGE_BYTES : 2 * BLK_BYTES);
                         // stages: hi0 hi1 (+ norm image) | lo0 lo1 | hi0 hi1   (packed row = [hi 0..127 | lo 128..255])
-                        const int kc = sp == 1 ? 128 : 0;
+                        const int kc = sp == 1 ? 2 * KBW : 0;
                         tma_load_2d(dst, &tmap_t, fb, kc, n * BN);
-                        tma_load_2d(dst + BLK_BYTES, &tmap_t, fb, kc + (FP8 ? 2 * BK : BK), n * BN);
+                        tma_load_2d(dst + BLK_BYTES, &tmap_t, fb, kc + KBW, n * BN);
                         if (sp == 0) bulk_load_1d(dst + 2 * BLK_BYTES, P.text + (size_t)n * EXT_BYTES, EXT_BYTES, fb);
                     }
-                    __syncwarp();
-                    if (++stage == nstage) { stage = 0; sphase ^= 1; }
                 }
-                if (++n == NT) { n = 0; ++m; }
+                __syncwarp();
+                if (++stage == nstage) { stage = 0; sphase ^= 1; }
             }
+            if (++n == NT) { n = 0; ++m; }
         }
     } else if (warp == 1 || warp == ISS2_WARP) {
         // ===================== MMA issuers (whole warp converged, one elected lane issues) =====================
@@ -431,35 +459,40 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         int m = m_first, n = n_first + x;
         if (n >= NT) { n -= NT; ++m; }
         const uint64_t extA = make_sdesc_ext(sExtA);
-        auto issue_stage = [&](int sp, uint32_t d_tmem, uint32_t sb) {
-            if (sp == 0) {
+        auto issue_kblock = [&](int sp, int kk, uint32_t d_tmem, uint32_t sb) {
+            if (sp == 0 && kk == 0) {
                 // norm step first (overwrites): acc = [1 1 1 bias..] x [split3(||b||^2) 1 1 1 ..]
                 const uint64_t extB = make_sdesc_ext(sb + 2 * BLK_BYTES);
 #pragma unroll
                 for (int h = 0; h < MH; ++h) umma_bf16(d_tmem + h * BN, extA, extB, IDESC, 0u);
             }
+            // A block: hi for stages 0,1 (x B hi, x B lo), lo for stage 2 (x B hi)
+            const int ablk = (sp == 2 ? 2 : 0) + kk;
+            const uint64_t bdesc = make_sdesc(sb + kk * BLK_BYTES);
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                // A block: hi for stages 0,1 (x B hi, x B lo), lo for stage 2 (x B hi)
-                const int ablk = (sp == 2 ? 2 : 0) + kk;
-                const uint64_t bdesc = make_sdesc(sb + kk * BLK_BYTES);
+            for (int h = 0; h < MH; ++h) {      // the same B k-block feeds both A tiles
+                const uint64_t adesc = make_sdesc(sA + (ablk * MH + h) * BLK_BYTES);
 #pragma unroll
-                for (int h = 0; h < MH; ++h) {      // the same B k-block feeds both A tiles
-                    const uint64_t adesc = make_sdesc(sA + (h * nablk + ablk) * BLK_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) { // +32 B per MMA (K=16 bf16 / K=32 e4m3) inside the swizzle span
-                        if (FP8) umma_e4m3(d_tmem + h * BN, adesc + 2 * k, bdesc + 2 * k, IDESC_E4M3, 1u);
-                        else umma_bf16(d_tmem + h * BN, adesc + 2 * k, bdesc + 2 * k, IDESC, 1u);
-                    }
+                for (int k = 0; k < BK / 16; ++k) { // +32 B per MMA (K=16 bf16 / K=32 e4m3) inside the swizzle span
+                    if (FP8) umma_e4m3(d_tmem + h * BN, adesc + 2 * k, bdesc + 2 * k, IDESC_E4M3, 1u);
+                    else umma_bf16(d_tmem + h * BN, adesc + 2 * k, bdesc + 2 * k, IDESC, 1u);
                 }
             }
         };
-        int a_seen = 0;                      // A loads this warp has waited for (never skips a phase of bar_afull)
+        int a_seen = 0;                      // A row tiles this warp has waited for (never skips a phase of the A barriers)
         for (int lt = x; lt < ntiles; lt += 2) {
             TR(0);
-            const uint32_t acc = (uint32_t)x, acc_phase = (uint32_t)((lt >> 1) & 1);
-            while (a_seen <= m - m_first) { mbar_wait(bar_afull, (uint32_t)(a_seen & 1)); ++a_seen; }
-            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+            const uint32_t acc = (uint32_t)x;
+            const int a_need = m - m_first;
+            while (a_seen < a_need) {        // row tiles this warp had no item in
+                const uint32_t ap = (uint32_t)(a_seen & 1);
+                mbar_wait(bar_ak0, ap); mbar_wait(bar_ak1, ap);
+                if (!exact) mbar_wait(bar_alo, ap);
+                ++a_seen;
+            }
+            const bool a_fresh = a_seen == a_need;       // first item of this warp in the row tile: A may still be landing
+            const uint32_t ap = (uint32_t)(a_need & 1);
+            mbar_wait(bar_tempty + 8 * acc, (uint32_t)(((lt >> 1) & 1) ^ 1));     // accumulator drained by the epilogue of item lt - 2
             const uint32_t d_tmem = tmem_base + acc * (MH * BN);     // accumulator (acc, h) at + h * BN
             const bool more = lt + 1 < ntiles;
             // split mode: the B ring (2 stages) is shorter than one item (3 stages), so this warp may only look at
@@ -469,13 +502,26 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                 const int sidx = exact ? lt : 3 * lt + sp;           // running B stage index
                 const int st = exact ? (sidx & 3) : (sidx & 1);
                 mbar_wait(bar_full + 8 * st, (uint32_t)((exact ? (sidx >> 2) : (sidx >> 1)) & 1));
+                if (a_fresh && sp == 0) mbar_wait(bar_ak0, ap);
+                if (a_fresh && sp == 2) mbar_wait(bar_alo, ap);
                 tc_fence_after();
                 if (sp == 0) {
                     TR(1);
                     if (exact && lt > 0) asm volatile("bar.sync %0, 64;" ::"r"(2 + x) : "memory");   // item lt-1 has been issued
                     TR(2);
                 }
-                if (elect_one()) issue_stage(sp, d_tmem, sB + st * STAGE_BYTES);
+                const uint32_t sb = stage_addr(st);
+                if (a_fresh && sp == 0) {
+                    // first item of this warp in the row tile: start on k-block 0 while k-block 1 of A is still landing
+                    if (elect_one()) issue_kblock(sp, 0, d_tmem, sb);
+                    __syncwarp();
+                    mbar_wait(bar_ak1, ap);
+                    tc_fence_after();
+                    if (elect_one()) issue_kblock(sp, 1, d_tmem, sb);
+                } else if (elect_one()) {
+                    issue_kblock(sp, 0, d_tmem, sb);
+                    issue_kblock(sp, 1, d_tmem, sb);
+                }
                 __syncwarp();
                 if (sp == nsp - 1) {
                     TR(3);
@@ -492,6 +538,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                 }
                 __syncwarp();
             }
+            if (a_fresh) ++a_seen;
             TR(4);
             n += 2;
             if (n >= NT) { n -= NT; ++m; }
@@ -506,37 +553,50 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         const uint32_t mul = P.mul256;
         int cur_m = -1;
         int m = m_first, n = n_first;
-        // first CTA that owns an item of row tile m_first (inverse of the partition above)
-        const int ft = m_first * NT, big = P.tr * (P.tq + 1);
-        const int slot_first = cta - (ft < big ? ft / (P.tq + 1) : P.tr + (ft - big) / P.tq);
+        const int slot_first = sch.z;          // this CTA's index among the CTAs that touch row tile m_first
         Sel2 s2; s2.reset();
         Sel3 s3; s3.reset();
+        const uint32_t taddr_warp = tmem_base + ((uint32_t)(quarter * 32) << 16) + mh * BN + slice * SLICE;
 
         auto flush = [&](int mm) {
-            Cand3 c; c.reset();
+            // segment slot = index of this CTA among the CTAs that touch row tile mm: only the
+            // CTA's first row tile can have started in an earlier CTA
+            const int slot = mm == m_first ? slot_first : 0;
+            L2Cand *dst = P.part + ((size_t)(mm * MH * BM + row) * P.smax + slot) * 3;
             if (exact) {
-                if ((s2.m1 >> 8) != 0xFFFFFFu) c.insert(s2.value(s2.m1), s2.i1);
-                if ((s2.m2 >> 8) != 0xFFFFFFu) c.insert(s2.value(s2.m2), s2.i2);
+                // (value, quad base column) as one u64 per entry: the two slices of a row merge with four min / max
+                unsigned long long k1 = (s2.m1 >> 8) != 0xFFFFFFu ? (((unsigned long long)(s2.m1 >> 8) << 32) | (unsigned)s2.i1) : ~0ull;
+                unsigned long long k2 = (s2.m2 >> 8) != 0xFFFFFFu ? (((unsigned long long)(s2.m2 >> 8) << 32) | (unsigned)s2.i2) : ~0ull;
+                unsigned long long *sc = reinterpret_cast<unsigned long long *>(scratch);
+                if (slice > 0) { sc[((slice - 1) * MH * BM + row) * 2] = k1; sc[((slice - 1) * MH * BM + row) * 2 + 1] = k2; }
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                if (slice == 0) {
+                    for (int sl = 0; sl < NSLICE - 1; ++sl) {
+                        const unsigned long long o1 = sc[(sl * MH * BM + row) * 2], o2 = sc[(sl * MH * BM + row) * 2 + 1];
+                        const unsigned long long lo = min_u64(k1, o1), hi = max_u64(k1, o1);
+                        k2 = min_u64(min_u64(k2, o2), hi); k1 = lo;
+                    }
+                    dst[0] = k1 == ~0ull ? L2Cand{__int_as_float(0x7f800000), -1} : L2Cand{(float)((int)(k1 >> 32) - 0x400000), (int)(unsigned)k1};
+                    dst[1] = k2 == ~0ull ? L2Cand{__int_as_float(0x7f800000), -1} : L2Cand{(float)((int)(k2 >> 32) - 0x400000), (int)(unsigned)k2};
+                    dst[2] = L2Cand{__int_as_float(0x7f800000), -1};
+                }
             } else {
+                Cand3 c; c.reset();
                 if ((s3.m1 >> 8) < 0x7EFFFFu) c.insert(__uint_as_float(s3.m1) - shift, s3.i1);
                 if ((s3.m2 >> 8) < 0x7EFFFFu) c.insert(__uint_as_float(s3.m2) - shift, s3.i2);
                 if ((s3.m3 >> 8) < 0x7EFFFFu) c.insert(__uint_as_float(s3.m3) - shift, s3.i3);
-            }
-            if (slice > 0) {
+                if (slice > 0) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) scratch[((slice - 1) * MH * BM + row) * 3 + k] = L2Cand{c.d[k], c.i[k]};
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-            if (slice == 0) {
-                for (int sl = 0; sl < NSLICE - 1; ++sl)
+                    for (int k = 0; k < 3; ++k) scratch[((slice - 1) * MH * BM + row) * 3 + k] = L2Cand{c.d[k], c.i[k]};
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                if (slice == 0) {
+                    for (int sl = 0; sl < NSLICE - 1; ++sl)
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) { const L2Cand o = scratch[(sl * MH * BM + row) * 3 + k]; c.insert(o.d, o.idx); }
-                // segment slot = index of this CTA among the CTAs that touch row tile mm: only the
-                // CTA's first row tile can have started in an earlier CTA
-                const int slot = mm == m_first ? slot_first : 0;
-                L2Cand *dst = P.part + ((size_t)(mm * MH * BM + row) * P.smax + slot) * 3;
+                        for (int k = 0; k < 3; ++k) { const L2Cand o = scratch[(sl * MH * BM + row) * 3 + k]; c.insert(o.d, o.idx); }
 #pragma unroll
-                for (int k = 0; k < 3; ++k) dst[k] = L2Cand{c.d[k], c.i[k]};
+                    for (int k = 0; k < 3; ++k) dst[k] = L2Cand{c.d[k], c.i[k]};
+                }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             s2.reset(); s3.reset();
@@ -551,7 +611,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
             TRE(13);
             if (lt == 0) TRK(4);
             const int col0 = n * BN + slice * SLICE;
-            const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (MH * BN) + mh * BN + slice * SLICE;
+            const uint32_t taddr0 = taddr_warp + acc * (MH * BN);
 #pragma unroll 1
             for (int ch = 0; ch < SLICE / 32; ++ch) {
                 uint32_t r[32];
@@ -622,7 +682,88 @@ int make_tmap(pm_ctx *ctx, CUtensorMap *tm, const void *base, int rows_pad, int 
 }  // namespace
 
 static long long *g_k2_trace = nullptr;
+static int g_k2_trace_cta = 0;
 extern "C" void pm_debug_set_k2_trace(long long *p) { g_k2_trace = p; }
+extern "C" void pm_debug_set_k2_trace_cta(int cta) { g_k2_trace_cta = cta; }
+
+// Work partition of K2: CTA c owns `count` consecutive items of the (row tile, column tile) space starting at `first`.
+// A CTA whose range crosses into the next row tile pays for it -- it reloads its two A tiles (a bubble of the tensor pipe)
+// and flushes one more candidate segment, ~2 work items' worth of time at cfg2 -- and those CTAs used to finish last.  The
+// partition therefore balances COST = items + L2_SCHED_BOUNDARY_COST per row-tile crossing instead of item counts: the
+// smallest makespan for which a left-to-right greedy fill covers all items is found by bisection.  The table ([G][4] ints:
+// first, count, segment slot of the first row tile, 0) lives in device memory and is rebuilt only when the shape changes.
+constexpr double L2_SCHED_BOUNDARY_COST = 2.0;
+
+struct L2Sched {
+    int MT = -1, NT = -1, G = 0, smax = 1;
+    bool uploaded = false;
+    unsigned long long last_use = 0;
+    std::vector<int> table;      // [G][4]
+};
+constexpr int L2_SCHED_CACHE = 8;          // shapes kept (device copies side by side in one workspace slot)
+struct L2SchedCache {
+    L2Sched e[L2_SCHED_CACHE];
+    unsigned long long clock = 0;
+};
+
+static void l2_sched_build(L2Sched &S, int MT, int NT, int G)
+{
+    const long long T = (long long)MT * NT;
+    S.MT = MT; S.NT = NT; S.G = G;
+    S.table.assign((size_t)G * 4, 0);
+    auto fill = [&](double L, std::vector<int> *out) -> bool {
+        long long s = 0;
+        for (int c = 0; c < G; ++c) {
+            // largest k >= 1 with k + B * crossings(s, k) <= L
+            long long k = 0;
+            if (s < T) {
+                long long lo = 1, hi = T - s;
+                auto cost = [&](long long kk) { return (double)kk + L2_SCHED_BOUNDARY_COST * (double)((s + kk - 1) / NT - s / NT); };
+                if (cost(1) > L) k = 1;          // every CTA that has work left takes at least one item
+                else {
+                    while (lo < hi) { const long long mid = (lo + hi + 1) / 2; if (cost(mid) <= L) lo = mid; else hi = mid - 1; }
+                    k = lo;
+                }
+            }
+            if (out) { (*out)[(size_t)c * 4] = (int)s; (*out)[(size_t)c * 4 + 1] = (int)k; }
+            s += k;
+        }
+        return s >= T;
+    };
+    double lo = (double)T / G, hi = (double)T / G + L2_SCHED_BOUNDARY_COST * ((double)MT / G + 2.0) + 2.0;
+    while (!fill(hi, nullptr)) hi *= 1.5;
+    for (int it = 0; it < 40; ++it) { const double mid = 0.5 * (lo + hi); if (fill(mid, nullptr)) hi = mid; else lo = mid; }
+    fill(hi, &S.table);
+    // segment slots: CTA c's slot in row tile m = number of CTAs before it that touch m; only a CTA's FIRST row tile can
+    // have started in an earlier CTA
+    S.smax = 1;
+    std::vector<int> touch((size_t)MT, 0);
+    for (int c = 0; c < G; ++c) {
+        const int first = S.table[(size_t)c * 4], cnt = S.table[(size_t)c * 4 + 1];
+        if (cnt <= 0) continue;
+        const int m0 = first / NT, m1 = (first + cnt - 1) / NT;
+        S.table[(size_t)c * 4 + 2] = touch[(size_t)m0];
+        for (int m = m0; m <= m1; ++m) { ++touch[(size_t)m]; if (touch[(size_t)m] > S.smax) S.smax = touch[(size_t)m]; }
+    }
+}
+
+// the cached partition for this shape (least recently used entry replaced); *slot = its index
+static L2Sched &l2_sched_get(pm_ctx *ctx, int MT, int NT, int *slot = nullptr)
+{
+    if (!ctx->l2_sched) ctx->l2_sched = new L2SchedCache();
+    L2SchedCache &C = *static_cast<L2SchedCache *>(ctx->l2_sched);
+    const int G = l2_tc_grid(ctx, MT, NT);
+    int hit = -1, lru = 0;
+    for (int k = 0; k < L2_SCHED_CACHE; ++k) {
+        if (C.e[k].MT == MT && C.e[k].NT == NT && C.e[k].G == G) hit = k;
+        if (C.e[k].last_use < C.e[lru].last_use) lru = k;
+    }
+    if (hit < 0) { hit = lru; l2_sched_build(C.e[hit], MT, NT, G); C.e[hit].uploaded = false; }
+    C.e[hit].last_use = ++C.clock;
+    if (slot) *slot = hit;
+    return C.e[hit];
+}
+void l2_sched_free(pm_ctx *ctx) { delete static_cast<L2SchedCache *>(ctx->l2_sched); ctx->l2_sched = nullptr; }
 
 int l2_tc_grid(pm_ctx *ctx, int MT, int NT)
 {
@@ -630,21 +771,8 @@ int l2_tc_grid(pm_ctx *ctx, int MT, int NT)
     return (int)(T < ctx->num_sms ? T : ctx->num_sms);
 }
 
-// Max number of CTAs (segments) that can touch one row tile.  CTA c owns items
-// [c * tq + min(c, tr), ...) with tq = T / G, tr = T % G (the kernel uses the same formula).
-int l2_tc_smax(pm_ctx *ctx, int MT, int NT)
-{
-    const int T = MT * NT;
-    const int G = l2_tc_grid(ctx, MT, NT);
-    const int tq = T / G, tr = T % G, big = tr * (tq + 1);
-    auto owner = [&](int item) { return item < big ? item / (tq + 1) : tr + (item - big) / tq; };
-    int smax = 1;
-    for (int m = 0; m < MT; ++m) {
-        const int c0 = owner(m * NT), c1 = owner(m * NT + NT - 1);
-        if (c1 - c0 + 1 > smax) smax = c1 - c0 + 1;
-    }
-    return smax;
-}
+// Max number of CTAs (segments) that can touch one row tile under the partition above.
+int l2_tc_smax(pm_ctx *ctx, int MT, int NT) { return l2_sched_get(ctx, MT, NT).smax; }
 
 int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, int nt_pad,
                  const void *text, const L2Flags *flags, L2Cand *part, int smax, float *dump, int fp8,
@@ -676,8 +804,21 @@ int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, 
     P.trace = g_k2_trace; P.span = g_pm_span;
     P.chain_done = chain_done; P.wait_seq = wait_seq; P.chain_mark = chain_mark; P.mark_seq = mark_seq;
     if ((long long)P.MT * P.NT >= (1ll << 30)) return pm_fail(ctx, PM_BAD_ARG, "L2 matching: more than 2^30 work items");
-    const int G = l2_tc_grid(ctx, P.MT, P.NT);
-    P.tq = (P.MT * P.NT) / G; P.tr = (P.MT * P.NT) % G;
+    int sslot = 0;
+    L2Sched &S = l2_sched_get(ctx, P.MT, P.NT, &sslot);
+    const int G = S.G;
+    const bool ws_fresh = ctx->slot_ptr[WS_L2_SCHED] == nullptr;
+    PM_WS(ctx, dsched_all, int *, WS_L2_SCHED, (size_t)L2_SCHED_CACHE * ctx->num_sms * 16);
+    if (ws_fresh) for (int k = 0; k < L2_SCHED_CACHE; ++k) static_cast<L2SchedCache *>(ctx->l2_sched)->e[k].uploaded = false;
+    int *dsched = dsched_all + (size_t)sslot * ctx->num_sms * 4;
+    if (!S.uploaded) {
+        // A new shape: the copy is enqueued on the stream, i.e. after every earlier kernel that may still read the entry
+        // it replaces and before this launch (a copy is not subject to programmatic early launch).  Pageable source: the
+        // runtime stages it before the call returns, so the host vector may change afterwards.
+        PM_CUDA(ctx, cudaMemcpyAsync(dsched, S.table.data(), S.table.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        S.uploaded = true;
+    }
+    P.sched = dsched; P.trace_cta = g_k2_trace_cta;
     {
         pm_prof_scope prof(ctx, fp8 ? 1 : 0);       // profile class 1 = the Hamming matching kernel
         cudaError_t le = fp8 ? pm_launch_pdl(l2_tc_kernel<true>, dim3(G), dim3(TC_THREADS), (size_t)SMEM_TOTAL, ctx->stream, tq, tt, P)

@@ -95,6 +95,7 @@ int pm_destroy(pm_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     pm_comm_release(ctx);
+    l2_sched_free(ctx);
     for (int s = 0; s < PM_NSLOTS; ++s) if (ctx->slot_ptr[s]) cudaFree(ctx->slot_ptr[s]);
     if (ctx->prof_alloc)
         for (int w = 0; w < 3; ++w)

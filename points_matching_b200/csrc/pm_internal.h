@@ -19,9 +19,10 @@ enum pm_slot {
     WS_HAM_Q, WS_HAM_T, WS_HAM_PART, WS_COLBEST,
     WS_P1, WS_P2, WS_SAMPLES, WS_F32, WS_COUNTS, WS_KEY, WS_MASK, WS_FOUT, WS_REFIT, WS_MISC,
     WS_KNN, WS_KNN2, WS_IDX, WS_KP, WS_LINES,
-    WS_Q_U8, WS_T_U8, WS_T_NORMF, WS_L2_FBPART, WS_SHARD, WS_KP2, WS_PAIRRES
+    WS_Q_U8, WS_T_U8, WS_T_NORMF, WS_L2_FBPART, WS_SHARD, WS_KP2, WS_PAIRRES, WS_L2_SCHED
 };
-static_assert(WS_PAIRRES < PM_NSLOTS, "workspace slots");
+static_assert(WS_L2_SCHED < PM_NSLOTS, "workspace slots");
+void l2_sched_free(pm_ctx *ctx);        // l2_tc.cu
 void pm_comm_release(pm_ctx *ctx);      // pm_nccl.cu: destroys an owned communicator (pm_destroy)
 
 struct pm_ctx {
@@ -35,12 +36,14 @@ struct pm_ctx {
     std::string err;
     int32_t l2_stats[4] = {0, 0, 0, 0};
     unsigned compact_epoch = 0;    // filter.cu: tag of the current compaction call
+    unsigned long long compact_tickets = 0;   // filter.cu: tiles handed out by all compaction calls so far (ticket base of the next)
     int l2_rot = 0;                // l2.cu: which of the three rotating L2Flags blocks the next call uses
     // opt-in chain pipelining (pm_set_pipelining, l2.cu): consecutive one-call kNN-2 + ratio chains overlap
     int pipelining = 0;
     bool tail_is_chain = false;    // the last kernel enqueued through this ctx is the tail of signalling chain `chain_seq`
     unsigned long long chain_seq = 0;   // signalling chains enqueued so far (the tail of chain s stores s to chain_done)
     int chain_shape[4] = {0, 0, 0, 0};  // nq, nt, dim, is_u8 of the last signalling chain
+    void *l2_sched = nullptr;      // l2_tc.cu: K2's work partitions (small cache keyed by shape)
     void *tmap_encode = nullptr;   // cuTensorMapEncodeTiled entry point
     // cached TMA descriptors (l2_tc.cu): [2 * set + 0] query operand, [2 * set + 1] train operand
     alignas(64) unsigned char tmap_store[4][128] = {};
@@ -186,14 +189,13 @@ int pmk_hamming_knn2(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, 
                      int q_index_base, pm_dmatch *dout);
 int pmk_hamming_col_best(pm_ctx *ctx, const uint8_t *dq, int nq, const uint8_t *dt, int nt, int bytes,
                          int q_index_base, uint64_t *dcol_best);
-// filter.cu (fb: optional helper blocks that run the L2 fallback scan before the tiles read the kNN rows, l2_fallback.cuh)
-struct L2FallbackArgs;
+// filter.cu
 int pmk_ratio_filter(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout,
-                     int32_t *dn_out, const pm_gather_out *gather = nullptr, const L2FallbackArgs *fb = nullptr);
+                     int32_t *dn_out, const pm_gather_out *gather = nullptr);
 // same, as the tail of signalling chain `seq` (stores seq to chain_done when the last block is done)
 int pmk_ratio_filter_tail(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout,
                           int32_t *dn_out, unsigned long long *chain_done, unsigned *chain_ctr, unsigned long long seq,
-                          const pm_gather_out *gather = nullptr, const L2FallbackArgs *fb = nullptr);
+                          const pm_gather_out *gather = nullptr);
 int pmk_cross_check(pm_ctx *ctx, const pm_dmatch *dknn, int nq, int stride, const uint64_t *dcol_best,
                     int nt, pm_dmatch *dout, int32_t *dn_out);
 int pmk_minmax_filter(pm_ctx *ctx, const pm_dmatch *dm, int n, int stride, pm_dmatch *dout,
