@@ -827,6 +827,10 @@ def bench_lmeds(ctx, rank, world, args):
     return out
 
 
+def _say(msg):
+    print(f"bench.py:   {msg}", file=sys.stderr, flush=True)
+
+
 def bench_cfg5(ctx, torch, dev, world, rank, barrier):
     """BASELINE config 5 (1024 pairs x 8k SIFT, match + RANSAC-F per pair, pairs partitioned across ranks): every
     rank runs its 1024 / world pairs, cycling through 4 distinct synthetic pairs (8192 x 8192 x 128), 4096 8-point
@@ -858,13 +862,16 @@ def bench_cfg5(ctx, torch, dev, world, rank, barrier):
         return float(tmax.item()), last
 
     # (a) the C ABI's batched entry: one call enqueues every pair, no host round trip inside a pair
+    _say("cfg5: inputs ready")
     nctx = pm.Context(dev.index)
     lanes = int(os.environ.get("PM_BENCH_LANES", "0")) or 8       # pairs in flight (internal streams of the batched call)
     nctx.set_batch_lanes(lanes)
     nctx.batch_warmup(n, n, 128, False, 4096)       # lanes and their workspaces exist before anything is timed
     match_and_estimate_batch_native(nctx, plist[:8 * world], n_hyp=4096)      # warm-up: 8 pairs on every rank
+    _say("cfg5: warm")
     ms_n, res_n = timed(lambda: match_and_estimate_batch_native(nctx, plist, n_hyp=4096))
     last_n = res_n[-1][1]
+    _say("cfg5: device-resident batch done")
     # (b) end to end from host memory: u8 descriptors (SIFT's native range) + keypoints in pinned buffers, every pair uploaded
     #     inside the timed region by the lane that processes it; 96 bytes per pair come back
     lo = rank * pairs
@@ -873,7 +880,9 @@ def bench_cfg5(ctx, torch, dev, world, rank, barrier):
              [h[2].data_ptr() for h in hsel], [h[3].data_ptr() for h in hsel], 0.75, 4096)
     nctx.batch_warmup(n, n, 128, True, 4096)
     nctx.match_estimate_batched(*[a[:16] if isinstance(a, list) else a for a in hargs], seed=lo)
+    _say("cfg5: host batch warm")
     ms_e, rec = timed(lambda: nctx.match_estimate_batched(*hargs, seed=lo))
+    _say("cfg5: host batch done")
     # parity: the host-buffer u8 run and the device-resident f32 run are the same pairs with the same seeds -> identical records
     same = all(int(r["n_matches"]) == o["n_matches"] and int(r["n_inliers"]) == o["n_inliers"] and
                (o["F"] is None) == (int(r["has_model"]) == 0) and (o["F"] is None or np.array_equal(o["F"], r["F"].reshape(3, 3)))
@@ -892,6 +901,7 @@ def bench_cfg5(ctx, torch, dev, world, rank, barrier):
         planted = np.isin(gall["queryIdx"], qi)
         oracle_ok = o0["n_matches"] == len(gall) and float(orc.sampson_f64(o0["F"], k1[gall["queryIdx"]][planted], k2[gall["trainIdx"]][planted]).mean()) < 0.5
     ok = bool(same and oracle_ok)
+    _say("cfg5: parity done")
     if world > 1:
         import torch.distributed as dist
         flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
@@ -1058,6 +1068,11 @@ def start_watchdog(limit_s):
 
     def bark():
         print(f"bench.py: watchdog: still running after {limit_s} s -- giving up", file=sys.stderr, flush=True)
+        try:
+            import faulthandler
+            faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        except Exception:
+            pass
         os._exit(2)
 
     t = threading.Timer(limit_s, bark)

@@ -16,7 +16,7 @@
 
 #include "pm.h"
 
-#define CK(call) do { int st__ = (call); if (st__ != PM_OK) { std::fprintf(stderr, "%s -> %d\n", #call, st__); ok = false; return; } } while (0)
+#define CK(call) do { int st__ = (call); if (st__ != PM_OK) { std::fprintf(stderr, "%s -> %d: %s\n", #call, st__, ctx ? pm_last_error(ctx) : ""); ok = false; std::_Exit(1); } } while (0)
 #define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { std::fprintf(stderr, "%s: %s\n", #call, cudaGetErrorString(e__)); ok = false; return; } } while (0)
 
 static uint64_t rng_state = 0x1234567ull;

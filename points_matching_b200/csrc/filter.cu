@@ -117,7 +117,9 @@ __global__ void __launch_bounds__(FB) compact_lookback_kernel(Pred pred, int n, 
             }
         } else {
             if (lane == 0) st_volatile_u64(&status[tile], tag | (1ull << 32) | (unsigned)total);
+            unsigned spins = 0;
             for (int hi = tile - 1; hi >= 0;) {
+                if (++spins > (1u << 22)) pm_hang_trap(0x20u, (unsigned)tile, (unsigned)hi, epoch);
                 const int p = hi - lane;
                 unsigned long long v = tag | (2ull << 32);                 // before tile 0: inclusive prefix 0
                 if (p >= 0) v = ld_volatile_u64(&status[p]);
@@ -293,4 +295,9 @@ int pmk_gather_matches(pm_ctx *ctx, const pm_dmatch *dm, const int32_t *dn, int 
         dm, dn, max_matches, (const float2 *)dkp1, nkp1, (const float2 *)dkp2, nkp2, (float2 *)dp1, (float2 *)dp2, (float4 *)dpts4);
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
+}
+
+int pm_hang_init_filter(pm_hang_rec *dev_view)
+{
+    return cudaMemcpyToSymbol(g_pm_hang_rec, &dev_view, sizeof(dev_view)) == cudaSuccess ? PM_OK : PM_CUDA_ERR;
 }

@@ -750,3 +750,8 @@ int pmk_l2_col_best(pm_ctx *ctx, const float *dq, int nq, const float *dt, int n
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }
+
+int pm_hang_init_l2(pm_hang_rec *dev_view)
+{
+    return cudaMemcpyToSymbol(g_pm_hang_rec, &dev_view, sizeof(dev_view)) == cudaSuccess ? PM_OK : PM_CUDA_ERR;
+}

@@ -90,15 +90,22 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+// tag: call site << 16 | work item (hang report only)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0)
 {
-    uint32_t ok;
+    uint32_t ok, spins = 0;
+    unsigned long long t0 = 0;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && (++spins & 1023u) == 0) {          // try_wait itself may block for a while: judge by the clock
+            const unsigned long long now = pm_now_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > PM_WAIT_LIMIT_NS) pm_hang_trap(0x30u | (threadIdx.x >> 5 << 8), (bar & 0x3FFu) | (parity << 12), tag, blockIdx.x);
+        }
     } while (!ok);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1)
@@ -413,7 +420,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         int stage = 0; uint32_t sphase = 0, apar = 0;
         for (int lt = 0; lt < ntiles; ++lt) {
             if (m != cur_m) {
-                if (cur_m >= 0) { mbar_wait(bar_aempty, apar); apar ^= 1; }    // every MMA of the old row tile is done
+                if (cur_m >= 0) { mbar_wait(bar_aempty, apar, (1u << 16) | (uint32_t)lt); apar ^= 1; }    // every MMA of the old row tile is done
                 if (elect_one()) {
                     if (lt > 0) {                                               // (the first row tile's hi blocks are on their way)
                         mbar_expect_tx(bar_ak0, (uint32_t)(MH * BLK_BYTES));
@@ -432,7 +439,9 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                 cur_m = m;
             }
             for (int sp = 0; sp < nsp; ++sp) {
-                mbar_wait(bar_empty + 8 * stage, sphase ^ 1);
+                // (not for the very first stage: it was filled before this loop, and an issuer that has already consumed
+                // it has moved `empty` into its next phase -- waiting for the "previous" phase here would never return)
+                if (lt > 0 || sp > 0) mbar_wait(bar_empty + 8 * stage, sphase ^ 1, (2u << 16) | (uint32_t)lt);
                 if (elect_one()) {
                     const uint32_t fb = bar_full + 8 * stage, dst = stage_addr(stage);
                     if (lt > 0 || sp > 0) {                                     // (the very first stage is on its way)
@@ -486,13 +495,13 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
             const int a_need = m - m_first;
             while (a_seen < a_need) {        // row tiles this warp had no item in
                 const uint32_t ap = (uint32_t)(a_seen & 1);
-                mbar_wait(bar_ak0, ap); mbar_wait(bar_ak1, ap);
-                if (!exact) mbar_wait(bar_alo, ap);
+                mbar_wait(bar_ak0, ap, (3u << 16) | (uint32_t)lt); mbar_wait(bar_ak1, ap, (3u << 16) | (uint32_t)lt);
+                if (!exact) mbar_wait(bar_alo, ap, (3u << 16) | (uint32_t)lt);
                 ++a_seen;
             }
             const bool a_fresh = a_seen == a_need;       // first item of this warp in the row tile: A may still be landing
             const uint32_t ap = (uint32_t)(a_need & 1);
-            mbar_wait(bar_tempty + 8 * acc, (uint32_t)(((lt >> 1) & 1) ^ 1));     // accumulator drained by the epilogue of item lt - 2
+            mbar_wait(bar_tempty + 8 * acc, (uint32_t)(((lt >> 1) & 1) ^ 1), (4u << 16) | (uint32_t)lt);     // accumulator drained by the epilogue of item lt - 2
             const uint32_t d_tmem = tmem_base + acc * (MH * BN);     // accumulator (acc, h) at + h * BN
             const bool more = lt + 1 < ntiles;
             // split mode: the B ring (2 stages) is shorter than one item (3 stages), so this warp may only look at
@@ -501,9 +510,9 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
             for (int sp = 0; sp < nsp; ++sp) {
                 const int sidx = exact ? lt : 3 * lt + sp;           // running B stage index
                 const int st = exact ? (sidx & 3) : (sidx & 1);
-                mbar_wait(bar_full + 8 * st, (uint32_t)((exact ? (sidx >> 2) : (sidx >> 1)) & 1));
-                if (a_fresh && sp == 0) mbar_wait(bar_ak0, ap);
-                if (a_fresh && sp == 2) mbar_wait(bar_alo, ap);
+                mbar_wait(bar_full + 8 * st, (uint32_t)((exact ? (sidx >> 2) : (sidx >> 1)) & 1), (5u << 16) | (uint32_t)lt);
+                if (a_fresh && sp == 0) mbar_wait(bar_ak0, ap, (6u << 16) | (uint32_t)lt);
+                if (a_fresh && sp == 2) mbar_wait(bar_alo, ap, (7u << 16) | (uint32_t)lt);
                 tc_fence_after();
                 if (sp == 0) {
                     TR(1);
@@ -515,7 +524,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                     // first item of this warp in the row tile: start on k-block 0 while k-block 1 of A is still landing
                     if (elect_one()) issue_kblock(sp, 0, d_tmem, sb);
                     __syncwarp();
-                    mbar_wait(bar_ak1, ap);
+                    mbar_wait(bar_ak1, ap, (8u << 16) | (uint32_t)lt);
                     tc_fence_after();
                     if (elect_one()) issue_kblock(sp, 1, d_tmem, sb);
                 } else if (elect_one()) {
@@ -606,7 +615,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
             const uint32_t acc = (uint32_t)(lt & 1), acc_phase = (uint32_t)((lt >> 1) & 1);
             if (m != cur_m) { if (cur_m >= 0) flush(cur_m); cur_m = m; }
             TRE(12);
-            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            mbar_wait(bar_tfull + 8 * acc, acc_phase, (9u << 16) | (uint32_t)lt);
             tc_fence_after();
             TRE(13);
             if (lt == 0) TRK(4);
@@ -779,11 +788,14 @@ int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, 
                  int tmap_set, const unsigned long long *chain_done, unsigned long long wait_seq,
                  unsigned long long *chain_mark, unsigned long long mark_seq)
 {
-    static std::atomic<bool> attr_set{false};           // lanes of the batched pair call launch from several host threads
-    if (!attr_set.load(std::memory_order_acquire)) {
+    // per DEVICE, not per process: a host with one thread (and one ctx) per GPU needs it on every device it drives
+    static std::atomic<unsigned long long> attr_devices{0};     // lanes of the batched pair call launch from several host threads
+    const unsigned long long dev_bit = 1ull << (ctx->device & 63);
+    if (!(attr_devices.load(std::memory_order_acquire) & dev_bit)) {
+        PM_CUDA(ctx, cudaSetDevice(ctx->device));
         PM_CUDA(ctx, cudaFuncSetAttribute(l2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
         PM_CUDA(ctx, cudaFuncSetAttribute(l2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        attr_set.store(true, std::memory_order_release);
+        attr_devices.fetch_or(dev_bit, std::memory_order_release);
     }
     static_assert(sizeof(CUtensorMap) == 128, "tmap_store size");
     CUtensorMap *tmaps = reinterpret_cast<CUtensorMap *>(ctx->tmap_store) + 2 * tmap_set;   // one cached pair per buffer set
@@ -827,4 +839,9 @@ int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, 
     }
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
+}
+
+int pm_hang_init_l2_tc(pm_hang_rec *dev_view)
+{
+    return cudaMemcpyToSymbol(g_pm_hang_rec, &dev_view, sizeof(dev_view)) == cudaSuccess ? PM_OK : PM_CUDA_ERR;
 }

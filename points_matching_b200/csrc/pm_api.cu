@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <vector>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include <cfloat>
@@ -30,6 +31,29 @@ struct pm_nvtx_scope {
 };
 #define PM_NVTX() pm_nvtx_scope nvtx_scope__(__func__)
 
+pm_hang_rec *pm_hang_host = nullptr;
+static int pm_hang_setup()
+{
+    // one host-mapped record per process (every device can write it); per-device symbol initialisation
+    static std::mutex mu;
+    static unsigned long long done_devices = 0;
+    std::lock_guard<std::mutex> lk(mu);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return PM_CUDA_ERR;
+    if (!pm_hang_host) {
+        void *h = nullptr;
+        if (cudaHostAlloc(&h, sizeof(pm_hang_rec), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return PM_CUDA_ERR;
+        memset(h, 0, sizeof(pm_hang_rec));
+        pm_hang_host = static_cast<pm_hang_rec *>(h);
+    }
+    if (done_devices & (1ull << (dev & 63))) return PM_OK;
+    pm_hang_rec *d = nullptr;
+    if (cudaHostGetDevicePointer((void **)&d, pm_hang_host, 0) != cudaSuccess) return PM_CUDA_ERR;
+    if (pm_hang_init_filter(d) != PM_OK || pm_hang_init_l2(d) != PM_OK || pm_hang_init_l2_tc(d) != PM_OK) return PM_CUDA_ERR;
+    done_devices |= 1ull << (dev & 63);
+    return PM_OK;
+}
+
 unsigned long long *g_pm_span = nullptr;
 extern "C" void pm_debug_set_span(unsigned long long *p) { g_pm_span = p; }
 
@@ -40,7 +64,15 @@ int pm_fail(pm_ctx *ctx, int status, const char *fmt, ...)
     va_start(ap, fmt);
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
-    if (ctx) ctx->err = buf;
+    if (ctx) {
+        ctx->err = buf;
+        if (status == PM_CUDA_ERR && pm_hang_host && pm_hang_host->code) {
+            char more[160];
+            snprintf(more, sizeof(more), " [device-side wait gave up: code 0x%x, a=%u b=%u c=%u]", pm_hang_host->code, pm_hang_host->a,
+                     pm_hang_host->b, pm_hang_host->c);
+            ctx->err += more;
+        }
+    }
     return status;
 }
 
@@ -79,6 +111,7 @@ int pm_create(pm_ctx **out, int device)
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PM_NO_DEVICE;
     if (prop.major != 10) return PM_NO_DEVICE;          // sm_100a kernels only
     if (cudaSetDevice(device) != cudaSuccess) return PM_CUDA_ERR;
+    if (pm_hang_setup() != PM_OK) return PM_CUDA_ERR;
     pm_ctx *ctx = new pm_ctx();
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;

@@ -114,6 +114,39 @@ void *pm_ws(pm_ctx *ctx, int slot, size_t bytes);   // nullptr on failure (ctx->
 // (%globaltimer, ns).  nullptr in normal operation.
 extern unsigned long long *g_pm_span;
 
+// Hang detector: every device-side wait in libpm (mbarrier waits of K2, the look-back of K5, the chain waits) counts its
+// polls; a wait that exceeds PM_SPIN_LIMIT polls (seconds: far beyond any legitimate wait) writes what it was waiting for
+// into a host-mapped record and traps, so a protocol fault surfaces as PM_CUDA_ERR with a message instead of a silent
+// hang.  g_pm_hang_rec (one per translation unit, set by pm_hang_init_<tu> at pm_create) points at mapped host memory.
+struct pm_hang_rec { unsigned code, a, b, c; };
+#define PM_SPIN_LIMIT (1u << 27)
+#define PM_WAIT_LIMIT_NS 3000000000ull     /* 3 s on %globaltimer */
+extern pm_hang_rec *pm_hang_host;       // the host view of the record (pm_api.cu); nullptr until the first pm_create
+int pm_hang_init_filter(pm_hang_rec *dev_view);
+int pm_hang_init_l2(pm_hang_rec *dev_view);
+int pm_hang_init_l2_tc(pm_hang_rec *dev_view);
+#ifdef __CUDACC__
+static __device__ pm_hang_rec *g_pm_hang_rec = nullptr;
+static __device__ __forceinline__ unsigned long long pm_now_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+static __device__ __noinline__ void pm_hang_trap(unsigned code, unsigned a, unsigned b, unsigned c)
+{
+    pm_hang_rec *r = g_pm_hang_rec;
+    if (r && atomicCAS_system(&r->code, 0u, code) == 0u) {      // the first waiter to give up describes itself
+        r->a = a; r->b = b; r->c = c;
+        __threadfence_system();
+        // give the other waiters of this kernel a moment to reach their own limit before the context dies
+        const unsigned long long t0 = pm_now_ns();
+        while (pm_now_ns() - t0 < 2000000ull) { }
+    }
+    __trap();
+}
+#endif
+
 // Programmatic dependent launch (PDL): every kernel of a chain is launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization and begins with pm_pdl_prologue():
 // it lets the NEXT kernel of the stream start launching right away (its CTAs become
@@ -142,8 +175,10 @@ __device__ __forceinline__ void pm_chain_wait(const unsigned long long *chain_do
 {
     if (chain_done && threadIdx.x == 0) {
         unsigned long long v;
+        unsigned spins = 0;
         do {
             asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(chain_done) : "memory");
+            if (++spins > (1u << 24)) pm_hang_trap(0x10u, (unsigned)seq, (unsigned)v, blockIdx.x);
         } while (v < seq);
     }
 }
