@@ -11,6 +11,7 @@
 //   lane l (0..31): p_l = fma-chain over k = 128c + 4l + e (c ascending, e = 0..3) of (a_k-b_k)^2
 //   then the xor-butterfly p += shfl_xor(p, 16|8|4|2|1)
 // which the oracle restates bit for bit (orc_l2sq_f32_rerank).
+#include <atomic>
 #include <cuda_bf16.h>
 #include "pm_internal.h"
 #include "l2_common.h"
@@ -352,7 +353,9 @@ l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__rest
             s_role = stay;
         }
         __syncthreads();
+        if (span && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); span[32 + 2 * blockIdx.x] = tt; }
         if (s_role) l2_fallback_items<T>(fb);
+        if (span && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); span[33 + 2 * blockIdx.x] = s_role ? tt : 0ull; }
         return;
     }
     if (span && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); span[32 + 2 * blockIdx.x] = tt; }
@@ -478,8 +481,25 @@ l2_finish_kernel(const L2Cand *__restrict__ part, int ncand, const float *__rest
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
-            s_role = atomicAdd(&flags->rows_done, 1u) == (unsigned)(row_blocks - 1);
-            if (s_role) __threadfence();
+            int role = atomicAdd(&flags->rows_done, 1u) == (unsigned)(row_blocks - 1);     // the last one: the list is complete
+            if (!role) {
+                // not the last: help all the same, IF every row block is known to have started (then waiting for the rest
+                // of them cannot starve anybody) -- with the whole grid resident, which is the normal case, the scan runs
+                // on every SM instead of on the few that host the helper blocks
+                unsigned v;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&flags->rows_started) : "memory");
+                if (v >= (unsigned)row_blocks) {
+                    int spin = 0;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&flags->rows_done) : "memory");
+                        if (v < (unsigned)row_blocks) __nanosleep(64);
+                    } while (v < (unsigned)row_blocks && ++spin < (1 << 22));
+                    role = v >= (unsigned)row_blocks;
+                }
+            } else {
+                __threadfence();
+            }
+            s_role = role;
         }
         __syncthreads();
         if (s_role) l2_fallback_items<T>(fb);
@@ -643,20 +663,21 @@ static int l2_chain(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt,
     L2_WS2(q8, uint8_t *, WS_Q_U8, (size_t)mq_pad * L2_KDIM);
     L2_WS2(part, L2Cand *, WS_L2_PART, (size_t)mq_pad * smax * 3 * sizeof(L2Cand));
     L2_WS2(flagged, int *, WS_L2_FLAGGED, (size_t)nq * 4);
-    // fallback scratch: < 2 * L2FB_MAX_GRID items of two keys, then the per-row countdowns (zero between calls)
-    const bool fb_fresh = ctx->slot_bytes[WS_L2_FBPART] < (size_t)nset * L2FB_SCRATCH_BYTES;
-    L2_WS2(fbpart, unsigned long long *, WS_L2_FBPART, (size_t)L2FB_SCRATCH_BYTES);
+    // fallback scratch (l2_fallback.cuh): per-(row, segment) key pairs, then the per-row countdowns (zero between calls)
+    const size_t fb_bytes = l2_fb_scratch_bytes(nq);
+    const bool fb_fresh = ctx->slot_bytes[WS_L2_FBPART] < (size_t)nset * ((fb_bytes + 255) & ~(size_t)255);
+    L2_WS2(fbpart, unsigned long long *, WS_L2_FBPART, fb_bytes);
     if (fb_fresh) PM_CUDA(ctx, cudaMemsetAsync(ctx->slot_ptr[WS_L2_FBPART], 0, ctx->slot_bytes[WS_L2_FBPART], ctx->stream));
 #undef L2_WS2
     L2FallbackArgs fb;
     fb.q = dq; fb.t = dt; fb.is_u8 = is_u8; fb.nq = nq; fb.nt = nt; fb.dim = dim; fb.vec = vec; fb.q_index_base = q_index_base;
     fb.flags = flags; fb.flagged = flagged; fb.fb_part = fbpart;
-    fb.fb_cnt = reinterpret_cast<unsigned *>(fbpart + 4 * L2FB_MAX_GRID); fb.out = dout;
+    fb.fb_cnt = reinterpret_cast<unsigned *>(fbpart + 2 * l2_fb_slots(nq)); fb.out = dout;
     // K3: 8 lanes per row, 32 rows per block, at most one resident wave of row blocks (a second wave would double its
     // latency), plus the helper blocks of the split-mode fallback scan (they leave at once in exact-integer mode)
     const int fin_blocks = min(pm_cdiv(nq, 32), 3 * ctx->num_sms);
     const int fin_helpers = g_l2_fb_no_helpers ? 0 : min(max(3 * ctx->num_sms - fin_blocks, ctx->num_sms), L2FB_MAX_GRID - 1);
-    fb.workers = fin_helpers + 1;
+    fb.workers = fin_helpers + fin_blocks;
     const int pack_nt = phase == 2 ? 0 : nt, pack_nt_pad = phase == 2 ? 0 : nt_pad;
     const L2Flags *tflags_in = phase == 2 ? tflags : nullptr;
     const int pack_blocks = min(pm_cdiv(mq_pad + pack_nt_pad, 32), 8 * ctx->num_sms);
@@ -674,6 +695,17 @@ static int l2_chain(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt,
     int st = l2_tc_launch(ctx, qpack, mq_pad, tpack, nt_pad, text, flags, part, smax, g_l2_dump, 0, set,
                           run_ahead ? chain_done : nullptr, run_ahead ? seq - 1 : 0, signalling ? chain_mark : nullptr, seq);
     if (st != PM_OK) return st;
+    {
+        // K3 carries 42 KB of static shared memory (the fallback scan's staging): ask for the full carveout so that three
+        // blocks still fit on an SM (the default carveout admitted one, which tripled the row phase)
+        static std::atomic<unsigned long long> k3_attr_devices{0};
+        const unsigned long long dev_bit = 1ull << (ctx->device & 63);
+        if (!(k3_attr_devices.load(std::memory_order_acquire) & dev_bit)) {
+            PM_CUDA(ctx, cudaFuncSetAttribute(l2_finish_kernel<uint8_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            PM_CUDA(ctx, cudaFuncSetAttribute(l2_finish_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            k3_attr_devices.fetch_or(dev_bit, std::memory_order_release);
+        }
+    }
     if (is_u8)
         PM_CUDA(ctx, pm_launch_pdl(l2_finish_kernel<uint8_t>, dim3(fin_blocks + fin_helpers), dim3(256), 0, ctx->stream, (const L2Cand *)part, smax * 3,
                                    (const float *)qnorm, (const uint8_t *)q8, (const uint8_t *)t8, (const float *)tnormf,

@@ -394,7 +394,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     TRK(2);
     const L2Flags fl = *P.flags;
     const bool exact = l2_exact_mode(fl);
-    const int nsp = exact ? 1 : 3;           // B stages (k-block pairs) per work item
+    const int nsp = exact ? 1 : 2;           // B stages (k-block pairs) per work item
     const int nstage = exact ? 4 : 2;        // B ring depth
     const float shift = l2_split_shift(fl.max_qnorm_bits);
     const float nb_off = exact ? L2_EXACT_BIAS : shift;            // bias folded into the norm step
@@ -446,7 +446,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                     const uint32_t fb = bar_full + 8 * stage, dst = stage_addr(stage);
                     if (lt > 0 || sp > 0) {                                     // (the very first stage is on its way)
                         mbar_expect_tx(fb, sp == 0 ? STAGE_BYTES : 2 * BLK_BYTES);
-                        // stages: hi0 hi1 (+ norm image) | lo0 lo1 | hi0 hi1   (packed row = [hi 0..127 | lo 128..255])
+                        // stages: hi0 hi1 (+ norm image) | lo0 lo1   (packed row = [hi 0..127 | lo 128..255])
                         const int kc = sp == 1 ? 2 * KBW : 0;
                         tma_load_2d(dst, &tmap_t, fb, kc, n * BN);
                         tma_load_2d(dst + BLK_BYTES, &tmap_t, fb, kc + KBW, n * BN);
@@ -468,16 +468,16 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         int m = m_first, n = n_first + x;
         if (n >= NT) { n -= NT; ++m; }
         const uint64_t extA = make_sdesc_ext(sExtA);
-        auto issue_kblock = [&](int sp, int kk, uint32_t d_tmem, uint32_t sb) {
-            if (sp == 0 && kk == 0) {
-                // norm step first (overwrites): acc = [1 1 1 bias..] x [split3(||b||^2) 1 1 1 ..]
+        // one 64-wide k-block: A block `ablk` (0,1 hi / 2,3 lo) of both row tiles x B block `bk` of the stage at sb;
+        // `first`: the norm step goes in front (it overwrites the accumulators)
+        auto issue_kblock = [&](int ablk, int bk, bool first, uint32_t d_tmem, uint32_t sb) {
+            if (first) {
+                // acc = [1 1 1 bias..] x [split3(||b||^2) 1 1 1 ..]
                 const uint64_t extB = make_sdesc_ext(sb + 2 * BLK_BYTES);
 #pragma unroll
                 for (int h = 0; h < MH; ++h) umma_bf16(d_tmem + h * BN, extA, extB, IDESC, 0u);
             }
-            // A block: hi for stages 0,1 (x B hi, x B lo), lo for stage 2 (x B hi)
-            const int ablk = (sp == 2 ? 2 : 0) + kk;
-            const uint64_t bdesc = make_sdesc(sb + kk * BLK_BYTES);
+            const uint64_t bdesc = make_sdesc(sb + bk * BLK_BYTES);
 #pragma unroll
             for (int h = 0; h < MH; ++h) {      // the same B k-block feeds both A tiles
                 const uint64_t adesc = make_sdesc(sA + (ablk * MH + h) * BLK_BYTES);
@@ -504,15 +504,18 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
             mbar_wait(bar_tempty + 8 * acc, (uint32_t)(((lt >> 1) & 1) ^ 1), (4u << 16) | (uint32_t)lt);     // accumulator drained by the epilogue of item lt - 2
             const uint32_t d_tmem = tmem_base + acc * (MH * BN);     // accumulator (acc, h) at + h * BN
             const bool more = lt + 1 < ntiles;
-            // split mode: the B ring (2 stages) is shorter than one item (3 stages), so this warp may only look at
-            // the ring once the other issuer is done with it -- a wait two phases ahead would alias
+            // split mode: the B ring (2 stages) holds exactly one item, so this warp may only LOOK at the ring once the
+            // other issuer is done with item lt - 1 -- an mbarrier parity wait one whole ring ahead would alias with the
+            // phase before it and return at once
             if (!exact && lt > 0) asm volatile("bar.sync %0, 64;" ::"r"(2 + x) : "memory");
             for (int sp = 0; sp < nsp; ++sp) {
-                const int sidx = exact ? lt : 3 * lt + sp;           // running B stage index
+                // exact: one stage per item, ring of 4.  split: two stages per item -- [B hi + norm image], [B lo] -- ring
+                // of 2: stage 0 serves A hi x B hi AND A lo x B hi, stage 1 serves A hi x B lo (an earlier version loaded
+                // B hi a second time as a third stage)
+                const int sidx = exact ? lt : 2 * lt + sp;           // running B stage index
                 const int st = exact ? (sidx & 3) : (sidx & 1);
                 mbar_wait(bar_full + 8 * st, (uint32_t)((exact ? (sidx >> 2) : (sidx >> 1)) & 1), (5u << 16) | (uint32_t)lt);
                 if (a_fresh && sp == 0) mbar_wait(bar_ak0, ap, (6u << 16) | (uint32_t)lt);
-                if (a_fresh && sp == 2) mbar_wait(bar_alo, ap, (7u << 16) | (uint32_t)lt);
                 tc_fence_after();
                 if (sp == 0) {
                     TR(1);
@@ -520,16 +523,27 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
                     TR(2);
                 }
                 const uint32_t sb = stage_addr(st);
-                if (a_fresh && sp == 0) {
-                    // first item of this warp in the row tile: start on k-block 0 while k-block 1 of A is still landing
-                    if (elect_one()) issue_kblock(sp, 0, d_tmem, sb);
-                    __syncwarp();
-                    mbar_wait(bar_ak1, ap, (8u << 16) | (uint32_t)lt);
-                    tc_fence_after();
-                    if (elect_one()) issue_kblock(sp, 1, d_tmem, sb);
-                } else if (elect_one()) {
-                    issue_kblock(sp, 0, d_tmem, sb);
-                    issue_kblock(sp, 1, d_tmem, sb);
+                if (sp == 0) {
+                    if (a_fresh) {
+                        // first item of this warp in the row tile: start on k-block 0 while the rest of A is still landing
+                        if (elect_one()) issue_kblock(0, 0, true, d_tmem, sb);
+                        __syncwarp();
+                        mbar_wait(bar_ak1, ap, (8u << 16) | (uint32_t)lt);
+                        tc_fence_after();
+                        if (elect_one()) issue_kblock(1, 1, false, d_tmem, sb);
+                        __syncwarp();
+                        if (!exact) { mbar_wait(bar_alo, ap, (7u << 16) | (uint32_t)lt); tc_fence_after(); }
+                    } else if (elect_one()) {
+                        issue_kblock(0, 0, true, d_tmem, sb);
+                        issue_kblock(1, 1, false, d_tmem, sb);
+                    }
+                    if (!exact && elect_one()) {       // A lo x B hi
+                        issue_kblock(2, 0, false, d_tmem, sb);
+                        issue_kblock(3, 1, false, d_tmem, sb);
+                    }
+                } else if (elect_one()) {              // A hi x B lo
+                    issue_kblock(0, 0, false, d_tmem, sb);
+                    issue_kblock(1, 1, false, d_tmem, sb);
                 }
                 __syncwarp();
                 if (sp == nsp - 1) {

@@ -8,7 +8,7 @@ import points_matching_b200 as pm
 from points_matching_b200 import _lib, synth
 ctx = pm.Context(0)
 NQ = NT = 10000
-q, t = synth.sift_pair(NQ, NT, seed=1234)
+q, t = (synth.surf_pair(NQ, NT, seed=77) if os.environ.get("PM_SURF", "0") != "0" else synth.sift_pair(NQ, NT, seed=1234))
 dq, dt = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
 knn = torch.zeros((NQ, 2, 4), dtype=torch.int32, device="cuda")
 tr = torch.zeros((64, 16), dtype=torch.int64, device="cuda")

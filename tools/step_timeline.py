@@ -9,7 +9,7 @@ from points_matching_b200 import _lib, synth
 ctx = pm.Context(0)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); ctx.set_stream(stream.cuda_stream)
 NQ = NT = 10000
-q, t = synth.sift_pair(NQ, NT, seed=1234)
+q, t = (synth.surf_pair(NQ, NT, seed=77) if os.environ.get("PM_SURF", "0") != "0" else synth.sift_pair(NQ, NT, seed=1234))
 dq, dt = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
 knn = torch.zeros((NQ, 2, 4), dtype=torch.int32, device="cuda")
 good = torch.zeros((NQ, 4), dtype=torch.int32, device="cuda")
@@ -50,6 +50,14 @@ for rep in range(5):
     torch.cuda.synchronize()
     rows.append(span.cpu().numpy().copy())
 r = rows[-1]
+hb = r[32 + 2 * 313:32 + 2 * 444].reshape(-1, 2)
+stay = hb[:, 1] > 0
+if stay.any():
+    hs, he = (hb[stay, 0] - r[7]) / 1e3, (hb[stay, 1] - r[7]) / 1e3
+    print("K3 helpers: %d of %d stayed; start (past their waits) min/med/max %.2f %.2f %.2f  end min/med/max %.2f %.2f %.2f us"
+          % (stay.sum(), len(hb), hs.min(), np.median(hs), hs.max(), he.min(), np.median(he), he.max()))
+else:
+    print("K3 helpers: none stayed (or exact mode)")
 blk = r[32:32 + 2 * 313].reshape(-1, 2)
 st, en = (blk[:, 0] - r[7]) / 1e3, (blk[:, 1] - r[7]) / 1e3
 print("K3 per-block (us after the first block passed the wait): start min/med/max %.2f %.2f %.2f  end min/med/max %.2f %.2f %.2f  dur med %.2f max %.2f"
