@@ -864,7 +864,7 @@ def bench_cfg5(ctx, torch, dev, world, rank, barrier):
     # (a) the C ABI's batched entry: one call enqueues every pair, no host round trip inside a pair
     _say("cfg5: inputs ready")
     nctx = pm.Context(dev.index)
-    lanes = int(os.environ.get("PM_BENCH_LANES", "0")) or 8       # pairs in flight (internal streams of the batched call)
+    lanes = int(os.environ.get("PM_BENCH_LANES", "0")) or 4       # groups of pairs in flight (internal streams of the batched call)
     nctx.set_batch_lanes(lanes)
     nctx.batch_warmup(n, n, 128, False, 4096)       # lanes and their workspaces exist before anything is timed
     match_and_estimate_batch_native(nctx, plist[:8 * world], n_hyp=4096)      # warm-up: 8 pairs on every rank

@@ -284,12 +284,15 @@ int pm_match_estimate_batched(pm_ctx *ctx, int n_pairs, const void *const *desc1
                               const float *const *kp1, const float *const *kp2, float ratio,
                               const pm_ransac_params *prm, pm_pair_result *results);
 
-/* Number of pairs the batched call keeps in flight (1..8 internal streams with their own workspaces, one
- * host thread enqueues each; default 4).  Results do not depend on it.  Measured per 8192 x 8192 pair with 4096
- * hypotheses: 1 / 2 / 4 / 6 / 8 lanes = 207 / 130 / 86 / 71 / 67 us.  A lane and its workspaces are created
- * the first time it is used (cudaMalloc synchronises the device), so the first batch after a change of lanes or
- * shapes is slow: warm up once.  PM_BATCH_THREADS=0 (environment) makes one host thread enqueue all lanes
- * (94 us per pair at 8 lanes). */
+/* The batched calls cut the pairs into groups of 16 consecutive pairs (PM_PAIR_GROUP in the environment overrides): the
+ * pairs of a group run their matching chains one after the other and then share ONE launch of every RANSAC kernel (the
+ * pair is a grid dimension), so those kernels fill the GPU instead of running at a fraction of a wave per pair.  Group g
+ * runs on lane g mod `lanes` (1..8 internal streams with their own workspaces, one host thread enqueues each; default 4), so
+ * the latency-bound kernels of one group overlap the matching of another.  Results do not depend on either number.
+ * Measured per 8192 x 8192 pair with 4096 hypotheses: 1 lane, groups of 1 = 203 us; 8 lanes, groups of 1 (the round-1 form) =
+ * 60 us; 4 lanes, groups of 16 = 43 us.  A lane and its workspaces are created the first time it is used (cudaMalloc
+ * synchronises the device), so the first batch after a change of lanes or shapes is slow: warm up once.
+ * PM_BATCH_THREADS=0 (environment) makes one host thread enqueue all lanes. */
 int pm_set_batch_lanes(pm_ctx *ctx, int lanes);
 /* Optional: create the lanes and their workspaces for pairs of up to n1 x n2 descriptors now (a throw-away batch
  * of empty pairs; synchronises), so that the first real batch does not pay for it. */

@@ -830,38 +830,68 @@ int pm_find_fundamental_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int
     return pmk_ransac_finish(ctx, dp1, dp2, n, dFw, prm->threshold, prm->metric, prm->refit, dF, dmask, dn_inliers);
 }
 
-// main.cpp:43-98 for one image pair, entirely in stream order (no host round trip): the match count stays on
-// the device (dn_good) and bounds every RANSAC kernel through its n_dev argument.  13 launches: K1, K2, K3, K5 (which
-// also gathers the keypoint coordinates of the survivors), sample sets, K6, K7, best+pick, mask, three refit passes
-// and the refit solve, which writes the result record.
-static int pair_enqueue(pm_ctx *ctx, const void *dd1, int n1, const void *dd2, int n2, int dim, int is_u8, const float *dkp1,
-                        const float *dkp2, float ratio, const pm_ransac_params *prm, uint64_t seed, pm_pair_result *dres)
+// main.cpp:43-98 for a GROUP of image pairs, entirely in stream order (no host round trip): per pair the matching chain
+// K1, K2, K3, K5 (which also gathers the keypoint coordinates of the survivors into the pair's slot), then ONE launch per
+// RANSAC kernel for the whole group (pmk_pair_group_ransac: sample sets, K6, K7, best+pick, mask, three refit passes and
+// the refit solve, which writes the result records).  The match counts stay on the device and bound every RANSAC kernel
+// through its n_dev argument.  A group of one pair is the single-pair entry.
+static int pair_group_enqueue(pm_ctx *ctx, int cnt, const void *const *dd1, const int32_t *n1, const void *const *dd2,
+                              const int32_t *n2, int dim, int is_u8, const float *const *dkp1, const float *const *dkp2, float ratio,
+                              const pm_ransac_params *prm, uint64_t seed0, pm_pair_result *dres, bool host_inputs)
 {
     const int m = prm->sample_size, per = m == 8 ? 1 : 3, nh = prm->n_hyp;
-    const int nmax = n1 > 0 ? n1 : 1;
+    int nmax = 1, n2max = 1;
+    for (int b = 0; b < cnt; ++b) { if (n1[b] > nmax) nmax = n1[b]; if (n2[b] > n2max) n2max = n2[b]; }
+    const size_t P = (size_t)cnt;
     PM_WS(ctx, dknn, pm_dmatch *, WS_KNN, (size_t)nmax * 2 * sizeof(pm_dmatch));
     PM_WS(ctx, dgood, pm_dmatch *, WS_OUT2, (size_t)nmax * sizeof(pm_dmatch));
-    PM_WS(ctx, dkey, uint64_t *, WS_KEY, 64);
-    int32_t *dn_good = reinterpret_cast<int32_t *>(dkey + 2), *dn_inl = dn_good + 1;
-    PM_WS(ctx, dp1, float *, WS_P1, (size_t)nmax * 8);
-    PM_WS(ctx, dp2, float *, WS_P2, (size_t)nmax * 8);
-    PM_WS(ctx, dpts, float *, WS_MISC, (size_t)nmax * 16);      // the matches as {x1, y1, x2, y2}
-    PM_WS(ctx, ds, int32_t *, WS_SAMPLES, (size_t)nh * m * 4);
-    PM_WS(ctx, dF32, float *, WS_F32, ((size_t)nh * per + 1) * 12 * 4);
-    PM_WS(ctx, dcounts, int32_t *, WS_COUNTS, (size_t)nh * per * 4);
-    PM_WS(ctx, dmask, uint8_t *, WS_MASK, (size_t)nmax);
-    PM_WS(ctx, dF, double *, WS_FOUT, 16 * 8);
-    float *dFw = dF32 + (size_t)nh * per * 12;
+    PM_WS(ctx, dkey, uint64_t *, WS_KEY, P * 64);
+    PM_WS(ctx, dp1, float *, WS_P1, P * nmax * 8);
+    PM_WS(ctx, dp2, float *, WS_P2, P * nmax * 8);
+    PM_WS(ctx, dpts, float *, WS_MISC, P * nmax * 16);          // the matches as {x1, y1, x2, y2}
+    PM_WS(ctx, ds, int32_t *, WS_SAMPLES, P * nh * m * 4);
+    PM_WS(ctx, dF32, float *, WS_F32, P * ((size_t)nh * per + 1) * 12 * 4);
+    PM_WS(ctx, dcounts, int32_t *, WS_COUNTS, P * nh * per * 4);
+    PM_WS(ctx, dmask, uint8_t *, WS_MASK, P * nmax);
+    PM_WS(ctx, dF, double *, WS_FOUT, P * 16 * 8);
+    PM_WS(ctx, drefit, double *, WS_REFIT, P * PM_REFIT_WS_DOUBLES * sizeof(double));
+    uint8_t *s1 = nullptr, *s2 = nullptr; float *sk1 = nullptr, *sk2 = nullptr;
+    const size_t elem = is_u8 ? 1 : 4;
+    if (host_inputs) {       // staging for HOST descriptors / keypoints: reused pair after pair in stream order
+        PM_WS(ctx, a1, uint8_t *, WS_Q_RAW, (size_t)nmax * dim * elem);
+        PM_WS(ctx, a2, uint8_t *, WS_T_RAW, (size_t)n2max * dim * elem);
+        PM_WS(ctx, a3, float *, WS_KP, (size_t)nmax * 8);
+        PM_WS(ctx, a4, float *, WS_KP2, (size_t)n2max * 8);
+        s1 = a1; s2 = a2; sk1 = a3; sk2 = a4;
+    }
     int st;
-    // K5 gathers while it scatters: the good matches leave as DMatch records AND as the two point lists
-    const pm_gather_out g = {dkp1, n1, dkp2, n2, dp1, dp2, dpts};
-    if ((st = pmk_l2_knn2_fused(ctx, dd1, n1, dd2, n2, dim, is_u8, 0, dknn, 0, ratio, dgood, dn_good, &g)) != PM_OK) return st;
-    if ((st = pmk_sample_sets(ctx, nmax, nh, m, seed, ds, dn_good)) != PM_OK) return st;
-    if ((st = pmk_ransac_solve(ctx, dp1, dp2, nmax, ds, nh, m, dF32, dn_good)) != PM_OK) return st;
-    if ((st = pmk_ransac_score(ctx, dp1, dp2, nmax, dF32, nh * per, prm->threshold, prm->metric, dcounts, dn_good, dpts)) != PM_OK) return st;
-    if ((st = pmk_ransac_best_pick(ctx, dcounts, nh * per, 0, dF32, dkey, dFw, dn_inl)) != PM_OK) return st;
-    return pmk_ransac_finish(ctx, dp1, dp2, nmax, dFw, prm->threshold, prm->metric, prm->refit, dF, dmask, dn_inl, dn_good,
-                             dpts, 1, dkey, m, dres);      // its last kernel writes the pair's result record
+    for (int b = 0; b < cnt; ++b) {
+        const void *d1 = dd1[b], *d2 = dd2[b];
+        const float *k1 = dkp1[b], *k2 = dkp2[b];
+        if (host_inputs) {
+            if (n1[b]) { H2D(ctx, s1, d1, (size_t)n1[b] * dim * elem); H2D(ctx, sk1, k1, (size_t)n1[b] * 8); }
+            if (n2[b]) { H2D(ctx, s2, d2, (size_t)n2[b] * dim * elem); H2D(ctx, sk2, k2, (size_t)n2[b] * 8); }
+            d1 = s1; d2 = s2; k1 = sk1; k2 = sk2;
+        }
+        int32_t *dn_good = reinterpret_cast<int32_t *>(dkey + (size_t)b * 8 + 2);
+        // K5 gathers while it scatters: the good matches leave as DMatch records AND as the pair's point lists
+        const pm_gather_out g = {k1, n1[b], k2, n2[b], dp1 + (size_t)b * nmax * 2, dp2 + (size_t)b * nmax * 2, dpts + (size_t)b * nmax * 4};
+        if ((st = pmk_l2_knn2_fused(ctx, d1, n1[b], d2, n2[b], dim, is_u8, 0, dknn, 0, ratio, dgood, dn_good, &g)) != PM_OK) return st;
+    }
+    pm_pair_group G;
+    G.n_pairs = cnt; G.nmax = nmax; G.n_hyp = nh; G.m = m; G.metric = prm->metric; G.refit_on = prm->refit != 0;
+    G.threshold = prm->threshold; G.seed0 = seed0;
+    G.p1 = reinterpret_cast<const float2 *>(dp1); G.p2 = reinterpret_cast<const float2 *>(dp2);
+    G.pts4 = reinterpret_cast<const float4 *>(dpts);
+    G.samples = ds; G.F32 = dF32; G.counts = dcounts; G.key = dkey; G.mask = dmask; G.refit = drefit; G.Fout = dF; G.res = dres;
+    return pmk_pair_group_ransac(ctx, G);
+}
+
+// pairs per group of the batched calls (PM_PAIR_GROUP overrides; results do not depend on it)
+static int pair_group_size()
+{
+    static const int grp_env = getenv("PM_PAIR_GROUP") ? atoi(getenv("PM_PAIR_GROUP")) : 0;
+    return grp_env > 0 ? (grp_env < 64 ? grp_env : 64) : 16;
 }
 
 static int pair_check(pm_ctx *ctx, int dim, const pm_ransac_params *prm)
@@ -883,22 +913,8 @@ int pm_match_estimate_pair_dev(pm_ctx *ctx, const void *dd1, int n1, const void 
     if (st != PM_OK) return st;
     PM_REQUIRE(ctx, n1 >= 0 && n2 >= 0 && dres, "negative size or null result");
     PM_REQUIRE(ctx, (n1 == 0 || (dd1 && dkp1)) && (n2 == 0 || (dd2 && dkp2)), "null pointer");
-    return pair_enqueue(ctx, dd1, n1, dd2, n2, dim, is_u8, dkp1, dkp2, ratio, prm, seed, dres);
-}
-
-// One pair whose descriptors / keypoints are HOST buffers: staged into this (lane) ctx's raw slots on its own stream, then
-// the device-resident chain.  The copies of one lane overlap the kernels of the others.
-static int pair_enqueue_host(pm_ctx *ctx, const void *h1, int n1, const void *h2, int n2, int dim, int is_u8, const float *hk1,
-                             const float *hk2, float ratio, const pm_ransac_params *prm, uint64_t seed, pm_pair_result *dres)
-{
-    const size_t elem = is_u8 ? 1 : 4, b1 = (size_t)n1 * dim * elem, b2 = (size_t)n2 * dim * elem;
-    PM_WS(ctx, d1, uint8_t *, WS_Q_RAW, b1);
-    PM_WS(ctx, d2, uint8_t *, WS_T_RAW, b2);
-    PM_WS(ctx, k1, float *, WS_KP, (size_t)(n1 > 0 ? n1 : 1) * 8);
-    PM_WS(ctx, k2, float *, WS_KP2, (size_t)(n2 > 0 ? n2 : 1) * 8);
-    if (n1) { H2D(ctx, d1, h1, b1); H2D(ctx, k1, hk1, (size_t)n1 * 8); }
-    if (n2) { H2D(ctx, d2, h2, b2); H2D(ctx, k2, hk2, (size_t)n2 * 8); }
-    return pair_enqueue(ctx, d1, n1, d2, n2, dim, is_u8, k1, k2, ratio, prm, seed, dres);
+    const int32_t c1 = n1, c2 = n2;
+    return pair_group_enqueue(ctx, 1, &dd1, &c1, &dd2, &c2, dim, is_u8, &dkp1, &dkp2, ratio, prm, seed, dres, false);
 }
 
 static int batched_impl(pm_ctx *ctx, int n_pairs, const void *const *dd1, const int32_t *n1, const void *const *dd2,
@@ -948,18 +964,22 @@ static int batched_impl(pm_ctx *ctx, int n_pairs, const void *const *dd1, const 
         PM_REQUIRE(ctx, n1[p] >= 0 && n2[p] >= 0, "negative size");
         PM_REQUIRE(ctx, (n1[p] == 0 || (dd1[p] && dkp1[p])) && (n2[p] == 0 || (dd2[p] && dkp2[p])), "null pointer");
     }
-    const int L = n_pairs < ctx->batch_lanes ? n_pairs : ctx->batch_lanes;
-    auto enqueue = host_inputs ? pair_enqueue_host : pair_enqueue;
+    // consecutive pairs form groups of `grp` (their RANSAC kernels share launches); group g runs on lane g % L
+    const int grp = pair_group_size();
+    const int n_groups = pm_cdiv(n_pairs, grp);
+    const int L = n_groups < ctx->batch_lanes ? n_groups : ctx->batch_lanes;
+    auto enqueue_group = [&](pm_ctx *c, int g) {
+        const int p0 = g * grp, cnt = n_pairs - p0 < grp ? n_pairs - p0 : grp;
+        return pair_group_enqueue(c, cnt, dd1 + p0, n1 + p0, dd2 + p0, n2 + p0, dim, is_u8, dkp1 + p0, dkp2 + p0, ratio, prm,
+                                  prm->seed + (uint64_t)p0, dres + p0, host_inputs);
+    };
     if (L <= 1) {
-        for (int p = 0; p < n_pairs; ++p) {
-            st = enqueue(ctx, dd1[p], n1[p], dd2[p], n2[p], dim, is_u8, dkp1[p], dkp2[p], ratio, prm, prm->seed + (uint64_t)p, dres + p);
-            if (st != PM_OK) return st;
-        }
+        for (int g = 0; g < n_groups; ++g)
+            if ((st = enqueue_group(ctx, g)) != PM_OK) return st;
         return PM_OK;
     }
-    // Pairs are independent: pair p runs on lane p % L (a child context with its own stream and workspaces), so
-    // the single-warp / single-wave kernels of one pair (minimal solves, the refit eigen-solve) overlap the
-    // other lanes' matching.  The lanes fork from and join the ctx stream through events: to the caller the
+    // Groups are independent: group g runs on lane g % L (a child context with its own stream and workspaces), so
+    // the latency-bound kernels of one group (minimal solves, the refit eigen-solves) overlap the other lanes' matching.  The lanes fork from and join the ctx stream through events: to the caller the
     // call still behaves like one stream-ordered operation.
     PM_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!ctx->ev_fork) PM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
@@ -981,12 +1001,10 @@ static int batched_impl(pm_ctx *ctx, int n_pairs, const void *const *dd1, const 
     for (int k = 0; k < L; ++k) { before[k] = ctx->lane[k]->launches; lane_st[k] = PM_OK; }
     auto run_lane = [&](int k) {
         cudaSetDevice(ctx->device);
-        for (int p = k; p < n_pairs && lane_st[k] == PM_OK; p += L)
-            lane_st[k] = enqueue(ctx->lane[k], dd1[p], n1[p], dd2[p], n2[p], dim, is_u8, dkp1[p], dkp2[p], ratio, prm,
-                                 prm->seed + (uint64_t)p, dres + p);
+        for (int g = k; g < n_groups && lane_st[k] == PM_OK; g += L) lane_st[k] = enqueue_group(ctx->lane[k], g);
     };
     static const bool lane_threads = !(getenv("PM_BATCH_THREADS") && atoi(getenv("PM_BATCH_THREADS")) == 0);
-    if (n_pairs >= 2 * L && lane_threads) {
+    if (n_groups >= 2 * L && lane_threads) {
         std::vector<std::thread> workers;
         for (int k = 1; k < L; ++k) workers.emplace_back(run_lane, k);
         run_lane(0);
@@ -1023,7 +1041,7 @@ int pm_batch_warmup(pm_ctx *ctx, int n1, int n2, int dim, int is_u8, const pm_ra
     PM_REQUIRE(ctx, n1 > 0 && n2 > 0, "sizes must be positive");
     PM_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t elem = is_u8 ? 1 : 4, b1 = (size_t)n1 * dim * elem, b2 = (size_t)n2 * dim * elem;
-    const int np = 2 * ctx->batch_lanes;
+    const int np = ctx->batch_lanes * pair_group_size();       // one full group for every lane
     uint8_t *buf = nullptr;
     const size_t off_d2 = (b1 + 255) & ~(size_t)255, off_k1 = off_d2 + ((b2 + 255) & ~(size_t)255),
                  off_k2 = off_k1 + (((size_t)n1 * 8 + 255) & ~(size_t)255), off_res = off_k2 + (((size_t)n2 * 8 + 255) & ~(size_t)255),

@@ -8,7 +8,7 @@
 
 #include "../../include/pm.h"
 
-#define PM_NSLOTS 40
+#define PM_NSLOTS 44
 #define PM_PROF_RING 4096
 #define PM_MAX_LANES 8   /* measured, us per cfg5 pair (every lane warmed up first): 1 / 2 / 4 / 6 / 8 lanes = 207 / 130 / 86 / 71 / 67 */
 
@@ -19,9 +19,9 @@ enum pm_slot {
     WS_HAM_Q, WS_HAM_T, WS_HAM_PART, WS_COLBEST,
     WS_P1, WS_P2, WS_SAMPLES, WS_F32, WS_COUNTS, WS_KEY, WS_MASK, WS_FOUT, WS_REFIT, WS_MISC,
     WS_KNN, WS_KNN2, WS_IDX, WS_KP, WS_LINES,
-    WS_Q_U8, WS_T_U8, WS_T_NORMF, WS_L2_FBPART, WS_SHARD, WS_KP2, WS_PAIRRES, WS_L2_SCHED
+    WS_Q_U8, WS_T_U8, WS_T_NORMF, WS_L2_FBPART, WS_SHARD, WS_KP2, WS_PAIRRES, WS_L2_SCHED, WS_HAND
 };
-static_assert(WS_L2_SCHED < PM_NSLOTS, "workspace slots");
+static_assert(WS_HAND < PM_NSLOTS, "workspace slots");
 void l2_sched_free(pm_ctx *ctx);        // l2_tc.cu
 void pm_comm_release(pm_ctx *ctx);      // pm_nccl.cu: destroys an owned communicator (pm_destroy)
 
@@ -265,6 +265,20 @@ int pmk_ransac_finish(pm_ctx *ctx, const float *dp1, const float *dp2, int n, co
                       const uint64_t *dkey = nullptr, int sample_size = 0, pm_pair_result *dres = nullptr);
 int pmk_sample_sets(pm_ctx *ctx, int n_points, int n_hyp, int m, uint64_t seed, int32_t *dout,
                     const int32_t *dn = nullptr, int h_base = 0);
+// a group of image pairs whose RANSAC kernels run as one launch each (ransac.cu); slot b = pair b of the group:
+//   p1 / p2 [b][nmax] float2, pts4 [b][nmax] float4, samples [b][n_hyp * m], F32 [b][(n_models + 1) * 12] (winner last),
+//   counts [b][n_models], key [b][8] u64 (key, -, {n_good, n_inl} as ints at +2), mask [b][nmax], refit [b][RF workspace],
+//   Fout [b][16] f64, res [b]
+struct pm_pair_group {
+    int n_pairs, nmax, n_hyp, m, metric, refit_on;
+    float threshold;
+    uint64_t seed0;
+    const float2 *p1, *p2; const float4 *pts4;
+    int32_t *samples; float *F32; int32_t *counts; uint64_t *key; uint8_t *mask; double *refit; double *Fout;
+    pm_pair_result *res;
+};
+#define PM_REFIT_WS_DOUBLES (64 * (5 + 2 + 45) + 16)
+int pmk_pair_group_ransac(pm_ctx *ctx, const pm_pair_group &G);
 int pmk_pair_result(pm_ctx *ctx, const uint64_t *dkey, const int32_t *dn_good, const int32_t *dn_inl, const double *dF,
                     int n_max, int m, pm_pair_result *dres);
 int pmk_ransac_pick(pm_ctx *ctx, const uint64_t *dkey, const float *dF32, int id_base, int n_models, float *dFw);

@@ -50,7 +50,9 @@ __device__ void rank2_project3(double (&F)[9])
             double a = 0, b = 0, g = 0;
 #pragma unroll
             for (int k = 0; k < 3; ++k) { a += A[k * 3 + p] * A[k * 3 + p]; b += A[k * 3 + q] * A[k * 3 + q]; g += A[k * 3 + p] * A[k * 3 + q]; }
-            if (g == 0.0 || fabs(g) <= 1e-17 * sqrt(a * b)) continue;
+            // converged when the columns are orthogonal to working precision.  (The first version asked for 1e-17, below
+            // the rounding noise of g itself: almost every matrix then ran all 30 sweeps -- 62 us per launch of the projection.)
+            if (g == 0.0 || g * g <= 5.3e-32 * (a * b)) continue;
             changed = true;
             const double zeta = (b - a) / (2 * g);
             const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1 + zeta * zeta));
@@ -155,6 +157,12 @@ __device__ __forceinline__ int eff_n(int n, const int32_t *n_dev)
     return n_dev ? min(n, max(*n_dev, 0)) : n;
 }
 
+// Grouped launches of the pair pipeline (BASELINE config 5): several image pairs share ONE launch of every RANSAC kernel --
+// the pair is a grid dimension and every per-pair array advances by its stride.  s[k] is the element stride of the k-th
+// pointer argument of the kernel in declaration order (zero strides + a unit grid dimension = the single-problem call).
+struct PairStride { long long s[8]; };
+static const PairStride PS0 = {{0, 0, 0, 0, 0, 0, 0, 0}};
+
 // =====================================================================================
 // K6: minimal solvers, 8 lanes per hypothesis
 // =====================================================================================
@@ -163,8 +171,10 @@ template <int M>
 __global__ void __launch_bounds__(SOLVE_THREADS)
 ransac_solve_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2, int n,
                     const int32_t *__restrict__ samples, int n_hyp, float *__restrict__ Fout, const int32_t *n_dev,
-                    double *__restrict__ Fout64)
+                    double *__restrict__ Fout64, double *__restrict__ hand, PairStride ps)
 {
+    { const long long pb = blockIdx.y; p1 += pb * ps.s[0]; p2 += pb * ps.s[1]; samples += pb * ps.s[2]; Fout += pb * ps.s[3]; if (n_dev) n_dev += pb * ps.s[4];
+      if (hand) hand += pb * (long long)n_hyp * 16; }
     n = eff_n(n, n_dev);
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int h = gtid >> 3, sub = threadIdx.x & 7;
@@ -249,49 +259,15 @@ ransac_solve_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2
         for (int i = k; i < 9; ++i) { z[i] -= s * v[i]; if (M == 7) z2[i] -= t * v[i]; }
     }
     if (M == 8) {
-        // The rank-2 projection (3x3 Jacobi with FP64 divides and square roots) is the long tail of the
-        // solve and runs on ONE lane per hypothesis: hand the 32 hypotheses of the block to the 32 lanes
-        // of warp 0 through shared memory instead of running it 8 times with 4 active lanes each.
-        __shared__ double hand[SOLVE_THREADS / 8][16];
-        const int slot = threadIdx.x >> 3;
-        if (sub == 0) {
+        // The rank-2 projection (3x3 Jacobi with FP64 divides and square roots) is the long, serial tail of the solve and
+        // needs ONE lane per hypothesis: it runs as a kernel of its own (ransac_project_kernel, one thread per hypothesis)
+        // so that the 8-lane blocks here retire as soon as the null vector is known instead of idling behind one warp.
+        if (live && sub == 0) {
+            double *hnd = hand + (size_t)h * 16;
 #pragma unroll
-            for (int i = 0; i < 9; ++i) hand[slot][i] = z[i];
-            hand[slot][9] = s1; hand[slot][10] = s2; hand[slot][11] = c1x; hand[slot][12] = c1y;
-            hand[slot][13] = c2x; hand[slot][14] = c2y; hand[slot][15] = (live && valid) ? 1.0 : 0.0;
+            for (int i = 0; i < 9; ++i) hnd[i] = z[i];
+            hnd[9] = s1; hnd[10] = s2; hnd[11] = c1x; hnd[12] = c1y; hnd[13] = c2x; hnd[14] = c2y; hnd[15] = valid ? 1.0 : 0.0;
         }
-        __syncthreads();
-        if (threadIdx.x >= SOLVE_THREADS / 8) return;
-        const int hh = blockIdx.x * (SOLVE_THREADS / 8) + threadIdx.x;
-        if (hh >= n_hyp) return;
-        double F0[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) F0[i] = hand[threadIdx.x][i];
-        s1 = hand[threadIdx.x][9]; s2 = hand[threadIdx.x][10]; c1x = hand[threadIdx.x][11]; c1y = hand[threadIdx.x][12];
-        c2x = hand[threadIdx.x][13]; c2y = hand[threadIdx.x][14]; valid = hand[threadIdx.x][15] != 0.0;
-        rank2_project3(F0);
-        // F = T2^T F0 T1, T = [s 0 -s cx; 0 s -s cy; 0 0 1]
-        double Mx[9];
-        Mx[0] = s2 * F0[0]; Mx[1] = s2 * F0[1]; Mx[2] = s2 * F0[2];
-        Mx[3] = s2 * F0[3]; Mx[4] = s2 * F0[4]; Mx[5] = s2 * F0[5];
-        Mx[6] = -s2 * c2x * F0[0] - s2 * c2y * F0[3] + F0[6];
-        Mx[7] = -s2 * c2x * F0[1] - s2 * c2y * F0[4] + F0[7];
-        Mx[8] = -s2 * c2x * F0[2] - s2 * c2y * F0[5] + F0[8];
-        double F[9];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            F[i * 3 + 0] = Mx[i * 3 + 0] * s1;
-            F[i * 3 + 1] = Mx[i * 3 + 1] * s1;
-            F[i * 3 + 2] = -Mx[i * 3 + 0] * s1 * c1x - Mx[i * 3 + 1] * s1 * c1y + Mx[i * 3 + 2];
-        }
-        if (fabs(F[8]) > FLT_EPSILON) {
-            const double inv = 1.0 / F[8];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) F[i] *= inv;
-        }
-#pragma unroll
-        for (int i = 0; i < 9; ++i) valid = valid && isfinite(F[i]);
-        store_model(Fout + (size_t)hh * 12, F, valid, Fout64 ? Fout64 + (size_t)hh * 9 : nullptr);
     } else {
         if (!live || sub != 0) return;
         // 7-point: det(lambda*f1 + (1-lambda)*f2) = 0  (OpenCV run7Point)
@@ -343,6 +319,45 @@ ransac_solve_kernel(const float2 *__restrict__ p1, const float2 *__restrict__ p2
             store_model(Fout + ((size_t)h * 3 + k) * 12, F, ok, Fout64 ? Fout64 + ((size_t)h * 3 + k) * 9 : nullptr);
         }
     }
+}
+
+// Second half of the 8-point solve: rank-2 projection of the null vector's 3x3, de-normalisation, F[8] = 1.  One thread per
+// hypothesis (hand[h] = {z[9], s1, s2, c1x, c1y, c2x, c2y, valid}); blockIdx.y = pair of a grouped launch.
+__global__ void __launch_bounds__(128)
+ransac_project_kernel(const double *__restrict__ hand, int n_hyp, float *__restrict__ Fout, double *__restrict__ Fout64, long long f_stride)
+{
+    const int hh = blockIdx.x * blockDim.x + threadIdx.x;
+    if (hh >= n_hyp) return;
+    hand += (size_t)blockIdx.y * n_hyp * 16 + (size_t)hh * 16;
+    Fout += (long long)blockIdx.y * f_stride;
+    double F0[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) F0[i] = hand[i];
+    const double s1 = hand[9], s2 = hand[10], c1x = hand[11], c1y = hand[12], c2x = hand[13], c2y = hand[14];
+    bool valid = hand[15] != 0.0;
+    rank2_project3(F0);
+    // F = T2^T F0 T1, T = [s 0 -s cx; 0 s -s cy; 0 0 1]
+    double Mx[9];
+    Mx[0] = s2 * F0[0]; Mx[1] = s2 * F0[1]; Mx[2] = s2 * F0[2];
+    Mx[3] = s2 * F0[3]; Mx[4] = s2 * F0[4]; Mx[5] = s2 * F0[5];
+    Mx[6] = -s2 * c2x * F0[0] - s2 * c2y * F0[3] + F0[6];
+    Mx[7] = -s2 * c2x * F0[1] - s2 * c2y * F0[4] + F0[7];
+    Mx[8] = -s2 * c2x * F0[2] - s2 * c2y * F0[5] + F0[8];
+    double F[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        F[i * 3 + 0] = Mx[i * 3 + 0] * s1;
+        F[i * 3 + 1] = Mx[i * 3 + 1] * s1;
+        F[i * 3 + 2] = -Mx[i * 3 + 0] * s1 * c1x - Mx[i * 3 + 1] * s1 * c1y + Mx[i * 3 + 2];
+    }
+    if (fabs(F[8]) > FLT_EPSILON) {
+        const double inv = 1.0 / F[8];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) F[i] *= inv;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) valid = valid && isfinite(F[i]);
+    store_model(Fout + (size_t)hh * 12, F, valid, Fout64 ? Fout64 + (size_t)hh * 9 : nullptr);
 }
 
 // =====================================================================================
@@ -429,9 +444,10 @@ __device__ __forceinline__ void sc_cp_async16(void *smem, const void *gmem)
 template <int METRIC, int MPT>
 __global__ void __launch_bounds__(SC_THREADS)
 ransac_score_kernel(const float4 *__restrict__ pts, int n, int chunk_pts, const float *__restrict__ Fm,
-                    int n_models, float thr2, int32_t *__restrict__ counts, int use_atomic, const int32_t *n_dev)
+                    int n_models, float thr2, int32_t *__restrict__ counts, int use_atomic, const int32_t *n_dev, PairStride ps)
 {
     __shared__ __align__(16) float4 tile[2][SC_TILE];
+    { const long long pb = blockIdx.z; pts += pb * ps.s[0]; Fm += pb * ps.s[1]; counts += pb * ps.s[2]; if (n_dev) n_dev += pb * ps.s[3]; }
     n = eff_n(n, n_dev);
     const int tid = threadIdx.x;
     const int m0 = blockIdx.x * (SC_THREADS * MPT);
@@ -510,9 +526,10 @@ ransac_best_kernel(const int32_t *__restrict__ counts, int n_models, int id_base
 // same winner as ransac_best_kernel + ransac_pick_kernel (max over the same keys).
 __global__ void __launch_bounds__(1024)
 ransac_best_pick_kernel(const int32_t *__restrict__ counts, int n_models, int id_base, const float *__restrict__ Fm,
-                        unsigned long long *key_out, float *Fw, int32_t *n_inl)
+                        unsigned long long *key_out, float *Fw, int32_t *n_inl, PairStride ps)
 {
     __shared__ unsigned long long sh[32];
+    { const long long pb = blockIdx.x; counts += pb * ps.s[0]; Fm += pb * ps.s[1]; key_out += pb * ps.s[2]; Fw += pb * ps.s[3]; if (n_inl) n_inl += pb * ps.s[4]; }
     unsigned long long best = 0;
     for (int m = threadIdx.x; m < n_models; m += blockDim.x) {
         const int c = counts[m];
@@ -575,8 +592,9 @@ __global__ void ransac_update_best_kernel(const unsigned long long *key, const f
 template <int METRIC>
 __global__ void __launch_bounds__(256)
 ransac_mask_kernel(const float4 *__restrict__ pts, int n, const float *__restrict__ Fw, float thr2,
-                   uint8_t *__restrict__ mask, int32_t *n_inl, const int32_t *n_dev)
+                   uint8_t *__restrict__ mask, int32_t *n_inl, const int32_t *n_dev, PairStride ps)
 {
+    { const long long pb = blockIdx.y; pts += pb * ps.s[0]; Fw += pb * ps.s[1]; mask += pb * ps.s[2]; n_inl += pb * ps.s[3]; if (n_dev) n_dev += pb * ps.s[4]; }
     n = eff_n(n, n_dev);
     float F[9];
 #pragma unroll
@@ -615,8 +633,10 @@ __device__ void block_reduce_store(double (&v)[NV], double *dst)
 
 // pass 1: sums of x1,y1,x2,y2 and the count over the selected points
 __global__ void __launch_bounds__(RF_THREADS)
-refit_sum_kernel(const float4 *__restrict__ pts, int n, const uint8_t *__restrict__ mask, double *partial, const int32_t *n_dev)
+refit_sum_kernel(const float4 *__restrict__ pts, int n, const uint8_t *__restrict__ mask, double *partial, const int32_t *n_dev,
+                 PairStride ps)
 {
+    { const long long pb = blockIdx.y; pts += pb * ps.s[0]; if (mask) mask += pb * ps.s[1]; partial += pb * ps.s[2]; if (n_dev) n_dev += pb * ps.s[3]; }
     n = eff_n(n, n_dev);
     double v[5] = {0, 0, 0, 0, 0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -660,9 +680,11 @@ __device__ __forceinline__ void refit_scale_inblock(const double *__restrict__ p
 // pass 2: mean distances to the centroids.  fused != 0: the centroids come from pass 1's partial sums (partial_in)
 __global__ void __launch_bounds__(RF_THREADS)
 refit_scale_kernel(const float4 *__restrict__ pts, int n, const uint8_t *__restrict__ mask,
-                   double *__restrict__ stats, double *partial, const int32_t *n_dev, const double *partial_in)
+                   double *__restrict__ stats, double *partial, const int32_t *n_dev, const double *partial_in, PairStride ps)
 {
     __shared__ double sst[8];
+    { const long long pb = blockIdx.y; pts += pb * ps.s[0]; if (mask) mask += pb * ps.s[1]; stats += pb * ps.s[2]; partial += pb * ps.s[3];
+      if (n_dev) n_dev += pb * ps.s[4]; if (partial_in) partial_in += pb * ps.s[5]; }
     n = eff_n(n, n_dev);
     if (partial_in) refit_mean_inblock(partial_in, sst, stats);
     else { if (threadIdx.x < 5) sst[threadIdx.x] = stats[threadIdx.x]; __syncthreads(); }
@@ -679,9 +701,11 @@ refit_scale_kernel(const float4 *__restrict__ pts, int n, const uint8_t *__restr
 // pass 3: upper triangle of the 9x9 normal matrix sum r r^T (45 entries)
 __global__ void __launch_bounds__(RF_THREADS)
 refit_ata_kernel(const float4 *__restrict__ pts, int n, const uint8_t *__restrict__ mask,
-                 double *__restrict__ stats, double *partial, const int32_t *n_dev, const double *partial_in)
+                 double *__restrict__ stats, double *partial, const int32_t *n_dev, const double *partial_in, PairStride ps)
 {
     __shared__ double sst[8];
+    { const long long pb = blockIdx.y; pts += pb * ps.s[0]; if (mask) mask += pb * ps.s[1]; stats += pb * ps.s[2]; partial += pb * ps.s[3];
+      if (n_dev) n_dev += pb * ps.s[4]; if (partial_in) partial_in += pb * ps.s[5]; }
     n = eff_n(n, n_dev);
     if (threadIdx.x < 5) sst[threadIdx.x] = stats[threadIdx.x];      // centroids and count (pass 2's block 0 wrote them)
     __syncthreads();
@@ -719,14 +743,31 @@ __device__ __forceinline__ void write_pair_result(const PairOut &po, const doubl
     po.res->has_model = ok; po.res->reserved = 0;
 }
 
+// no refit: the record carries the winning minimal model itself (one warp per pair of a grouped launch)
+__global__ void pair_group_result_kernel(const float *__restrict__ Fw, long long fw_stride, PairOut po, PairStride ps)
+{
+    const long long pb = blockIdx.x;
+    Fw += pb * fw_stride;
+    po.key += pb * ps.s[4]; po.n_good += pb * ps.s[5]; po.n_inl += pb * ps.s[6]; po.res += pb * ps.s[7];
+    if (threadIdx.x != 0) return;
+    double F[9];
+    for (int i = 0; i < 9; ++i) F[i] = (double)Fw[i];
+    write_pair_result(po, F);
+}
+
 // pass 4 (one warp): 9x9 cyclic Jacobi (lanes 0..8 each own index k of the rotation
 // updates), smallest eigenvector, rank-2 projection, de-normalisation.  Falls back to the
 // winning minimal model when there are < 8 points or the system is degenerate.
 __global__ void __launch_bounds__(32)
 refit_solve_kernel(const double *__restrict__ partial, const double *__restrict__ stats,
-                   const float *__restrict__ Ffallback, double *__restrict__ Fout, int32_t *ok_out, PairOut po)
+                   const float *__restrict__ Ffallback, double *__restrict__ Fout, int32_t *ok_out, PairOut po, PairStride ps)
 {
     __shared__ double A[81], V[81];
+    {   // one warp (block) per pair in a grouped launch
+        const long long pb = blockIdx.x;
+        partial += pb * ps.s[0]; stats += pb * ps.s[1]; if (Ffallback) Ffallback += pb * ps.s[2]; Fout += pb * ps.s[3];
+        if (po.res) { po.key += pb * ps.s[4]; po.n_good += pb * ps.s[5]; po.n_inl += pb * ps.s[6]; po.res += pb * ps.s[7]; }
+    }
     const int lane = threadIdx.x;
     for (int e = lane; e < 81; e += 32) { A[e] = 0; V[e] = (e % 10 == 0) ? 1.0 : 0.0; }
     __syncwarp();
@@ -1035,13 +1076,13 @@ int run_refit(pm_ctx *ctx, const float4 *pts, int n, const uint8_t *dmask, const
     // one partial-sum region per pass (a pass reads the previous pass's partials while it writes its own)
     PM_WS(ctx, ws, double *, WS_REFIT, (size_t)(RF_BLOCKS * (5 + 2 + 45) + 16) * sizeof(double));
     double *part1 = ws, *part2 = ws + RF_BLOCKS * 5, *part3 = part2 + RF_BLOCKS * 2, *stats = part3 + RF_BLOCKS * 45;
-    refit_sum_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, part1, dn);
+    refit_sum_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, part1, dn, PS0);
     PM_CHECK_LAUNCH(ctx);
-    refit_scale_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, stats, part2, dn, part1);
+    refit_scale_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, stats, part2, dn, part1, PS0);
     PM_CHECK_LAUNCH(ctx);
-    refit_ata_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, stats, part3, dn, part2);
+    refit_ata_kernel<<<RF_BLOCKS, RF_THREADS, 0, ctx->stream>>>(pts, n, dmask, stats, part3, dn, part2, PS0);
     PM_CHECK_LAUNCH(ctx);
-    refit_solve_kernel<<<1, 32, 0, ctx->stream>>>(part3, stats, dFfallback, dF, dok, po);
+    refit_solve_kernel<<<1, 32, 0, ctx->stream>>>(part3, stats, dFfallback, dF, dok, po, PS0);
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }
@@ -1053,10 +1094,14 @@ int pmk_ransac_solve(pm_ctx *ctx, const float *dp1, const float *dp2, int n, con
 {
     if (n_hyp <= 0) return PM_OK;
     const int blocks = pm_cdiv(n_hyp * 8, SOLVE_THREADS);
-    if (m == 8)
-        ransac_solve_kernel<8><<<blocks, SOLVE_THREADS, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dsamples, n_hyp, dF32, dn, dF64);
-    else
-        ransac_solve_kernel<7><<<blocks, SOLVE_THREADS, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dsamples, n_hyp, dF32, dn, dF64);
+    if (m == 8) {
+        PM_WS(ctx, hand, double *, WS_HAND, (size_t)n_hyp * 16 * sizeof(double));
+        ransac_solve_kernel<8><<<blocks, SOLVE_THREADS, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dsamples, n_hyp, dF32, dn, dF64, hand, PS0);
+        PM_CHECK_LAUNCH(ctx);
+        ransac_project_kernel<<<pm_cdiv(n_hyp, 128), 128, 0, ctx->stream>>>(hand, n_hyp, dF32, dF64, 0);
+    } else {
+        ransac_solve_kernel<7><<<blocks, SOLVE_THREADS, 0, ctx->stream>>>((const float2 *)dp1, (const float2 *)dp2, n, dsamples, n_hyp, dF32, dn, dF64, nullptr, PS0);
+    }
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }
@@ -1091,11 +1136,11 @@ int pmk_ransac_score(pm_ctx *ctx, const float *dp1, const float *dp2, int n, con
     {
         pm_prof_scope prof(ctx, 2);
         if (metric == PM_METRIC_SAMPSON) {
-            if (mpt == 1) ransac_score_kernel<PM_METRIC_SAMPSON, 1><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic, dn);
-            else ransac_score_kernel<PM_METRIC_SAMPSON, SC_MPT><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic, dn);
+            if (mpt == 1) ransac_score_kernel<PM_METRIC_SAMPSON, 1><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic, dn, PS0);
+            else ransac_score_kernel<PM_METRIC_SAMPSON, SC_MPT><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic, dn, PS0);
         } else {
-            if (mpt == 1) ransac_score_kernel<PM_METRIC_SYMEPI, 1><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic, dn);
-            else ransac_score_kernel<PM_METRIC_SYMEPI, SC_MPT><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic, dn);
+            if (mpt == 1) ransac_score_kernel<PM_METRIC_SYMEPI, 1><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic, dn, PS0);
+            else ransac_score_kernel<PM_METRIC_SYMEPI, SC_MPT><<<grid, SC_THREADS, 0, ctx->stream>>>(pts, n, chunk_pts, dF32, n_models, thr2, dcounts, use_atomic, dn, PS0);
         }
     }
     PM_CHECK_LAUNCH(ctx);
@@ -1116,7 +1161,7 @@ int pmk_ransac_best(pm_ctx *ctx, const int32_t *dcounts, int n_models, int id_ba
 int pmk_ransac_best_pick(pm_ctx *ctx, const int32_t *dcounts, int n_models, int id_base, const float *dF32, uint64_t *dkey,
                          float *dFw, int32_t *dn_inl)
 {
-    ransac_best_pick_kernel<<<1, 1024, 0, ctx->stream>>>(dcounts, n_models, id_base, dF32, (unsigned long long *)dkey, dFw, dn_inl);
+    ransac_best_pick_kernel<<<1, 1024, 0, ctx->stream>>>(dcounts, n_models, id_base, dF32, (unsigned long long *)dkey, dFw, dn_inl, PS0);
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }
@@ -1150,9 +1195,9 @@ int pmk_ransac_finish(pm_ctx *ctx, const float *dp1, const float *dp2, int n, co
     const float thr2 = thr * thr;
     if (n > 0) {
         if (metric == PM_METRIC_SAMPSON)
-            ransac_mask_kernel<PM_METRIC_SAMPSON><<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>(pts, n, dFw, thr2, dmask, dn_inl, dn);
+            ransac_mask_kernel<PM_METRIC_SAMPSON><<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>(pts, n, dFw, thr2, dmask, dn_inl, dn, PS0);
         else
-            ransac_mask_kernel<PM_METRIC_SYMEPI><<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>(pts, n, dFw, thr2, dmask, dn_inl, dn);
+            ransac_mask_kernel<PM_METRIC_SYMEPI><<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>(pts, n, dFw, thr2, dmask, dn_inl, dn, PS0);
         PM_CHECK_LAUNCH(ctx);
     }
     // dres: the pair pipeline's record; with a refit its last kernel writes it, else a kernel of its own
@@ -1219,8 +1264,9 @@ int pmk_lmeds_finish(pm_ctx *ctx, const float *dp1, const float *dp2, int n, con
 // sets are identical to the host generator's -- one thread per hypothesis.
 // h_base: row h of `out` is hypothesis h_base + h of the stream (batches / shards of one job draw disjoint ranges).
 __global__ void sample_sets_kernel(int n_points, int n_hyp, int m, unsigned long long seed, int32_t *__restrict__ out,
-                                   const int32_t *n_dev, int h_base)
+                                   const int32_t *n_dev, int h_base, PairStride ps)
 {
+    { const long long pb = blockIdx.y; out += pb * ps.s[0]; if (n_dev) n_dev += pb * ps.s[1]; seed += (unsigned long long)(pb * ps.s[2]); }
     n_points = eff_n(n_points, n_dev);
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= n_hyp) return;
@@ -1248,7 +1294,7 @@ __global__ void sample_sets_kernel(int n_points, int n_hyp, int m, unsigned long
 int pmk_sample_sets(pm_ctx *ctx, int n_points, int n_hyp, int m, uint64_t seed, int32_t *dout, const int32_t *dn, int h_base)
 {
     if (n_hyp <= 0) return PM_OK;
-    sample_sets_kernel<<<pm_cdiv(n_hyp, 128), 128, 0, ctx->stream>>>(n_points, n_hyp, m, (unsigned long long)seed, dout, dn, h_base);
+    sample_sets_kernel<<<pm_cdiv(n_hyp, 128), 128, 0, ctx->stream>>>(n_points, n_hyp, m, (unsigned long long)seed, dout, dn, h_base, PS0);
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }
@@ -1300,6 +1346,94 @@ int pmk_ransac_winner_resolve(pm_ctx *ctx, const float *dp1, const float *dp2, i
     if (st != PM_OK) return st;
     winner_pick_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long *)dkey, dF3, per, dFw);
     PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}
+
+// The RANSAC half of the pair pipeline for a GROUP of image pairs in ONE launch per kernel (the pair is a grid
+// dimension): sample sets, minimal solves, scoring, winner, mask, the three refit passes and the refit solve -- nine
+// launches for the whole group instead of nine per pair, and grids large enough to fill the GPU (one pair's 4096
+// hypotheses are 0.43 waves of the solver and 0.27 of the scorer).  Slot b of every array belongs to pair b of the group;
+// the arithmetic per pair is exactly that of the single-pair calls.
+int pmk_pair_group_ransac(pm_ctx *ctx, const pm_pair_group &G)
+{
+    const int P = G.n_pairs, m = G.m, per = m == 8 ? 1 : 3, nh = G.n_hyp, nm = nh * per, nmax = G.nmax;
+    if (P <= 0) return PM_OK;
+    const long long sF = (long long)(nm + 1) * 12, sKeyI = 16 /* ints per 64-byte key record */;
+    const int32_t *n_good = reinterpret_cast<const int32_t *>(G.key + 2);     // [b]: + b * 16 ints
+    int32_t *n_inl = reinterpret_cast<int32_t *>(G.key + 2) + 1;
+    float *Fw = G.F32 + (size_t)nm * 12;                                       // slot b: + b * sF
+    // sample sets: pair b draws from seed0 + b, bounded by its own match count
+    sample_sets_kernel<<<dim3(pm_cdiv(nh, 128), P), 128, 0, ctx->stream>>>(nmax, nh, m, (unsigned long long)G.seed0, G.samples, n_good, 0,
+                                                                           PairStride{{(long long)nh * m, sKeyI, 1, 0, 0, 0, 0, 0}});
+    PM_CHECK_LAUNCH(ctx);
+    {
+        const dim3 grid(pm_cdiv(nh * 8, SOLVE_THREADS), P);
+        const PairStride ps = {{nmax, nmax, (long long)nh * m, sF, sKeyI, 0, 0, 0}};
+        if (m == 8) {
+            PM_WS(ctx, hand, double *, WS_HAND, (size_t)P * nh * 16 * sizeof(double));
+            ransac_solve_kernel<8><<<grid, SOLVE_THREADS, 0, ctx->stream>>>(G.p1, G.p2, nmax, G.samples, nh, G.F32, n_good, nullptr, hand, ps);
+            PM_CHECK_LAUNCH(ctx);
+            ransac_project_kernel<<<dim3(pm_cdiv(nh, 128), P), 128, 0, ctx->stream>>>(hand, nh, G.F32, nullptr, sF);
+        } else {
+            ransac_solve_kernel<7><<<grid, SOLVE_THREADS, 0, ctx->stream>>>(G.p1, G.p2, nmax, G.samples, nh, G.F32, n_good, nullptr, nullptr, ps);
+        }
+        PM_CHECK_LAUNCH(ctx);
+    }
+    {
+        // scoring: 4 models per thread when that still leaves >= 8 CTAs per SM with 512-point chunks, else 1 model per
+        // thread (a group of 8 pairs x 4096 hypotheses x 4096 matches: 2048 CTAs instead of 128)
+        int mpt = SC_MPT;
+        if ((long long)pm_cdiv(nm, SC_THREADS * SC_MPT) * pm_cdiv(nmax, SC_TILE) * P < 8 * ctx->num_sms) mpt = 1;
+        const int mblocks = pm_cdiv(nm, SC_THREADS * mpt);
+        int chunks = 1;
+        if ((long long)mblocks * P < 8 * ctx->num_sms && nmax > SC_TILE)
+            chunks = min(pm_cdiv(8 * ctx->num_sms, mblocks * P), pm_cdiv(nmax, SC_TILE));
+        int chunk_pts = pm_round_up(pm_cdiv(nmax, chunks), SC_TILE);
+        chunks = pm_cdiv(nmax, chunk_pts);
+        const int use_atomic = chunks > 1;
+        if (use_atomic) PM_CUDA(ctx, cudaMemsetAsync(G.counts, 0, (size_t)P * nm * 4, ctx->stream));
+        const float thr2 = G.threshold * G.threshold;
+        const dim3 grid(mblocks, chunks, P);
+        const PairStride ps = {{nmax, sF, nm, sKeyI, 0, 0, 0, 0}};
+        pm_prof_scope prof(ctx, 2);
+        if (G.metric == PM_METRIC_SAMPSON) {
+            if (mpt == 1) ransac_score_kernel<PM_METRIC_SAMPSON, 1><<<grid, SC_THREADS, 0, ctx->stream>>>(G.pts4, nmax, chunk_pts, G.F32, nm, thr2, G.counts, use_atomic, n_good, ps);
+            else ransac_score_kernel<PM_METRIC_SAMPSON, SC_MPT><<<grid, SC_THREADS, 0, ctx->stream>>>(G.pts4, nmax, chunk_pts, G.F32, nm, thr2, G.counts, use_atomic, n_good, ps);
+        } else {
+            if (mpt == 1) ransac_score_kernel<PM_METRIC_SYMEPI, 1><<<grid, SC_THREADS, 0, ctx->stream>>>(G.pts4, nmax, chunk_pts, G.F32, nm, thr2, G.counts, use_atomic, n_good, ps);
+            else ransac_score_kernel<PM_METRIC_SYMEPI, SC_MPT><<<grid, SC_THREADS, 0, ctx->stream>>>(G.pts4, nmax, chunk_pts, G.F32, nm, thr2, G.counts, use_atomic, n_good, ps);
+        }
+    }
+    PM_CHECK_LAUNCH(ctx);
+    ransac_best_pick_kernel<<<P, 1024, 0, ctx->stream>>>(G.counts, nm, 0, G.F32, (unsigned long long *)G.key, Fw, n_inl,
+                                                         PairStride{{nm, sF, 8, sF, sKeyI, 0, 0, 0}});
+    PM_CHECK_LAUNCH(ctx);
+    const float thr2 = G.threshold * G.threshold;
+    {
+        const dim3 grid(pm_cdiv(nmax, 256), P);
+        const PairStride ps = {{nmax, sF, nmax, sKeyI, sKeyI, 0, 0, 0}};
+        if (G.metric == PM_METRIC_SAMPSON) ransac_mask_kernel<PM_METRIC_SAMPSON><<<grid, 256, 0, ctx->stream>>>(G.pts4, nmax, Fw, thr2, G.mask, n_inl, n_good, ps);
+        else ransac_mask_kernel<PM_METRIC_SYMEPI><<<grid, 256, 0, ctx->stream>>>(G.pts4, nmax, Fw, thr2, G.mask, n_inl, n_good, ps);
+        PM_CHECK_LAUNCH(ctx);
+    }
+    const long long sR = RF_BLOCKS * (5 + 2 + 45) + 16;
+    double *part1 = G.refit, *part2 = part1 + RF_BLOCKS * 5, *part3 = part2 + RF_BLOCKS * 2, *stats = part3 + RF_BLOCKS * 45;
+    const PairOut po = {(const unsigned long long *)G.key, n_good, n_inl, nmax, m, G.res};
+    if (G.refit_on) {
+        refit_sum_kernel<<<dim3(RF_BLOCKS, P), RF_THREADS, 0, ctx->stream>>>(G.pts4, nmax, G.mask, part1, n_good, PairStride{{nmax, nmax, sR, sKeyI, 0, 0, 0, 0}});
+        PM_CHECK_LAUNCH(ctx);
+        refit_scale_kernel<<<dim3(RF_BLOCKS, P), RF_THREADS, 0, ctx->stream>>>(G.pts4, nmax, G.mask, stats, part2, n_good, part1,
+                                                                              PairStride{{nmax, nmax, sR, sR, sKeyI, sR, 0, 0}});
+        PM_CHECK_LAUNCH(ctx);
+        refit_ata_kernel<<<dim3(RF_BLOCKS, P), RF_THREADS, 0, ctx->stream>>>(G.pts4, nmax, G.mask, stats, part3, n_good, part2,
+                                                                            PairStride{{nmax, nmax, sR, sR, sKeyI, sR, 0, 0}});
+        PM_CHECK_LAUNCH(ctx);
+        refit_solve_kernel<<<P, 32, 0, ctx->stream>>>(part3, stats, Fw, G.Fout, nullptr, po, PairStride{{sR, sR, sF, 16, 8, sKeyI, sKeyI, 1}});
+        PM_CHECK_LAUNCH(ctx);
+    } else {
+        pair_group_result_kernel<<<P, 32, 0, ctx->stream>>>(Fw, sF, po, PairStride{{0, 0, 0, 0, 8, sKeyI, sKeyI, 1}});
+        PM_CHECK_LAUNCH(ctx);
+    }
     return PM_OK;
 }
 
