@@ -48,11 +48,12 @@ def load_peaks():
         return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
-def config_dict(n_gpus):
+def config_dict(n_gpus, lanes=4):
     return {"workload": "cfg2: synthetic SIFT-like 128-d f32 descriptors 10000x10000, L2 kNN-2 + ratio 0.75",
             "nq_per_gpu": NQ, "nt": NT, "dim": DIM, "ratio": RATIO,
             "sharding": "query rows per rank, train replicated" if n_gpus > 1 else "single GPU",
-            "l2_policy": f"rotating {POOL} distinct input sets ({POOL * (NQ + NT) * DIM * 4 / 1e6:.0f} MB) > 126 MB L2"}
+            "l2_policy": f"rotating {POOL} distinct input sets ({POOL * (NQ + NT) * DIM * 4 / 1e6:.0f} MB) > 126 MB L2",
+            "gpu_lanes": lanes}
 
 
 class ClockSampler:
@@ -166,7 +167,7 @@ def run_reference(args):
     sample = f"{rows} of {NQ} query rows x {NT} train rows per step; {desc}"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args.gpus),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args.gpus, args.lanes),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -228,24 +229,59 @@ def run_ours(args):
     ngood = torch.zeros(4, dtype=torch.int32, device=dev)
     qbase = rank * NQ
 
-    # consecutive steps overlap: K1 of step i+1 runs while K3 / K5 of step i drain (pm_set_pipelining; the
-    # inputs are resident and complete before the loop starts, as that mode requires)
-    ctx.set_pipelining(not args.no_pipelining)
+    # Lanes: the steps of the timed loop go round-robin over `--lanes` contexts (own stream, own workspaces, own output
+    # buffers each) -- every step is still one whole pass K1 -> K2 -> K3 -> K5 over its own input set, but the launch
+    # hand-offs and the small kernels of one lane run under the GEMM of another.  One lane: consecutive steps overlap
+    # through pm_set_pipelining instead (K1 of step i+1 under K3 / K5 of step i; the inputs are resident and complete
+    # before the loop starts, as that mode requires).  Lane 0 is `ctx`: every other leg, and the per-kernel timing, use it alone.
+    n_lanes = max(1, args.lanes)
+    pipelining = (not args.no_pipelining) and n_lanes == 1
+    ctx.set_pipelining(pipelining)
+    lane_ctx, lane_stream, lane_out = [ctx], [stream], [(knn, good, ngood)]
+    for _ in range(1, n_lanes):
+        c = pm.Context(local)
+        s_ = torch.cuda.Stream(device=dev)
+        c.set_stream(s_.cuda_stream)
+        lane_ctx.append(c); lane_stream.append(s_)
+        lane_out.append((torch.zeros_like(knn), torch.zeros_like(good), torch.zeros_like(ngood)))
 
     # one device-resident C-ABI call per step: K1 pack -> K2 GEMM + fused top-2 -> K3 re-rank -> K5 ratio test + compaction.
     # The ctypes arguments are built once (a step is ~34 us of GPU work: per-call Python argument marshalling is not free)
     import ctypes as C
     from points_matching_b200 import _lib as _pmlib
     _fn = _pmlib.lib().pm_knn2_ratio_l2_f32_dev
-    _h = ctx._h
     _pool_args = [(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr())) for a, b in pool]
     _nq, _nt, _dim, _ratio, _base = C.c_int(NQ), C.c_int(NT), C.c_int(DIM), C.c_float(RATIO), C.c_int(qbase)
-    _knn, _good, _ngood = C.c_void_p(knn.data_ptr()), C.c_void_p(good.data_ptr()), C.c_void_p(ngood.data_ptr())
+    _lane_args = [(c._h, C.c_void_p(o[0].data_ptr()), C.c_void_p(o[1].data_ptr()), C.c_void_p(o[2].data_ptr()))
+                  for c, o in zip(lane_ctx, lane_out)]
 
-    def step(i):
+    def step_on(lane, i):
         a, b = _pool_args[i % POOL]
-        if _fn(_h, a, _nq, b, _nt, _dim, _ratio, _base, _knn, _good, _ngood) != 0:
-            ctx._chk(-2)
+        h, k_, g_, n_ = _lane_args[lane]
+        if _fn(h, a, _nq, b, _nt, _dim, _ratio, _base, k_, g_, n_) != 0:
+            lane_ctx[lane]._chk(-2)
+
+    def step(i):                                     # lane 0 alone (per-kernel timing, parity, the other legs)
+        step_on(0, i)
+
+    def join_lanes():                                # lane 0's stream waits for everything the other lanes have queued
+        for s_ in lane_stream[1:]:
+            e = torch.cuda.Event()
+            e.record(s_)
+            stream.wait_event(e)
+
+    def timed_loop(n):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for s_ in lane_stream[1:]:                   # no lane starts before the opening event
+            s_.wait_event(a)
+        for i in range(n):
+            step_on(i % n_lanes, i)
+        join_lanes()
+        b.record(stream)
+        barrier()
+        return a.elapsed_time(b)
 
     steps, warm = max(1, args.steps), max(3, args.warmup)
     sampler = ClockSampler(local) if rank == 0 else None
@@ -254,21 +290,29 @@ def run_ours(args):
     ramp = 0
     while time.perf_counter() < t_end:
         for i in range(50):
-            step(ramp + i)
+            step_on((ramp + i) % n_lanes, ramp + i)
         ramp += 50
         torch.cuda.synchronize()
-    for i in range(warm):
-        step(i)
+    for i in range(max(warm, 3 * n_lanes)):
+        step_on(i % n_lanes, i)
     barrier()
-    launches0 = ctx.launch_count()
+    launches0 = sum(c.launch_count() for c in lane_ctx)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for i in range(steps):
-        step(i)
-    ev1.record(stream)
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    launches = ctx.launch_count() - launches0
+    ms_total = timed_loop(steps)
+    launches = sum(c.launch_count() for c in lane_ctx) - launches0
+    # the same loop on lane 0 alone: what one stream of consecutive steps costs (explanatory)
+    ms_single = ms_total
+    if n_lanes > 1:
+        ctx.set_pipelining(not args.no_pipelining)
+        for i in range(warm):
+            step(i)
+        barrier()
+        ev0.record(stream)
+        for i in range(steps):
+            step(i)
+        ev1.record(stream)
+        barrier()
+        ms_single = ev0.elapsed_time(ev1)
     # per-kernel timing for the roofline: the same K steps replayed with an event pair around every
     # K2 launch (kept out of the region above: the event records would serialise the
     # programmatic-dependent-launch overlap between the kernels of a step)
@@ -311,6 +355,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_step = float(tmax.item()) / steps
+    ms_step_single = ms_single / steps
     value = world * NQ * NT / (ms_step * 1e-3)
 
     # ---- roofline of the dominant kernel (K2, tcgen05 GEMM + fused top-k) -----------------
@@ -333,7 +378,11 @@ def run_ours(args):
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "kernel": "l2_tc_kernel (tcgen05.mma cta_group::1 kind::f16 bf16, M128 N128 K16, 256x128 work items, fused top-2 epilogue)",
-                "kernel_ms": k2_avg_ms, "kernel_share_of_step": k2_avg_ms / ms_step if ms_step else None,
+                "kernel_ms": k2_avg_ms,
+                # the event-timed launch against one stream of consecutive steps (with several lanes the step period is
+                # shorter than one event-timed K2: its launch latency and prologue run under the other lanes' kernels --
+                # the in-chain share below is the one that compares with the lane-interleaved step)
+                "kernel_share_of_step": k2_avg_ms / ms_step_single if ms_step_single else None,
                 "peak_source": peaks["source"] + (", sustained bf16 (timed window %.1f s)" % window_s if sustained_window else
                                                   ", BURST bf16 (timed window %.1f ms at the boost clock)" % (window_s * 1e3)),
                 "frac_of_sustained_peak": achieved / peaks["bf16_sustained"],
@@ -356,32 +405,57 @@ def run_ours(args):
         hq.append(pool[k][0].cpu().pin_memory()); ht.append(pool[k][1].cpu().pin_memory())
     hknn = torch.zeros((NQ, 2, 4), dtype=torch.int32).pin_memory()
     hgood = torch.zeros((NQ, 4), dtype=torch.int32).pin_memory()
+    # one host thread per lane, each with its own context and pinned result buffers: a call is synchronous (it returns with
+    # the matches on the host), so the upload of one lane's step runs under the kernels and the download of another's
+    from concurrent.futures import ThreadPoolExecutor
+    lane_host = [(hknn, hgood)] + [(torch.zeros_like(hknn).pin_memory(), torch.zeros_like(hgood).pin_memory()) for _ in lane_ctx[1:]]
+    pool_exec = ThreadPoolExecutor(max_workers=n_lanes)
     e_steps = max(3, min(steps, 200))
     n_host_good = 0
+
+    def host_calls(lane, n_calls, n_active):
+        c, (hk, hg) = lane_ctx[lane], lane_host[lane]
+        r = 0
+        for i in range(lane, n_calls, n_active):
+            r = c.knn2_ratio_l2_ptr(hq[i % 4].data_ptr(), NQ, ht[i % 4].data_ptr(), NT, DIM, RATIO, hk.data_ptr(), hg.data_ptr())
+        return r
+
+    def host_block(n_calls, n_active):
+        if n_active == 1:
+            return host_calls(0, n_calls, 1)
+        futs = [pool_exec.submit(host_calls, l, n_calls, n_active) for l in range(n_active)]
+        return [f.result() for f in futs][0]
+
     t_warm, i = time.perf_counter() + 0.3, 0    # warm-up by time: the first few hundred calls run up to 1.4x slower (host / PCIe side ramping up)
     while time.perf_counter() < t_warm or i < 3:
-        ctx.knn2_ratio_l2_ptr(hq[i % 4].data_ptr(), NQ, ht[i % 4].data_ptr(), NT, DIM, RATIO, hknn.data_ptr(), hgood.data_ptr())
+        host_block(2 * n_lanes, n_lanes)
         i += 1
+
     # five blocks of e_steps / 5 calls; the reported figure is the MEDIAN block (host-side interference -- other
     # tenants on the PCIe switch, the nvidia-smi sampler -- moved single blocks by 2x between otherwise equal runs)
-    e_blocks, e_per = [], max(1, e_steps // 5)
-    for b in range(5):
-        barrier()
-        ev0.record(stream)
-        for i in range(e_per):
-            n_host_good = ctx.knn2_ratio_l2_ptr(hq[i % 4].data_ptr(), NQ, ht[i % 4].data_ptr(), NT, DIM, RATIO,
-                                                hknn.data_ptr(), hgood.data_ptr())
-        ev1.record(stream)
-        barrier()
-        emax = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(emax, op=dist.ReduceOp.MAX)
-        e_blocks.append(float(emax.item()) / e_per)
+    def e2e_blocks(n_active):
+        nonlocal n_host_good
+        blocks, per = [], max(n_active, -(-max(1, e_steps // 5) // n_active) * n_active)
+        for b in range(5):
+            barrier()
+            ev0.record(stream)
+            n_host_good = host_block(per, n_active)
+            ev1.record(stream)          # every call has returned: all lanes' work is complete
+            barrier()
+            emax = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(emax, op=dist.ReduceOp.MAX)
+            blocks.append(float(emax.item()) / per)
+        return blocks, per
+
+    e_blocks, e_per = e2e_blocks(n_lanes)
+    e_one = e_blocks if n_lanes == 1 else e2e_blocks(1)[0]
     e_steps = 5 * e_per
     e_ms = float(np.median(e_blocks))
     e2e = {"value": world * NQ * NT / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
            "h2d_bytes_per_step": (NQ + NT) * DIM * 4, "d2h_bytes_per_step": NQ * 2 * 16 + NQ * 16 + 4,
-           "api": "pm_knn2_ratio_l2_f32 (host buffers, pinned)", "steps": e_steps,
+           "api": "pm_knn2_ratio_l2_f32 (host buffers, pinned)" + (f"; {n_lanes} host threads, one context each" if n_lanes > 1 else ""),
+           "steps": e_steps, "lanes": n_lanes, "ms_per_step_one_lane": float(np.median(e_one)),
            "ms_per_step_blocks": e_blocks, "timing": "median of 5 blocks, max over ranks per block"}
 
     # ---- the same call with SIFT shipped as bytes (pm_knn2_l2_u8: 4x fewer PCIe bytes, identical matches) ----
@@ -392,21 +466,37 @@ def run_ours(args):
         ht8 = torch.from_numpy(t0.astype(np.uint8)).pin_memory()
         L = _lib.lib()
 
-        def u8_call():
-            st = L.pm_knn2_l2_u8(ctx._h, C.c_void_p(hq8.data_ptr()), NQ, C.c_void_p(ht8.data_ptr()), NT, DIM, C.c_void_p(hknn.data_ptr()))
-            assert st == 0, st
+        lane_h = [c._h for c in lane_ctx]
 
-        for _ in range(3):
-            u8_call()
-        barrier()
-        ev0.record(stream)
-        for _ in range(e_steps):
-            u8_call()
-        ev1.record(stream)
-        barrier()
-        u8_ms = ev0.elapsed_time(ev1) / e_steps
+        def u8_calls(lane, n_calls, n_active):
+            out = C.c_void_p(lane_host[lane][0].data_ptr())
+            for _ in range(lane, n_calls, n_active):
+                st = L.pm_knn2_l2_u8(lane_h[lane], C.c_void_p(hq8.data_ptr()), NQ, C.c_void_p(ht8.data_ptr()), NT, DIM, out)
+                assert st == 0, st
+
+        def u8_block(n_calls, n_active):
+            if n_active == 1:
+                return u8_calls(0, n_calls, 1)
+            for f in [pool_exec.submit(u8_calls, l, n_calls, n_active) for l in range(n_active)]:
+                f.result()
+
+        def u8_time(n_active):
+            t_w = time.perf_counter() + 0.1
+            while time.perf_counter() < t_w:
+                u8_block(2 * n_active, n_active)
+            per = -(-e_steps // n_active) * n_active
+            barrier()
+            ev0.record(stream)
+            u8_block(per, n_active)
+            ev1.record(stream)
+            barrier()
+            return ev0.elapsed_time(ev1) / per
+
+        u8_ms = u8_time(n_lanes)
+        u8_one = u8_ms if n_lanes == 1 else u8_time(1)
         e2e["u8_wire_format"] = {"value": world * NQ * NT / (u8_ms * 1e-3), "unit": UNIT, "ms_per_step": u8_ms,
                                  "h2d_bytes_per_step": (NQ + NT) * DIM, "d2h_bytes_per_step": NQ * 2 * 16,
+                                 "lanes": n_lanes, "ms_per_step_one_lane": u8_one,
                                  "api": "pm_knn2_l2_u8 (kNN-2 only, host buffers, pinned)"}
         return None
 
@@ -492,11 +582,14 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": config_dict(world),
+            "config": config_dict(world, n_lanes),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "parity_ok": parity_ok, "secondary": secondary, "extra": extra,
             "notes": {"good_matches_last_step": n_good_last, "clock_ramp_steps": ramp,
-                      "step_overlap": "none" if args.no_pipelining else "pm_set_pipelining: K1 of step i+1 under K3/K5 of step i",
+                      "step_overlap": (f"{n_lanes} lanes: steps round-robin over {n_lanes} contexts (own stream + workspaces), each step one whole "
+                                       "K1-K2-K3-K5 pass over its own input set") if n_lanes > 1 else
+                                      ("none" if args.no_pipelining else "pm_set_pipelining: K1 of step i+1 under K3/K5 of step i"),
+                      "ms_per_step_one_lane": ms_step_single,
                       "dtype_detail": "bf16 operands (exact for 0..255 integers), fp32 accumulate in TMEM, fp32 norms / selection / output"},
             "summary": summary}
     sys.stdout.flush()
@@ -1092,6 +1185,7 @@ def main():
     ap.add_argument("--no-cfg5", action="store_true")
     ap.add_argument("--ransac-steps", type=int, default=5)
     ap.add_argument("--no-pipelining", action="store_true", help="consecutive steps strictly serial (no cross-step overlap)")
+    ap.add_argument("--lanes", type=int, default=4, help="contexts (stream + workspaces each) the timed steps and the e2e calls go round-robin over")
     ap.add_argument("--no-ramp", action="store_true", help="skip the 1 s clock ramp (profiling runs under ncu)")
     args = ap.parse_args()
     start_watchdog(float(os.environ.get("PM_BENCH_WATCHDOG_S", "1200")))
