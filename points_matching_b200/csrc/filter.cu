@@ -241,6 +241,46 @@ __global__ void gather_matches_kernel(const pm_dmatch *__restrict__ m, const int
     if (pts4) pts4[i] = make_float4(a.x, a.y, b.x, b.y);
 }
 
+// ---- cross-check: only the train rows that are somebody's best match need a column minimum ----
+__global__ void cross_mark_kernel(const pm_dmatch *__restrict__ knn, int nq, int stride, int nt, uint8_t *__restrict__ mark)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const int j = knn[(size_t)i * stride].trainIdx;
+    if (j >= 0 && j < nt) mark[j] = 1;
+}
+
+// marked rows -> list (unordered: one warp-aggregated atomic per 32 rows)
+__global__ void cross_list_kernel(const uint8_t *__restrict__ mark, int nt, int *__restrict__ list, int *__restrict__ count)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool m = j < nt && mark[j] != 0;
+    const unsigned b = __ballot_sync(0xffffffffu, m);
+    if (!b) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(b) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(b));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (m) list[base + __popc(b & ((1u << lane) - 1u))] = j;
+}
+
+template <typename V>
+__global__ void cross_gather_rows_kernel(const V *__restrict__ src, int row_elems, const int *__restrict__ list, long long total,
+                                         V *__restrict__ dst)
+{
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / row_elems), w = (int)(idx - (long long)r * row_elems);
+        dst[idx] = src[(size_t)list[r] * row_elems + w];
+    }
+}
+
+__global__ void cross_scatter_kernel(const int *__restrict__ list, int n, const unsigned long long *__restrict__ small_,
+                                     unsigned long long *__restrict__ col)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) col[list[k]] = small_[k];
+}
+
 }  // namespace
 
 int pmk_ratio_filter(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout, int32_t *dn_out,
@@ -253,6 +293,53 @@ int pmk_ratio_filter_tail(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float rati
                           unsigned long long *chain_done, unsigned *chain_ctr, unsigned long long seq, const pm_gather_out *gather)
 {
     return run_compact(ctx, RatioPred{dknn, ratio}, nq, dout, dn_out, chain_done, chain_ctr, seq, gather);
+}
+
+int pmk_cross_mark(pm_ctx *ctx, const pm_dmatch *dknn, int nq, int stride, int nt, uint8_t *dmark)
+{
+    PM_CUDA(ctx, cudaMemsetAsync(dmark, 0, (size_t)nt, ctx->stream));
+    if (nq > 0) {
+        cross_mark_kernel<<<pm_cdiv(nq, 256), 256, 0, ctx->stream>>>(dknn, nq, stride, nt, dmark);
+        PM_CHECK_LAUNCH(ctx);
+    }
+    return PM_OK;
+}
+
+int pmk_cross_list(pm_ctx *ctx, const uint8_t *dmark, int nt, int32_t *dlist, int32_t *dcount)
+{
+    PM_CUDA(ctx, cudaMemsetAsync(dcount, 0, 4, ctx->stream));
+    cross_list_kernel<<<pm_cdiv(nt, 256), 256, 0, ctx->stream>>>(dmark, nt, dlist, dcount);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}
+
+int pmk_cross_gather_rows(pm_ctx *ctx, const void *dsrc, size_t row_bytes, const int32_t *dlist, int n, void *ddst)
+{
+    if (n <= 0) return PM_OK;
+    const uintptr_t al = (uintptr_t)dsrc | (uintptr_t)ddst | (uintptr_t)row_bytes;
+    const int blocks = 8 * ctx->num_sms;
+    if ((al & 15) == 0)
+        cross_gather_rows_kernel<uint4><<<blocks, 256, 0, ctx->stream>>>((const uint4 *)dsrc, (int)(row_bytes / 16), dlist,
+                                                                           (long long)n * (long long)(row_bytes / 16), (uint4 *)ddst);
+    else if ((al & 3) == 0)
+        cross_gather_rows_kernel<uint32_t><<<blocks, 256, 0, ctx->stream>>>((const uint32_t *)dsrc, (int)(row_bytes / 4), dlist,
+                                                                              (long long)n * (long long)(row_bytes / 4), (uint32_t *)ddst);
+    else
+        cross_gather_rows_kernel<uint8_t><<<blocks, 256, 0, ctx->stream>>>((const uint8_t *)dsrc, (int)row_bytes, dlist,
+                                                                             (long long)n * (long long)row_bytes, (uint8_t *)ddst);
+    PM_CHECK_LAUNCH(ctx);
+    return PM_OK;
+}
+
+int pmk_cross_scatter(pm_ctx *ctx, const int32_t *dlist, int n, const uint64_t *dsmall, uint64_t *dcol_best, int nt)
+{
+    PM_CUDA(ctx, cudaMemsetAsync(dcol_best, 0xFF, (size_t)nt * 8, ctx->stream));      // never-marked rows: no candidate
+    if (n > 0) {
+        cross_scatter_kernel<<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>(dlist, n, (const unsigned long long *)dsmall,
+                                                                         (unsigned long long *)dcol_best);
+        PM_CHECK_LAUNCH(ctx);
+    }
+    return PM_OK;
 }
 
 int pmk_cross_check(pm_ctx *ctx, const pm_dmatch *dknn, int nq, int stride, const uint64_t *dcol_best, int nt,

@@ -541,11 +541,10 @@ static int match_cross_host(pm_ctx *ctx, const void *q, int nq, const void *t, i
     int st;
     if (kind == 0) {
         if ((st = pmk_l2_knn2(ctx, dq, nq, dt, nt, width, 0, 0, dknn)) != PM_OK) return st;
-        if ((st = pmk_l2_col_best(ctx, (const float *)dq, nq, (const float *)dt, nt, width, 0, dcol)) != PM_OK) return st;
     } else {
         if ((st = pmk_hamming_knn2(ctx, dq, nq, dt, nt, width, 0, dknn)) != PM_OK) return st;
-        if ((st = pmk_hamming_col_best(ctx, dq, nq, dt, nt, width, 0, dcol)) != PM_OK) return st;
     }
+    if ((st = pmk_cross_col_best(ctx, kind != 0, dq, nq, dt, nt, width, 0, dknn, dcol, nullptr)) != PM_OK) return st;
     if ((st = pmk_cross_check(ctx, dknn, nq, 2, dcol, nt, dout, dn)) != PM_OK) return st;
     if ((st = read_count(ctx, dn, n_out)) != PM_OK) return st;
     if (*n_out) { D2H(ctx, out, dout, (size_t)*n_out * sizeof(pm_dmatch)); PM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); }
@@ -1184,3 +1183,45 @@ int pm_residuals(pm_ctx *ctx, const float *p1, const float *p2, int n, const dou
 }
 
 }  // extern "C"
+
+// Column side of a cross-check (BFMatcher crossCheck = true: (i, j) stays iff i is also the nearest query of train row j).
+// Only train rows that are the best match of some query can ever be asked about, so the reverse pass runs over THOSE
+// rows only: at most (number of queries over all ranks) of the nt rows -- one eighth of them at BASELINE config 3.
+// Falls back to the reverse pass over the whole train set when more than 3/4 of the rows are marked.
+static int g_cross_full = 0;       // debug / test switch: always the full reverse pass
+extern "C" void pm_debug_cross_full(int on) { g_cross_full = on; }
+
+int pmk_cross_col_best(pm_ctx *ctx, int hamming, const void *dq, int nq, const void *dt, int nt, int width, int q_index_base,
+                       const pm_dmatch *dknn, uint64_t *dcol_best, pm_mark_reduce_fn reduce_marks)
+{
+    if (nt <= 0) return PM_OK;
+    const size_t row_bytes = (size_t)width * (hamming ? 1 : 4);
+    int st, n_marked = nt;
+    PM_WS(ctx, mark, uint8_t *, WS_X_MARK, (size_t)nt + 64);
+    PM_WS(ctx, list, int32_t *, WS_X_LIST, (size_t)nt * 4 + 64);
+    int32_t *count = list + nt;
+    if (!g_cross_full) {
+        if ((st = pmk_cross_mark(ctx, dknn, nq, 2, nt, mark)) != PM_OK) return st;
+        if (reduce_marks && (st = reduce_marks(ctx, mark, (size_t)nt)) != PM_OK) return st;
+        if ((st = pmk_cross_list(ctx, mark, nt, list, count)) != PM_OK) return st;
+        if ((st = read_count(ctx, count, &n_marked)) != PM_OK) return st;
+    }
+    if (nq <= 0) {                                   // an empty shard loses every minimum
+        PM_CUDA(ctx, cudaMemsetAsync(dcol_best, 0xFF, (size_t)nt * 8, ctx->stream));
+        return PM_OK;
+    }
+    if (g_cross_full || (long long)n_marked * 4 > (long long)nt * 3)
+        return hamming ? pmk_hamming_col_best(ctx, (const uint8_t *)dq, nq, (const uint8_t *)dt, nt, width, q_index_base, dcol_best)
+                       : pmk_l2_col_best(ctx, (const float *)dq, nq, (const float *)dt, nt, width, q_index_base, dcol_best);
+    if (n_marked > 0) {
+        PM_WS(ctx, rows, uint8_t *, WS_X_ROWS, (size_t)n_marked * row_bytes);
+        PM_WS(ctx, small_, uint64_t *, WS_X_COL, (size_t)n_marked * 8);
+        if ((st = pmk_cross_gather_rows(ctx, dt, row_bytes, list, n_marked, rows)) != PM_OK) return st;
+        st = hamming ? pmk_hamming_col_best(ctx, (const uint8_t *)dq, nq, rows, n_marked, width, q_index_base, small_)
+                     : pmk_l2_col_best(ctx, (const float *)dq, nq, (const float *)rows, n_marked, width, q_index_base, small_);
+        if (st != PM_OK) return st;
+        return pmk_cross_scatter(ctx, list, n_marked, small_, dcol_best, nt);
+    }
+    return pmk_cross_scatter(ctx, list, 0, nullptr, dcol_best, nt);
+}
+

@@ -8,7 +8,7 @@
 
 #include "../../include/pm.h"
 
-#define PM_NSLOTS 44
+#define PM_NSLOTS 48
 #define PM_PROF_RING 4096
 #define PM_MAX_LANES 8   /* measured, us per cfg5 pair (every lane warmed up first): 1 / 2 / 4 / 6 / 8 lanes = 207 / 130 / 86 / 71 / 67 */
 
@@ -19,9 +19,10 @@ enum pm_slot {
     WS_HAM_Q, WS_HAM_T, WS_HAM_PART, WS_COLBEST,
     WS_P1, WS_P2, WS_SAMPLES, WS_F32, WS_COUNTS, WS_KEY, WS_MASK, WS_FOUT, WS_REFIT, WS_MISC,
     WS_KNN, WS_KNN2, WS_IDX, WS_KP, WS_LINES,
-    WS_Q_U8, WS_T_U8, WS_T_NORMF, WS_L2_FBPART, WS_SHARD, WS_KP2, WS_PAIRRES, WS_L2_SCHED, WS_HAND
+    WS_Q_U8, WS_T_U8, WS_T_NORMF, WS_L2_FBPART, WS_SHARD, WS_KP2, WS_PAIRRES, WS_L2_SCHED, WS_HAND,
+    WS_X_MARK, WS_X_LIST, WS_X_ROWS, WS_X_COL
 };
-static_assert(WS_HAND < PM_NSLOTS, "workspace slots");
+static_assert(WS_X_COL < PM_NSLOTS, "workspace slots");
 void l2_sched_free(pm_ctx *ctx);        // l2_tc.cu
 void pm_comm_release(pm_ctx *ctx);      // pm_nccl.cu: destroys an owned communicator (pm_destroy)
 
@@ -231,6 +232,18 @@ int pmk_ratio_filter(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm
 int pmk_ratio_filter_tail(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float ratio, pm_dmatch *dout,
                           int32_t *dn_out, unsigned long long *chain_done, unsigned *chain_ctr, unsigned long long seq,
                           const pm_gather_out *gather = nullptr);
+// Cross-check, column side restricted to the train rows that ARE somebody's best match (filter.cu): the rows of the
+// forward result mark their best train row; the marked rows are listed (any order), gathered into a compact row set and,
+// after the reverse pass over that set, their packed minima are scattered back into the [nt] column array.
+int pmk_cross_mark(pm_ctx *ctx, const pm_dmatch *dknn, int nq, int stride, int nt, uint8_t *dmark);
+int pmk_cross_list(pm_ctx *ctx, const uint8_t *dmark, int nt, int32_t *dlist, int32_t *dcount);
+int pmk_cross_gather_rows(pm_ctx *ctx, const void *dsrc, size_t row_bytes, const int32_t *dlist, int n, void *ddst);
+int pmk_cross_scatter(pm_ctx *ctx, const int32_t *dlist, int n, const uint64_t *dsmall, uint64_t *dcol_best, int nt);
+// The column side of a cross-check for this rank's query shard (pm_api.cu).  reduce_marks (may be null: one rank) makes the
+// mark bytes the union over the ranks, in place, on the ctx stream.  Synchronises the stream once (one 4-byte count).
+typedef int (*pm_mark_reduce_fn)(pm_ctx *ctx, uint8_t *dmark, size_t n);
+int pmk_cross_col_best(pm_ctx *ctx, int hamming, const void *dq, int nq, const void *dt, int nt, int width, int q_index_base,
+                       const pm_dmatch *dknn, uint64_t *dcol_best, pm_mark_reduce_fn reduce_marks);
 int pmk_cross_check(pm_ctx *ctx, const pm_dmatch *dknn, int nq, int stride, const uint64_t *dcol_best,
                     int nt, pm_dmatch *dout, int32_t *dn_out);
 int pmk_minmax_filter(pm_ctx *ctx, const pm_dmatch *dm, int n, int stride, pm_dmatch *dout,

@@ -153,6 +153,16 @@ int pm_comm_info(pm_ctx *ctx, int *n_ranks, int *rank)
     return PM_OK;
 }
 
+// union of the "is somebody's best match" marks over the ranks (pmk_cross_col_best)
+static int reduce_marks_nccl(pm_ctx *ctx, uint8_t *dmark, size_t n)
+{
+    NcclApi *a = nullptr;
+    int st = nccl_ready(ctx, &a);
+    if (st != PM_OK) return st;
+    PM_NCCL(ctx, a, a->AllReduce(dmark, dmark, n, ncclUint8, ncclMax, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    return PM_OK;
+}
+
 int pm_match_cross_sharded_dev(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int width, int norm,
                                int q_index_base, pm_dmatch *dknn, uint64_t *dcol_best, pm_dmatch *dout, int32_t *dn_out)
 {
@@ -177,13 +187,12 @@ int pm_match_cross_sharded_dev(pm_ctx *ctx, const void *dq, int nq, const void *
         st = norm == 6 ? pmk_hamming_knn2(ctx, (const uint8_t *)dq, nq, (const uint8_t *)dt, nt, width, q_index_base, dknn)
                        : pmk_l2_knn2(ctx, dq, nq, dt, nt, width, 0, q_index_base, dknn);
         if (st != PM_OK) return st;
-        st = norm == 6 ? pmk_hamming_col_best(ctx, (const uint8_t *)dq, nq, (const uint8_t *)dt, nt, width, q_index_base, dcol_best)
-                       : pmk_l2_col_best(ctx, (const float *)dq, nq, (const float *)dt, nt, width, q_index_base, dcol_best);
-        if (st != PM_OK) return st;
-    } else {
-        fill_u64_kernel<<<pm_cdiv(nt, 256), 256, 0, ctx->stream>>>((unsigned long long *)dcol_best, nt, ~0ull);   // an empty shard loses every min
-        PM_CHECK_LAUNCH(ctx);
     }
+    // reverse pass over the train rows some rank's query points at (every rank takes part in the mark exchange, also one
+    // with an empty shard: its column minima are all "none")
+    st = pmk_cross_col_best(ctx, norm == 6, dq, nq, dt, nt, width, q_index_base, dknn, dcol_best,
+                            ctx->n_ranks > 1 ? reduce_marks_nccl : nullptr);
+    if (st != PM_OK) return st;
     if (ctx->n_ranks > 1)
         PM_NCCL(ctx, a, a->AllReduce(dcol_best, dcol_best, (size_t)nt, ncclUint64, ncclMin, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     return pmk_cross_check(ctx, dknn, nq, 2, dcol_best, nt, dout, dn_out);

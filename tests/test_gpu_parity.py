@@ -203,6 +203,32 @@ def test_l2_cross_check(ctx, pm, orc):
     assert (x["queryIdx"] == keep).all() and (x["trainIdx"] == fwd["trainIdx"][keep, 0]).all()
 
 
+@pytest.mark.parametrize("norm", ["hamming", "l2"])
+@pytest.mark.parametrize("shape", [(900, 9000), (3000, 3500), (4000, 1000), (1, 5000), (700, 1)])
+def test_cross_check_marked_rows_equals_full_reverse_pass(ctx, pm, norm, shape):
+    """The reverse pass over the marked train rows only (the default) keeps exactly the matches the reverse pass over the
+    whole train set keeps (pm_debug_cross_full): few queries against many train rows (restricted), about as many (the
+    3/4 rule falls back to the full pass), more queries than train rows, single rows."""
+    from points_matching_b200 import _lib
+    nq, nt = shape
+    if norm == "hamming":
+        q, t = synth.orb_pair(nq, nt, seed=nq + nt)
+        t[nt // 2] = t[0]                              # duplicate train rows: equal distances, lowest index wins
+        code = pm.NORM_HAMMING
+    else:
+        q, t = synth.sift_pair(nq, nt, seed=nq + nt)
+        t[nt // 2] = t[0]
+        code = pm.NORM_L2
+    a = ctx.match_cross(q, t, code)
+    _lib.lib().pm_debug_cross_full(1)
+    try:
+        b = ctx.match_cross(q, t, code)
+    finally:
+        _lib.lib().pm_debug_cross_full(0)
+    assert len(a) == len(b) and (a == b).all()
+    assert len(a) > 0
+
+
 # --------------------------------------------------------------------------- filters
 def test_filters_vs_oracle(ctx, pm, orc):
     q, t = synth.sift_pair(40000, 300, seed=3)          # > 16384 rows: multi-block compaction path
