@@ -232,45 +232,42 @@ __global__ void ham_finalize_kernel(const unsigned long long *__restrict__ part,
 // =====================================================================================
 constexpr int HT_W = 8;          // words per row (256 bits)
 
-// one warp per row: lane l expands byte l of the row into 8 operand bytes
+// eight lanes per row (four rows per warp at a time): lane s expands word s of the row into 32 operand bytes
 __global__ void __launch_bounds__(256)
 ham_expand_kernel(const uint32_t *__restrict__ q, int nq, int mq_pad, const uint32_t *__restrict__ t, int nt, int nt_pad,
                   uint8_t *__restrict__ qx, uint8_t *__restrict__ tx, float *__restrict__ qnorm, uint8_t *__restrict__ text,
                   L2Flags *flags, L2Cand *__restrict__ part, int part_per_row)
 {
     pm_pdl_prologue();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int total = mq_pad + nt_pad, stride = gridDim.x * (blockDim.x >> 5);
-    for (int grow = blockIdx.x * (blockDim.x >> 5) + warp; grow < total; grow += stride) {
+    const int lane = threadIdx.x & 31, sub = lane & 7;
+    const int total = mq_pad + nt_pad, stride = gridDim.x * (blockDim.x >> 3);
+    for (int grow = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); grow < total; grow += stride) {   // mq_pad, nt_pad: multiples of 256
         const bool is_train = grow >= mq_pad;
         const int row = is_train ? grow - mq_pad : grow;
         const int n = is_train ? nt : nq;
-        uint32_t w = 0u;
-        if (row < n && lane < HT_W) w = (is_train ? t : q)[(size_t)row * HT_W + lane];
+        const uint32_t w = row < n ? __ldg((is_train ? t : q) + (size_t)row * HT_W + sub) : 0u;
         int pc = __popc(w);
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
-        pc = __shfl_sync(0xffffffffu, pc, 0);
-        const uint32_t word = __shfl_sync(0xffffffffu, w, lane >> 2);
-        const uint32_t byte = (word >> (8 * (lane & 3))) & 0xFFu;
+        pc += __shfl_xor_sync(0xffffffffu, pc, 4);
+        pc += __shfl_xor_sync(0xffffffffu, pc, 2);
+        pc += __shfl_xor_sync(0xffffffffu, pc, 1);
         const uint32_t one = is_train ? 0xC0u : 0x38u;                 // E4M3 -2.0 / 1.0
-        uint32_t lo = 0u, hi = 0u;
+        uint32_t o[8];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            lo |= ((byte >> b) & 1u) ? one << (8 * b) : 0u;
-            hi |= ((byte >> (b + 4)) & 1u) ? one << (8 * b) : 0u;
-        }
-        reinterpret_cast<uint2 *>((is_train ? tx : qx) + (size_t)row * L2_PACK_COLS)[lane] = make_uint2(lo, hi);
+        for (int k = 0; k < 8; ++k)                                     // four bits -> four bytes (bit b of the row -> byte b)
+            o[k] = ((((w >> (4 * k)) & 0xFu) * 0x00204081u) & 0x01010101u) * one;
+        uint4 *dst = reinterpret_cast<uint4 *>((is_train ? tx : qx) + (size_t)row * L2_PACK_COLS + 32 * sub);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
         if (is_train) {
-            if (lane < 2) {
+            if (sub < 2) {
                 const uint4 s3 = bf16_split3(row < n ? (float)pc : __uint_as_float(L2_PAD_NORM_BITS));
-                uint8_t *e = text + (size_t)(row >> 7) * L2_EXT_BYTES + ext_row_offset(row & 127) + lane * 128;
-                *reinterpret_cast<uint4 *>(e) = lane == 0 ? make_uint4(s3.x, s3.y | 0x3F800000u, 0x3F803F80u, 0u)
-                                                          : make_uint4(0u, 0u, 0u, 0u);
+                uint8_t *e = text + (size_t)(row >> 7) * L2_EXT_BYTES + ext_row_offset(row & 127) + sub * 128;
+                *reinterpret_cast<uint4 *>(e) = sub == 0 ? make_uint4(s3.x, s3.y | 0x3F800000u, 0x3F803F80u, 0u)
+                                                         : make_uint4(0u, 0u, 0u, 0u);
             }
         } else {
-            if (lane == 0) qnorm[row] = (float)pc;
-            for (int k = lane; k < part_per_row; k += 32) part[(size_t)row * part_per_row + k] = L2Cand{L2_INF, -1};
+            if (sub == 0) qnorm[row] = (float)pc;
+            for (int k = sub; k < part_per_row; k += 8) part[(size_t)row * part_per_row + k] = L2Cand{L2_INF, -1};
         }
     }
     // integer data with tiny norms: K2 / the finish kernel run in exact mode
@@ -363,7 +360,7 @@ int ham_tc_run(pm_ctx *ctx, const uint32_t *pq, int nq, const uint32_t *pt, int 
     PM_WS(ctx, qnorm, float *, WS_Q_NORM, (size_t)mq_pad * 4);
     PM_WS(ctx, text, uint8_t *, WS_T_NORM, (size_t)(nt_pad / 128) * L2_EXT_BYTES);
     PM_WS(ctx, part, L2Cand *, WS_L2_PART, (size_t)mq_pad * smax * 3 * sizeof(L2Cand));
-    const int xblocks = min(pm_cdiv(mq_pad + nt_pad, 8), 8 * ctx->num_sms);
+    const int xblocks = min(pm_cdiv(mq_pad + nt_pad, 32), 8 * ctx->num_sms);
     PM_CUDA(ctx, pm_launch_pdl(ham_expand_kernel, dim3(xblocks), dim3(256), 0, ctx->stream, pq, nq, mq_pad, pt, nt, nt_pad, qx, tx,
                                qnorm, text, flags, part, smax * 3));
     PM_CHECK_LAUNCH(ctx);
