@@ -321,17 +321,21 @@ int pm_fundamental_8point(pm_ctx *ctx, const float *p1, const float *p2, int n, 
  *   pm_comm_unique_id  rank 0 makes the 128-byte ncclUniqueId and ships it to the other ranks (MPI, torch.distributed, a file)
  *   pm_comm_init       ncclCommInitRank on the ctx's device; the ctx owns the communicator (destroyed by pm_destroy)
  *   pm_set_comm        or: borrow the caller's ncclComm_t (void* = ncclComm_t); NULL detaches
- * The collectives run on the ctx stream between the kernels they connect: nothing is synchronised. */
+ * The collectives run on the ctx stream between the kernels they connect. */
 #define PM_COMM_ID_BYTES 128
 int pm_comm_unique_id(void *id /* [PM_COMM_ID_BYTES] */);
 int pm_comm_init(pm_ctx *ctx, int n_ranks, int rank, const void *id /* [PM_COMM_ID_BYTES] */);
 int pm_set_comm(pm_ctx *ctx, void *nccl_comm, int n_ranks, int rank);
 int pm_comm_info(pm_ctx *ctx, int *n_ranks, int *rank);   /* 1, 0 without a communicator */
 /* BFMatcher(norm, crossCheck=true).match over a query set sharded by rows: this rank holds rows [q_index_base,
- * q_index_base + nq) and the whole (replicated) train set.  kNN-2 of the shard -> dknn ([nq][2], optional), packed column
- * minima of the shard -> dcol_best ([nt], scratch the caller provides) -> ncclAllReduce(ncclMin, ncclUint64) in place ->
- * local filter: the shard's mutual matches in queryIdx order -> dout ([nq]), *dn_out.  Concatenating the ranks' lists in rank
- * order gives exactly the single-GPU result.  norm: 4 = L2 (f32 rows of `width` floats), 6 = Hamming (rows of `width` bytes). */
+ * q_index_base + nq) and the whole (replicated) train set.  kNN-2 of the shard -> dknn ([nq][2], optional); the train rows that
+ * are the best match of some query are marked (ncclAllReduce(ncclMax, ncclUint8) of the [nt] mark bytes: the union over the
+ * ranks) and only those rows take part in the reverse pass against the shard (all rows when more than 3/4 are marked) -> packed
+ * column minima -> dcol_best ([nt], scratch the caller provides; rows nobody points at hold "none") -> ncclAllReduce(ncclMin,
+ * ncclUint64) in place -> local filter: the shard's mutual matches in queryIdx order -> dout ([nq]), *dn_out.  Concatenating
+ * the ranks' lists in rank order gives exactly the single-GPU result.  The call reads ONE 4-byte count back from the device
+ * (the number of marked rows sizes the reverse pass), i.e. it waits for the forward pass; the rest stays enqueued.
+ * norm: 4 = L2 (f32 rows of `width` floats), 6 = Hamming (rows of `width` bytes). */
 int pm_match_cross_sharded_dev(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int width, int norm,
                                int q_index_base, pm_dmatch *dknn, uint64_t *dcol_best, pm_dmatch *dout, int32_t *dn_out);
 /* Fixed-width all-gather of per-rank match lists (the "gather of match results" of the north_star): dall is
