@@ -449,13 +449,20 @@ def run_ours(args):
         return blocks, per
 
     e_blocks, e_per = e2e_blocks(n_lanes)
-    e_one = e_blocks if n_lanes == 1 else e2e_blocks(1)[0]
+    e_one, e_one_per = (e_blocks, e_per) if n_lanes == 1 else e2e_blocks(1)
+    # the faster of the two host-side arrangements is the figure (the block times are already the max over ranks, so every
+    # rank decides alike): on one or two GPUs the lanes hide everything but the upload; with eight ranks on one host the
+    # PCIe root / host memory is the limit and four uploading threads per rank only add contention
+    e_lanes_used = n_lanes
+    if float(np.median(e_one)) < float(np.median(e_blocks)):
+        e_blocks, e_one, e_per, e_lanes_used = e_one, e_blocks, e_one_per, 1
     e_steps = 5 * e_per
     e_ms = float(np.median(e_blocks))
     e2e = {"value": world * NQ * NT / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
            "h2d_bytes_per_step": (NQ + NT) * DIM * 4, "d2h_bytes_per_step": NQ * 2 * 16 + NQ * 16 + 4,
-           "api": "pm_knn2_ratio_l2_f32 (host buffers, pinned)" + (f"; {n_lanes} host threads, one context each" if n_lanes > 1 else ""),
-           "steps": e_steps, "lanes": n_lanes, "ms_per_step_one_lane": float(np.median(e_one)),
+           "api": "pm_knn2_ratio_l2_f32 (host buffers, pinned)" + (f"; {e_lanes_used} host threads, one context each" if e_lanes_used > 1 else ""),
+           "steps": e_steps, "lanes": e_lanes_used,
+           ("ms_per_step_one_lane" if e_lanes_used > 1 else f"ms_per_step_{n_lanes}_lanes"): float(np.median(e_one)),
            "ms_per_step_blocks": e_blocks, "timing": "median of 5 blocks, max over ranks per block"}
 
     # ---- the same call with SIFT shipped as bytes (pm_knn2_l2_u8: 4x fewer PCIe bytes, identical matches) ----
