@@ -194,6 +194,21 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference)")
     torch.cuda.set_device(local)
+    numa_note = None
+    if world > 1 and not args.no_affinity:
+        # several ranks on one host: keep this rank's threads (and so the first-touch pages of its pinned staging
+        # buffers) on the cores next to its GPU
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            hnd = pynvml.nvmlDeviceGetHandleByIndex(local)
+            words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1} & os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                numa_note = f"rank threads bound to the {len(cpus)} cores local to GPU {local}"
+        except Exception as e:      # noqa: BLE001 -- an optimisation only
+            numa_note = f"cpu affinity not set: {e}"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -461,7 +476,7 @@ def run_ours(args):
     e2e = {"value": world * NQ * NT / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
            "h2d_bytes_per_step": (NQ + NT) * DIM * 4, "d2h_bytes_per_step": NQ * 2 * 16 + NQ * 16 + 4,
            "api": "pm_knn2_ratio_l2_f32 (host buffers, pinned)" + (f"; {e_lanes_used} host threads, one context each" if e_lanes_used > 1 else ""),
-           "steps": e_steps, "lanes": e_lanes_used,
+           "steps": e_steps, "lanes": e_lanes_used, "value_per_gpu": NQ * NT / (e_ms * 1e-3),
            ("ms_per_step_one_lane" if e_lanes_used > 1 else f"ms_per_step_{n_lanes}_lanes"): float(np.median(e_one)),
            "ms_per_step_blocks": e_blocks, "timing": "median of 5 blocks, max over ranks per block"}
 
@@ -596,7 +611,7 @@ def run_ours(args):
                       "step_overlap": (f"{n_lanes} lanes: steps round-robin over {n_lanes} contexts (own stream + workspaces), each step one whole "
                                        "K1-K2-K3-K5 pass over its own input set") if n_lanes > 1 else
                                       ("none" if args.no_pipelining else "pm_set_pipelining: K1 of step i+1 under K3/K5 of step i"),
-                      "ms_per_step_one_lane": ms_step_single,
+                      "ms_per_step_one_lane": ms_step_single, "host_affinity": numa_note,
                       "dtype_detail": "bf16 operands (exact for 0..255 integers), fp32 accumulate in TMEM, fp32 norms / selection / output"},
             "summary": summary}
     sys.stdout.flush()
@@ -1203,6 +1218,7 @@ def main():
     ap.add_argument("--no-cfg5", action="store_true")
     ap.add_argument("--ransac-steps", type=int, default=5)
     ap.add_argument("--no-pipelining", action="store_true", help="consecutive steps strictly serial (no cross-step overlap)")
+    ap.add_argument("--no-affinity", action="store_true", help="N > 1: do not bind the rank to its GPU's local cores")
     ap.add_argument("--lanes", type=int, default=4, help="contexts (stream + workspaces each) the timed steps and the e2e calls go round-robin over")
     ap.add_argument("--no-ramp", action="store_true", help="skip the 1 s clock ramp (profiling runs under ncu)")
     args = ap.parse_args()
