@@ -333,8 +333,9 @@ int pm_comm_info(pm_ctx *ctx, int *n_ranks, int *rank);   /* 1, 0 without a comm
  * ranks) and only those rows take part in the reverse pass against the shard (all rows when more than 3/4 are marked) -> packed
  * column minima -> dcol_best ([nt], scratch the caller provides; rows nobody points at hold "none") -> ncclAllReduce(ncclMin,
  * ncclUint64) in place -> local filter: the shard's mutual matches in queryIdx order -> dout ([nq]), *dn_out.  Concatenating
- * the ranks' lists in rank order gives exactly the single-GPU result.  The call reads ONE 4-byte count back from the device
- * (the number of marked rows sizes the reverse pass), i.e. it waits for the forward pass; the rest stays enqueued.
+ * the ranks' lists in rank order gives exactly the single-GPU result.  With several ranks the call reads ONE 4-byte count back
+ * from the device (the number of marked rows sizes the reverse pass), i.e. it waits for the forward pass and the rest stays
+ * enqueued; on one rank the reverse pass is sized by the bound min(nq, nt) and nothing is synchronised.
  * norm: 4 = L2 (f32 rows of `width` floats), 6 = Hamming (rows of `width` bytes). */
 int pm_match_cross_sharded_dev(pm_ctx *ctx, const void *dq, int nq, const void *dt, int nt, int width, int norm,
                                int q_index_base, pm_dmatch *dknn, uint64_t *dcol_best, pm_dmatch *dout, int32_t *dn_out);

@@ -265,20 +265,23 @@ __global__ void cross_list_kernel(const uint8_t *__restrict__ mark, int nt, int 
 }
 
 template <typename V>
-__global__ void cross_gather_rows_kernel(const V *__restrict__ src, int row_elems, const int *__restrict__ list, long long total,
-                                         V *__restrict__ dst)
+__global__ void cross_gather_rows_kernel(const V *__restrict__ src, int row_elems, const int *__restrict__ list,
+                                         const int *__restrict__ count, long long total, V *__restrict__ dst)
 {
+    const int live = *count;                       // rows past the listed ones (the launch is sized by a bound) become zero rows
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(idx / row_elems), w = (int)(idx - (long long)r * row_elems);
-        dst[idx] = src[(size_t)list[r] * row_elems + w];
+        V v = V();
+        if (r < live) v = src[(size_t)list[r] * row_elems + w];
+        dst[idx] = v;
     }
 }
 
-__global__ void cross_scatter_kernel(const int *__restrict__ list, int n, const unsigned long long *__restrict__ small_,
-                                     unsigned long long *__restrict__ col)
+__global__ void cross_scatter_kernel(const int *__restrict__ list, const int *__restrict__ count, int n,
+                                     const unsigned long long *__restrict__ small_, unsigned long long *__restrict__ col)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) col[list[k]] = small_[k];
+    if (k < n && k < *count) col[list[k]] = small_[k];
 }
 
 }  // namespace
@@ -313,29 +316,31 @@ int pmk_cross_list(pm_ctx *ctx, const uint8_t *dmark, int nt, int32_t *dlist, in
     return PM_OK;
 }
 
-int pmk_cross_gather_rows(pm_ctx *ctx, const void *dsrc, size_t row_bytes, const int32_t *dlist, int n, void *ddst)
+int pmk_cross_gather_rows(pm_ctx *ctx, const void *dsrc, size_t row_bytes, const int32_t *dlist, const int32_t *dcount, int n,
+                          void *ddst)
 {
     if (n <= 0) return PM_OK;
     const uintptr_t al = (uintptr_t)dsrc | (uintptr_t)ddst | (uintptr_t)row_bytes;
     const int blocks = 8 * ctx->num_sms;
     if ((al & 15) == 0)
-        cross_gather_rows_kernel<uint4><<<blocks, 256, 0, ctx->stream>>>((const uint4 *)dsrc, (int)(row_bytes / 16), dlist,
+        cross_gather_rows_kernel<uint4><<<blocks, 256, 0, ctx->stream>>>((const uint4 *)dsrc, (int)(row_bytes / 16), dlist, dcount,
                                                                            (long long)n * (long long)(row_bytes / 16), (uint4 *)ddst);
     else if ((al & 3) == 0)
-        cross_gather_rows_kernel<uint32_t><<<blocks, 256, 0, ctx->stream>>>((const uint32_t *)dsrc, (int)(row_bytes / 4), dlist,
+        cross_gather_rows_kernel<uint32_t><<<blocks, 256, 0, ctx->stream>>>((const uint32_t *)dsrc, (int)(row_bytes / 4), dlist, dcount,
                                                                               (long long)n * (long long)(row_bytes / 4), (uint32_t *)ddst);
     else
-        cross_gather_rows_kernel<uint8_t><<<blocks, 256, 0, ctx->stream>>>((const uint8_t *)dsrc, (int)row_bytes, dlist,
+        cross_gather_rows_kernel<uint8_t><<<blocks, 256, 0, ctx->stream>>>((const uint8_t *)dsrc, (int)row_bytes, dlist, dcount,
                                                                              (long long)n * (long long)row_bytes, (uint8_t *)ddst);
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
 }
 
-int pmk_cross_scatter(pm_ctx *ctx, const int32_t *dlist, int n, const uint64_t *dsmall, uint64_t *dcol_best, int nt)
+int pmk_cross_scatter(pm_ctx *ctx, const int32_t *dlist, const int32_t *dcount, int n, const uint64_t *dsmall, uint64_t *dcol_best,
+                      int nt)
 {
     PM_CUDA(ctx, cudaMemsetAsync(dcol_best, 0xFF, (size_t)nt * 8, ctx->stream));      // never-marked rows: no candidate
     if (n > 0) {
-        cross_scatter_kernel<<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>(dlist, n, (const unsigned long long *)dsmall,
+        cross_scatter_kernel<<<pm_cdiv(n, 256), 256, 0, ctx->stream>>>(dlist, dcount, n, (const unsigned long long *)dsmall,
                                                                          (unsigned long long *)dcol_best);
         PM_CHECK_LAUNCH(ctx);
     }

@@ -1200,11 +1200,17 @@ int pmk_cross_col_best(pm_ctx *ctx, int hamming, const void *dq, int nq, const v
     PM_WS(ctx, mark, uint8_t *, WS_X_MARK, (size_t)nt + 64);
     PM_WS(ctx, list, int32_t *, WS_X_LIST, (size_t)nt * 4 + 64);
     int32_t *count = list + nt;
-    if (!g_cross_full) {
+    const bool bound_says_full = !reduce_marks && (long long)(nq < nt ? nq : nt) * 4 > (long long)nt * 3;
+    if (!g_cross_full && !bound_says_full) {
         if ((st = pmk_cross_mark(ctx, dknn, nq, 2, nt, mark)) != PM_OK) return st;
         if (reduce_marks && (st = reduce_marks(ctx, mark, (size_t)nt)) != PM_OK) return st;
         if ((st = pmk_cross_list(ctx, mark, nt, list, count)) != PM_OK) return st;
-        if ((st = read_count(ctx, count, &n_marked)) != PM_OK) return st;
+        if (reduce_marks) {
+            // several ranks: the number of marked rows (queries of ALL ranks) is only known on the device
+            if ((st = read_count(ctx, count, &n_marked)) != PM_OK) return st;
+        } else {
+            n_marked = nq < nt ? nq : nt;            // one rank: at most one marked row per query -- no read-back, the
+        }                                            // kernels below take the exact count from the device
     }
     if (nq <= 0) {                                   // an empty shard loses every minimum
         PM_CUDA(ctx, cudaMemsetAsync(dcol_best, 0xFF, (size_t)nt * 8, ctx->stream));
@@ -1216,12 +1222,12 @@ int pmk_cross_col_best(pm_ctx *ctx, int hamming, const void *dq, int nq, const v
     if (n_marked > 0) {
         PM_WS(ctx, rows, uint8_t *, WS_X_ROWS, (size_t)n_marked * row_bytes);
         PM_WS(ctx, small_, uint64_t *, WS_X_COL, (size_t)n_marked * 8);
-        if ((st = pmk_cross_gather_rows(ctx, dt, row_bytes, list, n_marked, rows)) != PM_OK) return st;
+        if ((st = pmk_cross_gather_rows(ctx, dt, row_bytes, list, count, n_marked, rows)) != PM_OK) return st;
         st = hamming ? pmk_hamming_col_best(ctx, (const uint8_t *)dq, nq, rows, n_marked, width, q_index_base, small_)
                      : pmk_l2_col_best(ctx, (const float *)dq, nq, (const float *)rows, n_marked, width, q_index_base, small_);
         if (st != PM_OK) return st;
-        return pmk_cross_scatter(ctx, list, n_marked, small_, dcol_best, nt);
+        return pmk_cross_scatter(ctx, list, count, n_marked, small_, dcol_best, nt);
     }
-    return pmk_cross_scatter(ctx, list, 0, nullptr, dcol_best, nt);
+    return pmk_cross_scatter(ctx, list, count, 0, nullptr, dcol_best, nt);
 }
 

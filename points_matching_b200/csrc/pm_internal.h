@@ -237,10 +237,13 @@ int pmk_ratio_filter_tail(pm_ctx *ctx, const pm_dmatch *dknn, int nq, float rati
 // after the reverse pass over that set, their packed minima are scattered back into the [nt] column array.
 int pmk_cross_mark(pm_ctx *ctx, const pm_dmatch *dknn, int nq, int stride, int nt, uint8_t *dmark);
 int pmk_cross_list(pm_ctx *ctx, const uint8_t *dmark, int nt, int32_t *dlist, int32_t *dcount);
-int pmk_cross_gather_rows(pm_ctx *ctx, const void *dsrc, size_t row_bytes, const int32_t *dlist, int n, void *ddst);
-int pmk_cross_scatter(pm_ctx *ctx, const int32_t *dlist, int n, const uint64_t *dsmall, uint64_t *dcol_best, int nt);
+int pmk_cross_gather_rows(pm_ctx *ctx, const void *dsrc, size_t row_bytes, const int32_t *dlist, const int32_t *dcount, int n,
+                          void *ddst);        // n: launch size (a bound); rows past *dcount are written as zeros
+int pmk_cross_scatter(pm_ctx *ctx, const int32_t *dlist, const int32_t *dcount, int n, const uint64_t *dsmall, uint64_t *dcol_best,
+                      int nt);
 // The column side of a cross-check for this rank's query shard (pm_api.cu).  reduce_marks (may be null: one rank) makes the
-// mark bytes the union over the ranks, in place, on the ctx stream.  Synchronises the stream once (one 4-byte count).
+// mark bytes the union over the ranks, in place, on the ctx stream.  One rank: nothing is synchronised (the reverse pass is
+// sized by the bound min(nq, nt)); several ranks: the stream is synchronised once to read the 4-byte count of marked rows.
 typedef int (*pm_mark_reduce_fn)(pm_ctx *ctx, uint8_t *dmark, size_t n);
 int pmk_cross_col_best(pm_ctx *ctx, int hamming, const void *dq, int nq, const void *dt, int nt, int width, int q_index_base,
                        const pm_dmatch *dknn, uint64_t *dcol_best, pm_mark_reduce_fn reduce_marks);
