@@ -109,7 +109,7 @@ __device__ __noinline__ void l2_fallback_items(const L2FallbackArgs &A)
     __shared__ __align__(16) float x_t[L2FB_CHUNK][L2_KDIM];        // 32 KB
     __shared__ __align__(16) float x_q[L2FB_ROWS][L2_KDIM];         // 8 KB
     __shared__ unsigned long long x_k[L2FB_ROWS][8][2];
-    __shared__ int x_item, x_last[L2FB_ROWS];
+    __shared__ int x_item, x_last[L2FB_ROWS], x_idx[L2FB_ROWS];
     const int nf = *reinterpret_cast<volatile int *>(&A.flags->n_flagged);
     if (nf <= 0) return;
     const T *q = reinterpret_cast<const T *>(A.q), *t = reinterpret_cast<const T *>(A.t);
@@ -131,12 +131,32 @@ __device__ __noinline__ void l2_fallback_items(const L2FallbackArgs &A)
         if (item >= items) break;
         const int bt = item / split, sg = item - bt * split;
         const int r0 = bt * rpb, nr = min(rpb, nf - r0);
-        // stage the query rows of the batch (zero past dim)
-        for (int e = threadIdx.x; e < L2FB_ROWS * L2_KDIM; e += blockDim.x) {
-            const int r = e >> 7, k = e & (L2_KDIM - 1);
-            float v = 0.f;
-            if (r < nr && k < A.dim) v = (float)q[(size_t)(*reinterpret_cast<volatile const int *>(&A.flagged[r0 + r])) * A.dim + k];
-            x_q[r][k] = v;
+        // stage the query rows of the batch (zero past dim).  The row numbers first, once per item: they were written by
+        // other blocks of this launch, so they are read past L1 (ld.cg) -- as plain loads the compiler may keep in flight
+        // together (one volatile load per ELEMENT, each followed by its dependent row load, made an item ~10 us)
+        if ((int)threadIdx.x < L2FB_ROWS) x_idx[threadIdx.x] = (int)threadIdx.x < nr ? __ldcg(&A.flagged[r0 + (int)threadIdx.x]) : 0;
+        __syncthreads();
+        if (A.vec) {
+            float4 v[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int idx = (int)threadIdx.x + 256 * i, r = idx >> 5, c4 = idx & 31;      // 16 rows x 32 quads
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < nr) v[i] = l2fb_load_quad(q + (size_t)x_idx[r] * L2_KDIM, c4);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int idx = (int)threadIdx.x + 256 * i, r = idx >> 5, c4 = idx & 31;
+                *reinterpret_cast<float4 *>(&x_q[r][4 * c4]) = v[i];
+            }
+        } else {
+#pragma unroll 4
+            for (int e = threadIdx.x; e < L2FB_ROWS * L2_KDIM; e += blockDim.x) {
+                const int r = e >> 7, k = e & (L2_KDIM - 1);
+                float v = 0.f;
+                if (r < nr && k < A.dim) v = (float)q[(size_t)x_idx[r] * A.dim + k];
+                x_q[r][k] = v;
+            }
         }
         unsigned long long m0 = ~0ull, m1 = ~0ull;          // thread r < nr: running top-2 of row r0 + r over this segment
         const int ch_end = min(nchunk, (sg + 1) * seg_chunks);
@@ -224,9 +244,13 @@ __device__ __noinline__ void l2_fallback_items(const L2FallbackArgs &A)
             if (!x_last[r]) continue;
             const int fr = r0 + r;
             unsigned long long k0 = ~0ull, k1 = ~0ull;
-            for (int c = lane; c < 2 * split; c += 32) {
-                const unsigned long long key = *reinterpret_cast<volatile unsigned long long *>(&A.fb_part[(size_t)fr * split * 2 + c]);
-                k1 = min_u64(k1, max_u64(k0, key)); k0 = min_u64(k0, key);
+            const unsigned long long *slots = A.fb_part + (size_t)fr * split * 2;       // other blocks wrote them: ld.cg
+            for (int c = lane; c < 2 * split; c += 128) {                                // four loads in flight per lane
+                unsigned long long key[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) key[u] = c + 32 * u < 2 * split ? __ldcg(slots + c + 32 * u) : ~0ull;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { k1 = min_u64(k1, max_u64(k0, key[u])); k0 = min_u64(k0, key[u]); }
             }
 #pragma unroll
             for (int o = 1; o <= 16; o <<= 1) {
@@ -235,7 +259,7 @@ __device__ __noinline__ void l2_fallback_items(const L2FallbackArgs &A)
                 k1 = min_u64(min_u64(k1, y1), hi); k0 = lo;
             }
             if (lane < 2) {
-                const int i = *reinterpret_cast<volatile const int *>(&A.flagged[fr]);
+                const int i = x_idx[r];
                 reinterpret_cast<uint4 *>(A.out + (size_t)i * 2)[lane] = l2fb_record(i + A.q_index_base, lane == 0 ? k0 : k1);
             }
         }
