@@ -34,7 +34,7 @@ def show_bench(path):
     if c5:
         print('cfg5 %.1f image pairs/s (%.3f ms/pair) last %s' % (c5['image_pairs_per_s'], c5['ms_per_pair'], c5['last_pair']))
         if 'native_batched' in c5:
-            print('   native batched %.3f ms/pair, staged python %.3f ms/pair, same result %s' % (c5['native_batched']['ms_per_pair'], c5['staged_python']['ms_per_pair'], c5['same_result_both_paths']))
+        
 
 
 def show_launches(path):
