@@ -33,8 +33,10 @@ def show_bench(path):
     c5 = (d.get('extra') or {}).get('cfg5')
     if c5:
         print('cfg5 %.1f image pairs/s (%.3f ms/pair) last %s' % (c5['image_pairs_per_s'], c5['ms_per_pair'], c5['last_pair']))
-        if 'native_batched' in c5:
-        
+        if c5.get('e2e'):
+            print('   from host buffers: %.1f image pairs/s (%.3f ms/pair)' % (c5['e2e']['value'], c5['e2e']['ms_per_pair']))
+    if d.get('summary'):
+        print('parity', d['summary'].get('parity'))
 
 
 def show_launches(path):
