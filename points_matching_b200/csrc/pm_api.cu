@@ -355,6 +355,18 @@ int pm_ransac_finish_dev(pm_ctx *ctx, const float *dp1, const float *dp2, int n,
 // host-buffer entry points (synchronous; H2D + kernels + D2H)
 // ---------------------------------------------------------------------------------
 #define H2D(ctx, dst, src, bytes) PM_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (ctx)->stream))
+#define H2D_ON(ctx, strm, dst, src, bytes) PM_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, strm))
+
+// the ctx's upload stream and its events (chunked host kNN, host-buffer pair groups), created on first use
+static int copy_stream_ready(pm_ctx *ctx)
+{
+    if (ctx->copy_stream) return PM_OK;
+    PM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    PM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fence, cudaEventDisableTiming));
+    PM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_train, cudaEventDisableTiming));
+    for (int i = 0; i < 8; ++i) PM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
+    return PM_OK;
+}
 #define D2H(ctx, dst, src, bytes) PM_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (ctx)->stream))
 
 // Upload + L2 kNN-2 with the H2D copies overlapped with compute: the train set goes first and is packed
@@ -374,12 +386,7 @@ static int l2_upload_and_match(pm_ctx *ctx, const void *q, int nq, const void *t
         if (nt) H2D(ctx, dt, t, (size_t)nt * row);
         return pmk_l2_knn2(ctx, dq, nq, dt, nt, dim, is_u8, 0, dknn);
     }
-    if (!ctx->copy_stream) {
-        PM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        PM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fence, cudaEventDisableTiming));
-        PM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_train, cudaEventDisableTiming));
-        for (int i = 0; i < 8; ++i) PM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
-    }
+    { int cst = copy_stream_ready(ctx); if (cst != PM_OK) return cst; }
     const int chunk = pm_round_up(pm_cdiv(nq, nchunks), 256);
     // the copy stream may not overwrite the raw buffers before earlier work on the compute stream is done
     PM_CUDA(ctx, cudaEventRecord(ctx->ev_fence, ctx->stream));
@@ -856,26 +863,45 @@ static int pair_group_enqueue(pm_ctx *ctx, int cnt, const void *const *dd1, cons
     PM_WS(ctx, drefit, double *, WS_REFIT, P * PM_REFIT_WS_DOUBLES * sizeof(double));
     uint8_t *s1 = nullptr, *s2 = nullptr; float *sk1 = nullptr, *sk2 = nullptr;
     const size_t elem = is_u8 ? 1 : 4;
-    if (host_inputs) {       // staging for HOST descriptors / keypoints: reused pair after pair in stream order
-        PM_WS(ctx, a1, uint8_t *, WS_Q_RAW, (size_t)nmax * dim * elem);
-        PM_WS(ctx, a2, uint8_t *, WS_T_RAW, (size_t)n2max * dim * elem);
-        PM_WS(ctx, a3, float *, WS_KP, (size_t)nmax * 8);
-        PM_WS(ctx, a4, float *, WS_KP2, (size_t)n2max * 8);
+    // staging for HOST descriptors / keypoints: TWO sets, filled by the ctx's upload stream -- the upload of pair b + 1
+    // runs under the matching chain of pair b (ev_chunk[set]: "set uploaded", ev_chunk[2 + set]: "the chain that read the
+    // set is done"; an event that was never recorded counts as complete)
+    const size_t st1 = ((size_t)nmax * dim * elem + 255) & ~(size_t)255, st2 = ((size_t)n2max * dim * elem + 255) & ~(size_t)255;
+    const size_t stk1 = ((size_t)nmax * 8 + 255) & ~(size_t)255, stk2 = ((size_t)n2max * 8 + 255) & ~(size_t)255;
+    if (host_inputs) {
+        PM_WS(ctx, a1, uint8_t *, WS_Q_RAW, 2 * st1);
+        PM_WS(ctx, a2, uint8_t *, WS_T_RAW, 2 * st2);
+        PM_WS(ctx, a3, float *, WS_KP, 2 * stk1);
+        PM_WS(ctx, a4, float *, WS_KP2, 2 * stk2);
         s1 = a1; s2 = a2; sk1 = a3; sk2 = a4;
+        int cst = copy_stream_ready(ctx);
+        if (cst != PM_OK) return cst;
+        // the first uploads may not overtake earlier work of this stream that still reads the staging sets or the slots
+        PM_CUDA(ctx, cudaEventRecord(ctx->ev_fence, ctx->stream));
+        PM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fence, 0));
     }
     int st;
     for (int b = 0; b < cnt; ++b) {
         const void *d1 = dd1[b], *d2 = dd2[b];
         const float *k1 = dkp1[b], *k2 = dkp2[b];
         if (host_inputs) {
-            if (n1[b]) { H2D(ctx, s1, d1, (size_t)n1[b] * dim * elem); H2D(ctx, sk1, k1, (size_t)n1[b] * 8); }
-            if (n2[b]) { H2D(ctx, s2, d2, (size_t)n2[b] * dim * elem); H2D(ctx, sk2, k2, (size_t)n2[b] * 8); }
-            d1 = s1; d2 = s2; k1 = sk1; k2 = sk2;
+            const int set = b & 1;
+            uint8_t *u1 = s1 + set * st1, *u2 = s2 + set * st2;
+            float *uk1 = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(sk1) + set * stk1);
+            float *uk2 = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(sk2) + set * stk2);
+            cudaStream_t cs = ctx->copy_stream;
+            if (b >= 2) PM_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_chunk[2 + set], 0));      // chain b - 2 has read the set
+            if (n1[b]) { H2D_ON(ctx, cs, u1, d1, (size_t)n1[b] * dim * elem); H2D_ON(ctx, cs, uk1, k1, (size_t)n1[b] * 8); }
+            if (n2[b]) { H2D_ON(ctx, cs, u2, d2, (size_t)n2[b] * dim * elem); H2D_ON(ctx, cs, uk2, k2, (size_t)n2[b] * 8); }
+            PM_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[set], cs));
+            PM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[set], 0));
+            d1 = u1; d2 = u2; k1 = uk1; k2 = uk2;
         }
         int32_t *dn_good = reinterpret_cast<int32_t *>(dkey + (size_t)b * 8 + 2);
         // K5 gathers while it scatters: the good matches leave as DMatch records AND as the pair's point lists
         const pm_gather_out g = {k1, n1[b], k2, n2[b], dp1 + (size_t)b * nmax * 2, dp2 + (size_t)b * nmax * 2, dpts + (size_t)b * nmax * 4};
         if ((st = pmk_l2_knn2_fused(ctx, d1, n1[b], d2, n2[b], dim, is_u8, 0, dknn, 0, ratio, dgood, dn_good, &g)) != PM_OK) return st;
+        if (host_inputs) PM_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[2 + (b & 1)], ctx->stream));
     }
     pm_pair_group G;
     G.n_pairs = cnt; G.nmax = nmax; G.n_hyp = nh; G.m = m; G.metric = prm->metric; G.refit_on = prm->refit != 0;
