@@ -62,6 +62,23 @@ def test_cross_check(golden, orc, case):
     assert (x["distance"] == g[case + "_xd"]).all()
 
 
+def test_cross_check_needs_only_the_marked_train_rows(orc):
+    """The product's reverse pass runs over the train rows that are some query's best match only (pm_api.cu,
+    pmk_cross_col_best).  The rule restated on the oracle: column minima computed over those rows alone, scattered into an
+    otherwise empty column array, keep exactly the matches the full column pass keeps."""
+    from points_matching_b200 import synth
+    q, t = synth.orb_pair(300, 2500, seed=11)
+    t[1200] = t[3]                                           # duplicate train rows: equal distances
+    fwd = orc.knn2_hamming(q, t)
+    full = orc.cross_check(fwd, orc.col_best_hamming(q, t))
+    marked = np.unique(fwd["trainIdx"][:, 0])
+    assert 0 < len(marked) <= 300
+    col = np.full(t.shape[0], np.iinfo(np.uint64).max, dtype=np.uint64)
+    col[marked] = orc.col_best_hamming(q, np.ascontiguousarray(t[marked]))
+    part = orc.cross_check(fwd, col)
+    assert len(part) == len(full) and (part == full).all()
+
+
 def _rel(a, b):
     return np.abs(a - b).max() / np.abs(b).max()
 
