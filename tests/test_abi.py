@@ -91,3 +91,27 @@ def test_cpp_host_layer_compiles_and_links(L):
     assert os.path.exists(exe)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 2 and "usage" in r.stderr
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs the reference's CPU routine (OpenCV batchDistance, else the oracle port) and
+    prints ONE JSON line with the contract's keys; without a GPU the product arm refuses to run (no CPU fallback)."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "sift_knn2_match_pairs_per_sec" and d["unit"] == "pairs/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert "workload" in d["config"]
+    import torch
+    if not torch.cuda.is_available():
+        ours = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
+                              capture_output=True, text=True, timeout=600, cwd=ROOT)
+        assert ours.returncode != 0 and "no CUDA device" in (ours.stderr + ours.stdout)
