@@ -587,7 +587,8 @@ def run_ours(args):
     flags = [v.get("ok") for v in parity_all.values() if isinstance(v, dict) and "ok" in v]
     parity_ok = bool(flags) and all(bool(x) for x in flags)
     summary = {
-        "l2_pairs_per_s": value, "l2_step_us": ms_step * 1e3, "k2_us_event_timed": k2_avg_ms * 1e3,
+        "l2_pairs_per_s": value, "l2_step_us": ms_step * 1e3, "l2_step_us_one_lane": ms_step_single * 1e3, "lanes": n_lanes,
+        "k2_us_event_timed": k2_avg_ms * 1e3,
         "k2_frac_of_burst_peak": achieved / peaks["bf16_burst"], "k2_frac_of_sustained_peak": achieved / peaks["bf16_sustained"],
         "k2_us_in_chain": k2_chain_us, "l2_e2e_pairs_per_s": e2e["value"], "l2_e2e_u8_pairs_per_s": get(e2e, "u8_wire_format", "value"),
         "ransac_hyp_per_s": get(secondary, "value"), "ransac_k7_frac_of_measured_fp32": get(secondary, "roofline", "frac"),
