@@ -425,8 +425,8 @@ def run_ours(args):
     from concurrent.futures import ThreadPoolExecutor
     lane_host = [(hknn, hgood)] + [(torch.zeros_like(hknn).pin_memory(), torch.zeros_like(hgood).pin_memory()) for _ in lane_ctx[1:]]
     pool_exec = ThreadPoolExecutor(max_workers=n_lanes)
-    e_steps = max(3, min(steps, 200))
-    n_host_good = 0
+    e_steps = min(max(steps, 100), 200)          # five blocks of at least 20 calls whatever --steps is (a block of four calls
+    n_host_good = 0                              # cannot show what four lanes overlap)
 
     def host_calls(lane, n_calls, n_active):
         c, (hk, hg) = lane_ctx[lane], lane_host[lane]
