@@ -366,12 +366,14 @@ int pm_measure_peak(pm_ctx *ctx, int which, double *value);
  *   pm_debug_force_exact(on)        L2: exact FP32 kernel for every row (cross-check of the two paths)
  *   pm_debug_fallback_no_helpers(on) L2 split mode: no helper blocks, the last row block of K3 runs the flagged-row scan alone
  *   pm_debug_cross_full(on)         cross-check: reverse pass over the whole train set instead of the marked rows only
+ *   pm_debug_k2_repeat(n)           the L2 GEMM kernel is launched n times back to back inside one profiling event pair (same result)
  *   pm_debug_set_l2_dump(p), pm_debug_set_k2_trace(p)   K2 tile dump / clock64 trace (PM_K2_TRACE builds) */
 void pm_debug_set_span(unsigned long long *p);
 void pm_debug_hamming_path(int path);
 void pm_debug_force_exact(int on);
 void pm_debug_fallback_no_helpers(int on);
 void pm_debug_cross_full(int on);
+void pm_debug_k2_repeat(int n);
 void pm_debug_set_l2_dump(float *ddump);
 void pm_debug_set_k2_trace(long long *p);
 void pm_debug_set_k2_trace_cta(int cta);

@@ -54,7 +54,7 @@ EXPORTS = [
     "pm_match_estimate_batched", "pm_find_fundamental_adaptive", "pm_find_fundamental_mat", "pm_fundamental_7point",
     "pm_comm_unique_id", "pm_comm_init", "pm_set_comm", "pm_comm_info", "pm_match_cross_sharded_dev",
     "pm_allgather_matches_dev", "pm_find_fundamental_sharded_dev", "pm_measure_peak",
-    "pm_debug_set_span", "pm_debug_hamming_path", "pm_debug_force_exact", "pm_debug_fallback_no_helpers", "pm_debug_cross_full",
+    "pm_debug_set_span", "pm_debug_hamming_path", "pm_debug_force_exact", "pm_debug_fallback_no_helpers", "pm_debug_cross_full", "pm_debug_k2_repeat",
     "pm_debug_set_l2_dump", "pm_debug_set_k2_trace", "pm_debug_set_k2_trace_cta",
 ]
 

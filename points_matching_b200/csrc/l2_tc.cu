@@ -797,6 +797,9 @@ int l2_tc_grid(pm_ctx *ctx, int MT, int NT)
 // Max number of CTAs (segments) that can touch one row tile under the partition above.
 int l2_tc_smax(pm_ctx *ctx, int MT, int NT) { return l2_sched_get(ctx, MT, NT).smax; }
 
+static int g_k2_repeat = 1;
+extern "C" void pm_debug_k2_repeat(int n) { g_k2_repeat = n > 1 ? (n < 64 ? n : 64) : 1; }
+
 int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, int nt_pad,
                  const void *text, const L2Flags *flags, L2Cand *part, int smax, float *dump, int fp8,
                  int tmap_set, const unsigned long long *chain_done, unsigned long long wait_seq,
@@ -847,9 +850,16 @@ int l2_tc_launch(pm_ctx *ctx, const void *qpack, int mq_pad, const void *tpack, 
     P.sched = dsched; P.trace_cta = g_k2_trace_cta;
     {
         pm_prof_scope prof(ctx, fp8 ? 1 : 0);       // profile class 1 = the Hamming matching kernel
-        cudaError_t le = fp8 ? pm_launch_pdl(l2_tc_kernel<true>, dim3(G), dim3(TC_THREADS), (size_t)SMEM_TOTAL, ctx->stream, tq, tt, P)
-                             : pm_launch_pdl(l2_tc_kernel<false>, dim3(G), dim3(TC_THREADS), (size_t)SMEM_TOTAL, ctx->stream, tq, tt, P);
-        if (le != cudaSuccess) return pm_fail(ctx, PM_CUDA_ERR, "l2_tc_kernel launch: %s", cudaGetErrorString(le));
+        // pm_debug_k2_repeat(n): the launch is repeated n times inside ONE event pair (the kernel only reads its operands and
+        // rewrites the same candidates, so the result does not change) -- its steady-state duration, with the launch
+        // latency and prologue of launch k + 1 under launch k as in any back-to-back use
+        for (int rep = 0; rep < (g_k2_repeat > 1 ? g_k2_repeat : 1); ++rep) {
+            cudaError_t le = fp8 ? pm_launch_pdl(l2_tc_kernel<true>, dim3(G), dim3(TC_THREADS), (size_t)SMEM_TOTAL, ctx->stream, tq, tt, P)
+                                 : pm_launch_pdl(l2_tc_kernel<false>, dim3(G), dim3(TC_THREADS), (size_t)SMEM_TOTAL, ctx->stream, tq, tt, P);
+            if (le != cudaSuccess) return pm_fail(ctx, PM_CUDA_ERR, "l2_tc_kernel launch: %s", cudaGetErrorString(le));
+            ++ctx->launches;
+        }
+        --ctx->launches;                            // PM_CHECK_LAUNCH below counts one
     }
     PM_CHECK_LAUNCH(ctx);
     return PM_OK;
