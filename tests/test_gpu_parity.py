@@ -229,6 +229,22 @@ def test_cross_check_marked_rows_equals_full_reverse_pass(ctx, pm, norm, shape):
     assert len(a) > 0
 
 
+def test_k2_repeat_hook_changes_nothing(ctx, pm):
+    """bench.py times the GEMM kernel with one event pair around 8 consecutive launches (pm_debug_k2_repeat): the repeated
+    launches re-write the same candidates, so every result is bit-identical -- integer data, general floats, Hamming."""
+    from points_matching_b200 import _lib
+    cases = [(synth.sift_pair(3000, 5000, seed=31), pm.NORM_L2), (synth.surf_pair(2000, 3000, seed=32), pm.NORM_L2),
+             (synth.orb_pair(2500, 2600, seed=33), pm.NORM_HAMMING)]
+    ref = [ctx.knn2(q, t, norm) for (q, t), norm in cases]
+    _lib.lib().pm_debug_k2_repeat(3)
+    try:
+        got = [ctx.knn2(q, t, norm) for (q, t), norm in cases]
+    finally:
+        _lib.lib().pm_debug_k2_repeat(1)
+    for a, b in zip(ref, got):
+        assert (a == b).all()
+
+
 # --------------------------------------------------------------------------- filters
 def test_filters_vs_oracle(ctx, pm, orc):
     q, t = synth.sift_pair(40000, 300, seed=3)          # > 16384 rows: multi-block compaction path
